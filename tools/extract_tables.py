@@ -10,9 +10,10 @@ The reference keeps Table 9-44 (rangeTabLPS), Table 9-45 (state transitions) and
   /root/reference/h264/mn_vars.go:184-440       CodedblockPatternMN switch (ctxIdx 70..104)
 
 This script parses those literals (data only; no reference code is copied) and writes the same
-numbers as flat C arrays, twice: once for the CPU oracle (oracle/ref_tables.h) and once for the
-CUDA product (h264decode_b200/csrc/tables.inc).  The two outputs are deliberately separate files
-so that the product never includes anything under oracle/.
+numbers as flat C arrays, three times: for the CPU oracle (oracle/ref_tables.h), for the CUDA product
+(h264decode_b200/csrc/tables.inc) and for the synthetic-data harness (harness/harness_tables.h).  The
+outputs are deliberately separate files so that neither the product nor the harness includes anything
+under oracle/.
 
 Two variants are emitted:
   REF  : the numbers exactly as the reference has them, typos included (A1..A4) -- parity default.
@@ -150,6 +151,7 @@ def render(prefix, guard):
 TARGETS = [
     ("oracle/ref_tables.h", "orc_", "ORACLE_REF_TABLES_H"),
     ("h264decode_b200/csrc/tables.inc", "h264b_", "H264B_TABLES_INC"),
+    ("harness/harness_tables.h", "hz_", "HARNESS_TABLES_H"),
 ]
 
 
