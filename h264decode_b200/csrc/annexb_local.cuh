@@ -1,0 +1,116 @@
+// annexb_local.cuh -- position-local form of the reference's sequential Annex-B split + RBSP strip.
+//
+// The reference walks the stream one byte at a time (readNalUnit, h264/server.go:64-111) and then walks each NAL
+// again (NewNalUnit body loop, h264/nalUnit.go:106-126).  Both walks are equivalent to per-byte predicates that
+// look at most 9 bytes back and 1 byte ahead, which is what makes the path data-parallel:
+//
+//   SC(p)    <=> s[p-3..p] == 00 00 00 01                       (isStartSequence, server.go:28-39; 4-byte only, A8)
+//   a        =  p+1 for SC(p): first byte of a NAL; the NAL runs up to and including the NEXT start code (A8)
+//   H(a)     =  1, or 4 for types 14/20, or for type 21: 3 if s[a+1]&0x80 else 4        (nalUnit.go:79,86-103)
+//   EPB(p)   <=> s[p]==3 && s[p-1]==0 && s[p-2]==0 && p-2 >= a+H                         (nalUnit.go:32-37,113; A7)
+//   keep(p)  <=> a <= p exists && p >= a+H && !SC(p) && !SC(p+1) && !EPB(p)
+//               (!SC(p) && !SC(p+1): the Peek failure at nalUnit.go:107-111 drops the NAL's last two bytes, which in
+//                stream framing are the 00 01 that end the next start code)
+//
+// Everything here is __host__ __device__ so that tests/ can run the exact same predicates on the CPU against the
+// oracle's sequential restatement.
+#pragma once
+#include <stdint.h>
+
+#ifndef H264B_HD
+#if defined(__CUDACC__)
+#define H264B_HD __host__ __device__ __forceinline__
+#else
+#define H264B_HD static inline
+#endif
+#endif
+
+namespace h264b {
+
+// NAL header length from the first two NAL bytes (nalUnit.go:79,86-103)
+H264B_HD uint32_t nal_header_bytes(uint32_t b0, uint32_t b1) {
+    uint32_t t = b0 & 31u;
+    if (t == 14u || t == 20u) return 4u;  // SVC (flag 1) and MVC (flag 0) extensions are both 3 bytes
+    if (t == 21u) return (b1 & 0x80u) ? 3u : 4u;  // 3D-AVC ext is 2 bytes, MVC 3
+    return 1u;
+}
+
+// Byte accessor over a window with out-of-range positions reading as 0xFF (matches nothing).
+template <class Get>
+H264B_HD bool is_sc_end(const Get& get, int64_t p) {  // SC(p): p is the 01 of 00 00 00 01
+    return get(p) == 1u && get(p - 1) == 0u && get(p - 2) == 0u && get(p - 3) == 0u;
+}
+
+// keep(p) in stream mode for a byte known to lie at or after the first NAL start.
+// get(q) must return s[q] for every q in [p-9, p+2] that lies inside the stream and 0xFF otherwise.
+template <class Get>
+H264B_HD bool keep_byte_stream(const Get& get, int64_t p) {
+    if (is_sc_end(get, p) || is_sc_end(get, p + 1)) return false;  // positions b-1 and b-2
+    bool epb_ok = true;
+#pragma unroll
+    for (int d = 0; d < 6; d++) {  // most recent NAL start a = p-d, if within reach of its header / EPB guard
+        if (is_sc_end(get, p - d - 1)) {
+            uint32_t H = nal_header_bytes(get(p - d), get(p - d + 1));
+            if ((uint32_t)d < H) return false;  // header byte
+            epb_ok = (uint32_t)d >= H + 2u;     // both zeros of a 00 00 03 must be body bytes (A7)
+            break;
+        }
+    }
+    if (epb_ok && get(p) == 3u && get(p - 1) == 0u && get(p - 2) == 0u) return false;  // emulation prevention
+    return true;
+}
+
+// keep(p) for NewNalUnit called directly on one frame [a, a+N): no start codes involved; the body is
+// [a+H, a+N-3], plus the byte a+N-2 when the frame ends in an emulation-prevention triple (the match at cursor
+// N-3 copies both zeros, nalUnit.go:113-117).
+template <class Get>
+H264B_HD bool keep_byte_frame(const Get& get, int64_t a, int64_t N, uint32_t H, int64_t p) {
+    int64_t rel = p - a;
+    if (rel < (int64_t)H) return false;
+    auto epb = [&](int64_t q) {
+        return q - a - 2 >= (int64_t)H && q - a < N && get(q) == 3u && get(q - 1) == 0u && get(q - 2) == 0u;
+    };
+    if (rel <= N - 3) return !epb(p);
+    if (rel == N - 2) return epb(p + 1);
+    return false;
+}
+
+// ---- word-parallel detection used by the kernel's fast path ------------------------------------------------
+// bit 7 of each byte of the result is set iff that byte of w is zero (exact, no cross-byte carries)
+H264B_HD uint32_t zero_bytes(uint32_t w) { return ~(((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w | 0x7F7F7F7Fu); }
+// gather bit 7 of each byte into bits 0..3 (byte 0 -> bit 0)
+H264B_HD uint32_t pack_msb4(uint32_t m) { return ((m & 0x80808080u) * 0x00204081u) >> 28; }
+
+// For a 16-byte granule (little-endian words w[0..3], byte j of the granule = byte j&3 of w[j>>2]) and the 4 bytes
+// before it (prev, byte 3 = the byte just before the granule), return per-byte bit masks (bit j = granule byte j):
+//   z  : byte == 0          e : raw emulation-prevention candidate  s[p]==3 && s[p-1]==0 && s[p-2]==0
+//   sc : start-code end     s[p]==1 && s[p-1]==s[p-2]==s[p-3]==0
+struct GranuleMasks {
+    uint32_t z, e, sc;
+};
+H264B_HD GranuleMasks granule_masks(const uint32_t w[4], uint32_t prev) {
+    uint32_t z = pack_msb4(zero_bytes(w[0])) | (pack_msb4(zero_bytes(w[1])) << 4) |
+                 (pack_msb4(zero_bytes(w[2])) << 8) | (pack_msb4(zero_bytes(w[3])) << 12);
+    uint32_t zp = pack_msb4(zero_bytes(prev));  // bits 0..3 = bytes g-4..g-1
+    uint32_t zz = (z << 4) | zp;                // bit k <-> position g-4+k, k in [0,20)
+    // two / three zeros immediately before position g+j  <=> zz bits (j+3, j+2) / (j+3, j+2, j+1)
+    uint32_t two = (zz >> 3) & (zz >> 2);
+    uint32_t three = two & (zz >> 1);
+    GranuleMasks m;
+    m.z = z;
+    m.e = 0;
+    m.sc = 0;
+    if ((two & 0xFFFFu) != 0) {  // rare for entropy-coded payloads: only now look for 03 / 01 bytes
+        uint32_t t = pack_msb4(zero_bytes(w[0] ^ 0x03030303u)) | (pack_msb4(zero_bytes(w[1] ^ 0x03030303u)) << 4) |
+                     (pack_msb4(zero_bytes(w[2] ^ 0x03030303u)) << 8) |
+                     (pack_msb4(zero_bytes(w[3] ^ 0x03030303u)) << 12);
+        uint32_t o = pack_msb4(zero_bytes(w[0] ^ 0x01010101u)) | (pack_msb4(zero_bytes(w[1] ^ 0x01010101u)) << 4) |
+                     (pack_msb4(zero_bytes(w[2] ^ 0x01010101u)) << 8) |
+                     (pack_msb4(zero_bytes(w[3] ^ 0x01010101u)) << 12);
+        m.e = t & two & 0xFFFFu;
+        m.sc = o & three & 0xFFFFu;
+    }
+    return m;
+}
+
+}  // namespace h264b

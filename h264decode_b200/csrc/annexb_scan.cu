@@ -1,0 +1,704 @@
+// annexb_scan.cu -- K1/K2: single-pass Annex-B split + RBSP emulation-prevention strip for sm_100a.
+//
+// Replaces the byte-at-a-time loops of readNalUnit (h264/server.go:64-111) and NewNalUnit (h264/nalUnit.go:75-131)
+// of the reference with one streaming pass: every input byte is read from HBM once and every kept byte written once
+// (algorithmic traffic N_in + N_rbsp + 20 B per NAL).
+//
+// Structure (one CTA = 256 threads, tiles of 16 KiB handed out by an atomic ticket so that tile i is always started
+// before tile i+1):
+//   load     one elected thread issues a TMA 1-D bulk copy (cp.async.bulk + mbarrier complete_tx) of the tile plus a
+//            16-byte halo on each side into shared memory
+//   detect   each thread reads 16-byte granules (LDS.128, conflict-free interleaved mapping), finds zero bytes with
+//            word-parallel arithmetic and only where two zeros precede a byte looks for 03 (emulation prevention)
+//            and 01 (start-code end); start-code bits go to a per-tile bitmap
+//   adjust   granules with a start code within reach (header bytes, the 2-byte tail rule, zeros that belong to a
+//            header) re-evaluate their 16 keep bits with the exact per-byte predicate of annexb_local.cuh
+//   scan     packed (kept bytes | start codes << 16) block scan: shuffle scan per warp, 32 warp totals by warp 0
+//   chain    decoupled look-back over per-tile descriptors gives the tile's exclusive (kept bytes, NAL index) prefix
+//   scatter  kept bytes go to a shared-memory staging buffer laid out with the alignment of the global destination
+//            (word stores for untouched granules, byte stores at the seams; 1 pad word per 32 against conflicts)
+//   store    staging -> global as aligned 16-byte stores; only the first/last partial granule of a tile uses bytes
+//   index    threads owning a start code write (start, rbsp offset, first 4 NAL bytes) for NAL k = prefix + rank
+// A tiny finalize kernel turns those into h264b_nal records (lengths are differences of neighbours).
+#include "annexb_local.cuh"
+#include "common.cuh"
+
+namespace h264b {
+
+constexpr int kThreads = 256;
+constexpr int kRows = 4;                          // granules per thread per tile
+constexpr int kGranules = kThreads * kRows;       // 1024
+constexpr int kTile = kGranules * 16;             // 16384 bytes
+constexpr int kHalo = 16;
+constexpr int kInBytes = kHalo + kTile + kHalo;   // 16416
+constexpr int kStageWords = (kTile / 4 + 8) + ((kTile / 4 + 8) >> 5) + 4;
+constexpr uint64_t kStatusAgg = 1ull << 62, kStatusPrefix = 2ull << 62, kValueMask = (1ull << 62) - 1;
+
+struct ScanScratchHeader {   // device scratch, zeroed / initialised by scan_init_kernel
+    unsigned int ticket;
+    unsigned int pad;
+    unsigned long long first_start;
+    unsigned long long total_sc;
+    unsigned long long total_kept;
+    unsigned long long n_epb;
+    unsigned long long reserved[3];
+};  // 64 bytes
+
+struct ScanArgs {
+    const uint8_t *in;
+    uint64_t n;
+    uint8_t *out;
+    ScanScratchHeader *hdr;
+    unsigned long long *desc_kept;
+    unsigned long long *desc_nal;
+    unsigned long long *nal_start;
+    unsigned long long *nal_rbsp_off;
+    uint32_t *nal_hdr;
+    uint32_t nal_cap;
+    uint32_t n_tiles;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t skew(uint32_t w) { return w + (w >> 5); }
+
+__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ init
+__global__ void scan_init_kernel(ScanScratchHeader *hdr, unsigned long long *desc, uint64_t n_desc, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        hdr->ticket = 0;
+        hdr->first_start = n;
+        hdr->total_sc = 0;
+        hdr->total_kept = 0;
+        hdr->n_epb = 0;
+    }
+    for (; i < n_desc; i += (uint64_t)gridDim.x * blockDim.x) desc[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ first start code
+// first_start = 1 + position of the first 00 00 00 01 (bytes before it are not part of any NAL, server.go:68-72).
+// Chunks are visited in order by each CTA and a CTA stops as soon as a smaller position is already known.
+__global__ void __launch_bounds__(256) first_start_kernel(const uint8_t *in, uint64_t n, ScanScratchHeader *hdr) {
+    const uint64_t n_gran = (n + 15) / 16;
+    for (uint64_t chunk = blockIdx.x;; chunk += gridDim.x) {
+        uint64_t g = chunk * 256 + threadIdx.x;
+        if (chunk * 256 >= n_gran) return;
+        if (ld_relaxed(&hdr->first_start) <= chunk * 256 * 16) return;
+        if (g < n_gran) {
+            uint64_t pos = g * 16;
+            uint4 v = *reinterpret_cast<const uint4 *>(in + pos);
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            uint32_t prev = pos ? *reinterpret_cast<const uint32_t *>(in + pos - 4) : 0xFFFFFFFFu;
+            GranuleMasks m = granule_masks(w, prev);
+            if (m.sc) {
+                uint64_t q = pos + (uint64_t)(__ffs(m.sc) - 1);
+                if (q < n) atomicMin(&hdr->first_start, (unsigned long long)(q + 1));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ main pass
+struct __align__(16) ScanSmem {
+    uint8_t in[kInBytes];                 // [0,16): low halo, [16,16+kTile): tile, then high halo
+    uint32_t stage[kStageWords];          // compacted bytes, skewed word layout
+    uint16_t scbits[kGranules + 2];       // start-code-end bits per granule, [0] = halo granule before the tile
+    uint32_t warp_tot[kRows * 8];         // packed warp totals, later exclusive offsets
+    unsigned long long tile_kept_prefix;  // exclusive prefixes of this tile
+    unsigned long long tile_nal_prefix;
+    uint32_t tile_total;                  // packed total of this tile
+    uint32_t tile;
+    unsigned long long mbar;
+};
+
+__device__ __forceinline__ void stage_byte(uint32_t *stage, uint32_t b, uint32_t v) {
+    reinterpret_cast<uint8_t *>(stage)[skew(b >> 2) * 4 + (b & 3)] = (uint8_t)v;
+}
+
+__global__ void __launch_bounds__(kThreads, 4) annexb_scan_kernel(ScanArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    ScanSmem &sm = *reinterpret_cast<ScanSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t mbar = smem_u32(&sm.mbar);
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint64_t e0 = ld_relaxed(&a.hdr->first_start);  // written by first_start_kernel (previous launch)
+    const uint64_t n16 = (a.n + 15) & ~15ull;
+    uint32_t parity = 0;
+
+    for (;;) {
+        // ---------------------------------------------------------------- ticket + TMA load
+        if (tid == 0) sm.tile = atomicAdd(&a.hdr->ticket, 1u);
+        __syncthreads();  // also: everybody is done with the previous tile's shared memory
+        const uint32_t tile = sm.tile;
+        if (tile >= a.n_tiles) break;
+        const uint64_t base = (uint64_t)tile * kTile;
+        const uint64_t lo = tile ? base - kHalo : base;
+        uint64_t hi = base + kTile + kHalo;
+        if (hi > n16) hi = n16;
+        if (tid == 0) {
+            uint32_t bytes = (uint32_t)(hi - lo);
+            uint32_t dst = smem_u32(sm.in + (lo - (base - kHalo)));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                "l"(a.in + lo), "r"(bytes), "r"(mbar)
+                : "memory");
+        }
+        // bytes outside the stream read as 0xFF (they match no predicate): low halo of tile 0 ...
+        if (tile == 0 && tid < 4) reinterpret_cast<uint32_t *>(sm.in)[tid] = 0xFFFFFFFFu;
+        // ... and everything the copy does not write at the end of the stream
+        const uint32_t loaded_end = (uint32_t)(hi - (base - kHalo));  // offset in sm.in
+        for (uint32_t o = loaded_end + tid * 4; o < (uint32_t)kInBytes; o += kThreads * 4)
+            *reinterpret_cast<uint32_t *>(sm.in + o) = 0xFFFFFFFFu;
+        {
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(mbar), "r"(parity)
+                    : "memory");
+            }
+            parity ^= 1;
+        }
+        if (hi > a.n && hi - a.n < 16) {  // the last 16-byte granule holds bytes past n: blank them
+            uint32_t first_bad = (uint32_t)(a.n - (base - kHalo));
+            if (tid < 16 && first_bad + tid < loaded_end) sm.in[first_bad + tid] = 0xFF;
+        }
+        __syncthreads();  // the 0xFF fills above are plain stores other threads read
+        const uint8_t *tile_in = sm.in + kHalo;  // tile_in[i] = s[base + i], valid for i in [-16, kTile+16)
+
+        // ---------------------------------------------------------------- detect
+        uint32_t em[kRows];  // raw EPB mask | start-code mask << 16
+#pragma unroll
+        for (int r = 0; r < kRows; r++) {
+            const int gi = r * kThreads + tid;
+            const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            const uint32_t prev = *reinterpret_cast<const uint32_t *>(tile_in + gi * 16 - 4);
+            GranuleMasks m = granule_masks(w, prev);
+            em[r] = m.e | (m.sc << 16);
+            sm.scbits[gi + 1] = (uint16_t)m.sc;
+        }
+        if (tid < 2) {  // halo granules: only start codes ending in [base-6, base-1] and at base+kTile matter
+            const int gi = tid ? kGranules : -1;
+            const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            const uint32_t prev = tid ? *reinterpret_cast<const uint32_t *>(tile_in + gi * 16 - 4) : 0xFFFFFFFFu;
+            sm.scbits[gi + 1] = (uint16_t)granule_masks(w, prev).sc;
+        }
+        __syncthreads();
+
+        // ---------------------------------------------------------------- adjust + count
+        const bool tile_has_head = base < e0;            // some bytes precede the first NAL
+        const bool tile_has_end = base + kTile > a.n;    // some granules reach past the stream
+        auto get = [&](int64_t p) -> uint32_t { return tile_in[p - (int64_t)base]; };
+        uint32_t keep[kRows], packed[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; r++) {
+            const int gi = r * kThreads + tid;
+            const uint64_t gpos = base + (uint64_t)gi * 16;
+            uint32_t k16 = ~em[r] & 0xFFFFu;
+            // start-code ends q in [g-6, g+16] change what this granule keeps
+            const uint32_t near = ((uint32_t)sm.scbits[gi] >> 10) | sm.scbits[gi + 1] | (sm.scbits[gi + 2] & 1u);
+            if (near) {
+                k16 = 0;
+#pragma unroll 1
+                for (int j = 0; j < 16; j++)
+                    if (keep_byte_stream(get, (int64_t)gpos + j)) k16 |= 1u << j;
+            }
+            if (tile_has_head) {
+                if (gpos + 16 <= e0)
+                    k16 = 0;
+                else if (gpos < e0)
+                    k16 &= ~((1u << (uint32_t)(e0 - gpos)) - 1u);
+            }
+            uint32_t sc = em[r] >> 16;
+            if (tile_has_end) {
+                if (gpos >= a.n) {
+                    k16 = 0;
+                    sc = 0;
+                } else if (gpos + 16 > a.n) {
+                    uint32_t valid = (1u << (uint32_t)(a.n - gpos)) - 1u;
+                    k16 &= valid;
+                    sc &= valid;
+                }
+                em[r] = (em[r] & 0xFFFFu) | (sc << 16);
+            }
+            keep[r] = k16;
+            packed[r] = __popc(k16) | (__popc(sc) << 16);
+        }
+
+        // ---------------------------------------------------------------- block scan (row-major granule order)
+        uint32_t incl[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; r++) {
+            uint32_t x = packed[r];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+                if (lane >= d) x += y;
+            }
+            incl[r] = x;
+            if (lane == 31) sm.warp_tot[r * 8 + warp] = x;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t x = sm.warp_tot[lane], own = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+                if (lane >= d) x += y;
+            }
+            sm.warp_tot[lane] = x - own;  // exclusive
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, x, 31);
+            const unsigned long long agg_kept = total & 0xFFFFu, agg_nal = total >> 16;
+            // ------------------------------------------------------------ decoupled look-back (warp 0)
+            unsigned long long pre_kept = 0, pre_nal = 0;
+            if (tile > 0) {
+                if (lane == 0) {
+                    st_relaxed(&a.desc_kept[tile], kStatusAgg | agg_kept);
+                    st_relaxed(&a.desc_nal[tile], kStatusAgg | agg_nal);
+                }
+                bool done_k = false, done_n = false;
+                for (int64_t j = (int64_t)tile - 1; !(done_k && done_n); j -= 32) {
+                    const int64_t idx = j - lane;
+                    unsigned long long dk = kStatusPrefix, dn = kStatusPrefix;  // virtual tile -1: prefix 0
+                    bool pending;
+                    do {  // all 32 lanes poll together; lanes before tile 0 have nothing to wait for
+                        if (idx >= 0) {
+                            dk = ld_relaxed(&a.desc_kept[idx]);
+                            dn = ld_relaxed(&a.desc_nal[idx]);
+                        }
+                        pending = idx >= 0 && ((dk >> 62) == 0 || (dn >> 62) == 0);
+                    } while (__any_sync(0xFFFFFFFFu, pending));
+                    if (!done_k) {
+                        const uint32_t pm = __ballot_sync(0xFFFFFFFFu, (dk >> 62) == 2);
+                        const int first = pm ? __ffs(pm) - 1 : 31;
+                        unsigned long long v = (lane <= first) ? (dk & kValueMask) : 0ull;
+#pragma unroll
+                        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+                        pre_kept += v;
+                        done_k = pm != 0;
+                    }
+                    if (!done_n) {
+                        const uint32_t pm = __ballot_sync(0xFFFFFFFFu, (dn >> 62) == 2);
+                        const int first = pm ? __ffs(pm) - 1 : 31;
+                        unsigned long long v = (lane <= first) ? (dn & kValueMask) : 0ull;
+#pragma unroll
+                        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+                        pre_nal += v;
+                        done_n = pm != 0;
+                    }
+                }
+            }
+            if (lane == 0) {
+                st_relaxed(&a.desc_kept[tile], kStatusPrefix | (pre_kept + agg_kept));
+                st_relaxed(&a.desc_nal[tile], kStatusPrefix | (pre_nal + agg_nal));
+                sm.tile_kept_prefix = pre_kept;
+                sm.tile_nal_prefix = pre_nal;
+                sm.tile_total = total;
+                if (tile == a.n_tiles - 1) {
+                    a.hdr->total_kept = pre_kept + agg_kept;
+                    a.hdr->total_sc = pre_nal + agg_nal;
+                }
+            }
+        }
+        __syncthreads();
+        const uint64_t gout = sm.tile_kept_prefix;       // global output offset of this tile's first kept byte
+        const uint64_t nal0 = sm.tile_nal_prefix;
+        const uint32_t tile_kept = sm.tile_total & 0xFFFFu;
+        const uint32_t align = (uint32_t)(gout & 15);    // staging mirrors the destination's 16-byte phase
+
+        // ---------------------------------------------------------------- scatter to staging + NAL index
+#pragma unroll
+        for (int r = 0; r < kRows; r++) {
+            const int gi = r * kThreads + tid;
+            const uint32_t excl = sm.warp_tot[r * 8 + warp] + incl[r] - packed[r];
+            const uint32_t loff = excl & 0xFFFFu;
+            const uint32_t k16 = keep[r];
+            const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            uint32_t off = align + loff;
+            if (k16 == 0xFFFFu) {
+                const uint32_t s = off & 3u, W = off >> 2;
+                if (s == 0) {
+                    sm.stage[skew(W)] = w[0];
+                    sm.stage[skew(W + 1)] = w[1];
+                    sm.stage[skew(W + 2)] = w[2];
+                    sm.stage[skew(W + 3)] = w[3];
+                } else {
+                    const uint32_t sh = s * 8;
+                    sm.stage[skew(W + 1)] = __funnelshift_l(w[0], w[1], sh);
+                    sm.stage[skew(W + 2)] = __funnelshift_l(w[1], w[2], sh);
+                    sm.stage[skew(W + 3)] = __funnelshift_l(w[2], w[3], sh);
+                    // head: granule bytes 0..3-s ; tail: granule bytes 16-s..15
+                    stage_byte(sm.stage, off, w[0] & 0xFF);
+                    if (s <= 2) stage_byte(sm.stage, off + 1, (w[0] >> 8) & 0xFF);
+                    if (s == 1) stage_byte(sm.stage, off + 2, (w[0] >> 16) & 0xFF);
+                    stage_byte(sm.stage, off + 15, w[3] >> 24);
+                    if (s >= 2) stage_byte(sm.stage, off + 14, (w[3] >> 16) & 0xFF);
+                    if (s == 3) stage_byte(sm.stage, off + 13, (w[3] >> 8) & 0xFF);
+                }
+            } else if (k16) {
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    if (k16 & (1u << j)) stage_byte(sm.stage, off++, (w[j >> 2] >> ((j & 3) * 8)) & 0xFF);
+            }
+            uint32_t sc = em[r] >> 16;
+            if (sc) {  // NAL index entries for the start codes that end in this granule
+                uint64_t k = nal0 + (excl >> 16);
+                while (sc) {
+                    const int j = __ffs(sc) - 1;
+                    sc &= sc - 1;
+                    if (k < a.nal_cap) {
+                        const int i0 = gi * 16 + j + 1;  // tile-relative offset of the NAL's first byte
+                        a.nal_start[k] = base + (uint64_t)i0;
+                        a.nal_rbsp_off[k] = gout + loff + __popc(k16 & ((1u << j) - 1u));
+                        a.nal_hdr[k] = (uint32_t)tile_in[i0] | ((uint32_t)tile_in[i0 + 1] << 8) |
+                                       ((uint32_t)tile_in[i0 + 2] << 16) | ((uint32_t)tile_in[i0 + 3] << 24);
+                    }
+                    k++;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---------------------------------------------------------------- staging -> global, aligned 16-byte stores
+        {
+            const uint32_t end = align + tile_kept;  // staging holds bytes [align, end)
+            const uint32_t n_gran = (end + 15) >> 4;
+            uint8_t *gbase = a.out + (gout - align);  // 16-byte aligned
+            for (uint32_t j = tid; j < n_gran; j += kThreads) {
+                const uint32_t p0 = skew(j * 4);
+                uint4 v;
+                v.x = sm.stage[p0];
+                v.y = sm.stage[p0 + 1];
+                v.z = sm.stage[p0 + 2];
+                v.w = sm.stage[p0 + 3];
+                const uint32_t b0 = j * 16;
+                if (b0 >= align && b0 + 16 <= end) {
+                    *reinterpret_cast<uint4 *>(gbase + b0) = v;
+                } else {  // seam with the neighbouring tile's bytes: byte-granular
+                    const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int b = 0; b < 16; b++)
+                        if (b0 + b >= align && b0 + b < end) gbase[b0 + b] = (uint8_t)(ww[b >> 2] >> ((b & 3) * 8));
+                }
+            }
+        }
+        // the loop-top __syncthreads orders these shared-memory reads before the next tile's writes
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ finalize
+__device__ __forceinline__ void decode_nal_header(uint32_t hdr4, h264b_nal &o, h264b_nal_ext *ext) {
+    const uint32_t b0 = hdr4 & 0xFF, b1 = (hdr4 >> 8) & 0xFF, b2 = (hdr4 >> 16) & 0xFF, b3 = hdr4 >> 24;
+    o.forbidden_zero_bit = (uint8_t)(b0 >> 7);
+    o.ref_idc = (uint8_t)((b0 >> 5) & 3);
+    o.type = (uint8_t)(b0 & 31);
+    o.header_bytes = (uint8_t)nal_header_bytes(b0, b1);
+    if (!ext) return;
+    h264b_nal_ext e;
+    memset(&e, 0, sizeof(e));
+    const uint32_t t = b0 & 31;
+    if (t == 14 || t == 20 || t == 21) {
+        const uint32_t bits = (b1 << 16) | (b2 << 8) | b3;  // 24 extension bits, MSB first
+        const uint32_t flag = bits >> 23;
+        if (t != 21) e.svc_extension_flag = (uint8_t)flag; else e.avc_3d_extension_flag = (uint8_t)flag;
+        if (t != 21 && flag) {  // nalUnit.go:39-51
+            e.idr_flag = (bits >> 22) & 1;
+            e.priority_id = (bits >> 16) & 63;
+            e.no_inter_layer_pred_flag = (bits >> 15) & 1;
+            e.dependency_id = (bits >> 12) & 7;
+            e.quality_id = (bits >> 8) & 15;
+            e.temporal_id = (bits >> 5) & 7;
+            e.use_ref_base_pic_flag = (bits >> 4) & 1;
+            e.discardable_flag = (bits >> 3) & 1;
+            e.output_flag = (bits >> 2) & 1;
+            e.reserved_three_2bits = bits & 3;
+        } else if (t == 21 && flag) {  // nalUnit.go:53-61 (16 bits)
+            e.view_idx = (bits >> 15) & 255;
+            e.depth_flag = (bits >> 14) & 1;
+            e.non_idr_flag = (bits >> 13) & 1;
+            e.temporal_id = (bits >> 10) & 7;
+            e.anchor_pic_flag = (bits >> 9) & 1;
+            e.inter_view_flag = (bits >> 8) & 1;
+        } else {  // nalUnit.go:62-71
+            e.non_idr_flag = (bits >> 22) & 1;
+            e.priority_id = (bits >> 16) & 63;
+            e.view_id = (bits >> 6) & 1023;
+            e.temporal_id = (bits >> 3) & 7;
+            e.anchor_pic_flag = (bits >> 2) & 1;
+            e.inter_view_flag = (bits >> 1) & 1;
+            e.reserved_one_bit = bits & 1;
+        }
+    }
+    *ext = e;
+}
+
+__global__ void __launch_bounds__(256) scan_finalize_kernel(ScanArgs a, h264b_nal *nals, h264b_nal_ext *ext,
+                                                             h264b_scan_summary *summary) {
+    const uint64_t K = a.hdr->total_sc;
+    const uint64_t n_nals = K ? K - 1 : 0;
+    const uint64_t lim = n_nals < a.nal_cap ? n_nals : (a.nal_cap ? (uint64_t)a.nal_cap - 1 : 0);
+    unsigned long long epb = 0;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < lim;
+         k += (uint64_t)gridDim.x * blockDim.x) {
+        h264b_nal o;
+        o.start = a.nal_start[k];
+        o.rbsp_off = a.nal_rbsp_off[k];
+        o.num_bytes = (uint32_t)(a.nal_start[k + 1] - o.start);
+        o.rbsp_len = (uint32_t)(a.nal_rbsp_off[k + 1] - o.rbsp_off);
+        decode_nal_header(a.nal_hdr[k], o, ext ? &ext[k] : nullptr);
+        const uint32_t removed = o.num_bytes - o.header_bytes - 2u - o.rbsp_len;
+        o.flags = (removed ? H264B_F_HAS_EPB : 0u) | (o.num_bytes < 8 ? H264B_F_SHORT_NAL : 0u);
+        epb += removed;
+        nals[k] = o;
+    }
+    if (epb) atomicAdd(&a.hdr->n_epb, epb);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        summary->n_start_codes = K;
+        summary->n_nals = n_nals;
+        summary->first_start = a.hdr->first_start;
+        // kept-byte prefix at the last start code = RBSP bytes of all emitted NAL units
+        summary->rbsp_bytes = (K && K - 1 < a.nal_cap) ? a.nal_rbsp_off[K - 1] : 0;
+        summary->status = (K > a.nal_cap) ? H264B_E_CAPACITY : H264B_OK;
+        summary->reserved = 0;
+    }
+}
+__global__ void scan_summary_epb_kernel(const ScanScratchHeader *hdr, h264b_scan_summary *summary) {
+    summary->n_epb = hdr->n_epb;
+}
+
+// ------------------------------------------------------------------------------------------------ frames (NewNalUnit)
+// One CTA per frame; RBSP of frame i is written at rbsp + off[i] (never longer than the frame).
+__global__ void __launch_bounds__(256) nal_frames_kernel(const uint8_t *in, uint64_t total, const uint64_t *off,
+                                                         const uint32_t *len, uint32_t n_frames, h264b_nal *nals,
+                                                         h264b_nal_ext *ext, uint8_t *rbsp) {
+    __shared__ uint32_t warp_tot[8];
+    __shared__ uint32_t running;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        const int64_t a0 = (int64_t)off[f], N = (int64_t)len[f];
+        auto get = [&](int64_t p) -> uint32_t {
+            return (p >= a0 && p < a0 + N && (uint64_t)p < total) ? (uint32_t)in[p] : 0xFFu;
+        };
+        const uint32_t b0 = get(a0), b1 = get(a0 + 1);
+        const uint32_t H = nal_header_bytes(b0, b1);
+        if (tid == 0) running = 0;
+        __syncthreads();
+        for (int64_t chunk = 0; chunk < N; chunk += 256 * 16) {
+            const int64_t p0 = a0 + chunk + (int64_t)tid * 16;
+            uint32_t k16 = 0;
+            for (int j = 0; j < 16; j++)
+                if (p0 + j < a0 + N && keep_byte_frame(get, a0, N, H, p0 + j)) k16 |= 1u << j;
+            uint32_t x = __popc(k16);
+            const uint32_t own = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+                if (lane >= d) x += y;
+            }
+            if (lane == 31) warp_tot[warp] = x;
+            __syncthreads();
+            uint32_t wbase = 0, tot = 0;
+            for (int w2 = 0; w2 < 8; w2++) {
+                if (w2 < warp) wbase += warp_tot[w2];
+                tot += warp_tot[w2];
+            }
+            uint32_t o = running + wbase + x - own;
+            for (int j = 0; j < 16; j++)
+                if (k16 & (1u << j)) rbsp[a0 + o++] = (uint8_t)get(p0 + j);
+            __syncthreads();
+            if (tid == 0) running += tot;
+            __syncthreads();
+        }
+        if (tid == 0) {
+            h264b_nal o;
+            o.start = (uint64_t)a0;
+            o.rbsp_off = (uint64_t)a0;
+            o.num_bytes = (uint32_t)N;
+            o.rbsp_len = running;
+            const uint32_t hdr4 = b0 | (b1 << 8) | (get(a0 + 2) << 16) | (get(a0 + 3) << 24);
+            decode_nal_header(hdr4, o, ext ? &ext[f] : nullptr);
+            // a frame shorter than its header makes the reference panic (bit_reader.go:298): flag it
+            o.flags = ((int64_t)o.header_bytes > N ? H264B_F_OVERRUN : 0u) | (N < 8 ? H264B_F_SHORT_NAL : 0u);
+            if ((int64_t)o.header_bytes <= N) {
+                const int64_t body = N - (int64_t)o.header_bytes - 2;
+                // direct-call edge: a trailing 00 00 03 keeps byte N-2 and removes the 03
+                const int64_t expect = body > 0 ? body : 0;
+                if ((int64_t)running != expect) o.flags |= H264B_F_HAS_EPB;
+            }
+            nals[f] = o;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ slice selection
+// Ordered list of the NAL units of type 1 / 5 (server.go:147-162 dispatches exactly those to the slice parser).
+// Single CTA, ballot-based stable compaction; the list is small (one entry per slice).
+__global__ void __launch_bounds__(1024) slice_select_kernel(const h264b_nal *nals, const h264b_scan_summary *summary,
+                                                            uint32_t nal_cap, uint32_t data_off, uint32_t max_slices,
+                                                            uint64_t *s_off, uint32_t *s_len, uint32_t *s_nal,
+                                                            uint32_t *n_out) {
+    __shared__ uint32_t warp_cnt[32];
+    __shared__ uint32_t base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint64_t n = summary->n_nals;
+    if (n > nal_cap) n = nal_cap;
+    if (tid == 0) base = 0;
+    __syncthreads();
+    for (uint64_t k0 = 0; k0 < n; k0 += 1024) {
+        const uint64_t k = k0 + tid;
+        bool is_slice = false;
+        h264b_nal u;
+        if (k < n) {
+            u = nals[k];
+            is_slice = (u.type == 1 || u.type == 5);
+        }
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, is_slice);
+        if (lane == 0) warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        uint32_t wbase = 0, tot = 0;
+        for (int w2 = 0; w2 < 32; w2++) {
+            if (w2 < warp) wbase += warp_cnt[w2];
+            tot += warp_cnt[w2];
+        }
+        if (is_slice) {
+            const uint32_t idx = base + wbase + __popc(m & ((1u << lane) - 1u));
+            if (idx < max_slices) {
+                const uint32_t skip = data_off < u.rbsp_len ? data_off : u.rbsp_len;
+                s_off[idx] = u.rbsp_off + skip;
+                s_len[idx] = u.rbsp_len - skip;
+                s_nal[idx] = (uint32_t)k;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) base += tot;
+        __syncthreads();
+    }
+    if (tid == 0) *n_out = base < max_slices ? base : max_slices;
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static uint64_t scratch_layout(uint64_t n, uint32_t nal_cap, uint64_t *o_desc, uint64_t *o_start, uint64_t *o_roff,
+                               uint64_t *o_hdr) {
+    const uint64_t n_tiles = (n + kTile - 1) / kTile;
+    uint64_t o = sizeof(ScanScratchHeader);
+    *o_desc = o;
+    o += 2 * n_tiles * 8;
+    *o_start = o;
+    o += (uint64_t)nal_cap * 8;
+    *o_roff = o;
+    o += (uint64_t)nal_cap * 8;
+    *o_hdr = o;
+    o += (uint64_t)nal_cap * 4;
+    return (o + 255) & ~255ull;
+}
+
+int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint8_t *d_rbsp, h264b_nal *d_nals,
+                       h264b_nal_ext *d_ext, uint32_t nal_cap, h264b_scan_summary *d_summary, uint32_t flags) {
+    (void)flags;
+    if (((uintptr_t)d_stream & 15) || ((uintptr_t)d_rbsp & 15))
+        return set_error(ctx, H264B_E_INVALID, "annexb_scan: d_stream and d_rbsp must be 16-byte aligned");
+    if (n >= (1ull << 46)) return set_error(ctx, H264B_E_INVALID, "annexb_scan: stream too long");
+    uint64_t o_desc, o_start, o_roff, o_hdr;
+    const uint64_t need = scratch_layout(n, nal_cap, &o_desc, &o_start, &o_roff, &o_hdr);
+    if (need > ctx->scan_scratch_bytes) {
+        if (ctx->scan_scratch) cudaFree(ctx->scan_scratch);
+        ctx->scan_scratch = nullptr;
+        ctx->scan_scratch_bytes = 0;
+        H264B_CUDA(ctx, cudaMalloc(&ctx->scan_scratch, need));
+        ctx->scan_scratch_bytes = need;
+    }
+    uint8_t *s = (uint8_t *)ctx->scan_scratch;
+    const uint64_t n_tiles = (n + kTile - 1) / kTile;
+    ScanArgs a;
+    a.in = d_stream;
+    a.n = n;
+    a.out = d_rbsp;
+    a.hdr = (ScanScratchHeader *)s;
+    a.desc_kept = (unsigned long long *)(s + o_desc);
+    a.desc_nal = a.desc_kept + n_tiles;
+    a.nal_start = (unsigned long long *)(s + o_start);
+    a.nal_rbsp_off = (unsigned long long *)(s + o_roff);
+    a.nal_hdr = (uint32_t *)(s + o_hdr);
+    a.nal_cap = nal_cap;
+    a.n_tiles = (uint32_t)n_tiles;
+
+    const int init_blocks = (int)((2 * n_tiles + 255) / 256 < 1 ? 1 : ((2 * n_tiles + 255) / 256 > 1184 ? 1184 : (2 * n_tiles + 255) / 256));
+    scan_init_kernel<<<init_blocks, 256, 0, ctx->stream>>>(a.hdr, a.desc_kept, 2 * n_tiles, n);
+    H264B_LAUNCH_CHECK(ctx, "scan_init_kernel");
+    if (n_tiles) {
+        const uint64_t chunks = (n + 4095) / 4096;
+        const int fs_blocks = (int)(chunks < (uint64_t)ctx->sm_count * 4 ? chunks : (uint64_t)ctx->sm_count * 4);
+        first_start_kernel<<<fs_blocks, 256, 0, ctx->stream>>>(d_stream, n, a.hdr);
+        H264B_LAUNCH_CHECK(ctx, "first_start_kernel");
+
+        static bool attr_set = false;
+        const size_t smem = sizeof(ScanSmem);
+        if (!attr_set) {
+            H264B_CUDA(ctx, cudaFuncSetAttribute(annexb_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem));
+            attr_set = true;
+        }
+        int occ = 0;
+        H264B_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, annexb_scan_kernel, kThreads, smem));
+        if (occ < 1) occ = 1;
+        uint64_t grid = (uint64_t)ctx->sm_count * occ;
+        if (grid > n_tiles) grid = n_tiles;
+        annexb_scan_kernel<<<(int)grid, kThreads, smem, ctx->stream>>>(a);
+        H264B_LAUNCH_CHECK(ctx, "annexb_scan_kernel");
+    }
+    int fin_blocks = ctx->sm_count * 2;
+    scan_finalize_kernel<<<fin_blocks, 256, 0, ctx->stream>>>(a, d_nals, d_ext, d_summary);
+    H264B_LAUNCH_CHECK(ctx, "scan_finalize_kernel");
+    scan_summary_epb_kernel<<<1, 1, 0, ctx->stream>>>(a.hdr, d_summary);
+    H264B_LAUNCH_CHECK(ctx, "scan_summary_epb_kernel");
+    return H264B_OK;
+}
+
+int launch_nal_frames(h264b_ctx *ctx, const uint8_t *d_frames, uint64_t total, const uint64_t *d_off,
+                      const uint32_t *d_len, uint32_t n_frames, h264b_nal *d_nals, h264b_nal_ext *d_ext,
+                      uint8_t *d_rbsp) {
+    if (!n_frames) return H264B_OK;
+    int blocks = (int)(n_frames < (uint32_t)ctx->sm_count * 8 ? n_frames : (uint32_t)ctx->sm_count * 8);
+    nal_frames_kernel<<<blocks, 256, 0, ctx->stream>>>(d_frames, total, d_off, d_len, n_frames, d_nals, d_ext, d_rbsp);
+    H264B_LAUNCH_CHECK(ctx, "nal_frames_kernel");
+    return H264B_OK;
+}
+
+int launch_slice_select(h264b_ctx *ctx, const h264b_nal *d_nals, const h264b_scan_summary *d_summary,
+                        uint32_t nal_cap, uint32_t slice_data_offset, uint32_t max_slices, uint64_t *d_off,
+                        uint32_t *d_len, uint32_t *d_slice_nal, uint32_t *d_n_slices) {
+    slice_select_kernel<<<1, 1024, 0, ctx->stream>>>(d_nals, d_summary, nal_cap, slice_data_offset, max_slices, d_off,
+                                                     d_len, d_slice_nal, d_n_slices);
+    H264B_LAUNCH_CHECK(ctx, "slice_select_kernel");
+    return H264B_OK;
+}
+
+}  // namespace h264b
+
+extern "C" uint64_t h264b_annexb_scratch_bytes(uint64_t n) {
+    uint64_t a, b, c, d;
+    return h264b::scratch_layout(n, 0, &a, &b, &c, &d);
+}

@@ -1,0 +1,464 @@
+// api.cu -- context management and the host-buffer entry points of libh264b200 (see include/h264b200.h).
+// Everything that computes runs in the kernels of annexb_scan.cu / cabac_engine.cu / ctx_init.cu; this file only
+// moves bytes between host and device and sequences launches.  There is no CPU implementation of the path here.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace h264b {
+
+int set_error(h264b_ctx *ctx, int code, const char *fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+int ensure_dev(h264b_ctx *ctx, int slot, size_t bytes, void **out) {
+    if (bytes < 256) bytes = 256;
+    if (ctx->d_buf_bytes[slot] < bytes) {
+        if (ctx->d_buf[slot]) {
+            H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_buf[slot]);
+            ctx->d_buf[slot] = nullptr;
+            ctx->d_buf_bytes[slot] = 0;
+        }
+        const size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&ctx->d_buf[slot], want);
+        if (e != cudaSuccess) return set_error(ctx, H264B_E_NOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+        ctx->d_buf_bytes[slot] = want;
+    }
+    *out = ctx->d_buf[slot];
+    return H264B_OK;
+}
+
+int ensure_pin(h264b_ctx *ctx, int slot, size_t bytes, void **out) {
+    if (bytes < 256) bytes = 256;
+    if (ctx->h_pin_bytes[slot] < bytes) {
+        if (ctx->h_pin[slot]) {
+            H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFreeHost(ctx->h_pin[slot]);
+            ctx->h_pin[slot] = nullptr;
+            ctx->h_pin_bytes[slot] = 0;
+        }
+        const size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaHostAlloc(&ctx->h_pin[slot], want, cudaHostAllocDefault);
+        if (e != cudaSuccess)
+            return set_error(ctx, H264B_E_NOMEM, "cudaHostAlloc(%zu): %s", want, cudaGetErrorString(e));
+        ctx->h_pin_bytes[slot] = want;
+    }
+    *out = ctx->h_pin[slot];
+    return H264B_OK;
+}
+
+}  // namespace h264b
+
+using namespace h264b;
+
+#define CHECK_CTX(ctx)                      \
+    do {                                    \
+        if (!(ctx)) return H264B_E_INVALID; \
+        cudaSetDevice((ctx)->device);       \
+    } while (0)
+#define RC(expr)                  \
+    do {                          \
+        int rc_ = (expr);         \
+        if (rc_) return rc_;      \
+    } while (0)
+
+extern "C" {
+
+int32_t h264b_version(void) { return H264B_VERSION; }
+
+int32_t h264b_device_count(int32_t *count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (count) *count = (e == cudaSuccess) ? n : 0;
+    return (e == cudaSuccess && n > 0) ? H264B_OK : H264B_E_NO_DEVICE;
+}
+
+int32_t h264b_create(int32_t device, h264b_ctx **out) {
+    if (!out) return H264B_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return H264B_E_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return H264B_E_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return H264B_E_CUDA;
+    if (prop.major < 10) return H264B_E_NO_DEVICE;  // sm_100a code only
+    h264b_ctx *ctx = (h264b_ctx *)calloc(1, sizeof(h264b_ctx));
+    if (!ctx) return H264B_E_NOMEM;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        free(ctx);
+        return H264B_E_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    int rc = build_tables(ctx);
+    if (rc) {
+        fprintf(stderr, "h264b_create: %s\n", ctx->err);
+        h264b_destroy(ctx);
+        return rc;
+    }
+    ctx->launches = 0;  // table construction is not counted
+    *out = ctx;
+    return H264B_OK;
+}
+
+void h264b_destroy(h264b_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int v = 0; v < 2; v++) {
+        cudaFree(ctx->d_cabac_tab[v]);
+        cudaFree(ctx->d_range_lps[v]);
+        cudaFree(ctx->d_trans[v]);
+        cudaFree(ctx->d_mn[v]);
+        cudaFree(ctx->d_state_lut[v]);
+    }
+    for (int i = 0; i < 16; i++) cudaFree(ctx->d_buf[i]);
+    for (int i = 0; i < 8; i++)
+        if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
+    cudaFree(ctx->scan_scratch);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    free(ctx);
+}
+
+const char *h264b_last_error(const h264b_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+int32_t h264b_set_stream(h264b_ctx *ctx, void *cuda_stream) {
+    CHECK_CTX(ctx);
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return H264B_OK;
+}
+
+int32_t h264b_sync(h264b_ctx *ctx) {
+    CHECK_CTX(ctx);
+    H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return H264B_OK;
+}
+
+int32_t h264b_host_alloc(h264b_ctx *ctx, size_t bytes, void **out) {
+    CHECK_CTX(ctx);
+    if (!out) return H264B_E_INVALID;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return set_error(ctx, H264B_E_NOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return H264B_OK;
+}
+int32_t h264b_host_free(h264b_ctx *ctx, void *p) {
+    CHECK_CTX(ctx);
+    if (p) H264B_CUDA(ctx, cudaFreeHost(p));
+    return H264B_OK;
+}
+int32_t h264b_dev_alloc(h264b_ctx *ctx, size_t bytes, void **out) {
+    CHECK_CTX(ctx);
+    if (!out) return H264B_E_INVALID;
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return set_error(ctx, H264B_E_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return H264B_OK;
+}
+int32_t h264b_dev_free(h264b_ctx *ctx, void *p) {
+    CHECK_CTX(ctx);
+    if (p) H264B_CUDA(ctx, cudaFree(p));
+    return H264B_OK;
+}
+int32_t h264b_memcpy_h2d(h264b_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    CHECK_CTX(ctx);
+    if (bytes) H264B_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return H264B_OK;
+}
+int32_t h264b_memcpy_d2h(h264b_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    CHECK_CTX(ctx);
+    if (bytes) H264B_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return H264B_OK;
+}
+int32_t h264b_launch_count(const h264b_ctx *ctx, uint64_t *count) {
+    if (!ctx || !count) return H264B_E_INVALID;
+    *count = ctx->launches;
+    return H264B_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ "_dev" entries
+int32_t h264b_annexb_scan_dev(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint8_t *d_rbsp, h264b_nal *d_nals,
+                              h264b_nal_ext *d_ext, uint32_t nal_cap, h264b_scan_summary *d_summary, uint32_t flags) {
+    CHECK_CTX(ctx);
+    if (!d_rbsp || !d_nals || !d_summary || (!d_stream && n)) return set_error(ctx, H264B_E_INVALID, "null pointer");
+    return launch_annexb_scan(ctx, d_stream, n, d_rbsp, d_nals, d_ext, nal_cap, d_summary, flags);
+}
+
+int32_t h264b_ctx_init_dev(h264b_ctx *ctx, const h264b_slice_qp *d_params, uint32_t n_slices, uint32_t n_ctx,
+                           uint8_t *d_states, uint32_t flags) {
+    CHECK_CTX(ctx);
+    if (n_slices && (!d_params || !d_states)) return set_error(ctx, H264B_E_INVALID, "null pointer");
+    return launch_ctx_init(ctx, d_params, n_slices, n_ctx, d_states, flags);
+}
+
+int32_t h264b_cabac_decode_dev(h264b_ctx *ctx, const h264b_cabac_job *job) {
+    CHECK_CTX(ctx);
+    if (!job) return H264B_E_INVALID;
+    return launch_cabac(ctx, job);
+}
+
+// ------------------------------------------------------------------------------------------------ host entries
+// device slots: 0 stream/frames/bytes  1 rbsp  2 nals  3 ext  4 summary+counters  5 off  6 len  7 ops  8 n_ops
+//               9 qp  10 init/final states  11 bins  12 final  13 slice_nal  14 states(K4)  15 scalar io
+// pinned slots: 0 nals  1 ext  2 rbsp  3 bins  4 final  5 slice_nal  6 misc
+static uint32_t default_nal_cap(uint64_t n) {
+    uint64_t c = n / 64 + 1024;
+    return (uint32_t)(c > 0x7FFFFFF0ull ? 0x7FFFFFF0ull : c);
+}
+
+static int scan_host_common(h264b_ctx *ctx, const uint8_t *stream, uint64_t n, uint32_t flags, uint32_t *cap_io,
+                            h264b_scan_summary *summary, uint8_t **d_rbsp_out, h264b_nal **d_nals_out,
+                            h264b_nal_ext **d_ext_out, h264b_scan_summary **d_sum_out, bool want_ext) {
+    void *d_stream, *d_rbsp, *d_nals, *d_ext = nullptr, *d_sum;
+    RC(ensure_dev(ctx, 0, n + 64, &d_stream));
+    RC(ensure_dev(ctx, 1, n + 64, &d_rbsp));
+    RC(ensure_dev(ctx, 4, 256, &d_sum));
+    if (n) H264B_CUDA(ctx, cudaMemcpyAsync(d_stream, stream, n, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t cap = *cap_io;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        RC(ensure_dev(ctx, 2, (size_t)cap * sizeof(h264b_nal), &d_nals));
+        if (want_ext) RC(ensure_dev(ctx, 3, (size_t)cap * sizeof(h264b_nal_ext), &d_ext));
+        RC(launch_annexb_scan(ctx, (const uint8_t *)d_stream, n, (uint8_t *)d_rbsp, (h264b_nal *)d_nals,
+                              (h264b_nal_ext *)d_ext, cap, (h264b_scan_summary *)d_sum, flags));
+        H264B_CUDA(ctx, cudaMemcpyAsync(summary, d_sum, sizeof(*summary), cudaMemcpyDeviceToHost, ctx->stream));
+        H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (summary->status != H264B_E_CAPACITY) break;
+        if (summary->n_start_codes + 1 > 0x7FFFFFF0ull) return set_error(ctx, H264B_E_CAPACITY, "too many NAL units");
+        cap = (uint32_t)(summary->n_start_codes + 1);
+    }
+    if (summary->status != H264B_OK) return set_error(ctx, H264B_E_CAPACITY, "NAL index capacity");
+    *cap_io = cap;
+    *d_rbsp_out = (uint8_t *)d_rbsp;
+    *d_nals_out = (h264b_nal *)d_nals;
+    *d_ext_out = (h264b_nal_ext *)d_ext;
+    *d_sum_out = (h264b_scan_summary *)d_sum;
+    return H264B_OK;
+}
+
+int32_t h264b_annexb_scan(h264b_ctx *ctx, const uint8_t *stream, uint64_t n, uint32_t flags, int32_t want_rbsp,
+                          const h264b_nal **nals, const h264b_nal_ext **ext, h264b_scan_summary *summary,
+                          const uint8_t **rbsp, const uint8_t **d_rbsp_out) {
+    CHECK_CTX(ctx);
+    if (!summary || (!stream && n)) return set_error(ctx, H264B_E_INVALID, "null pointer");
+    uint32_t cap = default_nal_cap(n);
+    uint8_t *d_rbsp;
+    h264b_nal *d_nals;
+    h264b_nal_ext *d_ext;
+    h264b_scan_summary *d_sum;
+    RC(scan_host_common(ctx, stream, n, flags, &cap, summary, &d_rbsp, &d_nals, &d_ext, &d_sum, ext != nullptr));
+    void *h_nals, *h_ext = nullptr, *h_rbsp = nullptr;
+    const size_t nn = (size_t)summary->n_nals;
+    RC(ensure_pin(ctx, 0, nn * sizeof(h264b_nal), &h_nals));
+    if (nn) H264B_CUDA(ctx, cudaMemcpyAsync(h_nals, d_nals, nn * sizeof(h264b_nal), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ext) {
+        RC(ensure_pin(ctx, 1, nn * sizeof(h264b_nal_ext), &h_ext));
+        if (nn)
+            H264B_CUDA(ctx, cudaMemcpyAsync(h_ext, d_ext, nn * sizeof(h264b_nal_ext), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (want_rbsp) {
+        RC(ensure_pin(ctx, 2, (size_t)summary->rbsp_bytes, &h_rbsp));
+        if (summary->rbsp_bytes)
+            H264B_CUDA(ctx, cudaMemcpyAsync(h_rbsp, d_rbsp, (size_t)summary->rbsp_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nals) *nals = (const h264b_nal *)h_nals;
+    if (ext) *ext = (const h264b_nal_ext *)h_ext;
+    if (rbsp) *rbsp = (const uint8_t *)h_rbsp;
+    if (d_rbsp_out) *d_rbsp_out = d_rbsp;
+    return H264B_OK;
+}
+
+int32_t h264b_nal_units(h264b_ctx *ctx, const uint8_t *frames, uint64_t total_bytes, const uint64_t *frame_off,
+                        const uint32_t *frame_len, uint32_t n_frames, uint32_t flags, h264b_nal *nals,
+                        h264b_nal_ext *ext, uint8_t *rbsp) {
+    (void)flags;
+    CHECK_CTX(ctx);
+    if (!n_frames) return H264B_OK;
+    if (!frame_off || !frame_len || !nals || !rbsp || (!frames && total_bytes))
+        return set_error(ctx, H264B_E_INVALID, "null pointer");
+    for (uint32_t i = 0; i < n_frames; i++)
+        if (frame_off[i] + frame_len[i] > total_bytes) return set_error(ctx, H264B_E_INVALID, "frame %u out of range", i);
+    void *d_in, *d_out, *d_nals, *d_ext = nullptr, *d_off, *d_len;
+    RC(ensure_dev(ctx, 0, total_bytes + 64, &d_in));
+    RC(ensure_dev(ctx, 1, total_bytes + 64, &d_out));
+    RC(ensure_dev(ctx, 2, (size_t)n_frames * sizeof(h264b_nal), &d_nals));
+    if (ext) RC(ensure_dev(ctx, 3, (size_t)n_frames * sizeof(h264b_nal_ext), &d_ext));
+    RC(ensure_dev(ctx, 5, (size_t)n_frames * 8, &d_off));
+    RC(ensure_dev(ctx, 6, (size_t)n_frames * 4, &d_len));
+    if (total_bytes) H264B_CUDA(ctx, cudaMemcpyAsync(d_in, frames, total_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    H264B_CUDA(ctx, cudaMemcpyAsync(d_off, frame_off, (size_t)n_frames * 8, cudaMemcpyHostToDevice, ctx->stream));
+    H264B_CUDA(ctx, cudaMemcpyAsync(d_len, frame_len, (size_t)n_frames * 4, cudaMemcpyHostToDevice, ctx->stream));
+    RC(launch_nal_frames(ctx, (const uint8_t *)d_in, total_bytes, (const uint64_t *)d_off, (const uint32_t *)d_len,
+                         n_frames, (h264b_nal *)d_nals, (h264b_nal_ext *)d_ext, (uint8_t *)d_out));
+    H264B_CUDA(ctx, cudaMemcpyAsync(nals, d_nals, (size_t)n_frames * sizeof(h264b_nal), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ext)
+        H264B_CUDA(ctx, cudaMemcpyAsync(ext, d_ext, (size_t)n_frames * sizeof(h264b_nal_ext), cudaMemcpyDeviceToHost, ctx->stream));
+    if (total_bytes) H264B_CUDA(ctx, cudaMemcpyAsync(rbsp, d_out, total_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return H264B_OK;
+}
+
+int32_t h264b_ctx_init(h264b_ctx *ctx, const h264b_slice_qp *params, uint32_t n_slices, uint32_t n_ctx,
+                       uint8_t *states, uint32_t flags) {
+    CHECK_CTX(ctx);
+    if (!n_slices) return H264B_OK;
+    if (!params || !states) return set_error(ctx, H264B_E_INVALID, "null pointer");
+    void *d_p, *d_s;
+    RC(ensure_dev(ctx, 9, (size_t)n_slices * sizeof(h264b_slice_qp), &d_p));
+    RC(ensure_dev(ctx, 14, (size_t)n_slices * n_ctx, &d_s));
+    H264B_CUDA(ctx, cudaMemcpyAsync(d_p, params, (size_t)n_slices * sizeof(h264b_slice_qp), cudaMemcpyHostToDevice, ctx->stream));
+    RC(launch_ctx_init(ctx, (const h264b_slice_qp *)d_p, n_slices, n_ctx, (uint8_t *)d_s, flags));
+    H264B_CUDA(ctx, cudaMemcpyAsync(states, d_s, (size_t)n_slices * n_ctx, cudaMemcpyDeviceToHost, ctx->stream));
+    H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return H264B_OK;
+}
+
+int32_t h264b_cabac_decode(h264b_ctx *ctx, const h264b_cabac_job *job) {
+    CHECK_CTX(ctx);
+    if (!job) return H264B_E_INVALID;
+    const h264b_cabac_job &j = *job;
+    if (!j.n_slices) return H264B_OK;
+    if (!j.bytes || !j.off || !j.len || !j.bins || !j.final || (!j.ops && j.n_ops_max) || (!j.qp && !j.init_states))
+        return set_error(ctx, H264B_E_INVALID, "cabac: null pointer in job");
+    for (uint32_t s = 0; s < j.n_slices; s++)
+        if (j.off[s] + j.len[s] > j.total_bytes) return set_error(ctx, H264B_E_INVALID, "slice %u out of range", s);
+    const size_t ns = j.n_slices;
+    void *d_bytes, *d_off, *d_len, *d_ops, *d_nops = nullptr, *d_qp = nullptr, *d_init = nullptr, *d_bins, *d_fin,
+         *d_fst = nullptr;
+    RC(ensure_dev(ctx, 0, j.total_bytes + 64, &d_bytes));
+    RC(ensure_dev(ctx, 5, ns * 8, &d_off));
+    RC(ensure_dev(ctx, 6, ns * 4, &d_len));
+    RC(ensure_dev(ctx, 7, (size_t)j.n_ops_max * 2 + 16, &d_ops));
+    RC(ensure_dev(ctx, 11, ns * j.bins_stride_words * 4, &d_bins));
+    RC(ensure_dev(ctx, 12, ns * sizeof(h264b_cabac_final), &d_fin));
+    H264B_CUDA(ctx, cudaMemcpyAsync(d_bytes, j.bytes, j.total_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    H264B_CUDA(ctx, cudaMemcpyAsync(d_off, j.off, ns * 8, cudaMemcpyHostToDevice, ctx->stream));
+    H264B_CUDA(ctx, cudaMemcpyAsync(d_len, j.len, ns * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (j.n_ops_max)
+        H264B_CUDA(ctx, cudaMemcpyAsync(d_ops, j.ops, (size_t)j.n_ops_max * 2, cudaMemcpyHostToDevice, ctx->stream));
+    if (j.n_ops) {
+        RC(ensure_dev(ctx, 8, ns * 4, &d_nops));
+        H264B_CUDA(ctx, cudaMemcpyAsync(d_nops, j.n_ops, ns * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (j.qp) {
+        RC(ensure_dev(ctx, 9, ns * sizeof(h264b_slice_qp), &d_qp));
+        H264B_CUDA(ctx, cudaMemcpyAsync(d_qp, j.qp, ns * sizeof(h264b_slice_qp), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const size_t st_bytes = ns * j.n_ctx;
+    if (j.init_states || j.final_states) {
+        void *d_st;
+        RC(ensure_dev(ctx, 10, 2 * st_bytes, &d_st));
+        if (j.init_states) {
+            d_init = d_st;
+            H264B_CUDA(ctx, cudaMemcpyAsync(d_init, j.init_states, st_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        if (j.final_states) d_fst = (uint8_t *)d_st + st_bytes;
+    }
+    h264b_cabac_job dj = j;
+    dj.bytes = (const uint8_t *)d_bytes;
+    dj.off = (const uint64_t *)d_off;
+    dj.len = (const uint32_t *)d_len;
+    dj.ops = (const uint16_t *)d_ops;
+    dj.n_ops = (const uint32_t *)d_nops;
+    dj.qp = (const h264b_slice_qp *)d_qp;
+    dj.init_states = (const uint8_t *)d_init;
+    dj.bins = (uint32_t *)d_bins;
+    dj.final = (h264b_cabac_final *)d_fin;
+    dj.final_states = (uint8_t *)d_fst;
+    RC(launch_cabac(ctx, &dj));
+    H264B_CUDA(ctx, cudaMemcpyAsync(j.bins, d_bins, ns * j.bins_stride_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    H264B_CUDA(ctx, cudaMemcpyAsync(j.final, d_fin, ns * sizeof(h264b_cabac_final), cudaMemcpyDeviceToHost, ctx->stream));
+    if (j.final_states)
+        H264B_CUDA(ctx, cudaMemcpyAsync(j.final_states, d_fst, st_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return H264B_OK;
+}
+
+int32_t h264b_stream_decode(h264b_ctx *ctx, const h264b_stream_job *job, h264b_stream_result *res) {
+    CHECK_CTX(ctx);
+    if (!job || !res) return H264B_E_INVALID;
+    const h264b_stream_job &j = *job;
+    if ((!j.stream && j.n) || !j.qp || (!j.ops && j.n_ops_max))
+        return set_error(ctx, H264B_E_INVALID, "stream_decode: null pointer in job");
+    memset(res, 0, sizeof(*res));
+    // 1. split + strip (the RBSP stays on the device)
+    uint32_t cap = default_nal_cap(j.n);
+    uint8_t *d_rbsp;
+    h264b_nal *d_nals;
+    h264b_nal_ext *d_ext;
+    h264b_scan_summary *d_sum;
+    RC(scan_host_common(ctx, j.stream, j.n, j.flags, &cap, &res->scan, &d_rbsp, &d_nals, &d_ext, &d_sum, false));
+    // 2. slice NAL list on the device
+    const size_t ms = j.max_slices ? j.max_slices : 1;
+    void *d_off, *d_len, *d_snal, *d_ops, *d_nops = nullptr, *d_qp, *d_bins, *d_fin;
+    RC(ensure_dev(ctx, 5, ms * 8, &d_off));
+    RC(ensure_dev(ctx, 6, ms * 4, &d_len));
+    RC(ensure_dev(ctx, 13, ms * 4 + 16, &d_snal));
+    uint32_t *d_ns = (uint32_t *)((uint8_t *)d_sum + 64);
+    RC(launch_slice_select(ctx, d_nals, d_sum, cap, j.slice_data_offset, j.max_slices, (uint64_t *)d_off,
+                           (uint32_t *)d_len, (uint32_t *)d_snal, d_ns));
+    uint32_t n_slices = 0;
+    H264B_CUDA(ctx, cudaMemcpyAsync(&n_slices, d_ns, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    // meanwhile: schedule and per-slice parameters
+    RC(ensure_dev(ctx, 7, (size_t)j.n_ops_max * 2 + 16, &d_ops));
+    RC(ensure_dev(ctx, 9, ms * sizeof(h264b_slice_qp), &d_qp));
+    if (j.n_ops_max)
+        H264B_CUDA(ctx, cudaMemcpyAsync(d_ops, j.ops, (size_t)j.n_ops_max * 2, cudaMemcpyHostToDevice, ctx->stream));
+    H264B_CUDA(ctx, cudaMemcpyAsync(d_qp, j.qp, ms * sizeof(h264b_slice_qp), cudaMemcpyHostToDevice, ctx->stream));
+    if (j.n_ops) {
+        RC(ensure_dev(ctx, 8, ms * 4, &d_nops));
+        H264B_CUDA(ctx, cudaMemcpyAsync(d_nops, j.n_ops, ms * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // 3. CABAC over the slices, contexts initialised in-kernel by the K4 rule
+    const uint32_t stride = (j.n_ops_max + 1 + 31) / 32;
+    res->n_slices = n_slices;
+    res->bins_stride_words = stride;
+    void *h_nals, *h_bins, *h_fin, *h_snal;
+    const size_t nn = (size_t)res->scan.n_nals;
+    RC(ensure_pin(ctx, 0, nn * sizeof(h264b_nal), &h_nals));
+    if (nn) H264B_CUDA(ctx, cudaMemcpyAsync(h_nals, d_nals, nn * sizeof(h264b_nal), cudaMemcpyDeviceToHost, ctx->stream));
+    res->nals = (const h264b_nal *)h_nals;
+    if (n_slices) {
+        RC(ensure_dev(ctx, 11, (size_t)n_slices * stride * 4, &d_bins));
+        RC(ensure_dev(ctx, 12, (size_t)n_slices * sizeof(h264b_cabac_final), &d_fin));
+        h264b_cabac_job cj;
+        memset(&cj, 0, sizeof(cj));
+        cj.bytes = d_rbsp;
+        cj.total_bytes = j.n + 16;
+        cj.off = (const uint64_t *)d_off;
+        cj.len = (const uint32_t *)d_len;
+        cj.n_slices = n_slices;
+        cj.n_ctx = j.n_ctx;
+        cj.ops = (const uint16_t *)d_ops;
+        cj.n_ops_max = j.n_ops_max;
+        cj.n_ops = (const uint32_t *)d_nops;
+        cj.qp = (const h264b_slice_qp *)d_qp;
+        cj.bins = (uint32_t *)d_bins;
+        cj.bins_stride_words = stride;
+        cj.final = (h264b_cabac_final *)d_fin;
+        cj.flags = j.flags;
+        RC(launch_cabac(ctx, &cj));
+        RC(ensure_pin(ctx, 3, (size_t)n_slices * stride * 4, &h_bins));
+        RC(ensure_pin(ctx, 4, (size_t)n_slices * sizeof(h264b_cabac_final), &h_fin));
+        RC(ensure_pin(ctx, 5, (size_t)n_slices * 4, &h_snal));
+        H264B_CUDA(ctx, cudaMemcpyAsync(h_bins, d_bins, (size_t)n_slices * stride * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        H264B_CUDA(ctx, cudaMemcpyAsync(h_fin, d_fin, (size_t)n_slices * sizeof(h264b_cabac_final), cudaMemcpyDeviceToHost, ctx->stream));
+        H264B_CUDA(ctx, cudaMemcpyAsync(h_snal, d_snal, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        res->bins = (const uint32_t *)h_bins;
+        res->final = (const h264b_cabac_final *)h_fin;
+        res->slice_nal = (const uint32_t *)h_snal;
+    }
+    H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t s = 0; s < n_slices; s++) res->total_bins += res->final[s].n_bins;
+    return H264B_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+// cabac_engine.cu -- K3: the CABAC arithmetic-decoding engine, one slice per warp lane.
+//
+// Reference functions replaced (h264/cabac.go): initDecodingEngine :439-446, BinaryDecision core :525-536 +
+// StateTransitionProcess :544-553 + RenormD :503-511 composed as DecodeDecision, DecodeBypass :468-481,
+// DecodeTerminate :486-499; tables h264/rangeTabLPS.go and h264/stateTransxTab.go (folded into one 128 x 64-bit
+// table indexed by the context's state byte, see ctx_init.cu).
+//
+// Mapping.  CABAC is serial inside a slice and slices share nothing, so a lane owns a slice.  All slices follow one
+// shared op schedule, hence every lane of a warp executes the same op kind on the same ctxIdx at the same time: no
+// divergence on the op, and the context-state access  state[ctxIdx][lane]  is one conflict-free 32-byte row of
+// shared memory.  Per-lane bit windows drift apart (bits per bin are data dependent); refills are warp-synchronised:
+// when any lane runs low, every lane that has room takes 32 more bits, so the refill code runs once per ~15-30 bins
+// instead of (divergently) on almost every bin.  The next 32-bit word of each lane's bitstream is prefetched one
+// refill ahead, which hides the (uncoalesced, L2-resident) load completely; bitstream traffic is ~0.11 B per bin.
+#include "cabac_lane.cuh"
+#include "common.cuh"
+
+namespace h264b {
+
+constexpr int kWarpsPerCta = 2;
+
+struct CabacArgs {
+    h264b_cabac_job j;
+    const uint64_t *tab;   // 128-entry engine table
+    const uint8_t *lut;    // K4 state LUT [5][52][1024]
+    uint32_t lanes_per_warp;
+    uint32_t n_warps;
+};
+
+__device__ __forceinline__ int idc_class_dev(int idc) { return (idc >= -1 && idc <= 2) ? idc + 1 : 4; }
+__device__ __forceinline__ int clip3_dev(int x, int y, int z) { return z < x ? x : (z > y ? y : z); }
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t *s_tab = reinterpret_cast<uint64_t *>(smem);                  // 128 x 8 B
+    uint8_t *s_state_all = smem + 1024;                                    // [warp][n_ctx][32]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 128; i += kWarpsPerCta * 32) s_tab[i] = a.tab[i];
+    __syncthreads();
+    const h264b_cabac_job &j = a.j;
+    const uint32_t n_ctx = j.n_ctx;
+    uint8_t *s_state = s_state_all + (size_t)warp * n_ctx * 32;
+
+    const uint32_t gw = blockIdx.x * kWarpsPerCta + warp;
+    if (gw >= a.n_warps) return;
+    const uint32_t slice = gw * a.lanes_per_warp + lane;
+    const bool valid = lane < (int)a.lanes_per_warp && slice < j.n_slices;
+
+    // ---- per-lane setup
+    uint32_t my_ops = 0;
+    uint64_t off = 0;
+    uint32_t len = 0;
+    if (valid) {
+        my_ops = j.n_ops ? j.n_ops[slice] : j.n_ops_max;
+        if (my_ops > j.n_ops_max) my_ops = j.n_ops_max;
+        off = j.off[slice];
+        len = j.len[slice];
+    }
+    // initial context states: given, or the K4 rule (state LUT row of this slice's (idc class, clipped qp))
+    if (valid) {
+        const uint8_t *src;
+        if (j.init_states) {
+            src = j.init_states + (size_t)slice * n_ctx;
+        } else {
+            const h264b_slice_qp p = j.qp[slice];
+            src = a.lut + ((size_t)idc_class_dev(p.cabac_init_idc) * 52 + clip3_dev(0, 51, p.slice_qp_y)) * 1024;
+        }
+        for (uint32_t c = 0; c < n_ctx; c++) s_state[c * 32 + lane] = src[c];
+    }
+    __syncwarp();
+
+    LaneDecoder eng = {};
+    if (valid) eng.init(j.bytes, j.total_bytes, off, (j.flags & H264B_BYPASS_SPEC_OR) != 0);
+
+    uint32_t warp_ops = my_ops;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) warp_ops = max(warp_ops, __shfl_xor_sync(0xFFFFFFFFu, warp_ops, d));
+
+    uint32_t *bins = valid ? j.bins + (size_t)slice * j.bins_stride_words : nullptr;
+    uint32_t word = 0;
+    uint32_t next_op = warp_ops ? j.ops[0] : 0;
+    for (uint32_t i = 0; i < warp_ops; i++) {
+        const uint32_t op = next_op;
+        if (i + 1 < warp_ops) next_op = j.ops[i + 1];
+        const bool active = i < my_ops;
+        if (__any_sync(0xFFFFFFFFu, active && eng.must_refill())) {
+            if (active) eng.refill_if_room();
+        }
+        const uint32_t kind = op >> 14;
+        uint32_t bin = 0;
+        if (kind == H264B_OP_DECISION) {
+            uint32_t c = op & 0x3FFu;
+            if (c >= n_ctx) c = 0;
+            uint8_t *sp = s_state + c * 32 + lane;
+            if (active) {
+                const uint64_t e = s_tab[*sp & 127u];
+                uint8_t ns;
+                bin = eng.decision(e, &ns);
+                *sp = ns;
+            }
+        } else if (kind == H264B_OP_BYPASS) {
+            if (active) bin = eng.bypass();
+        } else {
+            if (active) bin = eng.terminate();
+        }
+        if (active) {  // a lane that has finished keeps its last partial word for the tail below
+            word |= bin << (i & 31u);
+            if ((i & 31u) == 31u) {
+                bins[i >> 5] = word;
+                word = 0;
+            }
+        }
+    }
+    // ---- tail: optional final DecodeTerminate, flush, final record
+    if (valid) {
+        uint32_t n_bins = my_ops;
+        if (j.flags & H264B_CABAC_FINAL_TERMINATE) {
+            if (eng.must_refill()) eng.refill_if_room();
+            const uint32_t bin = eng.terminate();
+            word |= bin << (my_ops & 31u);  // `word` holds bins (my_ops & ~31) .. my_ops-1 (empty after a flush)
+            n_bins++;
+        }
+        if (n_bins & 31u) bins[n_bins >> 5] = word;
+        else if ((j.flags & H264B_CABAC_FINAL_TERMINATE) && (n_bins & 31u) == 0) bins[(n_bins - 1) >> 5] = word;
+        h264b_cabac_final f;
+        const uint64_t bits_read = eng.bits_read();
+        f.cod_i_range = eng.cod_i_range();
+        f.cod_i_offset = eng.cod_i_offset();
+        f.bits_read = bits_read;
+        f.flags = bits_read > 8ull * len ? H264B_F_OVERRUN : 0u;
+        f.n_bins = n_bins;
+        j.final[slice] = f;
+        if (j.final_states) {
+            uint8_t *dst = j.final_states + (size_t)slice * n_ctx;
+            for (uint32_t c = 0; c < n_ctx; c++) dst[c] = s_state[c * 32 + lane];
+        }
+    }
+}
+
+int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job) {
+    const h264b_cabac_job &j = *job;
+    if (j.n_ctx < 1 || j.n_ctx > 1024) return set_error(ctx, H264B_E_INVALID, "cabac: n_ctx must be 1..1024");
+    if (!j.n_slices) return H264B_OK;
+    if (!j.bytes || !j.off || !j.len || !j.bins || !j.final || (!j.ops && j.n_ops_max))
+        return set_error(ctx, H264B_E_INVALID, "cabac: null pointer in job");
+    if (!j.qp && !j.init_states) return set_error(ctx, H264B_E_INVALID, "cabac: need qp or init_states");
+    if (j.bins_stride_words < (j.n_ops_max + 1 + 31) / 32)
+        return set_error(ctx, H264B_E_INVALID, "cabac: bins_stride_words too small");
+    if ((uintptr_t)j.bytes & 3) return set_error(ctx, H264B_E_INVALID, "cabac: bytes must be 4-byte aligned");
+    const int v = (j.flags & H264B_TABLES_SPEC) ? 1 : 0;
+    CabacArgs a;
+    a.j = j;
+    a.tab = ctx->d_cabac_tab[v];
+    a.lut = ctx->d_state_lut[v];
+    // Few slices: spread them one (or a few) per warp so every slice gets its own scheduler slot and no lane waits on
+    // a neighbour's bank conflict; many slices: 32 per warp.
+    const uint32_t target_warps = (uint32_t)ctx->sm_count * 8;
+    uint32_t lpw = (j.n_slices + target_warps - 1) / target_warps;
+    if (lpw < 1) lpw = 1;
+    if (lpw > 32) lpw = 32;
+    a.lanes_per_warp = lpw;
+    a.n_warps = (j.n_slices + lpw - 1) / lpw;
+    const size_t smem = 1024 + (size_t)kWarpsPerCta * j.n_ctx * 32;
+    const int blocks = (int)((a.n_warps + kWarpsPerCta - 1) / kWarpsPerCta);
+    H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cabac_decode_kernel<<<blocks, kWarpsPerCta * 32, smem, ctx->stream>>>(a);
+    H264B_LAUNCH_CHECK(ctx, "cabac_decode_kernel");
+    return H264B_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- scalar drop-ins
+struct StepIo {
+    int64_t R, O;
+    int32_t p_state, val_mps, bin, pad;
+    uint32_t bits_used, n_bits;
+    uint8_t bits[32];
+};
+
+// One engine primitive with explicit state, bit-at-a-time like the reference (used only for per-call drop-in of
+// the Go functions; the batch kernel above is the throughput path).
+__global__ void engine_step_kernel(StepIo *io, uint32_t kind, uint32_t flags, const uint64_t *tab) {
+    int64_t R = io->R, O = io->O;
+    uint32_t used = 0;
+    auto read_bit = [&]() -> uint32_t {
+        uint32_t b = 0;
+        if (used < io->n_bits && used < 256) b = (io->bits[used >> 3] >> (7 - (used & 7))) & 1u;
+        used++;
+        return b;
+    };
+    auto renorm = [&]() {
+        while (R < 256) {
+            R <<= 1;
+            O = (int64_t)(((uint64_t)O << 1) | read_bit());
+        }
+    };
+    int32_t bin = 0;
+    if (kind == H264B_OP_DECISION) {
+        const uint32_t s = (uint32_t)(io->p_state & 63) | ((uint32_t)(io->val_mps & 1) << 6);
+        const uint64_t e = tab[s];
+        const uint32_t tlo = (uint32_t)e, thi = (uint32_t)(e >> 32);
+        const int64_t lps = (tlo >> ((uint32_t)((R >> 6) & 3) * 8)) & 0xFF;
+        R -= lps;
+        uint32_t sel = thi;
+        if (O >= R) {
+            O = (int64_t)((uint64_t)O - (uint64_t)R);
+            R = lps;
+            sel = thi >> 16;
+        }
+        bin = (sel >> 8) & 1;
+        if (!(flags & 0x80000000u)) {  // composed DecodeDecision; the bare BinaryDecision core stops here (A6)
+            io->p_state = sel & 63;
+            io->val_mps = (sel >> 6) & 1;
+            renorm();
+        }
+    } else if (kind == H264B_OP_BYPASS) {
+        uint64_t o = (uint64_t)O << 1;
+        const uint32_t b = read_bit();
+        o = (flags & H264B_BYPASS_SPEC_OR) ? (o | b) : (o << b);
+        O = (int64_t)o;
+        if (O >= R) {
+            O = (int64_t)((uint64_t)O - (uint64_t)R);
+            bin = 1;
+        }
+    } else if (kind == H264B_OP_TERMINATE) {
+        R -= 2;
+        if (O >= R) {
+            bin = 1;
+        } else {
+            renorm();
+        }
+    } else if (kind == 3u) {  // StateTransitionProcess alone: bin given in io->bin
+        const uint32_t s = (uint32_t)(io->p_state & 63) | ((uint32_t)(io->val_mps & 1) << 6);
+        const uint32_t thi = (uint32_t)(tab[s] >> 32);
+        const uint32_t sel = (io->bin == io->val_mps) ? thi : (thi >> 16);
+        io->p_state = sel & 63;
+        io->val_mps = (sel >> 6) & 1;
+        bin = io->bin;
+    } else if (kind == 4u) {  // RenormD alone
+        renorm();
+    } else if (kind == 5u) {  // initDecodingEngine
+        R = 510;
+        O = 0;
+        for (int i = 0; i < 9; i++) O = (O << 1) | read_bit();
+    }
+    io->R = R;
+    io->O = O;
+    io->bin = bin;
+    io->bits_used = used;
+}
+
+}  // namespace h264b
+
+extern "C" int32_t h264b_engine_step(h264b_ctx *ctx, uint32_t kind, uint32_t flags, const uint8_t *bits,
+                                     uint32_t n_bits, int64_t *R, int64_t *O, int32_t *p_state, int32_t *val_mps,
+                                     int32_t *bin_val, uint32_t *bits_used) {
+    using namespace h264b;
+    if (!ctx || !R || !O) return H264B_E_INVALID;
+    if (n_bits > 256) n_bits = 256;
+    StepIo h;
+    memset(&h, 0, sizeof(h));
+    h.R = *R;
+    h.O = *O;
+    h.p_state = p_state ? *p_state : 0;
+    h.val_mps = val_mps ? *val_mps : 0;
+    h.bin = bin_val ? *bin_val : 0;
+    h.n_bits = n_bits;
+    if (bits && n_bits) memcpy(h.bits, bits, (n_bits + 7) / 8);
+    void *d;
+    int rc = ensure_dev(ctx, 15, sizeof(StepIo), &d);
+    if (rc) return rc;
+    H264B_CUDA(ctx, cudaMemcpyAsync(d, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    engine_step_kernel<<<1, 1, 0, ctx->stream>>>((StepIo *)d, kind, flags,
+                                                 ctx->d_cabac_tab[(flags & H264B_TABLES_SPEC) ? 1 : 0]);
+    H264B_LAUNCH_CHECK(ctx, "engine_step_kernel");
+    H264B_CUDA(ctx, cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *R = h.R;
+    *O = h.O;
+    if (p_state) *p_state = h.p_state;
+    if (val_mps) *val_mps = h.val_mps;
+    if (bin_val) *bin_val = h.bin;
+    if (bits_used) *bits_used = h.bits_used;
+    return H264B_OK;
+}
+
+extern "C" int32_t h264b_binary_decision(h264b_ctx *ctx, uint32_t flags, int32_t p_state, int32_t val_mps, int64_t *R,
+                                         int64_t *O, int32_t *bin_val) {
+    return h264b_engine_step(ctx, H264B_OP_DECISION, flags | 0x80000000u, nullptr, 0, R, O, &p_state, &val_mps,
+                             bin_val, nullptr);
+}
+
+extern "C" int32_t h264b_state_transition(h264b_ctx *ctx, uint32_t flags, int32_t *p_state, int32_t *val_mps,
+                                          int32_t bin_val) {
+    int64_t R = 0, O = 0;
+    return h264b_engine_step(ctx, 3u, flags, nullptr, 0, &R, &O, p_state, val_mps, &bin_val, nullptr);
+}

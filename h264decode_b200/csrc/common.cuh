@@ -1,0 +1,73 @@
+// common.cuh -- shared declarations of libh264b200 (CUDA, sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/h264b200.h"
+
+struct h264b_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t own_stream;
+    cudaStream_t stream;  // the one "_dev" work goes to (own_stream unless h264b_set_stream was called)
+    char err[512];
+    uint64_t launches;
+
+    // grow-only device scratch
+    void *scan_scratch;
+    size_t scan_scratch_bytes;
+
+    // constant device tables, built once in h264b_create: [0] = REF, [1] = SPEC
+    uint64_t *d_cabac_tab[2];   // 128 entries, see cabac_engine.cu
+    uint8_t *d_range_lps[2];    // 256 bytes
+    uint8_t *d_trans[2];        // 64 LPS + 64 MPS
+    int16_t *d_mn[2];           // [5][1024] (m | n << 8) by idc class, see ctx_init.cu
+    uint8_t *d_state_lut[2];    // [5][52][1024] state bytes
+
+    // host-level (pinned) staging, grow-only
+    void *h_pin[8];
+    size_t h_pin_bytes[8];
+    void *d_buf[16];
+    size_t d_buf_bytes[16];
+};
+
+namespace h264b {
+
+int set_error(h264b_ctx *ctx, int code, const char *fmt, ...);
+int ensure_dev(h264b_ctx *ctx, int slot, size_t bytes, void **out);   // grow-only device buffer per slot
+int ensure_pin(h264b_ctx *ctx, int slot, size_t bytes, void **out);   // grow-only pinned buffer per slot
+
+#define H264B_CUDA(ctx, call)                                                                        \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return h264b::set_error((ctx), H264B_E_CUDA, "%s failed: %s (%s:%d)", #call,             \
+                                    cudaGetErrorString(e_), __FILE__, __LINE__);                     \
+    } while (0)
+
+#define H264B_LAUNCH_CHECK(ctx, name)                                                                \
+    do {                                                                                             \
+        cudaError_t e_ = cudaGetLastError();                                                         \
+        if (e_ != cudaSuccess)                                                                       \
+            return h264b::set_error((ctx), H264B_E_CUDA, "launch of %s failed: %s", name,            \
+                                    cudaGetErrorString(e_));                                         \
+        (ctx)->launches++;                                                                           \
+    } while (0)
+
+// kernels' host-side launchers (each file owns its kernels)
+int build_tables(h264b_ctx *ctx);  // tables.cu
+int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint8_t *d_rbsp, h264b_nal *d_nals,
+                       h264b_nal_ext *d_ext, uint32_t nal_cap, h264b_scan_summary *d_summary, uint32_t flags);
+int launch_nal_frames(h264b_ctx *ctx, const uint8_t *d_frames, uint64_t total, const uint64_t *d_off,
+                      const uint32_t *d_len, uint32_t n_frames, h264b_nal *d_nals, h264b_nal_ext *d_ext,
+                      uint8_t *d_rbsp);
+int launch_ctx_init(h264b_ctx *ctx, const h264b_slice_qp *d_params, uint32_t n_slices, uint32_t n_ctx,
+                    uint8_t *d_states, uint32_t flags);
+int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job);
+int launch_slice_select(h264b_ctx *ctx, const h264b_nal *d_nals, const h264b_scan_summary *d_summary,
+                        uint32_t nal_cap, uint32_t slice_data_offset, uint32_t max_slices, uint64_t *d_off,
+                        uint32_t *d_len, uint32_t *d_slice_nal, uint32_t *d_n_slices);
+
+}  // namespace h264b

@@ -1,0 +1,249 @@
+/* h264b200.h -- C ABI of libh264b200.so: the B200-native (sm_100a) data-parallel front end of an H.264
+ * decoder, a drop-in for the corresponding hot path of mrmod/h264decode (pure Go, package h264).
+ *
+ * The reference has no FFI layer; its boundary for this path is the exported Go API of package h264.  Each
+ * entry point below names the reference function(s) it replaces (paths relative to the reference root).  A Go
+ * shim binds these symbols through cgo (INTEGRATION.md shows the stub); tests bind them through ctypes.
+ *
+ * Conventions
+ *   - every function returns an int32 status (H264B_OK == 0); h264b_last_error() gives text for the last failure
+ *   - plain pointers and sizes only; no C++ or torch types
+ *   - "_dev" entry points take DEVICE pointers, enqueue work on the context's CUDA stream and return without
+ *     synchronising (except where stated); all other entry points take HOST pointers and are synchronous
+ *   - there is no CPU fallback: without a CUDA device h264b_create fails with H264B_E_NO_DEVICE
+ *   - one h264b_ctx drives one GPU; contexts are independent (one per process-rank or several per process);
+ *     a context must not be used from two threads at once
+ *   - behaviour flags select the reference-exact (REF, default, bit 0) or ITU-T-corrected (SPEC) variant of each
+ *     documented deviation of the reference
+ */
+#ifndef H264B200_H
+#define H264B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; these are its exports */
+#endif
+
+#define H264B_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define H264B_OK 0
+#define H264B_E_INVALID 1   /* bad argument */
+#define H264B_E_CUDA 2      /* a CUDA call failed; see h264b_last_error */
+#define H264B_E_NOMEM 3
+#define H264B_E_CAPACITY 4  /* an output buffer was too small; the summary says how much is needed */
+#define H264B_E_NO_DEVICE 5 /* no usable CUDA device: this library has no CPU path */
+
+/* behaviour flags */
+#define H264B_TABLES_SPEC 0x1u           /* corrected rangeTabLPS / transIdx / (m,n) tables (A1..A3); default REF */
+#define H264B_BYPASS_SPEC_OR 0x2u        /* DecodeBypass as (O<<1)|bit (A5); default REF: O<<=1 then O<<=bit */
+#define H264B_CABAC_FINAL_TERMINATE 0x4u /* after a slice's n_ops bins decode one more DecodeTerminate bin */
+
+/* per-unit flag bits written by kernels (never abort a batch; SURVEY.md §5 failure handling) */
+#define H264B_F_OVERRUN 0x1u    /* the reference would have panicked reading past the slice's last byte (A10) */
+#define H264B_F_HAS_EPB 0x2u    /* NAL: at least one emulation-prevention byte was removed */
+#define H264B_F_SHORT_NAL 0x4u  /* NAL shorter than 8 bytes: the reference's log line server.go:108 may panic (A13) */
+
+typedef struct h264b_ctx h264b_ctx;
+
+/* ------------------------------------------------------------------ context / memory / stream plumbing */
+int32_t h264b_version(void);
+int32_t h264b_device_count(int32_t *count);
+int32_t h264b_create(int32_t device, h264b_ctx **out);
+void h264b_destroy(h264b_ctx *ctx);
+const char *h264b_last_error(const h264b_ctx *ctx);
+/* Run all "_dev" work on the caller's cudaStream_t (e.g. torch's current stream); NULL = the context's own. */
+int32_t h264b_set_stream(h264b_ctx *ctx, void *cuda_stream);
+int32_t h264b_sync(h264b_ctx *ctx);
+/* Pinned host memory: ingest code reads sockets/files straight into it (replaces the growing []byte of
+ * H264Reader.BufferToReader, h264/bit_reader.go:27-39). */
+int32_t h264b_host_alloc(h264b_ctx *ctx, size_t bytes, void **out);
+int32_t h264b_host_free(h264b_ctx *ctx, void *p);
+int32_t h264b_dev_alloc(h264b_ctx *ctx, size_t bytes, void **out);
+int32_t h264b_dev_free(h264b_ctx *ctx, void *p);
+int32_t h264b_memcpy_h2d(h264b_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async on the stream */
+int32_t h264b_memcpy_d2h(h264b_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* async on the stream */
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int32_t h264b_launch_count(const h264b_ctx *ctx, uint64_t *count);
+
+/* ------------------------------------------------------------------ Annex-B split + RBSP strip (K1/K2)
+ * Replaces, for a whole byte stream at once:
+ *   isStartSequence               h264/server.go:28-39      (00 00 00 01 only, A8)
+ *   readNalUnit                   h264/server.go:64-111     (NAL k = bytes after start code k up to AND INCLUDING
+ *                                                            start code k+1; the NAL after the last start code and the
+ *                                                            bytes before the first one are not emitted)
+ *   NewNalUnit                    h264/nalUnit.go:75-131    (header parse, extension headers :39-71, and the
+ *                                                            emulation-prevention strip loop :106-126 incl. A7)
+ *   NalUnit / (*NalUnit).RBSP()   h264/nalUnit.go:3-30,72
+ */
+typedef struct {
+    uint64_t start;       /* stream offset of the NAL's first byte (startOffset, server.go:88) */
+    uint64_t rbsp_off;    /* offset of its RBSP in the rbsp output buffer */
+    uint32_t num_bytes;   /* NalUnit.NumBytes (includes the following start code) */
+    uint32_t rbsp_len;    /* len(NalUnit.rbsp) */
+    uint8_t forbidden_zero_bit, ref_idc, type, header_bytes; /* nalUnit.go:82-84, :79,94,97,100 */
+    uint32_t flags;       /* H264B_F_HAS_EPB | H264B_F_SHORT_NAL */
+} h264b_nal; /* 32 bytes */
+
+/* extension-header fields of NAL types 14/20/21 (nalUnit.go:39-71); all zero for other types */
+typedef struct {
+    uint8_t svc_extension_flag, avc_3d_extension_flag, idr_flag, priority_id;
+    uint8_t no_inter_layer_pred_flag, dependency_id, quality_id, temporal_id;
+    uint8_t use_ref_base_pic_flag, discardable_flag, output_flag, reserved_three_2bits;
+    uint8_t non_idr_flag, anchor_pic_flag, inter_view_flag, reserved_one_bit;
+    uint16_t view_id;
+    uint8_t view_idx, depth_flag;
+    uint32_t pad;
+} h264b_nal_ext; /* 24 bytes */
+
+typedef struct {
+    uint64_t n_start_codes; /* occurrences of 00 00 00 01 */
+    uint64_t n_nals;        /* = max(n_start_codes, 1) - 1 : NAL units the reference would emit */
+    uint64_t rbsp_bytes;    /* RBSP bytes of those NAL units */
+    uint64_t first_start;   /* offset just after the first start code (== n when there is none) */
+    uint64_t n_epb;         /* emulation-prevention bytes removed inside emitted NAL units */
+    uint32_t status;        /* H264B_OK or H264B_E_CAPACITY (nal_cap too small; n_nals says what is needed) */
+    uint32_t reserved;
+} h264b_scan_summary; /* 48 bytes */
+
+/* Bytes of device scratch h264b_annexb_scan_dev needs for an n-byte stream (the context owns and grows it). */
+uint64_t h264b_annexb_scratch_bytes(uint64_t n);
+
+/* Device-resident scan.  d_stream: n bytes, 16-byte aligned.  d_rbsp: 16-byte aligned, capacity >= n + 16.
+ * d_nals: nal_cap records.  d_ext: nal_cap records or NULL.  d_summary: one record.  Asynchronous. */
+int32_t h264b_annexb_scan_dev(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint8_t *d_rbsp,
+                              h264b_nal *d_nals, h264b_nal_ext *d_ext, uint32_t nal_cap,
+                              h264b_scan_summary *d_summary, uint32_t flags);
+
+/* Host-buffer scan (the call a Go caller makes): copies the stream in, runs the kernels, copies the NAL index
+ * and the RBSP bytes back into context-owned pinned buffers that stay valid until the next call on ctx.
+ * want_rbsp == 0 leaves the RBSP on the device (d_rbsp_out, if not NULL, receives its device address for a
+ * following h264b_cabac_decode_dev). */
+int32_t h264b_annexb_scan(h264b_ctx *ctx, const uint8_t *stream, uint64_t n, uint32_t flags, int32_t want_rbsp,
+                          const h264b_nal **nals, const h264b_nal_ext **ext, h264b_scan_summary *summary,
+                          const uint8_t **rbsp, const uint8_t **d_rbsp_out);
+
+/* NewNalUnit(frame, numBytesInNal) for a batch of independent frames (direct-call semantics, including the
+ * 00 00 03-at-the-end edge of nalUnit.go:113-117): frames are concatenated in `frames`, frame i occupying
+ * [frame_off[i], frame_off[i] + frame_len[i]).  RBSP of frame i is written at rbsp + frame_off[i].
+ * Host buffers; synchronous.  nals[i].start = frame_off[i]. */
+int32_t h264b_nal_units(h264b_ctx *ctx, const uint8_t *frames, uint64_t total_bytes, const uint64_t *frame_off,
+                        const uint32_t *frame_len, uint32_t n_frames, uint32_t flags, h264b_nal *nals,
+                        h264b_nal_ext *ext, uint8_t *rbsp);
+
+/* ------------------------------------------------------------------ context-variable initialisation (K4)
+ * Replaces PreCtxState (h264/cabac.go:118-121), Clip3 (:131-139), the state split of initCabac (:158-164) and
+ * the MNVars / CodedblockPatternMN lookups (h264/mn_vars.go:15-175,184-440), for every (slice, ctxIdx) at once.
+ * State byte = pStateIdx | valMPS << 6.  cabac_init_idc -1 (= NoCabacInitIdc, mn_vars.go:7) selects the
+ * single-column entries of ctxIdx 0..10 and the I/SI column of ctxIdx 70..104. */
+typedef struct {
+    int32_t slice_qp_y;     /* SliceQPy (cabac.go:113-115); clipped to 0..51 inside PreCtxState */
+    int32_t cabac_init_idc; /* -1, 0, 1, 2; anything else: Go missing-key semantics (MN{0,0}, I column for 70..104) */
+} h264b_slice_qp;
+
+int32_t h264b_ctx_init_dev(h264b_ctx *ctx, const h264b_slice_qp *d_params, uint32_t n_slices, uint32_t n_ctx,
+                           uint8_t *d_states /* [n_slices][n_ctx] */, uint32_t flags);
+int32_t h264b_ctx_init(h264b_ctx *ctx, const h264b_slice_qp *params, uint32_t n_slices, uint32_t n_ctx,
+                       uint8_t *states, uint32_t flags);
+/* scalar drop-ins (each runs a one-thread kernel: there is no CPU implementation in this library) */
+int32_t h264b_pre_ctx_state(h264b_ctx *ctx, int32_t m, int32_t n, int32_t slice_qp_y, int32_t *pre_ctx_state);
+int32_t h264b_mn(h264b_ctx *ctx, int32_t ctx_idx, int32_t cabac_init_idc, uint32_t flags, int32_t *m, int32_t *n);
+
+/* ------------------------------------------------------------------ CABAC arithmetic decoding engine (K3)
+ * Replaces initDecodingEngine (h264/cabac.go:439-446), the arithmetic core of BinaryDecision (:525-536) composed
+ * with StateTransitionProcess (:544-553) and RenormD (:503-511) as "DecodeDecision", DecodeBypass (:468-481),
+ * DecodeTerminate (:486-499), with rangeTabLPS (h264/rangeTabLPS.go) and stateTransxTab (h264/stateTransxTab.go).
+ * One slice per warp lane; all slices follow one shared op schedule, slice s using its first n_ops[s] entries. */
+#define H264B_OP_DECISION 0u
+#define H264B_OP_BYPASS 1u
+#define H264B_OP_TERMINATE 2u
+#define H264B_OP(kind, ctx_idx) ((uint16_t)(((kind) << 14) | ((ctx_idx)&0x3FFu)))
+
+typedef struct {
+    int64_t cod_i_range;
+    int64_t cod_i_offset;
+    uint64_t bits_read; /* BitReader.bitsRead relative to the slice's first byte: 9 + renorm shifts + bypass bins */
+    uint32_t flags;     /* H264B_F_OVERRUN: everything else in this record and the slice's bins are unspecified */
+    uint32_t n_bins;    /* bins produced (n_ops[s], +1 with H264B_CABAC_FINAL_TERMINATE) */
+} h264b_cabac_final;    /* 32 bytes */
+
+typedef struct {
+    const uint8_t *bytes;          /* slice data; slice s = bytes[off[s] .. off[s]+len[s]) */
+    uint64_t total_bytes;          /* readable bytes at `bytes` (loads are clamped to it) */
+    const uint64_t *off;           /* [n_slices] */
+    const uint32_t *len;           /* [n_slices] */
+    uint32_t n_slices;
+    uint32_t n_ctx;                /* context variables per slice, 1..1024 */
+    const uint16_t *ops;           /* [n_ops_max] shared schedule, H264B_OP(kind, ctxIdx) */
+    uint32_t n_ops_max;
+    const uint32_t *n_ops;         /* [n_slices] or NULL (= n_ops_max for every slice) */
+    const h264b_slice_qp *qp;      /* [n_slices]: initial states by the K4 rule; used when init_states == NULL */
+    const uint8_t *init_states;    /* [n_slices][n_ctx] or NULL */
+    uint32_t *bins;                /* [n_slices][bins_stride_words]: bin i of slice s = bit (i & 31) of word i >> 5 */
+    uint32_t bins_stride_words;    /* >= (n_ops_max + 1 + 31) / 32 */
+    h264b_cabac_final *final;      /* [n_slices] */
+    uint8_t *final_states;         /* [n_slices][n_ctx] or NULL */
+    uint32_t flags;
+    uint32_t reserved;
+} h264b_cabac_job;
+
+/* all pointers in job are DEVICE pointers; asynchronous */
+int32_t h264b_cabac_decode_dev(h264b_ctx *ctx, const h264b_cabac_job *job);
+/* all pointers in job are HOST pointers; synchronous */
+int32_t h264b_cabac_decode(h264b_ctx *ctx, const h264b_cabac_job *job);
+
+/* Single engine steps with explicit state, for per-call drop-in use of the Go functions (each runs a one-thread
+ * kernel).  bits/n_bits: the bits the step may consume, MSB-first in `bits`; *bits_used reports how many it took.
+ * kind: H264B_OP_*; for a decision *p_state_idx / *val_mps are the context and are updated. */
+int32_t h264b_engine_step(h264b_ctx *ctx, uint32_t kind, uint32_t flags, const uint8_t *bits, uint32_t n_bits,
+                          int64_t *cod_i_range, int64_t *cod_i_offset, int32_t *p_state_idx, int32_t *val_mps,
+                          int32_t *bin_val, uint32_t *bits_used);
+/* the un-composed reference primitives (cabac.go:525-536 and :544-553 on their own, A6) */
+int32_t h264b_binary_decision(h264b_ctx *ctx, uint32_t flags, int32_t p_state_idx, int32_t val_mps,
+                              int64_t *cod_i_range, int64_t *cod_i_offset, int32_t *bin_val);
+int32_t h264b_state_transition(h264b_ctx *ctx, uint32_t flags, int32_t *p_state_idx, int32_t *val_mps,
+                               int32_t bin_val);
+
+/* ------------------------------------------------------------------ whole front end of one stream
+ * split + strip + (slice NALs of type 1 / 5) context init + CABAC bins, the slice data staying on the device
+ * between the stages.  The CABAC data of a slice NAL starts at RBSP byte `slice_data_offset` (the reference's
+ * slice-header parser, h264/slice.go:835-1048, is not on this path: SURVEY.md §8 f1).  Slice j (j-th NAL of type
+ * 1 or 5 in stream order) uses qp[j] and n_ops[j].  Host pointers; synchronous; outputs in context-owned pinned
+ * memory valid until the next call on ctx. */
+typedef struct {
+    const uint8_t *stream;
+    uint64_t n;
+    uint32_t slice_data_offset;
+    uint32_t n_ctx;
+    const uint16_t *ops;
+    uint32_t n_ops_max;
+    const uint32_t *n_ops;        /* [max_slices] or NULL */
+    const h264b_slice_qp *qp;     /* [max_slices] */
+    uint32_t max_slices;
+    uint32_t flags;
+} h264b_stream_job;
+
+typedef struct {
+    h264b_scan_summary scan;
+    const h264b_nal *nals;          /* [scan.n_nals] */
+    uint32_t n_slices;
+    uint32_t bins_stride_words;
+    const uint32_t *slice_nal;      /* [n_slices] index into nals */
+    const uint32_t *bins;           /* [n_slices][bins_stride_words] */
+    const h264b_cabac_final *final; /* [n_slices] */
+    uint64_t total_bins;
+} h264b_stream_result;
+
+int32_t h264b_stream_decode(h264b_ctx *ctx, const h264b_stream_job *job, h264b_stream_result *result);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,169 @@
+// hd_emul.cpp -- CPU harness around the product's __host__ __device__ headers (annexb_local.cuh, cabac_lane.cuh).
+// Built by tests/test_hd_logic.py with g++.  It drives the very same per-byte predicates / per-lane arithmetic the
+// CUDA kernels use, in the same order of decisions (fast path vs exact path), so that their logic can be checked
+// against the oracle without a GPU.  Test infrastructure: not part of the product.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../h264decode_b200/csrc/annexb_local.cuh"
+#include "../../h264decode_b200/csrc/cabac_lane.cuh"
+#include "../../h264decode_b200/csrc/tables.inc"
+
+using namespace h264b;
+
+extern "C" {
+
+// Whole-stream split + strip with the position-local rules, granule by granule like annexb_scan_kernel:
+// granules with a start-code end in [g-6, g+16] use keep_byte_stream, the others use ~raw-EPB mask.
+// Outputs: nal_start / nal_rbsp_off / nal_hdr per start code (K entries), rbsp bytes; returns K.
+// *fast_slow_mismatch counts granules where the fast mask differs from the exact predicate although no start code
+// is near (must be 0).
+int64_t emul_stream(const uint8_t *s, int64_t n, uint64_t *nal_start, uint64_t *nal_rbsp_off, uint32_t *nal_hdr,
+                    int64_t cap, uint8_t *rbsp, int64_t *rbsp_total, int64_t *first_start, int64_t *fast_slow_mismatch) {
+    auto get = [&](int64_t p) -> uint32_t { return (p >= 0 && p < n) ? s[p] : 0xFFu; };
+    const int64_t n_gran = (n + 15) / 16;
+    std::vector<uint16_t> sc(n_gran + 2, 0), em(n_gran + 2, 0);
+    int64_t e0 = n;
+    for (int64_t g = 0; g < n_gran; g++) {
+        uint32_t w[4];
+        for (int i = 0; i < 4; i++)
+            w[i] = get(g * 16 + i * 4) | (get(g * 16 + i * 4 + 1) << 8) | (get(g * 16 + i * 4 + 2) << 16) |
+                   (get(g * 16 + i * 4 + 3) << 24);
+        uint32_t prev = get(g * 16 - 4) | (get(g * 16 - 3) << 8) | (get(g * 16 - 2) << 16) | (get(g * 16 - 1) << 24);
+        GranuleMasks m = granule_masks(w, prev);
+        sc[g + 1] = (uint16_t)m.sc;
+        em[g + 1] = (uint16_t)m.e;
+        if (m.sc && e0 == n) {
+            int64_t q = g * 16 + __builtin_ctz(m.sc);
+            if (q < n) e0 = q + 1;
+        }
+    }
+    *first_start = e0;
+    int64_t K = 0, kept = 0, mism = 0;
+    for (int64_t g = 0; g < n_gran; g++) {
+        const int64_t gpos = g * 16;
+        uint32_t k16 = ~(uint32_t)em[g + 1] & 0xFFFFu;
+        const uint32_t near = ((uint32_t)sc[g] >> 10) | sc[g + 1] | (sc[g + 2] & 1u);
+        uint32_t exact = 0;
+        for (int j = 0; j < 16; j++)
+            if (keep_byte_stream(get, gpos + j)) exact |= 1u << j;
+        if (near)
+            k16 = exact;
+        else if (k16 != exact)
+            mism++;
+        if (gpos + 16 <= e0)
+            k16 = 0;
+        else if (gpos < e0)
+            k16 &= ~((1u << (uint32_t)(e0 - gpos)) - 1u);
+        uint32_t scm = sc[g + 1];
+        if (gpos + 16 > n) {
+            uint32_t valid = (1u << (uint32_t)(n - gpos)) - 1u;
+            k16 &= valid;
+            scm &= valid;
+        }
+        for (int j = 0; j < 16; j++) {
+            if (scm & (1u << j)) {
+                if (K < cap) {
+                    const int64_t a = gpos + j + 1;
+                    nal_start[K] = (uint64_t)a;
+                    nal_rbsp_off[K] = (uint64_t)kept;
+                    nal_hdr[K] = get(a) | (get(a + 1) << 8) | (get(a + 2) << 16) | (get(a + 3) << 24);
+                }
+                K++;
+            }
+            if (k16 & (1u << j)) rbsp[kept++] = s[gpos + j];
+        }
+    }
+    *rbsp_total = kept;
+    *fast_slow_mismatch = mism;
+    return K;
+}
+
+uint32_t emul_header_bytes(uint32_t b0, uint32_t b1) { return nal_header_bytes(b0, b1); }
+
+// NewNalUnit on one frame with keep_byte_frame; returns rbsp length
+int64_t emul_frame(const uint8_t *f, int64_t N, uint8_t *rbsp) {
+    auto get = [&](int64_t p) -> uint32_t { return (p >= 0 && p < N) ? f[p] : 0xFFu; };
+    const uint32_t H = nal_header_bytes(get(0), get(1));
+    int64_t k = 0;
+    for (int64_t p = 0; p < N; p++)
+        if (keep_byte_frame(get, 0, N, H, p)) rbsp[k++] = f[p];
+    return k;
+}
+
+static void build_tab(int spec, uint64_t *tab) {
+    const uint8_t *range_lps = spec ? h264b_range_tab_lps_spec : h264b_range_tab_lps_ref;
+    const uint8_t *tl = spec ? h264b_trans_idx_lps_spec : h264b_trans_idx_lps_ref;
+    const uint8_t *tm = spec ? h264b_trans_idx_mps_spec : h264b_trans_idx_mps_ref;
+    for (uint32_t s = 0; s < 128; s++) {  // same packing as cabac_table_kernel (ctx_init.cu)
+        const uint32_t p = s & 63, v = s >> 6;
+        const uint32_t lo = range_lps[p * 4] | (range_lps[p * 4 + 1] << 8) | (range_lps[p * 4 + 2] << 16) |
+                            ((uint32_t)range_lps[p * 4 + 3] << 24);
+        const uint32_t next_mps = tm[p] | (v << 6);
+        const uint32_t v_lps = (p == 0) ? 1 - v : v;
+        const uint32_t next_lps = tl[p] | (v_lps << 6);
+        const uint32_t hi = next_mps | (v << 8) | (next_lps << 16) | ((1 - v) << 24);
+        tab[s] = ((uint64_t)hi << 32) | lo;
+    }
+}
+
+struct EmulFinal {
+    int64_t R, O;
+    uint64_t bits_read;
+    uint32_t overrun, n_bins;
+};
+
+// One lane of cabac_decode_kernel: flags bit0 = SPEC tables, bit1 = SPEC_OR bypass, bit2 = final terminate,
+// bit3 = also refill at random eligible moments (what happens when another lane of the warp triggers the refill)
+void emul_cabac(const uint8_t *buf, uint64_t total, uint64_t off, uint32_t len, const uint16_t *ops, uint32_t n_ops,
+                uint8_t *states, uint32_t n_ctx, uint32_t flags, uint32_t *bins, EmulFinal *fin) {
+    uint64_t tab[128];
+    build_tab(flags & 1, tab);
+    uint32_t word = 0, n_bins = n_ops;
+    LaneDecoder eng = {};
+    eng.init(buf, total, off, (flags & 2u) != 0);
+    uint32_t lcg = 12345u + n_ops;
+    for (uint32_t i = 0; i < n_ops; i++) {
+        if (eng.must_refill()) eng.refill_if_room();
+        if (flags & 8u) {  // a neighbouring lane triggered the warp-wide refill: take bits early whenever there is room
+            lcg = lcg * 1664525u + 1013904223u;
+            if ((lcg >> 28) < 5u) eng.refill_if_room();
+        }
+        const uint32_t kind = ops[i] >> 14;
+        uint32_t bin;
+        if (kind == 0) {
+            uint32_t c = ops[i] & 0x3FFu;
+            if (c >= n_ctx) c = 0;
+            uint8_t ns;
+            bin = eng.decision(tab[states[c] & 127u], &ns);
+            states[c] = ns;
+        } else if (kind == 1) {
+            bin = eng.bypass();
+        } else {
+            bin = eng.terminate();
+        }
+        word |= bin << (i & 31u);
+        if ((i & 31u) == 31u) {
+            bins[i >> 5] = word;
+            word = 0;
+        }
+    }
+    if (flags & 4u) {
+        if (eng.must_refill()) eng.refill_if_room();
+        word |= eng.terminate() << (n_ops & 31u);
+        n_bins++;
+    }
+    if (n_bins & 31u)
+        bins[n_bins >> 5] = word;
+    else if ((flags & 4u))
+        bins[(n_bins - 1) >> 5] = word;
+    fin->R = eng.cod_i_range();
+    fin->O = eng.cod_i_offset();
+    fin->bits_read = eng.bits_read();
+    fin->overrun = fin->bits_read > 8ull * len;
+    fin->n_bins = n_bins;
+}
+
+}  // extern "C"
