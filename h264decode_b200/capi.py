@@ -1,0 +1,364 @@
+"""ctypes binding of include/h264b200.h -- one Python method per exported symbol, numpy in / numpy out.
+
+No compute happens here.  If libh264b200.so is missing the import fails (build it with
+`python -m h264decode_b200.build`); if no CUDA device is present Context() raises H264BError(NO_DEVICE).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libh264b200.so")
+
+OK, E_INVALID, E_CUDA, E_NOMEM, E_CAPACITY, E_NO_DEVICE = range(6)
+TABLES_SPEC, BYPASS_SPEC_OR, CABAC_FINAL_TERMINATE = 1, 2, 4
+F_OVERRUN, F_HAS_EPB, F_SHORT_NAL = 1, 2, 4
+OP_DECISION, OP_BYPASS, OP_TERMINATE = 0, 1, 2
+
+# every symbol include/h264b200.h declares (tests check that the library exports exactly these)
+SYMBOLS = [
+    "h264b_version", "h264b_device_count", "h264b_create", "h264b_destroy", "h264b_last_error", "h264b_set_stream",
+    "h264b_sync", "h264b_host_alloc", "h264b_host_free", "h264b_dev_alloc", "h264b_dev_free", "h264b_memcpy_h2d",
+    "h264b_memcpy_d2h", "h264b_launch_count", "h264b_annexb_scratch_bytes", "h264b_annexb_scan_dev",
+    "h264b_annexb_scan", "h264b_nal_units", "h264b_ctx_init_dev", "h264b_ctx_init", "h264b_pre_ctx_state", "h264b_mn",
+    "h264b_cabac_decode_dev", "h264b_cabac_decode", "h264b_engine_step", "h264b_binary_decision",
+    "h264b_state_transition", "h264b_stream_decode",
+]
+
+NAL_DTYPE = np.dtype([("start", "<u8"), ("rbsp_off", "<u8"), ("num_bytes", "<u4"), ("rbsp_len", "<u4"),
+                      ("forbidden_zero_bit", "u1"), ("ref_idc", "u1"), ("type", "u1"), ("header_bytes", "u1"),
+                      ("flags", "<u4")])
+NAL_EXT_DTYPE = np.dtype([(n, "u1") for n in (
+    "svc_extension_flag", "avc_3d_extension_flag", "idr_flag", "priority_id", "no_inter_layer_pred_flag",
+    "dependency_id", "quality_id", "temporal_id", "use_ref_base_pic_flag", "discardable_flag", "output_flag",
+    "reserved_three_2bits", "non_idr_flag", "anchor_pic_flag", "inter_view_flag", "reserved_one_bit")] +
+    [("view_id", "<u2"), ("view_idx", "u1"), ("depth_flag", "u1"), ("pad", "<u4")])
+FINAL_DTYPE = np.dtype([("cod_i_range", "<i8"), ("cod_i_offset", "<i8"), ("bits_read", "<u8"), ("flags", "<u4"),
+                        ("n_bins", "<u4")])
+SLICE_QP_DTYPE = np.dtype([("slice_qp_y", "<i4"), ("cabac_init_idc", "<i4")])
+assert NAL_DTYPE.itemsize == 32 and NAL_EXT_DTYPE.itemsize == 24 and FINAL_DTYPE.itemsize == 32
+
+
+class ScanSummary(C.Structure):
+    _fields_ = [("n_start_codes", C.c_uint64), ("n_nals", C.c_uint64), ("rbsp_bytes", C.c_uint64),
+                ("first_start", C.c_uint64), ("n_epb", C.c_uint64), ("status", C.c_uint32), ("reserved", C.c_uint32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class CabacJob(C.Structure):
+    _fields_ = [("bytes", C.c_void_p), ("total_bytes", C.c_uint64), ("off", C.c_void_p), ("len", C.c_void_p),
+                ("n_slices", C.c_uint32), ("n_ctx", C.c_uint32), ("ops", C.c_void_p), ("n_ops_max", C.c_uint32),
+                ("n_ops", C.c_void_p), ("qp", C.c_void_p), ("init_states", C.c_void_p), ("bins", C.c_void_p),
+                ("bins_stride_words", C.c_uint32), ("final", C.c_void_p), ("final_states", C.c_void_p),
+                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class StreamJob(C.Structure):
+    _fields_ = [("stream", C.c_void_p), ("n", C.c_uint64), ("slice_data_offset", C.c_uint32), ("n_ctx", C.c_uint32),
+                ("ops", C.c_void_p), ("n_ops_max", C.c_uint32), ("n_ops", C.c_void_p), ("qp", C.c_void_p),
+                ("max_slices", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class StreamResult(C.Structure):
+    _fields_ = [("scan", ScanSummary), ("nals", C.c_void_p), ("n_slices", C.c_uint32),
+                ("bins_stride_words", C.c_uint32), ("slice_nal", C.c_void_p), ("bins", C.c_void_p),
+                ("final", C.c_void_p), ("total_bins", C.c_uint64)]
+
+
+class H264BError(RuntimeError):
+    def __init__(self, code, msg=""):
+        super().__init__("h264b status %d: %s" % (code, msg))
+        self.code = code
+
+
+def load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libh264b200.so is not built (%s); run `python -m h264decode_b200.build` -- there is no "
+                          "fallback implementation" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32
+    P = C.POINTER
+    sig = {
+        "h264b_version": (i32, []),
+        "h264b_device_count": (i32, [P(i32)]),
+        "h264b_create": (i32, [i32, P(vp)]),
+        "h264b_destroy": (None, [vp]),
+        "h264b_last_error": (C.c_char_p, [vp]),
+        "h264b_set_stream": (i32, [vp, vp]),
+        "h264b_sync": (i32, [vp]),
+        "h264b_host_alloc": (i32, [vp, C.c_size_t, P(vp)]),
+        "h264b_host_free": (i32, [vp, vp]),
+        "h264b_dev_alloc": (i32, [vp, C.c_size_t, P(vp)]),
+        "h264b_dev_free": (i32, [vp, vp]),
+        "h264b_memcpy_h2d": (i32, [vp, vp, vp, C.c_size_t]),
+        "h264b_memcpy_d2h": (i32, [vp, vp, vp, C.c_size_t]),
+        "h264b_launch_count": (i32, [vp, P(u64)]),
+        "h264b_annexb_scratch_bytes": (u64, [u64]),
+        "h264b_annexb_scan_dev": (i32, [vp, vp, u64, vp, vp, vp, u32, vp, u32]),
+        "h264b_annexb_scan": (i32, [vp, vp, u64, u32, i32, P(vp), P(vp), P(ScanSummary), P(vp), P(vp)]),
+        "h264b_nal_units": (i32, [vp, vp, u64, vp, vp, u32, u32, vp, vp, vp]),
+        "h264b_ctx_init_dev": (i32, [vp, vp, u32, u32, vp, u32]),
+        "h264b_ctx_init": (i32, [vp, vp, u32, u32, vp, u32]),
+        "h264b_pre_ctx_state": (i32, [vp, i32, i32, i32, P(i32)]),
+        "h264b_mn": (i32, [vp, i32, i32, u32, P(i32), P(i32)]),
+        "h264b_cabac_decode_dev": (i32, [vp, P(CabacJob)]),
+        "h264b_cabac_decode": (i32, [vp, P(CabacJob)]),
+        "h264b_engine_step": (i32, [vp, u32, u32, vp, u32, P(C.c_int64), P(C.c_int64), P(i32), P(i32), P(i32), P(u32)]),
+        "h264b_binary_decision": (i32, [vp, u32, i32, i32, P(C.c_int64), P(C.c_int64), P(i32)]),
+        "h264b_state_transition": (i32, [vp, u32, P(i32), P(i32), i32]),
+        "h264b_stream_decode": (i32, [vp, P(StreamJob), P(StreamResult)]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    return L
+
+
+_lib = load()
+
+
+def lib():
+    return _lib
+
+
+def make_op(kind, ctx=0):
+    return (kind << 14) | (ctx & 0x3FF)
+
+
+def _from_ptr(ptr, dtype, count):
+    """copy `count` records of `dtype` from a host pointer the library owns"""
+    if not count:
+        return np.zeros(0, dtype=dtype)
+    nbytes = int(count) * np.dtype(dtype).itemsize
+    buf = (C.c_uint8 * nbytes).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=int(count)).copy()
+
+
+class Context:
+    """One h264b_ctx: one GPU, one stream.  Methods mirror the C entry points one to one."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        rc = _lib.h264b_create(device, C.byref(h))
+        if rc != OK:
+            raise H264BError(rc, "h264b_create(device=%d) failed%s" % (
+                device, " -- no CUDA device; this library has no CPU path" if rc == E_NO_DEVICE else ""))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            _lib.h264b_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise H264BError(rc, (_lib.h264b_last_error(self.h) or b"").decode(errors="replace"))
+
+    # ---- plumbing
+    def set_stream(self, cuda_stream):
+        self._check(_lib.h264b_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def sync(self):
+        self._check(_lib.h264b_sync(self.h))
+
+    def launch_count(self):
+        n = C.c_uint64()
+        self._check(_lib.h264b_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def host_alloc(self, nbytes):
+        """pinned host memory as a uint8 numpy view (free with host_free(arr))"""
+        p = C.c_void_p()
+        self._check(_lib.h264b_host_alloc(self.h, nbytes, C.byref(p)))
+        arr = np.frombuffer((C.c_uint8 * max(nbytes, 1)).from_address(p.value), dtype=np.uint8, count=nbytes)
+        arr.flags.writeable = True
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[arr.ctypes.data] = p.value
+        return arr
+
+    def host_free(self, arr):
+        p = self._pinned.pop(arr.ctypes.data)
+        self._check(_lib.h264b_host_free(self.h, C.c_void_p(p)))
+
+    def dev_alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(_lib.h264b_dev_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def dev_free(self, p):
+        self._check(_lib.h264b_dev_free(self.h, C.c_void_p(p)))
+
+    def h2d(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self._check(_lib.h264b_memcpy_h2d(self.h, C.c_void_p(dptr), C.c_void_p(arr.ctypes.data), arr.nbytes))
+        return arr  # keep alive until sync
+
+    def d2h(self, arr, dptr):
+        self._check(_lib.h264b_memcpy_d2h(self.h, C.c_void_p(arr.ctypes.data), C.c_void_p(dptr), arr.nbytes))
+
+    # ---- Annex-B
+    def annexb_scan(self, stream, flags=0, want_rbsp=True, want_ext=True):
+        """-> (summary dict, nals[NAL_DTYPE], ext[NAL_EXT_DTYPE] | None, rbsp uint8[] | None)"""
+        s = np.ascontiguousarray(stream, dtype=np.uint8)
+        nals, ext, rbsp, drbsp = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        summ = ScanSummary()
+        self._check(_lib.h264b_annexb_scan(self.h, C.c_void_p(s.ctypes.data), len(s), flags, 1 if want_rbsp else 0,
+                                           C.byref(nals), C.byref(ext) if want_ext else None, C.byref(summ),
+                                           C.byref(rbsp), C.byref(drbsp)))
+        n = summ.n_nals
+        out_n = _from_ptr(nals.value, NAL_DTYPE, n)
+        out_e = _from_ptr(ext.value, NAL_EXT_DTYPE, n) if want_ext else None
+        out_r = _from_ptr(rbsp.value, np.uint8, summ.rbsp_bytes) if want_rbsp else None
+        d = summ.as_dict()
+        d["d_rbsp"] = drbsp.value
+        return d, out_n, out_e, out_r
+
+    def annexb_scan_dev(self, d_stream, n, d_rbsp, d_nals, d_ext, nal_cap, d_summary, flags=0):
+        self._check(_lib.h264b_annexb_scan_dev(self.h, C.c_void_p(d_stream), n, C.c_void_p(d_rbsp), C.c_void_p(d_nals),
+                                               C.c_void_p(d_ext) if d_ext else None, nal_cap, C.c_void_p(d_summary),
+                                               flags))
+
+    def nal_units(self, frames, flags=0):
+        """NewNalUnit for a list of byte strings -> (nals, ext, [rbsp bytes per frame])"""
+        lens = np.array([len(f) for f in frames], dtype=np.uint32)
+        offs = np.zeros(len(frames), dtype=np.uint64)
+        if len(frames):
+            offs[1:] = np.cumsum(lens[:-1].astype(np.uint64))
+        cat = np.frombuffer(b"".join(bytes(f) for f in frames), dtype=np.uint8).copy() if len(frames) else \
+            np.zeros(0, np.uint8)
+        nals = np.zeros(len(frames), dtype=NAL_DTYPE)
+        ext = np.zeros(len(frames), dtype=NAL_EXT_DTYPE)
+        rbsp = np.zeros(len(cat) + 16, dtype=np.uint8)
+        self._check(_lib.h264b_nal_units(self.h, C.c_void_p(cat.ctypes.data), len(cat), C.c_void_p(offs.ctypes.data),
+                                         C.c_void_p(lens.ctypes.data), len(frames), flags,
+                                         C.c_void_p(nals.ctypes.data), C.c_void_p(ext.ctypes.data),
+                                         C.c_void_p(rbsp.ctypes.data)))
+        outs = [bytes(rbsp[int(o):int(o) + int(nl["rbsp_len"])]) for o, nl in zip(offs, nals)]
+        return nals, ext, outs
+
+    # ---- context init
+    @staticmethod
+    def slice_qp(qp, idc):
+        p = np.zeros(len(qp), dtype=SLICE_QP_DTYPE)
+        p["slice_qp_y"] = qp
+        p["cabac_init_idc"] = idc
+        return p
+
+    def ctx_init(self, qp, idc, n_ctx, flags=0):
+        p = self.slice_qp(qp, idc)
+        out = np.zeros((len(p), n_ctx), dtype=np.uint8)
+        self._check(_lib.h264b_ctx_init(self.h, C.c_void_p(p.ctypes.data), len(p), n_ctx,
+                                        C.c_void_p(out.ctypes.data), flags))
+        return out
+
+    def ctx_init_dev(self, d_params, n_slices, n_ctx, d_states, flags=0):
+        self._check(_lib.h264b_ctx_init_dev(self.h, C.c_void_p(d_params), n_slices, n_ctx, C.c_void_p(d_states), flags))
+
+    def pre_ctx_state(self, m, n, qp):
+        out = C.c_int32()
+        self._check(_lib.h264b_pre_ctx_state(self.h, m, n, qp, C.byref(out)))
+        return out.value
+
+    def mn(self, ctx_idx, idc, flags=0):
+        m, n = C.c_int32(), C.c_int32()
+        self._check(_lib.h264b_mn(self.h, ctx_idx, idc, flags, C.byref(m), C.byref(n)))
+        return m.value, n.value
+
+    # ---- CABAC
+    def cabac_decode(self, data, off, length, ops, n_ops, n_ctx, qp=None, idc=None, init_states=None, flags=0,
+                     want_states=True):
+        """host buffers -> (bins uint32[n, stride], final[FINAL_DTYPE], final_states | None)"""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        ops = np.ascontiguousarray(ops, dtype=np.uint16)
+        n = len(off)
+        nops = None if n_ops is None else np.ascontiguousarray(n_ops, dtype=np.uint32)
+        stride = (len(ops) + 1 + 31) // 32
+        bins = np.zeros((n, stride), dtype=np.uint32)
+        fin = np.zeros(n, dtype=FINAL_DTYPE)
+        fst = np.zeros((n, n_ctx), dtype=np.uint8) if want_states else None
+        p = self.slice_qp(qp, idc) if qp is not None else None
+        init = None if init_states is None else np.ascontiguousarray(init_states, dtype=np.uint8)
+        j = CabacJob()
+        j.bytes = data.ctypes.data
+        j.total_bytes = len(data)
+        j.off = off.ctypes.data
+        j.len = length.ctypes.data
+        j.n_slices = n
+        j.n_ctx = n_ctx
+        j.ops = ops.ctypes.data
+        j.n_ops_max = len(ops)
+        j.n_ops = nops.ctypes.data if nops is not None else None
+        j.qp = p.ctypes.data if p is not None else None
+        j.init_states = init.ctypes.data if init is not None else None
+        j.bins = bins.ctypes.data
+        j.bins_stride_words = stride
+        j.final = fin.ctypes.data
+        j.final_states = fst.ctypes.data if fst is not None else None
+        j.flags = flags
+        self._check(_lib.h264b_cabac_decode(self.h, C.byref(j)))
+        return bins, fin, fst
+
+    def cabac_decode_dev(self, **kw):
+        j = CabacJob()
+        for k, v in kw.items():
+            setattr(j, k, v)
+        self._check(_lib.h264b_cabac_decode_dev(self.h, C.byref(j)))
+
+    def engine_step(self, kind, R, O, bits=b"", n_bits=None, p_state=0, val_mps=0, bin_val=0, flags=0):
+        """-> dict(R, O, p_state, val_mps, bin, bits_used)"""
+        r, o = C.c_int64(R), C.c_int64(O)
+        p, v, b, used = C.c_int32(p_state), C.c_int32(val_mps), C.c_int32(bin_val), C.c_uint32()
+        buf = np.frombuffer(bytes(bits) + b"\x00", dtype=np.uint8).copy()
+        nb = len(bits) * 8 if n_bits is None else n_bits
+        self._check(_lib.h264b_engine_step(self.h, kind, flags, C.c_void_p(buf.ctypes.data), nb, C.byref(r),
+                                           C.byref(o), C.byref(p), C.byref(v), C.byref(b), C.byref(used)))
+        return dict(R=r.value, O=o.value, p_state=p.value, val_mps=v.value, bin=b.value, bits_used=used.value)
+
+    def binary_decision(self, p_state, val_mps, R, O, flags=0):
+        r, o, b = C.c_int64(R), C.c_int64(O), C.c_int32()
+        self._check(_lib.h264b_binary_decision(self.h, flags, p_state, val_mps, C.byref(r), C.byref(o), C.byref(b)))
+        return b.value, r.value, o.value
+
+    def state_transition(self, p_state, val_mps, bin_val, flags=0):
+        p, v = C.c_int32(p_state), C.c_int32(val_mps)
+        self._check(_lib.h264b_state_transition(self.h, flags, C.byref(p), C.byref(v), bin_val))
+        return p.value, v.value
+
+    # ---- whole front end
+    def stream_decode(self, stream, ops, n_ops, qp, idc, n_ctx, slice_data_offset=0, flags=0):
+        """-> dict(scan, nals, slice_nal, bins, final, total_bins)"""
+        s = np.ascontiguousarray(stream, dtype=np.uint8)
+        ops = np.ascontiguousarray(ops, dtype=np.uint16)
+        p = self.slice_qp(qp, idc)
+        nops = None if n_ops is None else np.ascontiguousarray(n_ops, dtype=np.uint32)
+        j = StreamJob()
+        j.stream = s.ctypes.data
+        j.n = len(s)
+        j.slice_data_offset = slice_data_offset
+        j.n_ctx = n_ctx
+        j.ops = ops.ctypes.data
+        j.n_ops_max = len(ops)
+        j.n_ops = nops.ctypes.data if nops is not None else None
+        j.qp = p.ctypes.data
+        j.max_slices = len(p)
+        j.flags = flags
+        r = StreamResult()
+        self._check(_lib.h264b_stream_decode(self.h, C.byref(j), C.byref(r)))
+        ns, st = r.n_slices, r.bins_stride_words
+        return dict(scan=r.scan.as_dict(), nals=_from_ptr(r.nals, NAL_DTYPE, r.scan.n_nals),
+                    slice_nal=_from_ptr(r.slice_nal, np.uint32, ns),
+                    bins=_from_ptr(r.bins, np.uint32, ns * st).reshape(ns, st) if ns else np.zeros((0, st), np.uint32),
+                    final=_from_ptr(r.final, FINAL_DTYPE, ns), total_bins=r.total_bins)
