@@ -23,7 +23,7 @@ SYMBOLS = [
     "h264b_memcpy_d2h", "h264b_launch_count", "h264b_annexb_scratch_bytes", "h264b_annexb_scan_dev",
     "h264b_annexb_scan", "h264b_nal_units", "h264b_ctx_init_dev", "h264b_ctx_init", "h264b_pre_ctx_state", "h264b_mn",
     "h264b_cabac_decode_dev", "h264b_cabac_decode", "h264b_engine_step", "h264b_binary_decision",
-    "h264b_state_transition", "h264b_stream_decode",
+    "h264b_state_transition", "h264b_stream_decode", "h264b_slice_select_dev",
 ]
 
 NAL_DTYPE = np.dtype([("start", "<u8"), ("rbsp_off", "<u8"), ("num_bytes", "<u4"), ("rbsp_len", "<u4"),
@@ -52,7 +52,7 @@ class CabacJob(C.Structure):
     _fields_ = [("bytes", C.c_void_p), ("total_bytes", C.c_uint64), ("off", C.c_void_p), ("len", C.c_void_p),
                 ("n_slices", C.c_uint32), ("n_ctx", C.c_uint32), ("ops", C.c_void_p), ("n_ops_max", C.c_uint32),
                 ("n_ops", C.c_void_p), ("qp", C.c_void_p), ("init_states", C.c_void_p), ("bins", C.c_void_p),
-                ("bins_stride_words", C.c_uint32), ("final", C.c_void_p), ("final_states", C.c_void_p),
+                ("bins_off", C.c_void_p), ("bins_stride_words", C.c_uint32), ("final", C.c_void_p), ("final_states", C.c_void_p),
                 ("flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
@@ -63,9 +63,9 @@ class StreamJob(C.Structure):
 
 
 class StreamResult(C.Structure):
-    _fields_ = [("scan", ScanSummary), ("nals", C.c_void_p), ("n_slices", C.c_uint32),
-                ("bins_stride_words", C.c_uint32), ("slice_nal", C.c_void_p), ("bins", C.c_void_p),
-                ("final", C.c_void_p), ("total_bins", C.c_uint64)]
+    _fields_ = [("scan", ScanSummary), ("nals", C.c_void_p), ("n_slices", C.c_uint32), ("reserved", C.c_uint32),
+                ("slice_nal", C.c_void_p), ("bins_off", C.c_void_p), ("bins", C.c_void_p), ("final", C.c_void_p),
+                ("total_bins", C.c_uint64)]
 
 
 class H264BError(RuntimeError):
@@ -110,6 +110,7 @@ def load():
         "h264b_binary_decision": (i32, [vp, u32, i32, i32, P(C.c_int64), P(C.c_int64), P(i32)]),
         "h264b_state_transition": (i32, [vp, u32, P(i32), P(i32), i32]),
         "h264b_stream_decode": (i32, [vp, P(StreamJob), P(StreamResult)]),
+        "h264b_slice_select_dev": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -311,6 +312,12 @@ class Context:
         self._check(_lib.h264b_cabac_decode(self.h, C.byref(j)))
         return bins, fin, fst
 
+    def slice_select_dev(self, d_nals, d_summary, nal_cap, slice_data_offset, max_slices, d_off, d_len, d_slice_nal,
+                         d_n_slices):
+        self._check(_lib.h264b_slice_select_dev(self.h, C.c_void_p(d_nals), C.c_void_p(d_summary), nal_cap,
+                                                slice_data_offset, max_slices, C.c_void_p(d_off), C.c_void_p(d_len),
+                                                C.c_void_p(d_slice_nal), C.c_void_p(d_n_slices)))
+
     def cabac_decode_dev(self, **kw):
         j = CabacJob()
         for k, v in kw.items():
@@ -357,8 +364,10 @@ class Context:
         j.flags = flags
         r = StreamResult()
         self._check(_lib.h264b_stream_decode(self.h, C.byref(j), C.byref(r)))
-        ns, st = r.n_slices, r.bins_stride_words
+        ns = r.n_slices
+        boff = _from_ptr(r.bins_off, np.uint64, ns + 1)
+        flat = _from_ptr(r.bins, np.uint32, int(boff[-1]) if ns else 0)
         return dict(scan=r.scan.as_dict(), nals=_from_ptr(r.nals, NAL_DTYPE, r.scan.n_nals),
-                    slice_nal=_from_ptr(r.slice_nal, np.uint32, ns),
-                    bins=_from_ptr(r.bins, np.uint32, ns * st).reshape(ns, st) if ns else np.zeros((0, st), np.uint32),
+                    slice_nal=_from_ptr(r.slice_nal, np.uint32, ns), bins_off=boff, bins_flat=flat,
+                    bins=[flat[int(boff[i]):int(boff[i + 1])] for i in range(ns)],
                     final=_from_ptr(r.final, FINAL_DTYPE, ns), total_bins=r.total_bins)

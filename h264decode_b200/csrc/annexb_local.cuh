@@ -63,15 +63,17 @@ H264B_HD bool keep_byte_stream(const Get& get, int64_t p) {
 // keep(p) for NewNalUnit called directly on one frame [a, a+N): no start codes involved; the body is
 // [a+H, a+N-3], plus the byte a+N-2 when the frame ends in an emulation-prevention triple (the match at cursor
 // N-3 copies both zeros, nalUnit.go:113-117).
+// is p the 03 of an emulation-prevention triple that NewNalUnit removes from frame [a, a+N)?
+template <class Get>
+H264B_HD bool is_epb_frame(const Get& get, int64_t a, int64_t N, uint32_t H, int64_t p) {
+    return p - a - 2 >= (int64_t)H && p - a < N && get(p) == 3u && get(p - 1) == 0u && get(p - 2) == 0u;
+}
 template <class Get>
 H264B_HD bool keep_byte_frame(const Get& get, int64_t a, int64_t N, uint32_t H, int64_t p) {
     int64_t rel = p - a;
     if (rel < (int64_t)H) return false;
-    auto epb = [&](int64_t q) {
-        return q - a - 2 >= (int64_t)H && q - a < N && get(q) == 3u && get(q - 1) == 0u && get(q - 2) == 0u;
-    };
-    if (rel <= N - 3) return !epb(p);
-    if (rel == N - 2) return epb(p + 1);
+    if (rel <= N - 3) return !is_epb_frame(get, a, N, H, p);
+    if (rel == N - 2) return is_epb_frame(get, a, N, H, p + 1);
     return false;
 }
 

@@ -468,7 +468,9 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(ScanArgs a, h264b_na
         o.num_bytes = (uint32_t)(a.nal_start[k + 1] - o.start);
         o.rbsp_len = (uint32_t)(a.nal_rbsp_off[k + 1] - o.rbsp_off);
         decode_nal_header(a.nal_hdr[k], o, ext ? &ext[k] : nullptr);
-        const uint32_t removed = o.num_bytes - o.header_bytes - 2u - o.rbsp_len;
+        // body = NumBytes - HeaderBytes - 2 bytes (never negative in effect: a NAL shorter than that has no body)
+        const int64_t body = (int64_t)o.num_bytes - (int64_t)o.header_bytes - 2;
+        const uint32_t removed = (uint32_t)((body > 0 ? body : 0) - (int64_t)o.rbsp_len);
         o.flags = (removed ? H264B_F_HAS_EPB : 0u) | (o.num_bytes < 8 ? H264B_F_SHORT_NAL : 0u);
         epb += removed;
         nals[k] = o;
@@ -505,11 +507,15 @@ __global__ void __launch_bounds__(256) nal_frames_kernel(const uint8_t *in, uint
         const uint32_t H = nal_header_bytes(b0, b1);
         if (tid == 0) running = 0;
         __syncthreads();
+        int any_epb = 0;
         for (int64_t chunk = 0; chunk < N; chunk += 256 * 16) {
             const int64_t p0 = a0 + chunk + (int64_t)tid * 16;
             uint32_t k16 = 0;
-            for (int j = 0; j < 16; j++)
-                if (p0 + j < a0 + N && keep_byte_frame(get, a0, N, H, p0 + j)) k16 |= 1u << j;
+            for (int j = 0; j < 16; j++) {
+                if (p0 + j >= a0 + N) break;
+                if (keep_byte_frame(get, a0, N, H, p0 + j)) k16 |= 1u << j;
+                if (is_epb_frame(get, a0, N, H, p0 + j)) any_epb = 1;
+            }
             uint32_t x = __popc(k16);
             const uint32_t own = x;
 #pragma unroll
@@ -531,6 +537,7 @@ __global__ void __launch_bounds__(256) nal_frames_kernel(const uint8_t *in, uint
             if (tid == 0) running += tot;
             __syncthreads();
         }
+        any_epb = __syncthreads_or(any_epb);
         if (tid == 0) {
             h264b_nal o;
             o.start = (uint64_t)a0;
@@ -540,13 +547,8 @@ __global__ void __launch_bounds__(256) nal_frames_kernel(const uint8_t *in, uint
             const uint32_t hdr4 = b0 | (b1 << 8) | (get(a0 + 2) << 16) | (get(a0 + 3) << 24);
             decode_nal_header(hdr4, o, ext ? &ext[f] : nullptr);
             // a frame shorter than its header makes the reference panic (bit_reader.go:298): flag it
-            o.flags = ((int64_t)o.header_bytes > N ? H264B_F_OVERRUN : 0u) | (N < 8 ? H264B_F_SHORT_NAL : 0u);
-            if ((int64_t)o.header_bytes <= N) {
-                const int64_t body = N - (int64_t)o.header_bytes - 2;
-                // direct-call edge: a trailing 00 00 03 keeps byte N-2 and removes the 03
-                const int64_t expect = body > 0 ? body : 0;
-                if ((int64_t)running != expect) o.flags |= H264B_F_HAS_EPB;
-            }
+            o.flags = ((int64_t)o.header_bytes > N ? H264B_F_OVERRUN : 0u) | (N < 8 ? H264B_F_SHORT_NAL : 0u) |
+                      (any_epb ? H264B_F_HAS_EPB : 0u);
             nals[f] = o;
         }
         __syncthreads();

@@ -198,6 +198,16 @@ int32_t h264b_ctx_init_dev(h264b_ctx *ctx, const h264b_slice_qp *d_params, uint3
     return launch_ctx_init(ctx, d_params, n_slices, n_ctx, d_states, flags);
 }
 
+int32_t h264b_slice_select_dev(h264b_ctx *ctx, const h264b_nal *d_nals, const h264b_scan_summary *d_summary,
+                               uint32_t nal_cap, uint32_t slice_data_offset, uint32_t max_slices, uint64_t *d_off,
+                               uint32_t *d_len, uint32_t *d_slice_nal, uint32_t *d_n_slices) {
+    CHECK_CTX(ctx);
+    if (!d_nals || !d_summary || !d_off || !d_len || !d_slice_nal || !d_n_slices)
+        return set_error(ctx, H264B_E_INVALID, "null pointer");
+    return launch_slice_select(ctx, d_nals, d_summary, nal_cap, slice_data_offset, max_slices, d_off, d_len,
+                               d_slice_nal, d_n_slices);
+}
+
 int32_t h264b_cabac_decode_dev(h264b_ctx *ctx, const h264b_cabac_job *job) {
     CHECK_CTX(ctx);
     if (!job) return H264B_E_INVALID;
@@ -336,6 +346,7 @@ int32_t h264b_cabac_decode(h264b_ctx *ctx, const h264b_cabac_job *job) {
     RC(ensure_dev(ctx, 5, ns * 8, &d_off));
     RC(ensure_dev(ctx, 6, ns * 4, &d_len));
     RC(ensure_dev(ctx, 7, (size_t)j.n_ops_max * 2 + 16, &d_ops));
+    if (j.bins_off) return set_error(ctx, H264B_E_INVALID, "cabac: bins_off is for the _dev entry point");
     RC(ensure_dev(ctx, 11, ns * j.bins_stride_words * 4, &d_bins));
     RC(ensure_dev(ctx, 12, ns * sizeof(h264b_cabac_final), &d_fin));
     H264B_CUDA(ctx, cudaMemcpyAsync(d_bytes, j.bytes, j.total_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -417,18 +428,29 @@ int32_t h264b_stream_decode(h264b_ctx *ctx, const h264b_stream_job *job, h264b_s
         H264B_CUDA(ctx, cudaMemcpyAsync(d_nops, j.n_ops, ms * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
     H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    // 3. CABAC over the slices, contexts initialised in-kernel by the K4 rule
-    const uint32_t stride = (j.n_ops_max + 1 + 31) / 32;
+    // 3. CABAC over the slices, contexts initialised in-kernel by the K4 rule; bins in a compact layout
+    if (n_slices > j.max_slices) n_slices = j.max_slices;
     res->n_slices = n_slices;
-    res->bins_stride_words = stride;
-    void *h_nals, *h_bins, *h_fin, *h_snal;
+    void *h_nals, *h_bins, *h_fin, *h_snal, *h_boff, *d_boff;
     const size_t nn = (size_t)res->scan.n_nals;
     RC(ensure_pin(ctx, 0, nn * sizeof(h264b_nal), &h_nals));
     if (nn) H264B_CUDA(ctx, cudaMemcpyAsync(h_nals, d_nals, nn * sizeof(h264b_nal), cudaMemcpyDeviceToHost, ctx->stream));
     res->nals = (const h264b_nal *)h_nals;
+    RC(ensure_pin(ctx, 6, ((size_t)n_slices + 1) * 8, &h_boff));
+    uint64_t *boff = (uint64_t *)h_boff;
+    boff[0] = 0;
+    for (uint32_t s = 0; s < n_slices; s++) {
+        uint32_t nb = j.n_ops ? j.n_ops[s] : j.n_ops_max;
+        if (nb > j.n_ops_max) nb = j.n_ops_max;
+        boff[s + 1] = boff[s] + ((uint64_t)nb + 1 + 31) / 32;
+    }
+    res->bins_off = boff;
     if (n_slices) {
-        RC(ensure_dev(ctx, 11, (size_t)n_slices * stride * 4, &d_bins));
+        const size_t total_words = (size_t)boff[n_slices];
+        RC(ensure_dev(ctx, 10, ((size_t)n_slices + 1) * 8, &d_boff));
+        RC(ensure_dev(ctx, 11, total_words * 4, &d_bins));
         RC(ensure_dev(ctx, 12, (size_t)n_slices * sizeof(h264b_cabac_final), &d_fin));
+        H264B_CUDA(ctx, cudaMemcpyAsync(d_boff, boff, ((size_t)n_slices + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
         h264b_cabac_job cj;
         memset(&cj, 0, sizeof(cj));
         cj.bytes = d_rbsp;
@@ -442,14 +464,14 @@ int32_t h264b_stream_decode(h264b_ctx *ctx, const h264b_stream_job *job, h264b_s
         cj.n_ops = (const uint32_t *)d_nops;
         cj.qp = (const h264b_slice_qp *)d_qp;
         cj.bins = (uint32_t *)d_bins;
-        cj.bins_stride_words = stride;
+        cj.bins_off = (const uint64_t *)d_boff;
         cj.final = (h264b_cabac_final *)d_fin;
         cj.flags = j.flags;
         RC(launch_cabac(ctx, &cj));
-        RC(ensure_pin(ctx, 3, (size_t)n_slices * stride * 4, &h_bins));
+        RC(ensure_pin(ctx, 3, total_words * 4, &h_bins));
         RC(ensure_pin(ctx, 4, (size_t)n_slices * sizeof(h264b_cabac_final), &h_fin));
         RC(ensure_pin(ctx, 5, (size_t)n_slices * 4, &h_snal));
-        H264B_CUDA(ctx, cudaMemcpyAsync(h_bins, d_bins, (size_t)n_slices * stride * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        H264B_CUDA(ctx, cudaMemcpyAsync(h_bins, d_bins, total_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
         H264B_CUDA(ctx, cudaMemcpyAsync(h_fin, d_fin, (size_t)n_slices * sizeof(h264b_cabac_final), cudaMemcpyDeviceToHost, ctx->stream));
         H264B_CUDA(ctx, cudaMemcpyAsync(h_snal, d_snal, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));
         res->bins = (const uint32_t *)h_bins;

@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
 #pragma unroll
     for (int d = 16; d; d >>= 1) warp_ops = max(warp_ops, __shfl_xor_sync(0xFFFFFFFFu, warp_ops, d));
 
-    uint32_t *bins = valid ? j.bins + (size_t)slice * j.bins_stride_words : nullptr;
+    uint32_t *bins = valid ? j.bins + (j.bins_off ? (size_t)j.bins_off[slice] : (size_t)slice * j.bins_stride_words)
+                           : nullptr;
     uint32_t word = 0;
     uint32_t next_op = warp_ops ? j.ops[0] : 0;
     for (uint32_t i = 0; i < warp_ops; i++) {
@@ -144,7 +145,7 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job) {
     if (!j.bytes || !j.off || !j.len || !j.bins || !j.final || (!j.ops && j.n_ops_max))
         return set_error(ctx, H264B_E_INVALID, "cabac: null pointer in job");
     if (!j.qp && !j.init_states) return set_error(ctx, H264B_E_INVALID, "cabac: need qp or init_states");
-    if (j.bins_stride_words < (j.n_ops_max + 1 + 31) / 32)
+    if (!j.bins_off && j.bins_stride_words < (j.n_ops_max + 1 + 31) / 32)
         return set_error(ctx, H264B_E_INVALID, "cabac: bins_stride_words too small");
     if ((uintptr_t)j.bytes & 3) return set_error(ctx, H264B_E_INVALID, "cabac: bytes must be 4-byte aligned");
     const int v = (j.flags & H264B_TABLES_SPEC) ? 1 : 0;

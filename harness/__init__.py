@@ -192,3 +192,94 @@ def build_stream_cabac(n_slices, mean_bins, config=4, n_active=64, n_ctx=64, sli
     stream = assemble_annexb(pays, hdrs, params_every=slices_per_frame * frames_per_params)
     return dict(stream=stream, ops=ops, n_ops=nb, qp=qp, idc=idc, bins=g["bins"], final_states=g["final_states"],
                 n_active=n_active, n_ctx=n_ctx, payload_lens=g["lens"])
+
+
+# ------------------------------------------------------------------------------------------------ GPU generator
+_GPU_LIB_PATH = os.path.join(_HERE, "_build", "libharness_gpu.so")
+_gpu_lib = None
+
+
+def build_gpu(force=False):
+    """nvcc build of harness_gpu.cu (sm_100a); works without a GPU (cross-compile)."""
+    srcs = [os.path.join(_HERE, f) for f in ("harness_gpu.cu", "harness_core.h", "harness_tables.h")]
+    if (not force and os.path.exists(_GPU_LIB_PATH)
+            and all(os.path.getmtime(_GPU_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
+        return _GPU_LIB_PATH
+    os.makedirs(os.path.dirname(_GPU_LIB_PATH), exist_ok=True)
+    nvcc = "/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc"
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+                           "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared", "-o", _GPU_LIB_PATH,
+                           srcs[0]])
+    return _GPU_LIB_PATH
+
+
+def gpu_lib():
+    global _gpu_lib
+    if _gpu_lib is None:
+        L = C.CDLL(build_gpu())
+        vp, i64 = C.c_void_p, C.c_int64
+        L.hzg_gen_cabac_slices.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, i64, vp, vp, C.c_uint32, C.c_uint32, vp,
+                                           vp, vp, i64, vp, vp, i64, vp]
+        L.hzg_gen_cabac_slices.restype = C.c_int
+        L.hzg_random_payloads.argtypes = [C.c_int, C.c_uint32, C.c_uint64, i64, vp, vp, i64, vp]
+        L.hzg_random_payloads.restype = C.c_int
+        L.hzg_assemble.argtypes = [C.c_int, vp, i64, vp, vp, vp, i64, vp, vp, C.c_int, i64, i64]
+        L.hzg_assemble.restype = C.c_int
+        _gpu_lib = L
+    return _gpu_lib
+
+
+def slice_bins_normal(n_slices, mean_bins, config, id_base=0, sigma_frac=0.2, lo=0.16, hi=2.56):
+    """per-slice bin counts ~ N(mean, sigma) clipped (50 KB, sigma 10 KB, [8 KB, 128 KB])"""
+    rs = np.random.RandomState((0x48323634 + config * 0x1000 + id_base) & 0x7FFFFFFF)
+    z = rs.standard_normal(n_slices)
+    return np.maximum(np.clip(mean_bins * (1.0 + sigma_frac * z), mean_bins * lo, mean_bins * hi), 1).astype(np.uint32)
+
+
+def gpu_build_stream_cabac(torch, device, n_slices, mean_bins, config=4, n_active=64, n_ctx=64, slices_per_frame=8,
+                           frames_per_params=250, flags=0, id_base=0, want_bins=False):
+    """C4-shaped stream generated on the GPU (torch tensors for memory only).  Returns dict with device tensors
+    stream (uint8, padded), n (int), ops, n_ops, qp, idc (host numpy + device), bins (device or None), payload lens."""
+    L = gpu_lib()
+    nb = slice_bins_normal(n_slices, mean_bins, config, id_base)
+    ops = gen_schedule(config, int(nb.max()), n_active)
+    qp, idc = slice_params(n_slices, first=id_base)
+    dev = torch.device(device)
+    with torch.cuda.device(dev):
+        d_ops = torch.from_numpy(ops.view(np.int16)).to(dev)
+        d_nops = torch.from_numpy(nb.view(np.int32)).to(dev)
+        d_qp = torch.from_numpy(qp).to(dev)
+        d_idc = torch.from_numpy(idc).to(dev)
+        # <= ~1.02 bits per bin on average for this mix, plus escaping and flush; 1.4 bits/bin + 256 is generous
+        stride = int(int(nb.max()) * 1.4 / 8) + 256
+        stride = (stride + 15) // 16 * 16
+        d_data = torch.empty((n_slices, stride), dtype=torch.uint8, device=dev)
+        d_lens = torch.zeros(n_slices, dtype=torch.int64, device=dev)
+        words = int(nb.max()) // 32 + 1
+        d_bins = torch.zeros((n_slices, words), dtype=torch.int32, device=dev) if want_bins else None
+        d_states = torch.empty((n_slices, n_ctx), dtype=torch.uint8, device=dev)
+        rc = L.hzg_gen_cabac_slices(dev.index or 0, flags | ESCAPE, config, id_base, n_slices, d_ops.data_ptr(), d_nops.data_ptr(),
+                                    n_active, n_ctx, d_qp.data_ptr(), d_idc.data_ptr(), d_data.data_ptr(), stride,
+                                    d_lens.data_ptr(), d_bins.data_ptr() if want_bins else None, words,
+                                    d_states.data_ptr())
+        if rc != 0:
+            raise RuntimeError("hzg_gen_cabac_slices rc=%d" % rc)
+        pe = slices_per_frame * frames_per_params
+        pre = SC + SPS_NAL + SC + PPS_NAL
+        idx = torch.arange(n_slices, device=dev)
+        nal_sizes = d_lens + 5 + torch.where(idx % pe == 0, len(pre), 0)
+        ends = torch.cumsum(nal_sizes, 0)
+        pos = ends - (d_lens + 5)                      # position of each slice NAL's start code
+        total = int(ends[-1].item()) + 4
+        d_stream = torch.zeros(((total + 64 + 15) // 16) * 16, dtype=torch.uint8, device=dev)
+        hdr = np.where((np.arange(n_slices) % pe) == 0, 0x65, 0x41).astype(np.uint8)
+        d_hdr = torch.from_numpy(hdr).to(dev)
+        d_pre = torch.from_numpy(np.frombuffer(pre, np.uint8).copy()).to(dev)
+        rc = L.hzg_assemble(dev.index or 0, d_data.data_ptr(), stride, d_lens.data_ptr(), pos.data_ptr(), d_hdr.data_ptr(), n_slices,
+                            d_stream.data_ptr(), d_pre.data_ptr(), len(pre), pe, total - 4)
+        if rc != 0:
+            raise RuntimeError("hzg_assemble rc=%d" % rc)
+        lens = d_lens.cpu().numpy()
+        del d_data
+    return dict(stream=d_stream, n=total, ops=ops, n_ops=nb, qp=qp, idc=idc, bins=d_bins, final_states=d_states,
+                payload_lens=lens, n_active=n_active, n_ctx=n_ctx, n_nals=n_slices + 2 * ((n_slices + pe - 1) // pe))

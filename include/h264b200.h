@@ -183,8 +183,10 @@ typedef struct {
     const uint32_t *n_ops;         /* [n_slices] or NULL (= n_ops_max for every slice) */
     const h264b_slice_qp *qp;      /* [n_slices]: initial states by the K4 rule; used when init_states == NULL */
     const uint8_t *init_states;    /* [n_slices][n_ctx] or NULL */
-    uint32_t *bins;                /* [n_slices][bins_stride_words]: bin i of slice s = bit (i & 31) of word i >> 5 */
-    uint32_t bins_stride_words;    /* >= (n_ops_max + 1 + 31) / 32 */
+    uint32_t *bins;                /* bin i of slice s = bit (i & 31) of word (i >> 5) of the slice's row */
+    const uint64_t *bins_off;      /* [n_slices] word offset of each slice's row in `bins` (compact layout), or NULL:
+                                      row s starts at s * bins_stride_words */
+    uint32_t bins_stride_words;    /* >= (n_ops_max + 1 + 31) / 32 when bins_off == NULL */
     h264b_cabac_final *final;      /* [n_slices] */
     uint8_t *final_states;         /* [n_slices][n_ctx] or NULL */
     uint32_t flags;
@@ -231,14 +233,23 @@ typedef struct {
     h264b_scan_summary scan;
     const h264b_nal *nals;          /* [scan.n_nals] */
     uint32_t n_slices;
-    uint32_t bins_stride_words;
+    uint32_t reserved;
     const uint32_t *slice_nal;      /* [n_slices] index into nals */
-    const uint32_t *bins;           /* [n_slices][bins_stride_words] */
+    const uint64_t *bins_off;       /* [n_slices + 1] word offsets: slice s owns bins[bins_off[s] .. bins_off[s+1]) */
+    const uint32_t *bins;           /* compact: (n_ops[s] + 1 + 31) / 32 words per slice */
     const h264b_cabac_final *final; /* [n_slices] */
     uint64_t total_bins;
 } h264b_stream_result;
 
 int32_t h264b_stream_decode(h264b_ctx *ctx, const h264b_stream_job *job, h264b_stream_result *result);
+
+/* Device-resident building block of the above: the ordered list of slice NAL units (type 1 / 5, the ones
+ * handleConnection hands to the slice parser, h264/server.go:147-162) of a finished h264b_annexb_scan_dev, as
+ * (rbsp offset + slice_data_offset, remaining length) pairs ready for h264b_cabac_decode_dev.  All pointers are
+ * device pointers; d_n_slices receives min(count, max_slices).  Asynchronous. */
+int32_t h264b_slice_select_dev(h264b_ctx *ctx, const h264b_nal *d_nals, const h264b_scan_summary *d_summary,
+                               uint32_t nal_cap, uint32_t slice_data_offset, uint32_t max_slices, uint64_t *d_off,
+                               uint32_t *d_len, uint32_t *d_slice_nal, uint32_t *d_n_slices);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

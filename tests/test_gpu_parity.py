@@ -78,7 +78,8 @@ def check_scan(ctx, capi, stream):
     assert np.array_equal((nals["flags"] & capi.F_HAS_EPB) != 0, onal["epb"] == 3)
     if n:
         assert summ["first_start"] == onal["start"][0]
-        assert summ["n_epb"] == int((onal["num_bytes"] - onal["header_bytes"] - 2 - onal["rbsp_len"]).sum())
+        body = np.maximum(onal["num_bytes"] - onal["header_bytes"] - 2, 0)
+        assert summ["n_epb"] == int((body - onal["rbsp_len"]).sum())
         f = {name: i for i, name in enumerate(orc._NAL_FIELDS)}
         pairs = [("svc_extension_flag", "SvcExtensionFlag"), ("avc_3d_extension_flag", "Avc3dExtensionFlag"),
                  ("idr_flag", "IdrFlag"), ("priority_id", "PriorityId"),
@@ -172,6 +173,7 @@ def test_scan_large_properties(ctx, capi):
     assert np.array_equal(rbsp, orbsp)
     # conservation: every NAL byte is a header byte, one of the 2 tail bytes, an EPB or an RBSP byte
     assert int(nals["num_bytes"].sum()) == int(nals["header_bytes"].sum()) + 2 * len(nals) + summ["n_epb"] + len(rbsp)
+    assert summ["n_epb"] > 0
 
 
 # =========================================================================================== NewNalUnit (frames)
@@ -220,10 +222,10 @@ def compare_cabac(capi, bins, fin, fst, oracle_out, n_ops, final_term):
         if rc == orc.PANIC:
             nb = ofin["n_bins"]           # bins decoded before the reference would have panicked still agree
             for w in range(nb // 32):
-                assert bins[s, w] == obins[w]
+                assert bins[s][w] == obins[w]
             continue
         nw = (total + 31) // 32
-        got = bins[s, :nw].copy()
+        got = bins[s][:nw].copy()
         if total % 32:
             got[-1] &= np.uint32((1 << (total % 32)) - 1)
         assert np.array_equal(got, obins[:nw]), "slice %d bins" % s
@@ -348,4 +350,4 @@ def test_stream_decode_matches_oracle_pipeline(ctx, capi):
     assert r["total_bins"] == int(b["n_ops"].sum()) + len(sl)
     for i in range(len(sl)):   # and the decoded bins are the ones the encoder coded
         nw = (int(b["n_ops"][i]) + 1) // 32
-        assert np.array_equal(r["bins"][i, :nw], b["bins"][i, :nw])
+        assert np.array_equal(r["bins"][i][:nw], b["bins"][i, :nw])
