@@ -195,7 +195,11 @@ def run_gpu(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     ctx = capi.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: torch's events and the library's launches must be on the same one, and a NULL
+    # handle would mean "the context's own stream" to h264b_set_stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     flags = capi.BYPASS_SPEC_OR | capi.CABAC_FINAL_TERMINATE
 
