@@ -115,4 +115,34 @@ H264B_HD GranuleMasks granule_masks(const uint32_t w[4], uint32_t prev) {
     return m;
 }
 
+// keep mask of a granule at stream position gpos when start codes end within [gpos-6, gpos+16], in the bit domain
+// (same result as 16 x keep_byte_stream, checked exhaustively on the CPU by tests/test_hd_logic.py):
+//   e16      raw emulation-prevention mask of the granule (granule_masks().e)
+//   sc_prev / sc_own / sc_next   start-code-end masks of the previous, this and the next granule
+//   get(p)   stream byte accessor, used only for the (at most two) header bytes of each NAL that starts in reach
+template <class Get>
+H264B_HD uint32_t keep_mask_near_sc(const Get& get, int64_t gpos, uint32_t e16, uint32_t sc_prev, uint32_t sc_own,
+                                    uint32_t sc_next) {
+    // bit (16 + j) of these 64-bit masks <-> stream position gpos + j, j in [-16, 32)
+    const uint64_t S = (uint64_t)(sc_prev & 0xFFFFu) | ((uint64_t)(sc_own & 0xFFFFu) << 16) |
+                       ((uint64_t)(sc_next & 0xFFFFu) << 32);
+    uint64_t drop = S | (S >> 1);  // q and q-1: the NAL's last two bytes are never copied (nalUnit.go:107-111)
+    uint64_t no_epb = 0;
+    uint64_t cand = S & 0x7FFFFC00ull;  // start-code ends q in [gpos-6, gpos+14]: NAL starts that reach this granule
+    while (cand) {
+#if defined(__CUDA_ARCH__)
+        const int b = __ffsll((long long)cand) - 1;
+#else
+        const int b = __builtin_ctzll(cand);
+#endif
+        cand &= cand - 1;
+        const int64_t a = gpos + (b - 16) + 1;  // first byte of the NAL
+        const uint32_t H = nal_header_bytes(get(a), get(a + 1));
+        drop |= ((1ull << H) - 1ull) << (b + 1);           // header bytes a .. a+H-1
+        no_epb |= ((1ull << (H + 2u)) - 1ull) << (b + 1);  // a 03 at a .. a+H+1 has a header byte among its zeros (A7)
+    }
+    const uint32_t d16 = (uint32_t)(drop >> 16) & 0xFFFFu, n16 = (uint32_t)(no_epb >> 16) & 0xFFFFu;
+    return ~(d16 | (e16 & ~n16)) & 0xFFFFu;
+}
+
 }  // namespace h264b

@@ -12,12 +12,12 @@
 //            word-parallel arithmetic and only where two zeros precede a byte looks for 03 (emulation prevention)
 //            and 01 (start-code end); start-code bits go to a per-tile bitmap
 //   adjust   granules with a start code within reach (header bytes, the 2-byte tail rule, zeros that belong to a
-//            header) re-evaluate their 16 keep bits with the exact per-byte predicate of annexb_local.cuh
+//            header) recompute their 16 keep bits from the start-code bitmap (keep_mask_near_sc, annexb_local.cuh)
 //   scan     packed (kept bytes | start codes << 16) block scan: shuffle scan per warp, 32 warp totals by warp 0
 //   chain    decoupled look-back over per-tile descriptors gives the tile's exclusive (kept bytes, NAL index) prefix
-//   scatter  kept bytes go to a shared-memory staging buffer laid out with the alignment of the global destination
-//            (word stores for untouched granules, byte stores at the seams; 1 pad word per 32 against conflicts)
-//   store    staging -> global as aligned 16-byte stores; only the first/last partial granule of a tile uses bytes
+//   compact  the few 512-byte rows that lose bytes are compacted in place in the tile buffer (overlaps the look-back)
+//   store    every row is now `len` contiguous bytes: lanes exchange neighbour words by shuffle so that each lane
+//            writes one aligned 16-byte granule of the destination; only a row's two ragged ends use byte stores
 //   index    threads owning a start code write (start, rbsp offset, first 4 NAL bytes) for NAL k = prefix + rank
 // A tiny finalize kernel turns those into h264b_nal records (lengths are differences of neighbours).
 #include "annexb_local.cuh"
@@ -31,7 +31,6 @@ constexpr int kGranules = kThreads * kRows;       // 1024
 constexpr int kTile = kGranules * 16;             // 16384 bytes
 constexpr int kHalo = 16;
 constexpr int kInBytes = kHalo + kTile + kHalo;   // 16416
-constexpr int kStageWords = (kTile / 4 + 8) + ((kTile / 4 + 8) >> 5) + 4;
 constexpr uint64_t kStatusAgg = 1ull << 62, kStatusPrefix = 2ull << 62, kValueMask = (1ull << 62) - 1;
 
 struct ScanScratchHeader {   // device scratch, zeroed / initialised by scan_init_kernel
@@ -59,7 +58,6 @@ struct ScanArgs {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t skew(uint32_t w) { return w + (w >> 5); }
 
 __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long *p) {
     unsigned long long v;
@@ -110,21 +108,74 @@ __global__ void __launch_bounds__(256) first_start_kernel(const uint8_t *in, uin
 // ------------------------------------------------------------------------------------------------ main pass
 struct __align__(16) ScanSmem {
     uint8_t in[kInBytes];                 // [0,16): low halo, [16,16+kTile): tile, then high halo
-    uint32_t stage[kStageWords];          // compacted bytes, skewed word layout
     uint16_t scbits[kGranules + 2];       // start-code-end bits per granule, [0] = halo granule before the tile
-    uint32_t warp_tot[kRows * 8];         // packed warp totals, later exclusive offsets
+    uint32_t row_tot[kRows * 8];          // packed (kept | start codes << 16) per (row, warp); then exclusive offsets
     unsigned long long tile_kept_prefix;  // exclusive prefixes of this tile
     unsigned long long tile_nal_prefix;
-    uint32_t tile_total;                  // packed total of this tile
     uint32_t tile;
     unsigned long long mbar;
 };
 
-__device__ __forceinline__ void stage_byte(uint32_t *stage, uint32_t b, uint32_t v) {
-    reinterpret_cast<uint8_t *>(stage)[skew(b >> 2) * 4 + (b & 3)] = (uint8_t)v;
+// byte b (0..15) of a 16-byte granule held in four words, without dynamic register indexing
+__device__ __forceinline__ uint32_t granule_byte(const uint32_t y[4], int b) {
+    const uint32_t lo = (b & 4) ? y[1] : y[0], hi = (b & 4) ? y[3] : y[2];
+    return (((b & 8) ? hi : lo) >> ((b & 3) * 8)) & 0xFFu;
 }
 
-__global__ void __launch_bounds__(kThreads, 4) annexb_scan_kernel(ScanArgs a) {
+// Store `len` (<= 512) contiguous row bytes -- lane l holds row bytes [16l, 16l+16) in w -- to out[o .. o+len).
+// Lanes exchange neighbours' words by shuffle so that every lane writes one ALIGNED 16-byte granule; only the two
+// ragged ends of the row (shared with the neighbouring rows' bytes) are written byte by byte.
+__device__ __forceinline__ void store_row_shifted(uint8_t *out, uint64_t o, uint32_t len, const uint32_t w[4],
+                                                  int lane) {
+    const uint32_t sb = (uint32_t)o & 15u;  // warp-uniform
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        x[k] = __shfl_up_sync(0xFFFFFFFFu, w[k], 1);  // previous lane's granule (row bytes 16l-16 .. 16l-1)
+        x[4 + k] = w[k];
+    }
+    // this lane's output granule = row bytes [16l - sb, 16l - sb + 16) = bytes [16 - sb, 32 - sb) of x
+    const uint32_t off = 16u - sb, br8 = (off & 3u) * 8u;
+    uint32_t y[4];
+    switch (off >> 2) {  // warp-uniform
+        case 0:
+#pragma unroll
+            for (int k = 0; k < 4; k++) y[k] = __funnelshift_r(x[k], x[k + 1], br8);
+            break;
+        case 1:
+#pragma unroll
+            for (int k = 0; k < 4; k++) y[k] = __funnelshift_r(x[1 + k], x[2 + k], br8);
+            break;
+        case 2:
+#pragma unroll
+            for (int k = 0; k < 4; k++) y[k] = __funnelshift_r(x[2 + k], x[3 + k], br8);
+            break;
+        case 3:
+#pragma unroll
+            for (int k = 0; k < 4; k++) y[k] = __funnelshift_r(x[3 + k], x[4 + k], br8);
+            break;
+        default:  // sb == 0: already aligned
+#pragma unroll
+            for (int k = 0; k < 4; k++) y[k] = w[k];
+            break;
+    }
+    const int lo_b = 16 * lane - (int)sb;  // first row byte of this lane's output granule
+    uint8_t *dst = out + (o - sb) + 16u * (uint32_t)lane;
+    if (lo_b >= 0 && lo_b + 16 <= (int)len) {
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(y[0], y[1], y[2], y[3]);
+    } else {
+        const int b0 = lo_b < 0 ? -lo_b : 0;
+        const int b1 = (int)len - lo_b < 16 ? (int)len - lo_b : 16;
+        for (int b = b0; b < b1; b++) dst[b] = (uint8_t)granule_byte(y, b);
+    }
+    // the 33rd granule: the last sb bytes of lane 31's data when the row runs to byte 512
+    if (lane == 31 && sb != 0 && len + sb > 512u) {
+        uint8_t *d2 = out + o + 496;
+        for (uint32_t b = 16u - sb; b < 16u && 496u + b < len; b++) d2[b] = (uint8_t)granule_byte(w, (int)b);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 5) annexb_scan_kernel(ScanArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     ScanSmem &sm = *reinterpret_cast<ScanSmem *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -160,6 +211,7 @@ __global__ void __launch_bounds__(kThreads, 4) annexb_scan_kernel(ScanArgs a) {
                 : "memory");
         }
         // bytes outside the stream read as 0xFF (they match no predicate): low halo of tile 0 ...
+        const bool edge_tile = tile == 0 || hi < base + kTile + kHalo || hi > a.n;  // CTA-uniform
         if (tile == 0 && tid < 4) reinterpret_cast<uint32_t *>(sm.in)[tid] = 0xFFFFFFFFu;
         // ... and everything the copy does not write at the end of the stream
         const uint32_t loaded_end = (uint32_t)(hi - (base - kHalo));  // offset in sm.in
@@ -178,12 +230,14 @@ __global__ void __launch_bounds__(kThreads, 4) annexb_scan_kernel(ScanArgs a) {
             }
             parity ^= 1;
         }
-        if (hi > a.n && hi - a.n < 16) {  // the last 16-byte granule holds bytes past n: blank them
-            uint32_t first_bad = (uint32_t)(a.n - (base - kHalo));
-            if (tid < 16 && first_bad + tid < loaded_end) sm.in[first_bad + tid] = 0xFF;
+        if (edge_tile) {
+            if (hi > a.n && hi - a.n < 16) {  // the last 16-byte granule holds bytes past n: blank them
+                uint32_t first_bad = (uint32_t)(a.n - (base - kHalo));
+                if (tid < 16 && first_bad + tid < loaded_end) sm.in[first_bad + tid] = 0xFF;
+            }
+            __syncthreads();  // the 0xFF fills above are plain stores other threads read
         }
-        __syncthreads();  // the 0xFF fills above are plain stores other threads read
-        const uint8_t *tile_in = sm.in + kHalo;  // tile_in[i] = s[base + i], valid for i in [-16, kTile+16)
+        uint8_t *tile_in = sm.in + kHalo;  // tile_in[i] = s[base + i], valid for i in [-16, kTile+16)
 
         // ---------------------------------------------------------------- detect
         uint32_t em[kRows];  // raw EPB mask | start-code mask << 16
@@ -206,11 +260,13 @@ __global__ void __launch_bounds__(kThreads, 4) annexb_scan_kernel(ScanArgs a) {
         }
         __syncthreads();
 
-        // ---------------------------------------------------------------- adjust + count
+        // ---------------------------------------------------------------- adjust + count + per-row scan
         const bool tile_has_head = base < e0;            // some bytes precede the first NAL
         const bool tile_has_end = base + kTile > a.n;    // some granules reach past the stream
         auto get = [&](int64_t p) -> uint32_t { return tile_in[p - (int64_t)base]; };
-        uint32_t keep[kRows], packed[kRows];
+        uint32_t ks[kRows];    // keep mask | start-code mask << 16
+        uint32_t incl[kRows];  // inclusive packed scan (kept | start codes << 16) inside the (row, warp) group
+        uint32_t dirty = 0;    // warp-uniform bit per row: some granule of the row is not kept entirely
 #pragma unroll
         for (int r = 0; r < kRows; r++) {
             const int gi = r * kThreads + tid;
@@ -218,19 +274,16 @@ __global__ void __launch_bounds__(kThreads, 4) annexb_scan_kernel(ScanArgs a) {
             uint32_t k16 = ~em[r] & 0xFFFFu;
             // start-code ends q in [g-6, g+16] change what this granule keeps
             const uint32_t near = ((uint32_t)sm.scbits[gi] >> 10) | sm.scbits[gi + 1] | (sm.scbits[gi + 2] & 1u);
-            if (near) {
-                k16 = 0;
-#pragma unroll 1
-                for (int j = 0; j < 16; j++)
-                    if (keep_byte_stream(get, (int64_t)gpos + j)) k16 |= 1u << j;
-            }
+            if (near)  // rare: header bytes, the 2-byte tail rule and the EPB guard, all in the bit domain
+                k16 = keep_mask_near_sc(get, (int64_t)gpos, em[r] & 0xFFFFu, sm.scbits[gi], sm.scbits[gi + 1],
+                                        sm.scbits[gi + 2]);
+            uint32_t sc = em[r] >> 16;
             if (tile_has_head) {
                 if (gpos + 16 <= e0)
                     k16 = 0;
                 else if (gpos < e0)
                     k16 &= ~((1u << (uint32_t)(e0 - gpos)) - 1u);
             }
-            uint32_t sc = em[r] >> 16;
             if (tile_has_end) {
                 if (gpos >= a.n) {
                     k16 = 0;
@@ -240,37 +293,38 @@ __global__ void __launch_bounds__(kThreads, 4) annexb_scan_kernel(ScanArgs a) {
                     k16 &= valid;
                     sc &= valid;
                 }
-                em[r] = (em[r] & 0xFFFFu) | (sc << 16);
             }
-            keep[r] = k16;
-            packed[r] = __popc(k16) | (__popc(sc) << 16);
-        }
-
-        // ---------------------------------------------------------------- block scan (row-major granule order)
-        uint32_t incl[kRows];
+            ks[r] = k16 | (sc << 16);
+            const uint32_t packed = __popc(k16) | (__popc(sc) << 16);
+            uint32_t x;
+            if (__all_sync(0xFFFFFFFFu, packed == 16u)) {  // the usual row: 512 bytes in, 512 bytes out
+                x = 16u * (uint32_t)(lane + 1);
+            } else {
+                dirty |= 1u << r;
+                x = packed;
 #pragma unroll
-        for (int r = 0; r < kRows; r++) {
-            uint32_t x = packed[r];
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-                if (lane >= d) x += y;
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+                    if (lane >= d) x += y;
+                }
             }
             incl[r] = x;
-            if (lane == 31) sm.warp_tot[r * 8 + warp] = x;
+            if (lane == 31) sm.row_tot[r * 8 + warp] = x;
         }
         __syncthreads();
+
+        // ---------------------------------------------------------------- tile prefix (warp 0) | in-place compaction
         if (warp == 0) {
-            uint32_t x = sm.warp_tot[lane], own = x;
+            uint32_t x = sm.row_tot[lane], own = x;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
                 if (lane >= d) x += y;
             }
-            sm.warp_tot[lane] = x - own;  // exclusive
+            sm.row_tot[lane] = x - own;  // exclusive
             const uint32_t total = __shfl_sync(0xFFFFFFFFu, x, 31);
             const unsigned long long agg_kept = total & 0xFFFFu, agg_nal = total >> 16;
-            // ------------------------------------------------------------ decoupled look-back (warp 0)
+            // ------------------------------------------------------------ decoupled look-back
             unsigned long long pre_kept = 0, pre_nal = 0;
             if (tile > 0) {
                 if (lane == 0) {
@@ -314,93 +368,73 @@ __global__ void __launch_bounds__(kThreads, 4) annexb_scan_kernel(ScanArgs a) {
                 st_relaxed(&a.desc_nal[tile], kStatusPrefix | (pre_nal + agg_nal));
                 sm.tile_kept_prefix = pre_kept;
                 sm.tile_nal_prefix = pre_nal;
-                sm.tile_total = total;
                 if (tile == a.n_tiles - 1) {
                     a.hdr->total_kept = pre_kept + agg_kept;
                     a.hdr->total_sc = pre_nal + agg_nal;
                 }
             }
         }
-        __syncthreads();
-        const uint64_t gout = sm.tile_kept_prefix;       // global output offset of this tile's first kept byte
-        const uint64_t nal0 = sm.tile_nal_prefix;
-        const uint32_t tile_kept = sm.tile_total & 0xFFFFu;
-        const uint32_t align = (uint32_t)(gout & 15);    // staging mirrors the destination's 16-byte phase
-
-        // ---------------------------------------------------------------- scatter to staging + NAL index
+        // Rows that lose bytes are compacted in place inside their own 512-byte span of the tile buffer (nobody else
+        // reads it any more), so that afterwards EVERY row is `len` contiguous bytes starting at its span.
+        if (dirty) {
 #pragma unroll
-        for (int r = 0; r < kRows; r++) {
-            const int gi = r * kThreads + tid;
-            const uint32_t excl = sm.warp_tot[r * 8 + warp] + incl[r] - packed[r];
-            const uint32_t loff = excl & 0xFFFFu;
-            const uint32_t k16 = keep[r];
-            const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            uint32_t off = align + loff;
-            if (k16 == 0xFFFFu) {
-                const uint32_t s = off & 3u, W = off >> 2;
-                if (s == 0) {
-                    sm.stage[skew(W)] = w[0];
-                    sm.stage[skew(W + 1)] = w[1];
-                    sm.stage[skew(W + 2)] = w[2];
-                    sm.stage[skew(W + 3)] = w[3];
+            for (int r = 0; r < kRows; r++) {
+                if (!(dirty & (1u << r))) continue;  // warp-uniform
+                const int gi = r * kThreads + tid;
+                const uint32_t k16 = ks[r] & 0xFFFFu;
+                const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                __syncwarp();  // every lane has its bytes in registers before anyone overwrites the span
+                uint32_t loff = (incl[r] & 0xFFFFu) - __popc(k16);
+                uint8_t *row = tile_in + (r * kThreads + warp * 32) * 16;
+                if (k16 == 0xFFFFu && (loff & 3u) == 0) {
+                    uint32_t *d = reinterpret_cast<uint32_t *>(row + loff);
+                    d[0] = w[0];
+                    d[1] = w[1];
+                    d[2] = w[2];
+                    d[3] = w[3];
                 } else {
-                    const uint32_t sh = s * 8;
-                    sm.stage[skew(W + 1)] = __funnelshift_l(w[0], w[1], sh);
-                    sm.stage[skew(W + 2)] = __funnelshift_l(w[1], w[2], sh);
-                    sm.stage[skew(W + 3)] = __funnelshift_l(w[2], w[3], sh);
-                    // head: granule bytes 0..3-s ; tail: granule bytes 16-s..15
-                    stage_byte(sm.stage, off, w[0] & 0xFF);
-                    if (s <= 2) stage_byte(sm.stage, off + 1, (w[0] >> 8) & 0xFF);
-                    if (s == 1) stage_byte(sm.stage, off + 2, (w[0] >> 16) & 0xFF);
-                    stage_byte(sm.stage, off + 15, w[3] >> 24);
-                    if (s >= 2) stage_byte(sm.stage, off + 14, (w[3] >> 16) & 0xFF);
-                    if (s == 3) stage_byte(sm.stage, off + 13, (w[3] >> 8) & 0xFF);
-                }
-            } else if (k16) {
 #pragma unroll
-                for (int j = 0; j < 16; j++)
-                    if (k16 & (1u << j)) stage_byte(sm.stage, off++, (w[j >> 2] >> ((j & 3) * 8)) & 0xFF);
-            }
-            uint32_t sc = em[r] >> 16;
-            if (sc) {  // NAL index entries for the start codes that end in this granule
-                uint64_t k = nal0 + (excl >> 16);
-                while (sc) {
-                    const int j = __ffs(sc) - 1;
-                    sc &= sc - 1;
-                    if (k < a.nal_cap) {
-                        const int i0 = gi * 16 + j + 1;  // tile-relative offset of the NAL's first byte
-                        a.nal_start[k] = base + (uint64_t)i0;
-                        a.nal_rbsp_off[k] = gout + loff + __popc(k16 & ((1u << j) - 1u));
-                        a.nal_hdr[k] = (uint32_t)tile_in[i0] | ((uint32_t)tile_in[i0 + 1] << 8) |
-                                       ((uint32_t)tile_in[i0 + 2] << 16) | ((uint32_t)tile_in[i0 + 3] << 24);
-                    }
-                    k++;
+                    for (int j = 0; j < 16; j++)
+                        if (k16 & (1u << j)) row[loff++] = (uint8_t)(w[j >> 2] >> ((j & 3) * 8));
                 }
             }
         }
         __syncthreads();
+        const uint64_t gout = sm.tile_kept_prefix;  // global output offset of this tile's first kept byte
+        const uint64_t nal0 = sm.tile_nal_prefix;
 
-        // ---------------------------------------------------------------- staging -> global, aligned 16-byte stores
-        {
-            const uint32_t end = align + tile_kept;  // staging holds bytes [align, end)
-            const uint32_t n_gran = (end + 15) >> 4;
-            uint8_t *gbase = a.out + (gout - align);  // 16-byte aligned
-            for (uint32_t j = tid; j < n_gran; j += kThreads) {
-                const uint32_t p0 = skew(j * 4);
-                uint4 v;
-                v.x = sm.stage[p0];
-                v.y = sm.stage[p0 + 1];
-                v.z = sm.stage[p0 + 2];
-                v.w = sm.stage[p0 + 3];
-                const uint32_t b0 = j * 16;
-                if (b0 >= align && b0 + 16 <= end) {
-                    *reinterpret_cast<uint4 *>(gbase + b0) = v;
-                } else {  // seam with the neighbouring tile's bytes: byte-granular
-                    const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+        // ---------------------------------------------------------------- store rows + NAL index
 #pragma unroll
-                    for (int b = 0; b < 16; b++)
-                        if (b0 + b >= align && b0 + b < end) gbase[b0 + b] = (uint8_t)(ww[b >> 2] >> ((b & 3) * 8));
+        for (int r = 0; r < kRows; r++) {
+            const int gi = r * kThreads + tid;
+            const uint32_t rowoff = sm.row_tot[r * 8 + warp];  // warp-uniform
+            const uint32_t len = __shfl_sync(0xFFFFFFFFu, incl[r], 31) & 0xFFFFu;
+            const uint64_t o = gout + (rowoff & 0xFFFFu);
+            if (len) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                store_row_shifted(a.out, o, len, w, lane);
+            }
+            uint32_t sc = ks[r] >> 16;
+            if (sc) {  // NAL index entries for the start codes that end in this granule
+                const uint32_t k16 = ks[r] & 0xFFFFu;
+                const uint32_t excl = incl[r] - (__popc(k16) | (__popc(sc) << 16));
+                uint64_t k = nal0 + (rowoff >> 16) + (excl >> 16);
+                while (sc) {
+                    const int j = __ffs(sc) - 1;
+                    sc &= sc - 1;
+                    if (k < a.nal_cap) {
+                        const uint64_t st = base + (uint64_t)(gi * 16 + j + 1);  // the NAL's first byte
+                        a.nal_start[k] = st;
+                        a.nal_rbsp_off[k] = o + (excl & 0xFFFFu) + __popc(k16 & ((1u << j) - 1u));
+                        uint32_t h = 0;  // its first 4 bytes, from the (L2-resident) input: the tile copy may be compacted
+#pragma unroll
+                        for (int t = 0; t < 4; t++)
+                            h |= (uint32_t)(st + t < a.n ? a.in[st + t] : (uint8_t)0xFF) << (8 * t);
+                        a.nal_hdr[k] = h;
+                    }
+                    k++;
                 }
             }
         }

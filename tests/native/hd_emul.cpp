@@ -16,7 +16,8 @@ using namespace h264b;
 extern "C" {
 
 // Whole-stream split + strip with the position-local rules, granule by granule like annexb_scan_kernel:
-// granules with a start-code end in [g-6, g+16] use keep_byte_stream, the others use ~raw-EPB mask.
+// granules with a start-code end in [g-6, g+16] use keep_mask_near_sc, the others use ~raw-EPB mask; both are
+// compared with the exact per-byte predicate keep_byte_stream.
 // Outputs: nal_start / nal_rbsp_off / nal_hdr per start code (K entries), rbsp bytes; returns K.
 // *fast_slow_mismatch counts granules where the fast mask differs from the exact predicate although no start code
 // is near (must be 0).
@@ -49,10 +50,12 @@ int64_t emul_stream(const uint8_t *s, int64_t n, uint64_t *nal_start, uint64_t *
         uint32_t exact = 0;
         for (int j = 0; j < 16; j++)
             if (keep_byte_stream(get, gpos + j)) exact |= 1u << j;
-        if (near)
-            k16 = exact;
-        else if (k16 != exact)
+        if (near) {
+            k16 = keep_mask_near_sc(get, gpos, em[g + 1], sc[g], sc[g + 1], sc[g + 2]);
+            if (k16 != exact) mism++;
+        } else if (k16 != exact) {
             mism++;
+        }
         if (gpos + 16 <= e0)
             k16 = 0;
         else if (gpos < e0)
