@@ -145,4 +145,128 @@ H264B_HD uint32_t keep_mask_near_sc(const Get& get, int64_t gpos, uint32_t e16, 
     return ~(d16 | (e16 & ~n16)) & 0xFFFFu;
 }
 
+#if defined(__CUDA_ARCH__)
+H264B_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
+H264B_HD void store16(uint8_t *dst, const uint32_t v[4]) {  // dst is 16-byte aligned
+    *reinterpret_cast<uint4 *>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
+}
+#else
+H264B_HD void store16(uint8_t *dst, const uint32_t v[4]) {
+    for (int b = 0; b < 16; b++) dst[b] = (uint8_t)(v[b >> 2] >> ((b & 3) * 8));
+}
+H264B_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
+    s &= 31u;
+    return s ? ((lo >> s) | (hi << (32u - s))) : lo;
+}
+#endif
+
+// byte b (0..15) of a 16-byte granule held in four words, without dynamic register indexing
+H264B_HD uint32_t granule_byte(const uint32_t y[4], int b) {
+    const uint32_t lo = (b & 4) ? y[1] : y[0], hi = (b & 4) ? y[3] : y[2];
+    return (((b & 8) ? hi : lo) >> ((b & 3) * 8)) & 0xFFu;
+}
+
+// Store row t of a tile (one lane's part; the kernel calls this for all 32 lanes of the row's warp) -- `len` (<= 512) contiguous bytes, lane l holding row bytes [16l, 16l+16) in w -- to
+// out[o .. o+len).  After the in-place compaction every row of the tile is a contiguous run in shared memory (row t at
+// tile_in + 512 t), and rows follow each other without gaps in the output, so:
+//   * lanes exchange neighbours' words by shuffle and each writes one ALIGNED 16-byte granule of the destination;
+//   * the granule that straddles the seam with the previous row is written once, by this row's lane 0, which fetches
+//     the previous row's last bytes from shared memory;
+//   * only the first ragged granule of a tile (its other bytes belong to the previous tile) and the last one (next
+//     tile) are written byte by byte.
+// rowoff[0..31] = exclusive kept-byte offsets of the tile's rows (low 16 bits), x_row = rowoff[t], K = tile total.
+H264B_HD void store_row_lane(uint8_t *out, uint64_t o, uint32_t len, const uint32_t wp[4], const uint32_t w[4],
+                             int lane, int t, uint32_t x_row, uint32_t K, const uint8_t *tile_in,
+                             const uint32_t *rowoff) {
+    const uint32_t sb = (uint32_t)o & 15u;  // warp-uniform
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        x[k] = wp[k];  // previous lane's granule (row bytes 16l-16 .. 16l-1); by shuffle on the device
+        x[4 + k] = w[k];
+    }
+    // this lane's output granule = row bytes [16l - sb, 16l - sb + 16) = bytes [16 - sb, 32 - sb) of x
+    const uint32_t off = 16u - sb, br8 = (off & 3u) * 8u;
+    uint32_t y[4];
+    switch (off >> 2) {  // warp-uniform
+        case 0:
+#pragma unroll
+            for (int k = 0; k < 4; k++) y[k] = funnel_r(x[k], x[k + 1], br8);
+            break;
+        case 1:
+#pragma unroll
+            for (int k = 0; k < 4; k++) y[k] = funnel_r(x[1 + k], x[2 + k], br8);
+            break;
+        case 2:
+#pragma unroll
+            for (int k = 0; k < 4; k++) y[k] = funnel_r(x[2 + k], x[3 + k], br8);
+            break;
+        case 3:
+#pragma unroll
+            for (int k = 0; k < 4; k++) y[k] = funnel_r(x[3 + k], x[4 + k], br8);
+            break;
+        default:  // sb == 0: already aligned
+#pragma unroll
+            for (int k = 0; k < 4; k++) y[k] = w[k];
+            break;
+    }
+    const int lo_b = 16 * lane - (int)sb;  // first row byte of this lane's output granule
+    uint8_t *dst = out + (o - sb) + 16u * (uint32_t)lane;
+    if (lo_b >= 0 && lo_b + 16 <= (int)len) {
+        store16(dst, y);
+    } else if (lane == 0 && sb != 0 && len >= 16u - sb) {
+        // seam granule: its first sb bytes are the sb output bytes before this row.  The ones that belong to this tile
+        // (tile-output coordinates x_row - have .. x_row - 1) are fetched from shared memory; any others are the
+        // previous tile's and are written by it.
+        const uint32_t have = x_row < sb ? x_row : sb;  // how many of the sb bytes this tile holds
+        const uint32_t plen = t > 0 ? ((x_row - rowoff[t - 1]) & 0xFFFFu) : 0u;
+        uint32_t z[4] = {0u, 0u, 0u, 0u};
+        if (have == sb && plen >= sb) {  // usual case: all of them are the tail of row t-1
+            const uint32_t addr = 512u * (uint32_t)(t - 1) + plen - sb;  // byte offset in the tile buffer
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(tile_in + (addr & ~3u));
+            const uint32_t s8 = (addr & 3u) * 8u;
+            const uint32_t q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3], q4 = p[4];
+            z[0] = funnel_r(q0, q1, s8);
+            z[1] = funnel_r(q1, q2, s8);
+            z[2] = funnel_r(q2, q3, s8);
+            z[3] = funnel_r(q3, q4, s8);
+        } else {  // rare: tiny rows in between and / or the tile's first bytes; walk back byte by byte
+            int tt = t - 1;
+            for (int b = (int)sb - 1; b >= (int)(sb - have); b--) {
+                const uint32_t xo = x_row - sb + (uint32_t)b;  // tile-output coordinate of this byte
+                while (tt > 0 && (rowoff[tt] & 0xFFFFu) > xo) tt--;
+                const uint32_t v = tile_in[512 * tt + (int)(xo - (rowoff[tt] & 0xFFFFu))];
+                const uint32_t sh = (uint32_t)(b & 3) * 8u;
+                if (b < 4) z[0] |= v << sh; else if (b < 8) z[1] |= v << sh;
+                else if (b < 12) z[2] |= v << sh; else z[3] |= v << sh;
+            }
+        }
+        uint32_t r4[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {  // bytes < sb from z, the rest from y
+            const int nb = (int)sb - 4 * k;
+            const uint32_t m = nb >= 4 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
+            r4[k] = (z[k] & m) | (y[k] & ~m);
+        }
+        if (have == sb) {
+            store16(dst, r4);
+        } else {  // first ragged granule of the tile
+            for (int b = (int)(sb - have); b < 16; b++) dst[b] = (uint8_t)granule_byte(r4, b);
+        }
+    }
+    // the last ragged granule of the TILE (nothing after this row in the tile): bytes only
+    if (x_row + len == K && ((sb + len) & 15u) != 0) {
+        const uint32_t jt = (sb + len) >> 4, nb = (sb + len) & 15u;  // granule index in the row, valid bytes in it
+        if (jt < 32u) {
+            if ((uint32_t)lane == jt) {
+                const int b0 = lo_b < 0 ? -lo_b : 0;
+                for (int b = b0; b < (int)nb; b++) dst[b] = (uint8_t)granule_byte(y, b);
+            }
+        } else if (lane == 31) {  // 33rd granule: the last sb bytes of lane 31's data
+            uint8_t *d2 = out + o + 496;
+            for (uint32_t b = 16u - sb; b < 16u && 496u + b < len; b++) d2[b] = (uint8_t)granule_byte(w, (int)b);
+        }
+    }
+}
+
 }  // namespace h264b

@@ -30,6 +30,7 @@ constexpr int kRows = 4;                          // granules per thread per til
 constexpr int kGranules = kThreads * kRows;       // 1024
 constexpr int kTile = kGranules * 16;             // 16384 bytes
 constexpr int kHalo = 16;
+constexpr int kLook = 4;                          // predecessor tiles each lane inspects per look-back round
 constexpr int kInBytes = kHalo + kTile + kHalo;   // 16416
 constexpr uint64_t kStatusAgg = 1ull << 62, kStatusPrefix = 2ull << 62, kValueMask = (1ull << 62) - 1;
 
@@ -48,8 +49,7 @@ struct ScanArgs {
     uint64_t n;
     uint8_t *out;
     ScanScratchHeader *hdr;
-    unsigned long long *desc_kept;
-    unsigned long long *desc_nal;
+    ulonglong2 *desc;  // per tile: {status << 62 | kept bytes, start codes}
     unsigned long long *nal_start;
     unsigned long long *nal_rbsp_off;
     uint32_t *nal_hdr;
@@ -66,6 +66,15 @@ __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long lon
 }
 __device__ __forceinline__ void st_relaxed(unsigned long long *p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// 16-byte tile descriptors: one 128-bit transaction each way (L2 is the point of coherence: .cg / volatile)
+__device__ __forceinline__ ulonglong2 ld_desc(const ulonglong2 *p) {
+    ulonglong2 v;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_desc(ulonglong2 *p, unsigned long long x, unsigned long long y) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(x), "l"(y) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------ init
@@ -113,66 +122,18 @@ struct __align__(16) ScanSmem {
     unsigned long long tile_kept_prefix;  // exclusive prefixes of this tile
     unsigned long long tile_nal_prefix;
     uint32_t tile;
+    uint32_t tile_total;                  // packed total of this tile
     unsigned long long mbar;
 };
 
-// byte b (0..15) of a 16-byte granule held in four words, without dynamic register indexing
-__device__ __forceinline__ uint32_t granule_byte(const uint32_t y[4], int b) {
-    const uint32_t lo = (b & 4) ? y[1] : y[0], hi = (b & 4) ? y[3] : y[2];
-    return (((b & 8) ? hi : lo) >> ((b & 3) * 8)) & 0xFFu;
-}
-
-// Store `len` (<= 512) contiguous row bytes -- lane l holds row bytes [16l, 16l+16) in w -- to out[o .. o+len).
-// Lanes exchange neighbours' words by shuffle so that every lane writes one ALIGNED 16-byte granule; only the two
-// ragged ends of the row (shared with the neighbouring rows' bytes) are written byte by byte.
-__device__ __forceinline__ void store_row_shifted(uint8_t *out, uint64_t o, uint32_t len, const uint32_t w[4],
-                                                  int lane) {
-    const uint32_t sb = (uint32_t)o & 15u;  // warp-uniform
-    uint32_t x[8];
+// Device wrapper of store_row_lane (annexb_local.cuh): the previous lane's granule comes by shuffle.
+__device__ __forceinline__ void store_row(uint8_t *out, uint64_t o, uint32_t len, const uint32_t w[4], int lane,
+                                          int t, uint32_t x_row, uint32_t K, const uint8_t *tile_in,
+                                          const uint32_t *rowoff) {
+    uint32_t wp[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        x[k] = __shfl_up_sync(0xFFFFFFFFu, w[k], 1);  // previous lane's granule (row bytes 16l-16 .. 16l-1)
-        x[4 + k] = w[k];
-    }
-    // this lane's output granule = row bytes [16l - sb, 16l - sb + 16) = bytes [16 - sb, 32 - sb) of x
-    const uint32_t off = 16u - sb, br8 = (off & 3u) * 8u;
-    uint32_t y[4];
-    switch (off >> 2) {  // warp-uniform
-        case 0:
-#pragma unroll
-            for (int k = 0; k < 4; k++) y[k] = __funnelshift_r(x[k], x[k + 1], br8);
-            break;
-        case 1:
-#pragma unroll
-            for (int k = 0; k < 4; k++) y[k] = __funnelshift_r(x[1 + k], x[2 + k], br8);
-            break;
-        case 2:
-#pragma unroll
-            for (int k = 0; k < 4; k++) y[k] = __funnelshift_r(x[2 + k], x[3 + k], br8);
-            break;
-        case 3:
-#pragma unroll
-            for (int k = 0; k < 4; k++) y[k] = __funnelshift_r(x[3 + k], x[4 + k], br8);
-            break;
-        default:  // sb == 0: already aligned
-#pragma unroll
-            for (int k = 0; k < 4; k++) y[k] = w[k];
-            break;
-    }
-    const int lo_b = 16 * lane - (int)sb;  // first row byte of this lane's output granule
-    uint8_t *dst = out + (o - sb) + 16u * (uint32_t)lane;
-    if (lo_b >= 0 && lo_b + 16 <= (int)len) {
-        *reinterpret_cast<uint4 *>(dst) = make_uint4(y[0], y[1], y[2], y[3]);
-    } else {
-        const int b0 = lo_b < 0 ? -lo_b : 0;
-        const int b1 = (int)len - lo_b < 16 ? (int)len - lo_b : 16;
-        for (int b = b0; b < b1; b++) dst[b] = (uint8_t)granule_byte(y, b);
-    }
-    // the 33rd granule: the last sb bytes of lane 31's data when the row runs to byte 512
-    if (lane == 31 && sb != 0 && len + sb > 512u) {
-        uint8_t *d2 = out + o + 496;
-        for (uint32_t b = 16u - sb; b < 16u && 496u + b < len; b++) d2[b] = (uint8_t)granule_byte(w, (int)b);
-    }
+    for (int k = 0; k < 4; k++) wp[k] = __shfl_up_sync(0xFFFFFFFFu, w[k], 1);
+    store_row_lane(out, o, len, wp, w, lane, t, x_row, K, tile_in, rowoff);
 }
 
 __global__ void __launch_bounds__(kThreads, 5) annexb_scan_kernel(ScanArgs a) {
@@ -325,49 +286,64 @@ __global__ void __launch_bounds__(kThreads, 5) annexb_scan_kernel(ScanArgs a) {
             const uint32_t total = __shfl_sync(0xFFFFFFFFu, x, 31);
             const unsigned long long agg_kept = total & 0xFFFFu, agg_nal = total >> 16;
             // ------------------------------------------------------------ decoupled look-back
+            // One 16-byte descriptor per tile {status<<62 | kept bytes, start codes}, written and read with single
+            // 128-bit accesses (the same single-transaction property CUB's tile-state words rely on).  Window of
+            // 32 x kLook predecessors per round (each lane inspects kLook consecutive tiles, nearest first): resident
+            // tiles tend to reach this point together, so the distance to the nearest published prefix is of the
+            // order of the number of resident CTAs, while a round costs one L2 round trip.
             unsigned long long pre_kept = 0, pre_nal = 0;
             if (tile > 0) {
-                if (lane == 0) {
-                    st_relaxed(&a.desc_kept[tile], kStatusAgg | agg_kept);
-                    st_relaxed(&a.desc_nal[tile], kStatusAgg | agg_nal);
-                }
-                bool done_k = false, done_n = false;
-                for (int64_t j = (int64_t)tile - 1; !(done_k && done_n); j -= 32) {
-                    const int64_t idx = j - lane;
-                    unsigned long long dk = kStatusPrefix, dn = kStatusPrefix;  // virtual tile -1: prefix 0
+                if (lane == 0) st_desc(&a.desc[tile], kStatusAgg | agg_kept, agg_nal);
+                bool done = false;
+                for (int64_t j = (int64_t)tile - 1; !done; j -= 32 * kLook) {
+                    const int64_t first_idx = j - (int64_t)lane * kLook;  // this lane: first_idx, first_idx-1, ...
+                    ulonglong2 d[kLook];
                     bool pending;
-                    do {  // all 32 lanes poll together; lanes before tile 0 have nothing to wait for
-                        if (idx >= 0) {
-                            dk = ld_relaxed(&a.desc_kept[idx]);
-                            dn = ld_relaxed(&a.desc_nal[idx]);
+                    do {  // all 32 lanes poll together; positions before tile 0 count as a published prefix of 0
+                        pending = false;
+                        bool seen = false;
+#pragma unroll
+                        for (int u = 0; u < kLook; u++) {
+                            const int64_t idx = first_idx - u;
+                            d[u] = idx >= 0 ? ld_desc(&a.desc[idx]) : make_ulonglong2(kStatusPrefix, 0ull);
                         }
-                        pending = idx >= 0 && ((dk >> 62) == 0 || (dn >> 62) == 0);
+#pragma unroll
+                        for (int u = 0; u < kLook; u++) {  // blocked only by an unpublished tile nearer than a prefix
+                            if (!seen && (d[u].x >> 62) == 0) pending = true;
+                            seen = seen || (d[u].x >> 62) == 2;
+                        }
+                        // lanes farther back than a prefix found by a nearer lane do not matter
+                        const uint32_t pm = __ballot_sync(0xFFFFFFFFu, seen);
+                        if (pm & ((1u << lane) - 1u)) pending = false;
                     } while (__any_sync(0xFFFFFFFFu, pending));
-                    if (!done_k) {
-                        const uint32_t pm = __ballot_sync(0xFFFFFFFFu, (dk >> 62) == 2);
-                        const int first = pm ? __ffs(pm) - 1 : 31;
-                        unsigned long long v = (lane <= first) ? (dk & kValueMask) : 0ull;
+                    unsigned long long vk = 0, vn = 0;
+                    bool found = false;
 #pragma unroll
-                        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
-                        pre_kept += v;
-                        done_k = pm != 0;
+                    for (int u = 0; u < kLook; u++) {
+                        if (!found) {
+                            vk += d[u].x & kValueMask;
+                            vn += d[u].y;
+                        }
+                        found = found || (d[u].x >> 62) == 2;
                     }
-                    if (!done_n) {
-                        const uint32_t pm = __ballot_sync(0xFFFFFFFFu, (dn >> 62) == 2);
-                        const int first = pm ? __ffs(pm) - 1 : 31;
-                        unsigned long long v = (lane <= first) ? (dn & kValueMask) : 0ull;
+                    const uint32_t pm = __ballot_sync(0xFFFFFFFFu, found);
+                    const int first = pm ? __ffs(pm) - 1 : 31;
+                    if (lane > first) vk = vn = 0;
 #pragma unroll
-                        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
-                        pre_nal += v;
-                        done_n = pm != 0;
+                    for (int dd = 16; dd; dd >>= 1) {
+                        vk += __shfl_xor_sync(0xFFFFFFFFu, vk, dd);
+                        vn += __shfl_xor_sync(0xFFFFFFFFu, vn, dd);
                     }
+                    pre_kept += vk;
+                    pre_nal += vn;
+                    done = pm != 0;
                 }
             }
             if (lane == 0) {
-                st_relaxed(&a.desc_kept[tile], kStatusPrefix | (pre_kept + agg_kept));
-                st_relaxed(&a.desc_nal[tile], kStatusPrefix | (pre_nal + agg_nal));
+                st_desc(&a.desc[tile], kStatusPrefix | (pre_kept + agg_kept), pre_nal + agg_nal);
                 sm.tile_kept_prefix = pre_kept;
                 sm.tile_nal_prefix = pre_nal;
+                sm.tile_total = total;
                 if (tile == a.n_tiles - 1) {
                     a.hdr->total_kept = pre_kept + agg_kept;
                     a.hdr->total_sc = pre_nal + agg_nal;
@@ -403,6 +379,7 @@ __global__ void __launch_bounds__(kThreads, 5) annexb_scan_kernel(ScanArgs a) {
         __syncthreads();
         const uint64_t gout = sm.tile_kept_prefix;  // global output offset of this tile's first kept byte
         const uint64_t nal0 = sm.tile_nal_prefix;
+        const uint32_t tile_kept = sm.tile_total & 0xFFFFu;
 
         // ---------------------------------------------------------------- store rows + NAL index
 #pragma unroll
@@ -414,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 5) annexb_scan_kernel(ScanArgs a) {
             if (len) {
                 const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
                 const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                store_row_shifted(a.out, o, len, w, lane);
+                store_row(a.out, o, len, w, lane, r * 8 + warp, rowoff & 0xFFFFu, tile_kept, tile_in, sm.row_tot);
             }
             uint32_t sc = ks[r] >> 16;
             if (sc) {  // NAL index entries for the start codes that end in this granule
@@ -673,8 +650,7 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     a.n = n;
     a.out = d_rbsp;
     a.hdr = (ScanScratchHeader *)s;
-    a.desc_kept = (unsigned long long *)(s + o_desc);
-    a.desc_nal = a.desc_kept + n_tiles;
+    a.desc = (ulonglong2 *)(s + o_desc);
     a.nal_start = (unsigned long long *)(s + o_start);
     a.nal_rbsp_off = (unsigned long long *)(s + o_roff);
     a.nal_hdr = (uint32_t *)(s + o_hdr);
@@ -682,7 +658,7 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     a.n_tiles = (uint32_t)n_tiles;
 
     const int init_blocks = (int)((2 * n_tiles + 255) / 256 < 1 ? 1 : ((2 * n_tiles + 255) / 256 > 1184 ? 1184 : (2 * n_tiles + 255) / 256));
-    scan_init_kernel<<<init_blocks, 256, 0, ctx->stream>>>(a.hdr, a.desc_kept, 2 * n_tiles, n);
+    scan_init_kernel<<<init_blocks, 256, 0, ctx->stream>>>(a.hdr, (unsigned long long *)a.desc, 2 * n_tiles, n);
     H264B_LAUNCH_CHECK(ctx, "scan_init_kernel");
     if (n_tiles) {
         const uint64_t chunks = (n + 4095) / 4096;

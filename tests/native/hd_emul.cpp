@@ -86,6 +86,107 @@ int64_t emul_stream(const uint8_t *s, int64_t n, uint64_t *nal_start, uint64_t *
 
 uint32_t emul_header_bytes(uint32_t b0, uint32_t b1) { return nal_header_bytes(b0, b1); }
 
+// Tile-by-tile emulation of annexb_scan_kernel (same phases, same helper functions; warps and lanes as loops, the
+// look-back replaced by a running prefix).  `out` must hold n + 64 bytes and is pre-filled by the caller so that
+// stray writes are detectable.  Returns total kept bytes.
+int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out, int64_t out_align) {
+    const int kThreads = 256, kRows = 4, kGran = kThreads * kRows, kTile = kGran * 16, kHalo = 16;
+    auto gets = [&](int64_t p) -> uint32_t { return (p >= 0 && p < n) ? s[p] : 0xFFu; };
+    int64_t e0 = n;
+    for (int64_t p = 3; p < n; p++)
+        if (s[p] == 1 && s[p - 1] == 0 && s[p - 2] == 0 && s[p - 3] == 0) {
+            e0 = p + 1;
+            break;
+        }
+    const int64_t n_tiles = (n + kTile - 1) / kTile;
+    uint64_t gout = (uint64_t)out_align;  // emulate an arbitrary destination phase
+    std::vector<uint8_t> buf(kHalo + kTile + kHalo);
+    std::vector<uint16_t> scb(kGran + 2);
+    for (int64_t tile = 0; tile < n_tiles; tile++) {
+        const int64_t base = tile * kTile;
+        for (int i = 0; i < kHalo + kTile + kHalo; i++) buf[i] = (uint8_t)gets(base - kHalo + i);
+        uint8_t *tile_in = buf.data() + kHalo;
+        std::vector<uint32_t> em(kGran), ks(kGran), incl(kGran), packed(kGran);
+        auto masks_at = [&](int gi, bool have_prev) {
+            uint32_t w[4];
+            memcpy(w, tile_in + gi * 16, 16);
+            uint32_t prev = 0xFFFFFFFFu;
+            if (have_prev) memcpy(&prev, tile_in + gi * 16 - 4, 4);
+            return granule_masks(w, prev);
+        };
+        for (int gi = 0; gi < kGran; gi++) {
+            GranuleMasks m = masks_at(gi, true);
+            em[gi] = m.e | (m.sc << 16);
+            scb[gi + 1] = (uint16_t)m.sc;
+        }
+        scb[0] = (uint16_t)masks_at(-1, false).sc;
+        scb[kGran + 1] = (uint16_t)masks_at(kGran, true).sc;
+        auto get = [&](int64_t p) -> uint32_t { return tile_in[p - base]; };
+        uint32_t row_tot[32];
+        uint32_t dirty[32];
+        for (int r = 0; r < kRows; r++)
+            for (int warp = 0; warp < 8; warp++) {
+                uint32_t run = 0;
+                bool clean = true;
+                for (int lane = 0; lane < 32; lane++) {
+                    const int gi = r * kThreads + warp * 32 + lane;
+                    const int64_t gpos = base + (int64_t)gi * 16;
+                    uint32_t k16 = ~em[gi] & 0xFFFFu;
+                    const uint32_t near = ((uint32_t)scb[gi] >> 10) | scb[gi + 1] | (scb[gi + 2] & 1u);
+                    if (near) k16 = keep_mask_near_sc(get, gpos, em[gi] & 0xFFFFu, scb[gi], scb[gi + 1], scb[gi + 2]);
+                    uint32_t sc = em[gi] >> 16;
+                    if (base < e0) {
+                        if (gpos + 16 <= e0) k16 = 0;
+                        else if (gpos < e0) k16 &= ~((1u << (uint32_t)(e0 - gpos)) - 1u);
+                    }
+                    if (base + kTile > n) {
+                        if (gpos >= n) { k16 = 0; sc = 0; }
+                        else if (gpos + 16 > n) { uint32_t v = (1u << (uint32_t)(n - gpos)) - 1u; k16 &= v; sc &= v; }
+                    }
+                    ks[gi] = k16 | (sc << 16);
+                    packed[gi] = __builtin_popcount(k16) | (__builtin_popcount(sc) << 16);
+                    if (packed[gi] != 16u) clean = false;
+                    run += packed[gi];
+                    incl[gi] = run;
+                }
+                if (clean)
+                    for (int lane = 0; lane < 32; lane++) incl[r * kThreads + warp * 32 + lane] = 16u * (lane + 1);
+                row_tot[r * 8 + warp] = incl[r * kThreads + warp * 32 + 31];
+                dirty[r * 8 + warp] = !clean;
+            }
+        uint32_t total = 0, excl[32];
+        for (int t = 0; t < 32; t++) { excl[t] = total; total += row_tot[t]; }
+        // in-place compaction of dirty rows
+        for (int t = 0; t < 32; t++) {
+            if (!dirty[t]) continue;
+            const int r = t / 8, warp = t % 8;
+            uint32_t w[32][4];
+            for (int lane = 0; lane < 32; lane++) memcpy(w[lane], tile_in + (r * kThreads + warp * 32 + lane) * 16, 16);
+            uint8_t *row = tile_in + 512 * t;
+            for (int lane = 0; lane < 32; lane++) {
+                const int gi = r * kThreads + warp * 32 + lane;
+                const uint32_t k16 = ks[gi] & 0xFFFFu;
+                uint32_t loff = (incl[gi] & 0xFFFFu) - __builtin_popcount(k16);
+                for (int j = 0; j < 16; j++)
+                    if (k16 & (1u << j)) row[loff++] = (uint8_t)(w[lane][j >> 2] >> ((j & 3) * 8));
+            }
+        }
+        const uint32_t K = total & 0xFFFFu;
+        for (int t = 0; t < 32; t++) {
+            const int r = t / 8, warp = t % 8;
+            const uint32_t len = incl[r * kThreads + warp * 32 + 31] & 0xFFFFu;
+            if (!len) continue;
+            const uint64_t o = gout + (excl[t] & 0xFFFFu);
+            uint32_t w[32][4];
+            for (int lane = 0; lane < 32; lane++) memcpy(w[lane], tile_in + (512 * t + lane * 16), 16);
+            for (int lane = 0; lane < 32; lane++)
+                store_row_lane(out, o, len, lane ? w[lane - 1] : w[0], w[lane], lane, t, excl[t] & 0xFFFFu, K, tile_in, excl);
+        }
+        gout += K;
+    }
+    return (int64_t)(gout - (uint64_t)out_align);
+}
+
 // NewNalUnit on one frame with keep_byte_frame; returns rbsp length
 int64_t emul_frame(const uint8_t *f, int64_t N, uint8_t *rbsp) {
     auto get = [&](int64_t p) -> uint32_t { return (p >= 0 && p < N) ? f[p] : 0xFFu; };

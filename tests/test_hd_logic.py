@@ -35,6 +35,8 @@ def emul():
     L.emul_stream.restype = C.c_int64
     L.emul_stream.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                               C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.emul_stream_tiles.restype = C.c_int64
+    L.emul_stream_tiles.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
     L.emul_frame.restype = C.c_int64
     L.emul_frame.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     L.emul_cabac.restype = None
@@ -59,6 +61,14 @@ def run_emul_stream(L, s):
 def check_stream(L, s):
     K, st, ro, hd, rb, e0, mism = run_emul_stream(L, s)
     nal, rbsp = orc.read_nal_units_arrays(s)
+    # the kernel's tile pipeline (in-place compaction + aligned row stores), at two destination phases
+    s8 = np.ascontiguousarray(s, dtype=np.uint8)
+    for align in (0, 5):
+        out = np.full(len(s8) + 96, 0xEE, np.uint8)
+        tot = L.emul_stream_tiles(s8.ctypes.data, len(s8), out.ctypes.data, align)
+        assert tot >= len(rbsp)
+        assert np.array_equal(out[align:align + len(rbsp)], rbsp), "tile pipeline bytes differ (align %d)" % align
+        assert np.all(out[:align] == 0xEE) and np.all(out[align + tot:] == 0xEE), "stray writes"
     assert mism == 0
     assert max(K, 1) - 1 == len(nal["start"])
     n = len(nal["start"])
@@ -94,7 +104,7 @@ def random_stream(rng, n, p_zero, p_sc, ext_types=False):
 @pytest.mark.parametrize("seed", range(6))
 def test_local_split_strip_matches_oracle_random(emul, seed):
     rng = np.random.default_rng(seed)
-    for n in [0, 1, 3, 4, 5, 15, 16, 17, 31, 33, 100, 1000, 5000]:
+    for n in [0, 1, 3, 4, 5, 15, 16, 17, 31, 33, 100, 1000, 5000, 16383, 16385, 40000]:
         for p_zero, p_sc in [(0.5, 0.02), (0.2, 0.05), (0.9, 0.01), (0.05, 0.002)]:
             check_stream(emul, random_stream(rng, n, p_zero, p_sc, ext_types=(seed % 2 == 0)))
 

@@ -55,35 +55,37 @@ def main():
         print("  stall samples (pc sampling):")
         for h, v in sorted(st, key=lambda x: -x[1])[:10]:
             print("    %-40s %8.0f  %5.1f%%" % (h.replace("smsp__pcsamp_warps_issue_stalled_", ""), v, 100 * v / tot))
-    # source page: hottest lines
-    src = run(["-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + (["-k", "regex:" + filt] if filt else []))
-    try:
-        rd = list(csv.reader(io.StringIO(src)))
-        h = None
-        for i, r in enumerate(rd):
-            if "Source" in r and any("Sampl" in c for c in r):
-                h = i
-                break
-        if h is not None:
-            hd = rd[h]
-            si = hd.index("Source")
-            ci = [j for j, c in enumerate(hd) if c.startswith("# Samples") or c == "Warp Stall Sampling (All Samples)"]
-            ii = [j for j, c in enumerate(hd) if c == "Instructions Executed"]
-            agg = defaultdict(lambda: [0.0, 0.0])
-            for r in rd[h + 1:]:
-                if len(r) <= si:
-                    continue
-                s = num(r[ci[0]]) if ci else None
-                e = num(r[ii[0]]) if ii else None
-                agg[r[si].strip()][0] += s or 0
-                agg[r[si].strip()][1] += e or 0
-            tot = sum(v[0] for v in agg.values()) or 1
-            print("=" * 100)
-            print("hottest source lines by stall samples (first kernel instance matching %r):" % filt)
-            for k, v in sorted(agg.items(), key=lambda x: -x[1][0])[:40]:
-                print("  %6.1f%%  inst=%12.0f  %s" % (100 * v[0] / tot, v[1], k[:150]))
-    except Exception as e:  # the source page layout differs between ncu versions
-        print("source page not parsed:", e)
+    # source page: hottest source lines (per-file sections; rows with a line number carry the per-line aggregates)
+    src = run(["-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] +
+              (["-k", "regex:" + filt] if filt else []))
+    agg = {}
+    cur, hd = "", None
+    for r in csv.reader(io.StringIO(src)):
+        if not r:
+            continue
+        if r[0] == "File Path":
+            cur = r[1].split("/")[-1]
+        elif r[0] == "Line No":
+            hd = r
+        elif hd and r[0].isdigit():
+            try:
+                si, ii, ti = hd.index("# Samples"), hd.index("Instructions Executed"), hd.index("Thread Instructions Executed")
+                bi = hd.index("stall_barrier")
+                key = (cur, int(r[0]), r[1].strip())
+                v = agg.setdefault(key, [0.0, 0.0, 0.0, 0.0])
+                v[0] += num(r[si]) or 0
+                v[1] += num(r[ii]) or 0
+                v[2] += num(r[ti]) or 0
+                v[3] += num(r[bi]) or 0
+            except Exception:
+                pass
+    tot = sum(v[0] for v in agg.values()) or 1
+    toti = sum(v[1] for v in agg.values()) or 1
+    print("=" * 100)
+    print("hottest source lines (%% of stall samples | %% of warp instructions | avg active threads | barrier samples):")
+    for k, v in sorted(agg.items(), key=lambda x: -x[1][0])[:45]:
+        print("  %5.1f%% %5.1f%% %5.1f %6.0f  %s:%d  %s" % (100 * v[0] / tot, 100 * v[1] / toti, v[2] / v[1] if v[1] else 0,
+                                                  v[3], k[0], k[1], k[2][:110]))
 
 
 if __name__ == "__main__":
