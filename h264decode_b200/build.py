@@ -28,28 +28,31 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(force=False, verbose=False, extra=()):
-    if not force and up_to_date():
+def build(force=False, verbose=False, extra=(), out=None):
+    """out: alternative output path (experiment builds with extra -D flags; always rebuilt)"""
+    if out is None and not force and up_to_date():
         return LIB
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    objdir = os.path.join(HERE, "build" if out is None else "build_" + os.path.basename(out))
+    os.makedirs(objdir, exist_ok=True)
     for s in SOURCES:
-        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+        o = os.path.join(objdir, s.replace(".cu", ".o"))
         cmd = [nvcc()] + NVCC_FLAGS + list(extra) + ["-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             print(" ".join(cmd))
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     for s, p in procs:
-        out, _ = p.communicate()
-        if out.strip() and (verbose or p.returncode):
-            print(out)
+        log, _ = p.communicate()
+        if log.strip() and (verbose or p.returncode):
+            print(log)
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % s)
-    cmd = [nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    target = LIB if out is None else out
+    cmd = [nvcc(), "-shared", "-o", target] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

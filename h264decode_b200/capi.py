@@ -210,7 +210,8 @@ class Context:
 
     # ---- Annex-B
     def annexb_scan(self, stream, flags=0, want_rbsp=True, want_ext=True):
-        """-> (summary dict, nals[NAL_DTYPE], ext[NAL_EXT_DTYPE] | None, rbsp uint8[] | None)"""
+        """-> (summary dict, nals[NAL_DTYPE], ext[NAL_EXT_DTYPE] | None, rbsp uint8[len(stream)] | None);
+        the RBSP of NAL k is rbsp[nals[k].rbsp_off : nals[k].rbsp_off + nals[k].rbsp_len]"""
         s = np.ascontiguousarray(stream, dtype=np.uint8)
         nals, ext, rbsp, drbsp = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
         summ = ScanSummary()
@@ -220,7 +221,7 @@ class Context:
         n = summ.n_nals
         out_n = _from_ptr(nals.value, NAL_DTYPE, n)
         out_e = _from_ptr(ext.value, NAL_EXT_DTYPE, n) if want_ext else None
-        out_r = _from_ptr(rbsp.value, np.uint8, summ.rbsp_bytes) if want_rbsp else None
+        out_r = _from_ptr(rbsp.value, np.uint8, len(s) if n else 0) if want_rbsp else None
         d = summ.as_dict()
         d["d_rbsp"] = drbsp.value
         return d, out_n, out_e, out_r

@@ -15,6 +15,7 @@
 // Everything here is __host__ __device__ so that tests/ can run the exact same predicates on the CPU against the
 // oracle's sequential restatement.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #ifndef H264B_HD
@@ -26,6 +27,14 @@
 #endif
 
 namespace h264b {
+
+#if defined(__CUDA_ARCH__)
+H264B_HD uint32_t bits_popc(uint32_t x) { return (uint32_t)__popc(x); }
+H264B_HD int bits_msb(uint32_t x) { return 31 - __clz((int)x); }  // x != 0
+#else
+H264B_HD uint32_t bits_popc(uint32_t x) { return (uint32_t)__builtin_popcount(x); }
+H264B_HD int bits_msb(uint32_t x) { return 31 - __builtin_clz(x); }
+#endif
 
 // NAL header length from the first two NAL bytes (nalUnit.go:79,86-103)
 H264B_HD uint32_t nal_header_bytes(uint32_t b0, uint32_t b1) {
@@ -120,9 +129,11 @@ H264B_HD GranuleMasks granule_masks(const uint32_t w[4], uint32_t prev) {
 //   e16      raw emulation-prevention mask of the granule (granule_masks().e)
 //   sc_prev / sc_own / sc_next   start-code-end masks of the previous, this and the next granule
 //   get(p)   stream byte accessor, used only for the (at most two) header bytes of each NAL that starts in reach
+//   *epb_eff receives the emulation-prevention bytes that are really removed (raw candidates minus those whose zeros
+//   belong to a NAL header)
 template <class Get>
 H264B_HD uint32_t keep_mask_near_sc(const Get& get, int64_t gpos, uint32_t e16, uint32_t sc_prev, uint32_t sc_own,
-                                    uint32_t sc_next) {
+                                    uint32_t sc_next, uint32_t *epb_eff) {
     // bit (16 + j) of these 64-bit masks <-> stream position gpos + j, j in [-16, 32)
     const uint64_t S = (uint64_t)(sc_prev & 0xFFFFu) | ((uint64_t)(sc_own & 0xFFFFu) << 16) |
                        ((uint64_t)(sc_next & 0xFFFFu) << 32);
@@ -142,8 +153,30 @@ H264B_HD uint32_t keep_mask_near_sc(const Get& get, int64_t gpos, uint32_t e16, 
         no_epb |= ((1ull << (H + 2u)) - 1ull) << (b + 1);  // a 03 at a .. a+H+1 has a header byte among its zeros (A7)
     }
     const uint32_t d16 = (uint32_t)(drop >> 16) & 0xFFFFu, n16 = (uint32_t)(no_epb >> 16) & 0xFFFFu;
+    *epb_eff = e16 & ~n16 & ~d16;
     return ~(d16 | (e16 & ~n16)) & 0xFFFFu;
 }
+
+// ---- segmented EPB count ("how far has this NAL's RBSP shifted left so far") ----------------------------------
+// The RBSP of a NAL is written at the NAL's own position in the output buffer: a kept byte at stream position p goes
+// to out[p - c(p)], c(p) = emulation-prevention bytes removed in p's NAL before p.  c restarts at every NAL start, so
+// it is a SEGMENTED running count; an element of the scan is packed in 32 bits:
+//   bit 31      the span contains a NAL start (the count below is then "since the last start in the span")
+//   bits 28:16  start codes in the span (for NAL numbering; <= 4096 per 16 KiB tile)
+//   bits 14:0   EPBs removed (<= 16384 per tile)
+H264B_HD uint32_t seg_combine(uint32_t a, uint32_t b) {  // a = earlier span, b = later span
+    const uint32_t val = ((b >> 31) ? 0u : (a & 0x7FFFu)) + (b & 0x7FFFu);
+    return ((a | b) & 0x80000000u) | ((a + b) & 0x1FFF0000u) | val;
+}
+// element of one granule: ee = effective EPB mask, sc = start-code-end mask
+H264B_HD uint32_t seg_element(uint32_t ee, uint32_t sc) {
+    if (!sc) return bits_popc(ee);
+    const int last = bits_msb(sc);  // bit of the last start-code end; the new NAL starts just above it
+    const uint32_t above = last >= 15 ? 0u : (ee >> (last + 1));
+    return 0x80000000u | (bits_popc(sc) << 16) | bits_popc(above);
+}
+// count carried into a span whose exclusive prefix (inside the tile) is `pre`, given the tile's carry-in
+H264B_HD uint32_t seg_apply(uint32_t pre, uint32_t carry_in) { return (pre >> 31) ? (pre & 0x7FFFu) : carry_in + (pre & 0x7FFFu); }
 
 #if defined(__CUDA_ARCH__)
 H264B_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
@@ -166,105 +199,104 @@ H264B_HD uint32_t granule_byte(const uint32_t y[4], int b) {
     return (((b & 8) ? hi : lo) >> ((b & 3) * 8)) & 0xFFu;
 }
 
-// Store row t of a tile (one lane's part; the kernel calls this for all 32 lanes of the row's warp) -- `len` (<= 512) contiguous bytes, lane l holding row bytes [16l, 16l+16) in w -- to
-// out[o .. o+len).  After the in-place compaction every row of the tile is a contiguous run in shared memory (row t at
-// tile_in + 512 t), and rows follow each other without gaps in the output, so:
-//   * lanes exchange neighbours' words by shuffle and each writes one ALIGNED 16-byte granule of the destination;
-//   * the granule that straddles the seam with the previous row is written once, by this row's lane 0, which fetches
-//     the previous row's last bytes from shared memory;
-//   * only the first ragged granule of a tile (its other bytes belong to the previous tile) and the last one (next
-//     tile) are written byte by byte.
-// rowoff[0..31] = exclusive kept-byte offsets of the tile's rows (low 16 bits), x_row = rowoff[t], K = tile total.
+// Store one row of a tile (one lane's part; the kernel calls this for all 32 lanes of the row's warp): `len`
+// (<= 512) contiguous bytes, lane l holding row bytes [16l, 16l+16) in w, to out[o .. o+len).
+//   * lanes exchange neighbours' words (wp = previous lane's granule) and each writes one ALIGNED 16-byte granule;
+//     when the row has not shifted (o is 16-byte aligned, the usual case) that is a plain aligned copy;
+//   * prev_tail != nullptr: the previous row is contiguous with this one in the output and its bytes end at
+//     prev_tail (in the tile buffer): lane 0 completes the granule straddling the seam from there.  Otherwise this
+//     row's part of that granule is written byte by byte;
+//   * next_joins: the next row will complete the last, ragged granule; otherwise it is written byte by byte here.
 H264B_HD void store_row_lane(uint8_t *out, uint64_t o, uint32_t len, const uint32_t wp[4], const uint32_t w[4],
-                             int lane, int t, uint32_t x_row, uint32_t K, const uint8_t *tile_in,
-                             const uint32_t *rowoff) {
+                             int lane, const uint8_t *prev_tail, bool next_joins) {
     const uint32_t sb = (uint32_t)o & 15u;  // warp-uniform
-    uint32_t x[8];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        x[k] = wp[k];  // previous lane's granule (row bytes 16l-16 .. 16l-1); by shuffle on the device
-        x[4 + k] = w[k];
-    }
-    // this lane's output granule = row bytes [16l - sb, 16l - sb + 16) = bytes [16 - sb, 32 - sb) of x
-    const uint32_t off = 16u - sb, br8 = (off & 3u) * 8u;
     uint32_t y[4];
-    switch (off >> 2) {  // warp-uniform
-        case 0:
+    if (sb == 0) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) y[k] = funnel_r(x[k], x[k + 1], br8);
-            break;
-        case 1:
+        for (int k = 0; k < 4; k++) y[k] = w[k];
+    } else {
+        uint32_t x[8];
 #pragma unroll
-            for (int k = 0; k < 4; k++) y[k] = funnel_r(x[1 + k], x[2 + k], br8);
-            break;
-        case 2:
+        for (int k = 0; k < 4; k++) {
+            x[k] = wp[k];  // previous lane's granule (row bytes 16l-16 .. 16l-1); by shuffle on the device
+            x[4 + k] = w[k];
+        }
+        // this lane's output granule = row bytes [16l - sb, 16l - sb + 16) = bytes [16 - sb, 32 - sb) of x
+        const uint32_t off = 16u - sb, br8 = (off & 3u) * 8u;
+        switch (off >> 2) {  // warp-uniform
+            case 0:
 #pragma unroll
-            for (int k = 0; k < 4; k++) y[k] = funnel_r(x[2 + k], x[3 + k], br8);
-            break;
-        case 3:
+                for (int k = 0; k < 4; k++) y[k] = funnel_r(x[k], x[k + 1], br8);
+                break;
+            case 1:
 #pragma unroll
-            for (int k = 0; k < 4; k++) y[k] = funnel_r(x[3 + k], x[4 + k], br8);
-            break;
-        default:  // sb == 0: already aligned
+                for (int k = 0; k < 4; k++) y[k] = funnel_r(x[1 + k], x[2 + k], br8);
+                break;
+            case 2:
 #pragma unroll
-            for (int k = 0; k < 4; k++) y[k] = w[k];
-            break;
+                for (int k = 0; k < 4; k++) y[k] = funnel_r(x[2 + k], x[3 + k], br8);
+                break;
+            default:
+#pragma unroll
+                for (int k = 0; k < 4; k++) y[k] = funnel_r(x[3 + k], x[4 + k], br8);
+                break;
+        }
     }
     const int lo_b = 16 * lane - (int)sb;  // first row byte of this lane's output granule
     uint8_t *dst = out + (o - sb) + 16u * (uint32_t)lane;
     if (lo_b >= 0 && lo_b + 16 <= (int)len) {
         store16(dst, y);
-    } else if (lane == 0 && sb != 0 && len >= 16u - sb) {
-        // seam granule: its first sb bytes are the sb output bytes before this row.  The ones that belong to this tile
-        // (tile-output coordinates x_row - have .. x_row - 1) are fetched from shared memory; any others are the
-        // previous tile's and are written by it.
-        const uint32_t have = x_row < sb ? x_row : sb;  // how many of the sb bytes this tile holds
-        const uint32_t plen = t > 0 ? ((x_row - rowoff[t - 1]) & 0xFFFFu) : 0u;
-        uint32_t z[4] = {0u, 0u, 0u, 0u};
-        if (have == sb && plen >= sb) {  // usual case: all of them are the tail of row t-1
-            const uint32_t addr = 512u * (uint32_t)(t - 1) + plen - sb;  // byte offset in the tile buffer
-            const uint32_t *p = reinterpret_cast<const uint32_t *>(tile_in + (addr & ~3u));
+    } else if (lane == 0 && sb != 0) {  // seam granule (len >= 16 always holds for these rows)
+        if (prev_tail) {
+            const uint32_t addr = (uint32_t)(uintptr_t)(prev_tail - sb);  // only its low 2 bits matter below
+            const uint32_t *p = reinterpret_cast<const uint32_t *>((uintptr_t)(prev_tail - sb) & ~(uintptr_t)3);
             const uint32_t s8 = (addr & 3u) * 8u;
             const uint32_t q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3], q4 = p[4];
-            z[0] = funnel_r(q0, q1, s8);
-            z[1] = funnel_r(q1, q2, s8);
-            z[2] = funnel_r(q2, q3, s8);
-            z[3] = funnel_r(q3, q4, s8);
-        } else {  // rare: tiny rows in between and / or the tile's first bytes; walk back byte by byte
-            int tt = t - 1;
-            for (int b = (int)sb - 1; b >= (int)(sb - have); b--) {
-                const uint32_t xo = x_row - sb + (uint32_t)b;  // tile-output coordinate of this byte
-                while (tt > 0 && (rowoff[tt] & 0xFFFFu) > xo) tt--;
-                const uint32_t v = tile_in[512 * tt + (int)(xo - (rowoff[tt] & 0xFFFFu))];
-                const uint32_t sh = (uint32_t)(b & 3) * 8u;
-                if (b < 4) z[0] |= v << sh; else if (b < 8) z[1] |= v << sh;
-                else if (b < 12) z[2] |= v << sh; else z[3] |= v << sh;
-            }
-        }
-        uint32_t r4[4];
+            const uint32_t z[4] = {funnel_r(q0, q1, s8), funnel_r(q1, q2, s8), funnel_r(q2, q3, s8),
+                                   funnel_r(q3, q4, s8)};
+            uint32_t r4[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {  // bytes < sb from z, the rest from y
-            const int nb = (int)sb - 4 * k;
-            const uint32_t m = nb >= 4 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
-            r4[k] = (z[k] & m) | (y[k] & ~m);
-        }
-        if (have == sb) {
+            for (int k = 0; k < 4; k++) {  // bytes < sb from the previous row, the rest from this one
+                const int nb = (int)sb - 4 * k;
+                const uint32_t m = nb >= 4 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << (8 * nb)) - 1u));
+                r4[k] = (z[k] & m) | (y[k] & ~m);
+            }
             store16(dst, r4);
-        } else {  // first ragged granule of the tile
-            for (int b = (int)(sb - have); b < 16; b++) dst[b] = (uint8_t)granule_byte(r4, b);
+        } else {
+            for (int b = (int)sb; b < 16; b++) dst[b] = (uint8_t)granule_byte(y, b);
         }
     }
-    // the last ragged granule of the TILE (nothing after this row in the tile): bytes only
-    if (x_row + len == K && ((sb + len) & 15u) != 0) {
+    if (!next_joins && ((sb + len) & 15u) != 0) {  // last ragged granule, nobody else will complete it
         const uint32_t jt = (sb + len) >> 4, nb = (sb + len) & 15u;  // granule index in the row, valid bytes in it
         if (jt < 32u) {
             if ((uint32_t)lane == jt) {
                 const int b0 = lo_b < 0 ? -lo_b : 0;
                 for (int b = b0; b < (int)nb; b++) dst[b] = (uint8_t)granule_byte(y, b);
             }
-        } else if (lane == 31) {  // 33rd granule: the last sb bytes of lane 31's data
+        } else if (lane == 31) {  // 33rd granule: the last bytes of lane 31's data
             uint8_t *d2 = out + o + 496;
             for (uint32_t b = 16u - sb; b < 16u && 496u + b < len; b++) d2[b] = (uint8_t)granule_byte(w, (int)b);
+        }
+    }
+}
+
+// A row that contains NAL boundaries (or stream ends): one lane writes its granule's kept bytes one by one.
+//   c      EPB count of the open NAL at the granule's first byte
+//   k16 / ee / sc   keep, effective-EPB and start-code-end masks of the granule
+// on_start(j, c_end) is called for every start-code end at granule byte j with the EPB count of the NAL it ends.
+template <class OnStart>
+H264B_HD void store_granule_bytes(uint8_t *out, uint64_t gpos, const uint32_t w[4], uint32_t k16, uint32_t ee,
+                                  uint32_t sc, uint64_t c, const OnStart &on_start) {
+    for (int j = 0; j < 16; j++) {
+        const uint32_t bit = 1u << j;
+        if (ee & bit) {
+            c++;
+        } else if (k16 & bit) {
+            out[gpos + (uint64_t)j - c] = (uint8_t)granule_byte(w, j);
+        }
+        if (sc & bit) {
+            on_start(j, c);
+            c = 0;
         }
     }
 }

@@ -38,7 +38,7 @@ struct ScanScratchHeader {   // device scratch, zeroed / initialised by scan_ini
     unsigned int ticket;
     unsigned int pad;
     unsigned long long first_start;
-    unsigned long long total_sc;
+    unsigned long long total_sc;   // start codes found = slots handed out of the NAL record buffer
     unsigned long long total_kept;
     unsigned long long n_epb;
     unsigned long long reserved[3];
@@ -49,9 +49,17 @@ struct ScanArgs {
     uint64_t n;
     uint8_t *out;
     ScanScratchHeader *hdr;
-    ulonglong2 *desc;  // per tile: {status << 62 | kept bytes, start codes}
+    unsigned long long *desc;  // per tile: status << 62 | EPB carry of the NAL open at the tile's end
+    uint32_t *tile_nsc;        // per tile: start codes in it (0 unless written)
+    uint32_t *tile_slot;       // per tile: first slot of its records in the unordered record buffer
+    uint32_t *tile_ord;        // per tile: ordinal of its first start code (exclusive scan of tile_nsc)
+    // per start code, in slot order (tiles reserve slots with one atomicAdd): written by the main pass
+    unsigned long long *rec_start;
+    unsigned long long *rec_epb;
+    uint32_t *rec_hdr;
+    // the same in stream order (written by nal_permute_kernel, read by scan_finalize_kernel)
     unsigned long long *nal_start;
-    unsigned long long *nal_rbsp_off;
+    unsigned long long *nal_epb;  // [k]: EPBs removed from the NAL that ends at start code k
     uint32_t *nal_hdr;
     uint32_t nal_cap;
     uint32_t n_tiles;
@@ -79,6 +87,7 @@ __device__ __forceinline__ void st_desc(ulonglong2 *p, unsigned long long x, uns
 
 // ------------------------------------------------------------------------------------------------ init
 __global__ void scan_init_kernel(ScanScratchHeader *hdr, unsigned long long *desc, uint64_t n_desc, uint64_t n) {
+    // desc[0 .. n_desc) covers the tile descriptors and, right behind them, the per-tile start-code counts
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         hdr->ticket = 0;
@@ -118,23 +127,36 @@ __global__ void __launch_bounds__(256) first_start_kernel(const uint8_t *in, uin
 struct __align__(16) ScanSmem {
     uint8_t in[kInBytes];                 // [0,16): low halo, [16,16+kTile): tile, then high halo
     uint16_t scbits[kGranules + 2];       // start-code-end bits per granule, [0] = halo granule before the tile
-    uint32_t row_tot[kRows * 8];          // packed (kept | start codes << 16) per (row, warp); then exclusive offsets
-    unsigned long long tile_kept_prefix;  // exclusive prefixes of this tile
-    unsigned long long tile_nal_prefix;
+    uint32_t row_tot[kRows * 8];          // packed segmented elements per (row, warp); then exclusive prefixes
+    uint8_t row_class[kRows * 8];         // 0 untouched, 1 only EPBs removed, 2 contains NAL boundaries / stream ends
+    unsigned long long carry_in;          // EPBs already removed from the NAL that is open at the tile's first byte
+    unsigned long long nal_slot0;         // first record slot reserved for this tile's start codes
     uint32_t tile;
-    uint32_t tile_total;                  // packed total of this tile
     unsigned long long mbar;
 };
 
-// Device wrapper of store_row_lane (annexb_local.cuh): the previous lane's granule comes by shuffle.
 __device__ __forceinline__ void store_row(uint8_t *out, uint64_t o, uint32_t len, const uint32_t w[4], int lane,
-                                          int t, uint32_t x_row, uint32_t K, const uint8_t *tile_in,
-                                          const uint32_t *rowoff) {
+                                          const uint8_t *prev_tail, bool next_joins) {
     uint32_t wp[4];
+    if ((uint32_t)o & 15u) {  // warp-uniform: only shifted rows need the neighbour's bytes
 #pragma unroll
-    for (int k = 0; k < 4; k++) wp[k] = __shfl_up_sync(0xFFFFFFFFu, w[k], 1);
-    store_row_lane(out, o, len, wp, w, lane, t, x_row, K, tile_in, rowoff);
+        for (int k = 0; k < 4; k++) wp[k] = __shfl_up_sync(0xFFFFFFFFu, w[k], 1);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) wp[k] = 0;
+    }
+    store_row_lane(out, o, len, wp, w, lane, prev_tail, next_joins);
 }
+
+__device__ __forceinline__ uint32_t warp_seg_scan(uint32_t x, int lane) {  // inclusive segmented scan over the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane >= d) x = seg_combine(y, x);
+    }
+    return x;
+}
+
 
 __global__ void __launch_bounds__(kThreads, 5) annexb_scan_kernel(ScanArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -199,6 +221,9 @@ __global__ void __launch_bounds__(kThreads, 5) annexb_scan_kernel(ScanArgs a) {
             __syncthreads();  // the 0xFF fills above are plain stores other threads read
         }
         uint8_t *tile_in = sm.in + kHalo;  // tile_in[i] = s[base + i], valid for i in [-16, kTile+16)
+#ifdef H264B_EXP_LOADONLY
+        continue;
+#endif
 
         // ---------------------------------------------------------------- detect
         uint32_t em[kRows];  // raw EPB mask | start-code mask << 16
@@ -208,7 +233,13 @@ __global__ void __launch_bounds__(kThreads, 5) annexb_scan_kernel(ScanArgs a) {
             const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
             const uint32_t prev = *reinterpret_cast<const uint32_t *>(tile_in + gi * 16 - 4);
+#ifdef H264B_EXP_NODETECT
+            GranuleMasks m;
+            m.e = (w[0] == 0x12345678u && prev == 0x9ABCDEFu) ? 1u : 0u;
+            m.sc = 0;
+#else
             GranuleMasks m = granule_masks(w, prev);
+#endif
             em[r] = m.e | (m.sc << 16);
             sm.scbits[gi + 1] = (uint16_t)m.sc;
         }
@@ -221,198 +252,214 @@ __global__ void __launch_bounds__(kThreads, 5) annexb_scan_kernel(ScanArgs a) {
         }
         __syncthreads();
 
-        // ---------------------------------------------------------------- adjust + count + per-row scan
+        // ---------------------------------------------------------------- adjust + classify + per-row segmented scan
         const bool tile_has_head = base < e0;            // some bytes precede the first NAL
         const bool tile_has_end = base + kTile > a.n;    // some granules reach past the stream
         auto get = [&](int64_t p) -> uint32_t { return tile_in[p - (int64_t)base]; };
         uint32_t ks[kRows];    // keep mask | start-code mask << 16
-        uint32_t incl[kRows];  // inclusive packed scan (kept | start codes << 16) inside the (row, warp) group
-        uint32_t dirty = 0;    // warp-uniform bit per row: some granule of the row is not kept entirely
+        uint32_t ee[kRows];    // emulation-prevention bytes really removed
+        uint32_t incl[kRows];  // inclusive segmented scan inside the (row, warp) group
+        uint32_t cls = 0;      // 2 bits per row, warp-uniform
 #pragma unroll
         for (int r = 0; r < kRows; r++) {
             const int gi = r * kThreads + tid;
             const uint64_t gpos = base + (uint64_t)gi * 16;
-            uint32_t k16 = ~em[r] & 0xFFFFu;
+            uint32_t e16 = em[r] & 0xFFFFu;
+            uint32_t k16 = ~e16 & 0xFFFFu;
             // start-code ends q in [g-6, g+16] change what this granule keeps
             const uint32_t near = ((uint32_t)sm.scbits[gi] >> 10) | sm.scbits[gi + 1] | (sm.scbits[gi + 2] & 1u);
             if (near)  // rare: header bytes, the 2-byte tail rule and the EPB guard, all in the bit domain
-                k16 = keep_mask_near_sc(get, (int64_t)gpos, em[r] & 0xFFFFu, sm.scbits[gi], sm.scbits[gi + 1],
-                                        sm.scbits[gi + 2]);
+                k16 = keep_mask_near_sc(get, (int64_t)gpos, e16, sm.scbits[gi], sm.scbits[gi + 1], sm.scbits[gi + 2],
+                                        &e16);
             uint32_t sc = em[r] >> 16;
             if (tile_has_head) {
-                if (gpos + 16 <= e0)
+                if (gpos + 16 <= e0) {
                     k16 = 0;
-                else if (gpos < e0)
-                    k16 &= ~((1u << (uint32_t)(e0 - gpos)) - 1u);
+                    e16 = 0;
+                } else if (gpos < e0) {
+                    const uint32_t m = ~((1u << (uint32_t)(e0 - gpos)) - 1u);
+                    k16 &= m;
+                    e16 &= m;
+                }
             }
             if (tile_has_end) {
                 if (gpos >= a.n) {
                     k16 = 0;
                     sc = 0;
+                    e16 = 0;
                 } else if (gpos + 16 > a.n) {
-                    uint32_t valid = (1u << (uint32_t)(a.n - gpos)) - 1u;
+                    const uint32_t valid = (1u << (uint32_t)(a.n - gpos)) - 1u;
                     k16 &= valid;
                     sc &= valid;
+                    e16 &= valid;
                 }
             }
             ks[r] = k16 | (sc << 16);
-            const uint32_t packed = __popc(k16) | (__popc(sc) << 16);
+            ee[r] = e16;
             uint32_t x;
-            if (__all_sync(0xFFFFFFFFu, packed == 16u)) {  // the usual row: 512 bytes in, 512 bytes out
-                x = 16u * (uint32_t)(lane + 1);
+            if (__all_sync(0xFFFFFFFFu, k16 == 0xFFFFu)) {  // the usual row: nothing removed
+                x = 0;
+            } else if (__all_sync(0xFFFFFFFFu, (k16 | e16) == 0xFFFFu && sc == 0)) {  // only EPBs removed
+                cls |= 1u << (2 * r);
+                x = warp_seg_scan(bits_popc(e16), lane);
             } else {
-                dirty |= 1u << r;
-                x = packed;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-                    if (lane >= d) x += y;
-                }
+                cls |= 2u << (2 * r);
+                x = warp_seg_scan(seg_element(e16, sc), lane);
             }
             incl[r] = x;
-            if (lane == 31) sm.row_tot[r * 8 + warp] = x;
+            if (lane == 31) {
+                sm.row_tot[r * 8 + warp] = x;
+                sm.row_class[r * 8 + warp] = (uint8_t)((cls >> (2 * r)) & 3u);
+            }
         }
         __syncthreads();
 
-        // ---------------------------------------------------------------- tile prefix (warp 0) | in-place compaction
+        // ---------------------------------------------------------------- tile carry (warp 0) | in-place compaction
         if (warp == 0) {
-            uint32_t x = sm.row_tot[lane], own = x;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-                if (lane >= d) x += y;
-            }
-            sm.row_tot[lane] = x - own;  // exclusive
+            uint32_t x = sm.row_tot[lane];
+            const uint32_t own = x;
+            x = warp_seg_scan(x, lane);
+            uint32_t ex = __shfl_up_sync(0xFFFFFFFFu, x, 1);  // exclusive prefix of row `lane` inside the tile
+            if (lane == 0) ex = 0;
+            (void)own;
+            sm.row_tot[lane] = ex;
             const uint32_t total = __shfl_sync(0xFFFFFFFFu, x, 31);
-            const unsigned long long agg_kept = total & 0xFFFFu, agg_nal = total >> 16;
-            // ------------------------------------------------------------ decoupled look-back
-            // One 16-byte descriptor per tile {status<<62 | kept bytes, start codes}, written and read with single
-            // 128-bit accesses (the same single-transaction property CUB's tile-state words rely on).  Window of
-            // 32 x kLook predecessors per round (each lane inspects kLook consecutive tiles, nearest first): resident
-            // tiles tend to reach this point together, so the distance to the nearest published prefix is of the
-            // order of the number of resident CTAs, while a round costs one L2 round trip.
-            unsigned long long pre_kept = 0, pre_nal = 0;
+            const bool has_start = (total >> 31) != 0;
+            const unsigned long long t_val = total & 0x7FFFu, t_nsc = (total >> 16) & 0x1FFFu;
+            // ------------------------------------------------------------ short decoupled look-back
+            // One 64-bit descriptor per tile: status << 62 | EPB count.
+            //   status 1: "no NAL start in this tile: add my count and keep looking"
+            //   status 2: final EPB count of the NAL that is open at the tile's end.  A tile that contains a NAL start
+            //             publishes this at once, without looking back, so the chain only runs back to the nearest
+            //             tile holding a NAL start: a few tiles for real streams, never the whole resident cohort.
+            // NAL numbering needs no chain at all: the tile reserves nsc slots of the (unordered) record buffer with
+            // one atomicAdd and leaves its count for the post-pass that orders the records.
+            unsigned long long carry = 0;
+            if (lane == 0 && t_nsc) {
+                sm.nal_slot0 = atomicAdd(&a.hdr->total_sc, t_nsc);
+                a.tile_nsc[tile] = (uint32_t)t_nsc;
+                a.tile_slot[tile] = (uint32_t)sm.nal_slot0;
+            }
+#ifdef H264B_EXP_NOLOOKBACK
+            if (false) {
+#else
             if (tile > 0) {
-                if (lane == 0) st_desc(&a.desc[tile], kStatusAgg | agg_kept, agg_nal);
+#endif
+                if (lane == 0) st_relaxed(&a.desc[tile], ((has_start ? 2ull : 1ull) << 62) | t_val);
                 bool done = false;
                 for (int64_t j = (int64_t)tile - 1; !done; j -= 32 * kLook) {
                     const int64_t first_idx = j - (int64_t)lane * kLook;  // this lane: first_idx, first_idx-1, ...
-                    ulonglong2 d[kLook];
+                    unsigned long long d[kLook];
                     bool pending;
-                    do {  // all 32 lanes poll together; positions before tile 0 count as a published prefix of 0
+                    do {  // all 32 lanes poll together; positions before tile 0 count as final 0
                         pending = false;
                         bool seen = false;
 #pragma unroll
                         for (int u = 0; u < kLook; u++) {
                             const int64_t idx = first_idx - u;
-                            d[u] = idx >= 0 ? ld_desc(&a.desc[idx]) : make_ulonglong2(kStatusPrefix, 0ull);
+                            d[u] = idx >= 0 ? ld_relaxed(&a.desc[idx]) : (2ull << 62);
                         }
 #pragma unroll
-                        for (int u = 0; u < kLook; u++) {  // blocked only by an unpublished tile nearer than a prefix
-                            if (!seen && (d[u].x >> 62) == 0) pending = true;
-                            seen = seen || (d[u].x >> 62) == 2;
+                        for (int u = 0; u < kLook; u++) {  // blocked only by an unpublished tile nearer than a final one
+                            if (!seen && (d[u] >> 62) == 0) pending = true;
+                            seen = seen || (d[u] >> 62) == 2;
                         }
-                        // lanes farther back than a prefix found by a nearer lane do not matter
-                        const uint32_t pm = __ballot_sync(0xFFFFFFFFu, seen);
-                        if (pm & ((1u << lane) - 1u)) pending = false;
+                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, seen);
+                        if (m & ((1u << lane) - 1u)) pending = false;  // a nearer lane already found the end
                     } while (__any_sync(0xFFFFFFFFu, pending));
-                    unsigned long long vk = 0, vn = 0;
+                    unsigned long long v = 0;
                     bool found = false;
 #pragma unroll
                     for (int u = 0; u < kLook; u++) {
-                        if (!found) {
-                            vk += d[u].x & kValueMask;
-                            vn += d[u].y;
-                        }
-                        found = found || (d[u].x >> 62) == 2;
+                        if (!found) v += d[u] & kValueMask;
+                        found = found || (d[u] >> 62) == 2;
                     }
                     const uint32_t pm = __ballot_sync(0xFFFFFFFFu, found);
                     const int first = pm ? __ffs(pm) - 1 : 31;
-                    if (lane > first) vk = vn = 0;
+                    if (lane > first) v = 0;
 #pragma unroll
-                    for (int dd = 16; dd; dd >>= 1) {
-                        vk += __shfl_xor_sync(0xFFFFFFFFu, vk, dd);
-                        vn += __shfl_xor_sync(0xFFFFFFFFu, vn, dd);
-                    }
-                    pre_kept += vk;
-                    pre_nal += vn;
+                    for (int dd = 16; dd; dd >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, dd);
+                    carry += v;
                     done = pm != 0;
                 }
             }
             if (lane == 0) {
-                st_desc(&a.desc[tile], kStatusPrefix | (pre_kept + agg_kept), pre_nal + agg_nal);
-                sm.tile_kept_prefix = pre_kept;
-                sm.tile_nal_prefix = pre_nal;
-                sm.tile_total = total;
-                if (tile == a.n_tiles - 1) {
-                    a.hdr->total_kept = pre_kept + agg_kept;
-                    a.hdr->total_sc = pre_nal + agg_nal;
-                }
+                if (!has_start || tile == 0) st_relaxed(&a.desc[tile], (2ull << 62) | ((has_start ? t_val : carry + t_val) & kValueMask));
+                sm.carry_in = carry;
             }
         }
-        // Rows that lose bytes are compacted in place inside their own 512-byte span of the tile buffer (nobody else
-        // reads it any more), so that afterwards EVERY row is `len` contiguous bytes starting at its span.
-        if (dirty) {
+        // Rows that only lose emulation-prevention bytes are compacted in place inside their own 512-byte span of the
+        // tile buffer (nobody else reads it any more): afterwards they are `len` contiguous bytes like untouched rows.
 #pragma unroll
-            for (int r = 0; r < kRows; r++) {
-                if (!(dirty & (1u << r))) continue;  // warp-uniform
-                const int gi = r * kThreads + tid;
-                const uint32_t k16 = ks[r] & 0xFFFFu;
-                const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                __syncwarp();  // every lane has its bytes in registers before anyone overwrites the span
-                uint32_t loff = (incl[r] & 0xFFFFu) - __popc(k16);
-                uint8_t *row = tile_in + (r * kThreads + warp * 32) * 16;
-                if (k16 == 0xFFFFu && (loff & 3u) == 0) {
-                    uint32_t *d = reinterpret_cast<uint32_t *>(row + loff);
-                    d[0] = w[0];
-                    d[1] = w[1];
-                    d[2] = w[2];
-                    d[3] = w[3];
-                } else {
+        for (int r = 0; r < kRows; r++) {
+            if (((cls >> (2 * r)) & 3u) != 1u) continue;  // warp-uniform
+            const int gi = r * kThreads + tid;
+            const uint32_t k16 = ks[r] & 0xFFFFu;
+            const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            __syncwarp();  // every lane has its bytes in registers before anyone overwrites the span
+            uint32_t loff = 16u * (uint32_t)lane - (incl[r] - bits_popc(ee[r]));  // kept bytes of the lanes before
+            uint8_t *row = tile_in + (r * kThreads + warp * 32) * 16;
+            if (k16 == 0xFFFFu && (loff & 3u) == 0) {
+                uint32_t *d = reinterpret_cast<uint32_t *>(row + loff);
+                d[0] = w[0];
+                d[1] = w[1];
+                d[2] = w[2];
+                d[3] = w[3];
+            } else {
 #pragma unroll
-                    for (int j = 0; j < 16; j++)
-                        if (k16 & (1u << j)) row[loff++] = (uint8_t)(w[j >> 2] >> ((j & 3) * 8));
-                }
+                for (int j = 0; j < 16; j++)
+                    if (k16 & (1u << j)) row[loff++] = (uint8_t)(w[j >> 2] >> ((j & 3) * 8));
             }
         }
         __syncthreads();
-        const uint64_t gout = sm.tile_kept_prefix;  // global output offset of this tile's first kept byte
-        const uint64_t nal0 = sm.tile_nal_prefix;
-        const uint32_t tile_kept = sm.tile_total & 0xFFFFu;
+        const uint64_t carry_in = sm.carry_in;
+        const uint64_t slot0 = sm.nal_slot0;
 
         // ---------------------------------------------------------------- store rows + NAL index
+#ifdef H264B_EXP_NOSTORE
+        if (carry_in == 0x123456789ull)
+#endif
 #pragma unroll
         for (int r = 0; r < kRows; r++) {
             const int gi = r * kThreads + tid;
-            const uint32_t rowoff = sm.row_tot[r * 8 + warp];  // warp-uniform
-            const uint32_t len = __shfl_sync(0xFFFFFFFFu, incl[r], 31) & 0xFFFFu;
-            const uint64_t o = gout + (rowoff & 0xFFFFu);
-            if (len) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                store_row(a.out, o, len, w, lane, r * 8 + warp, rowoff & 0xFFFFu, tile_kept, tile_in, sm.row_tot);
-            }
-            uint32_t sc = ks[r] >> 16;
-            if (sc) {  // NAL index entries for the start codes that end in this granule
-                const uint32_t k16 = ks[r] & 0xFFFFu;
-                const uint32_t excl = incl[r] - (__popc(k16) | (__popc(sc) << 16));
-                uint64_t k = nal0 + (rowoff >> 16) + (excl >> 16);
-                while (sc) {
-                    const int j = __ffs(sc) - 1;
-                    sc &= sc - 1;
+            const int t = r * 8 + warp;
+            const uint32_t rowpre = sm.row_tot[t];  // warp-uniform
+            const uint32_t c2 = (cls >> (2 * r)) & 3u;
+            const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            if (c2 != 2u) {
+                // one contiguous run of len bytes, shifted left by the EPBs removed from its NAL so far
+                const uint64_t c_row = (rowpre >> 31) ? (uint64_t)(rowpre & 0x7FFFu) : carry_in + (rowpre & 0x7FFFu);
+                const uint32_t removed = __shfl_sync(0xFFFFFFFFu, incl[r], 31) & 0x7FFFu;
+                const uint64_t o = base + 512u * (uint32_t)t - c_row;
+                const uint8_t *prev_tail = nullptr;
+                if (t > 0 && sm.row_class[t - 1] != 2) {
+                    const uint32_t prev_removed = (rowpre - sm.row_tot[t - 1]) & 0x7FFFu;
+                    prev_tail = tile_in + 512 * t - prev_removed;
+                }
+                const bool next_joins = t < kRows * 8 - 1 && sm.row_class[t + 1] != 2;
+                store_row(a.out, o, 512u - removed, w, lane, prev_tail, next_joins);
+            } else {
+                uint32_t ex = __shfl_up_sync(0xFFFFFFFFu, incl[r], 1);
+                if (lane == 0) ex = 0;
+                const uint32_t pre = seg_combine(rowpre, ex);
+                const uint64_t c = (pre >> 31) ? (uint64_t)(pre & 0x7FFFu) : carry_in + (pre & 0x7FFFu);
+                const uint64_t gpos = base + (uint64_t)gi * 16;
+                uint64_t k = slot0 + ((pre >> 16) & 0x1FFFu);  // record slot of the first NAL that starts in this granule
+                store_granule_bytes(a.out, gpos, w, ks[r] & 0xFFFFu, ee[r], ks[r] >> 16, c, [&](int j, uint64_t c_end) {
                     if (k < a.nal_cap) {
-                        const uint64_t st = base + (uint64_t)(gi * 16 + j + 1);  // the NAL's first byte
-                        a.nal_start[k] = st;
-                        a.nal_rbsp_off[k] = o + (excl & 0xFFFFu) + __popc(k16 & ((1u << j) - 1u));
-                        uint32_t h = 0;  // its first 4 bytes, from the (L2-resident) input: the tile copy may be compacted
+                        const uint64_t st = gpos + (uint64_t)j + 1;  // the new NAL's first byte
+                        a.rec_start[k] = st;
+                        a.rec_epb[k] = c_end;  // EPBs removed from the NAL that ends with this start code
+                        uint32_t h = 0;  // its first 4 bytes, from the (L2-resident) input
 #pragma unroll
-                        for (int t = 0; t < 4; t++)
-                            h |= (uint32_t)(st + t < a.n ? a.in[st + t] : (uint8_t)0xFF) << (8 * t);
-                        a.nal_hdr[k] = h;
+                        for (int q = 0; q < 4; q++)
+                            h |= (uint32_t)(st + q < a.n ? a.in[st + q] : (uint8_t)0xFF) << (8 * q);
+                        a.rec_hdr[k] = h;
                     }
                     k++;
-                }
+                });
             }
         }
         // the loop-top __syncthreads orders these shared-memory reads before the next tile's writes
@@ -465,40 +512,96 @@ __device__ __forceinline__ void decode_nal_header(uint32_t hdr4, h264b_nal &o, h
     *ext = e;
 }
 
+// Post-pass 1: ordinal of every tile's first start code = exclusive scan of the per-tile counts (one CTA; the array
+// has one entry per 16 KiB of stream).
+__global__ void __launch_bounds__(1024) nal_order_kernel(const uint32_t *tile_nsc, uint32_t *tile_ord, uint32_t n_tiles) {
+    __shared__ unsigned long long warp_sum[32];
+    __shared__ unsigned long long running;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    const uint32_t per = (n_tiles + 1023u) / 1024u;  // contiguous entries per thread
+    const uint32_t lo = (uint32_t)tid * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
+    unsigned long long mine = 0;
+    for (uint32_t i = lo; i < hi; i++) mine += tile_nsc[i];
+    unsigned long long x = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = warp_sum[lane], own = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, w, d);
+            if (lane >= d) w += y;
+        }
+        warp_sum[lane] = w - own;
+    }
+    __syncthreads();
+    unsigned long long ord = warp_sum[warp] + x - mine;
+    for (uint32_t i = lo; i < hi; i++) {
+        tile_ord[i] = (uint32_t)ord;
+        ord += tile_nsc[i];
+    }
+}
+
+// Post-pass 2: move every tile's records from its reserved slots to their ordinals (stream order).
+__global__ void __launch_bounds__(256) nal_permute_kernel(ScanArgs a) {
+    const uint64_t cap = a.nal_cap;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < a.n_tiles; t += gridDim.x * blockDim.x) {
+        const uint32_t c = a.tile_nsc[t];
+        if (!c) continue;
+        const uint64_t slot = a.tile_slot[t], ord = a.tile_ord[t];
+        for (uint32_t i = 0; i < c; i++) {
+            if (slot + i < cap && ord + i < cap) {
+                a.nal_start[ord + i] = a.rec_start[slot + i];
+                a.nal_epb[ord + i] = a.rec_epb[slot + i];
+                a.nal_hdr[ord + i] = a.rec_hdr[slot + i];
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) scan_finalize_kernel(ScanArgs a, h264b_nal *nals, h264b_nal_ext *ext,
                                                              h264b_scan_summary *summary) {
     const uint64_t K = a.hdr->total_sc;
     const uint64_t n_nals = K ? K - 1 : 0;
     const uint64_t lim = n_nals < a.nal_cap ? n_nals : (a.nal_cap ? (uint64_t)a.nal_cap - 1 : 0);
-    unsigned long long epb = 0;
+    unsigned long long epb = 0, rbsp = 0;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < lim;
          k += (uint64_t)gridDim.x * blockDim.x) {
         h264b_nal o;
         o.start = a.nal_start[k];
-        o.rbsp_off = a.nal_rbsp_off[k];
         o.num_bytes = (uint32_t)(a.nal_start[k + 1] - o.start);
-        o.rbsp_len = (uint32_t)(a.nal_rbsp_off[k + 1] - o.rbsp_off);
         decode_nal_header(a.nal_hdr[k], o, ext ? &ext[k] : nullptr);
-        // body = NumBytes - HeaderBytes - 2 bytes (never negative in effect: a NAL shorter than that has no body)
+        // body = NumBytes - HeaderBytes - 2 bytes (a NAL shorter than that has no body); its RBSP sits at the body's
+        // own position in the output buffer
         const int64_t body = (int64_t)o.num_bytes - (int64_t)o.header_bytes - 2;
-        const uint32_t removed = (uint32_t)((body > 0 ? body : 0) - (int64_t)o.rbsp_len);
+        const uint32_t removed = (uint32_t)a.nal_epb[k + 1];
+        o.rbsp_off = o.start + o.header_bytes;
+        o.rbsp_len = (uint32_t)((body > 0 ? body : 0) - (int64_t)removed);
         o.flags = (removed ? H264B_F_HAS_EPB : 0u) | (o.num_bytes < 8 ? H264B_F_SHORT_NAL : 0u);
         epb += removed;
+        rbsp += o.rbsp_len;
         nals[k] = o;
     }
     if (epb) atomicAdd(&a.hdr->n_epb, epb);
+    if (rbsp) atomicAdd(&a.hdr->total_kept, rbsp);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         summary->n_start_codes = K;
         summary->n_nals = n_nals;
         summary->first_start = a.hdr->first_start;
-        // kept-byte prefix at the last start code = RBSP bytes of all emitted NAL units
-        summary->rbsp_bytes = (K && K - 1 < a.nal_cap) ? a.nal_rbsp_off[K - 1] : 0;
         summary->status = (K > a.nal_cap) ? H264B_E_CAPACITY : H264B_OK;
         summary->reserved = 0;
     }
 }
 __global__ void scan_summary_epb_kernel(const ScanScratchHeader *hdr, h264b_scan_summary *summary) {
     summary->n_epb = hdr->n_epb;
+    summary->rbsp_bytes = hdr->total_kept;  // RBSP bytes of all emitted NAL units
 }
 
 // ------------------------------------------------------------------------------------------------ frames (NewNalUnit)
@@ -613,19 +716,30 @@ __global__ void __launch_bounds__(1024) slice_select_kernel(const h264b_nal *nal
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-static uint64_t scratch_layout(uint64_t n, uint32_t nal_cap, uint64_t *o_desc, uint64_t *o_start, uint64_t *o_roff,
-                               uint64_t *o_hdr) {
+struct ScratchOffsets {
+    uint64_t desc, tile_nsc, tile_slot, tile_ord, rec_start, rec_epb, rec_hdr, nal_start, nal_epb, nal_hdr, total;
+};
+static ScratchOffsets scratch_layout(uint64_t n, uint32_t nal_cap) {
     const uint64_t n_tiles = (n + kTile - 1) / kTile;
-    uint64_t o = sizeof(ScanScratchHeader);
-    *o_desc = o;
-    o += 2 * n_tiles * 8;
-    *o_start = o;
-    o += (uint64_t)nal_cap * 8;
-    *o_roff = o;
-    o += (uint64_t)nal_cap * 8;
-    *o_hdr = o;
-    o += (uint64_t)nal_cap * 4;
-    return (o + 255) & ~255ull;
+    ScratchOffsets o;
+    uint64_t p = sizeof(ScanScratchHeader);
+    auto take = [&](uint64_t bytes) {
+        const uint64_t at = p;
+        p = (p + bytes + 15) & ~15ull;
+        return at;
+    };
+    o.desc = take(n_tiles * 8);
+    o.tile_nsc = take(n_tiles * 4);  // must directly follow desc: both are zeroed by scan_init_kernel in one sweep
+    o.tile_slot = take(n_tiles * 4);
+    o.tile_ord = take(n_tiles * 4);
+    o.rec_start = take((uint64_t)nal_cap * 8);
+    o.rec_epb = take((uint64_t)nal_cap * 8);
+    o.rec_hdr = take((uint64_t)nal_cap * 4);
+    o.nal_start = take((uint64_t)nal_cap * 8);
+    o.nal_epb = take((uint64_t)nal_cap * 8);
+    o.nal_hdr = take((uint64_t)nal_cap * 4);
+    o.total = (p + 255) & ~255ull;
+    return o;
 }
 
 int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint8_t *d_rbsp, h264b_nal *d_nals,
@@ -633,15 +747,17 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     (void)flags;
     if (((uintptr_t)d_stream & 15) || ((uintptr_t)d_rbsp & 15))
         return set_error(ctx, H264B_E_INVALID, "annexb_scan: d_stream and d_rbsp must be 16-byte aligned");
-    if (n >= (1ull << 46)) return set_error(ctx, H264B_E_INVALID, "annexb_scan: stream too long");
-    uint64_t o_desc, o_start, o_roff, o_hdr;
-    const uint64_t need = scratch_layout(n, nal_cap, &o_desc, &o_start, &o_roff, &o_hdr);
-    if (need > ctx->scan_scratch_bytes) {
-        if (ctx->scan_scratch) cudaFree(ctx->scan_scratch);
+    if (n >= (1ull << 45)) return set_error(ctx, H264B_E_INVALID, "annexb_scan: stream too long");
+    const ScratchOffsets so = scratch_layout(n, nal_cap);
+    if (so.total > ctx->scan_scratch_bytes) {
+        if (ctx->scan_scratch) {
+            H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->scan_scratch);
+        }
         ctx->scan_scratch = nullptr;
         ctx->scan_scratch_bytes = 0;
-        H264B_CUDA(ctx, cudaMalloc(&ctx->scan_scratch, need));
-        ctx->scan_scratch_bytes = need;
+        H264B_CUDA(ctx, cudaMalloc(&ctx->scan_scratch, so.total));
+        ctx->scan_scratch_bytes = so.total;
     }
     uint8_t *s = (uint8_t *)ctx->scan_scratch;
     const uint64_t n_tiles = (n + kTile - 1) / kTile;
@@ -650,15 +766,25 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     a.n = n;
     a.out = d_rbsp;
     a.hdr = (ScanScratchHeader *)s;
-    a.desc = (ulonglong2 *)(s + o_desc);
-    a.nal_start = (unsigned long long *)(s + o_start);
-    a.nal_rbsp_off = (unsigned long long *)(s + o_roff);
-    a.nal_hdr = (uint32_t *)(s + o_hdr);
+    a.desc = (unsigned long long *)(s + so.desc);
+    a.tile_nsc = (uint32_t *)(s + so.tile_nsc);
+    a.tile_slot = (uint32_t *)(s + so.tile_slot);
+    a.tile_ord = (uint32_t *)(s + so.tile_ord);
+    a.rec_start = (unsigned long long *)(s + so.rec_start);
+    a.rec_epb = (unsigned long long *)(s + so.rec_epb);
+    a.rec_hdr = (uint32_t *)(s + so.rec_hdr);
+    a.nal_start = (unsigned long long *)(s + so.nal_start);
+    a.nal_epb = (unsigned long long *)(s + so.nal_epb);
+    a.nal_hdr = (uint32_t *)(s + so.nal_hdr);
     a.nal_cap = nal_cap;
     a.n_tiles = (uint32_t)n_tiles;
 
-    const int init_blocks = (int)((2 * n_tiles + 255) / 256 < 1 ? 1 : ((2 * n_tiles + 255) / 256 > 1184 ? 1184 : (2 * n_tiles + 255) / 256));
-    scan_init_kernel<<<init_blocks, 256, 0, ctx->stream>>>(a.hdr, (unsigned long long *)a.desc, 2 * n_tiles, n);
+    // zero the descriptors and the per-tile counts (contiguous: [desc, tile_slot) in 8-byte words)
+    const uint64_t n_zero = (so.tile_slot - so.desc) / 8;
+    uint64_t ib = (n_zero + 255) / 256;
+    if (ib < 1) ib = 1;
+    if (ib > (uint64_t)ctx->sm_count * 8) ib = (uint64_t)ctx->sm_count * 8;
+    scan_init_kernel<<<(int)ib, 256, 0, ctx->stream>>>(a.hdr, a.desc, n_zero, n);
     H264B_LAUNCH_CHECK(ctx, "scan_init_kernel");
     if (n_tiles) {
         const uint64_t chunks = (n + 4095) / 4096;
@@ -680,6 +806,12 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
         if (grid > n_tiles) grid = n_tiles;
         annexb_scan_kernel<<<(int)grid, kThreads, smem, ctx->stream>>>(a);
         H264B_LAUNCH_CHECK(ctx, "annexb_scan_kernel");
+        nal_order_kernel<<<1, 1024, 0, ctx->stream>>>(a.tile_nsc, a.tile_ord, a.n_tiles);
+        H264B_LAUNCH_CHECK(ctx, "nal_order_kernel");
+        uint64_t pb = (n_tiles + 255) / 256;
+        if (pb > (uint64_t)ctx->sm_count * 8) pb = (uint64_t)ctx->sm_count * 8;
+        nal_permute_kernel<<<(int)pb, 256, 0, ctx->stream>>>(a);
+        H264B_LAUNCH_CHECK(ctx, "nal_permute_kernel");
     }
     int fin_blocks = ctx->sm_count * 2;
     scan_finalize_kernel<<<fin_blocks, 256, 0, ctx->stream>>>(a, d_nals, d_ext, d_summary);
@@ -710,7 +842,4 @@ int launch_slice_select(h264b_ctx *ctx, const h264b_nal *d_nals, const h264b_sca
 
 }  // namespace h264b
 
-extern "C" uint64_t h264b_annexb_scratch_bytes(uint64_t n) {
-    uint64_t a, b, c, d;
-    return h264b::scratch_layout(n, 0, &a, &b, &c, &d);
-}
+extern "C" uint64_t h264b_annexb_scratch_bytes(uint64_t n) { return h264b::scratch_layout(n, 0).total; }

@@ -272,10 +272,9 @@ int32_t h264b_annexb_scan(h264b_ctx *ctx, const uint8_t *stream, uint64_t n, uin
         if (nn)
             H264B_CUDA(ctx, cudaMemcpyAsync(h_ext, d_ext, nn * sizeof(h264b_nal_ext), cudaMemcpyDeviceToHost, ctx->stream));
     }
-    if (want_rbsp) {
-        RC(ensure_pin(ctx, 2, (size_t)summary->rbsp_bytes, &h_rbsp));
-        if (summary->rbsp_bytes)
-            H264B_CUDA(ctx, cudaMemcpyAsync(h_rbsp, d_rbsp, (size_t)summary->rbsp_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (want_rbsp) {  // position-preserving layout: the buffer is as long as the stream
+        RC(ensure_pin(ctx, 2, (size_t)n, &h_rbsp));
+        if (n && nn) H264B_CUDA(ctx, cudaMemcpyAsync(h_rbsp, d_rbsp, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     }
     H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (nals) *nals = (const h264b_nal *)h_nals;

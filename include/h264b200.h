@@ -82,7 +82,9 @@ int32_t h264b_launch_count(const h264b_ctx *ctx, uint64_t *count);
  */
 typedef struct {
     uint64_t start;       /* stream offset of the NAL's first byte (startOffset, server.go:88) */
-    uint64_t rbsp_off;    /* offset of its RBSP in the rbsp output buffer */
+    uint64_t rbsp_off;    /* offset of its RBSP in the rbsp output buffer (= start + header_bytes: the RBSP of a NAL
+                             is written at the position of the NAL's own body, so RBSPs never overlap and the buffer
+                             is as long as the stream; the bytes between two RBSPs are unspecified) */
     uint32_t num_bytes;   /* NalUnit.NumBytes (includes the following start code) */
     uint32_t rbsp_len;    /* len(NalUnit.rbsp) */
     uint8_t forbidden_zero_bit, ref_idc, type, header_bytes; /* nalUnit.go:82-84, :79,94,97,100 */
@@ -113,14 +115,16 @@ typedef struct {
 /* Bytes of device scratch h264b_annexb_scan_dev needs for an n-byte stream (the context owns and grows it). */
 uint64_t h264b_annexb_scratch_bytes(uint64_t n);
 
-/* Device-resident scan.  d_stream: n bytes, 16-byte aligned.  d_rbsp: 16-byte aligned, capacity >= n + 16.
+/* Device-resident scan.  d_stream: n bytes, 16-byte aligned (the 16-byte granule holding byte n-1 must be
+ * readable).  d_rbsp: 16-byte aligned, capacity >= n + 16.
  * d_nals: nal_cap records.  d_ext: nal_cap records or NULL.  d_summary: one record.  Asynchronous. */
 int32_t h264b_annexb_scan_dev(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint8_t *d_rbsp,
                               h264b_nal *d_nals, h264b_nal_ext *d_ext, uint32_t nal_cap,
                               h264b_scan_summary *d_summary, uint32_t flags);
 
 /* Host-buffer scan (the call a Go caller makes): copies the stream in, runs the kernels, copies the NAL index
- * and the RBSP bytes back into context-owned pinned buffers that stay valid until the next call on ctx.
+ * and the RBSP buffer (n bytes, indexed by h264b_nal.rbsp_off) back into context-owned pinned buffers that stay valid
+ * until the next call on ctx.
  * want_rbsp == 0 leaves the RBSP on the device (d_rbsp_out, if not NULL, receives its device address for a
  * following h264b_cabac_decode_dev). */
 int32_t h264b_annexb_scan(h264b_ctx *ctx, const uint8_t *stream, uint64_t n, uint32_t flags, int32_t want_rbsp,

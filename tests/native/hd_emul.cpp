@@ -51,7 +51,8 @@ int64_t emul_stream(const uint8_t *s, int64_t n, uint64_t *nal_start, uint64_t *
         for (int j = 0; j < 16; j++)
             if (keep_byte_stream(get, gpos + j)) exact |= 1u << j;
         if (near) {
-            k16 = keep_mask_near_sc(get, gpos, em[g + 1], sc[g], sc[g + 1], sc[g + 2]);
+            uint32_t ee_unused;
+            k16 = keep_mask_near_sc(get, gpos, em[g + 1], sc[g], sc[g + 1], sc[g + 2], &ee_unused);
             if (k16 != exact) mism++;
         } else if (k16 != exact) {
             mism++;
@@ -87,10 +88,14 @@ int64_t emul_stream(const uint8_t *s, int64_t n, uint64_t *nal_start, uint64_t *
 uint32_t emul_header_bytes(uint32_t b0, uint32_t b1) { return nal_header_bytes(b0, b1); }
 
 // Tile-by-tile emulation of annexb_scan_kernel (same phases, same helper functions; warps and lanes as loops, the
-// look-back replaced by a running prefix).  `out` must hold n + 64 bytes and is pre-filled by the caller so that
-// stray writes are detectable.  Returns total kept bytes.
-int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out, int64_t out_align) {
+// look-back replaced by a running carry).  RBSP bytes of a NAL land at the NAL body's own position in `out`
+// (position-preserving layout); `out` holds out_shift + n + 64 bytes, pre-filled by the caller so that stray writes
+// are detectable; out_shift (a multiple of 16 in the product) shifts the whole destination to exercise alignment.
+// nal_start / nal_epb / nal_hdr (cap entries) receive the per-start-code index.  Returns the number of start codes.
+int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out_base, int64_t out_shift, uint64_t *nal_start,
+                          uint64_t *nal_epb, uint32_t *nal_hdr, int64_t cap) {
     const int kThreads = 256, kRows = 4, kGran = kThreads * kRows, kTile = kGran * 16, kHalo = 16;
+    uint8_t *out = out_base + out_shift;
     auto gets = [&](int64_t p) -> uint32_t { return (p >= 0 && p < n) ? s[p] : 0xFFu; };
     int64_t e0 = n;
     for (int64_t p = 3; p < n; p++)
@@ -99,14 +104,14 @@ int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out, int64_t out
             break;
         }
     const int64_t n_tiles = (n + kTile - 1) / kTile;
-    uint64_t gout = (uint64_t)out_align;  // emulate an arbitrary destination phase
+    uint64_t carry = 0, nal0 = 0;  // what the look-back would deliver
     std::vector<uint8_t> buf(kHalo + kTile + kHalo);
     std::vector<uint16_t> scb(kGran + 2);
     for (int64_t tile = 0; tile < n_tiles; tile++) {
         const int64_t base = tile * kTile;
         for (int i = 0; i < kHalo + kTile + kHalo; i++) buf[i] = (uint8_t)gets(base - kHalo + i);
         uint8_t *tile_in = buf.data() + kHalo;
-        std::vector<uint32_t> em(kGran), ks(kGran), incl(kGran), packed(kGran);
+        std::vector<uint32_t> em(kGran), ks(kGran), ee(kGran), incl(kGran);
         auto masks_at = [&](int gi, bool have_prev) {
             uint32_t w[4];
             memcpy(w, tile_in + gi * 16, 16);
@@ -122,43 +127,46 @@ int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out, int64_t out
         scb[0] = (uint16_t)masks_at(-1, false).sc;
         scb[kGran + 1] = (uint16_t)masks_at(kGran, true).sc;
         auto get = [&](int64_t p) -> uint32_t { return tile_in[p - base]; };
-        uint32_t row_tot[32];
-        uint32_t dirty[32];
-        for (int r = 0; r < kRows; r++)
-            for (int warp = 0; warp < 8; warp++) {
-                uint32_t run = 0;
-                bool clean = true;
-                for (int lane = 0; lane < 32; lane++) {
-                    const int gi = r * kThreads + warp * 32 + lane;
-                    const int64_t gpos = base + (int64_t)gi * 16;
-                    uint32_t k16 = ~em[gi] & 0xFFFFu;
-                    const uint32_t near = ((uint32_t)scb[gi] >> 10) | scb[gi + 1] | (scb[gi + 2] & 1u);
-                    if (near) k16 = keep_mask_near_sc(get, gpos, em[gi] & 0xFFFFu, scb[gi], scb[gi + 1], scb[gi + 2]);
-                    uint32_t sc = em[gi] >> 16;
-                    if (base < e0) {
-                        if (gpos + 16 <= e0) k16 = 0;
-                        else if (gpos < e0) k16 &= ~((1u << (uint32_t)(e0 - gpos)) - 1u);
-                    }
-                    if (base + kTile > n) {
-                        if (gpos >= n) { k16 = 0; sc = 0; }
-                        else if (gpos + 16 > n) { uint32_t v = (1u << (uint32_t)(n - gpos)) - 1u; k16 &= v; sc &= v; }
-                    }
-                    ks[gi] = k16 | (sc << 16);
-                    packed[gi] = __builtin_popcount(k16) | (__builtin_popcount(sc) << 16);
-                    if (packed[gi] != 16u) clean = false;
-                    run += packed[gi];
-                    incl[gi] = run;
-                }
-                if (clean)
-                    for (int lane = 0; lane < 32; lane++) incl[r * kThreads + warp * 32 + lane] = 16u * (lane + 1);
-                row_tot[r * 8 + warp] = incl[r * kThreads + warp * 32 + 31];
-                dirty[r * 8 + warp] = !clean;
-            }
-        uint32_t total = 0, excl[32];
-        for (int t = 0; t < 32; t++) { excl[t] = total; total += row_tot[t]; }
-        // in-place compaction of dirty rows
+        uint32_t row_tot[32], row_pre[32], cls[32];
         for (int t = 0; t < 32; t++) {
-            if (!dirty[t]) continue;
+            const int r = t / 8, warp = t % 8;
+            bool all_full = true, epb_only = true;
+            for (int lane = 0; lane < 32; lane++) {
+                const int gi = r * kThreads + warp * 32 + lane;
+                const int64_t gpos = base + (int64_t)gi * 16;
+                uint32_t e16 = em[gi] & 0xFFFFu;
+                uint32_t k16 = ~e16 & 0xFFFFu;
+                const uint32_t near = ((uint32_t)scb[gi] >> 10) | scb[gi + 1] | (scb[gi + 2] & 1u);
+                if (near) k16 = keep_mask_near_sc(get, gpos, e16, scb[gi], scb[gi + 1], scb[gi + 2], &e16);
+                uint32_t sc = em[gi] >> 16;
+                if (base < e0) {
+                    if (gpos + 16 <= e0) { k16 = 0; e16 = 0; }
+                    else if (gpos < e0) { uint32_t m = ~((1u << (uint32_t)(e0 - gpos)) - 1u); k16 &= m; e16 &= m; }
+                }
+                if (base + kTile > n) {
+                    if (gpos >= n) { k16 = 0; sc = 0; e16 = 0; }
+                    else if (gpos + 16 > n) { uint32_t v = (1u << (uint32_t)(n - gpos)) - 1u; k16 &= v; sc &= v; e16 &= v; }
+                }
+                ks[gi] = k16 | (sc << 16);
+                ee[gi] = e16;
+                if (k16 != 0xFFFFu) all_full = false;
+                if (!((k16 | e16) == 0xFFFFu && sc == 0)) epb_only = false;
+            }
+            cls[t] = all_full ? 0 : (epb_only ? 1 : 2);
+            uint32_t run = 0;
+            for (int lane = 0; lane < 32; lane++) {
+                const int gi = r * kThreads + warp * 32 + lane;
+                const uint32_t el = cls[t] == 0 ? 0u : (cls[t] == 1 ? bits_popc(ee[gi]) : seg_element(ee[gi], ks[gi] >> 16));
+                run = lane ? seg_combine(run, el) : el;
+                incl[gi] = run;
+            }
+            row_tot[t] = run;
+        }
+        uint32_t total = 0;
+        for (int t = 0; t < 32; t++) { row_pre[t] = total; total = t ? seg_combine(total, row_tot[t]) : row_tot[t]; }
+        // in-place compaction of EPB-only rows
+        for (int t = 0; t < 32; t++) {
+            if (cls[t] != 1) continue;
             const int r = t / 8, warp = t % 8;
             uint32_t w[32][4];
             for (int lane = 0; lane < 32; lane++) memcpy(w[lane], tile_in + (r * kThreads + warp * 32 + lane) * 16, 16);
@@ -166,25 +174,52 @@ int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out, int64_t out
             for (int lane = 0; lane < 32; lane++) {
                 const int gi = r * kThreads + warp * 32 + lane;
                 const uint32_t k16 = ks[gi] & 0xFFFFu;
-                uint32_t loff = (incl[gi] & 0xFFFFu) - __builtin_popcount(k16);
+                uint32_t loff = 16u * lane - (incl[gi] - bits_popc(ee[gi]));
                 for (int j = 0; j < 16; j++)
                     if (k16 & (1u << j)) row[loff++] = (uint8_t)(w[lane][j >> 2] >> ((j & 3) * 8));
             }
         }
-        const uint32_t K = total & 0xFFFFu;
         for (int t = 0; t < 32; t++) {
             const int r = t / 8, warp = t % 8;
-            const uint32_t len = incl[r * kThreads + warp * 32 + 31] & 0xFFFFu;
-            if (!len) continue;
-            const uint64_t o = gout + (excl[t] & 0xFFFFu);
+            const uint32_t rowpre = row_pre[t];
             uint32_t w[32][4];
             for (int lane = 0; lane < 32; lane++) memcpy(w[lane], tile_in + (512 * t + lane * 16), 16);
-            for (int lane = 0; lane < 32; lane++)
-                store_row_lane(out, o, len, lane ? w[lane - 1] : w[0], w[lane], lane, t, excl[t] & 0xFFFFu, K, tile_in, excl);
+            if (cls[t] != 2) {
+                const uint64_t c_row = (rowpre >> 31) ? (uint64_t)(rowpre & 0x7FFFu) : carry + (rowpre & 0x7FFFu);
+                const uint32_t removed = incl[r * kThreads + warp * 32 + 31] & 0x7FFFu;
+                const uint64_t o = (uint64_t)base + 512u * t - c_row;
+                const uint8_t *prev_tail = nullptr;
+                if (t > 0 && cls[t - 1] != 2) prev_tail = tile_in + 512 * t - ((rowpre - row_pre[t - 1]) & 0x7FFFu);
+                const bool next_joins = t < 31 && cls[t + 1] != 2;
+                for (int lane = 0; lane < 32; lane++)
+                    store_row_lane(out, o, 512u - removed, lane ? w[lane - 1] : w[0], w[lane], lane, prev_tail, next_joins);
+            } else {
+                for (int lane = 0; lane < 32; lane++) {
+                    const int gi = r * kThreads + warp * 32 + lane;
+                    const uint32_t ex = lane ? incl[gi - 1] : 0u;
+                    const uint32_t pre = seg_combine(rowpre, ex);
+                    const uint64_t c = (pre >> 31) ? (uint64_t)(pre & 0x7FFFu) : carry + (pre & 0x7FFFu);
+                    const uint64_t gpos = (uint64_t)base + (uint64_t)gi * 16;
+                    uint64_t k = nal0 + ((pre >> 16) & 0x1FFFu);
+                    store_granule_bytes(out, gpos, w[lane], ks[gi] & 0xFFFFu, ee[gi], ks[gi] >> 16, c,
+                                        [&](int j, uint64_t c_end) {
+                                            if ((int64_t)k < cap) {
+                                                const uint64_t st = gpos + j + 1;
+                                                nal_start[k] = st;
+                                                nal_epb[k] = c_end;
+                                                uint32_t h = 0;
+                                                for (int q = 0; q < 4; q++) h |= gets((int64_t)st + q) << (8 * q);
+                                                nal_hdr[k] = h;
+                                            }
+                                            k++;
+                                        });
+                }
+            }
         }
-        gout += K;
+        carry = (total >> 31) ? (uint64_t)(total & 0x7FFFu) : carry + (total & 0x7FFFu);
+        nal0 += (total >> 16) & 0x1FFFu;
     }
-    return (int64_t)(gout - (uint64_t)out_align);
+    return (int64_t)nal0;
 }
 
 // NewNalUnit on one frame with keep_byte_frame; returns rbsp length

@@ -59,6 +59,26 @@ def test_ctx_init_many_slices(ctx):
 
 
 # =========================================================================================== K1/K2 Annex-B scan/strip
+def gather_rbsp(nals, rbsp):
+    """concatenate the per-NAL RBSPs (dense, in NAL order) from the position-preserving buffer"""
+    if len(nals) == 0:
+        return np.zeros(0, np.uint8)
+    lens = nals["rbsp_len"].astype(np.int64)
+    offs = nals["rbsp_off"].astype(np.int64)
+    dense_off = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    idx = np.repeat(offs - dense_off, lens) + np.arange(int(lens.sum()))
+    return rbsp[idx]
+
+
+def assert_rbsp_equal(nals, rbsp, onal, orbsp):
+    got = gather_rbsp(nals, rbsp)
+    assert len(got) == len(orbsp)
+    if not np.array_equal(got, orbsp):
+        bad = int(np.flatnonzero(got != orbsp)[0])
+        k = int(np.searchsorted(np.cumsum(onal["rbsp_len"]), bad, side="right"))
+        raise AssertionError("RBSP differs at dense byte %d (NAL %d, start %d)" % (bad, k, onal["start"][k]))
+
+
 def check_scan(ctx, capi, stream):
     s = np.ascontiguousarray(stream, dtype=np.uint8)
     summ, nals, ext, rbsp = ctx.annexb_scan(s)
@@ -68,13 +88,14 @@ def check_scan(ctx, capi, stream):
     assert summ["rbsp_bytes"] == len(orbsp)
     assert np.array_equal(nals["start"].astype(np.int64), onal["start"])
     assert np.array_equal(nals["num_bytes"].astype(np.int64), onal["num_bytes"])
-    assert np.array_equal(nals["rbsp_off"].astype(np.int64), onal["rbsp_off"])
     assert np.array_equal(nals["rbsp_len"].astype(np.int64), onal["rbsp_len"])
+    # position-preserving layout: a NAL's RBSP sits at its body's own offset
+    assert np.array_equal(nals["rbsp_off"].astype(np.int64), onal["start"] + onal["header_bytes"])
     assert np.array_equal(nals["forbidden_zero_bit"].astype(np.int64), onal["fzb"])
     assert np.array_equal(nals["ref_idc"].astype(np.int64), onal["ref_idc"])
     assert np.array_equal(nals["type"].astype(np.int64), onal["type"])
     assert np.array_equal(nals["header_bytes"].astype(np.int64), onal["header_bytes"])
-    assert np.array_equal(rbsp, orbsp)
+    assert_rbsp_equal(nals, rbsp, onal, orbsp)
     assert np.array_equal((nals["flags"] & capi.F_HAS_EPB) != 0, onal["epb"] == 3)
     if n:
         assert summ["first_start"] == onal["start"][0]
@@ -170,9 +191,10 @@ def test_scan_large_properties(ctx, capi):
     assert summ["n_nals"] == len(onal["start"])
     assert np.array_equal(nals["start"].astype(np.int64), onal["start"])
     assert np.array_equal(nals["rbsp_len"].astype(np.int64), onal["rbsp_len"])
-    assert np.array_equal(rbsp, orbsp)
+    assert_rbsp_equal(nals, rbsp, onal, orbsp)
+    assert summ["rbsp_bytes"] == len(orbsp)
     # conservation: every NAL byte is a header byte, one of the 2 tail bytes, an EPB or an RBSP byte
-    assert int(nals["num_bytes"].sum()) == int(nals["header_bytes"].sum()) + 2 * len(nals) + summ["n_epb"] + len(rbsp)
+    assert int(nals["num_bytes"].sum()) == int(nals["header_bytes"].sum()) + 2 * len(nals) + summ["n_epb"] + len(orbsp)
     assert summ["n_epb"] > 0
 
 

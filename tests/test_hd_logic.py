@@ -36,7 +36,8 @@ def emul():
     L.emul_stream.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                               C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.emul_stream_tiles.restype = C.c_int64
-    L.emul_stream_tiles.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+    L.emul_stream_tiles.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int64]
     L.emul_frame.restype = C.c_int64
     L.emul_frame.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     L.emul_cabac.restype = None
@@ -61,14 +62,29 @@ def run_emul_stream(L, s):
 def check_stream(L, s):
     K, st, ro, hd, rb, e0, mism = run_emul_stream(L, s)
     nal, rbsp = orc.read_nal_units_arrays(s)
-    # the kernel's tile pipeline (in-place compaction + aligned row stores), at two destination phases
+    # the kernel's tile pipeline (position-preserving RBSP layout: each NAL's RBSP at its body's own position)
     s8 = np.ascontiguousarray(s, dtype=np.uint8)
-    for align in (0, 5):
-        out = np.full(len(s8) + 96, 0xEE, np.uint8)
-        tot = L.emul_stream_tiles(s8.ctypes.data, len(s8), out.ctypes.data, align)
-        assert tot >= len(rbsp)
-        assert np.array_equal(out[align:align + len(rbsp)], rbsp), "tile pipeline bytes differ (align %d)" % align
-        assert np.all(out[:align] == 0xEE) and np.all(out[align + tot:] == 0xEE), "stray writes"
+    n_or = len(nal["start"])
+    for shift in (0, 16, 5):
+        out = np.full(len(s8) + 96 + shift, 0xEE, np.uint8)
+        cap = len(s8) // 4 + 2
+        t_st, t_epb, t_hd = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64), np.zeros(cap, np.uint32)
+        Kt = L.emul_stream_tiles(s8.ctypes.data, len(s8), out.ctypes.data, shift, t_st.ctypes.data, t_epb.ctypes.data,
+                                 t_hd.ctypes.data, cap)
+        assert max(Kt, 1) - 1 == n_or
+        written = np.zeros(len(out), bool)
+        for k in range(n_or):
+            a0 = int(t_st[k])
+            assert a0 == nal["start"][k]
+            H = int(nal["header_bytes"][k])
+            ln = max(int(t_st[k + 1]) - a0 - H - 2, 0) - int(t_epb[k + 1])
+            assert ln == nal["rbsp_len"][k]
+            got = out[shift + a0 + H: shift + a0 + H + ln]
+            exp = rbsp[int(nal["rbsp_off"][k]): int(nal["rbsp_off"][k]) + ln]
+            assert np.array_equal(got, exp), "tile pipeline bytes differ (NAL %d, shift %d)" % (k, shift)
+            written[shift + a0 + H: shift + a0 + H + ln] = True
+        # nothing may be written outside [first NAL body, stream end) and nothing before the destination
+        assert np.all(out[:shift] == 0xEE) and np.all(out[shift + len(s8):] == 0xEE), "stray writes"
     assert mism == 0
     assert max(K, 1) - 1 == len(nal["start"])
     n = len(nal["start"])
