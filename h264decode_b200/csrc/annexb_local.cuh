@@ -301,4 +301,35 @@ H264B_HD void store_granule_bytes(uint8_t *out, uint64_t gpos, const uint32_t w[
     }
 }
 
+// ---- NALs whose body spans several tiles ----------------------------------------------------------------------
+// The main pass treats every tile on its own: inside a tile a kept byte at stream position p goes to
+// out[p - (EPBs removed from p's NAL earlier IN THIS TILE)].  A NAL that continues into further tiles is therefore
+// laid out in pieces, one per tile, each compacted towards its own start; whenever an earlier piece lost EPBs the
+// later pieces sit too far right by the accumulated count G.  Real streams almost never have that (one EPB per
+// several MB of entropy-coded data), so the hot kernel needs no inter-tile communication at all and a tiny post-pass
+// slides the few affected pieces left (nal_fixup_kernel).  This helper walks the pieces of the NAL [a, b):
+//   a, b        first byte of this NAL / of the next one (b-1 is the 01 of the start code that ends it)
+//   H           header bytes
+//   end_local   EPB count the main pass recorded at that start code: EPBs since the NAL's start if it began in the
+//               same tile, else since the start of the tile
+//   tile_tot    per-tile packed totals (seg_combine format): low 15 bits = EPBs after the tile's last NAL start, or
+//               in the whole tile when it holds none
+// move(start, len, G) is called for every later piece that has to slide left by G > 0.  Returns the NAL's EPB total.
+template <class Move>
+H264B_HD uint64_t nal_pieces(uint64_t a, uint64_t b, uint32_t H, uint64_t end_local, const uint32_t *tile_tot,
+                             uint64_t tile_bytes, const Move &move) {
+    const uint64_t Tq = (a - 1) / tile_bytes, Tb = (b - 1) / tile_bytes;
+    if (Tq == Tb) return end_local;
+    uint64_t G = tile_tot[Tq] & 0x7FFFu;
+    for (uint64_t t = Tq + 1; t <= Tb; t++) {
+        const uint64_t lo = t * tile_bytes, body = a + H;
+        const uint64_t ps = lo > body ? lo : body;                    // first kept byte of the piece
+        const uint64_t pe = t < Tb ? (t + 1) * tile_bytes : b - 2;    // kept bytes are < pe (b-2, b-1: the tail rule)
+        const uint64_t e = t < Tb ? (uint64_t)(tile_tot[t] & 0x7FFFu) : end_local;
+        if (G && pe > ps && pe - ps > e) move(ps, pe - ps - e, G);
+        if (t < Tb) G += tile_tot[t] & 0x7FFFu;
+    }
+    return G + end_local;
+}
+
 }  // namespace h264b

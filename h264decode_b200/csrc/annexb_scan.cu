@@ -30,7 +30,6 @@ constexpr int kRows = 4;                          // granules per thread per til
 constexpr int kGranules = kThreads * kRows;       // 1024
 constexpr int kTile = kGranules * 16;             // 16384 bytes
 constexpr int kHalo = 16;
-constexpr int kLook = 4;                          // predecessor tiles each lane inspects per look-back round
 constexpr int kInBytes = kHalo + kTile + kHalo;   // 16416
 constexpr uint64_t kStatusAgg = 1ull << 62, kStatusPrefix = 2ull << 62, kValueMask = (1ull << 62) - 1;
 
@@ -41,7 +40,9 @@ struct ScanScratchHeader {   // device scratch, zeroed / initialised by scan_ini
     unsigned long long total_sc;   // start codes found = slots handed out of the NAL record buffer
     unsigned long long total_kept;
     unsigned long long n_epb;
-    unsigned long long reserved[3];
+    unsigned int n_fix;            // entries of fix_list
+    unsigned int pad2;
+    unsigned long long reserved[2];
 };  // 64 bytes
 
 struct ScanArgs {
@@ -49,10 +50,10 @@ struct ScanArgs {
     uint64_t n;
     uint8_t *out;
     ScanScratchHeader *hdr;
-    unsigned long long *desc;  // per tile: status << 62 | EPB carry of the NAL open at the tile's end
-    uint32_t *tile_nsc;        // per tile: start codes in it (0 unless written)
+    uint32_t *tile_tot;        // per tile: packed segmented total (seg_combine format): NAL start? | start codes | EPBs
     uint32_t *tile_slot;       // per tile: first slot of its records in the unordered record buffer
-    uint32_t *tile_ord;        // per tile: ordinal of its first start code (exclusive scan of tile_nsc)
+    uint32_t *tile_ord;        // per tile: ordinal of its first start code (exclusive scan of the start-code counts)
+    uint32_t *fix_list;        // NAL ordinals whose later pieces must slide left (written by scan_finalize_kernel)
     // per start code, in slot order (tiles reserve slots with one atomicAdd): written by the main pass
     unsigned long long *rec_start;
     unsigned long long *rec_epb;
@@ -86,17 +87,13 @@ __device__ __forceinline__ void st_desc(ulonglong2 *p, unsigned long long x, uns
 }
 
 // ------------------------------------------------------------------------------------------------ init
-__global__ void scan_init_kernel(ScanScratchHeader *hdr, unsigned long long *desc, uint64_t n_desc, uint64_t n) {
-    // desc[0 .. n_desc) covers the tile descriptors and, right behind them, the per-tile start-code counts
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) {
-        hdr->ticket = 0;
-        hdr->first_start = n;
-        hdr->total_sc = 0;
-        hdr->total_kept = 0;
-        hdr->n_epb = 0;
-    }
-    for (; i < n_desc; i += (uint64_t)gridDim.x * blockDim.x) desc[i] = 0;
+__global__ void scan_init_kernel(ScanScratchHeader *hdr, uint64_t n) {
+    hdr->ticket = 0;
+    hdr->first_start = n;
+    hdr->total_sc = 0;
+    hdr->total_kept = 0;
+    hdr->n_epb = 0;
+    hdr->n_fix = 0;
 }
 
 // ------------------------------------------------------------------------------------------------ first start code
@@ -129,7 +126,6 @@ struct __align__(16) ScanSmem {
     uint16_t scbits[kGranules + 2];       // start-code-end bits per granule, [0] = halo granule before the tile
     uint32_t row_tot[kRows * 8];          // packed segmented elements per (row, warp); then exclusive prefixes
     uint8_t row_class[kRows * 8];         // 0 untouched, 1 only EPBs removed, 2 contains NAL boundaries / stream ends
-    unsigned long long carry_in;          // EPBs already removed from the NAL that is open at the tile's first byte
     unsigned long long nal_slot0;         // first record slot reserved for this tile's start codes
     uint32_t tile;
     unsigned long long mbar;
@@ -326,67 +322,18 @@ __global__ void __launch_bounds__(kThreads, 5) annexb_scan_kernel(ScanArgs a) {
             const uint32_t total = __shfl_sync(0xFFFFFFFFu, x, 31);
             const bool has_start = (total >> 31) != 0;
             const unsigned long long t_val = total & 0x7FFFu, t_nsc = (total >> 16) & 0x1FFFu;
-            // ------------------------------------------------------------ short decoupled look-back
-            // One 64-bit descriptor per tile: status << 62 | EPB count.
-            //   status 1: "no NAL start in this tile: add my count and keep looking"
-            //   status 2: final EPB count of the NAL that is open at the tile's end.  A tile that contains a NAL start
-            //             publishes this at once, without looking back, so the chain only runs back to the nearest
-            //             tile holding a NAL start: a few tiles for real streams, never the whole resident cohort.
-            // NAL numbering needs no chain at all: the tile reserves nsc slots of the (unordered) record buffer with
-            // one atomicAdd and leaves its count for the post-pass that orders the records.
-            unsigned long long carry = 0;
-            if (lane == 0 && t_nsc) {
-                sm.nal_slot0 = atomicAdd(&a.hdr->total_sc, t_nsc);
-                a.tile_nsc[tile] = (uint32_t)t_nsc;
-                a.tile_slot[tile] = (uint32_t)sm.nal_slot0;
-            }
-#ifdef H264B_EXP_NOLOOKBACK
-            if (false) {
-#else
-            if (tile > 0) {
-#endif
-                if (lane == 0) st_relaxed(&a.desc[tile], ((has_start ? 2ull : 1ull) << 62) | t_val);
-                bool done = false;
-                for (int64_t j = (int64_t)tile - 1; !done; j -= 32 * kLook) {
-                    const int64_t first_idx = j - (int64_t)lane * kLook;  // this lane: first_idx, first_idx-1, ...
-                    unsigned long long d[kLook];
-                    bool pending;
-                    do {  // all 32 lanes poll together; positions before tile 0 count as final 0
-                        pending = false;
-                        bool seen = false;
-#pragma unroll
-                        for (int u = 0; u < kLook; u++) {
-                            const int64_t idx = first_idx - u;
-                            d[u] = idx >= 0 ? ld_relaxed(&a.desc[idx]) : (2ull << 62);
-                        }
-#pragma unroll
-                        for (int u = 0; u < kLook; u++) {  // blocked only by an unpublished tile nearer than a final one
-                            if (!seen && (d[u] >> 62) == 0) pending = true;
-                            seen = seen || (d[u] >> 62) == 2;
-                        }
-                        const uint32_t m = __ballot_sync(0xFFFFFFFFu, seen);
-                        if (m & ((1u << lane) - 1u)) pending = false;  // a nearer lane already found the end
-                    } while (__any_sync(0xFFFFFFFFu, pending));
-                    unsigned long long v = 0;
-                    bool found = false;
-#pragma unroll
-                    for (int u = 0; u < kLook; u++) {
-                        if (!found) v += d[u] & kValueMask;
-                        found = found || (d[u] >> 62) == 2;
-                    }
-                    const uint32_t pm = __ballot_sync(0xFFFFFFFFu, found);
-                    const int first = pm ? __ffs(pm) - 1 : 31;
-                    if (lane > first) v = 0;
-#pragma unroll
-                    for (int dd = 16; dd; dd >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, dd);
-                    carry += v;
-                    done = pm != 0;
+            // No inter-tile communication: a tile counts the EPBs of its open NAL from zero (see nal_pieces in
+            // annexb_local.cuh for how NALs that span tiles are finished).  It leaves its packed total for the
+            // post-pass and, when it holds start codes, reserves that many record slots with one atomicAdd.
+            if (lane == 0) {
+                a.tile_tot[tile] = total;
+                if (t_nsc) {
+                    sm.nal_slot0 = atomicAdd(&a.hdr->total_sc, t_nsc);
+                    a.tile_slot[tile] = (uint32_t)sm.nal_slot0;
                 }
             }
-            if (lane == 0) {
-                if (!has_start || tile == 0) st_relaxed(&a.desc[tile], (2ull << 62) | ((has_start ? t_val : carry + t_val) & kValueMask));
-                sm.carry_in = carry;
-            }
+            (void)has_start;
+            (void)t_val;
         }
         // Rows that only lose emulation-prevention bytes are compacted in place inside their own 512-byte span of the
         // tile buffer (nobody else reads it any more): afterwards they are `len` contiguous bytes like untouched rows.
@@ -413,12 +360,12 @@ __global__ void __launch_bounds__(kThreads, 5) annexb_scan_kernel(ScanArgs a) {
             }
         }
         __syncthreads();
-        const uint64_t carry_in = sm.carry_in;
+        const uint64_t carry_in = 0;  // per-tile counting (see above)
         const uint64_t slot0 = sm.nal_slot0;
 
         // ---------------------------------------------------------------- store rows + NAL index
 #ifdef H264B_EXP_NOSTORE
-        if (carry_in == 0x123456789ull)
+        if (slot0 == 0x123456789ull)
 #endif
 #pragma unroll
         for (int r = 0; r < kRows; r++) {
@@ -512,40 +459,34 @@ __device__ __forceinline__ void decode_nal_header(uint32_t hdr4, h264b_nal &o, h
     *ext = e;
 }
 
-// Post-pass 1: ordinal of every tile's first start code = exclusive scan of the per-tile counts (one CTA; the array
-// has one entry per 16 KiB of stream).
-__global__ void __launch_bounds__(1024) nal_order_kernel(const uint32_t *tile_nsc, uint32_t *tile_ord, uint32_t n_tiles) {
-    __shared__ unsigned long long warp_sum[32];
-    __shared__ unsigned long long running;
+// Post-pass 1: ordinal of every tile's first start code = exclusive scan of the per-tile start-code counts (one CTA;
+// the array has one entry per 16 KiB of stream; warps read it coalesced, 1024 entries per step).
+__global__ void __launch_bounds__(1024) nal_order_kernel(const uint32_t *tile_tot, uint32_t *tile_ord, uint32_t n_tiles) {
+    __shared__ uint32_t warp_sum[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) running = 0;
-    __syncthreads();
-    const uint32_t per = (n_tiles + 1023u) / 1024u;  // contiguous entries per thread
-    const uint32_t lo = (uint32_t)tid * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
-    unsigned long long mine = 0;
-    for (uint32_t i = lo; i < hi; i++) mine += tile_nsc[i];
-    unsigned long long x = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-        if (lane >= d) x += y;
-    }
-    if (lane == 31) warp_sum[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-        unsigned long long w = warp_sum[lane], own = w;
+    uint32_t running = 0;  // identical in every thread
+    for (uint32_t base = 0; base < n_tiles; base += 1024) {
+        const uint32_t i = base + (uint32_t)tid;
+        const uint32_t c = i < n_tiles ? ((tile_tot[i] >> 16) & 0x1FFFu) : 0u;
+        uint32_t x = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, w, d);
-            if (lane >= d) w += y;
+            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if (lane >= d) x += y;
         }
-        warp_sum[lane] = w - own;
-    }
-    __syncthreads();
-    unsigned long long ord = warp_sum[warp] + x - mine;
-    for (uint32_t i = lo; i < hi; i++) {
-        tile_ord[i] = (uint32_t)ord;
-        ord += tile_nsc[i];
+        if (lane == 31) warp_sum[warp] = x;
+        __syncthreads();
+        uint32_t w = warp_sum[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+            if (lane >= d) wi += y;
+        }
+        const uint32_t wbase = __shfl_sync(0xFFFFFFFFu, wi - w, warp);
+        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, wi, 31);
+        if (i < n_tiles) tile_ord[i] = running + wbase + x - c;
+        running += tot;
+        __syncthreads();
     }
 }
 
@@ -553,7 +494,7 @@ __global__ void __launch_bounds__(1024) nal_order_kernel(const uint32_t *tile_ns
 __global__ void __launch_bounds__(256) nal_permute_kernel(ScanArgs a) {
     const uint64_t cap = a.nal_cap;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < a.n_tiles; t += gridDim.x * blockDim.x) {
-        const uint32_t c = a.tile_nsc[t];
+        const uint32_t c = (a.tile_tot[t] >> 16) & 0x1FFFu;
         if (!c) continue;
         const uint64_t slot = a.tile_slot[t], ord = a.tile_ord[t];
         for (uint32_t i = 0; i < c; i++) {
@@ -566,22 +507,29 @@ __global__ void __launch_bounds__(256) nal_permute_kernel(ScanArgs a) {
     }
 }
 
+// Post-pass 3: the h264b_nal records; NALs whose later tile pieces have to slide left are queued for post-pass 4.
 __global__ void __launch_bounds__(256) scan_finalize_kernel(ScanArgs a, h264b_nal *nals, h264b_nal_ext *ext,
                                                              h264b_scan_summary *summary) {
     const uint64_t K = a.hdr->total_sc;
     const uint64_t n_nals = K ? K - 1 : 0;
-    const uint64_t lim = n_nals < a.nal_cap ? n_nals : (a.nal_cap ? (uint64_t)a.nal_cap - 1 : 0);
+    // more start codes than record slots: the index is incomplete (status H264B_E_CAPACITY, the caller retries
+    // with n_start_codes + 1 slots), so no record is produced at all
+    const uint64_t lim = K > a.nal_cap ? 0 : n_nals;
     unsigned long long epb = 0, rbsp = 0;
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < lim;
          k += (uint64_t)gridDim.x * blockDim.x) {
         h264b_nal o;
         o.start = a.nal_start[k];
-        o.num_bytes = (uint32_t)(a.nal_start[k + 1] - o.start);
+        const uint64_t next = a.nal_start[k + 1];
+        o.num_bytes = (uint32_t)(next - o.start);
         decode_nal_header(a.nal_hdr[k], o, ext ? &ext[k] : nullptr);
+        bool fix = false;
+        const uint64_t removed = nal_pieces(o.start, next, o.header_bytes, a.nal_epb[k + 1], a.tile_tot, (uint64_t)kTile,
+                                            [&](uint64_t, uint64_t, uint64_t) { fix = true; });
+        if (fix) a.fix_list[atomicAdd(&a.hdr->n_fix, 1u)] = (uint32_t)k;
         // body = NumBytes - HeaderBytes - 2 bytes (a NAL shorter than that has no body); its RBSP sits at the body's
         // own position in the output buffer
         const int64_t body = (int64_t)o.num_bytes - (int64_t)o.header_bytes - 2;
-        const uint32_t removed = (uint32_t)a.nal_epb[k + 1];
         o.rbsp_off = o.start + o.header_bytes;
         o.rbsp_len = (uint32_t)((body > 0 ? body : 0) - (int64_t)removed);
         o.flags = (removed ? H264B_F_HAS_EPB : 0u) | (o.num_bytes < 8 ? H264B_F_SHORT_NAL : 0u);
@@ -599,6 +547,34 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(ScanArgs a, h264b_na
         summary->reserved = 0;
     }
 }
+
+// Post-pass 4: slide the later pieces of the queued NALs left (one CTA per NAL, pieces in stream order, 4 KiB at a
+// time: everything is read into registers before anything is written, so the overlapping move is safe).
+__global__ void __launch_bounds__(256) nal_fixup_kernel(ScanArgs a) {
+    const uint32_t n_fix = a.hdr->n_fix;
+    for (uint32_t f = blockIdx.x; f < n_fix; f += gridDim.x) {
+        const uint64_t k = a.fix_list[f];
+        const uint64_t st = a.nal_start[k], next = a.nal_start[k + 1];
+        h264b_nal o;
+        decode_nal_header(a.nal_hdr[k], o, nullptr);
+        nal_pieces(st, next, o.header_bytes, a.nal_epb[k + 1], a.tile_tot, (uint64_t)kTile,
+                   [&](uint64_t ps, uint64_t len, uint64_t G) {
+                       for (uint64_t off = 0; off < len; off += 256 * 16) {
+                           const uint64_t p = ps + off + (uint64_t)threadIdx.x * 16;
+                           uint8_t v[16];
+                           const uint64_t end = ps + len;
+#pragma unroll
+                           for (int j = 0; j < 16; j++) v[j] = p + j < end ? a.out[p + j] : (uint8_t)0;
+                           __syncthreads();
+#pragma unroll
+                           for (int j = 0; j < 16; j++)
+                               if (p + j < end) a.out[p + j - G] = v[j];
+                           __syncthreads();
+                       }
+                   });
+    }
+}
+
 __global__ void scan_summary_epb_kernel(const ScanScratchHeader *hdr, h264b_scan_summary *summary) {
     summary->n_epb = hdr->n_epb;
     summary->rbsp_bytes = hdr->total_kept;  // RBSP bytes of all emitted NAL units
@@ -717,7 +693,7 @@ __global__ void __launch_bounds__(1024) slice_select_kernel(const h264b_nal *nal
 
 // ------------------------------------------------------------------------------------------------ launchers
 struct ScratchOffsets {
-    uint64_t desc, tile_nsc, tile_slot, tile_ord, rec_start, rec_epb, rec_hdr, nal_start, nal_epb, nal_hdr, total;
+    uint64_t tile_tot, tile_slot, tile_ord, fix_list, rec_start, rec_epb, rec_hdr, nal_start, nal_epb, nal_hdr, total;
 };
 static ScratchOffsets scratch_layout(uint64_t n, uint32_t nal_cap) {
     const uint64_t n_tiles = (n + kTile - 1) / kTile;
@@ -728,10 +704,10 @@ static ScratchOffsets scratch_layout(uint64_t n, uint32_t nal_cap) {
         p = (p + bytes + 15) & ~15ull;
         return at;
     };
-    o.desc = take(n_tiles * 8);
-    o.tile_nsc = take(n_tiles * 4);  // must directly follow desc: both are zeroed by scan_init_kernel in one sweep
+    o.tile_tot = take(n_tiles * 4);
     o.tile_slot = take(n_tiles * 4);
     o.tile_ord = take(n_tiles * 4);
+    o.fix_list = take((uint64_t)nal_cap * 4);
     o.rec_start = take((uint64_t)nal_cap * 8);
     o.rec_epb = take((uint64_t)nal_cap * 8);
     o.rec_hdr = take((uint64_t)nal_cap * 4);
@@ -766,10 +742,10 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     a.n = n;
     a.out = d_rbsp;
     a.hdr = (ScanScratchHeader *)s;
-    a.desc = (unsigned long long *)(s + so.desc);
-    a.tile_nsc = (uint32_t *)(s + so.tile_nsc);
+    a.tile_tot = (uint32_t *)(s + so.tile_tot);
     a.tile_slot = (uint32_t *)(s + so.tile_slot);
     a.tile_ord = (uint32_t *)(s + so.tile_ord);
+    a.fix_list = (uint32_t *)(s + so.fix_list);
     a.rec_start = (unsigned long long *)(s + so.rec_start);
     a.rec_epb = (unsigned long long *)(s + so.rec_epb);
     a.rec_hdr = (uint32_t *)(s + so.rec_hdr);
@@ -779,12 +755,7 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     a.nal_cap = nal_cap;
     a.n_tiles = (uint32_t)n_tiles;
 
-    // zero the descriptors and the per-tile counts (contiguous: [desc, tile_slot) in 8-byte words)
-    const uint64_t n_zero = (so.tile_slot - so.desc) / 8;
-    uint64_t ib = (n_zero + 255) / 256;
-    if (ib < 1) ib = 1;
-    if (ib > (uint64_t)ctx->sm_count * 8) ib = (uint64_t)ctx->sm_count * 8;
-    scan_init_kernel<<<(int)ib, 256, 0, ctx->stream>>>(a.hdr, a.desc, n_zero, n);
+    scan_init_kernel<<<1, 1, 0, ctx->stream>>>(a.hdr, n);
     H264B_LAUNCH_CHECK(ctx, "scan_init_kernel");
     if (n_tiles) {
         const uint64_t chunks = (n + 4095) / 4096;
@@ -806,7 +777,7 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
         if (grid > n_tiles) grid = n_tiles;
         annexb_scan_kernel<<<(int)grid, kThreads, smem, ctx->stream>>>(a);
         H264B_LAUNCH_CHECK(ctx, "annexb_scan_kernel");
-        nal_order_kernel<<<1, 1024, 0, ctx->stream>>>(a.tile_nsc, a.tile_ord, a.n_tiles);
+        nal_order_kernel<<<1, 1024, 0, ctx->stream>>>(a.tile_tot, a.tile_ord, a.n_tiles);
         H264B_LAUNCH_CHECK(ctx, "nal_order_kernel");
         uint64_t pb = (n_tiles + 255) / 256;
         if (pb > (uint64_t)ctx->sm_count * 8) pb = (uint64_t)ctx->sm_count * 8;
@@ -816,6 +787,10 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     int fin_blocks = ctx->sm_count * 2;
     scan_finalize_kernel<<<fin_blocks, 256, 0, ctx->stream>>>(a, d_nals, d_ext, d_summary);
     H264B_LAUNCH_CHECK(ctx, "scan_finalize_kernel");
+    if (n_tiles > 1) {
+        nal_fixup_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(a);
+        H264B_LAUNCH_CHECK(ctx, "nal_fixup_kernel");
+    }
     scan_summary_epb_kernel<<<1, 1, 0, ctx->stream>>>(a.hdr, d_summary);
     H264B_LAUNCH_CHECK(ctx, "scan_summary_epb_kernel");
     return H264B_OK;

@@ -104,7 +104,9 @@ int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out_base, int64_
             break;
         }
     const int64_t n_tiles = (n + kTile - 1) / kTile;
-    uint64_t carry = 0, nal0 = 0;  // what the look-back would deliver
+    const uint64_t carry = 0;  // every tile counts the EPBs of its open NAL from zero
+    uint64_t nal0 = 0;         // NAL numbering (the product orders the records in a post-pass)
+    std::vector<uint32_t> tile_tot((size_t)n_tiles + 1, 0);
     std::vector<uint8_t> buf(kHalo + kTile + kHalo);
     std::vector<uint16_t> scb(kGran + 2);
     for (int64_t tile = 0; tile < n_tiles; tile++) {
@@ -216,9 +218,19 @@ int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out_base, int64_
                 }
             }
         }
-        carry = (total >> 31) ? (uint64_t)(total & 0x7FFFu) : carry + (total & 0x7FFFu);
+        tile_tot[tile] = total;
         nal0 += (total >> 16) & 0x1FFFu;
     }
+    // post-pass: NALs that span tiles -- slide their later pieces left and total their EPB counts (nal_fixup_kernel,
+    // scan_finalize_kernel)
+    const int64_t K = (int64_t)nal0 < cap ? (int64_t)nal0 : cap;
+    std::vector<uint64_t> totals((size_t)K + 1, 0);
+    for (int64_t k = 0; k + 1 < K; k++) {
+        const uint32_t H = nal_header_bytes(nal_hdr[k] & 0xFF, (nal_hdr[k] >> 8) & 0xFF);
+        totals[k + 1] = nal_pieces(nal_start[k], nal_start[k + 1], H, nal_epb[k + 1], tile_tot.data(), (uint64_t)kTile,
+                                   [&](uint64_t ps, uint64_t len, uint64_t G) { memmove(out + ps - G, out + ps, len); });
+    }
+    for (int64_t k = 1; k < K; k++) nal_epb[k] = totals[k];
     return (int64_t)nal0;
 }
 

@@ -131,6 +131,15 @@ def test_scan_kats(ctx, capi):
     check_scan(ctx, capi, np.tile(np.array([0, 0, 3], np.uint8), 20000))
     check_scan(ctx, capi, np.tile(np.array([0, 0, 0, 1], np.uint8), 20000))
     check_scan(ctx, capi, np.full(70000, 0xFF, np.uint8))
+    # one NAL over several 16 KiB tiles that loses an EPB every third byte / only in its first tile / only late
+    sc, hdr = np.array([0, 0, 0, 1], np.uint8), np.array([0x65], np.uint8)
+    rng = np.random.default_rng(77)
+    body = rng.integers(4, 256, 60000).astype(np.uint8)
+    check_scan(ctx, capi, np.concatenate([sc, hdr, np.tile(np.array([0, 0, 3], np.uint8), 23000), sc, hdr, body, sc]))
+    b2 = body.copy(); b2[100:103] = [0, 0, 3]
+    check_scan(ctx, capi, np.concatenate([sc, hdr, b2, sc]))
+    b3 = body.copy(); b3[40000:40003] = [0, 0, 3]; b3[16380:16383] = [0, 0, 3]
+    check_scan(ctx, capi, np.concatenate([np.full(7, 9, np.uint8), sc, hdr, b3, sc, hdr, b2[:20000], sc]))
 
 
 @pytest.mark.parametrize("seed", range(4))
