@@ -124,6 +124,22 @@ H264B_HD GranuleMasks granule_masks(const uint32_t w[4], uint32_t prev) {
     return m;
 }
 
+// Cheap filter in front of granule_masks: non-zero iff some byte p of the granule has s[p] == 0 && s[p-1] == 0 (prev =
+// the 4 bytes before the granule).  Every emulation-prevention byte and every start-code end at p, p+1 or p+2 needs such
+// a pair, so a span of the stream without one is copied verbatim (the fast path of annexb_scan_kernel).
+H264B_HD uint32_t funnel_l8(uint32_t lo, uint32_t hi) { return (hi << 8) | (lo >> 24); }
+H264B_HD uint32_t zero_pair_bits(const uint32_t w[4], uint32_t prev) {
+    const uint32_t zp = zero_bytes(prev), z0 = zero_bytes(w[0]), z1 = zero_bytes(w[1]), z2 = zero_bytes(w[2]),
+                   z3 = zero_bytes(w[3]);
+    return (z0 & funnel_l8(zp, z0)) | (z1 & funnel_l8(z0, z1)) | (z2 & funnel_l8(z1, z2)) | (z3 & funnel_l8(z2, z3));
+}
+// the same for the last 7 positions of the 8 bytes (lo, hi) that precede a chunk: a start code ending there still
+// reaches into the chunk with its NAL header and its emulation-prevention guard
+H264B_HD uint32_t zero_pair_bits_tail8(uint32_t lo, uint32_t hi) {
+    const uint32_t zl = zero_bytes(lo), zh = zero_bytes(hi);
+    return (zl & (zl << 8)) | (zh & funnel_l8(zl, zh));
+}
+
 // keep mask of a granule at stream position gpos when start codes end within [gpos-6, gpos+16], in the bit domain
 // (same result as 16 x keep_byte_stream, checked exhaustively on the CPU by tests/test_hd_logic.py):
 //   e16      raw emulation-prevention mask of the granule (granule_masks().e)
@@ -162,8 +178,8 @@ H264B_HD uint32_t keep_mask_near_sc(const Get& get, int64_t gpos, uint32_t e16, 
 // to out[p - c(p)], c(p) = emulation-prevention bytes removed in p's NAL before p.  c restarts at every NAL start, so
 // it is a SEGMENTED running count; an element of the scan is packed in 32 bits:
 //   bit 31      the span contains a NAL start (the count below is then "since the last start in the span")
-//   bits 28:16  start codes in the span (for NAL numbering; <= 4096 per 16 KiB tile)
-//   bits 14:0   EPBs removed (<= 16384 per tile)
+//   bits 28:16  start codes in the span (for NAL numbering; <= 512 per 2 KiB chunk)
+//   bits 14:0   EPBs removed (<= 683 per chunk)
 H264B_HD uint32_t seg_combine(uint32_t a, uint32_t b) {  // a = earlier span, b = later span
     const uint32_t val = ((b >> 31) ? 0u : (a & 0x7FFFu)) + (b & 0x7FFFu);
     return ((a | b) & 0x80000000u) | ((a + b) & 0x1FFF0000u) | val;
@@ -301,33 +317,33 @@ H264B_HD void store_granule_bytes(uint8_t *out, uint64_t gpos, const uint32_t w[
     }
 }
 
-// ---- NALs whose body spans several tiles ----------------------------------------------------------------------
-// The main pass treats every tile on its own: inside a tile a kept byte at stream position p goes to
-// out[p - (EPBs removed from p's NAL earlier IN THIS TILE)].  A NAL that continues into further tiles is therefore
-// laid out in pieces, one per tile, each compacted towards its own start; whenever an earlier piece lost EPBs the
-// later pieces sit too far right by the accumulated count G.  Real streams almost never have that (one EPB per
-// several MB of entropy-coded data), so the hot kernel needs no inter-tile communication at all and a tiny post-pass
-// slides the few affected pieces left (nal_fixup_kernel).  This helper walks the pieces of the NAL [a, b):
+// ---- NALs whose body spans several pieces ---------------------------------------------------------------------
+// The main pass cuts the stream into fixed-size pieces (spans of chunks, each walked front to back by one warp) and
+// treats every piece on its own: inside a piece a kept byte at stream position p goes to
+// out[p - (EPBs removed from p's NAL earlier IN THIS PIECE)].  A NAL that continues into further pieces is therefore
+// laid out in parts, one per piece, each compacted towards its own start; whenever an earlier part lost EPBs the
+// later parts sit too far right by the accumulated count G.  Real streams almost never have that (one EPB per
+// several MB of entropy-coded data), so the hot kernel needs no communication between warps at all and a tiny
+// post-pass slides the few affected parts left (nal_fixup_kernel).  This helper walks the parts of the NAL [a, b):
 //   a, b        first byte of this NAL / of the next one (b-1 is the 01 of the start code that ends it)
 //   H           header bytes
 //   end_local   EPB count the main pass recorded at that start code: EPBs since the NAL's start if it began in the
-//               same tile, else since the start of the tile
-//   tile_tot    per-tile packed totals (seg_combine format): low 15 bits = EPBs after the tile's last NAL start, or
-//               in the whole tile when it holds none
-// move(start, len, G) is called for every later piece that has to slide left by G > 0.  Returns the NAL's EPB total.
+//               same piece, else since the start of the piece
+//   piece_epb   per piece: EPBs after the piece's last NAL start, or in the whole piece when it holds none
+// move(start, len, G) is called for every later part that has to slide left by G > 0.  Returns the NAL's EPB total.
 template <class Move>
-H264B_HD uint64_t nal_pieces(uint64_t a, uint64_t b, uint32_t H, uint64_t end_local, const uint32_t *tile_tot,
-                             uint64_t tile_bytes, const Move &move) {
-    const uint64_t Tq = (a - 1) / tile_bytes, Tb = (b - 1) / tile_bytes;
+H264B_HD uint64_t nal_pieces(uint64_t a, uint64_t b, uint32_t H, uint64_t end_local, const uint32_t *piece_epb,
+                             uint64_t piece_bytes, const Move &move) {
+    const uint64_t Tq = (a - 1) / piece_bytes, Tb = (b - 1) / piece_bytes;
     if (Tq == Tb) return end_local;
-    uint64_t G = tile_tot[Tq] & 0x7FFFu;
+    uint64_t G = piece_epb[Tq];
     for (uint64_t t = Tq + 1; t <= Tb; t++) {
-        const uint64_t lo = t * tile_bytes, body = a + H;
-        const uint64_t ps = lo > body ? lo : body;                    // first kept byte of the piece
-        const uint64_t pe = t < Tb ? (t + 1) * tile_bytes : b - 2;    // kept bytes are < pe (b-2, b-1: the tail rule)
-        const uint64_t e = t < Tb ? (uint64_t)(tile_tot[t] & 0x7FFFu) : end_local;
+        const uint64_t lo = t * piece_bytes, body = a + H;
+        const uint64_t ps = lo > body ? lo : body;                    // first kept byte of the part
+        const uint64_t pe = t < Tb ? (t + 1) * piece_bytes : b - 2;   // kept bytes are < pe (b-2, b-1: the tail rule)
+        const uint64_t e = t < Tb ? (uint64_t)piece_epb[t] : end_local;
         if (G && pe > ps && pe - ps > e) move(ps, pe - ps - e, G);
-        if (t < Tb) G += tile_tot[t] & 0x7FFFu;
+        if (t < Tb) G += piece_epb[t];
     }
     return G + end_local;
 }

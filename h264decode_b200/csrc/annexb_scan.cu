@@ -4,45 +4,53 @@
 // of the reference with one streaming pass: every input byte is read from HBM once and every kept byte written once
 // (algorithmic traffic N_in + N_rbsp + 20 B per NAL).
 //
-// Structure (one CTA = 256 threads, tiles of 16 KiB handed out by an atomic ticket so that tile i is always started
-// before tile i+1):
-//   load     one elected thread issues a TMA 1-D bulk copy (cp.async.bulk + mbarrier complete_tx) of the tile plus a
-//            16-byte halo on each side into shared memory
-//   detect   each thread reads 16-byte granules (LDS.128, conflict-free interleaved mapping), finds zero bytes with
-//            word-parallel arithmetic and only where two zeros precede a byte looks for 03 (emulation prevention)
-//            and 01 (start-code end); start-code bits go to a per-tile bitmap
-//   adjust   granules with a start code within reach (header bytes, the 2-byte tail rule, zeros that belong to a
-//            header) recompute their 16 keep bits from the start-code bitmap (keep_mask_near_sc, annexb_local.cuh)
-//   scan     packed (kept bytes | start codes << 16) block scan: shuffle scan per warp, 32 warp totals by warp 0
-//   chain    decoupled look-back over per-tile descriptors gives the tile's exclusive (kept bytes, NAL index) prefix
-//   compact  the few 512-byte rows that lose bytes are compacted in place in the tile buffer (overlaps the look-back)
-//   store    every row is now `len` contiguous bytes: lanes exchange neighbour words by shuffle so that each lane
-//            writes one aligned 16-byte granule of the destination; only a row's two ragged ends use byte stores
-//   index    threads owning a start code write (start, rbsp offset, first 4 NAL bytes) for NAL k = prefix + rank
-// A tiny finalize kernel turns those into h264b_nal records (lengths are differences of neighbours).
+// The RBSP of a NAL is written at the position of the NAL's own body (h264b_nal.rbsp_off = start + header_bytes), so
+// a span of the stream that holds neither a start code nor an emulation-prevention byte -- all but a few KiB per MB
+// of entropy-coded data -- is an aligned copy.  The kernel is built around that:
+//
+//   pieces   the stream is cut into spans of chunks ("pieces", 128 KiB by default); a warp takes a piece by atomic
+//            ticket and walks its 2 KiB chunks front to back.  Warps never talk to each other: no block barrier, no
+//            look-back.  What a NAL lost in an EARLIER piece is made up for by the post-pass (nal_pieces).
+//   ring     every warp owns a ring of kStages shared-memory slots; lane 0 keeps it full with TMA 1-D bulk loads
+//            (cp.async.bulk + mbarrier complete_tx) of chunk + 16-byte halos, kStages-1 chunks ahead of the consumer
+//   detect   LDS.128 per lane and granule, word-parallel search for two adjacent zero bytes (zero_pair_bits): every
+//            00 00 03 and 00 00 00 01 needs one
+//   clean    no pair anywhere and nothing removed from the open NAL so far: lane 0 hands the slot to the TMA again,
+//            one 2 KiB bulk store straight from shared memory to out + pos (no registers, no STG)
+//   dirty    otherwise the chunk takes the general path: exact masks (granule_masks), start-code bitmap, bit-domain
+//            fix-up near start codes (keep_mask_near_sc), per-row segmented scan of (EPBs | start codes), in-place
+//            compaction of rows that only lose EPBs, shuffle-aligned 16-byte row stores, byte stores and NAL records
+//            (start, EPB count, first 4 bytes, rank in piece) for rows with boundaries
+// Post-passes (tiny): exclusive scan of the per-piece start-code counts, permutation of the records into stream
+// order, h264b_nal records (lengths are differences of neighbours), and the slide of NAL parts described above.
 #include "annexb_local.cuh"
 #include "common.cuh"
 
 namespace h264b {
 
-constexpr int kThreads = 256;
-constexpr int kRows = 4;                          // granules per thread per tile
-constexpr int kGranules = kThreads * kRows;       // 1024
-constexpr int kTile = kGranules * 16;             // 16384 bytes
+constexpr int kRows = 4;                           // 512-byte rows per chunk (one granule per lane and row)
+constexpr int kChunkGran = 32 * kRows;             // 128 granules
+constexpr int kChunk = kChunkGran * 16;            // 2048 bytes
 constexpr int kHalo = 16;
-constexpr int kInBytes = kHalo + kTile + kHalo;   // 16416
-constexpr uint64_t kStatusAgg = 1ull << 62, kStatusPrefix = 2ull << 62, kValueMask = (1ull << 62) - 1;
+constexpr int kSlotBytes = kHalo + kChunk + kHalo; // 2080
+#ifndef H264B_SCAN_STAGES
+#define H264B_SCAN_STAGES 4
+#endif
+#ifndef H264B_SCAN_WARPS
+#define H264B_SCAN_WARPS 4
+#endif
+constexpr int kStages = H264B_SCAN_STAGES;         // ring slots per warp
+constexpr int kWarps = H264B_SCAN_WARPS;           // warps per CTA (independent of each other)
+constexpr uint32_t kMaxSpanChunks = 64;            // piece = 128 KiB for large streams
 
-struct ScanScratchHeader {   // device scratch, zeroed / initialised by scan_init_kernel
-    unsigned int ticket;
-    unsigned int pad;
+struct ScanScratchHeader {   // device scratch, initialised by scan_init_kernel
+    unsigned int ticket;           // next piece
+    unsigned int n_fix;            // entries of fix_list
     unsigned long long first_start;
     unsigned long long total_sc;   // start codes found = slots handed out of the NAL record buffer
     unsigned long long total_kept;
     unsigned long long n_epb;
-    unsigned int n_fix;            // entries of fix_list
-    unsigned int pad2;
-    unsigned long long reserved[2];
+    unsigned long long reserved[3];
 };  // 64 bytes
 
 struct ScanArgs {
@@ -50,98 +58,66 @@ struct ScanArgs {
     uint64_t n;
     uint8_t *out;
     ScanScratchHeader *hdr;
-    uint32_t *tile_tot;        // per tile: packed segmented total (seg_combine format): NAL start? | start codes | EPBs
-    uint32_t *tile_slot;       // per tile: first slot of its records in the unordered record buffer
-    uint32_t *tile_ord;        // per tile: ordinal of its first start code (exclusive scan of the start-code counts)
-    uint32_t *fix_list;        // NAL ordinals whose later pieces must slide left (written by scan_finalize_kernel)
-    // per start code, in slot order (tiles reserve slots with one atomicAdd): written by the main pass
+    uint32_t *piece_epb;       // per piece: EPBs after its last NAL start (or in the whole piece when it has none)
+    uint32_t *piece_nsc;       // per piece: start codes
+    uint32_t *piece_ord;       // per piece: ordinal of its first start code (exclusive scan of piece_nsc)
+    uint32_t *fix_list;        // NAL ordinals whose later parts must slide left (written by scan_finalize_kernel)
+    // per start code, in slot order (chunks reserve slots with one atomicAdd): written by the main pass
     unsigned long long *rec_start;
-    unsigned long long *rec_epb;
+    uint32_t *rec_epb;
     uint32_t *rec_hdr;
+    uint32_t *rec_rank;        // rank of the start code inside its piece
     // the same in stream order (written by nal_permute_kernel, read by scan_finalize_kernel)
     unsigned long long *nal_start;
-    unsigned long long *nal_epb;  // [k]: EPBs removed from the NAL that ends at start code k
+    uint32_t *nal_epb;         // [k]: EPBs removed (within the piece of start code k) from the NAL that ends there
     uint32_t *nal_hdr;
     uint32_t nal_cap;
-    uint32_t n_tiles;
+    uint32_t n_chunks;
+    uint32_t n_pieces;
+    uint32_t span_chunks;      // chunks per piece
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// 16-byte tile descriptors: one 128-bit transaction each way (L2 is the point of coherence: .cg / volatile)
-__device__ __forceinline__ ulonglong2 ld_desc(const ulonglong2 *p) {
-    ulonglong2 v;
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_desc(ulonglong2 *p, unsigned long long x, unsigned long long y) {
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(x), "l"(y) : "memory");
-}
-
 // ------------------------------------------------------------------------------------------------ init
 __global__ void scan_init_kernel(ScanScratchHeader *hdr, uint64_t n) {
     hdr->ticket = 0;
+    hdr->n_fix = 0;
     hdr->first_start = n;
     hdr->total_sc = 0;
     hdr->total_kept = 0;
     hdr->n_epb = 0;
-    hdr->n_fix = 0;
-}
-
-// ------------------------------------------------------------------------------------------------ first start code
-// first_start = 1 + position of the first 00 00 00 01 (bytes before it are not part of any NAL, server.go:68-72).
-// Chunks are visited in order by each CTA and a CTA stops as soon as a smaller position is already known.
-__global__ void __launch_bounds__(256) first_start_kernel(const uint8_t *in, uint64_t n, ScanScratchHeader *hdr) {
-    const uint64_t n_gran = (n + 15) / 16;
-    for (uint64_t chunk = blockIdx.x;; chunk += gridDim.x) {
-        uint64_t g = chunk * 256 + threadIdx.x;
-        if (chunk * 256 >= n_gran) return;
-        if (ld_relaxed(&hdr->first_start) <= chunk * 256 * 16) return;
-        if (g < n_gran) {
-            uint64_t pos = g * 16;
-            uint4 v = *reinterpret_cast<const uint4 *>(in + pos);
-            uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            uint32_t prev = pos ? *reinterpret_cast<const uint32_t *>(in + pos - 4) : 0xFFFFFFFFu;
-            GranuleMasks m = granule_masks(w, prev);
-            if (m.sc) {
-                uint64_t q = pos + (uint64_t)(__ffs(m.sc) - 1);
-                if (q < n) atomicMin(&hdr->first_start, (unsigned long long)(q + 1));
-            }
-        }
-        __syncthreads();
-    }
 }
 
 // ------------------------------------------------------------------------------------------------ main pass
-struct __align__(16) ScanSmem {
-    uint8_t in[kInBytes];                 // [0,16): low halo, [16,16+kTile): tile, then high halo
-    uint16_t scbits[kGranules + 2];       // start-code-end bits per granule, [0] = halo granule before the tile
-    uint32_t row_tot[kRows * 8];          // packed segmented elements per (row, warp); then exclusive prefixes
-    uint8_t row_class[kRows * 8];         // 0 untouched, 1 only EPBs removed, 2 contains NAL boundaries / stream ends
-    unsigned long long nal_slot0;         // first record slot reserved for this tile's start codes
-    uint32_t tile;
-    unsigned long long mbar;
+struct __align__(16) WarpRing {
+    uint8_t slot[kStages][kSlotBytes];    // each: [0,16) low halo, [16,16+kChunk) chunk, high halo
+    unsigned long long mbar[kStages];     // "bytes have landed"
+    unsigned long long slot_pos[kStages]; // stream offset of the chunk in the slot, ~0 = no more work
+    uint32_t slot_piece[kStages];
+    uint16_t scbits[kChunkGran + 2];      // start-code-end bits per granule, [0] = halo granule before the chunk
+    uint16_t pad[6];
 };
+static_assert(sizeof(WarpRing) % 16 == 0, "ring slots must stay 16-byte aligned");
 
-__device__ __forceinline__ void store_row(uint8_t *out, uint64_t o, uint32_t len, const uint32_t w[4], int lane,
-                                          const uint8_t *prev_tail, bool next_joins) {
-    uint32_t wp[4];
-    if ((uint32_t)o & 15u) {  // warp-uniform: only shifted rows need the neighbour's bytes
-#pragma unroll
-        for (int k = 0; k < 4; k++) wp[k] = __shfl_up_sync(0xFFFFFFFFu, w[k], 1);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; k++) wp[k] = 0;
+// TMA bulk store shared -> global (16-byte aligned on both sides, size a multiple of 16)
+__device__ __forceinline__ void bulk_store(uint8_t *dst_global, const uint8_t *src_shared, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global),
+                 "r"(smem_u32(src_shared)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
     }
-    store_row_lane(out, o, len, wp, w, lane, prev_tail, next_joins);
 }
 
 __device__ __forceinline__ uint32_t warp_seg_scan(uint32_t x, int lane) {  // inclusive segmented scan over the warp
@@ -153,263 +129,348 @@ __device__ __forceinline__ uint32_t warp_seg_scan(uint32_t x, int lane) {  // in
     return x;
 }
 
+// The general path is rare for real streams; its pieces are kept out of line so that the hot loop stays small.
+__device__ __noinline__ uint32_t keep_near_sc(const uint8_t *tile_in, uint64_t base, uint64_t gpos, uint32_t e16,
+                                              uint32_t sc_prev, uint32_t sc_own, uint32_t sc_next, uint32_t *epb_eff) {
+    auto get = [&](int64_t p) -> uint32_t { return tile_in[p - (int64_t)base]; };
+    return keep_mask_near_sc(get, (int64_t)gpos, e16, sc_prev, sc_own, sc_next, epb_eff);
+}
 
-__global__ void __launch_bounds__(kThreads, 5) annexb_scan_kernel(ScanArgs a) {
+__device__ __noinline__ void compact_row_in_place(uint8_t *row, const uint8_t *src, uint32_t k16, uint32_t loff) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(src);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    __syncwarp();  // every lane has its bytes in registers before anyone overwrites the span
+    if (k16 == 0xFFFFu && (loff & 3u) == 0) {
+        uint32_t *d = reinterpret_cast<uint32_t *>(row + loff);
+        d[0] = w[0];
+        d[1] = w[1];
+        d[2] = w[2];
+        d[3] = w[3];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            if (k16 & (1u << j)) row[loff++] = (uint8_t)(w[j >> 2] >> ((j & 3) * 8));
+    }
+}
+
+// one lane's granule of a row with NAL boundaries: kept bytes one by one, one record per start-code end
+//   c     EPBs removed so far (in this piece) from the NAL open at the granule's first byte
+//   k     record slot of the first start code of the granule;  rank: its rank inside the piece
+__device__ __noinline__ void store_boundary_granule(const ScanArgs &a, uint64_t gpos, const uint8_t *src, uint32_t k16,
+                                                    uint32_t ee, uint32_t sc, uint64_t c, uint64_t k, uint32_t rank,
+                                                    bool first_of_chunk) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(src);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    store_granule_bytes(a.out, gpos, w, k16, ee, sc, c, [&](int j, uint64_t c_end) {
+        const uint64_t st = gpos + (uint64_t)j + 1;  // the new NAL's first byte
+        if (first_of_chunk) {
+            atomicMin(&a.hdr->first_start, (unsigned long long)st);
+            first_of_chunk = false;
+        }
+        if (k < a.nal_cap) {
+            a.rec_start[k] = st;
+            a.rec_epb[k] = (uint32_t)c_end;  // EPBs removed (in this piece) from the NAL that ends with this start code
+            uint32_t h = 0;                  // its first 4 bytes, from the (L2-resident) input
+#pragma unroll
+            for (int q = 0; q < 4; q++) h |= (uint32_t)(st + q < a.n ? a.in[st + q] : (uint8_t)0xFF) << (8 * q);
+            a.rec_hdr[k] = h;
+            a.rec_rank[k] = rank;
+        }
+        k++;
+        rank++;
+    });
+}
+
+__device__ __noinline__ void store_row(uint8_t *out, uint64_t o, uint32_t len, const uint8_t *src, int lane,
+                                       const uint8_t *prev_tail, bool next_joins) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(src);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t wp[4];
+    if ((uint32_t)o & 15u) {  // warp-uniform: only shifted rows need the neighbour's bytes
+#pragma unroll
+        for (int k = 0; k < 4; k++) wp[k] = __shfl_up_sync(0xFFFFFFFFu, w[k], 1);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) wp[k] = 0;
+    }
+    store_row_lane(out, o, len, wp, w, lane, prev_tail, next_joins);
+}
+
+struct ChunkResult {
+    uint32_t carry_epb;  // EPBs removed from the open NAL since its start / the start of the piece
+    uint32_t piece_nsc;  // start codes of the piece so far
+    uint32_t clean;      // nothing to remove after all and nothing shifted: the caller bulk-stores the chunk
+};
+
+// General path of one chunk (whole warp).  tile_in[i] = s[pos + i] for i in [-16, kChunk + 16), bytes outside the
+// stream read as 0xFF.
+__device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, WarpRing &ring, uint8_t *tile_in, uint64_t pos,
+                                                  uint32_t carry_epb, uint32_t piece_nsc, int lane) {
+    // ---------------------------------------------------------------- exact masks + start-code bitmap
+    uint32_t em[kRows];  // raw EPB mask | start-code mask << 16
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+        const int gi = r * 32 + lane;
+        const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const uint32_t prev = *reinterpret_cast<const uint32_t *>(tile_in + gi * 16 - 4);
+        const GranuleMasks m = granule_masks(w, prev);
+        em[r] = m.e | (m.sc << 16);
+        ring.scbits[gi + 1] = (uint16_t)m.sc;
+    }
+    if (lane < 2) {  // halo granules: only start codes ending in [pos-6, pos-1] and at pos+kChunk matter
+        const int gi = lane ? kChunkGran : -1;
+        const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const uint32_t prev = lane ? *reinterpret_cast<const uint32_t *>(tile_in + gi * 16 - 4) : 0xFFFFFFFFu;
+        ring.scbits[gi + 1] = (uint16_t)granule_masks(w, prev).sc;
+    }
+    __syncwarp();
+
+    // ---------------------------------------------------------------- adjust + classify + per-row segmented scan
+    const bool has_end = pos + kChunk > a.n;  // some granules reach past the stream
+    uint32_t ks[kRows];    // keep mask | start-code mask << 16
+    uint32_t ee[kRows];    // emulation-prevention bytes really removed
+    uint32_t incl[kRows];  // inclusive segmented scan inside the row
+    uint32_t rp[kRows + 1];  // exclusive prefix of each row inside the chunk (warp-uniform); [kRows] = chunk total
+    uint32_t cls = 0;        // 2 bits per row, warp-uniform: 0 untouched, 1 only EPBs removed, 2 boundaries / stream end
+    rp[0] = 0;
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+        const int gi = r * 32 + lane;
+        const uint64_t gpos = pos + (uint64_t)gi * 16;
+        uint32_t e16 = em[r] & 0xFFFFu;
+        uint32_t k16 = ~e16 & 0xFFFFu;
+        // start-code ends q in [g-6, g+16] change what this granule keeps
+        const uint32_t near = ((uint32_t)ring.scbits[gi] >> 10) | ring.scbits[gi + 1] | (ring.scbits[gi + 2] & 1u);
+        if (near)  // header bytes, the 2-byte tail rule and the EPB guard, all in the bit domain
+            k16 = keep_near_sc(tile_in, pos, gpos, e16, ring.scbits[gi], ring.scbits[gi + 1], ring.scbits[gi + 2], &e16);
+        uint32_t sc = em[r] >> 16;
+        if (has_end) {
+            if (gpos >= a.n) {
+                k16 = 0;
+                sc = 0;
+                e16 = 0;
+            } else if (gpos + 16 > a.n) {
+                const uint32_t valid = (1u << (uint32_t)(a.n - gpos)) - 1u;
+                k16 &= valid;
+                sc &= valid;
+                e16 &= valid;
+            }
+        }
+        ks[r] = k16 | (sc << 16);
+        ee[r] = e16;
+        uint32_t x;
+        if (__all_sync(0xFFFFFFFFu, k16 == 0xFFFFu)) {  // nothing removed
+            x = 0;
+        } else if (__all_sync(0xFFFFFFFFu, (k16 | e16) == 0xFFFFu && sc == 0)) {  // only EPBs removed
+            cls |= 1u << (2 * r);
+            x = warp_seg_scan(bits_popc(e16), lane);
+        } else {
+            cls |= 2u << (2 * r);
+            x = warp_seg_scan(seg_element(e16, sc), lane);
+        }
+        incl[r] = x;
+        rp[r + 1] = seg_combine(rp[r], __shfl_sync(0xFFFFFFFFu, x, 31));
+    }
+    ChunkResult res;
+    res.carry_epb = carry_epb;
+    res.piece_nsc = piece_nsc;
+    res.clean = 0;
+    if (cls == 0 && carry_epb == 0) {  // false alarm (00 00 xx with xx > 3): a verbatim copy after all
+        res.clean = 1;
+        return res;
+    }
+    const uint32_t total = rp[kRows];
+    const uint32_t n_sc = (total >> 16) & 0x1FFFu;
+    unsigned long long slot0 = 0;
+    if (n_sc) {
+        if (lane == 0) slot0 = atomicAdd(&a.hdr->total_sc, (unsigned long long)n_sc);
+        slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+    }
+
+    // ---------------------------------------------------------------- in-place compaction of EPB-only rows
+    // inside their own 512-byte span of the slot: afterwards they are `len` contiguous bytes like untouched rows
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+        if (((cls >> (2 * r)) & 3u) != 1u) continue;  // warp-uniform
+        const int gi = r * 32 + lane;
+        const uint32_t loff = 16u * (uint32_t)lane - (incl[r] - bits_popc(ee[r]));  // kept bytes of the lanes before
+        compact_row_in_place(tile_in + r * 512, tile_in + gi * 16, ks[r] & 0xFFFFu, loff);
+    }
+    __syncwarp();
+
+    // ---------------------------------------------------------------- store rows + NAL records
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+        const int gi = r * 32 + lane;
+        const uint32_t c2 = (cls >> (2 * r)) & 3u;
+        if (c2 != 2u) {
+            // one contiguous run of len bytes, shifted left by the EPBs removed from its NAL so far in this piece
+            const uint64_t c_row = seg_apply(rp[r], carry_epb);
+            const uint32_t removed = c2 ? ((rp[r + 1] - rp[r]) & 0x7FFFu) : 0u;
+            const uint64_t o = pos + 512u * (uint32_t)r - c_row;
+            const uint8_t *prev_tail = nullptr;
+            if (r > 0 && ((cls >> (2 * r - 2)) & 3u) != 2u) {
+                const uint32_t prev_removed = (rp[r] - rp[r - 1]) & 0x7FFFu;
+                prev_tail = tile_in + 512 * r - prev_removed;
+            }
+            const bool next_joins = r < kRows - 1 && ((cls >> (2 * r + 2)) & 3u) != 2u;
+            store_row(a.out, o, 512u - removed, tile_in + gi * 16, lane, prev_tail, next_joins);
+        } else {
+            uint32_t ex = __shfl_up_sync(0xFFFFFFFFu, incl[r], 1);
+            if (lane == 0) ex = 0;
+            const uint32_t pre = seg_combine(rp[r], ex);
+            const uint64_t c = seg_apply(pre, carry_epb);
+            const uint32_t before = (pre >> 16) & 0x1FFFu;  // start codes of the chunk before this granule
+            store_boundary_granule(a, pos + (uint64_t)gi * 16, tile_in + gi * 16, ks[r] & 0xFFFFu, ee[r], ks[r] >> 16, c,
+                                   slot0 + before, piece_nsc + before, before == 0);
+        }
+    }
+    res.carry_epb = seg_apply(total, carry_epb);
+    res.piece_nsc = piece_nsc + n_sc;
+    return res;
+}
+
+__global__ void __launch_bounds__(kWarps * 32) annexb_scan_kernel(ScanArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    ScanSmem &sm = *reinterpret_cast<ScanSmem *>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t mbar = smem_u32(&sm.mbar);
-
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpRing &ring = reinterpret_cast<WarpRing *>(smem_raw)[warp];
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; s++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ring.mbar[s])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    const uint64_t e0 = ld_relaxed(&a.hdr->first_start);  // written by first_start_kernel (previous launch)
+    __syncwarp();
     const uint64_t n16 = (a.n + 15) & ~15ull;
-    uint32_t parity = 0;
 
-    for (;;) {
-        // ---------------------------------------------------------------- ticket + TMA load
-        if (tid == 0) sm.tile = atomicAdd(&a.hdr->ticket, 1u);
-        __syncthreads();  // also: everybody is done with the previous tile's shared memory
-        const uint32_t tile = sm.tile;
-        if (tile >= a.n_tiles) break;
-        const uint64_t base = (uint64_t)tile * kTile;
-        const uint64_t lo = tile ? base - kHalo : base;
-        uint64_t hi = base + kTile + kHalo;
+    // ---------------------------------------------------------------- producer (lane 0): pieces by ticket, chunks in order
+    uint32_t p_piece = 0, p_next = 0, p_end = 0;  // chunks [p_next, p_end) of piece p_piece are still to be loaded
+    bool p_done = false;
+    auto produce = [&](int s) {
+        if (!p_done && p_next == p_end) {
+            p_piece = atomicAdd(&a.hdr->ticket, 1u);
+            if (p_piece < a.n_pieces) {
+                p_next = p_piece * a.span_chunks;
+                p_end = p_next + a.span_chunks < a.n_chunks ? p_next + a.span_chunks : a.n_chunks;
+            } else {
+                p_done = true;
+            }
+        }
+        const uint32_t bar = smem_u32(&ring.mbar[s]);
+        if (p_done) {  // an arrival without bytes: the consumer sees "no more work"
+            ring.slot_pos[s] = ~0ull;
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+            return;
+        }
+        const uint64_t pos = (uint64_t)p_next * kChunk;
+        p_next++;
+        ring.slot_pos[s] = pos;
+        ring.slot_piece[s] = p_piece;
+        const uint64_t lo = pos ? pos - kHalo : 0;
+        uint64_t hi = pos + kChunk + kHalo;
         if (hi > n16) hi = n16;
-        if (tid == 0) {
-            uint32_t bytes = (uint32_t)(hi - lo);
-            uint32_t dst = smem_u32(sm.in + (lo - (base - kHalo)));
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-            asm volatile(
-                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                "l"(a.in + lo), "r"(bytes), "r"(mbar)
-                : "memory");
-        }
-        // bytes outside the stream read as 0xFF (they match no predicate): low halo of tile 0 ...
-        const bool edge_tile = tile == 0 || hi < base + kTile + kHalo || hi > a.n;  // CTA-uniform
-        if (tile == 0 && tid < 4) reinterpret_cast<uint32_t *>(sm.in)[tid] = 0xFFFFFFFFu;
-        // ... and everything the copy does not write at the end of the stream
-        const uint32_t loaded_end = (uint32_t)(hi - (base - kHalo));  // offset in sm.in
-        for (uint32_t o = loaded_end + tid * 4; o < (uint32_t)kInBytes; o += kThreads * 4)
-            *reinterpret_cast<uint32_t *>(sm.in + o) = 0xFFFFFFFFu;
-        {
-            uint32_t done = 0;
-            while (!done) {
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                    "selp.u32 %0, 1, 0, p;\n\t}"
-                    : "=r"(done)
-                    : "r"(mbar), "r"(parity)
-                    : "memory");
-            }
-            parity ^= 1;
-        }
-        if (edge_tile) {
-            if (hi > a.n && hi - a.n < 16) {  // the last 16-byte granule holds bytes past n: blank them
-                uint32_t first_bad = (uint32_t)(a.n - (base - kHalo));
-                if (tid < 16 && first_bad + tid < loaded_end) sm.in[first_bad + tid] = 0xFF;
-            }
-            __syncthreads();  // the 0xFF fills above are plain stores other threads read
-        }
-        uint8_t *tile_in = sm.in + kHalo;  // tile_in[i] = s[base + i], valid for i in [-16, kTile+16)
-#ifdef H264B_EXP_LOADONLY
-        continue;
-#endif
+        const uint32_t bytes = (uint32_t)(hi - lo);
+        const uint32_t dst = smem_u32(ring.slot[s] + (lo + kHalo - pos));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+            "l"(a.in + lo), "r"(bytes), "r"(bar)
+            : "memory");
+    };
+    if (lane == 0) {
+#pragma unroll 1
+        for (int s = 0; s < kStages - 1; s++) produce(s);
+    }
 
-        // ---------------------------------------------------------------- detect
-        uint32_t em[kRows];  // raw EPB mask | start-code mask << 16
+    // ---------------------------------------------------------------- consumer (whole warp)
+    uint32_t cur_piece = 0xFFFFFFFFu;
+    uint32_t carry_epb = 0, piece_nsc = 0;
+#pragma unroll 1
+    for (uint32_t it = 0;; it++) {
+        const int s = (int)(it % kStages);
+        mbar_wait(smem_u32(&ring.mbar[s]), (it / kStages) & 1u);
+        const uint64_t pos = ring.slot_pos[s];
+        if (pos == ~0ull) break;
+        const uint32_t piece = ring.slot_piece[s];
+        if (piece != cur_piece) {
+            if (cur_piece != 0xFFFFFFFFu && lane == 0) {
+                a.piece_epb[cur_piece] = carry_epb;
+                a.piece_nsc[cur_piece] = piece_nsc;
+            }
+            cur_piece = piece;
+            carry_epb = 0;
+            piece_nsc = 0;
+        }
+        uint8_t *buf = ring.slot[s];
+        uint8_t *tile_in = buf + kHalo;  // tile_in[i] = s[pos + i], valid for i in [-16, kChunk+16)
+
+        // bytes outside the stream read as 0xFF (they match no predicate)
+        const bool edge = pos == 0 || pos + kChunk + kHalo > a.n;  // warp-uniform
+        if (edge) {
+            if (pos == 0 && lane < 4) reinterpret_cast<uint32_t *>(buf)[lane] = 0xFFFFFFFFu;
+            uint64_t hi = pos + kChunk + kHalo;
+            if (hi > n16) hi = n16;
+            const uint32_t loaded_end = (uint32_t)(hi + kHalo - pos);  // offset in the slot
+            for (uint32_t o = loaded_end + lane * 4; o < (uint32_t)kSlotBytes; o += 128)
+                *reinterpret_cast<uint32_t *>(buf + o) = 0xFFFFFFFFu;
+            if (hi > a.n) {  // the last 16-byte granule holds bytes past n: blank them
+                const uint32_t first_bad = (uint32_t)(a.n + kHalo - pos);
+                if (lane < 16 && first_bad + lane < loaded_end) buf[first_bad + lane] = 0xFF;
+            }
+            __syncwarp();
+        }
+#ifdef H264B_EXP_LOADONLY
+        bool clean = false;
+        if (pos == 0x123456789ull) clean = true;
+#else
+        // ---------------------------------------------------------------- detect: two adjacent zero bytes anywhere?
+        uint32_t pairs = 0;
+#ifndef H264B_EXP_NODETECT
 #pragma unroll
         for (int r = 0; r < kRows; r++) {
-            const int gi = r * kThreads + tid;
+            const int gi = r * 32 + lane;
             const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
             const uint32_t prev = *reinterpret_cast<const uint32_t *>(tile_in + gi * 16 - 4);
-#ifdef H264B_EXP_NODETECT
-            GranuleMasks m;
-            m.e = (w[0] == 0x12345678u && prev == 0x9ABCDEFu) ? 1u : 0u;
-            m.sc = 0;
-#else
-            GranuleMasks m = granule_masks(w, prev);
+            pairs |= zero_pair_bits(w, prev);
+        }
+        if (lane == 0)  // a start code ending in the last bytes before the chunk still reaches into it
+            pairs |= zero_pair_bits_tail8(*reinterpret_cast<const uint32_t *>(buf + 8),
+                                          *reinterpret_cast<const uint32_t *>(buf + 12));
 #endif
-            em[r] = m.e | (m.sc << 16);
-            sm.scbits[gi + 1] = (uint16_t)m.sc;
+        bool clean = !__any_sync(0xFFFFFFFFu, pairs != 0) && carry_epb == 0 && pos + kChunk <= a.n;
+        if (!clean) {
+            const ChunkResult res = general_chunk(a, ring, tile_in, pos, carry_epb, piece_nsc, lane);
+            carry_epb = res.carry_epb;
+            piece_nsc = res.piece_nsc;
+            clean = res.clean != 0;
+            // generic-proxy writes to the slot (fills, compaction) are ordered before the TMA writes that reuse it
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        } else if (edge) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
-        if (tid < 2) {  // halo granules: only start codes ending in [base-6, base-1] and at base+kTile matter
-            const int gi = tid ? kGranules : -1;
-            const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            const uint32_t prev = tid ? *reinterpret_cast<const uint32_t *>(tile_in + gi * 16 - 4) : 0xFFFFFFFFu;
-            sm.scbits[gi + 1] = (uint16_t)granule_masks(w, prev).sc;
-        }
-        __syncthreads();
-
-        // ---------------------------------------------------------------- adjust + classify + per-row segmented scan
-        const bool tile_has_head = base < e0;            // some bytes precede the first NAL
-        const bool tile_has_end = base + kTile > a.n;    // some granules reach past the stream
-        auto get = [&](int64_t p) -> uint32_t { return tile_in[p - (int64_t)base]; };
-        uint32_t ks[kRows];    // keep mask | start-code mask << 16
-        uint32_t ee[kRows];    // emulation-prevention bytes really removed
-        uint32_t incl[kRows];  // inclusive segmented scan inside the (row, warp) group
-        uint32_t cls = 0;      // 2 bits per row, warp-uniform
-#pragma unroll
-        for (int r = 0; r < kRows; r++) {
-            const int gi = r * kThreads + tid;
-            const uint64_t gpos = base + (uint64_t)gi * 16;
-            uint32_t e16 = em[r] & 0xFFFFu;
-            uint32_t k16 = ~e16 & 0xFFFFu;
-            // start-code ends q in [g-6, g+16] change what this granule keeps
-            const uint32_t near = ((uint32_t)sm.scbits[gi] >> 10) | sm.scbits[gi + 1] | (sm.scbits[gi + 2] & 1u);
-            if (near)  // rare: header bytes, the 2-byte tail rule and the EPB guard, all in the bit domain
-                k16 = keep_mask_near_sc(get, (int64_t)gpos, e16, sm.scbits[gi], sm.scbits[gi + 1], sm.scbits[gi + 2],
-                                        &e16);
-            uint32_t sc = em[r] >> 16;
-            if (tile_has_head) {
-                if (gpos + 16 <= e0) {
-                    k16 = 0;
-                    e16 = 0;
-                } else if (gpos < e0) {
-                    const uint32_t m = ~((1u << (uint32_t)(e0 - gpos)) - 1u);
-                    k16 &= m;
-                    e16 &= m;
-                }
-            }
-            if (tile_has_end) {
-                if (gpos >= a.n) {
-                    k16 = 0;
-                    sc = 0;
-                    e16 = 0;
-                } else if (gpos + 16 > a.n) {
-                    const uint32_t valid = (1u << (uint32_t)(a.n - gpos)) - 1u;
-                    k16 &= valid;
-                    sc &= valid;
-                    e16 &= valid;
-                }
-            }
-            ks[r] = k16 | (sc << 16);
-            ee[r] = e16;
-            uint32_t x;
-            if (__all_sync(0xFFFFFFFFu, k16 == 0xFFFFu)) {  // the usual row: nothing removed
-                x = 0;
-            } else if (__all_sync(0xFFFFFFFFu, (k16 | e16) == 0xFFFFu && sc == 0)) {  // only EPBs removed
-                cls |= 1u << (2 * r);
-                x = warp_seg_scan(bits_popc(e16), lane);
-            } else {
-                cls |= 2u << (2 * r);
-                x = warp_seg_scan(seg_element(e16, sc), lane);
-            }
-            incl[r] = x;
-            if (lane == 31) {
-                sm.row_tot[r * 8 + warp] = x;
-                sm.row_class[r * 8 + warp] = (uint8_t)((cls >> (2 * r)) & 3u);
-            }
-        }
-        __syncthreads();
-
-        // ---------------------------------------------------------------- tile carry (warp 0) | in-place compaction
-        if (warp == 0) {
-            uint32_t x = sm.row_tot[lane];
-            const uint32_t own = x;
-            x = warp_seg_scan(x, lane);
-            uint32_t ex = __shfl_up_sync(0xFFFFFFFFu, x, 1);  // exclusive prefix of row `lane` inside the tile
-            if (lane == 0) ex = 0;
-            (void)own;
-            sm.row_tot[lane] = ex;
-            const uint32_t total = __shfl_sync(0xFFFFFFFFu, x, 31);
-            const bool has_start = (total >> 31) != 0;
-            const unsigned long long t_val = total & 0x7FFFu, t_nsc = (total >> 16) & 0x1FFFu;
-            // No inter-tile communication: a tile counts the EPBs of its open NAL from zero (see nal_pieces in
-            // annexb_local.cuh for how NALs that span tiles are finished).  It leaves its packed total for the
-            // post-pass and, when it holds start codes, reserves that many record slots with one atomicAdd.
-            if (lane == 0) {
-                a.tile_tot[tile] = total;
-                if (t_nsc) {
-                    sm.nal_slot0 = atomicAdd(&a.hdr->total_sc, t_nsc);
-                    a.tile_slot[tile] = (uint32_t)sm.nal_slot0;
-                }
-            }
-            (void)has_start;
-            (void)t_val;
-        }
-        // Rows that only lose emulation-prevention bytes are compacted in place inside their own 512-byte span of the
-        // tile buffer (nobody else reads it any more): afterwards they are `len` contiguous bytes like untouched rows.
-#pragma unroll
-        for (int r = 0; r < kRows; r++) {
-            if (((cls >> (2 * r)) & 3u) != 1u) continue;  // warp-uniform
-            const int gi = r * kThreads + tid;
-            const uint32_t k16 = ks[r] & 0xFFFFu;
-            const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            __syncwarp();  // every lane has its bytes in registers before anyone overwrites the span
-            uint32_t loff = 16u * (uint32_t)lane - (incl[r] - bits_popc(ee[r]));  // kept bytes of the lanes before
-            uint8_t *row = tile_in + (r * kThreads + warp * 32) * 16;
-            if (k16 == 0xFFFFu && (loff & 3u) == 0) {
-                uint32_t *d = reinterpret_cast<uint32_t *>(row + loff);
-                d[0] = w[0];
-                d[1] = w[1];
-                d[2] = w[2];
-                d[3] = w[3];
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; j++)
-                    if (k16 & (1u << j)) row[loff++] = (uint8_t)(w[j >> 2] >> ((j & 3) * 8));
-            }
-        }
-        __syncthreads();
-        const uint64_t carry_in = 0;  // per-tile counting (see above)
-        const uint64_t slot0 = sm.nal_slot0;
-
-        // ---------------------------------------------------------------- store rows + NAL index
-#ifdef H264B_EXP_NOSTORE
-        if (slot0 == 0x123456789ull)
 #endif
-#pragma unroll
-        for (int r = 0; r < kRows; r++) {
-            const int gi = r * kThreads + tid;
-            const int t = r * 8 + warp;
-            const uint32_t rowpre = sm.row_tot[t];  // warp-uniform
-            const uint32_t c2 = (cls >> (2 * r)) & 3u;
-            const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            if (c2 != 2u) {
-                // one contiguous run of len bytes, shifted left by the EPBs removed from its NAL so far
-                const uint64_t c_row = (rowpre >> 31) ? (uint64_t)(rowpre & 0x7FFFu) : carry_in + (rowpre & 0x7FFFu);
-                const uint32_t removed = __shfl_sync(0xFFFFFFFFu, incl[r], 31) & 0x7FFFu;
-                const uint64_t o = base + 512u * (uint32_t)t - c_row;
-                const uint8_t *prev_tail = nullptr;
-                if (t > 0 && sm.row_class[t - 1] != 2) {
-                    const uint32_t prev_removed = (rowpre - sm.row_tot[t - 1]) & 0x7FFFu;
-                    prev_tail = tile_in + 512 * t - prev_removed;
-                }
-                const bool next_joins = t < kRows * 8 - 1 && sm.row_class[t + 1] != 2;
-                store_row(a.out, o, 512u - removed, w, lane, prev_tail, next_joins);
-            } else {
-                uint32_t ex = __shfl_up_sync(0xFFFFFFFFu, incl[r], 1);
-                if (lane == 0) ex = 0;
-                const uint32_t pre = seg_combine(rowpre, ex);
-                const uint64_t c = (pre >> 31) ? (uint64_t)(pre & 0x7FFFu) : carry_in + (pre & 0x7FFFu);
-                const uint64_t gpos = base + (uint64_t)gi * 16;
-                uint64_t k = slot0 + ((pre >> 16) & 0x1FFFu);  // record slot of the first NAL that starts in this granule
-                store_granule_bytes(a.out, gpos, w, ks[r] & 0xFFFFu, ee[r], ks[r] >> 16, c, [&](int j, uint64_t c_end) {
-                    if (k < a.nal_cap) {
-                        const uint64_t st = gpos + (uint64_t)j + 1;  // the new NAL's first byte
-                        a.rec_start[k] = st;
-                        a.rec_epb[k] = c_end;  // EPBs removed from the NAL that ends with this start code
-                        uint32_t h = 0;  // its first 4 bytes, from the (L2-resident) input
-#pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            h |= (uint32_t)(st + q < a.n ? a.in[st + q] : (uint8_t)0xFF) << (8 * q);
-                        a.rec_hdr[k] = h;
-                    }
-                    k++;
-                });
-            }
+        __syncwarp();  // every lane is done reading (and writing) the slot
+        if (lane == 0) {
+#ifndef H264B_EXP_NOSTORE
+            // the bulk of a real stream leaves through the TMA: one 2 KiB bulk store straight from the slot
+            if (clean) bulk_store(a.out + pos, tile_in, kChunk);
+#endif
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // all but the newest store have finished reading shared memory: the slot of the previous chunk is free
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            produce((int)((it + kStages - 1) % kStages));
         }
-        // the loop-top __syncthreads orders these shared-memory reads before the next tile's writes
+    }
+    if (lane == 0) {
+        if (cur_piece != 0xFFFFFFFFu) {
+            a.piece_epb[cur_piece] = carry_epb;
+            a.piece_nsc[cur_piece] = piece_nsc;
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
 
@@ -459,55 +520,57 @@ __device__ __forceinline__ void decode_nal_header(uint32_t hdr4, h264b_nal &o, h
     *ext = e;
 }
 
-// Post-pass 1: ordinal of every tile's first start code = exclusive scan of the per-tile start-code counts (one CTA;
-// the array has one entry per 16 KiB of stream; warps read it coalesced, 1024 entries per step).
-__global__ void __launch_bounds__(1024) nal_order_kernel(const uint32_t *tile_tot, uint32_t *tile_ord, uint32_t n_tiles) {
+// Post-pass 1: ordinal of every piece's first start code = exclusive scan of the per-piece start-code counts.  One CTA;
+// the array has one entry per piece (128 KiB of stream): every thread sums a contiguous run, one block scan, done.
+__global__ void __launch_bounds__(1024) piece_order_kernel(const uint32_t *piece_nsc, uint32_t *piece_ord,
+                                                           uint32_t n_pieces) {
     __shared__ uint32_t warp_sum[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t running = 0;  // identical in every thread
-    for (uint32_t base = 0; base < n_tiles; base += 1024) {
-        const uint32_t i = base + (uint32_t)tid;
-        const uint32_t c = i < n_tiles ? ((tile_tot[i] >> 16) & 0x1FFFu) : 0u;
-        uint32_t x = c;
+    const uint32_t per = (n_pieces + 1023u) / 1024u;
+    const uint32_t lo = (uint32_t)tid * per < n_pieces ? (uint32_t)tid * per : n_pieces;
+    const uint32_t hi = lo + per < n_pieces ? lo + per : n_pieces;
+    uint32_t own = 0;
+    for (uint32_t i = lo; i < hi; i++) own += piece_nsc[i];
+    uint32_t x = own;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-            if (lane >= d) x += y;
-        }
-        if (lane == 31) warp_sum[warp] = x;
-        __syncthreads();
-        uint32_t w = warp_sum[lane], wi = w;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sum[warp] = x;
+    __syncthreads();
+    uint32_t w = warp_sum[lane], wi = w;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wi, d);
-            if (lane >= d) wi += y;
-        }
-        const uint32_t wbase = __shfl_sync(0xFFFFFFFFu, wi - w, warp);
-        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, wi, 31);
-        if (i < n_tiles) tile_ord[i] = running + wbase + x - c;
-        running += tot;
-        __syncthreads();
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+        if (lane >= d) wi += y;
+    }
+    uint32_t run = __shfl_sync(0xFFFFFFFFu, wi - w, warp) + x - own;  // start codes before this thread's run
+    for (uint32_t i = lo; i < hi; i++) {
+        piece_ord[i] = run;
+        run += piece_nsc[i];
     }
 }
 
-// Post-pass 2: move every tile's records from its reserved slots to their ordinals (stream order).
+// Post-pass 2: move every record from its slot to its ordinal (stream order): ordinal = first ordinal of the piece
+// that holds the start code + the record's rank inside that piece.
 __global__ void __launch_bounds__(256) nal_permute_kernel(ScanArgs a) {
     const uint64_t cap = a.nal_cap;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < a.n_tiles; t += gridDim.x * blockDim.x) {
-        const uint32_t c = (a.tile_tot[t] >> 16) & 0x1FFFu;
-        if (!c) continue;
-        const uint64_t slot = a.tile_slot[t], ord = a.tile_ord[t];
-        for (uint32_t i = 0; i < c; i++) {
-            if (slot + i < cap && ord + i < cap) {
-                a.nal_start[ord + i] = a.rec_start[slot + i];
-                a.nal_epb[ord + i] = a.rec_epb[slot + i];
-                a.nal_hdr[ord + i] = a.rec_hdr[slot + i];
-            }
+    uint64_t K = a.hdr->total_sc;
+    if (K > cap) K = cap;
+    const uint64_t piece_bytes = (uint64_t)a.span_chunks * kChunk;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < K; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t st = a.rec_start[i];
+        const uint64_t ord = (uint64_t)a.piece_ord[(st - 1) / piece_bytes] + a.rec_rank[i];
+        if (ord < cap) {
+            a.nal_start[ord] = st;
+            a.nal_epb[ord] = a.rec_epb[i];
+            a.nal_hdr[ord] = a.rec_hdr[i];
         }
     }
 }
 
-// Post-pass 3: the h264b_nal records; NALs whose later tile pieces have to slide left are queued for post-pass 4.
+// Post-pass 3: the h264b_nal records; NALs whose later parts have to slide left are queued for post-pass 4.
 __global__ void __launch_bounds__(256) scan_finalize_kernel(ScanArgs a, h264b_nal *nals, h264b_nal_ext *ext,
                                                              h264b_scan_summary *summary) {
     const uint64_t K = a.hdr->total_sc;
@@ -524,7 +587,8 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(ScanArgs a, h264b_na
         o.num_bytes = (uint32_t)(next - o.start);
         decode_nal_header(a.nal_hdr[k], o, ext ? &ext[k] : nullptr);
         bool fix = false;
-        const uint64_t removed = nal_pieces(o.start, next, o.header_bytes, a.nal_epb[k + 1], a.tile_tot, (uint64_t)kTile,
+        const uint64_t removed = nal_pieces(o.start, next, o.header_bytes, a.nal_epb[k + 1], a.piece_epb,
+                                            (uint64_t)a.span_chunks * kChunk,
                                             [&](uint64_t, uint64_t, uint64_t) { fix = true; });
         if (fix) a.fix_list[atomicAdd(&a.hdr->n_fix, 1u)] = (uint32_t)k;
         // body = NumBytes - HeaderBytes - 2 bytes (a NAL shorter than that has no body); its RBSP sits at the body's
@@ -548,16 +612,20 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(ScanArgs a, h264b_na
     }
 }
 
-// Post-pass 4: slide the later pieces of the queued NALs left (one CTA per NAL, pieces in stream order, 4 KiB at a
+// Post-pass 4: slide the later parts of the queued NALs left (one CTA per NAL, parts in stream order, 4 KiB at a
 // time: everything is read into registers before anything is written, so the overlapping move is safe).
-__global__ void __launch_bounds__(256) nal_fixup_kernel(ScanArgs a) {
+__global__ void __launch_bounds__(256) nal_fixup_kernel(ScanArgs a, h264b_scan_summary *summary) {
     const uint32_t n_fix = a.hdr->n_fix;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // totals of scan_finalize_kernel (complete: previous launch)
+        summary->n_epb = a.hdr->n_epb;
+        summary->rbsp_bytes = a.hdr->total_kept;  // RBSP bytes of all emitted NAL units
+    }
     for (uint32_t f = blockIdx.x; f < n_fix; f += gridDim.x) {
         const uint64_t k = a.fix_list[f];
         const uint64_t st = a.nal_start[k], next = a.nal_start[k + 1];
         h264b_nal o;
         decode_nal_header(a.nal_hdr[k], o, nullptr);
-        nal_pieces(st, next, o.header_bytes, a.nal_epb[k + 1], a.tile_tot, (uint64_t)kTile,
+        nal_pieces(st, next, o.header_bytes, a.nal_epb[k + 1], a.piece_epb, (uint64_t)a.span_chunks * kChunk,
                    [&](uint64_t ps, uint64_t len, uint64_t G) {
                        for (uint64_t off = 0; off < len; off += 256 * 16) {
                            const uint64_t p = ps + off + (uint64_t)threadIdx.x * 16;
@@ -575,10 +643,6 @@ __global__ void __launch_bounds__(256) nal_fixup_kernel(ScanArgs a) {
     }
 }
 
-__global__ void scan_summary_epb_kernel(const ScanScratchHeader *hdr, h264b_scan_summary *summary) {
-    summary->n_epb = hdr->n_epb;
-    summary->rbsp_bytes = hdr->total_kept;  // RBSP bytes of all emitted NAL units
-}
 
 // ------------------------------------------------------------------------------------------------ frames (NewNalUnit)
 // One CTA per frame; RBSP of frame i is written at rbsp + off[i] (never longer than the frame).
@@ -693,10 +757,10 @@ __global__ void __launch_bounds__(1024) slice_select_kernel(const h264b_nal *nal
 
 // ------------------------------------------------------------------------------------------------ launchers
 struct ScratchOffsets {
-    uint64_t tile_tot, tile_slot, tile_ord, fix_list, rec_start, rec_epb, rec_hdr, nal_start, nal_epb, nal_hdr, total;
+    uint64_t piece_epb, piece_nsc, piece_ord, fix_list, rec_start, rec_epb, rec_hdr, rec_rank, nal_start, nal_epb,
+        nal_hdr, total;
 };
-static ScratchOffsets scratch_layout(uint64_t n, uint32_t nal_cap) {
-    const uint64_t n_tiles = (n + kTile - 1) / kTile;
+static ScratchOffsets scratch_layout(uint64_t n_pieces, uint32_t nal_cap) {
     ScratchOffsets o;
     uint64_t p = sizeof(ScanScratchHeader);
     auto take = [&](uint64_t bytes) {
@@ -704,15 +768,16 @@ static ScratchOffsets scratch_layout(uint64_t n, uint32_t nal_cap) {
         p = (p + bytes + 15) & ~15ull;
         return at;
     };
-    o.tile_tot = take(n_tiles * 4);
-    o.tile_slot = take(n_tiles * 4);
-    o.tile_ord = take(n_tiles * 4);
+    o.piece_epb = take(n_pieces * 4);
+    o.piece_nsc = take(n_pieces * 4);
+    o.piece_ord = take(n_pieces * 4);
     o.fix_list = take((uint64_t)nal_cap * 4);
     o.rec_start = take((uint64_t)nal_cap * 8);
-    o.rec_epb = take((uint64_t)nal_cap * 8);
+    o.rec_epb = take((uint64_t)nal_cap * 4);
     o.rec_hdr = take((uint64_t)nal_cap * 4);
+    o.rec_rank = take((uint64_t)nal_cap * 4);
     o.nal_start = take((uint64_t)nal_cap * 8);
-    o.nal_epb = take((uint64_t)nal_cap * 8);
+    o.nal_epb = take((uint64_t)nal_cap * 4);
     o.nal_hdr = take((uint64_t)nal_cap * 4);
     o.total = (p + 255) & ~255ull;
     return o;
@@ -723,8 +788,31 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     (void)flags;
     if (((uintptr_t)d_stream & 15) || ((uintptr_t)d_rbsp & 15))
         return set_error(ctx, H264B_E_INVALID, "annexb_scan: d_stream and d_rbsp must be 16-byte aligned");
-    if (n >= (1ull << 45)) return set_error(ctx, H264B_E_INVALID, "annexb_scan: stream too long");
-    const ScratchOffsets so = scratch_layout(n, nal_cap);
+    if (n >= (1ull << 42)) return set_error(ctx, H264B_E_INVALID, "annexb_scan: stream too long");
+
+    // launch shape: as many warps as fit, each with its own ring of slots
+    static bool attr_set = false;
+    const size_t smem = sizeof(WarpRing) * kWarps;
+    if (!attr_set) {
+        H264B_CUDA(ctx, cudaFuncSetAttribute(annexb_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int occ = 0;
+    H264B_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, annexb_scan_kernel, kWarps * 32, smem));
+    if (occ < 1) occ = 1;
+    const uint64_t max_ctas = (uint64_t)ctx->sm_count * occ;
+
+    // pieces: 128 KiB for large streams; smaller when the stream would otherwise leave most warps without work
+    const uint64_t n_chunks = (n + kChunk - 1) / kChunk;
+    uint64_t span = ctx->scan_span_chunks;
+    if (!span) {
+        span = n_chunks / (max_ctas * kWarps * 4);
+        if (span > kMaxSpanChunks) span = kMaxSpanChunks;
+        if (span < 1) span = 1;
+    }
+    const uint64_t n_pieces = (n_chunks + span - 1) / span;
+
+    const ScratchOffsets so = scratch_layout(n_pieces, nal_cap);
     if (so.total > ctx->scan_scratch_bytes) {
         if (ctx->scan_scratch) {
             H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -736,63 +824,43 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
         ctx->scan_scratch_bytes = so.total;
     }
     uint8_t *s = (uint8_t *)ctx->scan_scratch;
-    const uint64_t n_tiles = (n + kTile - 1) / kTile;
     ScanArgs a;
     a.in = d_stream;
     a.n = n;
     a.out = d_rbsp;
     a.hdr = (ScanScratchHeader *)s;
-    a.tile_tot = (uint32_t *)(s + so.tile_tot);
-    a.tile_slot = (uint32_t *)(s + so.tile_slot);
-    a.tile_ord = (uint32_t *)(s + so.tile_ord);
+    a.piece_epb = (uint32_t *)(s + so.piece_epb);
+    a.piece_nsc = (uint32_t *)(s + so.piece_nsc);
+    a.piece_ord = (uint32_t *)(s + so.piece_ord);
     a.fix_list = (uint32_t *)(s + so.fix_list);
     a.rec_start = (unsigned long long *)(s + so.rec_start);
-    a.rec_epb = (unsigned long long *)(s + so.rec_epb);
+    a.rec_epb = (uint32_t *)(s + so.rec_epb);
     a.rec_hdr = (uint32_t *)(s + so.rec_hdr);
+    a.rec_rank = (uint32_t *)(s + so.rec_rank);
     a.nal_start = (unsigned long long *)(s + so.nal_start);
-    a.nal_epb = (unsigned long long *)(s + so.nal_epb);
+    a.nal_epb = (uint32_t *)(s + so.nal_epb);
     a.nal_hdr = (uint32_t *)(s + so.nal_hdr);
     a.nal_cap = nal_cap;
-    a.n_tiles = (uint32_t)n_tiles;
+    a.n_chunks = (uint32_t)n_chunks;
+    a.n_pieces = (uint32_t)n_pieces;
+    a.span_chunks = (uint32_t)span;
 
     scan_init_kernel<<<1, 1, 0, ctx->stream>>>(a.hdr, n);
     H264B_LAUNCH_CHECK(ctx, "scan_init_kernel");
-    if (n_tiles) {
-        const uint64_t chunks = (n + 4095) / 4096;
-        const int fs_blocks = (int)(chunks < (uint64_t)ctx->sm_count * 4 ? chunks : (uint64_t)ctx->sm_count * 4);
-        first_start_kernel<<<fs_blocks, 256, 0, ctx->stream>>>(d_stream, n, a.hdr);
-        H264B_LAUNCH_CHECK(ctx, "first_start_kernel");
-
-        static bool attr_set = false;
-        const size_t smem = sizeof(ScanSmem);
-        if (!attr_set) {
-            H264B_CUDA(ctx, cudaFuncSetAttribute(annexb_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)smem));
-            attr_set = true;
-        }
-        int occ = 0;
-        H264B_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, annexb_scan_kernel, kThreads, smem));
-        if (occ < 1) occ = 1;
-        uint64_t grid = (uint64_t)ctx->sm_count * occ;
-        if (grid > n_tiles) grid = n_tiles;
-        annexb_scan_kernel<<<(int)grid, kThreads, smem, ctx->stream>>>(a);
+    if (n_pieces) {
+        uint64_t grid = (n_pieces + kWarps - 1) / kWarps;
+        if (grid > max_ctas) grid = max_ctas;
+        annexb_scan_kernel<<<(int)grid, kWarps * 32, smem, ctx->stream>>>(a);
         H264B_LAUNCH_CHECK(ctx, "annexb_scan_kernel");
-        nal_order_kernel<<<1, 1024, 0, ctx->stream>>>(a.tile_tot, a.tile_ord, a.n_tiles);
-        H264B_LAUNCH_CHECK(ctx, "nal_order_kernel");
-        uint64_t pb = (n_tiles + 255) / 256;
-        if (pb > (uint64_t)ctx->sm_count * 8) pb = (uint64_t)ctx->sm_count * 8;
-        nal_permute_kernel<<<(int)pb, 256, 0, ctx->stream>>>(a);
+        piece_order_kernel<<<1, 1024, 0, ctx->stream>>>(a.piece_nsc, a.piece_ord, a.n_pieces);
+        H264B_LAUNCH_CHECK(ctx, "piece_order_kernel");
+        nal_permute_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a);
         H264B_LAUNCH_CHECK(ctx, "nal_permute_kernel");
     }
-    int fin_blocks = ctx->sm_count * 2;
-    scan_finalize_kernel<<<fin_blocks, 256, 0, ctx->stream>>>(a, d_nals, d_ext, d_summary);
+    scan_finalize_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a, d_nals, d_ext, d_summary);
     H264B_LAUNCH_CHECK(ctx, "scan_finalize_kernel");
-    if (n_tiles > 1) {
-        nal_fixup_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(a);
-        H264B_LAUNCH_CHECK(ctx, "nal_fixup_kernel");
-    }
-    scan_summary_epb_kernel<<<1, 1, 0, ctx->stream>>>(a.hdr, d_summary);
-    H264B_LAUNCH_CHECK(ctx, "scan_summary_epb_kernel");
+    nal_fixup_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(a, d_summary);
+    H264B_LAUNCH_CHECK(ctx, "nal_fixup_kernel");
     return H264B_OK;
 }
 
@@ -817,4 +885,7 @@ int launch_slice_select(h264b_ctx *ctx, const h264b_nal *d_nals, const h264b_sca
 
 }  // namespace h264b
 
-extern "C" uint64_t h264b_annexb_scratch_bytes(uint64_t n) { return h264b::scratch_layout(n, 0).total; }
+// upper bound: the smallest pieces (one chunk each); the record arrays are sized by nal_cap on top of this
+extern "C" uint64_t h264b_annexb_scratch_bytes(uint64_t n) {
+    return h264b::scratch_layout((n + h264b::kChunk - 1) / h264b::kChunk, 0).total;
+}

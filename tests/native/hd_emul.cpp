@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../h264decode_b200/csrc/annexb_local.cuh"
@@ -87,151 +88,217 @@ int64_t emul_stream(const uint8_t *s, int64_t n, uint64_t *nal_start, uint64_t *
 
 uint32_t emul_header_bytes(uint32_t b0, uint32_t b1) { return nal_header_bytes(b0, b1); }
 
-// Tile-by-tile emulation of annexb_scan_kernel (same phases, same helper functions; warps and lanes as loops, the
-// look-back replaced by a running carry).  RBSP bytes of a NAL land at the NAL body's own position in `out`
+// Piece-by-piece, chunk-by-chunk emulation of annexb_scan_kernel (same phases, same helper functions; the lanes of a
+// warp as loops).  Pieces are visited in a pseudo-random order (order_seed) because the product hands them to warps
+// by atomic ticket; records go to "slots" in visiting order and are permuted into stream order exactly as
+// piece_order_kernel / nal_permute_kernel do.  RBSP bytes of a NAL land at the NAL body's own position in `out`
 // (position-preserving layout); `out` holds out_shift + n + 64 bytes, pre-filled by the caller so that stray writes
 // are detectable; out_shift (a multiple of 16 in the product) shifts the whole destination to exercise alignment.
-// nal_start / nal_epb / nal_hdr (cap entries) receive the per-start-code index.  Returns the number of start codes.
+// nal_start / nal_epb / nal_hdr (cap entries) receive the per-start-code index (nal_epb: the NAL's EPB total, as
+// scan_finalize_kernel computes it).  Returns the number of start codes.
 int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out_base, int64_t out_shift, uint64_t *nal_start,
-                          uint64_t *nal_epb, uint32_t *nal_hdr, int64_t cap) {
-    const int kThreads = 256, kRows = 4, kGran = kThreads * kRows, kTile = kGran * 16, kHalo = 16;
+                          uint64_t *nal_epb, uint32_t *nal_hdr, int64_t cap, int64_t span_chunks, uint32_t order_seed,
+                          int64_t *stats) {
+    const int kRows = 4, kGran = 32 * kRows, kChunk = kGran * 16, kHalo = 16;
     uint8_t *out = out_base + out_shift;
     auto gets = [&](int64_t p) -> uint32_t { return (p >= 0 && p < n) ? s[p] : 0xFFu; };
-    int64_t e0 = n;
-    for (int64_t p = 3; p < n; p++)
-        if (s[p] == 1 && s[p - 1] == 0 && s[p - 2] == 0 && s[p - 3] == 0) {
-            e0 = p + 1;
-            break;
+    const int64_t n_chunks = (n + kChunk - 1) / kChunk;
+    if (span_chunks < 1) span_chunks = 1;
+    const int64_t n_pieces = (n_chunks + span_chunks - 1) / span_chunks;
+    const uint64_t piece_bytes = (uint64_t)span_chunks * kChunk;
+    std::vector<uint32_t> piece_epb((size_t)n_pieces + 1, 0), piece_nsc((size_t)n_pieces + 1, 0),
+        piece_ord((size_t)n_pieces + 1, 0);
+    std::vector<uint64_t> rec_start;
+    std::vector<uint32_t> rec_epb, rec_hdr, rec_rank;
+    std::vector<int64_t> order((size_t)n_pieces);
+    for (int64_t i = 0; i < n_pieces; i++) order[i] = i;
+    uint32_t lcg = order_seed;
+    if (order_seed)
+        for (int64_t i = n_pieces - 1; i > 0; i--) {
+            lcg = lcg * 1664525u + 1013904223u;
+            std::swap(order[i], order[(lcg >> 8) % (uint32_t)(i + 1)]);
         }
-    const int64_t n_tiles = (n + kTile - 1) / kTile;
-    const uint64_t carry = 0;  // every tile counts the EPBs of its open NAL from zero
-    uint64_t nal0 = 0;         // NAL numbering (the product orders the records in a post-pass)
-    std::vector<uint32_t> tile_tot((size_t)n_tiles + 1, 0);
-    std::vector<uint8_t> buf(kHalo + kTile + kHalo);
+    int64_t n_fast = 0, n_false_alarm = 0, n_general = 0;
+    std::vector<uint8_t> buf(kHalo + kChunk + kHalo);
     std::vector<uint16_t> scb(kGran + 2);
-    for (int64_t tile = 0; tile < n_tiles; tile++) {
-        const int64_t base = tile * kTile;
-        for (int i = 0; i < kHalo + kTile + kHalo; i++) buf[i] = (uint8_t)gets(base - kHalo + i);
-        uint8_t *tile_in = buf.data() + kHalo;
-        std::vector<uint32_t> em(kGran), ks(kGran), ee(kGran), incl(kGran);
-        auto masks_at = [&](int gi, bool have_prev) {
-            uint32_t w[4];
-            memcpy(w, tile_in + gi * 16, 16);
-            uint32_t prev = 0xFFFFFFFFu;
-            if (have_prev) memcpy(&prev, tile_in + gi * 16 - 4, 4);
-            return granule_masks(w, prev);
-        };
-        for (int gi = 0; gi < kGran; gi++) {
-            GranuleMasks m = masks_at(gi, true);
-            em[gi] = m.e | (m.sc << 16);
-            scb[gi + 1] = (uint16_t)m.sc;
-        }
-        scb[0] = (uint16_t)masks_at(-1, false).sc;
-        scb[kGran + 1] = (uint16_t)masks_at(kGran, true).sc;
-        auto get = [&](int64_t p) -> uint32_t { return tile_in[p - base]; };
-        uint32_t row_tot[32], row_pre[32], cls[32];
-        for (int t = 0; t < 32; t++) {
-            const int r = t / 8, warp = t % 8;
-            bool all_full = true, epb_only = true;
-            for (int lane = 0; lane < 32; lane++) {
-                const int gi = r * kThreads + warp * 32 + lane;
-                const int64_t gpos = base + (int64_t)gi * 16;
-                uint32_t e16 = em[gi] & 0xFFFFu;
-                uint32_t k16 = ~e16 & 0xFFFFu;
-                const uint32_t near = ((uint32_t)scb[gi] >> 10) | scb[gi + 1] | (scb[gi + 2] & 1u);
-                if (near) k16 = keep_mask_near_sc(get, gpos, e16, scb[gi], scb[gi + 1], scb[gi + 2], &e16);
-                uint32_t sc = em[gi] >> 16;
-                if (base < e0) {
-                    if (gpos + 16 <= e0) { k16 = 0; e16 = 0; }
-                    else if (gpos < e0) { uint32_t m = ~((1u << (uint32_t)(e0 - gpos)) - 1u); k16 &= m; e16 &= m; }
-                }
-                if (base + kTile > n) {
-                    if (gpos >= n) { k16 = 0; sc = 0; e16 = 0; }
-                    else if (gpos + 16 > n) { uint32_t v = (1u << (uint32_t)(n - gpos)) - 1u; k16 &= v; sc &= v; e16 &= v; }
-                }
-                ks[gi] = k16 | (sc << 16);
-                ee[gi] = e16;
-                if (k16 != 0xFFFFu) all_full = false;
-                if (!((k16 | e16) == 0xFFFFu && sc == 0)) epb_only = false;
+    for (int64_t oi = 0; oi < n_pieces; oi++) {
+        const int64_t piece = order[oi];
+        uint32_t carry_epb = 0, pnsc = 0;
+        const int64_t c_end = std::min((piece + 1) * span_chunks, n_chunks);
+        for (int64_t chunk = piece * span_chunks; chunk < c_end; chunk++) {
+            const int64_t pos = chunk * kChunk;
+            for (int i = 0; i < kHalo + kChunk + kHalo; i++) buf[i] = (uint8_t)gets(pos - kHalo + i);
+            uint8_t *tile_in = buf.data() + kHalo;
+            // ---- detect (fast path)
+            uint32_t pairs = 0;
+            for (int gi = 0; gi < kGran; gi++) {
+                uint32_t w[4], prev;
+                memcpy(w, tile_in + gi * 16, 16);
+                memcpy(&prev, tile_in + gi * 16 - 4, 4);
+                pairs |= zero_pair_bits(w, prev);
             }
-            cls[t] = all_full ? 0 : (epb_only ? 1 : 2);
-            uint32_t run = 0;
-            for (int lane = 0; lane < 32; lane++) {
-                const int gi = r * kThreads + warp * 32 + lane;
-                const uint32_t el = cls[t] == 0 ? 0u : (cls[t] == 1 ? bits_popc(ee[gi]) : seg_element(ee[gi], ks[gi] >> 16));
-                run = lane ? seg_combine(run, el) : el;
-                incl[gi] = run;
+            {
+                uint32_t lo, hi;
+                memcpy(&lo, buf.data() + 8, 4);
+                memcpy(&hi, buf.data() + 12, 4);
+                pairs |= zero_pair_bits_tail8(lo, hi);
             }
-            row_tot[t] = run;
-        }
-        uint32_t total = 0;
-        for (int t = 0; t < 32; t++) { row_pre[t] = total; total = t ? seg_combine(total, row_tot[t]) : row_tot[t]; }
-        // in-place compaction of EPB-only rows
-        for (int t = 0; t < 32; t++) {
-            if (cls[t] != 1) continue;
-            const int r = t / 8, warp = t % 8;
-            uint32_t w[32][4];
-            for (int lane = 0; lane < 32; lane++) memcpy(w[lane], tile_in + (r * kThreads + warp * 32 + lane) * 16, 16);
-            uint8_t *row = tile_in + 512 * t;
-            for (int lane = 0; lane < 32; lane++) {
-                const int gi = r * kThreads + warp * 32 + lane;
-                const uint32_t k16 = ks[gi] & 0xFFFFu;
-                uint32_t loff = 16u * lane - (incl[gi] - bits_popc(ee[gi]));
-                for (int j = 0; j < 16; j++)
-                    if (k16 & (1u << j)) row[loff++] = (uint8_t)(w[lane][j >> 2] >> ((j & 3) * 8));
-            }
-        }
-        for (int t = 0; t < 32; t++) {
-            const int r = t / 8, warp = t % 8;
-            const uint32_t rowpre = row_pre[t];
-            uint32_t w[32][4];
-            for (int lane = 0; lane < 32; lane++) memcpy(w[lane], tile_in + (512 * t + lane * 16), 16);
-            if (cls[t] != 2) {
-                const uint64_t c_row = (rowpre >> 31) ? (uint64_t)(rowpre & 0x7FFFu) : carry + (rowpre & 0x7FFFu);
-                const uint32_t removed = incl[r * kThreads + warp * 32 + 31] & 0x7FFFu;
-                const uint64_t o = (uint64_t)base + 512u * t - c_row;
-                const uint8_t *prev_tail = nullptr;
-                if (t > 0 && cls[t - 1] != 2) prev_tail = tile_in + 512 * t - ((rowpre - row_pre[t - 1]) & 0x7FFFu);
-                const bool next_joins = t < 31 && cls[t + 1] != 2;
-                for (int lane = 0; lane < 32; lane++)
-                    store_row_lane(out, o, 512u - removed, lane ? w[lane - 1] : w[0], w[lane], lane, prev_tail, next_joins);
+            bool clean = pairs == 0 && carry_epb == 0 && pos + kChunk <= n;
+            if (clean) {
+                n_fast++;
             } else {
-                for (int lane = 0; lane < 32; lane++) {
-                    const int gi = r * kThreads + warp * 32 + lane;
-                    const uint32_t ex = lane ? incl[gi - 1] : 0u;
-                    const uint32_t pre = seg_combine(rowpre, ex);
-                    const uint64_t c = (pre >> 31) ? (uint64_t)(pre & 0x7FFFu) : carry + (pre & 0x7FFFu);
-                    const uint64_t gpos = (uint64_t)base + (uint64_t)gi * 16;
-                    uint64_t k = nal0 + ((pre >> 16) & 0x1FFFu);
-                    store_granule_bytes(out, gpos, w[lane], ks[gi] & 0xFFFFu, ee[gi], ks[gi] >> 16, c,
-                                        [&](int j, uint64_t c_end) {
-                                            if ((int64_t)k < cap) {
-                                                const uint64_t st = gpos + j + 1;
-                                                nal_start[k] = st;
-                                                nal_epb[k] = c_end;
-                                                uint32_t h = 0;
-                                                for (int q = 0; q < 4; q++) h |= gets((int64_t)st + q) << (8 * q);
-                                                nal_hdr[k] = h;
-                                            }
-                                            k++;
-                                        });
+                // ---- general path: exact masks
+                std::vector<uint32_t> em(kGran), ks(kGran), ee(kGran), incl(kGran);
+                auto masks_at = [&](int gi, bool have_prev) {
+                    uint32_t w[4];
+                    memcpy(w, tile_in + gi * 16, 16);
+                    uint32_t prev = 0xFFFFFFFFu;
+                    if (have_prev) memcpy(&prev, tile_in + gi * 16 - 4, 4);
+                    return granule_masks(w, prev);
+                };
+                for (int gi = 0; gi < kGran; gi++) {
+                    GranuleMasks m = masks_at(gi, true);
+                    em[gi] = m.e | (m.sc << 16);
+                    scb[gi + 1] = (uint16_t)m.sc;
+                }
+                scb[0] = (uint16_t)masks_at(-1, false).sc;
+                scb[kGran + 1] = (uint16_t)masks_at(kGran, true).sc;
+                auto get = [&](int64_t p) -> uint32_t { return tile_in[p - pos]; };
+                uint32_t rp[kRows + 1], cls[kRows];
+                rp[0] = 0;
+                for (int r = 0; r < kRows; r++) {
+                    bool all_full = true, epb_only = true;
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int gi = r * 32 + lane;
+                        const int64_t gpos = pos + (int64_t)gi * 16;
+                        uint32_t e16 = em[gi] & 0xFFFFu;
+                        uint32_t k16 = ~e16 & 0xFFFFu;
+                        const uint32_t near = ((uint32_t)scb[gi] >> 10) | scb[gi + 1] | (scb[gi + 2] & 1u);
+                        if (near) k16 = keep_mask_near_sc(get, gpos, e16, scb[gi], scb[gi + 1], scb[gi + 2], &e16);
+                        uint32_t sc = em[gi] >> 16;
+                        if (pos + kChunk > n) {
+                            if (gpos >= n) { k16 = 0; sc = 0; e16 = 0; }
+                            else if (gpos + 16 > n) { uint32_t v = (1u << (uint32_t)(n - gpos)) - 1u; k16 &= v; sc &= v; e16 &= v; }
+                        }
+                        ks[gi] = k16 | (sc << 16);
+                        ee[gi] = e16;
+                        if (k16 != 0xFFFFu) all_full = false;
+                        if (!((k16 | e16) == 0xFFFFu && sc == 0)) epb_only = false;
+                    }
+                    cls[r] = all_full ? 0 : (epb_only ? 1 : 2);
+                    uint32_t run = 0;
+                    for (int lane = 0; lane < 32; lane++) {
+                        const int gi = r * 32 + lane;
+                        const uint32_t el = cls[r] == 0 ? 0u : (cls[r] == 1 ? bits_popc(ee[gi]) : seg_element(ee[gi], ks[gi] >> 16));
+                        run = lane ? seg_combine(run, el) : el;
+                        incl[gi] = run;
+                    }
+                    rp[r + 1] = seg_combine(rp[r], run);
+                }
+                bool all0 = true;
+                for (int r = 0; r < kRows; r++) all0 = all0 && cls[r] == 0;
+                if (all0 && carry_epb == 0) {
+                    clean = true;
+                    n_false_alarm++;
+                } else {
+                    n_general++;
+                    const uint32_t total = rp[kRows];
+                    const uint32_t n_sc = (total >> 16) & 0x1FFFu;
+                    const uint64_t slot0 = rec_start.size();
+                    rec_start.resize(slot0 + n_sc, 0);
+                    rec_epb.resize(slot0 + n_sc, 0);
+                    rec_hdr.resize(slot0 + n_sc, 0);
+                    rec_rank.resize(slot0 + n_sc, 0);
+                    // in-place compaction of EPB-only rows
+                    for (int r = 0; r < kRows; r++) {
+                        if (cls[r] != 1) continue;
+                        uint32_t w[32][4];
+                        for (int lane = 0; lane < 32; lane++) memcpy(w[lane], tile_in + (r * 32 + lane) * 16, 16);
+                        uint8_t *row = tile_in + 512 * r;
+                        for (int lane = 0; lane < 32; lane++) {
+                            const int gi = r * 32 + lane;
+                            const uint32_t k16 = ks[gi] & 0xFFFFu;
+                            uint32_t loff = 16u * lane - (incl[gi] - bits_popc(ee[gi]));
+                            for (int j = 0; j < 16; j++)
+                                if (k16 & (1u << j)) row[loff++] = (uint8_t)(w[lane][j >> 2] >> ((j & 3) * 8));
+                        }
+                    }
+                    for (int r = 0; r < kRows; r++) {
+                        uint32_t w[32][4];
+                        for (int lane = 0; lane < 32; lane++) memcpy(w[lane], tile_in + (512 * r + lane * 16), 16);
+                        if (cls[r] != 2) {
+                            const uint64_t c_row = seg_apply(rp[r], carry_epb);
+                            const uint32_t removed = cls[r] ? ((rp[r + 1] - rp[r]) & 0x7FFFu) : 0u;
+                            const uint64_t o = (uint64_t)pos + 512u * r - c_row;
+                            const uint8_t *prev_tail = nullptr;
+                            if (r > 0 && cls[r - 1] != 2) prev_tail = tile_in + 512 * r - ((rp[r] - rp[r - 1]) & 0x7FFFu);
+                            const bool next_joins = r < kRows - 1 && cls[r + 1] != 2;
+                            for (int lane = 0; lane < 32; lane++)
+                                store_row_lane(out, o, 512u - removed, lane ? w[lane - 1] : w[0], w[lane], lane, prev_tail, next_joins);
+                        } else {
+                            for (int lane = 0; lane < 32; lane++) {
+                                const int gi = r * 32 + lane;
+                                const uint32_t ex = lane ? incl[gi - 1] : 0u;
+                                const uint32_t pre = seg_combine(rp[r], ex);
+                                const uint64_t c = seg_apply(pre, carry_epb);
+                                const uint32_t before = (pre >> 16) & 0x1FFFu;
+                                const uint64_t gpos = (uint64_t)pos + (uint64_t)gi * 16;
+                                uint64_t k = slot0 + before;
+                                uint32_t rank = pnsc + before;
+                                store_granule_bytes(out, gpos, w[lane], ks[gi] & 0xFFFFu, ee[gi], ks[gi] >> 16, c,
+                                                    [&](int j, uint64_t c_end2) {
+                                                        const uint64_t st = gpos + j + 1;
+                                                        rec_start[k] = st;
+                                                        rec_epb[k] = (uint32_t)c_end2;
+                                                        uint32_t h = 0;
+                                                        for (int q = 0; q < 4; q++) h |= gets((int64_t)st + q) << (8 * q);
+                                                        rec_hdr[k] = h;
+                                                        rec_rank[k] = rank;
+                                                        k++;
+                                                        rank++;
+                                                    });
+                            }
+                        }
+                    }
+                    carry_epb = seg_apply(total, carry_epb);
+                    pnsc += n_sc;
                 }
             }
+            if (clean) memcpy(out + pos, tile_in, kChunk);  // the TMA bulk store
         }
-        tile_tot[tile] = total;
-        nal0 += (total >> 16) & 0x1FFFu;
+        piece_epb[piece] = carry_epb;
+        piece_nsc[piece] = pnsc;
     }
-    // post-pass: NALs that span tiles -- slide their later pieces left and total their EPB counts (nal_fixup_kernel,
-    // scan_finalize_kernel)
-    const int64_t K = (int64_t)nal0 < cap ? (int64_t)nal0 : cap;
-    std::vector<uint64_t> totals((size_t)K + 1, 0);
+    // post-pass 1 + 2: ordinals, permutation into stream order
+    uint32_t run = 0;
+    for (int64_t t = 0; t < n_pieces; t++) {
+        piece_ord[t] = run;
+        run += piece_nsc[t];
+    }
+    const int64_t Kall = (int64_t)rec_start.size();
+    std::vector<uint32_t> epb_local((size_t)std::min(Kall, cap) + 1, 0);
+    for (int64_t i = 0; i < Kall; i++) {
+        const uint64_t ord = (uint64_t)piece_ord[(rec_start[i] - 1) / piece_bytes] + rec_rank[i];
+        if ((int64_t)ord < cap) {
+            nal_start[ord] = rec_start[i];
+            epb_local[ord] = rec_epb[i];
+            nal_hdr[ord] = rec_hdr[i];
+        }
+    }
+    // post-pass 3 + 4: NALs that span pieces -- slide their later parts left and total their EPB counts
+    const int64_t K = Kall < cap ? Kall : cap;
+    for (int64_t k = 0; k < K; k++) nal_epb[k] = 0;
     for (int64_t k = 0; k + 1 < K; k++) {
         const uint32_t H = nal_header_bytes(nal_hdr[k] & 0xFF, (nal_hdr[k] >> 8) & 0xFF);
-        totals[k + 1] = nal_pieces(nal_start[k], nal_start[k + 1], H, nal_epb[k + 1], tile_tot.data(), (uint64_t)kTile,
-                                   [&](uint64_t ps, uint64_t len, uint64_t G) { memmove(out + ps - G, out + ps, len); });
+        nal_epb[k + 1] = nal_pieces(nal_start[k], nal_start[k + 1], H, epb_local[k + 1], piece_epb.data(), piece_bytes,
+                                    [&](uint64_t ps, uint64_t len, uint64_t G) { memmove(out + ps - G, out + ps, len); });
     }
-    for (int64_t k = 1; k < K; k++) nal_epb[k] = totals[k];
-    return (int64_t)nal0;
+    if (stats) {
+        stats[0] = n_fast;
+        stats[1] = n_false_alarm;
+        stats[2] = n_general;
+    }
+    return Kall;
 }
 
 // NewNalUnit on one frame with keep_byte_frame; returns rbsp length

@@ -37,7 +37,7 @@ def emul():
                               C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.emul_stream_tiles.restype = C.c_int64
     L.emul_stream_tiles.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
-                                    C.c_int64]
+                                    C.c_int64, C.c_int64, C.c_uint32, C.c_void_p]
     L.emul_frame.restype = C.c_int64
     L.emul_frame.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     L.emul_cabac.restype = None
@@ -65,12 +65,13 @@ def check_stream(L, s):
     # the kernel's tile pipeline (position-preserving RBSP layout: each NAL's RBSP at its body's own position)
     s8 = np.ascontiguousarray(s, dtype=np.uint8)
     n_or = len(nal["start"])
-    for shift in (0, 16, 5):
+    # (destination shift, chunks per piece, piece visiting order): pieces of 1, 2, 3 and 64 chunks, shuffled or not
+    for shift, span, seed in ((0, 1, 0), (16, 2, 7), (5, 3, 1234567), (0, 64, 99)):
         out = np.full(len(s8) + 96 + shift, 0xEE, np.uint8)
         cap = len(s8) // 4 + 2
         t_st, t_epb, t_hd = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64), np.zeros(cap, np.uint32)
         Kt = L.emul_stream_tiles(s8.ctypes.data, len(s8), out.ctypes.data, shift, t_st.ctypes.data, t_epb.ctypes.data,
-                                 t_hd.ctypes.data, cap)
+                                 t_hd.ctypes.data, cap, span, seed, None)
         assert max(Kt, 1) - 1 == n_or
         written = np.zeros(len(out), bool)
         for k in range(n_or):
@@ -137,7 +138,7 @@ def test_local_split_strip_kats(emul):
     check_stream(emul, np.tile(np.array([0, 0, 0, 1], np.uint8), 40))
     check_stream(emul, np.concatenate([np.array([0, 0, 0, 1, 0x65], np.uint8), np.tile(np.array([0, 0, 3], np.uint8), 40),
                                        np.array([0, 0, 0, 1], np.uint8)]))
-    # one NAL over several 16 KiB tiles that loses an EPB every third byte / only in its first tile / only late
+    # one NAL over several pieces that loses an EPB every third byte / only in its first tile / only late
     sc, hdr = np.array([0, 0, 0, 1], np.uint8), np.array([0x65], np.uint8)
     rng = np.random.default_rng(77)
     body = rng.integers(4, 256, 60000).astype(np.uint8)

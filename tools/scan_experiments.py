@@ -12,10 +12,9 @@ sys.path.insert(0, ROOT)
 VARIANTS = {
     "full": [],
     "loadonly": ["-DH264B_EXP_LOADONLY"],
-    "nolookback": ["-DH264B_EXP_NOLOOKBACK"],
     "nostore": ["-DH264B_EXP_NOSTORE"],
     "nodetect": ["-DH264B_EXP_NODETECT"],
-    "nolookback_nostore": ["-DH264B_EXP_NOLOOKBACK", "-DH264B_EXP_NOSTORE"],
+    "nodetect_nostore": ["-DH264B_EXP_NODETECT", "-DH264B_EXP_NOSTORE"],
 }
 OUTDIR = os.path.join(ROOT, "h264decode_b200", "exp")
 
