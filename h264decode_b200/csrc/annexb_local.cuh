@@ -124,21 +124,41 @@ H264B_HD GranuleMasks granule_masks(const uint32_t w[4], uint32_t prev) {
     return m;
 }
 
-// Cheap filter in front of granule_masks: non-zero iff some byte p of the granule has s[p] == 0 && s[p-1] == 0 (prev =
-// the 4 bytes before the granule).  Every emulation-prevention byte and every start-code end at p, p+1 or p+2 needs such
-// a pair, so a span of the stream without one is copied verbatim (the fast path of annexb_scan_kernel).
+// Cheap filter in front of granule_masks: does some byte p of a span have s[p] == 0 && s[p-1] == 0?  Every
+// emulation-prevention byte and every start-code end at p, p+1 or p+2 needs such a pair, so a span of the stream
+// without one is copied verbatim (the fast path of annexb_scan_kernel).  Two adjacent zero bytes are a zero 16-bit
+// half of either the word itself or the word shifted by one byte, so a running per-halfword minimum over both views
+// (one VIMNMX3.U16x2 per word on sm_100a) ends with a zero half iff the span holds a pair.
 H264B_HD uint32_t funnel_l8(uint32_t lo, uint32_t hi) { return (hi << 8) | (lo >> 24); }
-H264B_HD uint32_t zero_pair_bits(const uint32_t w[4], uint32_t prev) {
-    const uint32_t zp = zero_bytes(prev), z0 = zero_bytes(w[0]), z1 = zero_bytes(w[1]), z2 = zero_bytes(w[2]),
-                   z3 = zero_bytes(w[3]);
-    return (z0 & funnel_l8(zp, z0)) | (z1 & funnel_l8(z0, z1)) | (z2 & funnel_l8(z1, z2)) | (z3 & funnel_l8(z2, z3));
+H264B_HD uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    return __vimin3_u16x2(a, b, c);
+#else
+    uint32_t lo = a & 0xFFFFu, hi = a >> 16;
+    if ((b & 0xFFFFu) < lo) lo = b & 0xFFFFu;
+    if ((c & 0xFFFFu) < lo) lo = c & 0xFFFFu;
+    if ((b >> 16) < hi) hi = b >> 16;
+    if ((c >> 16) < hi) hi = c >> 16;
+    return lo | (hi << 16);
+#endif
+}
+// acc: running minimum (start with 0xFFFFFFFF); w: a 16-byte granule; prev: the 4 bytes before it
+H264B_HD uint32_t zero_pair_acc(uint32_t acc, const uint32_t w[4], uint32_t prev) {
+    acc = min3_u16x2(acc, w[0], funnel_l8(prev, w[0]));
+    acc = min3_u16x2(acc, w[1], funnel_l8(w[0], w[1]));
+    acc = min3_u16x2(acc, w[2], funnel_l8(w[1], w[2]));
+    acc = min3_u16x2(acc, w[3], funnel_l8(w[2], w[3]));
+    return acc;
 }
 // the same for the last 7 positions of the 8 bytes (lo, hi) that precede a chunk: a start code ending there still
 // reaches into the chunk with its NAL header and its emulation-prevention guard
-H264B_HD uint32_t zero_pair_bits_tail8(uint32_t lo, uint32_t hi) {
-    const uint32_t zl = zero_bytes(lo), zh = zero_bytes(hi);
-    return (zl & (zl << 8)) | (zh & funnel_l8(zl, zh));
+H264B_HD uint32_t zero_pair_acc_tail8(uint32_t acc, uint32_t lo, uint32_t hi) {
+    // pairs (b-8,b-7) .. (b-2,b-1): halves of lo, of hi, and of the 4 bytes b-7 .. b-4 (the pair (b-9,b-8) is out of reach:
+    // the byte shifted in below is made non-zero)
+    acc = min3_u16x2(acc, lo, (lo << 8) | 0xFFu);
+    return min3_u16x2(acc, hi, funnel_l8(lo, hi));
 }
+H264B_HD bool acc_has_pair(uint32_t acc) { return (acc & 0xFFFFu) == 0u || (acc >> 16) == 0u; }
 
 // keep mask of a granule at stream position gpos when start codes end within [gpos-6, gpos+16], in the bit domain
 // (same result as 16 x keep_byte_stream, checked exhaustively on the CPU by tests/test_hd_logic.py):

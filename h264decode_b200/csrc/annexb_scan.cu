@@ -28,20 +28,23 @@
 
 namespace h264b {
 
-constexpr int kRows = 4;                           // 512-byte rows per chunk (one granule per lane and row)
-constexpr int kChunkGran = 32 * kRows;             // 128 granules
-constexpr int kChunk = kChunkGran * 16;            // 2048 bytes
-constexpr int kHalo = 16;
-constexpr int kSlotBytes = kHalo + kChunk + kHalo; // 2080
+#ifndef H264B_SCAN_ROWS
+#define H264B_SCAN_ROWS 4
+#endif
 #ifndef H264B_SCAN_STAGES
 #define H264B_SCAN_STAGES 4
 #endif
 #ifndef H264B_SCAN_WARPS
 #define H264B_SCAN_WARPS 4
 #endif
+constexpr int kRows = H264B_SCAN_ROWS;             // 512-byte rows per chunk (one granule per lane and row), <= 16
+constexpr int kChunkGran = 32 * kRows;             // 128 granules
+constexpr int kChunk = kChunkGran * 16;            // 2048 bytes
+constexpr int kHalo = 16;
+constexpr int kSlotBytes = kHalo + kChunk + kHalo; // 2080
 constexpr int kStages = H264B_SCAN_STAGES;         // ring slots per warp
 constexpr int kWarps = H264B_SCAN_WARPS;           // warps per CTA (independent of each other)
-constexpr uint32_t kMaxSpanChunks = 64;            // piece = 128 KiB for large streams
+constexpr uint32_t kMaxSpanBytes = 128 * 1024;     // piece size for large streams
 
 struct ScanScratchHeader {   // device scratch, initialised by scan_init_kernel
     unsigned int ticket;           // next piece
@@ -92,13 +95,12 @@ __global__ void scan_init_kernel(ScanScratchHeader *hdr, uint64_t n) {
 // ------------------------------------------------------------------------------------------------ main pass
 struct __align__(16) WarpRing {
     uint8_t slot[kStages][kSlotBytes];    // each: [0,16) low halo, [16,16+kChunk) chunk, high halo
+    ulonglong2 meta[kStages];             // .x = stream offset of the chunk in the slot (~0: no more work), .y = its piece
     unsigned long long mbar[kStages];     // "bytes have landed"
-    unsigned long long slot_pos[kStages]; // stream offset of the chunk in the slot, ~0 = no more work
-    uint32_t slot_piece[kStages];
     uint16_t scbits[kChunkGran + 2];      // start-code-end bits per granule, [0] = halo granule before the chunk
-    uint16_t pad[6];
+    uint16_t pad[(8 - (kChunkGran + 2 + 4 * kStages) % 8) % 8];
 };
-static_assert(sizeof(WarpRing) % 16 == 0, "ring slots must stay 16-byte aligned");
+static_assert(sizeof(WarpRing) % 16 == 0 && kSlotBytes % 16 == 0, "ring slots must stay 16-byte aligned");
 
 // TMA bulk store shared -> global (16-byte aligned on both sides, size a multiple of 16)
 __device__ __forceinline__ void bulk_store(uint8_t *dst_global, const uint8_t *src_shared, uint32_t bytes) {
@@ -204,8 +206,23 @@ struct ChunkResult {
 
 // General path of one chunk (whole warp).  tile_in[i] = s[pos + i] for i in [-16, kChunk + 16), bytes outside the
 // stream read as 0xFF.
-__device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, WarpRing &ring, uint8_t *tile_in, uint64_t pos,
+__device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, uint16_t *scbits, uint8_t *buf, uint64_t pos,
                                                   uint32_t carry_epb, uint32_t piece_nsc, int lane) {
+    uint8_t *tile_in = buf + kHalo;
+    if (pos == 0 || pos + kChunk + kHalo > a.n) {  // bytes outside the stream read as 0xFF (they match no predicate)
+        const uint64_t n16 = (a.n + 15) & ~15ull;
+        if (pos == 0 && lane < 4) reinterpret_cast<uint32_t *>(buf)[lane] = 0xFFFFFFFFu;
+        uint64_t hi = pos + kChunk + kHalo;
+        if (hi > n16) hi = n16;
+        const uint32_t loaded_end = (uint32_t)(hi + kHalo - pos);  // offset in the slot
+        for (uint32_t o = loaded_end + lane * 4; o < (uint32_t)kSlotBytes; o += 128)
+            *reinterpret_cast<uint32_t *>(buf + o) = 0xFFFFFFFFu;
+        if (hi > a.n) {  // the last 16-byte granule holds bytes past n: blank them
+            const uint32_t first_bad = (uint32_t)(a.n + kHalo - pos);
+            if (lane < 16 && first_bad + lane < loaded_end) buf[first_bad + lane] = 0xFF;
+        }
+        __syncwarp();
+    }
     // ---------------------------------------------------------------- exact masks + start-code bitmap
     uint32_t em[kRows];  // raw EPB mask | start-code mask << 16
 #pragma unroll
@@ -216,14 +233,14 @@ __device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, WarpRing &r
         const uint32_t prev = *reinterpret_cast<const uint32_t *>(tile_in + gi * 16 - 4);
         const GranuleMasks m = granule_masks(w, prev);
         em[r] = m.e | (m.sc << 16);
-        ring.scbits[gi + 1] = (uint16_t)m.sc;
+        scbits[gi + 1] = (uint16_t)m.sc;
     }
     if (lane < 2) {  // halo granules: only start codes ending in [pos-6, pos-1] and at pos+kChunk matter
         const int gi = lane ? kChunkGran : -1;
         const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
         const uint32_t prev = lane ? *reinterpret_cast<const uint32_t *>(tile_in + gi * 16 - 4) : 0xFFFFFFFFu;
-        ring.scbits[gi + 1] = (uint16_t)granule_masks(w, prev).sc;
+        scbits[gi + 1] = (uint16_t)granule_masks(w, prev).sc;
     }
     __syncwarp();
 
@@ -242,9 +259,9 @@ __device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, WarpRing &r
         uint32_t e16 = em[r] & 0xFFFFu;
         uint32_t k16 = ~e16 & 0xFFFFu;
         // start-code ends q in [g-6, g+16] change what this granule keeps
-        const uint32_t near = ((uint32_t)ring.scbits[gi] >> 10) | ring.scbits[gi + 1] | (ring.scbits[gi + 2] & 1u);
+        const uint32_t near = ((uint32_t)scbits[gi] >> 10) | scbits[gi + 1] | (scbits[gi + 2] & 1u);
         if (near)  // header bytes, the 2-byte tail rule and the EPB guard, all in the bit domain
-            k16 = keep_near_sc(tile_in, pos, gpos, e16, ring.scbits[gi], ring.scbits[gi + 1], ring.scbits[gi + 2], &e16);
+            k16 = keep_near_sc(tile_in, pos, gpos, e16, scbits[gi], scbits[gi + 1], scbits[gi + 2], &e16);
         uint32_t sc = em[r] >> 16;
         if (has_end) {
             if (gpos >= a.n) {
@@ -279,6 +296,7 @@ __device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, WarpRing &r
     res.clean = 0;
     if (cls == 0 && carry_epb == 0) {  // false alarm (00 00 xx with xx > 3): a verbatim copy after all
         res.clean = 1;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // (the fills above)
         return res;
     }
     const uint32_t total = rp[kRows];
@@ -329,7 +347,59 @@ __device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, WarpRing &r
     }
     res.carry_epb = seg_apply(total, carry_epb);
     res.piece_nsc = piece_nsc + n_sc;
+    // generic-proxy writes to the slot (fills, compaction) are ordered before the TMA writes that will reuse it
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     return res;
+}
+
+// Producer side of a warp's ring (lane 0 only): pieces by ticket, their chunks in order.
+struct Producer {
+    uint64_t pos;    // stream offset of the next chunk to load
+    uint32_t left;   // chunks of the current piece still to load
+    uint32_t piece;
+    uint32_t done;   // the tickets have run out
+    uint32_t next_static;  // (H264B_SCAN_STATIC: pieces dealt round-robin instead of by ticket)
+};
+
+__device__ __forceinline__ void tma_load(uint32_t dst, const uint8_t *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// everything but an interior chunk of the current piece: next piece, first / last chunks of the stream, the end
+__device__ __noinline__ void produce_slow(const ScanArgs &a, WarpRing &ring, int s, Producer *p) {
+    if (!p->done && p->left == 0) {
+#ifdef H264B_SCAN_STATIC
+        p->piece = p->next_static;
+        p->next_static += gridDim.x * kWarps;
+#else
+        p->piece = atomicAdd(&a.hdr->ticket, 1u);
+#endif
+        if (p->piece < a.n_pieces) {
+            const uint32_t first = p->piece * a.span_chunks;
+            p->left = first + a.span_chunks < a.n_chunks ? a.span_chunks : a.n_chunks - first;
+            p->pos = (uint64_t)first * kChunk;
+        } else {
+            p->done = 1;
+        }
+    }
+    const uint32_t bar = smem_u32(&ring.mbar[s]);
+    if (p->done) {  // an arrival without bytes: the consumer sees "no more work"
+        ring.meta[s] = make_ulonglong2(~0ull, 0ull);
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+        return;
+    }
+    const uint64_t pos = p->pos, n16 = (a.n + 15) & ~15ull;
+    ring.meta[s] = make_ulonglong2(pos, (unsigned long long)p->piece);
+    const uint64_t lo = pos ? pos - kHalo : 0;
+    uint64_t hi = pos + kChunk + kHalo;
+    if (hi > n16) hi = n16;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tma_load(smem_u32(ring.slot[s] + (lo + kHalo - pos)), a.in + lo, (uint32_t)(hi - lo), bar);
+    p->pos = pos + kChunk;
+    p->left--;
 }
 
 __global__ void __launch_bounds__(kWarps * 32) annexb_scan_kernel(ScanArgs a) {
@@ -345,124 +415,114 @@ __global__ void __launch_bounds__(kWarps * 32) annexb_scan_kernel(ScanArgs a) {
     __syncwarp();
     const uint64_t n16 = (a.n + 15) & ~15ull;
 
-    // ---------------------------------------------------------------- producer (lane 0): pieces by ticket, chunks in order
-    uint32_t p_piece = 0, p_next = 0, p_end = 0;  // chunks [p_next, p_end) of piece p_piece are still to be loaded
-    bool p_done = false;
-    auto produce = [&](int s) {
-        if (!p_done && p_next == p_end) {
-            p_piece = atomicAdd(&a.hdr->ticket, 1u);
-            if (p_piece < a.n_pieces) {
-                p_next = p_piece * a.span_chunks;
-                p_end = p_next + a.span_chunks < a.n_chunks ? p_next + a.span_chunks : a.n_chunks;
-            } else {
-                p_done = true;
-            }
-        }
-        const uint32_t bar = smem_u32(&ring.mbar[s]);
-        if (p_done) {  // an arrival without bytes: the consumer sees "no more work"
-            ring.slot_pos[s] = ~0ull;
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-            return;
-        }
-        const uint64_t pos = (uint64_t)p_next * kChunk;
-        p_next++;
-        ring.slot_pos[s] = pos;
-        ring.slot_piece[s] = p_piece;
-        const uint64_t lo = pos ? pos - kHalo : 0;
-        uint64_t hi = pos + kChunk + kHalo;
-        if (hi > n16) hi = n16;
-        const uint32_t bytes = (uint32_t)(hi - lo);
-        const uint32_t dst = smem_u32(ring.slot[s] + (lo + kHalo - pos));
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-            "l"(a.in + lo), "r"(bytes), "r"(bar)
-            : "memory");
-    };
+    Producer prod = {0, 0, 0, 0, blockIdx.x * kWarps + (uint32_t)warp};
     if (lane == 0) {
+        Producer t = prod;
 #pragma unroll 1
-        for (int s = 0; s < kStages - 1; s++) produce(s);
+#ifdef H264B_SCAN_STG
+        for (int s = 0; s < kStages; s++) produce_slow(a, ring, s, &t);
+#else
+        for (int s = 0; s < kStages - 1; s++) produce_slow(a, ring, s, &t);
+#endif
+        prod = t;
     }
 
-    // ---------------------------------------------------------------- consumer (whole warp)
     uint32_t cur_piece = 0xFFFFFFFFu;
     uint32_t carry_epb = 0, piece_nsc = 0;
+    int s = 0;            // slot of the chunk being consumed
+    uint32_t parity = 0;  // phase parity of its barrier
 #pragma unroll 1
-    for (uint32_t it = 0;; it++) {
-        const int s = (int)(it % kStages);
-        mbar_wait(smem_u32(&ring.mbar[s]), (it / kStages) & 1u);
-        const uint64_t pos = ring.slot_pos[s];
+    for (;;) {
+        mbar_wait(smem_u32(&ring.mbar[s]), parity);
+        const ulonglong2 meta = ring.meta[s];
+        const uint64_t pos = meta.x;
         if (pos == ~0ull) break;
-        const uint32_t piece = ring.slot_piece[s];
-        if (piece != cur_piece) {
+        if ((uint32_t)meta.y != cur_piece) {
             if (cur_piece != 0xFFFFFFFFu && lane == 0) {
                 a.piece_epb[cur_piece] = carry_epb;
                 a.piece_nsc[cur_piece] = piece_nsc;
             }
-            cur_piece = piece;
+            cur_piece = (uint32_t)meta.y;
             carry_epb = 0;
             piece_nsc = 0;
         }
         uint8_t *buf = ring.slot[s];
         uint8_t *tile_in = buf + kHalo;  // tile_in[i] = s[pos + i], valid for i in [-16, kChunk+16)
 
-        // bytes outside the stream read as 0xFF (they match no predicate)
-        const bool edge = pos == 0 || pos + kChunk + kHalo > a.n;  // warp-uniform
-        if (edge) {
-            if (pos == 0 && lane < 4) reinterpret_cast<uint32_t *>(buf)[lane] = 0xFFFFFFFFu;
-            uint64_t hi = pos + kChunk + kHalo;
-            if (hi > n16) hi = n16;
-            const uint32_t loaded_end = (uint32_t)(hi + kHalo - pos);  // offset in the slot
-            for (uint32_t o = loaded_end + lane * 4; o < (uint32_t)kSlotBytes; o += 128)
-                *reinterpret_cast<uint32_t *>(buf + o) = 0xFFFFFFFFu;
-            if (hi > a.n) {  // the last 16-byte granule holds bytes past n: blank them
-                const uint32_t first_bad = (uint32_t)(a.n + kHalo - pos);
-                if (lane < 16 && first_bad + lane < loaded_end) buf[first_bad + lane] = 0xFF;
-            }
-            __syncwarp();
-        }
-#ifdef H264B_EXP_LOADONLY
-        bool clean = false;
-        if (pos == 0x123456789ull) clean = true;
-#else
         // ---------------------------------------------------------------- detect: two adjacent zero bytes anywhere?
-        uint32_t pairs = 0;
-#ifndef H264B_EXP_NODETECT
+        uint32_t acc = 0xFFFFFFFFu;
+#ifdef H264B_SCAN_STG
+        uint4 vv[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; r++) vv[r] = *reinterpret_cast<const uint4 *>(tile_in + (r * 32 + lane) * 16);
+#endif
+#if !defined(H264B_EXP_NODETECT) && !defined(H264B_EXP_LOADONLY)
 #pragma unroll
         for (int r = 0; r < kRows; r++) {
             const int gi = r * 32 + lane;
+#ifdef H264B_SCAN_STG
+            const uint4 v = vv[r];
+#else
             const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            const uint32_t prev = *reinterpret_cast<const uint32_t *>(tile_in + gi * 16 - 4);
-            pairs |= zero_pair_bits(w, prev);
-        }
-        if (lane == 0)  // a start code ending in the last bytes before the chunk still reaches into it
-            pairs |= zero_pair_bits_tail8(*reinterpret_cast<const uint32_t *>(buf + 8),
-                                          *reinterpret_cast<const uint32_t *>(buf + 12));
 #endif
-        bool clean = !__any_sync(0xFFFFFFFFu, pairs != 0) && carry_epb == 0 && pos + kChunk <= a.n;
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            acc = zero_pair_acc(acc, w, *reinterpret_cast<const uint32_t *>(tile_in + gi * 16 - 4));
+        }
+        {   // a start code ending in the last bytes before the chunk still reaches into it (same words for all lanes)
+            const uint2 t8 = *reinterpret_cast<const uint2 *>(buf + 8);
+            acc = zero_pair_acc_tail8(acc, t8.x, t8.y);
+        }
+#endif
+        // chunks that touch the ends of the stream always take the general path (it blanks the bytes outside)
+        const bool edge = pos == 0 || pos + kChunk + kHalo > a.n;
+        bool clean = !(__any_sync(0xFFFFFFFFu, acc_has_pair(acc)) || carry_epb != 0 || edge);
+#ifdef H264B_EXP_LOADONLY
+        clean = false;
+#else
         if (!clean) {
-            const ChunkResult res = general_chunk(a, ring, tile_in, pos, carry_epb, piece_nsc, lane);
+            const ChunkResult res = general_chunk(a, ring.scbits, buf, pos, carry_epb, piece_nsc, lane);
             carry_epb = res.carry_epb;
             piece_nsc = res.piece_nsc;
             clean = res.clean != 0;
-            // generic-proxy writes to the slot (fills, compaction) are ordered before the TMA writes that reuse it
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        } else if (edge) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
 #endif
         __syncwarp();  // every lane is done reading (and writing) the slot
-        if (lane == 0) {
+#ifdef H264B_SCAN_STG
+        const int s_prev = s;  // the registers hold the chunk: its slot is free at once
 #ifndef H264B_EXP_NOSTORE
-            // the bulk of a real stream leaves through the TMA: one 2 KiB bulk store straight from the slot
+        if (clean) {
+#pragma unroll
+            for (int r = 0; r < kRows; r++)
+                *reinterpret_cast<uint4 *>(a.out + pos + (uint32_t)(r * 32 + lane) * 16u) = vv[r];
+        }
+#endif
+#else
+        const int s_prev = s ? s - 1 : kStages - 1;
+#endif
+        if (lane == 0) {
+#ifndef H264B_SCAN_STG
+#ifndef H264B_EXP_NOSTORE
+            // the bulk of a real stream leaves through the TMA: one bulk store straight from the slot
             if (clean) bulk_store(a.out + pos, tile_in, kChunk);
 #endif
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             // all but the newest store have finished reading shared memory: the slot of the previous chunk is free
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            produce((int)((it + kStages - 1) % kStages));
+#endif
+            if (prod.left != 0 && prod.pos + kChunk + kHalo <= n16) {  // interior chunk of the current piece
+                ring.meta[s_prev] = make_ulonglong2(prod.pos, (unsigned long long)prod.piece);
+                tma_load(smem_u32(ring.slot[s_prev]), a.in + prod.pos - kHalo, kSlotBytes, smem_u32(&ring.mbar[s_prev]));
+                prod.pos += kChunk;
+                prod.left--;
+            } else {
+                Producer t = prod;
+                produce_slow(a, ring, s_prev, &t);
+                prod = t;
+            }
+        }
+        if (++s == kStages) {
+            s = 0;
+            parity ^= 1u;
         }
     }
     if (lane == 0) {
@@ -471,6 +531,107 @@ __global__ void __launch_bounds__(kWarps * 32) annexb_scan_kernel(ScanArgs a) {
             a.piece_nsc[cur_piece] = piece_nsc;
         }
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ main pass, LDG form
+// The same pass with the chunk held in registers: coalesced LDG.128 (one granule per lane and row, the next chunk of
+// the piece already in flight while this one is examined), the previous word by shuffle, STG.128 for clean chunks.
+// Only chunks that take the general path are staged in shared memory.
+struct __align__(16) WarpStage {
+    uint8_t buf[kSlotBytes];
+    uint16_t scbits[kChunkGran + 2];
+    uint16_t pad[(8 - (kChunkGran + 2) % 8) % 8];
+};
+
+struct ChunkRegs {
+    uint4 v[kRows];
+    uint2 t8;  // the 8 bytes before the chunk
+};
+
+__device__ __forceinline__ void load_chunk(ChunkRegs &c, const uint8_t *in, uint64_t pos, uint64_t n16, int lane) {
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+        const uint64_t g = pos + (uint32_t)(r * 32 + lane) * 16u;
+        c.v[r] = g < n16 ? __ldcs(reinterpret_cast<const uint4 *>(in + g)) : make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
+    c.t8 = pos ? *reinterpret_cast<const uint2 *>(in + pos - 8) : make_uint2(~0u, ~0u);
+}
+
+__global__ void __launch_bounds__(kWarps * 32) annexb_scan_ldg_kernel(ScanArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpStage &st = reinterpret_cast<WarpStage *>(smem_raw)[warp];
+    const uint64_t n16 = (a.n + 15) & ~15ull;
+#ifdef H264B_SCAN_STATIC
+    uint32_t next_static = blockIdx.x * kWarps + (uint32_t)warp;
+#endif
+#pragma unroll 1
+    for (;;) {
+#ifdef H264B_SCAN_STATIC
+        const uint32_t piece = next_static;
+        next_static += gridDim.x * kWarps;
+#else
+        uint32_t piece = 0;
+        if (lane == 0) piece = atomicAdd(&a.hdr->ticket, 1u);
+        piece = __shfl_sync(0xFFFFFFFFu, piece, 0);
+#endif
+        if (piece >= a.n_pieces) break;
+        const uint32_t c0 = piece * a.span_chunks;
+        const uint32_t c1 = c0 + a.span_chunks < a.n_chunks ? c0 + a.span_chunks : a.n_chunks;
+        uint32_t carry_epb = 0, piece_nsc = 0;
+        ChunkRegs cur;
+        load_chunk(cur, a.in, (uint64_t)c0 * kChunk, n16, lane);
+#pragma unroll 1
+        for (uint32_t c = c0; c < c1; c++) {
+            const uint64_t pos = (uint64_t)c * kChunk;
+            ChunkRegs nxt;
+            if (c + 1 < c1) load_chunk(nxt, a.in, pos + kChunk, n16, lane);
+            // ---------------------------------------------------------------- detect
+            uint32_t acc = 0xFFFFFFFFu;
+#ifndef H264B_EXP_NODETECT
+#pragma unroll
+            for (int r = 0; r < kRows; r++) {
+                uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, cur.v[r].w, 1);
+                const uint32_t wrap = r ? __shfl_sync(0xFFFFFFFFu, cur.v[r ? r - 1 : 0].w, 31) : cur.t8.y;
+                if (lane == 0) prev = wrap;
+                const uint32_t w[4] = {cur.v[r].x, cur.v[r].y, cur.v[r].z, cur.v[r].w};
+                acc = zero_pair_acc(acc, w, prev);
+            }
+            acc = zero_pair_acc_tail8(acc, cur.t8.x, cur.t8.y);
+#endif
+            const bool edge = pos == 0 || pos + kChunk + kHalo > a.n;
+            bool clean = !(__any_sync(0xFFFFFFFFu, acc_has_pair(acc)) || carry_epb != 0 || edge);
+            if (!clean) {
+                // stage the chunk and its halos exactly as a bulk load of [lo, hi) would have left them
+                uint8_t *tile_in = st.buf + kHalo;
+#pragma unroll
+                for (int r = 0; r < kRows; r++)
+                    if (pos + (uint32_t)(r * 32 + lane) * 16u < n16)
+                        *reinterpret_cast<uint4 *>(tile_in + (r * 32 + lane) * 16) = cur.v[r];
+                if (lane == 0 && pos) *reinterpret_cast<uint4 *>(st.buf) = *reinterpret_cast<const uint4 *>(a.in + pos - kHalo);
+                if (lane == 1 && pos + kChunk < n16)
+                    *reinterpret_cast<uint4 *>(tile_in + kChunk) = *reinterpret_cast<const uint4 *>(a.in + pos + kChunk);
+                __syncwarp();
+                const ChunkResult res = general_chunk(a, st.scbits, st.buf, pos, carry_epb, piece_nsc, lane);
+                carry_epb = res.carry_epb;
+                piece_nsc = res.piece_nsc;
+                clean = res.clean != 0;
+                __syncwarp();
+            }
+#ifndef H264B_EXP_NOSTORE
+            if (clean) {
+#pragma unroll
+                for (int r = 0; r < kRows; r++)
+                    __stcs(reinterpret_cast<uint4 *>(a.out + pos + (uint32_t)(r * 32 + lane) * 16u), cur.v[r]);
+            }
+#endif
+            cur = nxt;
+        }
+        if (lane == 0) {
+            a.piece_epb[piece] = carry_epb;
+            a.piece_nsc[piece] = piece_nsc;
+        }
     }
 }
 
@@ -792,13 +953,19 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
 
     // launch shape: as many warps as fit, each with its own ring of slots
     static bool attr_set = false;
+#ifdef H264B_SCAN_LDG
+    const auto main_kernel = annexb_scan_ldg_kernel;
+    const size_t smem = sizeof(WarpStage) * kWarps;
+#else
+    const auto main_kernel = annexb_scan_kernel;
     const size_t smem = sizeof(WarpRing) * kWarps;
+#endif
     if (!attr_set) {
-        H264B_CUDA(ctx, cudaFuncSetAttribute(annexb_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        H264B_CUDA(ctx, cudaFuncSetAttribute(main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     int occ = 0;
-    H264B_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, annexb_scan_kernel, kWarps * 32, smem));
+    H264B_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, main_kernel, kWarps * 32, smem));
     if (occ < 1) occ = 1;
     const uint64_t max_ctas = (uint64_t)ctx->sm_count * occ;
 
@@ -807,7 +974,7 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     uint64_t span = ctx->scan_span_chunks;
     if (!span) {
         span = n_chunks / (max_ctas * kWarps * 4);
-        if (span > kMaxSpanChunks) span = kMaxSpanChunks;
+        if (span > kMaxSpanBytes / kChunk) span = kMaxSpanBytes / kChunk;
         if (span < 1) span = 1;
     }
     const uint64_t n_pieces = (n_chunks + span - 1) / span;
@@ -850,7 +1017,7 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     if (n_pieces) {
         uint64_t grid = (n_pieces + kWarps - 1) / kWarps;
         if (grid > max_ctas) grid = max_ctas;
-        annexb_scan_kernel<<<(int)grid, kWarps * 32, smem, ctx->stream>>>(a);
+        main_kernel<<<(int)grid, kWarps * 32, smem, ctx->stream>>>(a);
         H264B_LAUNCH_CHECK(ctx, "annexb_scan_kernel");
         piece_order_kernel<<<1, 1024, 0, ctx->stream>>>(a.piece_nsc, a.piece_ord, a.n_pieces);
         H264B_LAUNCH_CHECK(ctx, "piece_order_kernel");

@@ -118,7 +118,7 @@ int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out_base, int64_
             lcg = lcg * 1664525u + 1013904223u;
             std::swap(order[i], order[(lcg >> 8) % (uint32_t)(i + 1)]);
         }
-    int64_t n_fast = 0, n_false_alarm = 0, n_general = 0;
+    int64_t n_fast = 0, n_false_alarm = 0, n_general = 0, n_filter_mismatch = 0;
     std::vector<uint8_t> buf(kHalo + kChunk + kHalo);
     std::vector<uint16_t> scb(kGran + 2);
     for (int64_t oi = 0; oi < n_pieces; oi++) {
@@ -130,20 +130,26 @@ int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out_base, int64_
             for (int i = 0; i < kHalo + kChunk + kHalo; i++) buf[i] = (uint8_t)gets(pos - kHalo + i);
             uint8_t *tile_in = buf.data() + kHalo;
             // ---- detect (fast path)
-            uint32_t pairs = 0;
+            uint32_t acc = 0xFFFFFFFFu;
             for (int gi = 0; gi < kGran; gi++) {
                 uint32_t w[4], prev;
                 memcpy(w, tile_in + gi * 16, 16);
                 memcpy(&prev, tile_in + gi * 16 - 4, 4);
-                pairs |= zero_pair_bits(w, prev);
+                acc = zero_pair_acc(acc, w, prev);
             }
             {
                 uint32_t lo, hi;
                 memcpy(&lo, buf.data() + 8, 4);
                 memcpy(&hi, buf.data() + 12, 4);
-                pairs |= zero_pair_bits_tail8(lo, hi);
+                acc = zero_pair_acc_tail8(acc, lo, hi);
             }
-            bool clean = pairs == 0 && carry_epb == 0 && pos + kChunk <= n;
+            {   // the filter against its definition: some p in [pos-7, pos+kChunk) with s[p] == 0 && s[p-1] == 0
+                bool brute = false;
+                for (int i = -7; i < kChunk; i++) brute = brute || (tile_in[i] == 0 && tile_in[i - 1] == 0);
+                if (brute != acc_has_pair(acc)) n_filter_mismatch++;
+            }
+            const bool edge = pos == 0 || pos + kChunk + kHalo > n;
+            bool clean = !acc_has_pair(acc) && carry_epb == 0 && !edge;
             if (clean) {
                 n_fast++;
             } else {
@@ -297,6 +303,7 @@ int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out_base, int64_
         stats[0] = n_fast;
         stats[1] = n_false_alarm;
         stats[2] = n_general;
+        stats[3] = n_filter_mismatch;
     }
     return Kall;
 }

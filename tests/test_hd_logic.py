@@ -70,8 +70,10 @@ def check_stream(L, s):
         out = np.full(len(s8) + 96 + shift, 0xEE, np.uint8)
         cap = len(s8) // 4 + 2
         t_st, t_epb, t_hd = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64), np.zeros(cap, np.uint32)
+        stats = np.zeros(4, np.int64)
         Kt = L.emul_stream_tiles(s8.ctypes.data, len(s8), out.ctypes.data, shift, t_st.ctypes.data, t_epb.ctypes.data,
-                                 t_hd.ctypes.data, cap, span, seed, None)
+                                 t_hd.ctypes.data, cap, span, seed, stats.ctypes.data)
+        assert stats[3] == 0, "zero-pair filter disagrees with its definition"
         assert max(Kt, 1) - 1 == n_or
         written = np.zeros(len(out), bool)
         for k in range(n_or):
@@ -147,6 +149,25 @@ def test_local_split_strip_kats(emul):
     check_stream(emul, np.concatenate([sc, hdr, b2, sc]))
     b3 = body.copy(); b3[40000:40003] = [0, 0, 3]; b3[16380:16383] = [0, 0, 3]
     check_stream(emul, np.concatenate([np.full(7, 9, np.uint8), sc, hdr, b3, sc, hdr, b2[:20000], sc]))
+
+
+def test_fast_path_is_taken_on_sparse_streams(emul):
+    """entropy-coded-looking payload: most chunks must take the verbatim-copy path, and the result still matches"""
+    rng = np.random.default_rng(5)
+    s = rng.integers(0, 256, 600000).astype(np.uint8)
+    s[:5] = [0, 0, 0, 1, 0x65]
+    s[300000:300005] = [0, 0, 0, 1, 0x41]
+    s[-4:] = [0, 0, 0, 1]
+    check_stream(emul, s)
+    out = np.zeros(len(s) + 96, np.uint8)
+    cap = len(s) // 4 + 2
+    a, b, c = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64), np.zeros(cap, np.uint32)
+    stats = np.zeros(4, np.int64)
+    emul.emul_stream_tiles(s.ctypes.data, len(s), out.ctypes.data, 0, a.ctypes.data, b.ctypes.data, c.ctypes.data, cap,
+                           64, 3, stats.ctypes.data)
+    n_chunks = (len(s) + 2047) // 2048
+    assert stats[0] + stats[1] + stats[2] == n_chunks
+    assert stats[0] > 0.9 * n_chunks and stats[2] < 0.05 * n_chunks, stats
 
 
 def test_local_split_strip_harness_streams(emul):

@@ -15,6 +15,14 @@ VARIANTS = {
     "nostore": ["-DH264B_EXP_NOSTORE"],
     "nodetect": ["-DH264B_EXP_NODETECT"],
     "nodetect_nostore": ["-DH264B_EXP_NODETECT", "-DH264B_EXP_NOSTORE"],
+    # launch-shape sweeps (results stay correct): rows per chunk, ring stages, warps per CTA, store / load form
+    "stat": ["-DH264B_SCAN_STATIC"],
+    "stat_w8": ["-DH264B_SCAN_STATIC", "-DH264B_SCAN_WARPS=8"],
+    "ldg": ["-DH264B_SCAN_LDG"],
+    "ldg_stat": ["-DH264B_SCAN_LDG", "-DH264B_SCAN_STATIC"],
+    "ldg_stat_w8": ["-DH264B_SCAN_LDG", "-DH264B_SCAN_STATIC", "-DH264B_SCAN_WARPS=8"],
+    "ldg_stat_r2": ["-DH264B_SCAN_LDG", "-DH264B_SCAN_STATIC", "-DH264B_SCAN_ROWS=2"],
+    "ldg_stat_nostore": ["-DH264B_SCAN_LDG", "-DH264B_SCAN_STATIC", "-DH264B_EXP_NOSTORE"],
 }
 OUTDIR = os.path.join(ROOT, "h264decode_b200", "exp")
 
@@ -41,7 +49,24 @@ def run(frames=4000):
     d_sum = torch.zeros(64, dtype=torch.uint8, device=dev)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    for name in VARIANTS:
+    # reference point: a plain device copy of the same bytes (what MEASURED_PEAKS.json's hbm_gbs is)
+    ts = []
+    for it in range(12):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        d_rbsp[:n].copy_(d_stream[:n])
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    t = float(np.median(ts[3:]))
+    print("%-20s %8.3f ms (min %.3f)  in %7.1f GB/s   alg(2N) %7.1f GB/s" % ("torch copy_", t, min(ts), n / t / 1e6,
+                                                                             2 * n / t / 1e6), flush=True)
+    names = [v for v in VARIANTS if not os.environ.get("SCAN_EXP") or v in os.environ["SCAN_EXP"].split(",")]
+    ref = None
+    spans = [int(x) for x in os.environ.get("SCAN_SPAN", "0").split(",")]
+    for name in names:
+        if not os.path.exists(os.path.join(OUTDIR, "lib_%s.so" % name)):
+            continue
         L = C.CDLL(os.path.join(OUTDIR, "lib_%s.so" % name))
         L.h264b_create.argtypes = [C.c_int32, C.POINTER(C.c_void_p)]
         L.h264b_set_stream.argtypes = [C.c_void_p, C.c_void_p]
@@ -51,18 +76,30 @@ def run(frames=4000):
         h = C.c_void_p()
         assert L.h264b_create(0, C.byref(h)) == 0
         L.h264b_set_stream(h, C.c_void_p(stream.cuda_stream))
-        ts = []
-        for it in range(6):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            rc = L.h264b_annexb_scan_dev(h, d_stream.data_ptr(), n, d_rbsp.data_ptr(), d_nals.data_ptr(), None, nal_cap,
-                                         d_sum.data_ptr(), 0)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            assert rc == 0
-            ts.append(e0.elapsed_time(e1))
-        t = float(np.median(ts[2:]))
-        print("%-20s %8.3f ms   in %7.1f GB/s   alg(2N) %7.1f GB/s" % (name, t, n / t / 1e6, 2 * n / t / 1e6), flush=True)
+        L.h264b_set_option.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
+        for span in spans:
+          L.h264b_set_option(h, 1, span)
+          d_rbsp.zero_()
+          ts = []
+          for it in range(12):
+              e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+              e0.record(stream)
+              rc = L.h264b_annexb_scan_dev(h, d_stream.data_ptr(), n, d_rbsp.data_ptr(), d_nals.data_ptr(), None, nal_cap,
+                                           d_sum.data_ptr(), 0)
+              e1.record(stream)
+              torch.cuda.synchronize()
+              assert rc == 0
+              ts.append(e0.elapsed_time(e1))
+          t = float(np.median(ts[3:]))
+          same = ""
+          if not any("EXP" in f for f in VARIANTS[name]):  # a complete variant: its results must equal the first one's
+              if ref is None:
+                  ref = (d_rbsp[:n].clone(), d_nals.clone())
+              else:
+                  same = "  results == %s: %s" % (names[0], bool(torch.equal(ref[0], d_rbsp[:n]) and torch.equal(ref[1], d_nals)))
+          print("%-20s %8.3f ms (min %.3f)  in %7.1f GB/s   alg(2N) %7.1f GB/s%s" % (name + ("/span%d" % span if span else ""), t, min(ts), n / t / 1e6,
+                                                                                     2 * n / t / 1e6, same), flush=True)
+          d_rbsp.zero_()
         L.h264b_destroy(h)
 
 
