@@ -15,13 +15,12 @@ OK, E_INVALID, E_CUDA, E_NOMEM, E_CAPACITY, E_NO_DEVICE = range(6)
 TABLES_SPEC, BYPASS_SPEC_OR, CABAC_FINAL_TERMINATE = 1, 2, 4
 F_OVERRUN, F_HAS_EPB, F_SHORT_NAL = 1, 2, 4
 OP_DECISION, OP_BYPASS, OP_TERMINATE = 0, 1, 2
-OPT_SCAN_SPAN_CHUNKS = 1
 
 # every symbol include/h264b200.h declares (tests check that the library exports exactly these)
 SYMBOLS = [
     "h264b_version", "h264b_device_count", "h264b_create", "h264b_destroy", "h264b_last_error", "h264b_set_stream",
     "h264b_sync", "h264b_host_alloc", "h264b_host_free", "h264b_dev_alloc", "h264b_dev_free", "h264b_memcpy_h2d",
-    "h264b_memcpy_d2h", "h264b_set_option", "h264b_launch_count", "h264b_annexb_scratch_bytes", "h264b_annexb_scan_dev",
+    "h264b_memcpy_d2h", "h264b_launch_count", "h264b_annexb_scratch_bytes", "h264b_annexb_scan_dev",
     "h264b_annexb_scan", "h264b_nal_units", "h264b_ctx_init_dev", "h264b_ctx_init", "h264b_pre_ctx_state", "h264b_mn",
     "h264b_cabac_decode_dev", "h264b_cabac_decode", "h264b_engine_step", "h264b_binary_decision",
     "h264b_state_transition", "h264b_stream_decode", "h264b_slice_select_dev",
@@ -96,7 +95,6 @@ def load():
         "h264b_dev_free": (i32, [vp, vp]),
         "h264b_memcpy_h2d": (i32, [vp, vp, vp, C.c_size_t]),
         "h264b_memcpy_d2h": (i32, [vp, vp, vp, C.c_size_t]),
-        "h264b_set_option": (i32, [vp, u32, u64]),
         "h264b_launch_count": (i32, [vp, P(u64)]),
         "h264b_annexb_scratch_bytes": (u64, [u64]),
         "h264b_annexb_scan_dev": (i32, [vp, vp, u64, vp, vp, vp, u32, vp, u32]),
@@ -174,9 +172,6 @@ class Context:
 
     def sync(self):
         self._check(_lib.h264b_sync(self.h))
-
-    def set_option(self, option, value):
-        self._check(_lib.h264b_set_option(self.h, option, value))
 
     def launch_count(self):
         n = C.c_uint64()

@@ -160,6 +160,21 @@ H264B_HD uint32_t zero_pair_acc_tail8(uint32_t acc, uint32_t lo, uint32_t hi) {
 }
 H264B_HD bool acc_has_pair(uint32_t acc) { return (acc & 0xFFFFu) == 0u || (acc >> 16) == 0u; }
 
+// Two-level filter of the copy kernel, per granule: non-zero iff the granule holds an emulation-prevention candidate
+// or a start-code end.  Either needs two zero bytes right before it, i.e. a pair ending at g-1 .. g+14: the cheap test
+// looks for pairs ending at g-1 (the last two bytes of prev) .. g+15, and only then are the exact masks evaluated.
+H264B_HD uint32_t granule_needs_general(const uint32_t w[4], uint32_t prev) {
+    if (!acc_has_pair(zero_pair_acc(0xFFFFFFFFu, w, prev)) && (prev >> 16) != 0u) return 0u;
+    const GranuleMasks m = granule_masks(w, prev);
+    return m.e | m.sc;
+}
+// ... and per chunk, for what lies outside it: a start code ending in the last bytes before the chunk reaches into it
+// (header bytes, EPB guard) and one ending right behind the chunk takes the chunk's last byte (the 2-byte tail rule);
+// both need zero pairs at the edges.  t8_lo/t8_hi: the 8 bytes before the chunk; last_word: its last 4 bytes.
+H264B_HD bool chunk_edges_need_general(uint32_t t8_lo, uint32_t t8_hi, uint32_t last_word) {
+    return acc_has_pair(zero_pair_acc_tail8(0xFFFFFFFFu, t8_lo, t8_hi)) || (last_word >> 16) == 0u;
+}
+
 // keep mask of a granule at stream position gpos when start codes end within [gpos-6, gpos+16], in the bit domain
 // (same result as 16 x keep_byte_stream, checked exhaustively on the CPU by tests/test_hd_logic.py):
 //   e16      raw emulation-prevention mask of the granule (granule_masks().e)
@@ -337,35 +352,52 @@ H264B_HD void store_granule_bytes(uint8_t *out, uint64_t gpos, const uint32_t w[
     }
 }
 
-// ---- NALs whose body spans several pieces ---------------------------------------------------------------------
-// The main pass cuts the stream into fixed-size pieces (spans of chunks, each walked front to back by one warp) and
-// treats every piece on its own: inside a piece a kept byte at stream position p goes to
-// out[p - (EPBs removed from p's NAL earlier IN THIS PIECE)].  A NAL that continues into further pieces is therefore
-// laid out in parts, one per piece, each compacted towards its own start; whenever an earlier part lost EPBs the
-// later parts sit too far right by the accumulated count G.  Real streams almost never have that (one EPB per
-// several MB of entropy-coded data), so the hot kernel needs no communication between warps at all and a tiny
-// post-pass slides the few affected parts left (nal_fixup_kernel).  This helper walks the parts of the NAL [a, b):
-//   a, b        first byte of this NAL / of the next one (b-1 is the 01 of the start code that ends it)
-//   H           header bytes
-//   end_local   EPB count the main pass recorded at that start code: EPBs since the NAL's start if it began in the
-//               same piece, else since the start of the piece
-//   piece_epb   per piece: EPBs after the piece's last NAL start, or in the whole piece when it holds none
-// move(start, len, G) is called for every later part that has to slide left by G > 0.  Returns the NAL's EPB total.
-template <class Move>
-H264B_HD uint64_t nal_pieces(uint64_t a, uint64_t b, uint32_t H, uint64_t end_local, const uint32_t *piece_epb,
-                             uint64_t piece_bytes, const Move &move) {
+// ---- NALs whose body spans several chunks ---------------------------------------------------------------------
+// The main pass treats every chunk ("piece": kChunk bytes of the stream) on its own: inside a chunk a kept byte at
+// stream position p goes to out[p - (EPBs removed from p's NAL earlier IN THIS CHUNK)].  A NAL that continues into
+// further chunks is therefore laid out in parts, one per chunk, each compacted towards its own start; whenever an
+// earlier part lost EPBs the later parts sit too far right by the accumulated count G.  Real streams almost never
+// have that (one EPB per several MB of entropy-coded data), so the hot kernels need no communication between chunks
+// at all and a tiny post-pass slides the few affected parts left (nal_fixup_kernel).
+//   tail[t]   per chunk, low 16 bits: EPBs after the chunk's last NAL start, or in the whole chunk when it holds none
+//   S[t]      exclusive prefix sum of tail[] (mod 2^32): for chunks Tq < t <= Tb of one NAL, G(t) = S[t] - S[Tq]
+//   a, b      first byte of this NAL / of the next one (b-1 is the 01 of the start code that ends it)
+//   end_local EPB count the main pass recorded at that start code: EPBs since the NAL's start if it began in the
+//             same chunk, else since the start of the chunk
+// EPBs removed from the whole NAL [a, b); *later_shift = G of its last part (non-zero: some part may have to move)
+H264B_HD uint64_t nal_removed(uint64_t a, uint64_t b, uint64_t end_local, const uint32_t *S, uint64_t piece_bytes,
+                              uint32_t *later_shift) {
     const uint64_t Tq = (a - 1) / piece_bytes, Tb = (b - 1) / piece_bytes;
-    if (Tq == Tb) return end_local;
-    uint64_t G = piece_epb[Tq];
+    const uint32_t G = Tq == Tb ? 0u : S[Tb] - S[Tq];
+    *later_shift = G;
+    return (uint64_t)G + end_local;
+}
+// move(start, len, G) is called, in stream order, for every run of later parts that has to slide left by G > 0
+// (parts that lost nothing themselves are contiguous with their successor and share its G: they move as one run).
+template <class Move>
+H264B_HD void nal_pieces(uint64_t a, uint64_t b, uint32_t H, uint64_t end_local, const uint32_t *tail, const uint32_t *S,
+                         uint64_t piece_bytes, const Move &move) {
+    const uint64_t Tq = (a - 1) / piece_bytes, Tb = (b - 1) / piece_bytes;
+    uint64_t run_ps = 0, run_len = 0, run_G = 0;
     for (uint64_t t = Tq + 1; t <= Tb; t++) {
+        const uint64_t G = S[t] - S[Tq];
+        if (!G) continue;
         const uint64_t lo = t * piece_bytes, body = a + H;
         const uint64_t ps = lo > body ? lo : body;                    // first kept byte of the part
         const uint64_t pe = t < Tb ? (t + 1) * piece_bytes : b - 2;   // kept bytes are < pe (b-2, b-1: the tail rule)
-        const uint64_t e = t < Tb ? (uint64_t)piece_epb[t] : end_local;
-        if (G && pe > ps && pe - ps > e) move(ps, pe - ps - e, G);
-        if (t < Tb) G += piece_epb[t];
+        const uint64_t e = t < Tb ? (uint64_t)(tail[t] & 0xFFFFu) : end_local;
+        if (!(pe > ps && pe - ps > e)) continue;
+        const uint64_t len = pe - ps - e;
+        if (run_len && G == run_G && ps == run_ps + run_len) {
+            run_len += len;
+        } else {
+            if (run_len) move(run_ps, run_len, run_G);
+            run_ps = ps;
+            run_len = len;
+            run_G = G;
+        }
     }
-    return G + end_local;
+    if (run_len) move(run_ps, run_len, run_G);
 }
 
 }  // namespace h264b

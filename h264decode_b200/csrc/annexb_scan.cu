@@ -6,23 +6,28 @@
 //
 // The RBSP of a NAL is written at the position of the NAL's own body (h264b_nal.rbsp_off = start + header_bytes), so
 // a span of the stream that holds neither a start code nor an emulation-prevention byte -- all but a few KiB per MB
-// of entropy-coded data -- is an aligned copy.  The kernel is built around that:
+// of entropy-coded data -- is an aligned copy.  The pass is built around that, as two kernels over 2 KiB chunks:
 //
-//   pieces   the stream is cut into spans of chunks ("pieces", 128 KiB by default); a warp takes a piece by atomic
-//            ticket and walks its 2 KiB chunks front to back.  Warps never talk to each other: no block barrier, no
-//            look-back.  What a NAL lost in an EARLIER piece is made up for by the post-pass (nal_pieces).
-//   ring     every warp owns a ring of kStages shared-memory slots; lane 0 keeps it full with TMA 1-D bulk loads
-//            (cp.async.bulk + mbarrier complete_tx) of chunk + 16-byte halos, kStages-1 chunks ahead of the consumer
-//   detect   LDS.128 per lane and granule, word-parallel search for two adjacent zero bytes (zero_pair_bits): every
-//            00 00 03 and 00 00 00 01 needs one
-//   clean    no pair anywhere and nothing removed from the open NAL so far: lane 0 hands the slot to the TMA again,
-//            one 2 KiB bulk store straight from shared memory to out + pos (no registers, no STG)
-//   dirty    otherwise the chunk takes the general path: exact masks (granule_masks), start-code bitmap, bit-domain
-//            fix-up near start codes (keep_mask_near_sc), per-row segmented scan of (EPBs | start codes), in-place
-//            compaction of rows that only lose EPBs, shuffle-aligned 16-byte row stores, byte stores and NAL records
-//            (start, EPB count, first 4 bytes, rank in piece) for rows with boundaries
-// Post-passes (tiny): exclusive scan of the per-piece start-code counts, permutation of the records into stream
+//   K1a  annexb_copy_kernel   one warp per chunk, no shared memory, ~32 registers, full occupancy: coalesced LDG.128
+//                             (one 16-byte granule per lane and row), word-parallel search for two adjacent zero
+//                             bytes (zero_pair_acc: every 00 00 03 and 00 00 00 01 needs such a pair), and -- for a
+//                             chunk without one -- STG.128 of the same registers: a copy at copy speed.  A chunk
+//                             with a pair (or at an end of the stream) is only flagged.
+//   K1b  annexb_dirty_kernel  the flagged chunks (a few per cent of random data, far fewer really hold anything): the
+//                             chunk + 16-byte halos are staged in shared memory by a TMA 1-D bulk load (cp.async.bulk
+//                             + mbarrier complete_tx); exact masks (granule_masks), start-code bitmap, bit-domain
+//                             fix-up near start codes (keep_mask_near_sc), per-row segmented scan of (EPBs | start
+//                             codes), in-place compaction of rows that only lose EPBs, shuffle-aligned 16-byte row
+//                             stores, byte stores and NAL records (start, EPB count, first 4 bytes, rank in chunk)
+//                             for rows with boundaries.
+// Chunks never talk to each other: no block barrier, no look-back, no ticket.  Inside a chunk a kept byte at stream
+// position p goes to out[p - (EPBs removed from p's NAL earlier in the chunk)]; what a NAL lost in EARLIER chunks is
+// made up for by the post-pass (nal_pieces, annexb_local.cuh): rare, because emulation-prevention bytes are rare.
+// Post-passes (tiny): exclusive scan of the per-chunk start-code counts, permutation of the records into stream
 // order, h264b_nal records (lengths are differences of neighbours), and the slide of NAL parts described above.
+//
+// (Measured alternatives -- 16 KiB CTA tiles with decoupled look-back, warp-private TMA rings with bulk stores,
+// register pipelines over 128 KiB pieces -- are in the git history and profiles/r1_scan_*; DESIGN.md has the numbers.)
 #include "annexb_local.cuh"
 #include "common.cuh"
 
@@ -31,25 +36,22 @@ namespace h264b {
 #ifndef H264B_SCAN_ROWS
 #define H264B_SCAN_ROWS 4
 #endif
-#ifndef H264B_SCAN_STAGES
-#define H264B_SCAN_STAGES 4
-#endif
 #ifndef H264B_SCAN_WARPS
-#define H264B_SCAN_WARPS 4
+#define H264B_SCAN_WARPS 8
 #endif
 constexpr int kRows = H264B_SCAN_ROWS;             // 512-byte rows per chunk (one granule per lane and row), <= 16
 constexpr int kChunkGran = 32 * kRows;             // 128 granules
-constexpr int kChunk = kChunkGran * 16;            // 2048 bytes
+constexpr int kChunk = kChunkGran * 16;            // 2048 bytes: the piece of nal_pieces()
 constexpr int kHalo = 16;
 constexpr int kSlotBytes = kHalo + kChunk + kHalo; // 2080
-constexpr int kStages = H264B_SCAN_STAGES;         // ring slots per warp
-constexpr int kWarps = H264B_SCAN_WARPS;           // warps per CTA (independent of each other)
-constexpr uint32_t kMaxSpanBytes = 128 * 1024;     // piece size for large streams
+constexpr int kWarpsA = H264B_SCAN_WARPS;          // chunks per CTA of the copy kernel
+constexpr int kWarpsB = 4;                         // warps per CTA of the dirty-chunk kernel (32 chunk flags each)
+constexpr int kOrderTile = 4096;                   // chunks per CTA of the ordinal scan
 
-struct ScanScratchHeader {   // device scratch, initialised by scan_init_kernel
-    unsigned int ticket;           // next piece
+struct ScanScratchHeader {   // device scratch; zeroed (together with the piece array) before every pass
+    unsigned int n_dirty;          // entries of dirty_list
     unsigned int n_fix;            // entries of fix_list
-    unsigned long long first_start;
+    unsigned long long first_inv;  // max over NAL starts of ~start (0: no start code): first_start = ~first_inv
     unsigned long long total_sc;   // start codes found = slots handed out of the NAL record buffer
     unsigned long long total_kept;
     unsigned long long n_epb;
@@ -61,53 +63,88 @@ struct ScanArgs {
     uint64_t n;
     uint8_t *out;
     ScanScratchHeader *hdr;
-    uint32_t *piece_epb;       // per piece: EPBs after its last NAL start (or in the whole piece when it has none)
-    uint32_t *piece_nsc;       // per piece: start codes
-    uint32_t *piece_ord;       // per piece: ordinal of its first start code (exclusive scan of piece_nsc)
+    uint32_t *piece;           // per chunk: start codes << 16 | EPBs after its last NAL start (or in the whole chunk
+                               // when it has none); stays 0 for the chunks the copy kernel handled
+    uint32_t *dirty_list;      // chunks left to the dirty-chunk kernel, any order
+    uint32_t *piece_ord;       // per chunk: ordinal of its first start code (exclusive scan of the counts)
+    uint32_t *piece_S;         // per chunk: exclusive scan of the EPB fields (see nal_pieces)
+    uint2 *tile_sum;           // per kOrderTile chunks: (start codes, EPB fields): first phase of those scans
     uint32_t *fix_list;        // NAL ordinals whose later parts must slide left (written by scan_finalize_kernel)
-    // per start code, in slot order (chunks reserve slots with one atomicAdd): written by the main pass
+    // per start code, in slot order (chunks reserve slots with one atomicAdd): written by the dirty-chunk kernel
     unsigned long long *rec_start;
     uint32_t *rec_epb;
     uint32_t *rec_hdr;
-    uint32_t *rec_rank;        // rank of the start code inside its piece
+    uint32_t *rec_rank;        // rank of the start code inside its chunk
     // the same in stream order (written by nal_permute_kernel, read by scan_finalize_kernel)
     unsigned long long *nal_start;
-    uint32_t *nal_epb;         // [k]: EPBs removed (within the piece of start code k) from the NAL that ends there
+    uint32_t *nal_epb;         // [k]: EPBs removed (within the chunk of start code k) from the NAL that ends there
     uint32_t *nal_hdr;
     uint32_t nal_cap;
     uint32_t n_chunks;
-    uint32_t n_pieces;
-    uint32_t span_chunks;      // chunks per piece
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// ------------------------------------------------------------------------------------------------ init
-__global__ void scan_init_kernel(ScanScratchHeader *hdr, uint64_t n) {
-    hdr->ticket = 0;
-    hdr->n_fix = 0;
-    hdr->first_start = n;
-    hdr->total_sc = 0;
-    hdr->total_kept = 0;
-    hdr->n_epb = 0;
+// ------------------------------------------------------------------------------------------------ K1a: copy + detect
+// One warp per chunk.  Everything a thread needs is its own granules (4 x 16 bytes, all loads in flight at once), the
+// last word of the lane before it (shuffle) and the 8 bytes in front of the chunk (one broadcast load).
+__global__ void __launch_bounds__(kWarpsA * 32) annexb_copy_kernel(ScanArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t chunk = blockIdx.x * kWarpsA + (uint32_t)warp;
+    if (chunk >= a.n_chunks) return;
+    const uint64_t pos = (uint64_t)chunk * kChunk;
+    const uint8_t *src = a.in + pos + lane * 16;
+    uint4 v[kRows];
+    uint2 t8 = make_uint2(~0u, ~0u);  // the 8 bytes before the chunk
+    if (pos + kChunk <= a.n) {        // warp-uniform: a whole chunk
+#pragma unroll
+        for (int r = 0; r < kRows; r++) v[r] = __ldcs(reinterpret_cast<const uint4 *>(src + r * 512));
+    } else {
+        const uint64_t n16 = (a.n + 15) & ~15ull;
+#pragma unroll
+        for (int r = 0; r < kRows; r++)
+            v[r] = pos + (uint32_t)(r * 32 + lane) * 16u < n16 ? __ldcs(reinterpret_cast<const uint4 *>(src + r * 512))
+                                                              : make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
+    if (pos) t8 = *reinterpret_cast<const uint2 *>(a.in + pos - 8);
+
+    // Does the chunk hold anything to remove or to index?  First the cheap filter (two adjacent zero bytes), then,
+    // only in the lanes it fires for, the exact masks.
+    uint32_t need = 0;
+#ifndef H264B_EXP_NODETECT
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+        uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, v[r].w, 1);
+        const uint32_t wrap = r ? __shfl_sync(0xFFFFFFFFu, v[r ? r - 1 : 0].w, 31) : t8.y;
+        if (lane == 0) prev = wrap;
+        const uint32_t w[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+        need |= granule_needs_general(w, prev);
+    }
+    const uint32_t last_word = __shfl_sync(0xFFFFFFFFu, v[kRows - 1].w, 31);
+    if (chunk_edges_need_general(t8.x, t8.y, last_word)) need |= 1u;
+#endif
+    // chunks that touch the ends of the stream always take the general path (it blanks the bytes outside)
+    const bool edge = pos == 0 || pos + kChunk + kHalo > a.n;
+    const bool dirty = __any_sync(0xFFFFFFFFu, need != 0) || edge;
+    if (dirty) {
+        if (lane == 0) a.dirty_list[atomicAdd(&a.hdr->n_dirty, 1u)] = chunk;
+        return;
+    }
+#ifndef H264B_EXP_NOSTORE
+    uint8_t *dst = a.out + pos + lane * 16;
+#pragma unroll
+    for (int r = 0; r < kRows; r++) __stcs(reinterpret_cast<uint4 *>(dst + r * 512), v[r]);
+#endif
 }
 
-// ------------------------------------------------------------------------------------------------ main pass
-struct __align__(16) WarpRing {
-    uint8_t slot[kStages][kSlotBytes];    // each: [0,16) low halo, [16,16+kChunk) chunk, high halo
-    ulonglong2 meta[kStages];             // .x = stream offset of the chunk in the slot (~0: no more work), .y = its piece
-    unsigned long long mbar[kStages];     // "bytes have landed"
+// ------------------------------------------------------------------------------------------------ K1b: dirty chunks
+struct __align__(16) WarpStage {
+    uint8_t buf[kSlotBytes];              // [0,16) low halo, [16,16+kChunk) chunk, high halo
+    unsigned long long mbar;              // "bytes have landed"
     uint16_t scbits[kChunkGran + 2];      // start-code-end bits per granule, [0] = halo granule before the chunk
-    uint16_t pad[(8 - (kChunkGran + 2 + 4 * kStages) % 8) % 8];
+    uint16_t pad[(8 - (kChunkGran + 2 + 4) % 8) % 8];
 };
-static_assert(sizeof(WarpRing) % 16 == 0 && kSlotBytes % 16 == 0, "ring slots must stay 16-byte aligned");
-
-// TMA bulk store shared -> global (16-byte aligned on both sides, size a multiple of 16)
-__device__ __forceinline__ void bulk_store(uint8_t *dst_global, const uint8_t *src_shared, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_global),
-                 "r"(smem_u32(src_shared)), "r"(bytes)
-                 : "memory");
-}
+static_assert(sizeof(WarpStage) % 16 == 0 && kSlotBytes % 16 == 0, "staging buffers must stay 16-byte aligned");
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
@@ -166,7 +203,7 @@ __device__ __noinline__ void store_boundary_granule(const ScanArgs &a, uint64_t 
     store_granule_bytes(a.out, gpos, w, k16, ee, sc, c, [&](int j, uint64_t c_end) {
         const uint64_t st = gpos + (uint64_t)j + 1;  // the new NAL's first byte
         if (first_of_chunk) {
-            atomicMin(&a.hdr->first_start, (unsigned long long)st);
+            atomicMax(&a.hdr->first_inv, ~(unsigned long long)st);
             first_of_chunk = false;
         }
         if (k < a.nal_cap) {
@@ -352,286 +389,46 @@ __device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, uint16_t *s
     return res;
 }
 
-// Producer side of a warp's ring (lane 0 only): pieces by ticket, their chunks in order.
-struct Producer {
-    uint64_t pos;    // stream offset of the next chunk to load
-    uint32_t left;   // chunks of the current piece still to load
-    uint32_t piece;
-    uint32_t done;   // the tickets have run out
-    uint32_t next_static;  // (H264B_SCAN_STATIC: pieces dealt round-robin instead of by ticket)
-};
-
-__device__ __forceinline__ void tma_load(uint32_t dst, const uint8_t *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-
-// everything but an interior chunk of the current piece: next piece, first / last chunks of the stream, the end
-__device__ __noinline__ void produce_slow(const ScanArgs &a, WarpRing &ring, int s, Producer *p) {
-    if (!p->done && p->left == 0) {
-#ifdef H264B_SCAN_STATIC
-        p->piece = p->next_static;
-        p->next_static += gridDim.x * kWarps;
-#else
-        p->piece = atomicAdd(&a.hdr->ticket, 1u);
-#endif
-        if (p->piece < a.n_pieces) {
-            const uint32_t first = p->piece * a.span_chunks;
-            p->left = first + a.span_chunks < a.n_chunks ? a.span_chunks : a.n_chunks - first;
-            p->pos = (uint64_t)first * kChunk;
-        } else {
-            p->done = 1;
-        }
-    }
-    const uint32_t bar = smem_u32(&ring.mbar[s]);
-    if (p->done) {  // an arrival without bytes: the consumer sees "no more work"
-        ring.meta[s] = make_ulonglong2(~0ull, 0ull);
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-        return;
-    }
-    const uint64_t pos = p->pos, n16 = (a.n + 15) & ~15ull;
-    ring.meta[s] = make_ulonglong2(pos, (unsigned long long)p->piece);
-    const uint64_t lo = pos ? pos - kHalo : 0;
-    uint64_t hi = pos + kChunk + kHalo;
-    if (hi > n16) hi = n16;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tma_load(smem_u32(ring.slot[s] + (lo + kHalo - pos)), a.in + lo, (uint32_t)(hi - lo), bar);
-    p->pos = pos + kChunk;
-    p->left--;
-}
-
-__global__ void __launch_bounds__(kWarps * 32) annexb_scan_kernel(ScanArgs a) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
+// One warp per listed chunk (grid-stride over the list): the TMA stages the chunk, the whole warp walks it.
+__global__ void __launch_bounds__(kWarpsB * 32) annexb_dirty_kernel(ScanArgs a) {
+    __shared__ WarpStage stage[kWarpsB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpRing &ring = reinterpret_cast<WarpRing *>(smem_raw)[warp];
+    WarpStage &st = stage[warp];
+    const uint32_t bar = smem_u32(&st.mbar);
     if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kStages; s++)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&ring.mbar[s])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
+    const uint32_t n_dirty = a.hdr->n_dirty;
     const uint64_t n16 = (a.n + 15) & ~15ull;
-
-    Producer prod = {0, 0, 0, 0, blockIdx.x * kWarps + (uint32_t)warp};
-    if (lane == 0) {
-        Producer t = prod;
-#pragma unroll 1
-#ifdef H264B_SCAN_STG
-        for (int s = 0; s < kStages; s++) produce_slow(a, ring, s, &t);
-#else
-        for (int s = 0; s < kStages - 1; s++) produce_slow(a, ring, s, &t);
-#endif
-        prod = t;
-    }
-
-    uint32_t cur_piece = 0xFFFFFFFFu;
-    uint32_t carry_epb = 0, piece_nsc = 0;
-    int s = 0;            // slot of the chunk being consumed
-    uint32_t parity = 0;  // phase parity of its barrier
-#pragma unroll 1
-    for (;;) {
-        mbar_wait(smem_u32(&ring.mbar[s]), parity);
-        const ulonglong2 meta = ring.meta[s];
-        const uint64_t pos = meta.x;
-        if (pos == ~0ull) break;
-        if ((uint32_t)meta.y != cur_piece) {
-            if (cur_piece != 0xFFFFFFFFu && lane == 0) {
-                a.piece_epb[cur_piece] = carry_epb;
-                a.piece_nsc[cur_piece] = piece_nsc;
-            }
-            cur_piece = (uint32_t)meta.y;
-            carry_epb = 0;
-            piece_nsc = 0;
+    uint32_t parity = 0;
+    for (uint32_t i = blockIdx.x * kWarpsB + (uint32_t)warp; i < n_dirty; i += gridDim.x * kWarpsB) {
+        const uint32_t chunk = a.dirty_list[i];
+        const uint64_t pos = (uint64_t)chunk * kChunk;
+        if (lane == 0) {  // TMA bulk load of the chunk and its halos, clipped to the stream
+            const uint64_t lo = pos ? pos - kHalo : 0;
+            uint64_t hi = pos + kChunk + kHalo;
+            if (hi > n16) hi = n16;
+            const uint32_t bytes = (uint32_t)(hi - lo);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    smem_u32(st.buf + (lo + kHalo - pos))),
+                "l"(a.in + lo), "r"(bytes), "r"(bar)
+                : "memory");
         }
-        uint8_t *buf = ring.slot[s];
-        uint8_t *tile_in = buf + kHalo;  // tile_in[i] = s[pos + i], valid for i in [-16, kChunk+16)
-
-        // ---------------------------------------------------------------- detect: two adjacent zero bytes anywhere?
-        uint32_t acc = 0xFFFFFFFFu;
-#ifdef H264B_SCAN_STG
-        uint4 vv[kRows];
-#pragma unroll
-        for (int r = 0; r < kRows; r++) vv[r] = *reinterpret_cast<const uint4 *>(tile_in + (r * 32 + lane) * 16);
-#endif
-#if !defined(H264B_EXP_NODETECT) && !defined(H264B_EXP_LOADONLY)
-#pragma unroll
-        for (int r = 0; r < kRows; r++) {
-            const int gi = r * 32 + lane;
-#ifdef H264B_SCAN_STG
-            const uint4 v = vv[r];
-#else
-            const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
-#endif
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            acc = zero_pair_acc(acc, w, *reinterpret_cast<const uint32_t *>(tile_in + gi * 16 - 4));
-        }
-        {   // a start code ending in the last bytes before the chunk still reaches into it (same words for all lanes)
-            const uint2 t8 = *reinterpret_cast<const uint2 *>(buf + 8);
-            acc = zero_pair_acc_tail8(acc, t8.x, t8.y);
-        }
-#endif
-        // chunks that touch the ends of the stream always take the general path (it blanks the bytes outside)
-        const bool edge = pos == 0 || pos + kChunk + kHalo > a.n;
-        bool clean = !(__any_sync(0xFFFFFFFFu, acc_has_pair(acc)) || carry_epb != 0 || edge);
-#ifdef H264B_EXP_LOADONLY
-        clean = false;
-#else
-        if (!clean) {
-            const ChunkResult res = general_chunk(a, ring.scbits, buf, pos, carry_epb, piece_nsc, lane);
-            carry_epb = res.carry_epb;
-            piece_nsc = res.piece_nsc;
-            clean = res.clean != 0;
-        }
-#endif
-        __syncwarp();  // every lane is done reading (and writing) the slot
-#ifdef H264B_SCAN_STG
-        const int s_prev = s;  // the registers hold the chunk: its slot is free at once
-#ifndef H264B_EXP_NOSTORE
-        if (clean) {
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        const ChunkResult res = general_chunk(a, st.scbits, st.buf, pos, 0u, 0u, lane);
+        if (res.clean) {  // a false alarm (00 00 03 whose zeros are header bytes, ...): the verbatim copy after all
 #pragma unroll
             for (int r = 0; r < kRows; r++)
-                *reinterpret_cast<uint4 *>(a.out + pos + (uint32_t)(r * 32 + lane) * 16u) = vv[r];
+                *reinterpret_cast<uint4 *>(a.out + pos + (uint32_t)(r * 32 + lane) * 16u) =
+                    *reinterpret_cast<const uint4 *>(st.buf + kHalo + (r * 32 + lane) * 16);
         }
-#endif
-#else
-        const int s_prev = s ? s - 1 : kStages - 1;
-#endif
-        if (lane == 0) {
-#ifndef H264B_SCAN_STG
-#ifndef H264B_EXP_NOSTORE
-            // the bulk of a real stream leaves through the TMA: one bulk store straight from the slot
-            if (clean) bulk_store(a.out + pos, tile_in, kChunk);
-#endif
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            // all but the newest store have finished reading shared memory: the slot of the previous chunk is free
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-#endif
-            if (prod.left != 0 && prod.pos + kChunk + kHalo <= n16) {  // interior chunk of the current piece
-                ring.meta[s_prev] = make_ulonglong2(prod.pos, (unsigned long long)prod.piece);
-                tma_load(smem_u32(ring.slot[s_prev]), a.in + prod.pos - kHalo, kSlotBytes, smem_u32(&ring.mbar[s_prev]));
-                prod.pos += kChunk;
-                prod.left--;
-            } else {
-                Producer t = prod;
-                produce_slow(a, ring, s_prev, &t);
-                prod = t;
-            }
-        }
-        if (++s == kStages) {
-            s = 0;
-            parity ^= 1u;
-        }
-    }
-    if (lane == 0) {
-        if (cur_piece != 0xFFFFFFFFu) {
-            a.piece_epb[cur_piece] = carry_epb;
-            a.piece_nsc[cur_piece] = piece_nsc;
-        }
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ main pass, LDG form
-// The same pass with the chunk held in registers: coalesced LDG.128 (one granule per lane and row, the next chunk of
-// the piece already in flight while this one is examined), the previous word by shuffle, STG.128 for clean chunks.
-// Only chunks that take the general path are staged in shared memory.
-struct __align__(16) WarpStage {
-    uint8_t buf[kSlotBytes];
-    uint16_t scbits[kChunkGran + 2];
-    uint16_t pad[(8 - (kChunkGran + 2) % 8) % 8];
-};
-
-struct ChunkRegs {
-    uint4 v[kRows];
-    uint2 t8;  // the 8 bytes before the chunk
-};
-
-__device__ __forceinline__ void load_chunk(ChunkRegs &c, const uint8_t *in, uint64_t pos, uint64_t n16, int lane) {
-#pragma unroll
-    for (int r = 0; r < kRows; r++) {
-        const uint64_t g = pos + (uint32_t)(r * 32 + lane) * 16u;
-        c.v[r] = g < n16 ? __ldcs(reinterpret_cast<const uint4 *>(in + g)) : make_uint4(~0u, ~0u, ~0u, ~0u);
-    }
-    c.t8 = pos ? *reinterpret_cast<const uint2 *>(in + pos - 8) : make_uint2(~0u, ~0u);
-}
-
-__global__ void __launch_bounds__(kWarps * 32) annexb_scan_ldg_kernel(ScanArgs a) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpStage &st = reinterpret_cast<WarpStage *>(smem_raw)[warp];
-    const uint64_t n16 = (a.n + 15) & ~15ull;
-#ifdef H264B_SCAN_STATIC
-    uint32_t next_static = blockIdx.x * kWarps + (uint32_t)warp;
-#endif
-#pragma unroll 1
-    for (;;) {
-#ifdef H264B_SCAN_STATIC
-        const uint32_t piece = next_static;
-        next_static += gridDim.x * kWarps;
-#else
-        uint32_t piece = 0;
-        if (lane == 0) piece = atomicAdd(&a.hdr->ticket, 1u);
-        piece = __shfl_sync(0xFFFFFFFFu, piece, 0);
-#endif
-        if (piece >= a.n_pieces) break;
-        const uint32_t c0 = piece * a.span_chunks;
-        const uint32_t c1 = c0 + a.span_chunks < a.n_chunks ? c0 + a.span_chunks : a.n_chunks;
-        uint32_t carry_epb = 0, piece_nsc = 0;
-        ChunkRegs cur;
-        load_chunk(cur, a.in, (uint64_t)c0 * kChunk, n16, lane);
-#pragma unroll 1
-        for (uint32_t c = c0; c < c1; c++) {
-            const uint64_t pos = (uint64_t)c * kChunk;
-            ChunkRegs nxt;
-            if (c + 1 < c1) load_chunk(nxt, a.in, pos + kChunk, n16, lane);
-            // ---------------------------------------------------------------- detect
-            uint32_t acc = 0xFFFFFFFFu;
-#ifndef H264B_EXP_NODETECT
-#pragma unroll
-            for (int r = 0; r < kRows; r++) {
-                uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, cur.v[r].w, 1);
-                const uint32_t wrap = r ? __shfl_sync(0xFFFFFFFFu, cur.v[r ? r - 1 : 0].w, 31) : cur.t8.y;
-                if (lane == 0) prev = wrap;
-                const uint32_t w[4] = {cur.v[r].x, cur.v[r].y, cur.v[r].z, cur.v[r].w};
-                acc = zero_pair_acc(acc, w, prev);
-            }
-            acc = zero_pair_acc_tail8(acc, cur.t8.x, cur.t8.y);
-#endif
-            const bool edge = pos == 0 || pos + kChunk + kHalo > a.n;
-            bool clean = !(__any_sync(0xFFFFFFFFu, acc_has_pair(acc)) || carry_epb != 0 || edge);
-            if (!clean) {
-                // stage the chunk and its halos exactly as a bulk load of [lo, hi) would have left them
-                uint8_t *tile_in = st.buf + kHalo;
-#pragma unroll
-                for (int r = 0; r < kRows; r++)
-                    if (pos + (uint32_t)(r * 32 + lane) * 16u < n16)
-                        *reinterpret_cast<uint4 *>(tile_in + (r * 32 + lane) * 16) = cur.v[r];
-                if (lane == 0 && pos) *reinterpret_cast<uint4 *>(st.buf) = *reinterpret_cast<const uint4 *>(a.in + pos - kHalo);
-                if (lane == 1 && pos + kChunk < n16)
-                    *reinterpret_cast<uint4 *>(tile_in + kChunk) = *reinterpret_cast<const uint4 *>(a.in + pos + kChunk);
-                __syncwarp();
-                const ChunkResult res = general_chunk(a, st.scbits, st.buf, pos, carry_epb, piece_nsc, lane);
-                carry_epb = res.carry_epb;
-                piece_nsc = res.piece_nsc;
-                clean = res.clean != 0;
-                __syncwarp();
-            }
-#ifndef H264B_EXP_NOSTORE
-            if (clean) {
-#pragma unroll
-                for (int r = 0; r < kRows; r++)
-                    __stcs(reinterpret_cast<uint4 *>(a.out + pos + (uint32_t)(r * 32 + lane) * 16u), cur.v[r]);
-            }
-#endif
-            cur = nxt;
-        }
-        if (lane == 0) {
-            a.piece_epb[piece] = carry_epb;
-            a.piece_nsc[piece] = piece_nsc;
-        }
+        if (lane == 0) a.piece[chunk] = (res.piece_nsc << 16) | res.carry_epb;
+        __syncwarp();  // every lane is done with the staging buffer before the next bulk load lands in it
     }
 }
 
@@ -681,48 +478,102 @@ __device__ __forceinline__ void decode_nal_header(uint32_t hdr4, h264b_nal &o, h
     *ext = e;
 }
 
-// Post-pass 1: ordinal of every piece's first start code = exclusive scan of the per-piece start-code counts.  One CTA;
-// the array has one entry per piece (128 KiB of stream): every thread sums a contiguous run, one block scan, done.
-__global__ void __launch_bounds__(1024) piece_order_kernel(const uint32_t *piece_nsc, uint32_t *piece_ord,
-                                                           uint32_t n_pieces) {
-    __shared__ uint32_t warp_sum[32];
+// Post-pass 1: exclusive scans over the chunks of (a) the start-code counts -> ordinal of every chunk's first start
+// code and (b) the EPB fields -> S of nal_pieces(); in two phases over tiles of kOrderTile chunks: tile totals, then
+// every CTA adds up the totals of the tiles before its own (a few hundred values for a 4 GB stream) and scans its tile.
+__device__ __forceinline__ uint2 block_sum2_256(uint2 x, uint2 *warp_sum, int tid) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        x.x += __shfl_xor_sync(0xFFFFFFFFu, x.x, d);
+        x.y += __shfl_xor_sync(0xFFFFFFFFu, x.y, d);
+    }
+    if ((tid & 31) == 0) warp_sum[tid >> 5] = x;
+    __syncthreads();
+    uint2 t = make_uint2(0, 0);
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        t.x += warp_sum[w].x;
+        t.y += warp_sum[w].y;
+    }
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(256) order_reduce_kernel(const uint32_t *piece, uint2 *tile_sum, uint32_t n_chunks) {
+    __shared__ uint2 warp_sum[8];
+    const int tid = threadIdx.x;
+    const uint32_t base = blockIdx.x * kOrderTile;
+    uint2 x = make_uint2(0, 0);
+#pragma unroll
+    for (int k = 0; k < kOrderTile / 256; k++) {
+        const uint32_t i = base + (uint32_t)(k * 256 + tid);
+        if (i < n_chunks) {
+            const uint32_t p = piece[i];
+            x.x += p >> 16;
+            x.y += p & 0xFFFFu;
+        }
+    }
+    x = block_sum2_256(x, warp_sum, tid);
+    if (tid == 0) tile_sum[blockIdx.x] = x;
+}
+
+__global__ void __launch_bounds__(256) order_apply_kernel(const uint32_t *piece, const uint2 *tile_sum,
+                                                           uint32_t *piece_ord, uint32_t *piece_S, uint32_t n_chunks) {
+    __shared__ uint2 warp_sum[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t per = (n_pieces + 1023u) / 1024u;
-    const uint32_t lo = (uint32_t)tid * per < n_pieces ? (uint32_t)tid * per : n_pieces;
-    const uint32_t hi = lo + per < n_pieces ? lo + per : n_pieces;
-    uint32_t own = 0;
-    for (uint32_t i = lo; i < hi; i++) own += piece_nsc[i];
-    uint32_t x = own;
+    uint2 before = make_uint2(0, 0);  // totals of the tiles before this one
+    for (uint32_t t = (uint32_t)tid; t < blockIdx.x; t += 256) {
+        const uint2 s = tile_sum[t];
+        before.x += s.x;
+        before.y += s.y;
+    }
+    before = block_sum2_256(before, warp_sum, tid);
+    constexpr int kPer = kOrderTile / 256;  // contiguous chunks per thread
+    const uint32_t first = blockIdx.x * kOrderTile + (uint32_t)tid * kPer;
+    uint32_t c[kPer];
+    uint2 own = make_uint2(0, 0);
+#pragma unroll
+    for (int k = 0; k < kPer; k++) {
+        c[k] = first + k < n_chunks ? piece[first + k] : 0u;
+        own.x += c[k] >> 16;
+        own.y += c[k] & 0xFFFFu;
+    }
+    uint2 x = own;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
-        if (lane >= d) x += y;
+        const uint32_t yx = __shfl_up_sync(0xFFFFFFFFu, x.x, d), yy = __shfl_up_sync(0xFFFFFFFFu, x.y, d);
+        if (lane >= d) {
+            x.x += yx;
+            x.y += yy;
+        }
     }
     if (lane == 31) warp_sum[warp] = x;
     __syncthreads();
-    uint32_t w = warp_sum[lane], wi = w;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wi, d);
-        if (lane >= d) wi += y;
+    uint2 run = make_uint2(before.x + x.x - own.x, before.y + x.y - own.y);
+    for (int w = 0; w < warp; w++) {
+        run.x += warp_sum[w].x;
+        run.y += warp_sum[w].y;
     }
-    uint32_t run = __shfl_sync(0xFFFFFFFFu, wi - w, warp) + x - own;  // start codes before this thread's run
-    for (uint32_t i = lo; i < hi; i++) {
-        piece_ord[i] = run;
-        run += piece_nsc[i];
+#pragma unroll
+    for (int k = 0; k < kPer; k++) {
+        if (first + k < n_chunks) {
+            piece_ord[first + k] = run.x;
+            piece_S[first + k] = run.y;
+        }
+        run.x += c[k] >> 16;
+        run.y += c[k] & 0xFFFFu;
     }
 }
 
-// Post-pass 2: move every record from its slot to its ordinal (stream order): ordinal = first ordinal of the piece
-// that holds the start code + the record's rank inside that piece.
+// Post-pass 2: move every record from its slot to its ordinal (stream order): ordinal = first ordinal of the chunk
+// that holds the start code + the record's rank inside that chunk.
 __global__ void __launch_bounds__(256) nal_permute_kernel(ScanArgs a) {
     const uint64_t cap = a.nal_cap;
     uint64_t K = a.hdr->total_sc;
     if (K > cap) K = cap;
-    const uint64_t piece_bytes = (uint64_t)a.span_chunks * kChunk;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < K; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t st = a.rec_start[i];
-        const uint64_t ord = (uint64_t)a.piece_ord[(st - 1) / piece_bytes] + a.rec_rank[i];
+        const uint64_t ord = (uint64_t)a.piece_ord[(st - 1) / kChunk] + a.rec_rank[i];
         if (ord < cap) {
             a.nal_start[ord] = st;
             a.nal_epb[ord] = a.rec_epb[i];
@@ -747,11 +598,9 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(ScanArgs a, h264b_na
         const uint64_t next = a.nal_start[k + 1];
         o.num_bytes = (uint32_t)(next - o.start);
         decode_nal_header(a.nal_hdr[k], o, ext ? &ext[k] : nullptr);
-        bool fix = false;
-        const uint64_t removed = nal_pieces(o.start, next, o.header_bytes, a.nal_epb[k + 1], a.piece_epb,
-                                            (uint64_t)a.span_chunks * kChunk,
-                                            [&](uint64_t, uint64_t, uint64_t) { fix = true; });
-        if (fix) a.fix_list[atomicAdd(&a.hdr->n_fix, 1u)] = (uint32_t)k;
+        uint32_t later_shift;
+        const uint64_t removed = nal_removed(o.start, next, a.nal_epb[k + 1], a.piece_S, (uint64_t)kChunk, &later_shift);
+        if (later_shift) a.fix_list[atomicAdd(&a.hdr->n_fix, 1u)] = (uint32_t)k;
         // body = NumBytes - HeaderBytes - 2 bytes (a NAL shorter than that has no body); its RBSP sits at the body's
         // own position in the output buffer
         const int64_t body = (int64_t)o.num_bytes - (int64_t)o.header_bytes - 2;
@@ -762,19 +611,68 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(ScanArgs a, h264b_na
         rbsp += o.rbsp_len;
         nals[k] = o;
     }
-    if (epb) atomicAdd(&a.hdr->n_epb, epb);
-    if (rbsp) atomicAdd(&a.hdr->total_kept, rbsp);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {  // one pair of atomics per warp
+        epb += __shfl_xor_sync(0xFFFFFFFFu, epb, d);
+        rbsp += __shfl_xor_sync(0xFFFFFFFFu, rbsp, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (epb) atomicAdd(&a.hdr->n_epb, epb);
+        if (rbsp) atomicAdd(&a.hdr->total_kept, rbsp);
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         summary->n_start_codes = K;
         summary->n_nals = n_nals;
-        summary->first_start = a.hdr->first_start;
+        summary->first_start = K ? ~a.hdr->first_inv : a.n;
         summary->status = (K > a.nal_cap) ? H264B_E_CAPACITY : H264B_OK;
         summary->reserved = 0;
     }
 }
 
-// Post-pass 4: slide the later parts of the queued NALs left (one CTA per NAL, parts in stream order, 4 KiB at a
-// time: everything is read into registers before anything is written, so the overlapping move is safe).
+// Post-pass 4: slide the later parts of the queued NALs left (one CTA per NAL, runs in stream order).  A run moves in
+// steps of 16 KiB: every thread assembles up to four destination-aligned 16-byte granules from aligned source words
+// (funnel shifts) in registers, the CTA synchronises, then stores -- the move overlaps itself, reads come first.
+constexpr int kMoveGran = 4;                         // granules per thread and step
+constexpr uint64_t kMoveStep = 256 * 16 * kMoveGran;  // 16 KiB
+
+__device__ __forceinline__ void move_left(uint8_t *out, uint64_t ps, uint64_t len, uint64_t G) {
+    const uint64_t d0 = ps - G, d1 = d0 + len;  // destination range
+    const uint32_t s8 = (uint32_t)((d0 + G) & 3u) * 8u;  // (the same for every granule: D is a multiple of 16)
+    (void)s8;
+    for (uint64_t base = d0 & ~15ull; base < d1; base += kMoveStep) {
+        uint32_t y[kMoveGran][4];
+#pragma unroll
+        for (int q = 0; q < kMoveGran; q++) {
+            const uint64_t D = base + (uint64_t)(q * 256 + (int)threadIdx.x) * 16u;
+            if (D < d1) {
+                const uint64_t src = D + G;
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(out + (src & ~3ull));
+                const uint32_t sh = (uint32_t)(src & 3u) * 8u;
+                const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = sh ? wp[4] : 0u;
+                y[q][0] = __funnelshift_r(w0, w1, sh);
+                y[q][1] = __funnelshift_r(w1, w2, sh);
+                y[q][2] = __funnelshift_r(w2, w3, sh);
+                y[q][3] = __funnelshift_r(w3, w4, sh);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kMoveGran; q++) {
+            const uint64_t D = base + (uint64_t)(q * 256 + (int)threadIdx.x) * 16u;
+            if (D < d1) {
+                if (D >= d0 && D + 16 <= d1) {
+                    *reinterpret_cast<uint4 *>(out + D) = make_uint4(y[q][0], y[q][1], y[q][2], y[q][3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j++)
+                        if (D + j >= d0 && D + j < d1) out[D + j] = (uint8_t)granule_byte(y[q], j);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(256) nal_fixup_kernel(ScanArgs a, h264b_scan_summary *summary) {
     const uint32_t n_fix = a.hdr->n_fix;
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // totals of scan_finalize_kernel (complete: previous launch)
@@ -786,24 +684,10 @@ __global__ void __launch_bounds__(256) nal_fixup_kernel(ScanArgs a, h264b_scan_s
         const uint64_t st = a.nal_start[k], next = a.nal_start[k + 1];
         h264b_nal o;
         decode_nal_header(a.nal_hdr[k], o, nullptr);
-        nal_pieces(st, next, o.header_bytes, a.nal_epb[k + 1], a.piece_epb, (uint64_t)a.span_chunks * kChunk,
-                   [&](uint64_t ps, uint64_t len, uint64_t G) {
-                       for (uint64_t off = 0; off < len; off += 256 * 16) {
-                           const uint64_t p = ps + off + (uint64_t)threadIdx.x * 16;
-                           uint8_t v[16];
-                           const uint64_t end = ps + len;
-#pragma unroll
-                           for (int j = 0; j < 16; j++) v[j] = p + j < end ? a.out[p + j] : (uint8_t)0;
-                           __syncthreads();
-#pragma unroll
-                           for (int j = 0; j < 16; j++)
-                               if (p + j < end) a.out[p + j - G] = v[j];
-                           __syncthreads();
-                       }
-                   });
+        nal_pieces(st, next, o.header_bytes, a.nal_epb[k + 1], a.piece, a.piece_S, (uint64_t)kChunk,
+                   [&](uint64_t ps, uint64_t len, uint64_t G) { move_left(a.out, ps, len, G); });
     }
 }
-
 
 // ------------------------------------------------------------------------------------------------ frames (NewNalUnit)
 // One CTA per frame; RBSP of frame i is written at rbsp + off[i] (never longer than the frame).
@@ -918,10 +802,11 @@ __global__ void __launch_bounds__(1024) slice_select_kernel(const h264b_nal *nal
 
 // ------------------------------------------------------------------------------------------------ launchers
 struct ScratchOffsets {
-    uint64_t piece_epb, piece_nsc, piece_ord, fix_list, rec_start, rec_epb, rec_hdr, rec_rank, nal_start, nal_epb,
-        nal_hdr, total;
+    uint64_t piece, dirty_list, piece_ord, piece_S, tile_sum, fix_list, rec_start, rec_epb, rec_hdr, rec_rank, nal_start,
+        nal_epb, nal_hdr, total;
 };
-static ScratchOffsets scratch_layout(uint64_t n_pieces, uint32_t nal_cap) {
+static ScratchOffsets scratch_layout(uint64_t n, uint32_t nal_cap) {
+    const uint64_t n_chunks = (n + kChunk - 1) / kChunk;
     ScratchOffsets o;
     uint64_t p = sizeof(ScanScratchHeader);
     auto take = [&](uint64_t bytes) {
@@ -929,9 +814,11 @@ static ScratchOffsets scratch_layout(uint64_t n_pieces, uint32_t nal_cap) {
         p = (p + bytes + 15) & ~15ull;
         return at;
     };
-    o.piece_epb = take(n_pieces * 4);
-    o.piece_nsc = take(n_pieces * 4);
-    o.piece_ord = take(n_pieces * 4);
+    o.piece = take(n_chunks * 4);  // directly behind the header: one memset clears both
+    o.dirty_list = take(n_chunks * 4);
+    o.piece_ord = take(n_chunks * 4);
+    o.piece_S = take(n_chunks * 4);
+    o.tile_sum = take((n_chunks + kOrderTile - 1) / kOrderTile * 8);
     o.fix_list = take((uint64_t)nal_cap * 4);
     o.rec_start = take((uint64_t)nal_cap * 8);
     o.rec_epb = take((uint64_t)nal_cap * 4);
@@ -950,36 +837,7 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     if (((uintptr_t)d_stream & 15) || ((uintptr_t)d_rbsp & 15))
         return set_error(ctx, H264B_E_INVALID, "annexb_scan: d_stream and d_rbsp must be 16-byte aligned");
     if (n >= (1ull << 42)) return set_error(ctx, H264B_E_INVALID, "annexb_scan: stream too long");
-
-    // launch shape: as many warps as fit, each with its own ring of slots
-    static bool attr_set = false;
-#ifdef H264B_SCAN_LDG
-    const auto main_kernel = annexb_scan_ldg_kernel;
-    const size_t smem = sizeof(WarpStage) * kWarps;
-#else
-    const auto main_kernel = annexb_scan_kernel;
-    const size_t smem = sizeof(WarpRing) * kWarps;
-#endif
-    if (!attr_set) {
-        H264B_CUDA(ctx, cudaFuncSetAttribute(main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
-    int occ = 0;
-    H264B_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, main_kernel, kWarps * 32, smem));
-    if (occ < 1) occ = 1;
-    const uint64_t max_ctas = (uint64_t)ctx->sm_count * occ;
-
-    // pieces: 128 KiB for large streams; smaller when the stream would otherwise leave most warps without work
-    const uint64_t n_chunks = (n + kChunk - 1) / kChunk;
-    uint64_t span = ctx->scan_span_chunks;
-    if (!span) {
-        span = n_chunks / (max_ctas * kWarps * 4);
-        if (span > kMaxSpanBytes / kChunk) span = kMaxSpanBytes / kChunk;
-        if (span < 1) span = 1;
-    }
-    const uint64_t n_pieces = (n_chunks + span - 1) / span;
-
-    const ScratchOffsets so = scratch_layout(n_pieces, nal_cap);
+    const ScratchOffsets so = scratch_layout(n, nal_cap);
     if (so.total > ctx->scan_scratch_bytes) {
         if (ctx->scan_scratch) {
             H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -991,14 +849,17 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
         ctx->scan_scratch_bytes = so.total;
     }
     uint8_t *s = (uint8_t *)ctx->scan_scratch;
+    const uint64_t n_chunks = (n + kChunk - 1) / kChunk;
     ScanArgs a;
     a.in = d_stream;
     a.n = n;
     a.out = d_rbsp;
     a.hdr = (ScanScratchHeader *)s;
-    a.piece_epb = (uint32_t *)(s + so.piece_epb);
-    a.piece_nsc = (uint32_t *)(s + so.piece_nsc);
+    a.piece = (uint32_t *)(s + so.piece);
+    a.dirty_list = (uint32_t *)(s + so.dirty_list);
     a.piece_ord = (uint32_t *)(s + so.piece_ord);
+    a.piece_S = (uint32_t *)(s + so.piece_S);
+    a.tile_sum = (uint2 *)(s + so.tile_sum);
     a.fix_list = (uint32_t *)(s + so.fix_list);
     a.rec_start = (unsigned long long *)(s + so.rec_start);
     a.rec_epb = (uint32_t *)(s + so.rec_epb);
@@ -1009,18 +870,26 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     a.nal_hdr = (uint32_t *)(s + so.nal_hdr);
     a.nal_cap = nal_cap;
     a.n_chunks = (uint32_t)n_chunks;
-    a.n_pieces = (uint32_t)n_pieces;
-    a.span_chunks = (uint32_t)span;
 
-    scan_init_kernel<<<1, 1, 0, ctx->stream>>>(a.hdr, n);
-    H264B_LAUNCH_CHECK(ctx, "scan_init_kernel");
-    if (n_pieces) {
-        uint64_t grid = (n_pieces + kWarps - 1) / kWarps;
-        if (grid > max_ctas) grid = max_ctas;
-        main_kernel<<<(int)grid, kWarps * 32, smem, ctx->stream>>>(a);
-        H264B_LAUNCH_CHECK(ctx, "annexb_scan_kernel");
-        piece_order_kernel<<<1, 1024, 0, ctx->stream>>>(a.piece_nsc, a.piece_ord, a.n_pieces);
-        H264B_LAUNCH_CHECK(ctx, "piece_order_kernel");
+    // header + per-chunk (start codes | EPBs) array: all zero
+    H264B_CUDA(ctx, cudaMemsetAsync(s, 0, so.piece + n_chunks * 4, ctx->stream));
+    if (n_chunks) {
+        annexb_copy_kernel<<<(unsigned)((n_chunks + kWarpsA - 1) / kWarpsA), kWarpsA * 32, 0, ctx->stream>>>(a);
+        H264B_LAUNCH_CHECK(ctx, "annexb_copy_kernel");
+        static int occ_b = 0;  // resident CTAs per SM: the kernel walks the list grid-stride, one wave
+        if (!occ_b) {
+            H264B_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, annexb_dirty_kernel, kWarpsB * 32, 0));
+            if (occ_b < 1) occ_b = 1;
+        }
+        uint64_t grid_b = (n_chunks + kWarpsB - 1) / kWarpsB;  // (the list is at most that long)
+        if (grid_b > (uint64_t)ctx->sm_count * occ_b) grid_b = (uint64_t)ctx->sm_count * occ_b;
+        annexb_dirty_kernel<<<(unsigned)grid_b, kWarpsB * 32, 0, ctx->stream>>>(a);
+        H264B_LAUNCH_CHECK(ctx, "annexb_dirty_kernel");
+        const unsigned tiles = (unsigned)((n_chunks + kOrderTile - 1) / kOrderTile);
+        order_reduce_kernel<<<tiles, 256, 0, ctx->stream>>>(a.piece, a.tile_sum, a.n_chunks);
+        H264B_LAUNCH_CHECK(ctx, "order_reduce_kernel");
+        order_apply_kernel<<<tiles, 256, 0, ctx->stream>>>(a.piece, a.tile_sum, a.piece_ord, a.piece_S, a.n_chunks);
+        H264B_LAUNCH_CHECK(ctx, "order_apply_kernel");
         nal_permute_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a);
         H264B_LAUNCH_CHECK(ctx, "nal_permute_kernel");
     }
@@ -1052,7 +921,5 @@ int launch_slice_select(h264b_ctx *ctx, const h264b_nal *d_nals, const h264b_sca
 
 }  // namespace h264b
 
-// upper bound: the smallest pieces (one chunk each); the record arrays are sized by nal_cap on top of this
-extern "C" uint64_t h264b_annexb_scratch_bytes(uint64_t n) {
-    return h264b::scratch_layout((n + h264b::kChunk - 1) / h264b::kChunk, 0).total;
-}
+// (the record arrays are sized by nal_cap on top of this)
+extern "C" uint64_t h264b_annexb_scratch_bytes(uint64_t n) { return h264b::scratch_layout(n, 0).total; }

@@ -177,15 +177,6 @@ int32_t h264b_memcpy_d2h(h264b_ctx *ctx, void *dst, const void *src, size_t byte
     if (bytes) H264B_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return H264B_OK;
 }
-int32_t h264b_set_option(h264b_ctx *ctx, uint32_t option, uint64_t value) {
-    CHECK_CTX(ctx);
-    if (option == H264B_OPT_SCAN_SPAN_CHUNKS) {
-        if (value > (1u << 20)) return set_error(ctx, H264B_E_INVALID, "scan span: at most 2^20 chunks");
-        ctx->scan_span_chunks = (uint32_t)value;
-        return H264B_OK;
-    }
-    return set_error(ctx, H264B_E_INVALID, "unknown option %u", option);
-}
 int32_t h264b_launch_count(const h264b_ctx *ctx, uint64_t *count) {
     if (!ctx || !count) return H264B_E_INVALID;
     *count = ctx->launches;

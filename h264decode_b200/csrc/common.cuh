@@ -18,7 +18,6 @@ struct h264b_ctx {
     // grow-only device scratch
     void *scan_scratch;
     size_t scan_scratch_bytes;
-    uint32_t scan_span_chunks;  // H264B_OPT_SCAN_SPAN_CHUNKS; 0 = automatic
 
     // constant device tables, built once in h264b_create: [0] = REF, [1] = SPEC
     uint64_t *d_cabac_tab[2];   // 128 entries, see cabac_engine.cu

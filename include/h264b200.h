@@ -67,11 +67,6 @@ int32_t h264b_dev_alloc(h264b_ctx *ctx, size_t bytes, void **out);
 int32_t h264b_dev_free(h264b_ctx *ctx, void *p);
 int32_t h264b_memcpy_h2d(h264b_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async on the stream */
 int32_t h264b_memcpy_d2h(h264b_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* async on the stream */
-/* Tuning knobs (never change results).  H264B_OPT_SCAN_SPAN_CHUNKS: 2 KiB chunks per piece of the Annex-B scan
- * (a piece is walked front to back by one warp); 0 = automatic (128 KiB pieces for large streams).  Tests use small
- * values to put piece boundaries everywhere. */
-#define H264B_OPT_SCAN_SPAN_CHUNKS 1u
-int32_t h264b_set_option(h264b_ctx *ctx, uint32_t option, uint64_t value);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int32_t h264b_launch_count(const h264b_ctx *ctx, uint64_t *count);
 

@@ -88,10 +88,12 @@ int64_t emul_stream(const uint8_t *s, int64_t n, uint64_t *nal_start, uint64_t *
 
 uint32_t emul_header_bytes(uint32_t b0, uint32_t b1) { return nal_header_bytes(b0, b1); }
 
-// Piece-by-piece, chunk-by-chunk emulation of annexb_scan_kernel (same phases, same helper functions; the lanes of a
-// warp as loops).  Pieces are visited in a pseudo-random order (order_seed) because the product hands them to warps
-// by atomic ticket; records go to "slots" in visiting order and are permuted into stream order exactly as
-// piece_order_kernel / nal_permute_kernel do.  RBSP bytes of a NAL land at the NAL body's own position in `out`
+// Chunk-by-chunk emulation of annexb_copy_kernel + annexb_dirty_kernel and the post-passes (same phases, same helper
+// functions; the lanes of a warp as loops).  The product treats every 2 KiB chunk as a piece of its own
+// (span_chunks == 1); larger pieces (a carry across the chunks of a piece) are exercised too because the helpers
+// support them.  Pieces are visited in a pseudo-random order (order_seed) because the GPU runs them in any order;
+// records go to "slots" in visiting order and are permuted into stream order exactly as order_*_kernel /
+// nal_permute_kernel do.  RBSP bytes of a NAL land at the NAL body's own position in `out`
 // (position-preserving layout); `out` holds out_shift + n + 64 bytes, pre-filled by the caller so that stray writes
 // are detectable; out_shift (a multiple of 16 in the product) shifts the whole destination to exercise alignment.
 // nal_start / nal_epb / nal_hdr (cap entries) receive the per-start-code index (nal_epb: the NAL's EPB total, as
@@ -130,30 +132,31 @@ int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out_base, int64_
             for (int i = 0; i < kHalo + kChunk + kHalo; i++) buf[i] = (uint8_t)gets(pos - kHalo + i);
             uint8_t *tile_in = buf.data() + kHalo;
             // ---- detect (fast path)
-            uint32_t acc = 0xFFFFFFFFu;
+            // the copy kernel's filter (annexb_copy_kernel): per granule, then the chunk's edges
+            uint32_t need = 0;
             for (int gi = 0; gi < kGran; gi++) {
                 uint32_t w[4], prev;
                 memcpy(w, tile_in + gi * 16, 16);
                 memcpy(&prev, tile_in + gi * 16 - 4, 4);
-                acc = zero_pair_acc(acc, w, prev);
+                need |= granule_needs_general(w, prev);
+                // the cheap part of the filter against its definition
+                bool brute = false;
+                for (int i = -1; i < 16; i++)
+                    brute = brute || (tile_in[gi * 16 + i] == 0 && tile_in[gi * 16 + i - 1] == 0);
+                if (brute != (acc_has_pair(zero_pair_acc(0xFFFFFFFFu, w, prev)) || (prev >> 16) == 0u)) n_filter_mismatch++;
             }
             {
-                uint32_t lo, hi;
+                uint32_t lo, hi, last;
                 memcpy(&lo, buf.data() + 8, 4);
                 memcpy(&hi, buf.data() + 12, 4);
-                acc = zero_pair_acc_tail8(acc, lo, hi);
-            }
-            {   // the filter against its definition: some p in [pos-7, pos+kChunk) with s[p] == 0 && s[p-1] == 0
-                bool brute = false;
-                for (int i = -7; i < kChunk; i++) brute = brute || (tile_in[i] == 0 && tile_in[i - 1] == 0);
-                if (brute != acc_has_pair(acc)) n_filter_mismatch++;
+                memcpy(&last, tile_in + kChunk - 4, 4);
+                if (chunk_edges_need_general(lo, hi, last)) need |= 1u;
             }
             const bool edge = pos == 0 || pos + kChunk + kHalo > n;
-            bool clean = !acc_has_pair(acc) && carry_epb == 0 && !edge;
-            if (clean) {
-                n_fast++;
-            } else {
-                // ---- general path: exact masks
+            const bool filter_clean = need == 0 && !edge;
+            // pieces longer than one chunk (not what the product runs) also carry the open NAL's EPB count along
+            bool clean = filter_clean && carry_epb == 0;
+            {   // ---- general path: exact masks (computed for every chunk here, to hold the filter against them)
                 std::vector<uint32_t> em(kGran), ks(kGran), ee(kGran), incl(kGran);
                 auto masks_at = [&](int gi, bool have_prev) {
                     uint32_t w[4];
@@ -203,7 +206,10 @@ int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out_base, int64_
                 }
                 bool all0 = true;
                 for (int r = 0; r < kRows; r++) all0 = all0 && cls[r] == 0;
-                if (all0 && carry_epb == 0) {
+                if (filter_clean && !all0) n_filter_mismatch++;  // the filter let through a chunk that needs work
+                if (clean) {
+                    n_fast++;  // left to the copy kernel
+                } else if (all0 && carry_epb == 0) {
                     clean = true;
                     n_false_alarm++;
                 } else {
@@ -291,13 +297,23 @@ int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out_base, int64_
             nal_hdr[ord] = rec_hdr[i];
         }
     }
-    // post-pass 3 + 4: NALs that span pieces -- slide their later parts left and total their EPB counts
+    // post-pass 3 + 4: NALs that span pieces -- total their EPB counts, slide their later parts left
+    std::vector<uint32_t> packed((size_t)n_pieces + 1, 0), S((size_t)n_pieces + 1, 0);
+    uint32_t srun = 0;
+    for (int64_t t = 0; t < n_pieces; t++) {
+        packed[t] = (piece_nsc[t] << 16) | (piece_epb[t] & 0xFFFFu);
+        S[t] = srun;
+        srun += piece_epb[t];
+    }
     const int64_t K = Kall < cap ? Kall : cap;
     for (int64_t k = 0; k < K; k++) nal_epb[k] = 0;
     for (int64_t k = 0; k + 1 < K; k++) {
         const uint32_t H = nal_header_bytes(nal_hdr[k] & 0xFF, (nal_hdr[k] >> 8) & 0xFF);
-        nal_epb[k + 1] = nal_pieces(nal_start[k], nal_start[k + 1], H, epb_local[k + 1], piece_epb.data(), piece_bytes,
-                                    [&](uint64_t ps, uint64_t len, uint64_t G) { memmove(out + ps - G, out + ps, len); });
+        uint32_t later;
+        nal_epb[k + 1] = nal_removed(nal_start[k], nal_start[k + 1], epb_local[k + 1], S.data(), piece_bytes, &later);
+        if (later)
+            nal_pieces(nal_start[k], nal_start[k + 1], H, epb_local[k + 1], packed.data(), S.data(), piece_bytes,
+                       [&](uint64_t ps, uint64_t len, uint64_t G) { memmove(out + ps - G, out + ps, len); });
     }
     if (stats) {
         stats[0] = n_fast;

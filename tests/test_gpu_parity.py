@@ -154,27 +154,23 @@ def test_scan_random_streams(ctx, capi, seed):
             check_scan(ctx, capi, random_stream(rng, n, p_zero, p_sc, ext_types=(seed % 2 == 0)))
 
 
-@pytest.mark.parametrize("span", [1, 2, 3, 64])
-def test_scan_piece_sizes(ctx, capi, span):
-    """pieces (the unit one warp walks on its own) of 1, 2, 3 and 64 chunks: NALs that span pieces, EPBs before/after
-    piece boundaries, record ordering when pieces finish out of order"""
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_scan_chunk_boundaries(ctx, capi, seed):
+    """2 KiB chunks are processed independently: NALs that span chunks, EPBs just before / after chunk boundaries,
+    sparse streams where most chunks take the verbatim-copy kernel and a few the general one"""
     from tests.test_hd_logic import random_stream
-    rng = np.random.default_rng(100 + span)
+    rng = np.random.default_rng(100 + seed)
     C = 2048
-    ctx.set_option(capi.OPT_SCAN_SPAN_CHUNKS, span)
-    try:
-        for n in [1, C - 1, C, C + 1, 2 * C + 5, 3 * C - 2, 7 * C + 9, 64 * C, 64 * C + 1, 130 * C + 77, 400 * C + 3]:
-            for p_zero, p_sc in [(0.5, 0.02), (0.2, 0.002), (0.9, 0.0005), (0.02, 0.0001), (0.004, 0.00002)]:
-                check_scan(ctx, capi, random_stream(rng, n, p_zero, p_sc, ext_types=(span % 2 == 0)))
-        sc, hdr = np.array([0, 0, 0, 1], np.uint8), np.array([0x65], np.uint8)
-        body = rng.integers(4, 256, 300000).astype(np.uint8)
-        for at in ([100], [2040, 2047, 2050], [4093], [131070, 131073], [5000, 140000, 290000]):
-            b = body.copy()
-            for p in at:
-                b[p:p + 3] = [0, 0, 3]
-            check_scan(ctx, capi, np.concatenate([sc, hdr, b, sc, hdr, body[:5000], sc]))
-    finally:
-        ctx.set_option(capi.OPT_SCAN_SPAN_CHUNKS, 0)
+    for n in [1, C - 1, C, C + 1, 2 * C + 5, 3 * C - 2, 7 * C + 9, 64 * C, 64 * C + 1, 130 * C + 77, 400 * C + 3]:
+        for p_zero, p_sc in [(0.5, 0.02), (0.2, 0.002), (0.9, 0.0005), (0.02, 0.0001), (0.004, 0.00002)]:
+            check_scan(ctx, capi, random_stream(rng, n, p_zero, p_sc, ext_types=(seed % 2 == 0)))
+    sc, hdr = np.array([0, 0, 0, 1], np.uint8), np.array([0x65], np.uint8)
+    body = rng.integers(4, 256, 300000).astype(np.uint8)
+    for at in ([100], [2040, 2047, 2050], [4093], [131070, 131073], [5000, 140000, 290000]):
+        b = body.copy()
+        for p in at:
+            b[p:p + 3] = [0, 0, 3]
+        check_scan(ctx, capi, np.concatenate([sc, hdr, b, sc, hdr, body[:5000], sc]))
 
 
 @pytest.mark.parametrize("T", [2048, 16384, 131072])

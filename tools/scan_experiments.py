@@ -11,18 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
     "full": [],
-    "loadonly": ["-DH264B_EXP_LOADONLY"],
-    "nostore": ["-DH264B_EXP_NOSTORE"],
-    "nodetect": ["-DH264B_EXP_NODETECT"],
-    "nodetect_nostore": ["-DH264B_EXP_NODETECT", "-DH264B_EXP_NOSTORE"],
-    # launch-shape sweeps (results stay correct): rows per chunk, ring stages, warps per CTA, store / load form
-    "stat": ["-DH264B_SCAN_STATIC"],
-    "stat_w8": ["-DH264B_SCAN_STATIC", "-DH264B_SCAN_WARPS=8"],
-    "ldg": ["-DH264B_SCAN_LDG"],
-    "ldg_stat": ["-DH264B_SCAN_LDG", "-DH264B_SCAN_STATIC"],
-    "ldg_stat_w8": ["-DH264B_SCAN_LDG", "-DH264B_SCAN_STATIC", "-DH264B_SCAN_WARPS=8"],
-    "ldg_stat_r2": ["-DH264B_SCAN_LDG", "-DH264B_SCAN_STATIC", "-DH264B_SCAN_ROWS=2"],
-    "ldg_stat_nostore": ["-DH264B_SCAN_LDG", "-DH264B_SCAN_STATIC", "-DH264B_EXP_NOSTORE"],
+    "nostore": ["-DH264B_EXP_NOSTORE"],     # K1a only reads and detects
+    "nodetect": ["-DH264B_EXP_NODETECT"],   # K1a is a plain copy (only the edge chunks are flagged)
+    "w4": ["-DH264B_SCAN_WARPS=4"],
+    "w16": ["-DH264B_SCAN_WARPS=16"],
+    "r2": ["-DH264B_SCAN_ROWS=2"],
+    "r8": ["-DH264B_SCAN_ROWS=8"],
 }
 OUTDIR = os.path.join(ROOT, "h264decode_b200", "exp")
 
@@ -76,9 +70,7 @@ def run(frames=4000):
         h = C.c_void_p()
         assert L.h264b_create(0, C.byref(h)) == 0
         L.h264b_set_stream(h, C.c_void_p(stream.cuda_stream))
-        L.h264b_set_option.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
         for span in spans:
-          L.h264b_set_option(h, 1, span)
           d_rbsp.zero_()
           ts = []
           for it in range(12):
