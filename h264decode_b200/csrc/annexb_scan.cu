@@ -70,18 +70,16 @@ struct ScanArgs {
     uint32_t *piece_S;         // per chunk: exclusive scan of the EPB fields (see nal_pieces)
     uint2 *tile_sum;           // per kOrderTile chunks: (start codes, EPB fields): first phase of those scans
     uint32_t *fix_list;        // NAL ordinals whose later parts must slide left (written by scan_finalize_kernel)
-    // per start code, in slot order (chunks reserve slots with one atomicAdd): written by the dirty-chunk kernel
-    unsigned long long *rec_start;
-    uint32_t *rec_epb;
-    uint32_t *rec_hdr;
-    uint32_t *rec_rank;        // rank of the start code inside its chunk
-    // the same in stream order (written by nal_permute_kernel, read by scan_finalize_kernel)
-    unsigned long long *nal_start;
-    uint32_t *nal_epb;         // [k]: EPBs removed (within the chunk of start code k) from the NAL that ends there
-    uint32_t *nal_hdr;
+    // One 16-byte record per start code: .x/.y = offset of the byte after it (the next NAL's first byte), .z = that
+    // NAL's first 4 bytes, .w = EPBs removed (within the start code's chunk) from the NAL that ENDS at this start code
+    // | rank of the start code inside its chunk << 16.
+    uint4 *rec;                // in slot order (chunks reserve slots with one atomicAdd): written by the dirty-chunk kernel
+    uint4 *nal_rec;            // in stream order (written by nal_permute_kernel, read by scan_finalize_kernel)
     uint32_t nal_cap;
     uint32_t n_chunks;
 };
+
+__device__ __forceinline__ uint64_t rec_start(const uint4 &r) { return (uint64_t)r.x | ((uint64_t)r.y << 32); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -139,10 +137,10 @@ __global__ void __launch_bounds__(kWarpsA * 32) annexb_copy_kernel(ScanArgs a) {
 
 // ------------------------------------------------------------------------------------------------ K1b: dirty chunks
 struct __align__(16) WarpStage {
-    uint8_t buf[kSlotBytes];              // [0,16) low halo, [16,16+kChunk) chunk, high halo
-    unsigned long long mbar;              // "bytes have landed"
+    uint8_t buf[2][kSlotBytes];           // double buffer; each: [0,16) low halo, [16,16+kChunk) chunk, high halo
+    unsigned long long mbar[2];           // "bytes have landed"
     uint16_t scbits[kChunkGran + 2];      // start-code-end bits per granule, [0] = halo granule before the chunk
-    uint16_t pad[(8 - (kChunkGran + 2 + 4) % 8) % 8];
+    uint16_t pad[(8 - (kChunkGran + 2) % 8) % 8];
 };
 static_assert(sizeof(WarpStage) % 16 == 0 && kSlotBytes % 16 == 0, "staging buffers must stay 16-byte aligned");
 
@@ -193,12 +191,19 @@ __device__ __noinline__ void compact_row_in_place(uint8_t *row, const uint8_t *s
 }
 
 // one lane's granule of a row with NAL boundaries: kept bytes one by one, one record per start-code end
-//   c     EPBs removed so far (in this piece) from the NAL open at the granule's first byte
-//   k     record slot of the first start code of the granule;  rank: its rank inside the piece
-__device__ __noinline__ void store_boundary_granule(const ScanArgs &a, uint64_t gpos, const uint8_t *src, uint32_t k16,
-                                                    uint32_t ee, uint32_t sc, uint64_t c, uint64_t k, uint32_t rank,
-                                                    bool first_of_chunk) {
-    const uint4 v = *reinterpret_cast<const uint4 *>(src);
+//   c     EPBs removed so far (in this chunk) from the NAL open at the granule's first byte
+//   k     record slot of the first start code of the granule;  rank: its rank inside the chunk
+// tile_in is the staged chunk (tile_in[i] = s[pos + i]); the row has not been compacted, and neither has any byte a
+// NAL header can reach (header bytes are dropped bytes: their rows are never "EPB-only")
+__device__ __noinline__ void store_boundary_granule(const ScanArgs &a, const uint8_t *tile_in, uint64_t pos, int gi,
+                                                    uint32_t k16, uint32_t ee, uint32_t sc, uint64_t c, uint64_t k,
+                                                    uint32_t rank, bool first_of_chunk) {
+    const uint64_t gpos = pos + (uint64_t)gi * 16;
+    const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
+    if (k16 == 0xFFFFu && sc == 0 && ((gpos - c) & 15u) == 0) {  // an ordinary granule of such a row (ee is 0 then)
+        *reinterpret_cast<uint4 *>(a.out + gpos - c) = v;
+        return;
+    }
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     store_granule_bytes(a.out, gpos, w, k16, ee, sc, c, [&](int j, uint64_t c_end) {
         const uint64_t st = gpos + (uint64_t)j + 1;  // the new NAL's first byte
@@ -207,13 +212,9 @@ __device__ __noinline__ void store_boundary_granule(const ScanArgs &a, uint64_t 
             first_of_chunk = false;
         }
         if (k < a.nal_cap) {
-            a.rec_start[k] = st;
-            a.rec_epb[k] = (uint32_t)c_end;  // EPBs removed (in this piece) from the NAL that ends with this start code
-            uint32_t h = 0;                  // its first 4 bytes, from the (L2-resident) input
-#pragma unroll
-            for (int q = 0; q < 4; q++) h |= (uint32_t)(st + q < a.n ? a.in[st + q] : (uint8_t)0xFF) << (8 * q);
-            a.rec_hdr[k] = h;
-            a.rec_rank[k] = rank;
+            const uint8_t *hb = tile_in + gi * 16 + j + 1;  // its first 4 bytes (0xFF past the end of the stream)
+            const uint32_t h = (uint32_t)hb[0] | ((uint32_t)hb[1] << 8) | ((uint32_t)hb[2] << 16) | ((uint32_t)hb[3] << 24);
+            a.rec[k] = make_uint4((uint32_t)st, (uint32_t)(st >> 32), h, (uint32_t)c_end | (rank << 16));
         }
         k++;
         rank++;
@@ -279,6 +280,14 @@ __device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, uint16_t *s
         const uint32_t prev = lane ? *reinterpret_cast<const uint32_t *>(tile_in + gi * 16 - 4) : 0xFFFFFFFFu;
         scbits[gi + 1] = (uint16_t)granule_masks(w, prev).sc;
     }
+    // Record slots for the chunk's start codes: the atomic is issued now, its result is only needed by the stores
+    // below.  (Bytes past the end of the stream are 0xFF in the slot, so no start code is counted there.)
+    uint32_t n_sc_raw = 0;
+#pragma unroll
+    for (int r = 0; r < kRows; r++) n_sc_raw += bits_popc(em[r] >> 16);
+    n_sc_raw = __reduce_add_sync(0xFFFFFFFFu, n_sc_raw);
+    unsigned long long slot0 = 0;
+    if (n_sc_raw && lane == 0) slot0 = atomicAdd(&a.hdr->total_sc, (unsigned long long)n_sc_raw);
     __syncwarp();
 
     // ---------------------------------------------------------------- adjust + classify + per-row segmented scan
@@ -337,12 +346,23 @@ __device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, uint16_t *s
         return res;
     }
     const uint32_t total = rp[kRows];
-    const uint32_t n_sc = (total >> 16) & 0x1FFFu;
-    unsigned long long slot0 = 0;
-    if (n_sc) {
-        if (lane == 0) slot0 = atomicAdd(&a.hdr->total_sc, (unsigned long long)n_sc);
-        slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+    const uint32_t n_sc = (total >> 16) & 0x1FFFu;  // == n_sc_raw
+
+    // ---------------------------------------------------------------- rows with boundaries: bytes + NAL records
+    if (n_sc) slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+        if (((cls >> (2 * r)) & 3u) != 2u) continue;  // warp-uniform
+        const int gi = r * 32 + lane;
+        uint32_t ex = __shfl_up_sync(0xFFFFFFFFu, incl[r], 1);
+        if (lane == 0) ex = 0;
+        const uint32_t pre = seg_combine(rp[r], ex);
+        const uint64_t c = seg_apply(pre, carry_epb);
+        const uint32_t before = (pre >> 16) & 0x1FFFu;  // start codes of the chunk before this granule
+        store_boundary_granule(a, tile_in, pos, gi, ks[r] & 0xFFFFu, ee[r], ks[r] >> 16, c, slot0 + before,
+                               piece_nsc + before, before == 0);
     }
+    __syncwarp();
 
     // ---------------------------------------------------------------- in-place compaction of EPB-only rows
     // inside their own 512-byte span of the slot: afterwards they are `len` contiguous bytes like untouched rows
@@ -355,32 +375,23 @@ __device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, uint16_t *s
     }
     __syncwarp();
 
-    // ---------------------------------------------------------------- store rows + NAL records
+    // ---------------------------------------------------------------- the other rows: shuffle-aligned 16-byte stores
 #pragma unroll
     for (int r = 0; r < kRows; r++) {
         const int gi = r * 32 + lane;
         const uint32_t c2 = (cls >> (2 * r)) & 3u;
-        if (c2 != 2u) {
-            // one contiguous run of len bytes, shifted left by the EPBs removed from its NAL so far in this piece
-            const uint64_t c_row = seg_apply(rp[r], carry_epb);
-            const uint32_t removed = c2 ? ((rp[r + 1] - rp[r]) & 0x7FFFu) : 0u;
-            const uint64_t o = pos + 512u * (uint32_t)r - c_row;
-            const uint8_t *prev_tail = nullptr;
-            if (r > 0 && ((cls >> (2 * r - 2)) & 3u) != 2u) {
-                const uint32_t prev_removed = (rp[r] - rp[r - 1]) & 0x7FFFu;
-                prev_tail = tile_in + 512 * r - prev_removed;
-            }
-            const bool next_joins = r < kRows - 1 && ((cls >> (2 * r + 2)) & 3u) != 2u;
-            store_row(a.out, o, 512u - removed, tile_in + gi * 16, lane, prev_tail, next_joins);
-        } else {
-            uint32_t ex = __shfl_up_sync(0xFFFFFFFFu, incl[r], 1);
-            if (lane == 0) ex = 0;
-            const uint32_t pre = seg_combine(rp[r], ex);
-            const uint64_t c = seg_apply(pre, carry_epb);
-            const uint32_t before = (pre >> 16) & 0x1FFFu;  // start codes of the chunk before this granule
-            store_boundary_granule(a, pos + (uint64_t)gi * 16, tile_in + gi * 16, ks[r] & 0xFFFFu, ee[r], ks[r] >> 16, c,
-                                   slot0 + before, piece_nsc + before, before == 0);
+        if (c2 == 2u) continue;
+        // one contiguous run of len bytes, shifted left by the EPBs removed from its NAL so far in this chunk
+        const uint64_t c_row = seg_apply(rp[r], carry_epb);
+        const uint32_t removed = c2 ? ((rp[r + 1] - rp[r]) & 0x7FFFu) : 0u;
+        const uint64_t o = pos + 512u * (uint32_t)r - c_row;
+        const uint8_t *prev_tail = nullptr;
+        if (r > 0 && ((cls >> (2 * r - 2)) & 3u) != 2u) {
+            const uint32_t prev_removed = (rp[r] - rp[r - 1]) & 0x7FFFu;
+            prev_tail = tile_in + 512 * r - prev_removed;
         }
+        const bool next_joins = r < kRows - 1 && ((cls >> (2 * r + 2)) & 3u) != 2u;
+        store_row(a.out, o, 512u - removed, tile_in + gi * 16, lane, prev_tail, next_joins);
     }
     res.carry_epb = seg_apply(total, carry_epb);
     res.piece_nsc = piece_nsc + n_sc;
@@ -389,46 +400,57 @@ __device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, uint16_t *s
     return res;
 }
 
-// One warp per listed chunk (grid-stride over the list): the TMA stages the chunk, the whole warp walks it.
+// One warp per listed chunk (grid-stride over the list): the TMA stages the chunk (the next one is already on its way
+// while this one is walked), the whole warp walks it.
 __global__ void __launch_bounds__(kWarpsB * 32) annexb_dirty_kernel(ScanArgs a) {
     __shared__ WarpStage stage[kWarpsB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpStage &st = stage[warp];
-    const uint32_t bar = smem_u32(&st.mbar);
     if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&st.mbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&st.mbar[1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
     const uint32_t n_dirty = a.hdr->n_dirty;
     const uint64_t n16 = (a.n + 15) & ~15ull;
-    uint32_t parity = 0;
-    for (uint32_t i = blockIdx.x * kWarpsB + (uint32_t)warp; i < n_dirty; i += gridDim.x * kWarpsB) {
-        const uint32_t chunk = a.dirty_list[i];
+    const uint32_t stride = gridDim.x * kWarpsB;
+    auto stage_chunk = [&](uint32_t chunk, int b) {  // lane 0: TMA bulk load of the chunk and its halos, clipped to the stream
         const uint64_t pos = (uint64_t)chunk * kChunk;
-        if (lane == 0) {  // TMA bulk load of the chunk and its halos, clipped to the stream
-            const uint64_t lo = pos ? pos - kHalo : 0;
-            uint64_t hi = pos + kChunk + kHalo;
-            if (hi > n16) hi = n16;
-            const uint32_t bytes = (uint32_t)(hi - lo);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-            asm volatile(
-                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                    smem_u32(st.buf + (lo + kHalo - pos))),
-                "l"(a.in + lo), "r"(bytes), "r"(bar)
-                : "memory");
-        }
-        mbar_wait(bar, parity);
-        parity ^= 1u;
-        const ChunkResult res = general_chunk(a, st.scbits, st.buf, pos, 0u, 0u, lane);
+        const uint64_t lo = pos ? pos - kHalo : 0;
+        uint64_t hi = pos + kChunk + kHalo;
+        if (hi > n16) hi = n16;
+        const uint32_t bytes = (uint32_t)(hi - lo), bar = smem_u32(&st.mbar[b]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(st.buf[b] + (lo + kHalo - pos))),
+            "l"(a.in + lo), "r"(bytes), "r"(bar)
+            : "memory");
+    };
+    uint32_t i = blockIdx.x * kWarpsB + (uint32_t)warp;
+    if (i >= n_dirty) return;
+    uint32_t chunk = a.dirty_list[i];
+    uint32_t chunk_next = i + stride < n_dirty ? a.dirty_list[i + stride] : 0u;
+    if (lane == 0) stage_chunk(chunk, 0);
+    uint32_t parity = 0;  // bit b: phase parity of buffer b's barrier
+    for (int b = 0; i < n_dirty; i += stride, b ^= 1) {
+        const uint32_t chunk_after = i + 2 * stride < n_dirty ? a.dirty_list[i + 2 * stride] : 0u;  // two ahead
+        if (lane == 0 && i + stride < n_dirty) stage_chunk(chunk_next, b ^ 1);
+        mbar_wait(smem_u32(&st.mbar[b]), (parity >> b) & 1u);
+        parity ^= 1u << b;
+        const uint64_t pos = (uint64_t)chunk * kChunk;
+        const ChunkResult res = general_chunk(a, st.scbits, st.buf[b], pos, 0u, 0u, lane);
         if (res.clean) {  // a false alarm (00 00 03 whose zeros are header bytes, ...): the verbatim copy after all
 #pragma unroll
             for (int r = 0; r < kRows; r++)
                 *reinterpret_cast<uint4 *>(a.out + pos + (uint32_t)(r * 32 + lane) * 16u) =
-                    *reinterpret_cast<const uint4 *>(st.buf + kHalo + (r * 32 + lane) * 16);
+                    *reinterpret_cast<const uint4 *>(st.buf[b] + kHalo + (r * 32 + lane) * 16);
         }
         if (lane == 0) a.piece[chunk] = (res.piece_nsc << 16) | res.carry_epb;
-        __syncwarp();  // every lane is done with the staging buffer before the next bulk load lands in it
+        __syncwarp();  // every lane is done with this buffer before (next iteration) a bulk load is aimed at it
+        chunk = chunk_next;
+        chunk_next = chunk_after;
     }
 }
 
@@ -572,13 +594,9 @@ __global__ void __launch_bounds__(256) nal_permute_kernel(ScanArgs a) {
     uint64_t K = a.hdr->total_sc;
     if (K > cap) K = cap;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < K; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t st = a.rec_start[i];
-        const uint64_t ord = (uint64_t)a.piece_ord[(st - 1) / kChunk] + a.rec_rank[i];
-        if (ord < cap) {
-            a.nal_start[ord] = st;
-            a.nal_epb[ord] = a.rec_epb[i];
-            a.nal_hdr[ord] = a.rec_hdr[i];
-        }
+        const uint4 r = a.rec[i];
+        const uint64_t ord = (uint64_t)a.piece_ord[(rec_start(r) - 1) / kChunk] + (r.w >> 16);
+        if (ord < cap) a.nal_rec[ord] = r;
     }
 }
 
@@ -594,12 +612,13 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(ScanArgs a, h264b_na
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < lim;
          k += (uint64_t)gridDim.x * blockDim.x) {
         h264b_nal o;
-        o.start = a.nal_start[k];
-        const uint64_t next = a.nal_start[k + 1];
+        const uint4 r0 = a.nal_rec[k], r1 = a.nal_rec[k + 1];
+        o.start = rec_start(r0);
+        const uint64_t next = rec_start(r1);
         o.num_bytes = (uint32_t)(next - o.start);
-        decode_nal_header(a.nal_hdr[k], o, ext ? &ext[k] : nullptr);
+        decode_nal_header(r0.z, o, ext ? &ext[k] : nullptr);
         uint32_t later_shift;
-        const uint64_t removed = nal_removed(o.start, next, a.nal_epb[k + 1], a.piece_S, (uint64_t)kChunk, &later_shift);
+        const uint64_t removed = nal_removed(o.start, next, r1.w & 0xFFFFu, a.piece_S, (uint64_t)kChunk, &later_shift);
         if (later_shift) a.fix_list[atomicAdd(&a.hdr->n_fix, 1u)] = (uint32_t)k;
         // body = NumBytes - HeaderBytes - 2 bytes (a NAL shorter than that has no body); its RBSP sits at the body's
         // own position in the output buffer
@@ -681,10 +700,10 @@ __global__ void __launch_bounds__(256) nal_fixup_kernel(ScanArgs a, h264b_scan_s
     }
     for (uint32_t f = blockIdx.x; f < n_fix; f += gridDim.x) {
         const uint64_t k = a.fix_list[f];
-        const uint64_t st = a.nal_start[k], next = a.nal_start[k + 1];
-        h264b_nal o;
-        decode_nal_header(a.nal_hdr[k], o, nullptr);
-        nal_pieces(st, next, o.header_bytes, a.nal_epb[k + 1], a.piece, a.piece_S, (uint64_t)kChunk,
+        const uint4 r0 = a.nal_rec[k], r1 = a.nal_rec[k + 1];
+        const uint64_t st = rec_start(r0), next = rec_start(r1);
+        nal_pieces(st, next, nal_header_bytes(r0.z & 0xFFu, (r0.z >> 8) & 0xFFu), r1.w & 0xFFFFu, a.piece, a.piece_S,
+                   (uint64_t)kChunk,
                    [&](uint64_t ps, uint64_t len, uint64_t G) { move_left(a.out, ps, len, G); });
     }
 }
@@ -802,8 +821,7 @@ __global__ void __launch_bounds__(1024) slice_select_kernel(const h264b_nal *nal
 
 // ------------------------------------------------------------------------------------------------ launchers
 struct ScratchOffsets {
-    uint64_t piece, dirty_list, piece_ord, piece_S, tile_sum, fix_list, rec_start, rec_epb, rec_hdr, rec_rank, nal_start,
-        nal_epb, nal_hdr, total;
+    uint64_t piece, dirty_list, piece_ord, piece_S, tile_sum, fix_list, rec, nal_rec, total;
 };
 static ScratchOffsets scratch_layout(uint64_t n, uint32_t nal_cap) {
     const uint64_t n_chunks = (n + kChunk - 1) / kChunk;
@@ -820,13 +838,8 @@ static ScratchOffsets scratch_layout(uint64_t n, uint32_t nal_cap) {
     o.piece_S = take(n_chunks * 4);
     o.tile_sum = take((n_chunks + kOrderTile - 1) / kOrderTile * 8);
     o.fix_list = take((uint64_t)nal_cap * 4);
-    o.rec_start = take((uint64_t)nal_cap * 8);
-    o.rec_epb = take((uint64_t)nal_cap * 4);
-    o.rec_hdr = take((uint64_t)nal_cap * 4);
-    o.rec_rank = take((uint64_t)nal_cap * 4);
-    o.nal_start = take((uint64_t)nal_cap * 8);
-    o.nal_epb = take((uint64_t)nal_cap * 4);
-    o.nal_hdr = take((uint64_t)nal_cap * 4);
+    o.rec = take((uint64_t)nal_cap * 16);
+    o.nal_rec = take((uint64_t)nal_cap * 16);
     o.total = (p + 255) & ~255ull;
     return o;
 }
@@ -861,13 +874,8 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     a.piece_S = (uint32_t *)(s + so.piece_S);
     a.tile_sum = (uint2 *)(s + so.tile_sum);
     a.fix_list = (uint32_t *)(s + so.fix_list);
-    a.rec_start = (unsigned long long *)(s + so.rec_start);
-    a.rec_epb = (uint32_t *)(s + so.rec_epb);
-    a.rec_hdr = (uint32_t *)(s + so.rec_hdr);
-    a.rec_rank = (uint32_t *)(s + so.rec_rank);
-    a.nal_start = (unsigned long long *)(s + so.nal_start);
-    a.nal_epb = (uint32_t *)(s + so.nal_epb);
-    a.nal_hdr = (uint32_t *)(s + so.nal_hdr);
+    a.rec = (uint4 *)(s + so.rec);
+    a.nal_rec = (uint4 *)(s + so.nal_rec);
     a.nal_cap = nal_cap;
     a.n_chunks = (uint32_t)n_chunks;
 

@@ -221,6 +221,38 @@ int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out_base, int64_
                     rec_epb.resize(slot0 + n_sc, 0);
                     rec_hdr.resize(slot0 + n_sc, 0);
                     rec_rank.resize(slot0 + n_sc, 0);
+                    // rows with boundaries first (bytes + records; header bytes come from the not yet compacted tile)
+                    for (int r = 0; r < kRows; r++) {
+                        if (cls[r] != 2) continue;
+                        for (int lane = 0; lane < 32; lane++) {
+                            const int gi = r * 32 + lane;
+                            uint32_t w[4];
+                            memcpy(w, tile_in + gi * 16, 16);
+                            const uint32_t ex = lane ? incl[gi - 1] : 0u;
+                            const uint32_t pre = seg_combine(rp[r], ex);
+                            const uint64_t c = seg_apply(pre, carry_epb);
+                            const uint32_t before = (pre >> 16) & 0x1FFFu;
+                            const uint64_t gpos = (uint64_t)pos + (uint64_t)gi * 16;
+                            const uint32_t k16 = ks[gi] & 0xFFFFu, sc = ks[gi] >> 16;
+                            if (k16 == 0xFFFFu && sc == 0 && ((gpos - c) & 15u) == 0) {  // ordinary granule of such a row
+                                memcpy(out + gpos - c, w, 16);
+                                continue;
+                            }
+                            uint64_t k = slot0 + before;
+                            uint32_t rank = pnsc + before;
+                            store_granule_bytes(out, gpos, w, k16, ee[gi], sc, c, [&](int j, uint64_t c_end2) {
+                                const uint64_t st = gpos + j + 1;
+                                const uint8_t *hb = tile_in + gi * 16 + j + 1;
+                                rec_start[k] = st;
+                                rec_epb[k] = (uint32_t)c_end2;
+                                rec_hdr[k] = (uint32_t)hb[0] | ((uint32_t)hb[1] << 8) | ((uint32_t)hb[2] << 16) |
+                                             ((uint32_t)hb[3] << 24);
+                                rec_rank[k] = rank;
+                                k++;
+                                rank++;
+                            });
+                        }
+                    }
                     // in-place compaction of EPB-only rows
                     for (int r = 0; r < kRows; r++) {
                         if (cls[r] != 1) continue;
@@ -235,42 +267,19 @@ int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out_base, int64_
                                 if (k16 & (1u << j)) row[loff++] = (uint8_t)(w[lane][j >> 2] >> ((j & 3) * 8));
                         }
                     }
+                    // the other rows
                     for (int r = 0; r < kRows; r++) {
+                        if (cls[r] == 2) continue;
                         uint32_t w[32][4];
                         for (int lane = 0; lane < 32; lane++) memcpy(w[lane], tile_in + (512 * r + lane * 16), 16);
-                        if (cls[r] != 2) {
-                            const uint64_t c_row = seg_apply(rp[r], carry_epb);
-                            const uint32_t removed = cls[r] ? ((rp[r + 1] - rp[r]) & 0x7FFFu) : 0u;
-                            const uint64_t o = (uint64_t)pos + 512u * r - c_row;
-                            const uint8_t *prev_tail = nullptr;
-                            if (r > 0 && cls[r - 1] != 2) prev_tail = tile_in + 512 * r - ((rp[r] - rp[r - 1]) & 0x7FFFu);
-                            const bool next_joins = r < kRows - 1 && cls[r + 1] != 2;
-                            for (int lane = 0; lane < 32; lane++)
-                                store_row_lane(out, o, 512u - removed, lane ? w[lane - 1] : w[0], w[lane], lane, prev_tail, next_joins);
-                        } else {
-                            for (int lane = 0; lane < 32; lane++) {
-                                const int gi = r * 32 + lane;
-                                const uint32_t ex = lane ? incl[gi - 1] : 0u;
-                                const uint32_t pre = seg_combine(rp[r], ex);
-                                const uint64_t c = seg_apply(pre, carry_epb);
-                                const uint32_t before = (pre >> 16) & 0x1FFFu;
-                                const uint64_t gpos = (uint64_t)pos + (uint64_t)gi * 16;
-                                uint64_t k = slot0 + before;
-                                uint32_t rank = pnsc + before;
-                                store_granule_bytes(out, gpos, w[lane], ks[gi] & 0xFFFFu, ee[gi], ks[gi] >> 16, c,
-                                                    [&](int j, uint64_t c_end2) {
-                                                        const uint64_t st = gpos + j + 1;
-                                                        rec_start[k] = st;
-                                                        rec_epb[k] = (uint32_t)c_end2;
-                                                        uint32_t h = 0;
-                                                        for (int q = 0; q < 4; q++) h |= gets((int64_t)st + q) << (8 * q);
-                                                        rec_hdr[k] = h;
-                                                        rec_rank[k] = rank;
-                                                        k++;
-                                                        rank++;
-                                                    });
-                            }
-                        }
+                        const uint64_t c_row = seg_apply(rp[r], carry_epb);
+                        const uint32_t removed = cls[r] ? ((rp[r + 1] - rp[r]) & 0x7FFFu) : 0u;
+                        const uint64_t o = (uint64_t)pos + 512u * r - c_row;
+                        const uint8_t *prev_tail = nullptr;
+                        if (r > 0 && cls[r - 1] != 2) prev_tail = tile_in + 512 * r - ((rp[r] - rp[r - 1]) & 0x7FFFu);
+                        const bool next_joins = r < kRows - 1 && cls[r + 1] != 2;
+                        for (int lane = 0; lane < 32; lane++)
+                            store_row_lane(out, o, 512u - removed, lane ? w[lane - 1] : w[0], w[lane], lane, prev_tail, next_joins);
                     }
                     carry_epb = seg_apply(total, carry_epb);
                     pnsc += n_sc;
