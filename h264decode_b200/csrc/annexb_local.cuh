@@ -160,19 +160,16 @@ H264B_HD uint32_t zero_pair_acc_tail8(uint32_t acc, uint32_t lo, uint32_t hi) {
 }
 H264B_HD bool acc_has_pair(uint32_t acc) { return (acc & 0xFFFFu) == 0u || (acc >> 16) == 0u; }
 
-// Two-level filter of the copy kernel, per granule: non-zero iff the granule holds an emulation-prevention candidate
-// or a start-code end.  Either needs two zero bytes right before it, i.e. a pair ending at g-1 .. g+14: the cheap test
-// looks for pairs ending at g-1 (the last two bytes of prev) .. g+15, and only then are the exact masks evaluated.
-H264B_HD uint32_t granule_needs_general(const uint32_t w[4], uint32_t prev) {
-    if (!acc_has_pair(zero_pair_acc(0xFFFFFFFFu, w, prev)) && (prev >> 16) != 0u) return 0u;
-    const GranuleMasks m = granule_masks(w, prev);
-    return m.e | m.sc;
-}
-// ... and per chunk, for what lies outside it: a start code ending in the last bytes before the chunk reaches into it
-// (header bytes, EPB guard) and one ending right behind the chunk takes the chunk's last byte (the 2-byte tail rule);
-// both need zero pairs at the edges.  t8_lo/t8_hi: the 8 bytes before the chunk; last_word: its last 4 bytes.
-H264B_HD bool chunk_edges_need_general(uint32_t t8_lo, uint32_t t8_hi, uint32_t last_word) {
-    return acc_has_pair(zero_pair_acc_tail8(0xFFFFFFFFu, t8_lo, t8_hi)) || (last_word >> 16) == 0u;
+// Two-level filter of the copy kernel, per granule: the exact masks, but computed only when the cheap test fires.
+// An emulation-prevention candidate or a start-code end at p needs two zero bytes right before it, i.e. a pair ending
+// at g-1 .. g+14: the cheap test looks for pairs ending at g-1 (the last two bytes of prev) .. g+15.
+H264B_HD GranuleMasks granule_masks_filtered(const uint32_t w[4], uint32_t prev) {
+    if (!acc_has_pair(zero_pair_acc(0xFFFFFFFFu, w, prev)) && (prev >> 16) != 0u) {
+        GranuleMasks m;
+        m.z = m.e = m.sc = 0;
+        return m;
+    }
+    return granule_masks(w, prev);
 }
 
 // keep mask of a granule at stream position gpos when start codes end within [gpos-6, gpos+16], in the bit domain
@@ -374,30 +371,48 @@ H264B_HD uint64_t nal_removed(uint64_t a, uint64_t b, uint64_t end_local, const 
 }
 // move(start, len, G) is called, in stream order, for every run of later parts that has to slide left by G > 0
 // (parts that lost nothing themselves are contiguous with their successor and share its G: they move as one run).
+// The walk may be cut into windows of parts [t_begin, t_end) (the GPU stages tail[] / S[] of a window in shared memory:
+// both are indexed [t - t0]); `run` carries the open run from one window to the next, nal_pieces_flush ends the walk.
+struct MoveRun {
+    uint64_t ps, len, G;
+};
 template <class Move>
-H264B_HD void nal_pieces(uint64_t a, uint64_t b, uint32_t H, uint64_t end_local, const uint32_t *tail, const uint32_t *S,
-                         uint64_t piece_bytes, const Move &move) {
-    const uint64_t Tq = (a - 1) / piece_bytes, Tb = (b - 1) / piece_bytes;
-    uint64_t run_ps = 0, run_len = 0, run_G = 0;
-    for (uint64_t t = Tq + 1; t <= Tb; t++) {
-        const uint64_t G = S[t] - S[Tq];
+H264B_HD void nal_pieces_window(uint64_t a, uint64_t b, uint32_t H, uint64_t end_local, const uint32_t *tail,
+                                const uint32_t *S, uint64_t t0, uint32_t S_Tq, uint64_t piece_bytes, uint64_t t_begin,
+                                uint64_t t_end, MoveRun &run, const Move &move) {
+    const uint64_t Tb = (b - 1) / piece_bytes;
+    for (uint64_t t = t_begin; t < t_end; t++) {
+        const uint64_t G = (uint32_t)(S[t - t0] - S_Tq);
         if (!G) continue;
         const uint64_t lo = t * piece_bytes, body = a + H;
         const uint64_t ps = lo > body ? lo : body;                    // first kept byte of the part
         const uint64_t pe = t < Tb ? (t + 1) * piece_bytes : b - 2;   // kept bytes are < pe (b-2, b-1: the tail rule)
-        const uint64_t e = t < Tb ? (uint64_t)(tail[t] & 0xFFFFu) : end_local;
+        const uint64_t e = t < Tb ? (uint64_t)(tail[t - t0] & 0xFFFFu) : end_local;
         if (!(pe > ps && pe - ps > e)) continue;
         const uint64_t len = pe - ps - e;
-        if (run_len && G == run_G && ps == run_ps + run_len) {
-            run_len += len;
+        if (run.len && G == run.G && ps == run.ps + run.len) {
+            run.len += len;
         } else {
-            if (run_len) move(run_ps, run_len, run_G);
-            run_ps = ps;
-            run_len = len;
-            run_G = G;
+            if (run.len) move(run.ps, run.len, run.G);
+            run.ps = ps;
+            run.len = len;
+            run.G = G;
         }
     }
-    if (run_len) move(run_ps, run_len, run_G);
+}
+template <class Move>
+H264B_HD void nal_pieces_flush(MoveRun &run, const Move &move) {
+    if (run.len) move(run.ps, run.len, run.G);
+    run.len = 0;
+}
+// the whole walk in one go (tail[] / S[] indexed by chunk)
+template <class Move>
+H264B_HD void nal_pieces(uint64_t a, uint64_t b, uint32_t H, uint64_t end_local, const uint32_t *tail, const uint32_t *S,
+                         uint64_t piece_bytes, const Move &move) {
+    const uint64_t Tq = (a - 1) / piece_bytes, Tb = (b - 1) / piece_bytes;
+    MoveRun run = {0, 0, 0};
+    nal_pieces_window(a, b, H, end_local, tail, S, 0, S[Tq], piece_bytes, Tq + 1, Tb + 1, run, move);
+    nal_pieces_flush(run, move);
 }
 
 }  // namespace h264b

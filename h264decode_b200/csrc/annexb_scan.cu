@@ -84,47 +84,94 @@ __device__ __forceinline__ uint64_t rec_start(const uint4 &r) { return (uint64_t
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ------------------------------------------------------------------------------------------------ K1a: copy + detect
+// NAL records of a chunk that holds start codes but no emulation-prevention candidate (rare path of the copy kernel,
+// kept out of line).  sc[r]: start-code-end mask of this lane's granule in row r.  Such a chunk loses no byte, so every
+// count of removed bytes in its records is zero.
+struct ScMasks {
+    uint32_t m[kRows];
+};
+__device__ __noinline__ void emit_records(const uint8_t *in, ScanScratchHeader *hdr, uint32_t *piece, uint4 *rec,
+                                          uint32_t nal_cap, uint32_t chunk, int lane, ScMasks scm) {
+    const uint32_t *sc = scm.m;
+    const uint64_t pos = (uint64_t)chunk * kChunk;
+    uint32_t before[kRows], total = 0;  // start codes of the chunk before this lane's granule of row r
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+        const uint32_t c = bits_popc(sc[r]);
+        uint32_t x = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if (lane >= d) x += y;
+        }
+        before[r] = total + x - c;
+        total += __shfl_sync(0xFFFFFFFFu, x, 31);
+    }
+    unsigned long long slot0 = 0;
+    if (lane == 0) {
+        slot0 = atomicAdd(&hdr->total_sc, (unsigned long long)total);
+        piece[chunk] = total << 16;
+    }
+    slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+        uint32_t m = sc[r], rank = before[r];
+        while (m) {
+            const int j = __ffs((int)m) - 1;
+            m &= m - 1;
+            const uint64_t st = pos + (uint32_t)(r * 32 + lane) * 16u + (uint32_t)j + 1u;  // the new NAL's first byte
+            if (rank == 0) atomicMax(&hdr->first_inv, ~(unsigned long long)st);
+            if (slot0 + rank < nal_cap) {
+                uint32_t h = 0;  // its first 4 bytes (inside the stream: the chunk is not at its end)
+#pragma unroll
+                for (int q = 0; q < 4; q++) h |= (uint32_t)in[st + q] << (8 * q);
+                rec[slot0 + rank] = make_uint4((uint32_t)st, (uint32_t)(st >> 32), h, rank << 16);
+            }
+            rank++;
+        }
+    }
+}
+
 // One warp per chunk.  Everything a thread needs is its own granules (4 x 16 bytes, all loads in flight at once), the
-// last word of the lane before it (shuffle) and the 8 bytes in front of the chunk (one broadcast load).
+// last word of the lane before it (shuffle) and the 4 bytes in front of the chunk (one broadcast load).
+//   * no emulation-prevention candidate in the chunk (all but one chunk in thousands): nothing moves, the chunk is
+//     stored as it is -- the bytes the reference drops around a start code (its last two bytes, the NAL header) lie
+//     between two RBSPs of the position-preserving layout, where the buffer is unspecified; start codes only add records
+//   * otherwise, and at the two ends of the stream: the chunk is listed for the dirty-chunk kernel
 __global__ void __launch_bounds__(kWarpsA * 32) annexb_copy_kernel(ScanArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t chunk = blockIdx.x * kWarpsA + (uint32_t)warp;
     if (chunk >= a.n_chunks) return;
     const uint64_t pos = (uint64_t)chunk * kChunk;
+    // chunks that touch the ends of the stream always take the general path (it blanks the bytes outside)
+    if (pos == 0 || pos + kChunk + kHalo > a.n) {
+        if (lane == 0) a.dirty_list[atomicAdd(&a.hdr->n_dirty, 1u)] = chunk;
+        return;
+    }
     const uint8_t *src = a.in + pos + lane * 16;
     uint4 v[kRows];
-    uint2 t8 = make_uint2(~0u, ~0u);  // the 8 bytes before the chunk
-    if (pos + kChunk <= a.n) {        // warp-uniform: a whole chunk
 #pragma unroll
-        for (int r = 0; r < kRows; r++) v[r] = __ldcs(reinterpret_cast<const uint4 *>(src + r * 512));
-    } else {
-        const uint64_t n16 = (a.n + 15) & ~15ull;
-#pragma unroll
-        for (int r = 0; r < kRows; r++)
-            v[r] = pos + (uint32_t)(r * 32 + lane) * 16u < n16 ? __ldcs(reinterpret_cast<const uint4 *>(src + r * 512))
-                                                              : make_uint4(~0u, ~0u, ~0u, ~0u);
-    }
-    if (pos) t8 = *reinterpret_cast<const uint2 *>(a.in + pos - 8);
+    for (int r = 0; r < kRows; r++) v[r] = __ldcs(reinterpret_cast<const uint4 *>(src + r * 512));
+    const uint32_t before = *reinterpret_cast<const uint32_t *>(a.in + pos - 4);  // the 4 bytes before the chunk
 
-    // Does the chunk hold anything to remove or to index?  First the cheap filter (two adjacent zero bytes), then,
-    // only in the lanes it fires for, the exact masks.
-    uint32_t need = 0;
-#ifndef H264B_EXP_NODETECT
+    uint32_t any_e = 0, any_sc = 0;
+    ScMasks sc;
 #pragma unroll
     for (int r = 0; r < kRows; r++) {
         uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, v[r].w, 1);
-        const uint32_t wrap = r ? __shfl_sync(0xFFFFFFFFu, v[r ? r - 1 : 0].w, 31) : t8.y;
+        const uint32_t wrap = r ? __shfl_sync(0xFFFFFFFFu, v[r ? r - 1 : 0].w, 31) : before;
         if (lane == 0) prev = wrap;
         const uint32_t w[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
-        need |= granule_needs_general(w, prev);
-    }
-    const uint32_t last_word = __shfl_sync(0xFFFFFFFFu, v[kRows - 1].w, 31);
-    if (chunk_edges_need_general(t8.x, t8.y, last_word)) need |= 1u;
+#ifdef H264B_EXP_NODETECT
+        sc.m[r] = 0;
+#else
+        const GranuleMasks m = granule_masks_filtered(w, prev);
+        any_e |= m.e;
+        sc.m[r] = m.sc;
+        any_sc |= m.sc;
 #endif
-    // chunks that touch the ends of the stream always take the general path (it blanks the bytes outside)
-    const bool edge = pos == 0 || pos + kChunk + kHalo > a.n;
-    const bool dirty = __any_sync(0xFFFFFFFFu, need != 0) || edge;
-    if (dirty) {
+    }
+    if (__any_sync(0xFFFFFFFFu, any_e != 0)) {
         if (lane == 0) a.dirty_list[atomicAdd(&a.hdr->n_dirty, 1u)] = chunk;
         return;
     }
@@ -133,6 +180,7 @@ __global__ void __launch_bounds__(kWarpsA * 32) annexb_copy_kernel(ScanArgs a) {
 #pragma unroll
     for (int r = 0; r < kRows; r++) __stcs(reinterpret_cast<uint4 *>(dst + r * 512), v[r]);
 #endif
+    if (__any_sync(0xFFFFFFFFu, any_sc != 0)) emit_records(a.in, a.hdr, a.piece, a.rec, a.nal_cap, chunk, lane, sc);
 }
 
 // ------------------------------------------------------------------------------------------------ K1b: dirty chunks
@@ -692,7 +740,10 @@ __device__ __forceinline__ void move_left(uint8_t *out, uint64_t ps, uint64_t le
     }
 }
 
+constexpr int kFixWindow = 1024;  // parts staged at a time (2 MiB of a NAL)
+
 __global__ void __launch_bounds__(256) nal_fixup_kernel(ScanArgs a, h264b_scan_summary *summary) {
+    __shared__ uint32_t sh_tail[kFixWindow], sh_S[kFixWindow];
     const uint32_t n_fix = a.hdr->n_fix;
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // totals of scan_finalize_kernel (complete: previous launch)
         summary->n_epb = a.hdr->n_epb;
@@ -702,9 +753,22 @@ __global__ void __launch_bounds__(256) nal_fixup_kernel(ScanArgs a, h264b_scan_s
         const uint64_t k = a.fix_list[f];
         const uint4 r0 = a.nal_rec[k], r1 = a.nal_rec[k + 1];
         const uint64_t st = rec_start(r0), next = rec_start(r1);
-        nal_pieces(st, next, nal_header_bytes(r0.z & 0xFFu, (r0.z >> 8) & 0xFFu), r1.w & 0xFFFFu, a.piece, a.piece_S,
-                   (uint64_t)kChunk,
-                   [&](uint64_t ps, uint64_t len, uint64_t G) { move_left(a.out, ps, len, G); });
+        const uint32_t H = nal_header_bytes(r0.z & 0xFFu, (r0.z >> 8) & 0xFFu);
+        const uint64_t Tq = (st - 1) / kChunk, Tb = (next - 1) / kChunk;
+        const uint32_t S_Tq = a.piece_S[Tq];
+        MoveRun run = {0, 0, 0};
+        const auto move = [&](uint64_t ps, uint64_t len, uint64_t G) { move_left(a.out, ps, len, G); };
+        for (uint64_t t0 = Tq + 1; t0 <= Tb; t0 += kFixWindow) {  // every thread walks the same parts (CTA-uniform)
+            const uint64_t t1 = t0 + kFixWindow <= Tb + 1 ? t0 + kFixWindow : Tb + 1;
+            __syncthreads();
+            for (uint64_t t = t0 + threadIdx.x; t < t1; t += 256) {
+                sh_tail[t - t0] = a.piece[t];
+                sh_S[t - t0] = a.piece_S[t];
+            }
+            __syncthreads();
+            nal_pieces_window(st, next, H, r1.w & 0xFFFFu, sh_tail, sh_S, t0, S_Tq, (uint64_t)kChunk, t0, t1, run, move);
+        }
+        nal_pieces_flush(run, move);
     }
 }
 

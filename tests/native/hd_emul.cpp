@@ -132,28 +132,27 @@ int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out_base, int64_
             for (int i = 0; i < kHalo + kChunk + kHalo; i++) buf[i] = (uint8_t)gets(pos - kHalo + i);
             uint8_t *tile_in = buf.data() + kHalo;
             // ---- detect (fast path)
-            // the copy kernel's filter (annexb_copy_kernel): per granule, then the chunk's edges
-            uint32_t need = 0;
+            // the copy kernel's filter (annexb_copy_kernel): per granule, exact masks only where the cheap test fires
+            uint32_t any_e = 0, any_sc = 0;
+            std::vector<uint32_t> sc_f(kGran);
             for (int gi = 0; gi < kGran; gi++) {
                 uint32_t w[4], prev;
                 memcpy(w, tile_in + gi * 16, 16);
                 memcpy(&prev, tile_in + gi * 16 - 4, 4);
-                need |= granule_needs_general(w, prev);
+                const GranuleMasks mf = granule_masks_filtered(w, prev), mx = granule_masks(w, prev);
+                if (mf.e != mx.e || mf.sc != mx.sc) n_filter_mismatch++;  // the filter may only skip empty granules
+                any_e |= mf.e;
+                any_sc |= mf.sc;
+                sc_f[gi] = mf.sc;
                 // the cheap part of the filter against its definition
                 bool brute = false;
                 for (int i = -1; i < 16; i++)
                     brute = brute || (tile_in[gi * 16 + i] == 0 && tile_in[gi * 16 + i - 1] == 0);
                 if (brute != (acc_has_pair(zero_pair_acc(0xFFFFFFFFu, w, prev)) || (prev >> 16) == 0u)) n_filter_mismatch++;
             }
-            {
-                uint32_t lo, hi, last;
-                memcpy(&lo, buf.data() + 8, 4);
-                memcpy(&hi, buf.data() + 12, 4);
-                memcpy(&last, tile_in + kChunk - 4, 4);
-                if (chunk_edges_need_general(lo, hi, last)) need |= 1u;
-            }
             const bool edge = pos == 0 || pos + kChunk + kHalo > n;
-            const bool filter_clean = need == 0 && !edge;
+            // no emulation-prevention candidate: the copy kernel stores the chunk as it is and writes the records itself
+            const bool filter_clean = any_e == 0 && !edge;
             // pieces longer than one chunk (not what the product runs) also carry the open NAL's EPB count along
             bool clean = filter_clean && carry_epb == 0;
             {   // ---- general path: exact masks (computed for every chunk here, to hold the filter against them)
@@ -206,9 +205,30 @@ int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out_base, int64_
                 }
                 bool all0 = true;
                 for (int r = 0; r < kRows; r++) all0 = all0 && cls[r] == 0;
-                if (filter_clean && !all0) n_filter_mismatch++;  // the filter let through a chunk that needs work
+                if (filter_clean) {  // the copy kernel's claim: nothing is removed in this chunk
+                    for (int gi = 0; gi < kGran; gi++)
+                        if (ee[gi]) n_filter_mismatch++;
+                }
                 if (clean) {
-                    n_fast++;  // left to the copy kernel
+                    n_fast++;  // left to the copy kernel: verbatim copy (below) + records, all counts zero
+                    uint32_t n_sc = 0;
+                    for (int gi = 0; gi < kGran; gi++) n_sc += bits_popc(sc_f[gi]);
+                    const uint64_t slot0 = rec_start.size();
+                    rec_start.resize(slot0 + n_sc, 0);
+                    rec_epb.resize(slot0 + n_sc, 0);
+                    rec_hdr.resize(slot0 + n_sc, 0);
+                    rec_rank.resize(slot0 + n_sc, 0);
+                    uint32_t rank = 0;
+                    for (int gi = 0; gi < kGran; gi++)
+                        for (int j = 0; j < 16; j++)
+                            if (sc_f[gi] & (1u << j)) {
+                                const int64_t st = pos + gi * 16 + j + 1;
+                                rec_start[slot0 + rank] = (uint64_t)st;
+                                rec_hdr[slot0 + rank] = gets(st) | (gets(st + 1) << 8) | (gets(st + 2) << 16) | (gets(st + 3) << 24);
+                                rec_rank[slot0 + rank] = pnsc + rank;
+                                rank++;
+                            }
+                    pnsc += n_sc;
                 } else if (all0 && carry_epb == 0) {
                     clean = true;
                     n_false_alarm++;
