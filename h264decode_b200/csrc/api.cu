@@ -121,7 +121,7 @@ void h264b_destroy(h264b_ctx *ctx) {
         cudaFree(ctx->d_mn[v]);
         cudaFree(ctx->d_state_lut[v]);
     }
-    for (int i = 0; i < 16; i++) cudaFree(ctx->d_buf[i]);
+    for (int i = 0; i < 20; i++) cudaFree(ctx->d_buf[i]);
     for (int i = 0; i < 8; i++)
         if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
     cudaFree(ctx->scan_scratch);
@@ -217,6 +217,7 @@ int32_t h264b_cabac_decode_dev(h264b_ctx *ctx, const h264b_cabac_job *job) {
 // ------------------------------------------------------------------------------------------------ host entries
 // device slots: 0 stream/frames/bytes  1 rbsp  2 nals  3 ext  4 summary+counters  5 off  6 len  7 ops  8 n_ops
 //               9 qp  10 init/final states  11 bins  12 final  13 slice_nal  14 states(K4)  15 scalar io
+//               16 length-bundle sort (cabac_engine.cu)
 // pinned slots: 0 nals  1 ext  2 rbsp  3 bins  4 final  5 slice_nal  6 misc
 static uint32_t default_nal_cap(uint64_t n) {
     uint64_t c = n / 64 + 1024;

@@ -23,9 +23,73 @@ struct CabacArgs {
     h264b_cabac_job j;
     const uint64_t *tab;   // 128-entry engine table
     const uint8_t *lut;    // K4 state LUT [5][52][1024]
+    const uint32_t *order; // slices sorted by length (longest first) or NULL: lane -> slice = order[index]
     uint32_t lanes_per_warp;
     uint32_t n_warps;
 };
+
+// ---------------------------------------------------------------------------------------------- length bundles
+// A warp runs until its longest slice is done, so the 32 slices of a warp should be equally long: slices are bucketed
+// by op count (2048 linear buckets between the shortest and the longest: a counting sort, order inside a bucket is
+// arbitrary) and dealt to warps longest first, which also puts the long warps at the front of the launch.
+constexpr int kLenBuckets = 2048;
+
+struct SortScratch {
+    uint32_t min_ops, max_ops;
+    uint32_t hist[kLenBuckets];    // then: running cursor of each bucket
+};
+
+__device__ __forceinline__ uint32_t len_bucket(uint32_t ops, uint32_t lo, uint32_t hi) {  // longest -> bucket 0
+    const uint64_t span = (uint64_t)(hi - lo) + 1;
+    return (uint32_t)(((uint64_t)(hi - ops) * kLenBuckets) / span);
+}
+
+__global__ void __launch_bounds__(256) sort_minmax_kernel(const uint32_t *n_ops, uint32_t n, uint32_t cap, SortScratch *s) {
+    uint32_t lo = 0xFFFFFFFFu, hi = 0;
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const uint32_t v = n_ops[i] < cap ? n_ops[i] : cap;
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+    lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+    hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&s->min_ops, lo);
+        atomicMax(&s->max_ops, hi);
+    }
+}
+
+__global__ void __launch_bounds__(256) sort_hist_kernel(const uint32_t *n_ops, uint32_t n, uint32_t cap, SortScratch *s) {
+    const uint32_t lo = s->min_ops, hi = s->max_ops;
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+        atomicAdd(&s->hist[len_bucket(n_ops[i] < cap ? n_ops[i] : cap, lo, hi)], 1u);
+}
+
+__global__ void __launch_bounds__(1024) sort_scan_kernel(SortScratch *s) {  // exclusive scan of the 2048 counts
+    __shared__ uint32_t warp_sum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t a = s->hist[2 * tid], b = s->hist[2 * tid + 1];
+    uint32_t x = a + b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sum[warp] = x;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < warp; w++) base += warp_sum[w];
+    const uint32_t excl = base + x - (a + b);
+    s->hist[2 * tid] = excl;
+    s->hist[2 * tid + 1] = excl + a;
+}
+
+__global__ void __launch_bounds__(256) sort_scatter_kernel(const uint32_t *n_ops, uint32_t n, uint32_t cap, SortScratch *s,
+                                                           uint32_t *order) {
+    const uint32_t lo = s->min_ops, hi = s->max_ops;
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+        order[atomicAdd(&s->hist[len_bucket(n_ops[i] < cap ? n_ops[i] : cap, lo, hi)], 1u)] = i;
+}
 
 __device__ __forceinline__ int idc_class_dev(int idc) { return (idc >= -1 && idc <= 2) ? idc + 1 : 4; }
 __device__ __forceinline__ int clip3_dev(int x, int y, int z) { return z < x ? x : (z > y ? y : z); }
@@ -43,8 +107,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
 
     const uint32_t gw = blockIdx.x * kWarpsPerCta + warp;
     if (gw >= a.n_warps) return;
-    const uint32_t slice = gw * a.lanes_per_warp + lane;
-    const bool valid = lane < (int)a.lanes_per_warp && slice < j.n_slices;
+    const uint32_t index = gw * a.lanes_per_warp + lane;
+    const bool valid = lane < (int)a.lanes_per_warp && index < j.n_slices;
+    const uint32_t slice = valid && a.order ? a.order[index] : index;
 
     // ---- per-lane setup
     uint32_t my_ops = 0;
@@ -79,8 +144,51 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
     uint32_t *bins = valid ? j.bins + (j.bins_off ? (size_t)j.bins_off[slice] : (size_t)slice * j.bins_stride_words)
                            : nullptr;
     uint32_t word = 0;
-    uint32_t next_op = warp_ops ? j.ops[0] : 0;
-    for (uint32_t i = 0; i < warp_ops; i++) {
+    uint32_t i = 0;
+    // ---- fast loop: while every lane of the warp is active and on the window engine (the usual case for all but the
+    // last few hundred ops of a length bundle) there is nothing to predicate: one op, one straight-line sequence
+    uint32_t warp_min = valid ? my_ops : 0u;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) warp_min = min(warp_min, __shfl_xor_sync(0xFFFFFFFFu, warp_min, d));
+    if (warp_min && !__any_sync(0xFFFFFFFFu, eng.lit)) {
+        CabacLane &w = eng.w;
+        uint32_t op_next = j.ops[0];
+        bool left = false;
+        while (i < warp_min && !left) {
+            const uint32_t op = op_next;
+            if (i + 1 < warp_ops) op_next = j.ops[i + 1];
+            if (__any_sync(0xFFFFFFFFu, w.must_refill())) {
+                if (w.can_refill()) w.refill();
+            }
+            const uint32_t kind = op >> 14;
+            uint32_t bin;
+            if (kind == H264B_OP_DECISION) {
+                uint32_t c = op & 0x3FFu;
+                if (c >= n_ctx) c = 0;
+                uint8_t *sp = s_state + c * 32 + lane;
+                uint8_t ns;
+                bin = w.decision(s_tab[*sp & 127u], &ns);
+                *sp = ns;
+            } else if (kind == H264B_OP_BYPASS) {
+                bin = w.bypass();
+            } else {
+                bin = w.terminate();
+                if (__any_sync(0xFFFFFFFFu, bin)) {  // a slice that goes on after its end: the generic loop takes over
+                    if (bin) eng.to_literal();
+                    left = true;
+                }
+            }
+            word |= bin << (i & 31u);
+            if ((i & 31u) == 31u) {
+                bins[i >> 5] = word;
+                word = 0;
+            }
+            i++;
+        }
+    }
+    // ---- generic loop: lanes that have finished, lanes on the literal engine
+    uint32_t next_op = i < warp_ops ? j.ops[i] : 0;
+    for (; i < warp_ops; i++) {
         const uint32_t op = next_op;
         if (i + 1 < warp_ops) next_op = j.ops[i + 1];
         const bool active = i < my_ops;
@@ -161,6 +269,27 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job) {
     if (lpw > 32) lpw = 32;
     a.lanes_per_warp = lpw;
     a.n_warps = (j.n_slices + lpw - 1) / lpw;
+    a.order = nullptr;
+    if (lpw > 1 && j.n_ops) {  // bundles of equally long slices
+        void *d_sort;
+        int rc = ensure_dev(ctx, 16, sizeof(SortScratch) + (size_t)j.n_slices * 4, &d_sort);
+        if (rc) return rc;
+        SortScratch *ss = (SortScratch *)d_sort;
+        uint32_t *order = (uint32_t *)(ss + 1);
+        H264B_CUDA(ctx, cudaMemsetAsync(ss, 0, sizeof(SortScratch), ctx->stream));
+        H264B_CUDA(ctx, cudaMemsetAsync(&ss->min_ops, 0xFF, 4, ctx->stream));
+        const int sb = (int)((j.n_slices + 255) / 256 < (uint32_t)ctx->sm_count * 4 ? (j.n_slices + 255) / 256
+                                                                                   : (uint32_t)ctx->sm_count * 4);
+        sort_minmax_kernel<<<sb, 256, 0, ctx->stream>>>(j.n_ops, j.n_slices, j.n_ops_max, ss);
+        H264B_LAUNCH_CHECK(ctx, "sort_minmax_kernel");
+        sort_hist_kernel<<<sb, 256, 0, ctx->stream>>>(j.n_ops, j.n_slices, j.n_ops_max, ss);
+        H264B_LAUNCH_CHECK(ctx, "sort_hist_kernel");
+        sort_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ss);
+        H264B_LAUNCH_CHECK(ctx, "sort_scan_kernel");
+        sort_scatter_kernel<<<sb, 256, 0, ctx->stream>>>(j.n_ops, j.n_slices, j.n_ops_max, ss, order);
+        H264B_LAUNCH_CHECK(ctx, "sort_scatter_kernel");
+        a.order = order;
+    }
     const size_t smem = 1024 + (size_t)kWarpsPerCta * j.n_ctx * 32;
     const int blocks = (int)((a.n_warps + kWarpsPerCta - 1) / kWarpsPerCta);
     H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

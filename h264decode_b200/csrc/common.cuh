@@ -29,8 +29,8 @@ struct h264b_ctx {
     // host-level (pinned) staging, grow-only
     void *h_pin[8];
     size_t h_pin_bytes[8];
-    void *d_buf[16];
-    size_t d_buf_bytes[16];
+    void *d_buf[20];
+    size_t d_buf_bytes[20];
 };
 
 namespace h264b {
