@@ -145,45 +145,65 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
                            : nullptr;
     uint32_t word = 0;
     uint32_t i = 0;
-    // ---- fast loop: while every lane of the warp is active and on the window engine (the usual case for all but the
-    // last few hundred ops of a length bundle) there is nothing to predicate: one op, one straight-line sequence
+    // ---- fast loop: blocks of 32 ops (one word of bins) while every lane of the warp is active and on the window
+    // engine -- the usual case for all but the tail of a length bundle.  Nothing is predicated: the 32 ops of a block
+    // are fetched with one coalesced load and handed out by shuffle, bins are funnel-shifted into the word, the table
+    // fields are picked with byte permutes.  Same arithmetic as CabacLane::decision / bypass / terminate.
     uint32_t warp_min = valid ? my_ops : 0u;
 #pragma unroll
     for (int d = 16; d; d >>= 1) warp_min = min(warp_min, __shfl_xor_sync(0xFFFFFFFFu, warp_min, d));
-    if (warp_min && !__any_sync(0xFFFFFFFFu, eng.lit)) {
+    if (warp_min >= 32u && !__any_sync(0xFFFFFFFFu, eng.lit)) {
         CabacLane &w = eng.w;
-        uint32_t op_next = j.ops[0];
         bool left = false;
-        while (i < warp_min && !left) {
-            const uint32_t op = op_next;
-            if (i + 1 < warp_ops) op_next = j.ops[i + 1];
-            if (__any_sync(0xFFFFFFFFu, w.must_refill())) {
-                if (w.can_refill()) w.refill();
-            }
-            const uint32_t kind = op >> 14;
-            uint32_t bin;
-            if (kind == H264B_OP_DECISION) {
-                uint32_t c = op & 0x3FFu;
-                if (c >= n_ctx) c = 0;
-                uint8_t *sp = s_state + c * 32 + lane;
-                uint8_t ns;
-                bin = w.decision(s_tab[*sp & 127u], &ns);
-                *sp = ns;
-            } else if (kind == H264B_OP_BYPASS) {
-                bin = w.bypass();
-            } else {
-                bin = w.terminate();
-                if (__any_sync(0xFFFFFFFFu, bin)) {  // a slice that goes on after its end: the generic loop takes over
-                    if (bin) eng.to_literal();
-                    left = true;
+        while (i + 32u <= warp_min && !left) {
+            uint32_t my_op = j.ops[i + (uint32_t)lane];
+            if ((my_op >> 14) == H264B_OP_DECISION && (my_op & 0x3FFu) >= n_ctx) my_op &= ~0x3FFu;  // as below: ctx 0
+            uint32_t k = 0;
+#pragma unroll 1
+            for (; k < 32u; k++) {
+                const uint32_t op = __shfl_sync(0xFFFFFFFFu, my_op, (int)k);
+                if (__builtin_expect(__any_sync(0xFFFFFFFFu, w.must_refill()), 0)) {
+                    if (w.can_refill()) w.refill();
+                }
+                const uint32_t kind = op >> 14;
+                uint32_t sel;  // the bin in bit 8
+                if (kind == H264B_OP_DECISION) {
+                    uint8_t *sp = s_state + (op & 0x3FFu) * 32u + (uint32_t)lane;
+                    const uint64_t e = s_tab[*sp & 127u];
+                    const uint32_t tlo = (uint32_t)e, thi = (uint32_t)(e >> 32);
+                    const uint32_t lps = __byte_perm(tlo, 0u, ((w.R >> 6) & 3u) | 0x4440u);  // rangeTabLPS[state][q]
+                    const uint32_t rm = w.R - lps, x = rm << 22;
+                    const bool is_lps = w.hi >= x;
+                    w.hi = is_lps ? w.hi - x : w.hi;
+                    const uint32_t r = is_lps ? lps : rm;
+                    sel = __byte_perm(thi, 0u, is_lps ? 0x4432u : 0x4410u);  // (next state, bin) of the path taken
+                    *sp = (uint8_t)sel;
+                    const uint32_t sh = clz32(r) - 23u;
+                    w.R = r << sh;
+                    w.shift(sh);
+                } else if (kind == H264B_OP_BYPASS) {
+                    sel = w.bypass() << 8;
+                } else {
+                    const uint32_t bin = w.terminate();
+                    sel = bin << 8;
+                    if (__any_sync(0xFFFFFFFFu, bin)) {  // a slice that goes on after its end: the generic loop takes over
+                        if (bin) eng.to_literal();
+                        left = true;
+                    }
+                }
+                word = __funnelshift_r(word, sel >> 8, 1);  // bin k of the block ends up in bit k
+                if (left) {
+                    k++;
+                    break;
                 }
             }
-            word |= bin << (i & 31u);
-            if ((i & 31u) == 31u) {
-                bins[i >> 5] = word;
+            i += k;
+            if (k == 32u) {
+                bins[(i >> 5) - 1u] = word;
                 word = 0;
+            } else {
+                word >>= 32u - k;  // a partial block: bins 0..k-1 in bits 0..k-1, the generic loop goes on from there
             }
-            i++;
         }
     }
     // ---- generic loop: lanes that have finished, lanes on the literal engine
