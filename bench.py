@@ -30,6 +30,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# DRAM bytes (read + write) per algorithmic byte of the Annex-B pass, from the ncu capture of this command line
+# (profiles/r1_ncu_scan_v10_full.txt: dram__bytes_read.sum + dram__bytes_write.sum of all launches of one pass)
+TRAFFIC_PER_ALG_BYTE = None
+TRAFFIC_SOURCE = None
 MEAN_BINS = 455_000      # ~50 KB of CABAC data per slice at ~0.88 bit/bin
 N_ACTIVE = 64
 N_CTX = 64
@@ -294,13 +298,20 @@ def run_gpu(args, rank, world, local_rank):
     ctx.sync()
     del d_bins, d_rbsp
     torch.cuda.empty_cache()
-    e2e_steps = max(1, min(args.steps, 3))
-    r = None
-    r = _stream_decode_raw(ctx, capi, h_stream, ops, n_ops, p, flags)  # warm-up: grows the pinned / device buffers
+    e2e_steps = max(2, min(args.steps, 4))
+    # warm-up: both job slots grow their pinned / device buffers
+    tk = [_stream_submit_raw(ctx, capi, h_stream, ops, n_ops, p, flags) for _ in range(2)]
+    for t in tk:
+        r = _stream_wait_raw(ctx, capi, t)
     barrier()
+    # timed: every step copies its stream in and its results out; consecutive steps overlap (two jobs in flight:
+    # H2D of step k+1 | kernels of step k | D2H of step k-1), which is how an ingest loop drives the library
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        r = _stream_decode_raw(ctx, capi, h_stream, ops, n_ops, p, flags)
+    pending = [_stream_submit_raw(ctx, capi, h_stream, ops, n_ops, p, flags)]
+    for k in range(1, e2e_steps):
+        pending.append(_stream_submit_raw(ctx, capi, h_stream, ops, n_ops, p, flags))
+        r = _stream_wait_raw(ctx, capi, pending.pop(0))
+    r = _stream_wait_raw(ctx, capi, pending.pop(0))
     torch.cuda.synchronize()
     t_e2e = (time.perf_counter() - t0) / e2e_steps
     e2e_ok = r["n_slices"] == n_slices and r["total_bins"] == total_bins
@@ -333,22 +344,28 @@ def run_gpu(args, rank, world, local_rank):
             "annexb_gbps": bytes_all / 1e9 / (t_scan_ms * 1e-3),
             "stage_ms": {"annexb_scan": t_scan_ms, "slice_select+cabac": t_cabac_ms},
             "stream_bytes_per_gpu": n, "bins_per_gpu": total_bins, "nals_per_gpu": n_nals,
-            "roofline": {"bound": "hbm", "kernel": "annexb_scan (init+first_start+scan+finalize launches)",
+            "roofline": {"bound": "hbm", "kernel": "annexb_copy_kernel + the six small launches of one Annex-B pass "
+                                                   "(memset, dirty chunks, ordinal scan x2, permute, finalize, fixup), "
+                                                   "timed together with CUDA events on the launching stream",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes": alg_bytes},
+                         "traffic": TRAFFIC_PER_ALG_BYTE * alg_bytes if TRAFFIC_PER_ALG_BYTE else None,
+                         "traffic_source": TRAFFIC_SOURCE, "peak_source": peak_src, "algorithmic_bytes": alg_bytes},
             "roofline_cabac": {"bound": "issue/latency (serial integer chain; not HBM, not tensor)",
                                "bins_per_s_per_gpu": total_bins / (t_cabac_ms * 1e-3),
                                "lanes": n_slices, "hbm_gbs_implied": total_bins * 0.235 / (t_cabac_ms * 1e-3) / 1e9},
             "e2e": {"value": bins_all / t_e2e_max, "unit": "bins/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": t_e2e_max * 1e3, "steps": e2e_steps,
-                    "api": "h264b_stream_decode (pinned host stream in; NAL index, packed bins, final states out)"},
+                    "api": "h264b_stream_submit / h264b_stream_wait, two jobs in flight (pinned host stream in; NAL index, "
+                           "packed bins, final states out; copies of consecutive steps overlap kernels)"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            ns = args.cpu_slices or max(16 * cores, 64)
+            # bounded sample: ~10-20 s of CPU work in all (all-core pass on `ns` slices, one-core pass on 1/8 of them)
+            ns = args.cpu_slices or max(128 * cores, 512)
             sample = make_cpu_sample(ns)
-            b1, s1, s1_scan, s1_cabac = cpu_reference_pass(sample, 1) if args.cpu_single else (None, None, None, None)
+            small = make_cpu_sample(max(ns // 8, 16)) if args.cpu_single else None
+            b1, s1, s1_scan, s1_cabac = cpu_reference_pass(small, 1) if args.cpu_single else (None, None, None, None)
             bN, sN, sN_scan, sN_cabac = cpu_reference_pass(sample, cores)
             out["cpu_baseline"] = {
                 "value": bN / sN, "unit": "bins/s", "cores": cores, "kind": "port",
@@ -368,8 +385,8 @@ def run_gpu(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def _stream_decode_raw(ctx, capi, h_stream, ops, n_ops, p, flags):
-    """h264b_stream_decode without copying the (multi-GB) results out of the library's pinned buffers again"""
+def _stream_submit_raw(ctx, capi, h_stream, ops, n_ops, p, flags):
+    """h264b_stream_submit on buffers that stay alive in the caller"""
     import ctypes as C
     j = capi.StreamJob()
     j.stream = h_stream.ctypes.data
@@ -382,8 +399,16 @@ def _stream_decode_raw(ctx, capi, h_stream, ops, n_ops, p, flags):
     j.qp = p.ctypes.data
     j.max_slices = len(p)
     j.flags = flags
+    t = C.c_uint64()
+    ctx._check(capi.lib().h264b_stream_submit(ctx.h, C.byref(j), C.byref(t)))
+    return t.value
+
+
+def _stream_wait_raw(ctx, capi, ticket):
+    """h264b_stream_wait without copying the (multi-GB) results out of the library's pinned buffers again"""
+    import ctypes as C
     r = capi.StreamResult()
-    ctx._check(capi.lib().h264b_stream_decode(ctx.h, C.byref(j), C.byref(r)))
+    ctx._check(capi.lib().h264b_stream_wait(ctx.h, ticket, C.byref(r)))
     return {"n_slices": r.n_slices, "total_bins": r.total_bins, "n_nals": r.scan.n_nals}
 
 

@@ -23,7 +23,8 @@ SYMBOLS = [
     "h264b_memcpy_d2h", "h264b_launch_count", "h264b_annexb_scratch_bytes", "h264b_annexb_scan_dev",
     "h264b_annexb_scan", "h264b_nal_units", "h264b_ctx_init_dev", "h264b_ctx_init", "h264b_pre_ctx_state", "h264b_mn",
     "h264b_cabac_decode_dev", "h264b_cabac_decode", "h264b_engine_step", "h264b_binary_decision",
-    "h264b_state_transition", "h264b_stream_decode", "h264b_slice_select_dev",
+    "h264b_state_transition", "h264b_stream_decode", "h264b_stream_submit", "h264b_stream_wait",
+    "h264b_slice_select_dev",
 ]
 
 NAL_DTYPE = np.dtype([("start", "<u8"), ("rbsp_off", "<u8"), ("num_bytes", "<u4"), ("rbsp_len", "<u4"),
@@ -110,6 +111,8 @@ def load():
         "h264b_binary_decision": (i32, [vp, u32, i32, i32, P(C.c_int64), P(C.c_int64), P(i32)]),
         "h264b_state_transition": (i32, [vp, u32, P(i32), P(i32), i32]),
         "h264b_stream_decode": (i32, [vp, P(StreamJob), P(StreamResult)]),
+        "h264b_stream_submit": (i32, [vp, P(StreamJob), P(u64)]),
+        "h264b_stream_wait": (i32, [vp, u64, P(StreamResult)]),
         "h264b_slice_select_dev": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -365,6 +368,36 @@ class Context:
         j.flags = flags
         r = StreamResult()
         self._check(_lib.h264b_stream_decode(self.h, C.byref(j), C.byref(r)))
+        return self._stream_result(r)
+
+    def stream_submit(self, stream, ops, n_ops, qp, idc, n_ctx, slice_data_offset=0, flags=0):
+        """asynchronous form: returns (ticket, keepalive); pass both to stream_wait.  Up to two jobs in flight."""
+        s = np.ascontiguousarray(stream, dtype=np.uint8)
+        ops = np.ascontiguousarray(ops, dtype=np.uint16)
+        p = self.slice_qp(qp, idc)
+        nops = None if n_ops is None else np.ascontiguousarray(n_ops, dtype=np.uint32)
+        j = StreamJob()
+        j.stream = s.ctypes.data
+        j.n = len(s)
+        j.slice_data_offset = slice_data_offset
+        j.n_ctx = n_ctx
+        j.ops = ops.ctypes.data
+        j.n_ops_max = len(ops)
+        j.n_ops = nops.ctypes.data if nops is not None else None
+        j.qp = p.ctypes.data
+        j.max_slices = len(p)
+        j.flags = flags
+        t = C.c_uint64()
+        self._check(_lib.h264b_stream_submit(self.h, C.byref(j), C.byref(t)))
+        return t.value, (s, ops, p, nops, j)
+
+    def stream_wait(self, ticket, keepalive=None):
+        r = StreamResult()
+        self._check(_lib.h264b_stream_wait(self.h, ticket, C.byref(r)))
+        return self._stream_result(r)
+
+    @staticmethod
+    def _stream_result(r):
         ns = r.n_slices
         boff = _from_ptr(r.bins_off, np.uint64, ns + 1)
         flat = _from_ptr(r.bins, np.uint32, int(boff[-1]) if ns else 0)

@@ -99,6 +99,21 @@ int32_t h264b_create(int32_t device, h264b_ctx **out) {
         return H264B_E_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    bool ok = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++) {
+        StreamSlot *sl = (StreamSlot *)calloc(1, sizeof(StreamSlot));
+        ok = sl && cudaEventCreate(&sl->e_in) == cudaSuccess && cudaEventCreate(&sl->e_compute) == cudaSuccess &&
+             cudaEventCreate(&sl->e_out) == cudaSuccess && cudaEventCreate(&sl->t_in0) == cudaSuccess &&
+             cudaEventCreate(&sl->t_c0) == cudaSuccess && cudaEventCreate(&sl->t_o0) == cudaSuccess;
+        ctx->slot[i] = sl;
+    }
+    ctx->trace = getenv("H264B_TRACE") != nullptr;
+    ok = ok && cudaEventCreate(&ctx->t_ref) == cudaSuccess;
+    if (!ok) {
+        h264b_destroy(ctx);
+        return H264B_E_CUDA;
+    }
     int rc = build_tables(ctx);
     if (rc) {
         fprintf(stderr, "h264b_create: %s\n", ctx->err);
@@ -125,6 +140,23 @@ void h264b_destroy(h264b_ctx *ctx) {
     for (int i = 0; i < 8; i++)
         if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
     cudaFree(ctx->scan_scratch);
+    for (int i = 0; i < 2; i++) {
+        StreamSlot *sl = ctx->slot[i];
+        if (!sl) continue;
+        for (int k = 0; k < kSlotDev; k++) cudaFree(sl->d[k]);
+        for (int k = 0; k < kSlotPin; k++)
+            if (sl->h[k]) cudaFreeHost(sl->h[k]);
+        if (sl->e_in) cudaEventDestroy(sl->e_in);
+        if (sl->e_compute) cudaEventDestroy(sl->e_compute);
+        if (sl->e_out) cudaEventDestroy(sl->e_out);
+        if (sl->t_in0) cudaEventDestroy(sl->t_in0);
+        if (sl->t_c0) cudaEventDestroy(sl->t_c0);
+        if (sl->t_o0) cudaEventDestroy(sl->t_o0);
+        free(sl);
+    }
+    if (ctx->t_ref) cudaEventDestroy(ctx->t_ref);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     free(ctx);
 }
@@ -392,72 +424,137 @@ int32_t h264b_cabac_decode(h264b_ctx *ctx, const h264b_cabac_job *job) {
     return H264B_OK;
 }
 
-int32_t h264b_stream_decode(h264b_ctx *ctx, const h264b_stream_job *job, h264b_stream_result *res) {
+// ---- the whole front end of one stream, asynchronously: two jobs in flight per context -------------------------
+// device buffers of a slot: 0 stream  1 rbsp  2 nals  3 summary + slice count  4 off  5 len  6 slice_nal  7 ops
+//                           8 n_ops  9 qp  10 bins_off  11 bins  12 final
+// pinned buffers of a slot: 0 nals  1 bins_off  2 bins  3 final  4 slice_nal  5 summary + slice count
+//                           6 ops  7 n_ops  8 qp (staging of the caller's small arrays: they may be pageable, and a
+//                           pageable source would make the copies -- and with them the whole submit -- synchronous)
+static int slot_dev(h264b_ctx *ctx, StreamSlot *sl, int i, size_t bytes, void **out) {
+    if (bytes < 256) bytes = 256;
+    if (sl->d_bytes[i] < bytes) {
+        if (sl->d[i]) {
+            H264B_CUDA(ctx, cudaDeviceSynchronize());
+            cudaFree(sl->d[i]);
+            sl->d[i] = nullptr;
+            sl->d_bytes[i] = 0;
+        }
+        const size_t want = bytes + bytes / 16;
+        cudaError_t e = cudaMalloc(&sl->d[i], want);
+        if (e != cudaSuccess) return set_error(ctx, H264B_E_NOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+        sl->d_bytes[i] = want;
+    }
+    *out = sl->d[i];
+    return H264B_OK;
+}
+static int slot_pin(h264b_ctx *ctx, StreamSlot *sl, int i, size_t bytes, void **out) {
+    if (bytes < 256) bytes = 256;
+    if (sl->h_bytes[i] < bytes) {
+        if (sl->h[i]) {
+            H264B_CUDA(ctx, cudaDeviceSynchronize());
+            cudaFreeHost(sl->h[i]);
+            sl->h[i] = nullptr;
+            sl->h_bytes[i] = 0;
+        }
+        const size_t want = bytes + bytes / 16;
+        cudaError_t e = cudaHostAlloc(&sl->h[i], want, cudaHostAllocDefault);
+        if (e != cudaSuccess) return set_error(ctx, H264B_E_NOMEM, "cudaHostAlloc(%zu): %s", want, cudaGetErrorString(e));
+        sl->h_bytes[i] = want;
+    }
+    *out = sl->h[i];
+    return H264B_OK;
+}
+
+int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_t *ticket) {
     CHECK_CTX(ctx);
-    if (!job || !res) return H264B_E_INVALID;
+    if (!job || !ticket) return H264B_E_INVALID;
     const h264b_stream_job &j = *job;
     if ((!j.stream && j.n) || !j.qp || (!j.ops && j.n_ops_max))
-        return set_error(ctx, H264B_E_INVALID, "stream_decode: null pointer in job");
-    memset(res, 0, sizeof(*res));
-    // 1. split + strip (the RBSP stays on the device)
-    uint32_t cap = default_nal_cap(j.n);
-    uint8_t *d_rbsp;
-    h264b_nal *d_nals;
-    h264b_nal_ext *d_ext;
-    h264b_scan_summary *d_sum;
-    RC(scan_host_common(ctx, j.stream, j.n, j.flags, &cap, &res->scan, &d_rbsp, &d_nals, &d_ext, &d_sum, false));
-    // 2. slice NAL list on the device
+        return set_error(ctx, H264B_E_INVALID, "stream_submit: null pointer in job");
+    StreamSlot *sl = ctx->slot[ctx->next_ticket & 1];
+    if (sl->busy) return set_error(ctx, H264B_E_INVALID, "stream_submit: two jobs are in flight, wait for one first");
+    // the slot's previous results may still be on their way out: reuse its buffers only after that
+    H264B_CUDA(ctx, cudaEventSynchronize(sl->e_out));
     const size_t ms = j.max_slices ? j.max_slices : 1;
-    void *d_off, *d_len, *d_snal, *d_ops, *d_nops = nullptr, *d_qp, *d_bins, *d_fin;
-    RC(ensure_dev(ctx, 5, ms * 8, &d_off));
-    RC(ensure_dev(ctx, 6, ms * 4, &d_len));
-    RC(ensure_dev(ctx, 13, ms * 4 + 16, &d_snal));
-    uint32_t *d_ns = (uint32_t *)((uint8_t *)d_sum + 64);
-    RC(launch_slice_select(ctx, d_nals, d_sum, cap, j.slice_data_offset, j.max_slices, (uint64_t *)d_off,
-                           (uint32_t *)d_len, (uint32_t *)d_snal, d_ns));
-    uint32_t n_slices = 0;
-    H264B_CUDA(ctx, cudaMemcpyAsync(&n_slices, d_ns, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    // meanwhile: schedule and per-slice parameters
-    RC(ensure_dev(ctx, 7, (size_t)j.n_ops_max * 2 + 16, &d_ops));
-    RC(ensure_dev(ctx, 9, ms * sizeof(h264b_slice_qp), &d_qp));
-    if (j.n_ops_max)
-        H264B_CUDA(ctx, cudaMemcpyAsync(d_ops, j.ops, (size_t)j.n_ops_max * 2, cudaMemcpyHostToDevice, ctx->stream));
-    H264B_CUDA(ctx, cudaMemcpyAsync(d_qp, j.qp, ms * sizeof(h264b_slice_qp), cudaMemcpyHostToDevice, ctx->stream));
-    if (j.n_ops) {
-        RC(ensure_dev(ctx, 8, ms * 4, &d_nops));
-        H264B_CUDA(ctx, cudaMemcpyAsync(d_nops, j.n_ops, ms * 4, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    // 3. CABAC over the slices, contexts initialised in-kernel by the K4 rule; bins in a compact layout
-    if (n_slices > j.max_slices) n_slices = j.max_slices;
-    res->n_slices = n_slices;
-    void *h_nals, *h_bins, *h_fin, *h_snal, *h_boff, *d_boff;
-    const size_t nn = (size_t)res->scan.n_nals;
-    RC(ensure_pin(ctx, 0, nn * sizeof(h264b_nal), &h_nals));
-    if (nn) H264B_CUDA(ctx, cudaMemcpyAsync(h_nals, d_nals, nn * sizeof(h264b_nal), cudaMemcpyDeviceToHost, ctx->stream));
-    res->nals = (const h264b_nal *)h_nals;
-    RC(ensure_pin(ctx, 6, ((size_t)n_slices + 1) * 8, &h_boff));
+    const uint32_t cap = default_nal_cap(j.n);
+    void *d_stream, *d_rbsp, *d_nals, *d_sum, *d_off, *d_len, *d_snal, *d_ops, *d_nops = nullptr, *d_qp, *d_boff, *d_bins,
+        *d_fin, *h_boff;
+    // bins layout: fixed by the caller's op counts, so it is known before the device knows how many slices there are
+    RC(slot_pin(ctx, sl, 1, (ms + 1) * 8, &h_boff));
     uint64_t *boff = (uint64_t *)h_boff;
     boff[0] = 0;
-    for (uint32_t s = 0; s < n_slices; s++) {
+    for (size_t s = 0; s < j.max_slices; s++) {
         uint32_t nb = j.n_ops ? j.n_ops[s] : j.n_ops_max;
         if (nb > j.n_ops_max) nb = j.n_ops_max;
         boff[s + 1] = boff[s] + ((uint64_t)nb + 1 + 31) / 32;
     }
-    res->bins_off = boff;
-    if (n_slices) {
-        const size_t total_words = (size_t)boff[n_slices];
-        RC(ensure_dev(ctx, 10, ((size_t)n_slices + 1) * 8, &d_boff));
-        RC(ensure_dev(ctx, 11, total_words * 4, &d_bins));
-        RC(ensure_dev(ctx, 12, (size_t)n_slices * sizeof(h264b_cabac_final), &d_fin));
-        H264B_CUDA(ctx, cudaMemcpyAsync(d_boff, boff, ((size_t)n_slices + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t total_words = (size_t)boff[j.max_slices];
+    RC(slot_dev(ctx, sl, 0, j.n + 64, &d_stream));
+    RC(slot_dev(ctx, sl, 1, j.n + 64, &d_rbsp));
+    RC(slot_dev(ctx, sl, 2, (size_t)cap * sizeof(h264b_nal), &d_nals));
+    RC(slot_dev(ctx, sl, 3, 256, &d_sum));
+    RC(slot_dev(ctx, sl, 4, ms * 8, &d_off));
+    RC(slot_dev(ctx, sl, 5, ms * 4, &d_len));
+    RC(slot_dev(ctx, sl, 6, ms * 4 + 16, &d_snal));
+    RC(slot_dev(ctx, sl, 7, (size_t)j.n_ops_max * 2 + 16, &d_ops));
+    if (j.n_ops) RC(slot_dev(ctx, sl, 8, ms * 4, &d_nops));
+    RC(slot_dev(ctx, sl, 9, ms * sizeof(h264b_slice_qp), &d_qp));
+    RC(slot_dev(ctx, sl, 10, (ms + 1) * 8, &d_boff));
+    RC(slot_dev(ctx, sl, 11, total_words * 4, &d_bins));
+    RC(slot_dev(ctx, sl, 12, ms * sizeof(h264b_cabac_final), &d_fin));
+    // The NAL index is copied out with the job up to a length the caller's slice bound makes likely (its true
+    // length is only known on the device); h264b_stream_wait fetches the rest in the rare case there is more.
+    size_t nal_prefix = 2 * ms + 65536;
+    if (nal_prefix > cap) nal_prefix = cap;
+    void *h_nals, *h_bins, *h_fin, *h_snal, *h_sum;
+    RC(slot_pin(ctx, sl, 0, nal_prefix * sizeof(h264b_nal), &h_nals));
+    RC(slot_pin(ctx, sl, 2, total_words * 4, &h_bins));
+    RC(slot_pin(ctx, sl, 3, ms * sizeof(h264b_cabac_final), &h_fin));
+    RC(slot_pin(ctx, sl, 4, ms * 4, &h_snal));
+    RC(slot_pin(ctx, sl, 5, 256, &h_sum));
+
+    // 1. inputs: host -> device on the copy-in stream (overlaps the kernels of the job before)
+    cudaStream_t in = ctx->s_in, out = ctx->s_out, cs = ctx->stream;
+    if (ctx->trace && ctx->next_ticket == 0) cudaEventRecord(ctx->t_ref, in);
+    H264B_CUDA(ctx, cudaStreamWaitEvent(in, sl->e_compute, 0));  // the slot's previous kernels have read its inputs
+    if (ctx->trace) cudaEventRecord(sl->t_in0, in);
+    if (j.n) H264B_CUDA(ctx, cudaMemcpyAsync(d_stream, j.stream, j.n, cudaMemcpyHostToDevice, in));
+    void *h_ops, *h_nops, *h_qp;
+    RC(slot_pin(ctx, sl, 6, (size_t)j.n_ops_max * 2, &h_ops));
+    RC(slot_pin(ctx, sl, 7, ms * 4, &h_nops));
+    RC(slot_pin(ctx, sl, 8, ms * sizeof(h264b_slice_qp), &h_qp));
+    if (j.n_ops_max) {
+        memcpy(h_ops, j.ops, (size_t)j.n_ops_max * 2);
+        H264B_CUDA(ctx, cudaMemcpyAsync(d_ops, h_ops, (size_t)j.n_ops_max * 2, cudaMemcpyHostToDevice, in));
+    }
+    if (j.max_slices) {
+        memcpy(h_qp, j.qp, (size_t)j.max_slices * sizeof(h264b_slice_qp));
+        H264B_CUDA(ctx, cudaMemcpyAsync(d_qp, h_qp, ms * sizeof(h264b_slice_qp), cudaMemcpyHostToDevice, in));
+        if (j.n_ops) {
+            memcpy(h_nops, j.n_ops, (size_t)j.max_slices * 4);
+            H264B_CUDA(ctx, cudaMemcpyAsync(d_nops, h_nops, ms * 4, cudaMemcpyHostToDevice, in));
+        }
+        H264B_CUDA(ctx, cudaMemcpyAsync(d_boff, boff, (ms + 1) * 8, cudaMemcpyHostToDevice, in));
+    }
+    H264B_CUDA(ctx, cudaEventRecord(sl->e_in, in));
+
+    // 2. kernels on the compute stream: split + strip, slice list, CABAC over the slices the device found
+    H264B_CUDA(ctx, cudaStreamWaitEvent(cs, sl->e_in, 0));
+    H264B_CUDA(ctx, cudaStreamWaitEvent(cs, sl->e_out, 0));  // (results of the slot's previous job have left)
+    if (ctx->trace) cudaEventRecord(sl->t_c0, cs);
+    uint32_t *d_ns = (uint32_t *)((uint8_t *)d_sum + 64);
+    RC(launch_annexb_scan(ctx, (const uint8_t *)d_stream, j.n, (uint8_t *)d_rbsp, (h264b_nal *)d_nals, nullptr, cap,
+                          (h264b_scan_summary *)d_sum, j.flags));
+    RC(launch_slice_select(ctx, (const h264b_nal *)d_nals, (const h264b_scan_summary *)d_sum, cap, j.slice_data_offset,
+                           j.max_slices, (uint64_t *)d_off, (uint32_t *)d_len, (uint32_t *)d_snal, d_ns));
+    if (j.max_slices) {
         h264b_cabac_job cj;
         memset(&cj, 0, sizeof(cj));
-        cj.bytes = d_rbsp;
+        cj.bytes = (const uint8_t *)d_rbsp;
         cj.total_bytes = j.n + 16;
         cj.off = (const uint64_t *)d_off;
         cj.len = (const uint32_t *)d_len;
-        cj.n_slices = n_slices;
+        cj.n_slices = j.max_slices;  // the bound; the kernels read the actual count from d_ns
         cj.n_ctx = j.n_ctx;
         cj.ops = (const uint16_t *)d_ops;
         cj.n_ops_max = j.n_ops_max;
@@ -467,20 +564,79 @@ int32_t h264b_stream_decode(h264b_ctx *ctx, const h264b_stream_job *job, h264b_s
         cj.bins_off = (const uint64_t *)d_boff;
         cj.final = (h264b_cabac_final *)d_fin;
         cj.flags = j.flags;
-        RC(launch_cabac(ctx, &cj));
-        RC(ensure_pin(ctx, 3, total_words * 4, &h_bins));
-        RC(ensure_pin(ctx, 4, (size_t)n_slices * sizeof(h264b_cabac_final), &h_fin));
-        RC(ensure_pin(ctx, 5, (size_t)n_slices * 4, &h_snal));
-        H264B_CUDA(ctx, cudaMemcpyAsync(h_bins, d_bins, total_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        H264B_CUDA(ctx, cudaMemcpyAsync(h_fin, d_fin, (size_t)n_slices * sizeof(h264b_cabac_final), cudaMemcpyDeviceToHost, ctx->stream));
-        H264B_CUDA(ctx, cudaMemcpyAsync(h_snal, d_snal, (size_t)n_slices * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        res->bins = (const uint32_t *)h_bins;
-        res->final = (const h264b_cabac_final *)h_fin;
-        res->slice_nal = (const uint32_t *)h_snal;
+        RC(launch_cabac(ctx, &cj, d_ns));
     }
-    H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    H264B_CUDA(ctx, cudaEventRecord(sl->e_compute, cs));
+
+    // 3. results: device -> host on the copy-out stream (overlaps the kernels of the job after)
+    H264B_CUDA(ctx, cudaStreamWaitEvent(out, sl->e_compute, 0));
+    if (ctx->trace) cudaEventRecord(sl->t_o0, out);
+    H264B_CUDA(ctx, cudaMemcpyAsync(h_sum, d_sum, 128, cudaMemcpyDeviceToHost, out));
+    H264B_CUDA(ctx, cudaMemcpyAsync(h_nals, d_nals, nal_prefix * sizeof(h264b_nal), cudaMemcpyDeviceToHost, out));
+    if (j.max_slices) {
+        if (total_words) H264B_CUDA(ctx, cudaMemcpyAsync(h_bins, d_bins, total_words * 4, cudaMemcpyDeviceToHost, out));
+        H264B_CUDA(ctx, cudaMemcpyAsync(h_fin, d_fin, ms * sizeof(h264b_cabac_final), cudaMemcpyDeviceToHost, out));
+        H264B_CUDA(ctx, cudaMemcpyAsync(h_snal, d_snal, ms * 4, cudaMemcpyDeviceToHost, out));
+    }
+    H264B_CUDA(ctx, cudaEventRecord(sl->e_out, out));
+    sl->job = j;
+    sl->nal_cap = cap;
+    sl->nal_prefix = nal_prefix;
+    sl->total_words = total_words;
+    sl->busy = true;
+    sl->ticket = ctx->next_ticket;
+    *ticket = ctx->next_ticket++;
+    return H264B_OK;
+}
+
+int32_t h264b_stream_wait(h264b_ctx *ctx, uint64_t ticket, h264b_stream_result *res) {
+    CHECK_CTX(ctx);
+    if (!res) return H264B_E_INVALID;
+    StreamSlot *sl = ctx->slot[ticket & 1];
+    if (!sl->busy || sl->ticket != ticket) return set_error(ctx, H264B_E_INVALID, "stream_wait: unknown ticket");
+    H264B_CUDA(ctx, cudaEventSynchronize(sl->e_out));
+    sl->busy = false;
+    if (ctx->trace) {
+        float a = 0, b = 0, c = 0, d = 0, e = 0, f = 0;
+        cudaEventElapsedTime(&a, ctx->t_ref, sl->t_in0);
+        cudaEventElapsedTime(&b, ctx->t_ref, sl->e_in);
+        cudaEventElapsedTime(&c, ctx->t_ref, sl->t_c0);
+        cudaEventElapsedTime(&d, ctx->t_ref, sl->e_compute);
+        cudaEventElapsedTime(&e, ctx->t_ref, sl->t_o0);
+        cudaEventElapsedTime(&f, ctx->t_ref, sl->e_out);
+        fprintf(stderr, "h264b trace: job %llu  H2D %.1f..%.1f  kernels %.1f..%.1f  D2H %.1f..%.1f ms\n",
+                (unsigned long long)ticket, a, b, c, d, e, f);
+    }
+    memset(res, 0, sizeof(*res));
+    memcpy(&res->scan, sl->h[5], sizeof(res->scan));
+    if (res->scan.status != H264B_OK)
+        return set_error(ctx, H264B_E_CAPACITY, "stream: more NAL units (%llu) than the index holds (%u)",
+                         (unsigned long long)res->scan.n_nals, sl->nal_cap);
+    uint32_t n_slices = *(const uint32_t *)((const uint8_t *)sl->h[5] + 64);
+    if (n_slices > sl->job.max_slices) n_slices = sl->job.max_slices;
+    void *h_nals = sl->h[0];
+    const size_t nn = (size_t)res->scan.n_nals;
+    if (nn > sl->nal_prefix) {  // more NAL units than the prefix copied with the job: fetch the whole index now (this
+        // queues behind whatever the copy-out stream is doing for the next job)
+        RC(slot_pin(ctx, sl, 0, nn * sizeof(h264b_nal), &h_nals));
+        H264B_CUDA(ctx, cudaMemcpyAsync(h_nals, sl->d[2], nn * sizeof(h264b_nal), cudaMemcpyDeviceToHost, ctx->s_out));
+        H264B_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+        sl->nal_prefix = nn;
+    }
+    res->nals = (const h264b_nal *)h_nals;
+    res->n_slices = n_slices;
+    res->bins_off = (const uint64_t *)sl->h[1];
+    res->bins = (const uint32_t *)sl->h[2];
+    res->final = (const h264b_cabac_final *)sl->h[3];
+    res->slice_nal = (const uint32_t *)sl->h[4];
     for (uint32_t s = 0; s < n_slices; s++) res->total_bins += res->final[s].n_bins;
     return H264B_OK;
+}
+
+int32_t h264b_stream_decode(h264b_ctx *ctx, const h264b_stream_job *job, h264b_stream_result *res) {
+    uint64_t ticket;
+    RC(h264b_stream_submit(ctx, job, &ticket));
+    return h264b_stream_wait(ctx, ticket, res);
 }
 
 }  // extern "C"

@@ -24,6 +24,7 @@ struct CabacArgs {
     const uint64_t *tab;   // 128-entry engine table
     const uint8_t *lut;    // K4 state LUT [5][52][1024]
     const uint32_t *order; // slices sorted by length (longest first) or NULL: lane -> slice = order[index]
+    const uint32_t *d_n;   // actual slice count on the device (<= j.n_slices, which then is only the bound) or NULL
     uint32_t lanes_per_warp;
     uint32_t n_warps;
 };
@@ -44,7 +45,9 @@ __device__ __forceinline__ uint32_t len_bucket(uint32_t ops, uint32_t lo, uint32
     return (uint32_t)(((uint64_t)(hi - ops) * kLenBuckets) / span);
 }
 
-__global__ void __launch_bounds__(256) sort_minmax_kernel(const uint32_t *n_ops, uint32_t n, uint32_t cap, SortScratch *s) {
+__global__ void __launch_bounds__(256) sort_minmax_kernel(const uint32_t *n_ops, uint32_t n, const uint32_t *d_n, uint32_t cap,
+                                                          SortScratch *s) {
+    if (d_n && *d_n < n) n = *d_n;
     uint32_t lo = 0xFFFFFFFFu, hi = 0;
     for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
         const uint32_t v = n_ops[i] < cap ? n_ops[i] : cap;
@@ -59,7 +62,9 @@ __global__ void __launch_bounds__(256) sort_minmax_kernel(const uint32_t *n_ops,
     }
 }
 
-__global__ void __launch_bounds__(256) sort_hist_kernel(const uint32_t *n_ops, uint32_t n, uint32_t cap, SortScratch *s) {
+__global__ void __launch_bounds__(256) sort_hist_kernel(const uint32_t *n_ops, uint32_t n, const uint32_t *d_n, uint32_t cap,
+                                                          SortScratch *s) {
+    if (d_n && *d_n < n) n = *d_n;
     const uint32_t lo = s->min_ops, hi = s->max_ops;
     for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
         atomicAdd(&s->hist[len_bucket(n_ops[i] < cap ? n_ops[i] : cap, lo, hi)], 1u);
@@ -84,8 +89,9 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(SortScratch *s) {  // e
     s->hist[2 * tid + 1] = excl + a;
 }
 
-__global__ void __launch_bounds__(256) sort_scatter_kernel(const uint32_t *n_ops, uint32_t n, uint32_t cap, SortScratch *s,
-                                                           uint32_t *order) {
+__global__ void __launch_bounds__(256) sort_scatter_kernel(const uint32_t *n_ops, uint32_t n, const uint32_t *d_n, uint32_t cap,
+                                                           SortScratch *s, uint32_t *order) {
+    if (d_n && *d_n < n) n = *d_n;
     const uint32_t lo = s->min_ops, hi = s->max_ops;
     for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
         order[atomicAdd(&s->hist[len_bucket(n_ops[i] < cap ? n_ops[i] : cap, lo, hi)], 1u)] = i;
@@ -108,8 +114,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
     const uint32_t gw = blockIdx.x * kWarpsPerCta + warp;
     if (gw >= a.n_warps) return;
     const uint32_t index = gw * a.lanes_per_warp + lane;
-    const bool valid = lane < (int)a.lanes_per_warp && index < j.n_slices;
-    const uint32_t slice = valid && a.order ? a.order[index] : index;
+    const uint32_t n_slices = a.d_n && *a.d_n < j.n_slices ? *a.d_n : j.n_slices;
+    if (gw * a.lanes_per_warp >= n_slices) return;
+    // Lanes without a slice of their own (a partly filled warp) shadow the warp's first lane: they decode the same
+    // slice and store nothing, so the loops below never have to predicate on "is there a slice in this lane".
+    const bool own = lane < (int)a.lanes_per_warp && index < n_slices;
+    const bool valid = true;
+    const uint32_t src_index = own ? index : gw * a.lanes_per_warp;
+    const uint32_t slice = a.order ? a.order[src_index] : src_index;
 
     // ---- per-lane setup
     uint32_t my_ops = 0;
@@ -141,8 +153,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
 #pragma unroll
     for (int d = 16; d; d >>= 1) warp_ops = max(warp_ops, __shfl_xor_sync(0xFFFFFFFFu, warp_ops, d));
 
-    uint32_t *bins = valid ? j.bins + (j.bins_off ? (size_t)j.bins_off[slice] : (size_t)slice * j.bins_stride_words)
-                           : nullptr;
+    uint32_t *bins = j.bins + (j.bins_off ? (size_t)j.bins_off[slice] : (size_t)slice * j.bins_stride_words);
     uint32_t word = 0;
     uint32_t i = 0;
     // ---- fast loop: blocks of 32 ops (one word of bins) while every lane of the warp is active and on the window
@@ -199,7 +210,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
             }
             i += k;
             if (k == 32u) {
-                bins[(i >> 5) - 1u] = word;
+                if (own) bins[(i >> 5) - 1u] = word;
                 word = 0;
             } else {
                 word >>= 32u - k;  // a partial block: bins 0..k-1 in bits 0..k-1, the generic loop goes on from there
@@ -235,13 +246,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
         if (active) {  // a lane that has finished keeps its last partial word for the tail below
             word |= bin << (i & 31u);
             if ((i & 31u) == 31u) {
-                bins[i >> 5] = word;
+                if (own) bins[i >> 5] = word;
                 word = 0;
             }
         }
     }
     // ---- tail: optional final DecodeTerminate, flush, final record
-    if (valid) {
+    if (own) {
         uint32_t n_bins = my_ops;
         if (j.flags & H264B_CABAC_FINAL_TERMINATE) {
             if (eng.must_refill()) eng.refill_if_room();
@@ -266,7 +277,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
     }
 }
 
-int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job) {
+int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n_slices) {
     const h264b_cabac_job &j = *job;
     if (j.n_ctx < 1 || j.n_ctx > 1024) return set_error(ctx, H264B_E_INVALID, "cabac: n_ctx must be 1..1024");
     if (!j.n_slices) return H264B_OK;
@@ -283,13 +294,14 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job) {
     a.lut = ctx->d_state_lut[v];
     // Few slices: spread them one (or a few) per warp so every slice gets its own scheduler slot and no lane waits on
     // a neighbour's bank conflict; many slices: 32 per warp.
-    const uint32_t target_warps = (uint32_t)ctx->sm_count * 8;
+    const uint32_t target_warps = (uint32_t)ctx->sm_count * 4;  // one warp per scheduler before lanes are doubled up
     uint32_t lpw = (j.n_slices + target_warps - 1) / target_warps;
     if (lpw < 1) lpw = 1;
     if (lpw > 32) lpw = 32;
     a.lanes_per_warp = lpw;
     a.n_warps = (j.n_slices + lpw - 1) / lpw;
     a.order = nullptr;
+    a.d_n = d_n_slices;
     if (lpw > 1 && j.n_ops) {  // bundles of equally long slices
         void *d_sort;
         int rc = ensure_dev(ctx, 16, sizeof(SortScratch) + (size_t)j.n_slices * 4, &d_sort);
@@ -300,13 +312,13 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job) {
         H264B_CUDA(ctx, cudaMemsetAsync(&ss->min_ops, 0xFF, 4, ctx->stream));
         const int sb = (int)((j.n_slices + 255) / 256 < (uint32_t)ctx->sm_count * 4 ? (j.n_slices + 255) / 256
                                                                                    : (uint32_t)ctx->sm_count * 4);
-        sort_minmax_kernel<<<sb, 256, 0, ctx->stream>>>(j.n_ops, j.n_slices, j.n_ops_max, ss);
+        sort_minmax_kernel<<<sb, 256, 0, ctx->stream>>>(j.n_ops, j.n_slices, d_n_slices, j.n_ops_max, ss);
         H264B_LAUNCH_CHECK(ctx, "sort_minmax_kernel");
-        sort_hist_kernel<<<sb, 256, 0, ctx->stream>>>(j.n_ops, j.n_slices, j.n_ops_max, ss);
+        sort_hist_kernel<<<sb, 256, 0, ctx->stream>>>(j.n_ops, j.n_slices, d_n_slices, j.n_ops_max, ss);
         H264B_LAUNCH_CHECK(ctx, "sort_hist_kernel");
         sort_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ss);
         H264B_LAUNCH_CHECK(ctx, "sort_scan_kernel");
-        sort_scatter_kernel<<<sb, 256, 0, ctx->stream>>>(j.n_ops, j.n_slices, j.n_ops_max, ss, order);
+        sort_scatter_kernel<<<sb, 256, 0, ctx->stream>>>(j.n_ops, j.n_slices, d_n_slices, j.n_ops_max, ss, order);
         H264B_LAUNCH_CHECK(ctx, "sort_scatter_kernel");
         a.order = order;
     }

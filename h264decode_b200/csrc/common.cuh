@@ -7,6 +7,7 @@
 
 #include "../../include/h264b200.h"
 
+struct StreamSlot;
 struct h264b_ctx {
     int device;
     int sm_count;
@@ -31,6 +32,29 @@ struct h264b_ctx {
     size_t h_pin_bytes[8];
     void *d_buf[20];
     size_t d_buf_bytes[20];
+
+    // h264b_stream_submit / h264b_stream_wait: two jobs in flight, each with its own buffers and events
+    cudaStream_t s_in, s_out;  // copy streams (host -> device, device -> host)
+    struct StreamSlot *slot[2];
+    uint64_t next_ticket;
+    cudaEvent_t t_ref;  // H264B_TRACE=1: time origin
+    int trace;
+};
+
+enum { kSlotDev = 14, kSlotPin = 9 };
+struct StreamSlot {
+    void *d[kSlotDev];
+    size_t d_bytes[kSlotDev];
+    void *h[kSlotPin];
+    size_t h_bytes[kSlotPin];
+    cudaEvent_t e_in, e_compute, e_out;
+    cudaEvent_t t_in0, t_c0, t_o0;  // H264B_TRACE=1: phase starts (timing events)
+    uint64_t ticket;     // job occupying the slot
+    bool busy;           // submitted, not yet waited for
+    h264b_stream_job job;
+    uint32_t nal_cap;
+    size_t nal_prefix;   // NAL records copied out with the job (the rest, if any, is fetched by h264b_stream_wait)
+    size_t total_words;
 };
 
 namespace h264b {
@@ -65,7 +89,7 @@ int launch_nal_frames(h264b_ctx *ctx, const uint8_t *d_frames, uint64_t total, c
                       uint8_t *d_rbsp);
 int launch_ctx_init(h264b_ctx *ctx, const h264b_slice_qp *d_params, uint32_t n_slices, uint32_t n_ctx,
                     uint8_t *d_states, uint32_t flags);
-int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job);
+int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n_slices = nullptr);
 int launch_slice_select(h264b_ctx *ctx, const h264b_nal *d_nals, const h264b_scan_summary *d_summary,
                         uint32_t nal_cap, uint32_t slice_data_offset, uint32_t max_slices, uint64_t *d_off,
                         uint32_t *d_len, uint32_t *d_slice_nal, uint32_t *d_n_slices);

@@ -402,3 +402,44 @@ def test_stream_decode_matches_oracle_pipeline(ctx, capi):
     for i in range(len(sl)):   # and the decoded bins are the ones the encoder coded
         nw = (int(b["n_ops"][i]) + 1) // 32
         assert np.array_equal(r["bins"][i][:nw], b["bins"][i, :nw])
+
+
+def test_stream_submit_wait_two_jobs_in_flight(ctx, capi):
+    """h264b_stream_submit / h264b_stream_wait: jobs overlap (two in flight), results stay per job and match the
+    oracle; a third submit without a wait is refused; max_slices larger than the slices the stream holds is fine"""
+    flags = capi.BYPASS_SPEC_OR | capi.CABAC_FINAL_TERMINATE
+    jobs = [hz.build_stream_cabac(n, 1500 + 100 * k, n_active=64, n_ctx=64, slices_per_frame=4, frames_per_params=3,
+                                  id_base=7000 * k) for k, n in enumerate([40, 9, 64, 1, 33])]
+
+    def check(b, r):
+        onal, orbsp = orc.read_nal_units_arrays(b["stream"])
+        assert r["scan"]["n_nals"] == len(onal["start"])
+        assert np.array_equal(r["nals"]["start"].astype(np.int64), onal["start"])
+        sl = np.flatnonzero((onal["type"] == 1) | (onal["type"] == 5))
+        assert np.array_equal(r["slice_nal"].astype(np.int64), sl)
+        init = orc.ctx_init(b["qp"], b["idc"], b["n_ctx"])
+        exp = oracle_decode_all(orbsp, onal["rbsp_off"][sl].astype(np.uint64), onal["rbsp_len"][sl].astype(np.uint32),
+                                b["ops"], b["n_ops"], init, orc.BYPASS_SPEC_OR, True)
+        compare_cabac(capi, r["bins"], r["final"], None, exp, b["n_ops"], True)
+        assert r["total_bins"] == int(b["n_ops"][:len(sl)].sum()) + len(sl)
+
+    def submit(b, extra=0):
+        qp = np.concatenate([b["qp"], np.full(extra, 26, np.int32)])
+        idc = np.concatenate([b["idc"], np.zeros(extra, np.int32)])
+        n_ops = np.concatenate([b["n_ops"], np.full(extra, 10, np.uint32)])
+        return ctx.stream_submit(b["stream"], b["ops"], n_ops, qp, idc, b["n_ctx"], flags=flags)
+
+    t0 = submit(jobs[0])
+    t1 = submit(jobs[1], extra=5)
+    with pytest.raises(capi.H264BError):
+        submit(jobs[2])
+    check(jobs[0], ctx.stream_wait(*t0))
+    t2 = submit(jobs[2])
+    check(jobs[1], ctx.stream_wait(*t1))
+    t3 = submit(jobs[3], extra=2)
+    check(jobs[2], ctx.stream_wait(*t2))
+    t4 = submit(jobs[4])
+    check(jobs[3], ctx.stream_wait(*t3))
+    check(jobs[4], ctx.stream_wait(*t4))
+    with pytest.raises(capi.H264BError):
+        ctx.stream_wait(*t4)
