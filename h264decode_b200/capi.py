@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libh264b200.so")
 
 OK, E_INVALID, E_CUDA, E_NOMEM, E_CAPACITY, E_NO_DEVICE = range(6)
-TABLES_SPEC, BYPASS_SPEC_OR, CABAC_FINAL_TERMINATE = 1, 2, 4
+TABLES_SPEC, BYPASS_SPEC_OR, CABAC_FINAL_TERMINATE, STREAM_WANT_RBSP = 1, 2, 4, 8
 F_OVERRUN, F_HAS_EPB, F_SHORT_NAL = 1, 2, 4
 OP_DECISION, OP_BYPASS, OP_TERMINATE = 0, 1, 2
 
@@ -66,7 +66,7 @@ class StreamJob(C.Structure):
 class StreamResult(C.Structure):
     _fields_ = [("scan", ScanSummary), ("nals", C.c_void_p), ("n_slices", C.c_uint32), ("reserved", C.c_uint32),
                 ("slice_nal", C.c_void_p), ("bins_off", C.c_void_p), ("bins", C.c_void_p), ("final", C.c_void_p),
-                ("total_bins", C.c_uint64)]
+                ("total_bins", C.c_uint64), ("rbsp", C.c_void_p), ("d_rbsp", C.c_void_p), ("ext", C.c_void_p)]
 
 
 class H264BError(RuntimeError):

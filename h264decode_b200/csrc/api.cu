@@ -426,8 +426,9 @@ int32_t h264b_cabac_decode(h264b_ctx *ctx, const h264b_cabac_job *job) {
 
 // ---- the whole front end of one stream, asynchronously: two jobs in flight per context -------------------------
 // device buffers of a slot: 0 stream  1 rbsp  2 nals  3 summary + slice count  4 off  5 len  6 slice_nal  7 ops
-//                           8 n_ops  9 qp  10 bins_off  11 bins  12 final
+//                           8 n_ops  9 qp  10 bins_off  11 bins  12 final  13 ext
 // pinned buffers of a slot: 0 nals  1 bins_off  2 bins  3 final  4 slice_nal  5 summary + slice count
+//                           9 rbsp  10 ext (H264B_STREAM_WANT_RBSP)
 //                           6 ops  7 n_ops  8 qp (staging of the caller's small arrays: they may be pageable, and a
 //                           pageable source would make the copies -- and with them the whole submit -- synchronous)
 static int slot_dev(h264b_ctx *ctx, StreamSlot *sl, int i, size_t bytes, void **out) {
@@ -469,7 +470,7 @@ int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_
     CHECK_CTX(ctx);
     if (!job || !ticket) return H264B_E_INVALID;
     const h264b_stream_job &j = *job;
-    if ((!j.stream && j.n) || !j.qp || (!j.ops && j.n_ops_max))
+    if ((!j.stream && j.n) || (j.max_slices && (!j.qp || (!j.ops && j.n_ops_max))))
         return set_error(ctx, H264B_E_INVALID, "stream_submit: null pointer in job");
     StreamSlot *sl = ctx->slot[ctx->next_ticket & 1];
     if (sl->busy) return set_error(ctx, H264B_E_INVALID, "stream_submit: two jobs are in flight, wait for one first");
@@ -523,7 +524,7 @@ int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_
     RC(slot_pin(ctx, sl, 6, (size_t)j.n_ops_max * 2, &h_ops));
     RC(slot_pin(ctx, sl, 7, ms * 4, &h_nops));
     RC(slot_pin(ctx, sl, 8, ms * sizeof(h264b_slice_qp), &h_qp));
-    if (j.n_ops_max) {
+    if (j.n_ops_max && j.max_slices) {
         memcpy(h_ops, j.ops, (size_t)j.n_ops_max * 2);
         H264B_CUDA(ctx, cudaMemcpyAsync(d_ops, h_ops, (size_t)j.n_ops_max * 2, cudaMemcpyHostToDevice, in));
     }
@@ -543,8 +544,10 @@ int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_
     H264B_CUDA(ctx, cudaStreamWaitEvent(cs, sl->e_out, 0));  // (results of the slot's previous job have left)
     if (ctx->trace) cudaEventRecord(sl->t_c0, cs);
     uint32_t *d_ns = (uint32_t *)((uint8_t *)d_sum + 64);
-    RC(launch_annexb_scan(ctx, (const uint8_t *)d_stream, j.n, (uint8_t *)d_rbsp, (h264b_nal *)d_nals, nullptr, cap,
-                          (h264b_scan_summary *)d_sum, j.flags));
+    void *d_ext = nullptr;
+    if (j.flags & H264B_STREAM_WANT_RBSP) RC(slot_dev(ctx, sl, 13, (size_t)cap * sizeof(h264b_nal_ext), &d_ext));
+    RC(launch_annexb_scan(ctx, (const uint8_t *)d_stream, j.n, (uint8_t *)d_rbsp, (h264b_nal *)d_nals,
+                          (h264b_nal_ext *)d_ext, cap, (h264b_scan_summary *)d_sum, j.flags));
     RC(launch_slice_select(ctx, (const h264b_nal *)d_nals, (const h264b_scan_summary *)d_sum, cap, j.slice_data_offset,
                            j.max_slices, (uint64_t *)d_off, (uint32_t *)d_len, (uint32_t *)d_snal, d_ns));
     if (j.max_slices) {
@@ -577,6 +580,13 @@ int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_
         if (total_words) H264B_CUDA(ctx, cudaMemcpyAsync(h_bins, d_bins, total_words * 4, cudaMemcpyDeviceToHost, out));
         H264B_CUDA(ctx, cudaMemcpyAsync(h_fin, d_fin, ms * sizeof(h264b_cabac_final), cudaMemcpyDeviceToHost, out));
         H264B_CUDA(ctx, cudaMemcpyAsync(h_snal, d_snal, ms * 4, cudaMemcpyDeviceToHost, out));
+    }
+    if (j.flags & H264B_STREAM_WANT_RBSP) {  // position-preserving layout: the buffer is as long as the stream
+        void *h_rbsp, *h_ext;
+        RC(slot_pin(ctx, sl, 9, j.n, &h_rbsp));
+        RC(slot_pin(ctx, sl, 10, nal_prefix * sizeof(h264b_nal_ext), &h_ext));
+        if (j.n) H264B_CUDA(ctx, cudaMemcpyAsync(h_rbsp, d_rbsp, j.n, cudaMemcpyDeviceToHost, out));
+        H264B_CUDA(ctx, cudaMemcpyAsync(h_ext, d_ext, nal_prefix * sizeof(h264b_nal_ext), cudaMemcpyDeviceToHost, out));
     }
     H264B_CUDA(ctx, cudaEventRecord(sl->e_out, out));
     sl->job = j;
@@ -620,6 +630,11 @@ int32_t h264b_stream_wait(h264b_ctx *ctx, uint64_t ticket, h264b_stream_result *
         // queues behind whatever the copy-out stream is doing for the next job)
         RC(slot_pin(ctx, sl, 0, nn * sizeof(h264b_nal), &h_nals));
         H264B_CUDA(ctx, cudaMemcpyAsync(h_nals, sl->d[2], nn * sizeof(h264b_nal), cudaMemcpyDeviceToHost, ctx->s_out));
+        if (sl->job.flags & H264B_STREAM_WANT_RBSP) {
+            void *h_ext;
+            RC(slot_pin(ctx, sl, 10, nn * sizeof(h264b_nal_ext), &h_ext));
+            H264B_CUDA(ctx, cudaMemcpyAsync(h_ext, sl->d[13], nn * sizeof(h264b_nal_ext), cudaMemcpyDeviceToHost, ctx->s_out));
+        }
         H264B_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
         sl->nal_prefix = nn;
     }
@@ -630,6 +645,9 @@ int32_t h264b_stream_wait(h264b_ctx *ctx, uint64_t ticket, h264b_stream_result *
     res->final = (const h264b_cabac_final *)sl->h[3];
     res->slice_nal = (const uint32_t *)sl->h[4];
     for (uint32_t s = 0; s < n_slices; s++) res->total_bins += res->final[s].n_bins;
+    res->rbsp = (sl->job.flags & H264B_STREAM_WANT_RBSP) ? (const uint8_t *)sl->h[9] : nullptr;
+    res->d_rbsp = (const uint8_t *)sl->d[1];
+    res->ext = (sl->job.flags & H264B_STREAM_WANT_RBSP) ? (const h264b_nal_ext *)sl->h[10] : nullptr;
     return H264B_OK;
 }
 

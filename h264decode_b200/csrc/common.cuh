@@ -41,7 +41,7 @@ struct h264b_ctx {
     int trace;
 };
 
-enum { kSlotDev = 14, kSlotPin = 9 };
+enum { kSlotDev = 14, kSlotPin = 11 };
 struct StreamSlot {
     void *d[kSlotDev];
     size_t d_bytes[kSlotDev];

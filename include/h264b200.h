@@ -42,6 +42,7 @@ extern "C" {
 #define H264B_TABLES_SPEC 0x1u           /* corrected rangeTabLPS / transIdx / (m,n) tables (A1..A3); default REF */
 #define H264B_BYPASS_SPEC_OR 0x2u        /* DecodeBypass as (O<<1)|bit (A5); default REF: O<<=1 then O<<=bit */
 #define H264B_CABAC_FINAL_TERMINATE 0x4u /* after a slice's n_ops bins decode one more DecodeTerminate bin */
+#define H264B_STREAM_WANT_RBSP 0x8u      /* h264b_stream_*: also copy the RBSP buffer and the extension headers back */
 
 /* per-unit flag bits written by kernels (never abort a batch; SURVEY.md §5 failure handling) */
 #define H264B_F_OVERRUN 0x1u    /* the reference would have panicked reading past the slice's last byte (A10) */
@@ -229,7 +230,7 @@ typedef struct {
     uint32_t n_ops_max;
     const uint32_t *n_ops;        /* [max_slices] or NULL */
     const h264b_slice_qp *qp;     /* [max_slices] */
-    uint32_t max_slices;
+    uint32_t max_slices;          /* 0: split + strip only (no CABAC stage; ops / n_ops / qp are ignored) */
     uint32_t flags;
 } h264b_stream_job;
 
@@ -243,6 +244,9 @@ typedef struct {
     const uint32_t *bins;           /* compact: (n_ops[s] + 1 + 31) / 32 words per slice */
     const h264b_cabac_final *final; /* [n_slices] */
     uint64_t total_bins;
+    const uint8_t *rbsp;            /* job.n bytes, indexed by h264b_nal.rbsp_off (H264B_STREAM_WANT_RBSP), else NULL */
+    const uint8_t *d_rbsp;          /* the same buffer on the device (for follow-up h264b_*_dev calls) */
+    const h264b_nal_ext *ext;       /* [scan.n_nals] (H264B_STREAM_WANT_RBSP), else NULL */
 } h264b_stream_result;
 
 int32_t h264b_stream_decode(h264b_ctx *ctx, const h264b_stream_job *job, h264b_stream_result *result);

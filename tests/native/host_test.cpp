@@ -1,0 +1,117 @@
+// host_test.cpp -- drives host/h264.hpp (the C++ mirror of the reference's Go API over the C ABI) and prints what it
+// gets as text; tests/test_host_cpp.py (GPU) builds it with g++, runs it and compares with the oracle.
+// Test infrastructure: not part of the product.
+#include <fcntl.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <fstream>
+#include <thread>
+
+#include "../../host/h264.hpp"
+
+static std::vector<uint8_t> slurp(const char *path) {
+    std::ifstream f(path, std::ios::binary);
+    return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+static uint64_t fnv(const std::vector<uint8_t> &v) {
+    uint64_t h = 1469598103934665603ull;
+    for (uint8_t b : v) h = (h ^ b) * 1099511628211ull;
+    return h;
+}
+static void print_nal(const h264::NalUnit &u) {
+    printf("nal %llu %d %d %d %d %d %zu %016llx %d %d %d %d %d %d %d\n", (unsigned long long)u.startOffset, u.NumBytes,
+           u.ForbiddenZeroBit, u.RefIdc, u.Type, u.HeaderBytes, u.RBSP().size(), (unsigned long long)fnv(u.RBSP()),
+           (int)u.EmulationPreventionThreeByte, u.SvcExtensionFlag, u.Avc3dExtensionFlag, u.PriorityId, u.ViewId,
+           u.TemporalId, u.ViewIdx);
+}
+
+int main(int argc, char **argv) {
+    if (argc < 2) return 2;
+    const std::string mode = argv[1];
+    try {
+        if (mode == "nals") {  // readNalUnit loop over a whole buffer
+            const auto s = slurp(argv[2]);
+            for (const auto &u : h264::ReadNalUnits(s.data(), s.size())) print_nal(u);
+        } else if (mode == "ingest") {  // the same stream through a pipe in odd-sized writes, batched ingest
+            const auto s = slurp(argv[2]);
+            const size_t batch = strtoull(argv[3], nullptr, 10), chunk = strtoull(argv[4], nullptr, 10),
+                         room = strtoull(argv[5], nullptr, 10);
+            int fds[2];
+            if (pipe(fds)) return 3;
+            std::thread writer([&] {
+                size_t off = 0, k = 0;
+                while (off < s.size()) {
+                    size_t n = chunk + (k++ % 7) * 13;  // ragged writes
+                    if (n > s.size() - off) n = s.size() - off;
+                    const ssize_t w = write(fds[1], s.data() + off, n);
+                    if (w <= 0) break;
+                    off += (size_t)w;
+                }
+                close(fds[1]);
+            });
+            h264::ByteStreamReader reader(h264::Device::Default(), batch, room);
+            const uint64_t n = reader.Run(fds[0], [](const h264::NalUnit &u) { print_nal(u); });
+            writer.join();
+            close(fds[0]);
+            printf("units %llu\n", (unsigned long long)n);
+        } else if (mode == "frame") {  // NewNalUnit(frame, len(frame)); a Go panic prints "panic"
+            const auto f = slurp(argv[2]);
+            try {
+                print_nal(h264::NewNalUnit(f.data(), (int)f.size()));
+            } catch (const h264::Panic &) {
+                printf("panic\n");
+            }
+        } else if (mode == "ctx") {  // PreCtxState / MNVars / InitContexts
+            for (int i = 2; i + 2 < argc; i += 3)
+                printf("pre %d\n", h264::PreCtxState(atoi(argv[i]), atoi(argv[i + 1]), atoi(argv[i + 2])));
+            for (int c : {0, 5, 10, 11, 39, 40, 70, 104, 105, 1023})
+                for (int idc : {-1, 0, 1, 2, 3}) {
+                    const h264::MN mn = h264::MNVars(c, idc);
+                    printf("mn %d %d %d %d\n", c, idc, mn.M, mn.N);
+                }
+            const auto st = h264::InitContexts({26, 0, 51, 30}, {0, -1, 2, 1}, 128);
+            printf("init %016llx %d %d\n", (unsigned long long)fnv(st), h264::SliceQPy(-3, 5), h264::Clip3(0, 51, 77));
+        } else if (mode == "engine") {  // the per-call engine methods on a bit string given as a byte file
+            const auto bytes = slurp(argv[2]);
+            h264::BitReader br;
+            br.bytes = bytes.data();
+            br.n = bytes.size();
+            h264::ArithmeticDecoding ad;
+            ad.bits = &br;
+            auto ro = ad.InitDecodingEngine();
+            int64_t R = ro.first, O = ro.second;
+            printf("init %lld %lld %llu\n", (long long)R, (long long)O, (unsigned long long)br.bitsRead);
+            h264::CABAC c;
+            c.PStateIdx = 20;
+            c.ValMPS = 1;
+            for (int i = 0; i < 24; i++) {
+                int bin;
+                if (i % 5 == 3) {
+                    auto r = ad.DecodeBypass(R, O);  // REF form (A5)
+                    O = r.first;
+                    bin = r.second;
+                } else if (i % 11 == 10) {
+                    auto r = ad.DecodeTerminate(R, O);
+                    R = std::get<0>(r);
+                    O = std::get<1>(r);
+                    bin = std::get<2>(r);
+                } else {
+                    bin = ad.DecodeDecision(c, R, O);
+                }
+                printf("step %d %d %lld %lld %d %d %llu\n", i, bin, (long long)R, (long long)O, c.PStateIdx, c.ValMPS,
+                       (unsigned long long)br.bitsRead);
+            }
+            auto bd = ad.BinaryDecision(c, R, O);  // bare core: no transition, no renorm
+            printf("core %d %lld %lld\n", std::get<0>(bd), (long long)std::get<1>(bd), (long long)std::get<2>(bd));
+            c.StateTransitionProcess(1 - c.ValMPS);
+            printf("trans %d %d\n", c.PStateIdx, c.ValMPS);
+        } else {
+            return 2;
+        }
+    } catch (const std::exception &e) {
+        printf("error %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

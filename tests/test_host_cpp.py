@@ -1,0 +1,162 @@
+"""The C++ host layer (host/h264.hpp: the reference's Go API re-stated over the C ABI) driven by
+tests/native/host_test.cpp.  CPU: it builds, links against the library and refuses to run without a GPU.  GPU: NAL
+units (whole buffer, batched ingest through a pipe, single frames), context init and the per-call engine methods
+against the oracle."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import harness as hz
+from oracle import oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "native", "host_test.cpp")
+EXE = os.path.join(HERE, "native", "_build", "host_test")
+
+
+@pytest.fixture(scope="module")
+def exe():
+    from h264decode_b200 import build
+    build.build()
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    deps = [SRC, os.path.join(ROOT, "host", "h264.hpp"), os.path.join(ROOT, "include", "h264b200.h")]
+    if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", SRC, "-o", EXE, "-L" + os.path.join(ROOT, "h264decode_b200"),
+                               "-lh264b200", "-Wl,-rpath,$ORIGIN/../../../h264decode_b200", "-lpthread"])
+    return EXE
+
+
+def run(exe, *args):
+    p = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=300)
+    return p.returncode, [l.split() for l in p.stdout.splitlines()]
+
+
+def fnv(b):
+    h = 1469598103934665603
+    for x in bytes(b):
+        h = ((h ^ x) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def test_host_layer_builds_and_has_no_cpu_path(exe):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    rc, out = run(exe, "ctx", 1, 2, 3)
+    assert rc == 1 and out[0][0] == "error" and "status" in out[0]
+
+
+def expect_nal_lines(stream):
+    nal, rbsp = orc.read_nal_units_arrays(stream)
+    f = {name: i for i, name in enumerate(orc._NAL_FIELDS)}
+    lines = []
+    for k in range(len(nal["start"])):
+        rb = rbsp[int(nal["rbsp_off"][k]):int(nal["rbsp_off"][k]) + int(nal["rbsp_len"][k])]
+        fl = nal["fields"][k]
+        lines.append(["nal", str(int(nal["start"][k])), str(int(nal["num_bytes"][k])), str(int(nal["fzb"][k])),
+                      str(int(nal["ref_idc"][k])), str(int(nal["type"][k])), str(int(nal["header_bytes"][k])), str(len(rb)),
+                      "%016x" % fnv(rb), str(int(nal["epb"][k])), str(int(fl[f["SvcExtensionFlag"]])),
+                      str(int(fl[f["Avc3dExtensionFlag"]])), str(int(fl[f["PriorityId"]])), str(int(fl[f["ViewId"]])),
+                      str(int(fl[f["TemporalId"]])), str(int(fl[f["ViewIdx"]]))])
+    return lines
+
+
+def make_stream(tmp_path, n=300000, seed=3):
+    from tests.test_hd_logic import random_stream
+    rng = np.random.default_rng(seed)
+    parts = [hz.build_stream_c1(n // 2), random_stream(rng, n // 4, 0.3, 0.003, ext_types=True),
+             hz.build_stream_cabac(24, 1500, slices_per_frame=4, frames_per_params=2)["stream"]]
+    s = np.concatenate(parts)
+    path = os.path.join(str(tmp_path), "stream.bin")
+    s.tofile(path)
+    return s, path
+
+
+@pytest.mark.gpu
+def test_read_nal_units_whole_buffer(exe, tmp_path):
+    s, path = make_stream(tmp_path)
+    rc, out = run(exe, "nals", path)
+    assert rc == 0
+    assert out == expect_nal_lines(s)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch,chunk,room", [(65536, 4000, 1 << 20), (10007, 333, 4096), (1 << 20, 65536, 1 << 20),
+                                              (3001, 17, 64)])
+def test_batched_ingest_through_a_pipe(exe, tmp_path, batch, chunk, room):
+    """handleConnection as modified: the same NAL units, same absolute offsets, whatever the batch / read sizes;
+    NAL units larger than a batch and than the carry room included"""
+    s, path = make_stream(tmp_path, n=120000 if batch < 20000 else 300000)
+    rc, out = run(exe, "ingest", path, batch, chunk, room)
+    assert rc == 0, out[-3:]
+    exp = expect_nal_lines(s)
+    assert out[-1] == ["units", str(len(exp))]
+    assert out[:-1] == exp
+
+
+@pytest.mark.gpu
+def test_new_nal_unit_single_frames(exe, tmp_path):
+    for i, hexs in enumerate(["67 42 00 00 03 01 AA BB 00 00 00 01", "65 11 22 00 00 03 44", "6E 80 00 00 00 03 55 66 77 88",
+                              "75 FF 80 AA BB CC DD", "65", "74 C5 A6"]):
+        f = bytes.fromhex(hexs)
+        path = os.path.join(str(tmp_path), "f%d.bin" % i)
+        open(path, "wb").write(f)
+        rc, out = run(exe, "frame", path)
+        st, o, rb = orc.new_nal_unit(f)
+        if st == orc.PANIC:
+            assert out == [["panic"]]
+            continue
+        assert rc == 0
+        assert out[0][2:9] == [str(o["NumBytes"]), str(o["ForbiddenZeroBit"]), str(o["RefIdc"]), str(o["Type"]),
+                               str(o["HeaderBytes"]), str(len(rb)), "%016x" % fnv(rb)]
+
+
+@pytest.mark.gpu
+def test_ctx_functions(exe):
+    triples = [(20, -15, 0), (-28, 127, 26), (57, 2, 51), (0, 0, 99), (-4, 127, -5)]
+    rc, out = run(exe, "ctx", *[x for t in triples for x in t])
+    assert rc == 0
+    pre = [l for l in out if l[0] == "pre"]
+    assert [int(l[1]) for l in pre] == [orc.pre_ctx_state(*t) for t in triples]
+    for l in out:
+        if l[0] == "mn":
+            assert (int(l[3]), int(l[4])) == orc.mn(int(l[1]), int(l[2])), l
+    init = [l for l in out if l[0] == "init"][0]
+    st = orc.ctx_init(np.array([26, 0, 51, 30], np.int32), np.array([0, -1, 2, 1], np.int32), 128)
+    assert init[1] == "%016x" % fnv(st.tobytes()) and init[2:] == ["28", "51"]
+
+
+@pytest.mark.gpu
+def test_engine_methods_per_call(exe, tmp_path):
+    """InitDecodingEngine / DecodeDecision / DecodeBypass (REF form) / DecodeTerminate / BinaryDecision /
+    StateTransitionProcess, one call at a time on a shared BitReader, like the Go methods"""
+    rng = np.random.default_rng(12)
+    data = rng.integers(0, 256, 64).astype(np.uint8)
+    path = os.path.join(str(tmp_path), "bits.bin")
+    data.tofile(path)
+    rc, out = run(exe, "engine", path)
+    assert rc == 0, out
+    L = orc.lib()
+    bits = orc.Bits(data)
+    R, O = C.c_int64(0), C.c_int64(0)
+    L.orc_init_decoding_engine(C.byref(bits.br), C.byref(R), C.byref(O))
+    assert out[0] == ["init", str(R.value), str(O.value), str(bits.bits_read)]
+    state = np.array([20 | (1 << 6)], np.uint8)
+    for i in range(24):
+        b = C.c_int64(0)
+        if i % 5 == 3:
+            L.orc_decode_bypass(0, C.byref(bits.br), R.value, C.byref(O), C.byref(b))
+        elif i % 11 == 10:
+            L.orc_decode_terminate(C.byref(bits.br), C.byref(R), C.byref(O), C.byref(b))
+        else:
+            L.orc_decode_decision(0, C.byref(bits.br), state.ctypes.data, C.byref(R), C.byref(O), C.byref(b))
+        assert out[1 + i] == ["step", str(i), str(b.value), str(R.value), str(O.value), str(int(state[0] & 63)),
+                              str(int(state[0] >> 6)), str(bits.bits_read)], i
+    bv, r2, o2 = orc.binary_decision(int(state[0] & 63), int(state[0] >> 6), R.value, O.value)
+    assert out[25] == ["core", str(bv), str(r2), str(o2)]
+    p2, v2 = orc.state_transition(int(state[0] & 63), int(state[0] >> 6), 1 - int(state[0] >> 6))
+    assert out[26] == ["trans", str(p2), str(v2)]
