@@ -24,6 +24,7 @@ SYMBOLS = [
     "h264b_annexb_scan", "h264b_nal_units", "h264b_ctx_init_dev", "h264b_ctx_init", "h264b_pre_ctx_state", "h264b_mn",
     "h264b_cabac_decode_dev", "h264b_cabac_decode", "h264b_engine_step", "h264b_binary_decision",
     "h264b_state_transition", "h264b_stream_decode", "h264b_stream_submit", "h264b_stream_wait",
+    "h264b_slice_headers_dev", "h264b_slice_headers",
     "h264b_slice_select_dev",
 ]
 
@@ -69,6 +70,35 @@ class StreamResult(C.Structure):
                 ("total_bins", C.c_uint64), ("rbsp", C.c_void_p), ("d_rbsp", C.c_void_p), ("ext", C.c_void_p)]
 
 
+PARAM_SET_FIELDS = ["use_separate_color_plane", "chroma_format", "frame_mbs_only", "pic_order_count_type",
+                    "log2_max_pic_order_cnt_lsb_min4", "delta_pic_order_always_zero",
+                    "bottom_field_pic_order_in_frame_present", "redundant_pic_cnt_present", "weighted_pred",
+                    "weighted_bipred", "entropy_coding_mode", "deblocking_filter_control_present",
+                    "num_slice_groups_minus1", "slice_group_map_type", "pic_size_in_map_units_minus1",
+                    "slice_group_change_rate_minus1", "pic_init_qp_minus26", "reserved"]
+
+
+class ParamSets(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in PARAM_SET_FIELDS]
+
+
+SLICE_HEADER_FIELDS = [
+    "first_mb_in_slice", "slice_type", "pps_id", "color_plane_id", "field_pic", "bottom_field", "idr_pic_id",
+    "pic_order_cnt_lsb", "delta_pic_order_cnt_bottom", "delta_pic_order_cnt0", "delta_pic_order_cnt1",
+    "redundant_pic_cnt", "direct_spatial_mv_pred", "num_ref_idx_active_override", "num_ref_idx_l0_active_minus1",
+    "num_ref_idx_l1_active_minus1", "ref_pic_list_modification_flag_l0", "ref_pic_list_modification_flag_l1",
+    "modification_of_pic_nums", "abs_diff_pic_num_minus1", "long_term_pic_num", "luma_log2_weight_denom",
+    "chroma_log2_weight_denom", "n_luma_weight_l0", "n_chroma_weight_l0", "n_luma_weight_l1", "n_chroma_weight_l1",
+    "no_output_of_prior_pics_flag", "long_term_reference_flag", "adaptive_ref_pic_marking_mode_flag",
+    "memory_management_control_operation", "difference_of_pic_nums_minus1", "long_term_frame_idx",
+    "max_long_term_frame_idx_plus1", "cabac_init_idc", "slice_qp_delta", "sp_for_switch", "slice_qs_delta",
+    "disable_deblocking_filter", "slice_alpha_c0_offset_div2", "slice_beta_offset_div2", "slice_group_change_cycle",
+    "chroma_array_type", "slice_qp_y"]
+SLICE_HEADER_DTYPE = np.dtype([(n, "<i8") for n in SLICE_HEADER_FIELDS] +
+                              [("header_bits", "<u8"), ("status", "<u4"), ("reserved", "<u4")])
+SH_OK, SH_PANIC, SH_HANG = 0, 1, 2
+
+
 class H264BError(RuntimeError):
     def __init__(self, code, msg=""):
         super().__init__("h264b status %d: %s" % (code, msg))
@@ -112,6 +142,8 @@ def load():
         "h264b_state_transition": (i32, [vp, u32, P(i32), P(i32), i32]),
         "h264b_stream_decode": (i32, [vp, P(StreamJob), P(StreamResult)]),
         "h264b_stream_submit": (i32, [vp, P(StreamJob), P(u64)]),
+        "h264b_slice_headers_dev": (i32, [vp, P(ParamSets), vp, u64, vp, vp, vp, vp, vp, vp, u32, vp]),
+        "h264b_slice_headers": (i32, [vp, P(ParamSets), vp, u64, vp, vp, vp, vp, u32, vp]),
         "h264b_stream_wait": (i32, [vp, u64, P(StreamResult)]),
         "h264b_slice_select_dev": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp, vp]),
     }
@@ -369,6 +401,29 @@ class Context:
         r = StreamResult()
         self._check(_lib.h264b_stream_decode(self.h, C.byref(j), C.byref(r)))
         return self._stream_result(r)
+
+    @staticmethod
+    def param_sets(**kw):
+        p = ParamSets()
+        for k, v in kw.items():
+            setattr(p, k, int(v))
+        return p
+
+    def slice_headers(self, params, data, off, length, nal_type, nal_ref_idc):
+        """host buffers -> SLICE_HEADER_DTYPE[n]"""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        t = np.ascontiguousarray(nal_type, dtype=np.uint8)
+        r = np.ascontiguousarray(nal_ref_idc, dtype=np.uint8)
+        out = np.zeros(len(off), dtype=SLICE_HEADER_DTYPE)
+        self._check(_lib.h264b_slice_headers(self.h, C.byref(params), data.ctypes.data, len(data), off.ctypes.data,
+                                             length.ctypes.data, t.ctypes.data, r.ctypes.data, len(off), out.ctypes.data))
+        return out
+
+    def slice_headers_dev(self, params, d_bytes, total_bytes, d_nals, d_slice_nal, n_slices, d_out):
+        self._check(_lib.h264b_slice_headers_dev(self.h, C.byref(params), d_bytes, total_bytes, None, None, None, None,
+                                                 d_nals, d_slice_nal, n_slices, d_out))
 
     def stream_submit(self, stream, ops, n_ops, qp, idc, n_ctx, slice_data_offset=0, flags=0):
         """asynchronous form: returns (ticket, keepalive); pass both to stream_wait.  Up to two jobs in flight."""

@@ -1,0 +1,114 @@
+// slice_header.cu -- "next" row f1: the slice-header walk of NewSliceContext (h264/slice.go:835-1048) for all slice
+// NAL units at once, one thread per slice (the walk is a serial Exp-Golomb parse of a few dozen bits; slices are
+// independent).  The parse itself is slice_header.cuh (shared with the CPU emulation of tests/).
+#include "common.cuh"
+#include "slice_header.cuh"
+
+namespace h264b {
+
+struct SliceHeaderArgs {
+    h264b_param_sets ps;
+    const uint8_t *bytes;
+    uint64_t total_bytes;
+    const uint64_t *off;
+    const uint32_t *len;
+    const uint8_t *nal_type, *nal_ref_idc;
+    const h264b_nal *nals;
+    const uint32_t *slice_nal;
+    uint32_t n_slices;
+    h264b_slice_header *out;
+};
+
+__global__ void __launch_bounds__(128) slice_header_kernel(SliceHeaderArgs a) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.n_slices) return;
+    uint64_t off, len;
+    uint32_t type, ref_idc;
+    if (a.nals) {
+        const h264b_nal u = a.nals[a.slice_nal[s]];
+        off = u.rbsp_off;
+        len = u.rbsp_len;
+        type = u.type;
+        ref_idc = u.ref_idc;
+    } else {
+        off = a.off[s];
+        len = a.len[s];
+        type = a.nal_type[s];
+        ref_idc = a.nal_ref_idc[s];
+    }
+    if (off > a.total_bytes) off = a.total_bytes;
+    if (len > a.total_bytes - off) len = a.total_bytes - off;
+    h264b_slice_header h;
+    parse_slice_header_record(a.ps, type, ref_idc, a.bytes + off, len, &h);
+    a.out[s] = h;
+}
+
+int launch_slice_headers(h264b_ctx *ctx, const SliceHeaderArgs &a) {
+    if (!a.n_slices) return H264B_OK;
+    slice_header_kernel<<<(a.n_slices + 127) / 128, 128, 0, ctx->stream>>>(a);
+    H264B_LAUNCH_CHECK(ctx, "slice_header_kernel");
+    return H264B_OK;
+}
+
+}  // namespace h264b
+
+using namespace h264b;
+
+extern "C" int32_t h264b_slice_headers_dev(h264b_ctx *ctx, const h264b_param_sets *params, const uint8_t *d_bytes,
+                                           uint64_t total_bytes, const uint64_t *d_off, const uint32_t *d_len,
+                                           const uint8_t *d_nal_type, const uint8_t *d_nal_ref_idc,
+                                           const h264b_nal *d_nals, const uint32_t *d_slice_nal, uint32_t n_slices,
+                                           h264b_slice_header *d_out) {
+    if (!ctx) return H264B_E_INVALID;
+    cudaSetDevice(ctx->device);
+    if (!params || (n_slices && (!d_bytes || !d_out)))
+        return set_error(ctx, H264B_E_INVALID, "slice_headers: null pointer");
+    if (n_slices && !d_nals && (!d_off || !d_len || !d_nal_type || !d_nal_ref_idc))
+        return set_error(ctx, H264B_E_INVALID, "slice_headers: need either the NAL index or off/len/type/ref_idc");
+    if (n_slices && d_nals && !d_slice_nal) return set_error(ctx, H264B_E_INVALID, "slice_headers: slice_nal is null");
+    SliceHeaderArgs a;
+    a.ps = *params;
+    a.bytes = d_bytes;
+    a.total_bytes = total_bytes;
+    a.off = d_off;
+    a.len = d_len;
+    a.nal_type = d_nal_type;
+    a.nal_ref_idc = d_nal_ref_idc;
+    a.nals = d_nals;
+    a.slice_nal = d_slice_nal;
+    a.n_slices = n_slices;
+    a.out = d_out;
+    return launch_slice_headers(ctx, a);
+}
+
+extern "C" int32_t h264b_slice_headers(h264b_ctx *ctx, const h264b_param_sets *params, const uint8_t *bytes,
+                                       uint64_t total_bytes, const uint64_t *off, const uint32_t *len,
+                                       const uint8_t *nal_type, const uint8_t *nal_ref_idc, uint32_t n_slices,
+                                       h264b_slice_header *out) {
+    if (!ctx) return H264B_E_INVALID;
+    cudaSetDevice(ctx->device);
+    if (!n_slices) return H264B_OK;
+    if (!params || !bytes || !off || !len || !nal_type || !nal_ref_idc || !out)
+        return set_error(ctx, H264B_E_INVALID, "slice_headers: null pointer");
+    void *d_bytes, *d_off, *d_len, *d_type, *d_ref, *d_out;
+    int rc;
+    if ((rc = ensure_dev(ctx, 0, total_bytes + 64, &d_bytes))) return rc;
+    if ((rc = ensure_dev(ctx, 5, (size_t)n_slices * 8, &d_off))) return rc;
+    if ((rc = ensure_dev(ctx, 6, (size_t)n_slices * 4, &d_len))) return rc;
+    if ((rc = ensure_dev(ctx, 17, (size_t)n_slices * 2, &d_type))) return rc;
+    d_ref = (uint8_t *)d_type + n_slices;
+    if ((rc = ensure_dev(ctx, 18, (size_t)n_slices * sizeof(h264b_slice_header), &d_out))) return rc;
+    H264B_CUDA(ctx, cudaMemcpyAsync(d_bytes, bytes, total_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    H264B_CUDA(ctx, cudaMemcpyAsync(d_off, off, (size_t)n_slices * 8, cudaMemcpyHostToDevice, ctx->stream));
+    H264B_CUDA(ctx, cudaMemcpyAsync(d_len, len, (size_t)n_slices * 4, cudaMemcpyHostToDevice, ctx->stream));
+    H264B_CUDA(ctx, cudaMemcpyAsync(d_type, nal_type, n_slices, cudaMemcpyHostToDevice, ctx->stream));
+    H264B_CUDA(ctx, cudaMemcpyAsync(d_ref, nal_ref_idc, n_slices, cudaMemcpyHostToDevice, ctx->stream));
+    rc = h264b_slice_headers_dev(ctx, params, (const uint8_t *)d_bytes, total_bytes, (const uint64_t *)d_off,
+                                 (const uint32_t *)d_len, (const uint8_t *)d_type, (const uint8_t *)d_ref, nullptr, nullptr,
+                                 n_slices, (h264b_slice_header *)d_out);
+    if (rc) return rc;
+    H264B_CUDA(ctx, cudaMemcpyAsync(out, d_out, (size_t)n_slices * sizeof(h264b_slice_header), cudaMemcpyDeviceToHost,
+                                    ctx->stream));
+    H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return H264B_OK;
+}

@@ -15,6 +15,7 @@
 //   MNVars / CodedblockPatternMN, MN    mn_vars.go           h264::MNVars, h264::MN
 //   ArithmeticDecoding.{DecodeBypass, DecodeTerminate, RenormD, BinaryDecision}  cabac.go:468-540
 //   (*CABAC).StateTransitionProcess     cabac.go:544-553     h264::CABAC::StateTransitionProcess
+//   NewSliceContext (header part)       slice.go:835-1048    h264::SliceHeaders
 //   (new, batch)                                             h264::InitContexts, h264::DecodeBins
 #pragma once
 #include <stdint.h>
@@ -369,6 +370,30 @@ struct ArithmeticDecoding {  // cabac.go:513-517; the methods keep the reference
         bits->advance(used, avail);
     }
 };
+
+// ------------------------------------------------------------------------------------------------ slice headers
+// The header part of NewSliceContext (slice.go:835-1048) for a batch of slice NAL units: header fields, SliceQPy,
+// and where slice_data() starts.  A header on which the reference would panic throws h264::Panic.
+inline std::vector<h264b_slice_header> SliceHeaders(const h264b_param_sets &ps, const std::vector<NalUnit> &slices,
+                                                    Device &dev = Device::Default()) {
+    std::vector<uint8_t> cat, type, ref;
+    std::vector<uint64_t> off;
+    std::vector<uint32_t> len;
+    for (const auto &u : slices) {
+        off.push_back(cat.size());
+        len.push_back((uint32_t)u.rbsp.size());
+        type.push_back((uint8_t)u.Type);
+        ref.push_back((uint8_t)u.RefIdc);
+        cat.insert(cat.end(), u.rbsp.begin(), u.rbsp.end());
+    }
+    cat.resize(cat.size() + 8);
+    std::vector<h264b_slice_header> out(slices.size());
+    dev.check(h264b_slice_headers(dev.ctx(), &ps, cat.data(), cat.size(), off.data(), len.data(), type.data(), ref.data(),
+                                  (uint32_t)slices.size(), out.data()));
+    for (const auto &h : out)
+        if (h.status == H264B_SH_PANIC) throw Panic("NewSliceContext: the reference panics on this slice header");
+    return out;
+}
 
 // new, batch: the whole engine for many slices at once (see h264b_cabac_job)
 inline void DecodeBins(const h264b_cabac_job &job, Device &dev = Device::Default()) {

@@ -215,6 +215,56 @@ int32_t h264b_binary_decision(h264b_ctx *ctx, uint32_t flags, int32_t p_state_id
 int32_t h264b_state_transition(h264b_ctx *ctx, uint32_t flags, int32_t *p_state_idx, int32_t *val_mps,
                                int32_t bin_val);
 
+/* ------------------------------------------------------------------ slice headers ("next" row f1)
+ * Replaces the header walk of NewSliceContext (h264/slice.go:835-1048, everything before NewSliceData) for all slice
+ * NAL units at once, one thread per slice: what the CABAC stage needs from the stream instead of from the caller --
+ * SliceQPY (SliceQPy, h264/cabac.go:113-115), cabac_init_idc, the slice type and the bit at which slice_data()
+ * begins.  The reference's deviations from ITU-T H.264 are reproduced (slice_header.cuh lists them). */
+typedef struct { /* the SPS / PPS fields the walk reads (h264/sps.go, h264/pps.go) */
+    int32_t use_separate_color_plane, chroma_format, frame_mbs_only, pic_order_count_type;
+    int32_t log2_max_pic_order_cnt_lsb_min4, delta_pic_order_always_zero;
+    int32_t bottom_field_pic_order_in_frame_present, redundant_pic_cnt_present, weighted_pred, weighted_bipred;
+    int32_t entropy_coding_mode, deblocking_filter_control_present, num_slice_groups_minus1, slice_group_map_type;
+    int32_t pic_size_in_map_units_minus1, slice_group_change_rate_minus1, pic_init_qp_minus26, reserved;
+} h264b_param_sets; /* 72 bytes */
+
+#define H264B_SH_OK 0u
+#define H264B_SH_PANIC 1u /* the reference would have panicked (read past the end of the RBSP, index out of range,
+                             divide by zero); the other fields are unspecified */
+#define H264B_SH_HANG 2u  /* the reference would loop forever (memory_management_control_operation 5 or >= 7) */
+
+typedef struct { /* SliceHeader, h264/slice.go:35-103; Go ints -> int64 */
+    int64_t first_mb_in_slice, slice_type, pps_id, color_plane_id, field_pic, bottom_field, idr_pic_id;
+    int64_t pic_order_cnt_lsb, delta_pic_order_cnt_bottom, delta_pic_order_cnt[2], redundant_pic_cnt;
+    int64_t direct_spatial_mv_pred, num_ref_idx_active_override, num_ref_idx_l0_active_minus1;
+    int64_t num_ref_idx_l1_active_minus1, ref_pic_list_modification_flag_l0, ref_pic_list_modification_flag_l1;
+    int64_t modification_of_pic_nums, abs_diff_pic_num_minus1, long_term_pic_num;
+    int64_t luma_log2_weight_denom, chroma_log2_weight_denom;
+    int64_t n_luma_weight_l0, n_chroma_weight_l0, n_luma_weight_l1, n_chroma_weight_l1; /* list lengths only */
+    int64_t no_output_of_prior_pics_flag, long_term_reference_flag, adaptive_ref_pic_marking_mode_flag;
+    int64_t memory_management_control_operation, difference_of_pic_nums_minus1, long_term_frame_idx;
+    int64_t max_long_term_frame_idx_plus1, cabac_init_idc, slice_qp_delta, sp_for_switch, slice_qs_delta;
+    int64_t disable_deblocking_filter, slice_alpha_c0_offset_div2, slice_beta_offset_div2, slice_group_change_cycle;
+    int64_t chroma_array_type;
+    int64_t slice_qp_y;   /* 26 + pic_init_qp_minus26 + slice_qp_delta */
+    uint64_t header_bits; /* BitReader.bitsRead at the end of the header */
+    uint32_t status;      /* H264B_SH_* */
+    uint32_t reserved;
+} h264b_slice_header; /* 46 x 8 + 8 bytes */
+
+/* Slice s = RBSP bytes [off[s], off[s] + len[s]) of `bytes`, from the NAL with (nal_type[s], nal_ref_idc[s]).  Device
+ * pointers; asynchronous.  With d_nals != NULL, off/len/type/ref_idc are taken from nals[slice_nal[s]] instead (the
+ * output of h264b_annexb_scan_dev + h264b_slice_select_dev with slice_data_offset 0) and d_off .. d_ref_idc may be
+ * NULL. */
+int32_t h264b_slice_headers_dev(h264b_ctx *ctx, const h264b_param_sets *params /* host */, const uint8_t *d_bytes,
+                                uint64_t total_bytes, const uint64_t *d_off, const uint32_t *d_len,
+                                const uint8_t *d_nal_type, const uint8_t *d_nal_ref_idc, const h264b_nal *d_nals,
+                                const uint32_t *d_slice_nal, uint32_t n_slices, h264b_slice_header *d_out);
+/* host pointers; synchronous */
+int32_t h264b_slice_headers(h264b_ctx *ctx, const h264b_param_sets *params, const uint8_t *bytes, uint64_t total_bytes,
+                            const uint64_t *off, const uint32_t *len, const uint8_t *nal_type,
+                            const uint8_t *nal_ref_idc, uint32_t n_slices, h264b_slice_header *out);
+
 /* ------------------------------------------------------------------ whole front end of one stream
  * split + strip + (slice NALs of type 1 / 5) context init + CABAC bins, the slice data staying on the device
  * between the stages.  The CABAC data of a slice NAL starts at RBSP byte `slice_data_offset` (the reference's

@@ -792,3 +792,246 @@ int orc_new_pps(int64_t sps_chroma_format, const uint8_t *rbsp, int64_t len, orc
     out->bits_read = b->bitsRead;
     return ORC_OK;
 }
+
+/* ====================================================================================================== slice header
+ * NewSliceContext, h264/slice.go:835-1048, up to the call of NewSliceData (:1046).  Test infrastructure. */
+#include <math.h>
+
+/* golomb() + bitVal() over ALL bits of the code (bit_reader.go:174-196, :50-59): bitVal adds 1 << (len-1-i) per set
+ * bit and Go shifts of 64 or more give 0, so the value is the code's bit string modulo 2^64 */
+static int sh_golomb(orc_bit_reader *b, int64_t *val) {
+    uint64_t t = 0;
+    int64_t zeros = -1, bit = 0;
+    while (bit != 1) {
+        zeros += 1;
+        if (b->byteOffset >= b->len) { /* :180 index out of range */
+            b->panicked = 1;
+            return ORC_PANIC;
+        }
+        bit = bit_array(b->bytes[b->byteOffset], b->bitOffset);
+        b->bitsRead += 1;
+        set_offset(b);
+        t = (t << 1) | (uint64_t)bit;
+    }
+    for (int64_t i = 0; i < zeros; i++) {
+        if (b->byteOffset >= b->len) { /* :189 */
+            b->panicked = 1;
+            return ORC_PANIC;
+        }
+        bit = bit_array(b->bytes[b->byteOffset], b->bitOffset);
+        b->bitsRead += 1;
+        set_offset(b);
+        t = (t << 1) | (uint64_t)bit;
+    }
+    *val = (int64_t)t;
+    return ORC_OK;
+}
+/* se(), bit_reader.go:158-161, through float64 exactly as written: int(math.Pow(-1, float64(codeNum+1)) *
+ * math.Ceil(float64(codeNum/2))) */
+static int64_t sh_se(int64_t bitval) {
+    const int64_t codeNum = (int64_t)((uint64_t)bitval - 1u);
+    const double sign = pow(-1.0, (double)(int64_t)((uint64_t)codeNum + 1u));
+    return (int64_t)(sign * ceil((double)(codeNum / 2)));
+}
+/* NextField(name, n), bit_reader.go:315-325 -> Read (:292-314): make([]int, n) panics for n < 0 */
+static int sh_field(orc_bit_reader *b, int64_t n, int64_t *val) {
+    uint64_t t = 0;
+    if (n < 0) {
+        b->panicked = 1;
+        return ORC_PANIC;
+    }
+    for (int64_t i = 0; i < n; i++) {
+        if (b->byteOffset >= b->len) { /* :298 */
+            b->panicked = 1;
+            return ORC_PANIC;
+        }
+        t = (t << 1) | (uint64_t)bit_array(b->bytes[b->byteOffset], b->bitOffset);
+        b->bitsRead += 1;
+        set_offset(b);
+    }
+    *val = (int64_t)t;
+    return ORC_OK;
+}
+/* sliceTypeMap, slice.go:105-116: 0 "P", 1 "B", 2 "I", 3 "SP", 4 "SI", 5..9 the same again, anything else "" */
+enum { ST_P, ST_B, ST_I, ST_SP, ST_SI, ST_NONE };
+static int slice_type_name(int64_t t) { return (t >= 0 && t <= 9) ? (int)(t % 5) : ST_NONE; }
+
+#define SH_UE(dst)                               \
+    do {                                         \
+        int64_t v_;                              \
+        if (sh_golomb(b, &v_)) goto panic;       \
+        (dst) = (int64_t)((uint64_t)v_ - 1u);    \
+    } while (0)
+#define SH_SE(dst)                         \
+    do {                                   \
+        int64_t v_;                        \
+        if (sh_golomb(b, &v_)) goto panic; \
+        (dst) = sh_se(v_);                 \
+    } while (0)
+#define SH_FLAG(dst)                          \
+    do {                                      \
+        int64_t v_;                           \
+        if (sh_field(b, 1, &v_)) goto panic;  \
+        (dst) = (v_ == 1);                    \
+    } while (0)
+
+int orc_new_slice_header(const orc_sps *sps, const orc_pps *pps, int64_t nal_type, int64_t nal_ref_idc,
+                         const uint8_t *rbsp, int64_t len, orc_slice_header *h) {
+    orc_bit_reader br, *b = &br;
+    memset(h, 0, sizeof(*h));
+    orc_br_init(b, rbsp, len);
+    const int idrPic = nal_type == 5;                                       /* :841-844 */
+    h->ChromaArrayType = sps->UseSeparateColorPlane ? 0 : sps->ChromaFormat; /* :846-850 */
+    SH_UE(h->FirstMbInSlice);                                                /* :858 */
+    SH_UE(h->SliceType);                                                     /* :859 */
+    const int st = slice_type_name(h->SliceType);                            /* :860 */
+    SH_UE(h->PPSID);                                                         /* :862 */
+    if (sps->UseSeparateColorPlane) {                                        /* :863-865 */
+        if (sh_field(b, 2, &h->ColorPlaneID)) goto panic;
+    }
+    /* frame_num is not read (:866-867) */
+    if (!sps->FrameMbsOnly) { /* :868-873 */
+        SH_FLAG(h->FieldPic);
+        if (h->FieldPic) SH_FLAG(h->BottomField);
+    }
+    if (idrPic) SH_UE(h->IDRPicID); /* :874-876 */
+    if (sps->PicOrderCountType == 0) { /* :877-882 */
+        if (sh_field(b, sps->Log2MaxPicOrderCntLSBMin4 + 4, &h->PicOrderCntLsb)) goto panic;
+        if (pps->BottomFieldPicOrderInFramePresent && !h->FieldPic) SH_SE(h->DeltaPicOrderCntBottom);
+    }
+    if (sps->PicOrderCountType == 1 && !sps->DeltaPicOrderAlwaysZero) { /* :883-888 */
+        SH_SE(h->DeltaPicOrderCnt0);
+        if (pps->BottomFieldPicOrderInFramePresent && !h->FieldPic) SH_SE(h->DeltaPicOrderCnt1);
+    }
+    if (pps->RedundantPicCntPresent) SH_UE(h->RedundantPicCnt); /* :889-891 */
+    if (st == ST_B) SH_FLAG(h->DirectSpatialMvPred);            /* :892-894 */
+    if (st == ST_B || st == ST_SP || st == ST_B) {              /* :895-903 ("B" twice, no "P") */
+        SH_FLAG(h->NumRefIdxActiveOverride);
+        if (h->NumRefIdxActiveOverride) {
+            SH_UE(h->NumRefIdxL0ActiveMinus1);
+            if (st == ST_B) SH_UE(h->NumRefIdxL1ActiveMinus1);
+        }
+    }
+    if (nal_type == 20 || nal_type == 21) { /* :905-908: nothing */
+    } else {
+        if (h->SliceType % 5 != 2 && h->SliceType % 5 != 4) { /* :911-924 */
+            SH_FLAG(h->RefPicListModificationFlagL0);
+            if (h->RefPicListModificationFlagL0) {
+                while (h->ModificationOfPicNums != 3) {
+                    SH_UE(h->ModificationOfPicNums);
+                    if (h->ModificationOfPicNums == 0 || h->ModificationOfPicNums == 1)
+                        SH_UE(h->AbsDiffPicNumMinus1);
+                    else if (h->ModificationOfPicNums == 2)
+                        SH_UE(h->LongTermPicNum);
+                }
+            }
+        }
+        if (h->SliceType % 5 == 1) { /* :925-937; ModificationOfPicNums keeps its value from list 0 */
+            SH_FLAG(h->RefPicListModificationFlagL1);
+            if (h->RefPicListModificationFlagL1) {
+                while (h->ModificationOfPicNums != 3) {
+                    SH_UE(h->ModificationOfPicNums);
+                    if (h->ModificationOfPicNums == 0 || h->ModificationOfPicNums == 1)
+                        SH_UE(h->AbsDiffPicNumMinus1);
+                    else if (h->ModificationOfPicNums == 2)
+                        SH_UE(h->LongTermPicNum);
+                }
+            }
+        }
+    }
+    if ((pps->WeightedPred && (st == ST_P || st == ST_SP)) || (pps->WeightedBipred == 1 && st == ST_B)) { /* :942-990 */
+        SH_UE(h->LumaLog2WeightDenom);
+        if (h->ChromaArrayType != 0) SH_UE(h->ChromaLog2WeightDenom);
+        for (int64_t i = 0; i <= h->NumRefIdxL0ActiveMinus1; i++) {
+            int64_t f, v;
+            SH_FLAG(f);
+            if (f) {
+                SH_SE(v); /* LumaWeightL0 = append(...) */
+                SH_SE(v); /* LumaOffsetL0 */
+                h->NLumaWeightL0++;
+            }
+            if (h->ChromaArrayType != 0) {
+                SH_FLAG(f);
+                if (f) {
+                    h->NChromaWeightL0++;                 /* ChromaWeightL0 = append(ChromaWeightL0, []int{}) */
+                    if (i >= h->NChromaWeightL0) goto panic; /* ChromaWeightL0[i]: index out of range (:964) */
+                    for (int j = 0; j < 2; j++) {
+                        SH_SE(v);
+                        SH_SE(v);
+                    }
+                }
+            }
+        }
+        if (h->SliceType % 5 == 1) {
+            for (int64_t i = 0; i <= h->NumRefIdxL1ActiveMinus1; i++) {
+                int64_t f, v;
+                SH_FLAG(f);
+                if (f) {
+                    SH_SE(v);
+                    SH_SE(v);
+                    h->NLumaWeightL1++;
+                }
+                if (h->ChromaArrayType != 0) {
+                    SH_FLAG(f);
+                    if (f) {
+                        h->NChromaWeightL1++;
+                        if (i >= h->NChromaWeightL1) goto panic; /* :983 */
+                        for (int j = 0; j < 2; j++) {
+                            SH_SE(v);
+                            SH_SE(v);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (nal_ref_idc != 0) { /* :991-1018 */
+        if (idrPic) {
+            SH_FLAG(h->NoOutputOfPriorPicsFlag);
+            SH_FLAG(h->LongTermReferenceFlag);
+        } else {
+            SH_FLAG(h->AdaptiveRefPicMarkingModeFlag);
+            if (h->AdaptiveRefPicMarkingModeFlag) {
+                SH_UE(h->MemoryManagementControlOperation);
+                const int64_t op = h->MemoryManagementControlOperation;
+                if (op != 0 && !(op == 1 || op == 2 || op == 3 || op == 4 || op == 6)) {
+                    h->bits_read = b->bitsRead; /* the loop body reads nothing and the operation never changes */
+                    return ORC_HANG;
+                }
+                while (h->MemoryManagementControlOperation != 0) { /* never re-read: ends in the panic below */
+                    if (op == 1 || op == 3) SH_UE(h->DifferenceOfPicNumsMinus1);
+                    if (op == 2) SH_UE(h->LongTermPicNum);
+                    if (op == 3 || op == 6) SH_UE(h->LongTermFrameIdx);
+                    if (op == 4) SH_UE(h->MaxLongTermFrameIdxPlus1);
+                }
+            }
+        }
+    }
+    if (pps->EntropyCodingMode == 1 && st != ST_I && st != ST_SI) SH_UE(h->CabacInit); /* :1019-1021 */
+    SH_SE(h->SliceQpDelta);                                                             /* :1022 */
+    if (st == ST_SP || st == ST_SI) {                                                   /* :1023-1028 */
+        if (st == ST_SP) SH_FLAG(h->SpForSwitch);
+        SH_SE(h->SliceQsDelta);
+    }
+    if (pps->DeblockingFilterControlPresent) { /* :1029-1035 */
+        SH_UE(h->DisableDeblockingFilter);
+        if (h->DisableDeblockingFilter != 1) {
+            SH_SE(h->SliceAlphaC0OffsetDiv2);
+            SH_SE(h->SliceBetaOffsetDiv2);
+        }
+    }
+    if (pps->NumSliceGroupsMinus1 > 0 && pps->SliceGroupMapType >= 3 && pps->SliceGroupMapType <= 5) { /* :1036-1040 */
+        if (pps->SliceGroupChangeRateMinus1 == 0) goto panic; /* integer divide by zero */
+        const int64_t q = (int64_t)((uint64_t)(pps->PicSizeInMapUnitsMinus1 / pps->SliceGroupChangeRateMinus1) + 1u);
+        /* int(math.Ceil(math.Log2(float64(q)))): NaN / -Inf for q <= 0 convert to the most negative int -> make panics */
+        if (q <= 0) goto panic;
+        const int64_t n = (int64_t)ceil(log2((double)q));
+        if (sh_field(b, n, &h->SliceGroupChangeCycle)) goto panic;
+    }
+    h->SliceQPy = (int64_t)((uint64_t)26 + (uint64_t)pps->PicInitQpMinus26 + (uint64_t)h->SliceQpDelta); /* cabac.go:113-115 */
+    h->bits_read = b->bitsRead;
+    return ORC_OK;
+panic:
+    h->bits_read = b->bitsRead;
+    return ORC_PANIC;
+}

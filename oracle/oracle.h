@@ -158,6 +158,31 @@ typedef struct {
     int64_t bits_read;
 } orc_pps;
 
+/* ---- slice header: NewSliceContext up to (not including) NewSliceData, h264/slice.go:835-1048 ("next" row f1) ----
+ * Literal restatement, quirks kept: frame_num is never read (:864-865); num_ref_idx_active_override is read for B and
+ * SP slices only (:897 tests "B" twice, never "P"); ModificationOfPicNums is not reset between list 0 and list 1
+ * (:917,:930); the memory_management_control_operation loop never reads the next operation (:1003-1016), so it either
+ * reads until the Go code panics at the end of the data or -- for operations that read nothing -- never ends
+ * (ORC_HANG); chroma weights index a slice that only grows when the flag is set (:960-966, panic when an earlier flag
+ * was clear); se() has the floor quirk A9 and goes through float64 (math.Pow / math.Ceil, bit_reader.go:158-161);
+ * SliceGroupChangeCycle divides by SliceGroupChangeRateMinus1 (panic when 0, :1033-1036). */
+#define ORC_HANG 2    /* the Go code would loop forever */
+typedef struct {
+    int64_t FirstMbInSlice, SliceType, PPSID, ColorPlaneID, FieldPic, BottomField, IDRPicID, PicOrderCntLsb,
+        DeltaPicOrderCntBottom, DeltaPicOrderCnt0, DeltaPicOrderCnt1, RedundantPicCnt, DirectSpatialMvPred,
+        NumRefIdxActiveOverride, NumRefIdxL0ActiveMinus1, NumRefIdxL1ActiveMinus1, RefPicListModificationFlagL0,
+        RefPicListModificationFlagL1, ModificationOfPicNums, AbsDiffPicNumMinus1, LongTermPicNum, LumaLog2WeightDenom,
+        ChromaLog2WeightDenom, NLumaWeightL0, NChromaWeightL0, NLumaWeightL1, NChromaWeightL1, NoOutputOfPriorPicsFlag,
+        LongTermReferenceFlag, AdaptiveRefPicMarkingModeFlag, MemoryManagementControlOperation,
+        DifferenceOfPicNumsMinus1, LongTermFrameIdx, MaxLongTermFrameIdxPlus1, CabacInit, SliceQpDelta, SpForSwitch,
+        SliceQsDelta, DisableDeblockingFilter, SliceAlphaC0OffsetDiv2, SliceBetaOffsetDiv2, SliceGroupChangeCycle,
+        ChromaArrayType;
+    int64_t SliceQPy;   /* cabac.go:113-115: 26 + PicInitQpMinus26 + SliceQpDelta */
+    int64_t bits_read;  /* BitReader.bitsRead when the header ends: where slice_data() starts */
+} orc_slice_header;
+int orc_new_slice_header(const orc_sps *sps, const orc_pps *pps, int64_t nal_type, int64_t nal_ref_idc,
+                         const uint8_t *rbsp, int64_t len, orc_slice_header *out);
+
 int orc_new_sps(const uint8_t *rbsp, int64_t len, orc_sps *out);                         /* sps.go:192-437 */
 int orc_new_pps(int64_t sps_chroma_format, const uint8_t *rbsp, int64_t len, orc_pps *out); /* pps.go:40-133 */
 

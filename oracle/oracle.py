@@ -353,3 +353,38 @@ def new_pps(rbsp, sps_chroma_format=1):
     p = PPS()
     st = lib().orc_new_pps(sps_chroma_format, r.ctypes.data, len(r), C.byref(p))
     return st, p.as_dict()
+
+
+# ------------------------------------------------------------------ slice header (next row f1)
+HANG = 2
+_SLICE_HEADER_FIELDS = [
+    "FirstMbInSlice", "SliceType", "PPSID", "ColorPlaneID", "FieldPic", "BottomField", "IDRPicID", "PicOrderCntLsb",
+    "DeltaPicOrderCntBottom", "DeltaPicOrderCnt0", "DeltaPicOrderCnt1", "RedundantPicCnt", "DirectSpatialMvPred",
+    "NumRefIdxActiveOverride", "NumRefIdxL0ActiveMinus1", "NumRefIdxL1ActiveMinus1", "RefPicListModificationFlagL0",
+    "RefPicListModificationFlagL1", "ModificationOfPicNums", "AbsDiffPicNumMinus1", "LongTermPicNum",
+    "LumaLog2WeightDenom", "ChromaLog2WeightDenom", "NLumaWeightL0", "NChromaWeightL0", "NLumaWeightL1",
+    "NChromaWeightL1", "NoOutputOfPriorPicsFlag", "LongTermReferenceFlag", "AdaptiveRefPicMarkingModeFlag",
+    "MemoryManagementControlOperation", "DifferenceOfPicNumsMinus1", "LongTermFrameIdx", "MaxLongTermFrameIdxPlus1",
+    "CabacInit", "SliceQpDelta", "SpForSwitch", "SliceQsDelta", "DisableDeblockingFilter", "SliceAlphaC0OffsetDiv2",
+    "SliceBetaOffsetDiv2", "SliceGroupChangeCycle", "ChromaArrayType", "SliceQPy", "bits_read"]
+
+
+class SliceHeader(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in _SLICE_HEADER_FIELDS]
+
+
+def new_slice_header(sps_fields, pps_fields, nal_type, nal_ref_idc, rbsp):
+    """sps_fields / pps_fields: dicts of the orc_sps / orc_pps scalar names NewSliceContext reads.
+    Returns (status, dict of header fields)."""
+    sps, pps = SPS(), PPS()
+    for k, v in sps_fields.items():
+        setattr(sps, k, int(v))
+    for k, v in pps_fields.items():
+        setattr(pps, k, int(v))
+    d = _u8(rbsp)
+    h = SliceHeader()
+    L = lib()
+    L.orc_new_slice_header.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+    rc = L.orc_new_slice_header(C.byref(sps), C.byref(pps), int(nal_type), int(nal_ref_idc), d.ctypes.data, len(d),
+                                C.byref(h))
+    return rc, {n: getattr(h, n) for n in _SLICE_HEADER_FIELDS}

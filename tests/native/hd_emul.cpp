@@ -10,6 +10,7 @@
 
 #include "../../h264decode_b200/csrc/annexb_local.cuh"
 #include "../../h264decode_b200/csrc/cabac_lane.cuh"
+#include "../../h264decode_b200/csrc/slice_header.cuh"
 #include "../../h264decode_b200/csrc/tables.inc"
 
 using namespace h264b;
@@ -351,6 +352,12 @@ int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out_base, int64_
         stats[3] = n_filter_mismatch;
     }
     return Kall;
+}
+
+// the slice-header walk of slice_header_kernel, one slice
+void emul_slice_header(const h264b_param_sets *ps, uint32_t nal_type, uint32_t nal_ref_idc, const uint8_t *rbsp,
+                       uint64_t len, h264b_slice_header *out) {
+    parse_slice_header_record(*ps, nal_type, nal_ref_idc, rbsp, len, out);
 }
 
 // NewNalUnit on one frame with keep_byte_frame; returns rbsp length

@@ -1,0 +1,371 @@
+"""Slice headers ("next" row f1, NewSliceContext h264/slice.go:835-1048): the product's parse (slice_header.cuh)
+against the oracle's literal restatement -- on the CPU through the emulation library (same source as the kernel), on
+the GPU through the C ABI.  Inputs: headers written by a small conformant bit writer (all slice types, field / IDR /
+POC variants, reference list modification, weight tables, reference marking, deblocking, slice groups) and random
+bytes (the walk must agree on garbage too, including where the reference would panic or never return)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+SPS_KEYS = {"use_separate_color_plane": "UseSeparateColorPlane", "chroma_format": "ChromaFormat",
+            "frame_mbs_only": "FrameMbsOnly", "pic_order_count_type": "PicOrderCountType",
+            "log2_max_pic_order_cnt_lsb_min4": "Log2MaxPicOrderCntLSBMin4",
+            "delta_pic_order_always_zero": "DeltaPicOrderAlwaysZero"}
+PPS_KEYS = {"bottom_field_pic_order_in_frame_present": "BottomFieldPicOrderInFramePresent",
+            "redundant_pic_cnt_present": "RedundantPicCntPresent", "weighted_pred": "WeightedPred",
+            "weighted_bipred": "WeightedBipred", "entropy_coding_mode": "EntropyCodingMode",
+            "deblocking_filter_control_present": "DeblockingFilterControlPresent",
+            "num_slice_groups_minus1": "NumSliceGroupsMinus1", "slice_group_map_type": "SliceGroupMapType",
+            "pic_size_in_map_units_minus1": "PicSizeInMapUnitsMinus1",
+            "slice_group_change_rate_minus1": "SliceGroupChangeRateMinus1", "pic_init_qp_minus26": "PicInitQpMinus26"}
+# product field -> oracle field
+FIELD_MAP = [("first_mb_in_slice", "FirstMbInSlice"), ("slice_type", "SliceType"), ("pps_id", "PPSID"),
+             ("color_plane_id", "ColorPlaneID"), ("field_pic", "FieldPic"), ("bottom_field", "BottomField"),
+             ("idr_pic_id", "IDRPicID"), ("pic_order_cnt_lsb", "PicOrderCntLsb"),
+             ("delta_pic_order_cnt_bottom", "DeltaPicOrderCntBottom"), ("delta_pic_order_cnt0", "DeltaPicOrderCnt0"),
+             ("delta_pic_order_cnt1", "DeltaPicOrderCnt1"), ("redundant_pic_cnt", "RedundantPicCnt"),
+             ("direct_spatial_mv_pred", "DirectSpatialMvPred"), ("num_ref_idx_active_override", "NumRefIdxActiveOverride"),
+             ("num_ref_idx_l0_active_minus1", "NumRefIdxL0ActiveMinus1"),
+             ("num_ref_idx_l1_active_minus1", "NumRefIdxL1ActiveMinus1"),
+             ("ref_pic_list_modification_flag_l0", "RefPicListModificationFlagL0"),
+             ("ref_pic_list_modification_flag_l1", "RefPicListModificationFlagL1"),
+             ("modification_of_pic_nums", "ModificationOfPicNums"), ("abs_diff_pic_num_minus1", "AbsDiffPicNumMinus1"),
+             ("long_term_pic_num", "LongTermPicNum"), ("luma_log2_weight_denom", "LumaLog2WeightDenom"),
+             ("chroma_log2_weight_denom", "ChromaLog2WeightDenom"), ("n_luma_weight_l0", "NLumaWeightL0"),
+             ("n_chroma_weight_l0", "NChromaWeightL0"), ("n_luma_weight_l1", "NLumaWeightL1"),
+             ("n_chroma_weight_l1", "NChromaWeightL1"), ("no_output_of_prior_pics_flag", "NoOutputOfPriorPicsFlag"),
+             ("long_term_reference_flag", "LongTermReferenceFlag"),
+             ("adaptive_ref_pic_marking_mode_flag", "AdaptiveRefPicMarkingModeFlag"),
+             ("memory_management_control_operation", "MemoryManagementControlOperation"),
+             ("difference_of_pic_nums_minus1", "DifferenceOfPicNumsMinus1"), ("long_term_frame_idx", "LongTermFrameIdx"),
+             ("max_long_term_frame_idx_plus1", "MaxLongTermFrameIdxPlus1"), ("cabac_init_idc", "CabacInit"),
+             ("slice_qp_delta", "SliceQpDelta"), ("sp_for_switch", "SpForSwitch"), ("slice_qs_delta", "SliceQsDelta"),
+             ("disable_deblocking_filter", "DisableDeblockingFilter"),
+             ("slice_alpha_c0_offset_div2", "SliceAlphaC0OffsetDiv2"), ("slice_beta_offset_div2", "SliceBetaOffsetDiv2"),
+             ("slice_group_change_cycle", "SliceGroupChangeCycle"), ("chroma_array_type", "ChromaArrayType"),
+             ("slice_qp_y", "SliceQPy"), ("header_bits", "bits_read")]
+
+
+class BitWriter:
+    def __init__(self):
+        self.bits = []
+
+    def u(self, n, v):
+        self.bits += [(v >> (n - 1 - i)) & 1 for i in range(n)]
+
+    def ue(self, k):
+        n = (k + 1).bit_length()
+        self.bits += [0] * (n - 1)
+        self.u(n, k + 1)
+
+    def se_ref(self, code_num):
+        """the reference's se() maps codeNum k to (-1)^(k+1) * floor(k/2): callers pick the codeNum"""
+        self.ue(code_num)
+
+    def bytes(self, trailing=b"\x80\x55\xAA\x33"):
+        b = self.bits + [1]
+        b += [0] * (-len(b) % 8)
+        return bytes(int("".join(map(str, b[i:i + 8])), 2) for i in range(0, len(b), 8)) + trailing
+
+
+def write_header(rng, ps, nal_type, ref_idc, slice_type):
+    """a header the reference's walk accepts (what it reads, not what the standard says), random field values"""
+    w = BitWriter()
+    name = ["P", "B", "I", "SP", "SI"][slice_type % 5]
+    w.ue(int(rng.integers(0, 400)))
+    w.ue(slice_type)
+    w.ue(int(rng.integers(0, 4)))
+    if ps["use_separate_color_plane"]:
+        w.u(2, int(rng.integers(0, 3)))
+    field = 0
+    if not ps["frame_mbs_only"]:
+        field = int(rng.integers(0, 2))
+        w.u(1, field)
+        if field:
+            w.u(1, int(rng.integers(0, 2)))
+    if nal_type == 5:
+        w.ue(int(rng.integers(0, 65536)))
+    if ps["pic_order_count_type"] == 0:
+        n = ps["log2_max_pic_order_cnt_lsb_min4"] + 4
+        w.u(n, int(rng.integers(0, 1 << n)))
+        if ps["bottom_field_pic_order_in_frame_present"] and not field:
+            w.se_ref(int(rng.integers(0, 40)))
+    if ps["pic_order_count_type"] == 1 and not ps["delta_pic_order_always_zero"]:
+        w.se_ref(int(rng.integers(0, 40)))
+        if ps["bottom_field_pic_order_in_frame_present"] and not field:
+            w.se_ref(int(rng.integers(0, 40)))
+    if ps["redundant_pic_cnt_present"]:
+        w.ue(int(rng.integers(0, 5)))
+    if name == "B":
+        w.u(1, int(rng.integers(0, 2)))
+    l0 = l1 = 0
+    if name in ("B", "SP"):
+        ov = int(rng.integers(0, 2))
+        w.u(1, ov)
+        if ov:
+            l0 = int(rng.integers(0, 4))
+            w.ue(l0)
+            if name == "B":
+                l1 = int(rng.integers(0, 4))
+                w.ue(l1)
+    if nal_type not in (20, 21):
+        ended = False
+        for lst in (0, 1):
+            if (lst == 0 and slice_type % 5 not in (2, 4)) or (lst == 1 and slice_type % 5 == 1):
+                f = int(rng.integers(0, 2))
+                w.u(1, f)
+                if f and not ended:
+                    for _ in range(int(rng.integers(0, 4))):
+                        op = int(rng.integers(0, 3))
+                        w.ue(op)
+                        w.ue(int(rng.integers(0, 30)))
+                    w.ue(3)
+                    ended = True   # the reference never resets ModificationOfPicNums: list 1 reads nothing more
+    cat = 0 if ps["use_separate_color_plane"] else ps["chroma_format"]
+    if (ps["weighted_pred"] and name in ("P", "SP")) or (ps["weighted_bipred"] == 1 and name == "B"):
+        w.ue(int(rng.integers(0, 8)))
+        if cat:
+            w.ue(int(rng.integers(0, 8)))
+        for lst, last in ((0, l0), (1, l1)):
+            if lst == 1 and slice_type % 5 != 1:
+                break
+            chroma_on = True   # once a chroma flag is clear the reference's indexing panics later: keep them set
+            for i in range(last + 1):
+                f = int(rng.integers(0, 2))
+                w.u(1, f)
+                if f:
+                    w.se_ref(int(rng.integers(0, 60)))
+                    w.se_ref(int(rng.integers(0, 60)))
+                if cat:
+                    w.u(1, 1 if chroma_on else 0)
+                    for _ in range(4):
+                        w.se_ref(int(rng.integers(0, 60)))
+    if ref_idc:
+        if nal_type == 5:
+            w.u(1, int(rng.integers(0, 2)))
+            w.u(1, int(rng.integers(0, 2)))
+        else:
+            w.u(1, 0)   # adaptive marking ends in a panic or a hang in the reference: covered by the garbage cases
+    if ps["entropy_coding_mode"] == 1 and name not in ("I", "SI"):
+        w.ue(int(rng.integers(0, 3)))
+    w.se_ref(int(rng.integers(0, 50)))
+    if name in ("SP", "SI"):
+        if name == "SP":
+            w.u(1, int(rng.integers(0, 2)))
+        w.se_ref(int(rng.integers(0, 50)))
+    if ps["deblocking_filter_control_present"]:
+        d = int(rng.integers(0, 3))
+        w.ue(d)
+        if d != 1:
+            w.se_ref(int(rng.integers(0, 13)))
+            w.se_ref(int(rng.integers(0, 13)))
+    if ps["num_slice_groups_minus1"] > 0 and 3 <= ps["slice_group_map_type"] <= 5:
+        q = ps["pic_size_in_map_units_minus1"] // ps["slice_group_change_rate_minus1"] + 1
+        n = int(np.ceil(np.log2(q)))
+        w.u(n, int(rng.integers(0, 1 << n)) if n else 0)
+    return w.bytes(), len(w.bits)
+
+
+def random_param_sets(rng):
+    return dict(use_separate_color_plane=int(rng.random() < 0.2), chroma_format=int(rng.integers(0, 4)),
+                frame_mbs_only=int(rng.random() < 0.6), pic_order_count_type=int(rng.integers(0, 3)),
+                log2_max_pic_order_cnt_lsb_min4=int(rng.integers(0, 13)), delta_pic_order_always_zero=int(rng.integers(0, 2)),
+                bottom_field_pic_order_in_frame_present=int(rng.integers(0, 2)),
+                redundant_pic_cnt_present=int(rng.random() < 0.3), weighted_pred=int(rng.integers(0, 2)),
+                weighted_bipred=int(rng.integers(0, 3)), entropy_coding_mode=int(rng.integers(0, 2)),
+                deblocking_filter_control_present=int(rng.integers(0, 2)),
+                num_slice_groups_minus1=int(rng.integers(0, 3)), slice_group_map_type=int(rng.integers(0, 7)),
+                pic_size_in_map_units_minus1=int(rng.integers(0, 9000)), slice_group_change_rate_minus1=int(rng.integers(0, 40)),
+                pic_init_qp_minus26=int(rng.integers(-26, 26)))
+
+
+def oracle_header(ps, nal_type, ref_idc, rbsp):
+    return orc.new_slice_header({SPS_KEYS[k]: v for k, v in ps.items() if k in SPS_KEYS},
+                                {PPS_KEYS[k]: v for k, v in ps.items() if k in PPS_KEYS}, nal_type, ref_idc, rbsp)
+
+
+def compare(got, status, exp_rc, exp, what):
+    assert status == exp_rc, (what, status, exp_rc)
+    if exp_rc == orc.PANIC:
+        return
+    for mine, theirs in FIELD_MAP:
+        if exp_rc == orc.HANG and mine in ("slice_qp_y",):
+            continue
+        assert int(got[mine]) == (exp[theirs] if mine != "header_bits" else exp["bits_read"]), (what, mine)
+
+
+def cases(seed, n_conformant, n_garbage):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n_conformant):
+        ps = random_param_sets(rng)
+        if ps["slice_group_change_rate_minus1"] == 0:
+            ps["slice_group_change_rate_minus1"] = 1
+        nal_type = int(rng.choice([1, 5, 1, 1, 20]))
+        ref_idc = int(rng.integers(0, 4))
+        st = int(rng.integers(0, 10))
+        rbsp, nbits = write_header(rng, ps, nal_type, ref_idc, st)
+        out.append((ps, nal_type, ref_idc, np.frombuffer(rbsp, np.uint8), nbits))
+    for k in range(n_garbage):
+        ps = random_param_sets(rng)
+        n = int(rng.integers(0, 40))
+        p_zero = [0.0, 0.3, 0.9][k % 3]
+        d = rng.integers(0, 256, n).astype(np.uint8)
+        d[rng.random(n) < p_zero] = 0
+        out.append((ps, int(rng.choice([1, 5, 20, 21])), int(rng.integers(0, 4)), d, None))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU: emulation
+@pytest.fixture(scope="module")
+def emul():
+    from tests import test_hd_logic
+    import os
+    import subprocess
+    deps = [test_hd_logic.SRC] + [os.path.join(test_hd_logic.HERE, "..", "h264decode_b200", "csrc", f)
+                                  for f in ("annexb_local.cuh", "cabac_lane.cuh", "slice_header.cuh", "tables.inc")]
+    out = test_hd_logic.OUT
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-x", "c++", test_hd_logic.SRC,
+                               "-o", out])
+    L = C.CDLL(out)
+    L.emul_slice_header.restype = None
+    L.emul_slice_header.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p]
+    return L
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_slice_header_walk_matches_oracle_cpu(emul, seed):
+    from h264decode_b200 import capi
+    n_ok = n_panic = n_hang = 0
+    for ps, nal_type, ref_idc, rbsp, nbits in cases(seed, 300, 600):
+        rc, exp = oracle_header(ps, nal_type, ref_idc, rbsp)
+        p = capi.Context.param_sets(**ps)
+        out = np.zeros(1, capi.SLICE_HEADER_DTYPE)
+        buf = np.ascontiguousarray(rbsp)
+        emul.emul_slice_header(C.byref(p), nal_type, ref_idc, buf.ctypes.data if len(buf) else None, len(buf),
+                               out.ctypes.data)
+        compare(out[0], int(out[0]["status"]), rc, exp, (seed, ps, nal_type, ref_idc, rbsp.tobytes().hex()))
+        if nbits is not None:
+            assert rc == orc.OK and exp["bits_read"] == nbits   # the writer and the walk agree on the header's extent
+        n_ok += rc == orc.OK
+        n_panic += rc == orc.PANIC
+        n_hang += rc == orc.HANG
+    assert n_ok > 300 and n_panic > 50 and n_hang > 0, (n_ok, n_panic, n_hang)
+
+
+def test_slice_header_known_answers():
+    """hand-checkable headers: first_mb 0, slice_type 7 (I), pps 0, idr_pic_id 1, POC lsb, qp delta"""
+    ps = dict(random_param_sets(np.random.default_rng(0)), use_separate_color_plane=0, chroma_format=1, frame_mbs_only=1,
+              pic_order_count_type=0, log2_max_pic_order_cnt_lsb_min4=0, bottom_field_pic_order_in_frame_present=0,
+              redundant_pic_cnt_present=0, weighted_pred=0, weighted_bipred=0, entropy_coding_mode=1,
+              deblocking_filter_control_present=0, num_slice_groups_minus1=0, pic_init_qp_minus26=-3)
+    w = BitWriter()
+    w.ue(0); w.ue(7); w.ue(0); w.ue(1); w.u(4, 9); w.u(1, 0); w.u(1, 1); w.ue(4)  # ... no_output 0, long_term 1, se code 4
+    rc, h = oracle_header(ps, 5, 3, np.frombuffer(w.bytes(), np.uint8))
+    assert rc == orc.OK
+    assert (h["FirstMbInSlice"], h["SliceType"], h["PPSID"], h["IDRPicID"], h["PicOrderCntLsb"]) == (0, 7, 0, 1, 9)
+    assert (h["NoOutputOfPriorPicsFlag"], h["LongTermReferenceFlag"], h["CabacInit"]) == (0, 1, 0)
+    assert h["SliceQpDelta"] == -2 and h["SliceQPy"] == 26 - 3 - 2 and h["bits_read"] == len(w.bits)
+    # a P slice reads cabac_init_idc but (reference quirk) no num_ref_idx_active_override_flag
+    w = BitWriter()
+    w.ue(3); w.ue(0); w.ue(0); w.u(4, 2); w.u(1, 0); w.ue(2); w.ue(3)  # ref_pic_list_mod 0 (ref_idc 0), cabac_init 2, se code 3
+    rc, h = oracle_header(ps, 1, 0, np.frombuffer(w.bytes(), np.uint8))
+    assert rc == orc.OK and (h["CabacInit"], h["SliceQpDelta"], h["NumRefIdxActiveOverride"]) == (2, 1, 0)
+    assert h["bits_read"] == len(w.bits)
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_slice_headers_gpu_match_oracle():
+    from h264decode_b200 import capi
+    ctx = capi.Context(0)
+    try:
+        rng = np.random.default_rng(77)
+        for trial in range(6):
+            ps = random_param_sets(rng)
+            if trial % 2 == 0 and ps["slice_group_change_rate_minus1"] == 0:
+                ps["slice_group_change_rate_minus1"] = 3
+            items = []
+            for _ in range(400):
+                nal_type, ref_idc = int(rng.choice([1, 5, 1, 20])), int(rng.integers(0, 4))
+                if rng.random() < 0.6:
+                    rbsp, _ = write_header(rng, ps if ps["slice_group_change_rate_minus1"] else dict(ps, num_slice_groups_minus1=0),
+                                           nal_type, ref_idc, int(rng.integers(0, 10)))
+                    d = np.frombuffer(rbsp, np.uint8)
+                else:
+                    n = int(rng.integers(0, 40))
+                    d = rng.integers(0, 256, n).astype(np.uint8)
+                    d[rng.random(n) < [0.0, 0.4, 0.9][_ % 3]] = 0
+                items.append((nal_type, ref_idc, d))
+            off, parts, pos = [], [], 0
+            for _, _, d in items:
+                off.append(pos)
+                parts.append(d)
+                pos += len(d)
+            data = np.concatenate(parts + [np.zeros(8, np.uint8)])
+            got = ctx.slice_headers(capi.Context.param_sets(**ps), data, off, [len(d) for _, _, d in items],
+                                    [t for t, _, _ in items], [r for _, r, _ in items])
+            for i, (t, r, d) in enumerate(items):
+                rc, exp = oracle_header(ps, t, r, d)
+                compare(got[i], int(got[i]["status"]), rc, exp, (trial, i, d.tobytes().hex()))
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_slice_headers_chained_on_device_after_the_scan():
+    """scan -> slice list -> slice headers without leaving the device: an Annex-B stream whose slice NAL units start
+    with written headers (emulation-prevention escaped like any payload)"""
+    import torch
+    import harness as hz
+    from h264decode_b200 import capi
+    rng = np.random.default_rng(5)
+    ps = dict(random_param_sets(rng), slice_group_change_rate_minus1=2)
+    payloads, headers = [], []
+    for i in range(300):
+        nal_type, ref_idc = (5, 3) if i % 10 == 0 else (1, int(rng.integers(0, 4)))
+        hdr, _ = write_header(rng, ps, nal_type, ref_idc, int(rng.integers(0, 10)))
+        body = rng.integers(0, 256, int(rng.integers(0, 3000))).astype(np.uint8)
+        payloads.append(hz.escape(np.concatenate([np.frombuffer(hdr, np.uint8), body])))
+        headers.append((ref_idc << 5) | nal_type)
+    stream = hz.assemble_annexb(payloads, headers)
+    onal, orbsp = orc.read_nal_units_arrays(stream)
+    sl = np.flatnonzero((onal["type"] == 1) | (onal["type"] == 5))
+    assert len(sl) == 300
+    ctx = capi.Context(0)
+    try:
+        dev = "cuda:0"
+        n = len(stream)
+        d_stream = torch.from_numpy(np.concatenate([stream, np.zeros(64, np.uint8)])).to(dev)
+        d_rbsp = torch.empty(n + 64, dtype=torch.uint8, device=dev)
+        cap = len(onal["start"]) + 8
+        d_nals = torch.empty(cap * 32, dtype=torch.uint8, device=dev)
+        d_sum = torch.zeros(64, dtype=torch.uint8, device=dev)
+        d_off = torch.empty(cap, dtype=torch.int64, device=dev)
+        d_len = torch.empty(cap, dtype=torch.int32, device=dev)
+        d_snal = torch.empty(cap, dtype=torch.int32, device=dev)
+        d_ns = torch.zeros(4, dtype=torch.int32, device=dev)
+        d_out = torch.empty(cap * capi.SLICE_HEADER_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        ctx.annexb_scan_dev(d_stream.data_ptr(), n, d_rbsp.data_ptr(), d_nals.data_ptr(), None, cap, d_sum.data_ptr(), 0)
+        ctx.slice_select_dev(d_nals.data_ptr(), d_sum.data_ptr(), cap, 0, cap, d_off.data_ptr(), d_len.data_ptr(),
+                             d_snal.data_ptr(), d_ns.data_ptr())
+        ctx.slice_headers_dev(capi.Context.param_sets(**ps), d_rbsp.data_ptr(), n + 16, d_nals.data_ptr(),
+                              d_snal.data_ptr(), len(sl), d_out.data_ptr())
+        ctx.sync()
+        assert int(d_ns.cpu()[0]) == len(sl)
+        got = np.frombuffer(d_out.cpu().numpy().tobytes(), dtype=capi.SLICE_HEADER_DTYPE, count=len(sl))
+        n_ok = 0
+        for i, k in enumerate(sl):
+            rb = orbsp[int(onal["rbsp_off"][k]):int(onal["rbsp_off"][k]) + int(onal["rbsp_len"][k])]
+            rc, exp = oracle_header(ps, int(onal["type"][k]), int(onal["ref_idc"][k]), rb)
+            compare(got[i], int(got[i]["status"]), rc, exp, i)
+            n_ok += rc == orc.OK
+        assert n_ok == len(sl)
+    finally:
+        ctx.close()
