@@ -31,9 +31,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # DRAM bytes (read + write) per algorithmic byte of the Annex-B pass, from the ncu capture of this command line
-# (profiles/r1_ncu_scan_v10_full.txt: dram__bytes_read.sum + dram__bytes_write.sum of all launches of one pass)
-TRAFFIC_PER_ALG_BYTE = None
-TRAFFIC_SOURCE = None
+# (profiles/r1_ncu_launch_list_bench.csv: dram__bytes_read.sum + dram__bytes_write.sum of the seven kernels of one pass,
+# 7.885 GB against 7.866 GB algorithmic; annexb_copy_kernel alone 7.826 GB, profiles/r1_ncu_copy_kernel_summary.txt)
+TRAFFIC_PER_ALG_BYTE = 1.0024
+TRAFFIC_SOURCE = "ncu dram__bytes_read.sum + dram__bytes_write.sum per pass (profiles/r1_ncu_launch_list_bench.csv)"
 MEAN_BINS = 455_000      # ~50 KB of CABAC data per slice at ~0.88 bit/bin
 N_ACTIVE = 64
 N_CTX = 64
@@ -293,28 +294,38 @@ def run_gpu(args, rank, world, local_rank):
     t_cabac_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
 
     # ---- e2e through the host-buffer entry point
-    h_stream = ctx.host_alloc(n)
-    ctx.d2h(h_stream, d_stream.data_ptr())
-    ctx.sync()
     del d_bins, d_rbsp
     torch.cuda.empty_cache()
     e2e_steps = max(2, min(args.steps, 4))
-    # warm-up: both job slots grow their pinned / device buffers
-    tk = [_stream_submit_raw(ctx, capi, h_stream, ops, n_ops, p, flags) for _ in range(2)]
-    for t in tk:
-        r = _stream_wait_raw(ctx, capi, t)
-    barrier()
-    # timed: every step copies its stream in and its results out; consecutive steps overlap (two jobs in flight:
-    # H2D of step k+1 | kernels of step k | D2H of step k-1), which is how an ingest loop drives the library
-    t0 = time.perf_counter()
-    pending = [_stream_submit_raw(ctx, capi, h_stream, ops, n_ops, p, flags)]
-    for k in range(1, e2e_steps):
-        pending.append(_stream_submit_raw(ctx, capi, h_stream, ops, n_ops, p, flags))
+    e2e_error = None
+    t_e2e, e2e_ok, h_stream = 0.0, True, None
+    try:
+        h_stream = ctx.host_alloc(n)
+        ctx.d2h(h_stream, d_stream.data_ptr())
+        ctx.sync()
+        # warm-up: both job slots grow their pinned / device buffers
+        tk = [_stream_submit_raw(ctx, capi, h_stream, ops, n_ops, p, flags) for _ in range(2)]
+        for t in tk:
+            r = _stream_wait_raw(ctx, capi, t)
+        barrier()
+        # timed: every step copies its stream in and its results out; consecutive steps overlap (two jobs in flight:
+        # H2D of step k+1 | kernels of step k | D2H of step k-1), which is how an ingest loop drives the library
+        t0 = time.perf_counter()
+        pending = [_stream_submit_raw(ctx, capi, h_stream, ops, n_ops, p, flags)]
+        for k in range(1, e2e_steps):
+            pending.append(_stream_submit_raw(ctx, capi, h_stream, ops, n_ops, p, flags))
+            r = _stream_wait_raw(ctx, capi, pending.pop(0))
         r = _stream_wait_raw(ctx, capi, pending.pop(0))
-    r = _stream_wait_raw(ctx, capi, pending.pop(0))
-    torch.cuda.synchronize()
-    t_e2e = (time.perf_counter() - t0) / e2e_steps
-    e2e_ok = r["n_slices"] == n_slices and r["total_bins"] == total_bins
+        torch.cuda.synchronize()
+        t_e2e = (time.perf_counter() - t0) / e2e_steps
+        e2e_ok = r["n_slices"] == n_slices and r["total_bins"] == total_bins
+    except Exception as ex:  # e.g. not enough pinned host memory for every rank of a big box: report, do not die
+        e2e_error = "%s: %s" % (type(ex).__name__, ex)
+        if dist is not None:
+            try:
+                barrier()
+            except Exception:
+                pass
     d2h_bytes = int(boff[-1]) * 4 + n_slices * 32 + n_slices * 4 + n_nals * 32 + 48 + 4
     h2d_bytes = n + len(ops) * 2 + n_slices * (8 + 4) + (n_slices + 1) * 8
 
@@ -324,10 +335,12 @@ def run_gpu(args, rank, world, local_rank):
         t = torch.tensor([t_total_ms, t_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_max_ms, t_e2e_max = float(t[0]), float(t[1])
-        c = torch.tensor([total_bins, n, int(ok and e2e_ok)], dtype=torch.int64, device=dev)
+        c = torch.tensor([total_bins, n, int(ok and e2e_ok), int(e2e_error is not None)], dtype=torch.int64, device=dev)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         bins_all, bytes_all = int(c[0]), int(c[1])
         ok = int(c[2]) == world
+        if int(c[3]) and e2e_error is None:
+            e2e_error = "the end-to-end leg failed on %d other rank(s)" % int(c[3])
     else:
         ok = ok and e2e_ok
 
@@ -353,7 +366,8 @@ def run_gpu(args, rank, world, local_rank):
             "roofline_cabac": {"bound": "issue/latency (serial integer chain; not HBM, not tensor)",
                                "bins_per_s_per_gpu": total_bins / (t_cabac_ms * 1e-3),
                                "lanes": n_slices, "hbm_gbs_implied": total_bins * 0.235 / (t_cabac_ms * 1e-3) / 1e9},
-            "e2e": {"value": bins_all / t_e2e_max, "unit": "bins/s", "h2d_bytes_per_step": h2d_bytes,
+            "e2e": {"value": (bins_all / t_e2e_max) if e2e_error is None else None, "error": e2e_error,
+                    "unit": "bins/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": t_e2e_max * 1e3, "steps": e2e_steps,
                     "api": "h264b_stream_submit / h264b_stream_wait, two jobs in flight (pinned host stream in; NAL index, "
                            "packed bins, final states out; copies of consecutive steps overlap kernels)"},
@@ -379,7 +393,8 @@ def run_gpu(args, rank, world, local_rank):
                 out["cpu_baseline"]["single_core_bins_per_s"] = b1 / s1
                 out["cpu_baseline"]["cabac_bins_per_s_1core"] = b1 / s1_cabac
         print(json.dumps(out))
-    ctx.host_free(h_stream)
+    if h_stream is not None:
+        ctx.host_free(h_stream)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
