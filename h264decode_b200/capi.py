@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libh264b200.so")
 
 OK, E_INVALID, E_CUDA, E_NOMEM, E_CAPACITY, E_NO_DEVICE = range(6)
-TABLES_SPEC, BYPASS_SPEC_OR, CABAC_FINAL_TERMINATE, STREAM_WANT_RBSP = 1, 2, 4, 8
+TABLES_SPEC, BYPASS_SPEC_OR, CABAC_FINAL_TERMINATE, STREAM_WANT_RBSP, STREAM_SLICE_HEADERS = 1, 2, 4, 8, 16
 F_OVERRUN, F_HAS_EPB, F_SHORT_NAL = 1, 2, 4
 OP_DECISION, OP_BYPASS, OP_TERMINATE = 0, 1, 2
 
@@ -61,13 +61,13 @@ class CabacJob(C.Structure):
 class StreamJob(C.Structure):
     _fields_ = [("stream", C.c_void_p), ("n", C.c_uint64), ("slice_data_offset", C.c_uint32), ("n_ctx", C.c_uint32),
                 ("ops", C.c_void_p), ("n_ops_max", C.c_uint32), ("n_ops", C.c_void_p), ("qp", C.c_void_p),
-                ("max_slices", C.c_uint32), ("flags", C.c_uint32)]
+                ("max_slices", C.c_uint32), ("flags", C.c_uint32), ("param_sets", C.c_void_p)]
 
 
 class StreamResult(C.Structure):
     _fields_ = [("scan", ScanSummary), ("nals", C.c_void_p), ("n_slices", C.c_uint32), ("reserved", C.c_uint32),
                 ("slice_nal", C.c_void_p), ("bins_off", C.c_void_p), ("bins", C.c_void_p), ("final", C.c_void_p),
-                ("total_bins", C.c_uint64), ("rbsp", C.c_void_p), ("d_rbsp", C.c_void_p), ("ext", C.c_void_p)]
+                ("total_bins", C.c_uint64), ("rbsp", C.c_void_p), ("d_rbsp", C.c_void_p), ("ext", C.c_void_p), ("headers", C.c_void_p)]
 
 
 PARAM_SET_FIELDS = ["use_separate_color_plane", "chroma_format", "frame_mbs_only", "pic_order_count_type",
@@ -425,11 +425,14 @@ class Context:
         self._check(_lib.h264b_slice_headers_dev(self.h, C.byref(params), d_bytes, total_bytes, None, None, None, None,
                                                  d_nals, d_slice_nal, n_slices, d_out))
 
-    def stream_submit(self, stream, ops, n_ops, qp, idc, n_ctx, slice_data_offset=0, flags=0):
-        """asynchronous form: returns (ticket, keepalive); pass both to stream_wait.  Up to two jobs in flight."""
+    def stream_submit(self, stream, ops, n_ops, qp, idc, n_ctx, slice_data_offset=0, flags=0, param_sets=None,
+                      max_slices=None):
+        """asynchronous form: returns (ticket, keepalive); pass both to stream_wait.  Up to two jobs in flight.
+        param_sets (ParamSets): take SliceQPY / cabac_init_idc / the CABAC data offset from the slice headers
+        (qp, idc may then be None; max_slices bounds the slice count)."""
         s = np.ascontiguousarray(stream, dtype=np.uint8)
         ops = np.ascontiguousarray(ops, dtype=np.uint16)
-        p = self.slice_qp(qp, idc)
+        p = self.slice_qp(qp, idc) if qp is not None else None
         nops = None if n_ops is None else np.ascontiguousarray(n_ops, dtype=np.uint32)
         j = StreamJob()
         j.stream = s.ctypes.data
@@ -439,12 +442,13 @@ class Context:
         j.ops = ops.ctypes.data
         j.n_ops_max = len(ops)
         j.n_ops = nops.ctypes.data if nops is not None else None
-        j.qp = p.ctypes.data
-        j.max_slices = len(p)
-        j.flags = flags
+        j.qp = p.ctypes.data if p is not None else None
+        j.max_slices = len(p) if p is not None else int(max_slices)
+        j.flags = flags | (STREAM_SLICE_HEADERS if param_sets is not None else 0)
+        j.param_sets = C.addressof(param_sets) if param_sets is not None else None
         t = C.c_uint64()
         self._check(_lib.h264b_stream_submit(self.h, C.byref(j), C.byref(t)))
-        return t.value, (s, ops, p, nops, j)
+        return t.value, (s, ops, p, nops, j, param_sets)
 
     def stream_wait(self, ticket, keepalive=None):
         r = StreamResult()
@@ -459,4 +463,5 @@ class Context:
         return dict(scan=r.scan.as_dict(), nals=_from_ptr(r.nals, NAL_DTYPE, r.scan.n_nals),
                     slice_nal=_from_ptr(r.slice_nal, np.uint32, ns), bins_off=boff, bins_flat=flat,
                     bins=[flat[int(boff[i]):int(boff[i + 1])] for i in range(ns)],
-                    final=_from_ptr(r.final, FINAL_DTYPE, ns), total_bins=r.total_bins)
+                    final=_from_ptr(r.final, FINAL_DTYPE, ns), total_bins=r.total_bins,
+                    headers=_from_ptr(r.headers, SLICE_HEADER_DTYPE, ns) if r.headers else None)

@@ -426,9 +426,9 @@ int32_t h264b_cabac_decode(h264b_ctx *ctx, const h264b_cabac_job *job) {
 
 // ---- the whole front end of one stream, asynchronously: two jobs in flight per context -------------------------
 // device buffers of a slot: 0 stream  1 rbsp  2 nals  3 summary + slice count  4 off  5 len  6 slice_nal  7 ops
-//                           8 n_ops  9 qp  10 bins_off  11 bins  12 final  13 ext
+//                           8 n_ops  9 qp  10 bins_off  11 bins  12 final  13 ext  14 slice headers
 // pinned buffers of a slot: 0 nals  1 bins_off  2 bins  3 final  4 slice_nal  5 summary + slice count
-//                           9 rbsp  10 ext (H264B_STREAM_WANT_RBSP)
+//                           9 rbsp  10 ext (H264B_STREAM_WANT_RBSP)  11 slice headers
 //                           6 ops  7 n_ops  8 qp (staging of the caller's small arrays: they may be pageable, and a
 //                           pageable source would make the copies -- and with them the whole submit -- synchronous)
 static int slot_dev(h264b_ctx *ctx, StreamSlot *sl, int i, size_t bytes, void **out) {
@@ -470,7 +470,9 @@ int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_
     CHECK_CTX(ctx);
     if (!job || !ticket) return H264B_E_INVALID;
     const h264b_stream_job &j = *job;
-    if ((!j.stream && j.n) || (j.max_slices && (!j.qp || (!j.ops && j.n_ops_max))))
+    const bool from_headers = (j.flags & H264B_STREAM_SLICE_HEADERS) != 0 && j.max_slices != 0;
+    if ((!j.stream && j.n) || (j.max_slices && ((!j.qp && !from_headers) || (!j.ops && j.n_ops_max))) ||
+        (from_headers && !j.param_sets))
         return set_error(ctx, H264B_E_INVALID, "stream_submit: null pointer in job");
     StreamSlot *sl = ctx->slot[ctx->next_ticket & 1];
     if (sl->busy) return set_error(ctx, H264B_E_INVALID, "stream_submit: two jobs are in flight, wait for one first");
@@ -529,8 +531,10 @@ int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_
         H264B_CUDA(ctx, cudaMemcpyAsync(d_ops, h_ops, (size_t)j.n_ops_max * 2, cudaMemcpyHostToDevice, in));
     }
     if (j.max_slices) {
-        memcpy(h_qp, j.qp, (size_t)j.max_slices * sizeof(h264b_slice_qp));
-        H264B_CUDA(ctx, cudaMemcpyAsync(d_qp, h_qp, ms * sizeof(h264b_slice_qp), cudaMemcpyHostToDevice, in));
+        if (!from_headers) {
+            memcpy(h_qp, j.qp, (size_t)j.max_slices * sizeof(h264b_slice_qp));
+            H264B_CUDA(ctx, cudaMemcpyAsync(d_qp, h_qp, ms * sizeof(h264b_slice_qp), cudaMemcpyHostToDevice, in));
+        }
         if (j.n_ops) {
             memcpy(h_nops, j.n_ops, (size_t)j.max_slices * 4);
             H264B_CUDA(ctx, cudaMemcpyAsync(d_nops, h_nops, ms * 4, cudaMemcpyHostToDevice, in));
@@ -548,8 +552,16 @@ int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_
     if (j.flags & H264B_STREAM_WANT_RBSP) RC(slot_dev(ctx, sl, 13, (size_t)cap * sizeof(h264b_nal_ext), &d_ext));
     RC(launch_annexb_scan(ctx, (const uint8_t *)d_stream, j.n, (uint8_t *)d_rbsp, (h264b_nal *)d_nals,
                           (h264b_nal_ext *)d_ext, cap, (h264b_scan_summary *)d_sum, j.flags));
-    RC(launch_slice_select(ctx, (const h264b_nal *)d_nals, (const h264b_scan_summary *)d_sum, cap, j.slice_data_offset,
-                           j.max_slices, (uint64_t *)d_off, (uint32_t *)d_len, (uint32_t *)d_snal, d_ns));
+    RC(launch_slice_select(ctx, (const h264b_nal *)d_nals, (const h264b_scan_summary *)d_sum, cap,
+                           from_headers ? 0u : j.slice_data_offset, j.max_slices, (uint64_t *)d_off, (uint32_t *)d_len,
+                           (uint32_t *)d_snal, d_ns));
+    void *d_hdr = nullptr;
+    if (from_headers) {  // SliceQPY, cabac_init_idc and the start of the CABAC data come from the slices' own headers
+        RC(slot_dev(ctx, sl, 14, ms * sizeof(h264b_slice_header), &d_hdr));
+        RC(launch_stream_slice_headers(ctx, j.param_sets, (const uint8_t *)d_rbsp, j.n + 16, (const h264b_nal *)d_nals,
+                                       (const uint32_t *)d_snal, d_ns, j.max_slices, (h264b_slice_header *)d_hdr,
+                                       (uint64_t *)d_off, (uint32_t *)d_len, (h264b_slice_qp *)d_qp));
+    }
     if (j.max_slices) {
         h264b_cabac_job cj;
         memset(&cj, 0, sizeof(cj));
@@ -580,6 +592,11 @@ int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_
         if (total_words) H264B_CUDA(ctx, cudaMemcpyAsync(h_bins, d_bins, total_words * 4, cudaMemcpyDeviceToHost, out));
         H264B_CUDA(ctx, cudaMemcpyAsync(h_fin, d_fin, ms * sizeof(h264b_cabac_final), cudaMemcpyDeviceToHost, out));
         H264B_CUDA(ctx, cudaMemcpyAsync(h_snal, d_snal, ms * 4, cudaMemcpyDeviceToHost, out));
+    }
+    if (from_headers) {
+        void *h_hdr;
+        RC(slot_pin(ctx, sl, 11, ms * sizeof(h264b_slice_header), &h_hdr));
+        H264B_CUDA(ctx, cudaMemcpyAsync(h_hdr, d_hdr, ms * sizeof(h264b_slice_header), cudaMemcpyDeviceToHost, out));
     }
     if (j.flags & H264B_STREAM_WANT_RBSP) {  // position-preserving layout: the buffer is as long as the stream
         void *h_rbsp, *h_ext;
@@ -648,6 +665,9 @@ int32_t h264b_stream_wait(h264b_ctx *ctx, uint64_t ticket, h264b_stream_result *
     res->rbsp = (sl->job.flags & H264B_STREAM_WANT_RBSP) ? (const uint8_t *)sl->h[9] : nullptr;
     res->d_rbsp = (const uint8_t *)sl->d[1];
     res->ext = (sl->job.flags & H264B_STREAM_WANT_RBSP) ? (const h264b_nal_ext *)sl->h[10] : nullptr;
+    res->headers = ((sl->job.flags & H264B_STREAM_SLICE_HEADERS) && sl->job.max_slices)
+                       ? (const h264b_slice_header *)sl->h[11]
+                       : nullptr;
     return H264B_OK;
 }
 

@@ -41,7 +41,7 @@ struct h264b_ctx {
     int trace;
 };
 
-enum { kSlotDev = 14, kSlotPin = 11 };
+enum { kSlotDev = 15, kSlotPin = 12 };
 struct StreamSlot {
     void *d[kSlotDev];
     size_t d_bytes[kSlotDev];
@@ -90,6 +90,10 @@ int launch_nal_frames(h264b_ctx *ctx, const uint8_t *d_frames, uint64_t total, c
 int launch_ctx_init(h264b_ctx *ctx, const h264b_slice_qp *d_params, uint32_t n_slices, uint32_t n_ctx,
                     uint8_t *d_states, uint32_t flags);
 int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n_slices = nullptr);
+int launch_stream_slice_headers(h264b_ctx *ctx, const h264b_param_sets *params, const uint8_t *d_rbsp, uint64_t total,
+                                const h264b_nal *d_nals, const uint32_t *d_slice_nal, const uint32_t *d_n_slices,
+                                uint32_t max_slices, h264b_slice_header *d_hdr, uint64_t *d_off, uint32_t *d_len,
+                                h264b_slice_qp *d_qp);
 int launch_slice_select(h264b_ctx *ctx, const h264b_nal *d_nals, const h264b_scan_summary *d_summary,
                         uint32_t nal_cap, uint32_t slice_data_offset, uint32_t max_slices, uint64_t *d_off,
                         uint32_t *d_len, uint32_t *d_slice_nal, uint32_t *d_n_slices);

@@ -16,12 +16,13 @@ struct SliceHeaderArgs {
     const h264b_nal *nals;
     const uint32_t *slice_nal;
     uint32_t n_slices;
+    const uint32_t *n_slices_dev;  // actual count on the device (n_slices is then the bound), or NULL
     h264b_slice_header *out;
 };
 
 __global__ void __launch_bounds__(128) slice_header_kernel(SliceHeaderArgs a) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= a.n_slices) return;
+    if (s >= a.n_slices || (a.n_slices_dev && s >= *a.n_slices_dev)) return;
     uint64_t off, len;
     uint32_t type, ref_idc;
     if (a.nals) {
@@ -43,10 +44,70 @@ __global__ void __launch_bounds__(128) slice_header_kernel(SliceHeaderArgs a) {
     a.out[s] = h;
 }
 
+// The CABAC stage's per-slice inputs from the parsed headers: (SliceQPY, cabac_init_idc) for the K4 rule and the start
+// of the CABAC data = the first byte boundary behind the header (cabac_alignment_one_bit, slice.go:583-587).
+__global__ void __launch_bounds__(256) slice_params_kernel(const h264b_slice_header *hdr, const uint32_t *n_slices_dev,
+                                                           uint32_t max_slices, uint64_t *off, uint32_t *len,
+                                                           h264b_slice_qp *qp) {
+    const uint32_t n = *n_slices_dev < max_slices ? *n_slices_dev : max_slices;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const h264b_slice_header &h = hdr[s];
+        h264b_slice_qp p;
+        p.slice_qp_y = 0;
+        p.cabac_init_idc = -1;
+        if (h.status != H264B_SH_OK) {
+            len[s] = 0;  // nothing to decode: the engine flags the slice (H264B_F_OVERRUN)
+        } else {
+            const int64_t q = h.slice_qp_y < -1000000 ? -1000000 : (h.slice_qp_y > 1000000 ? 1000000 : h.slice_qp_y);
+            p.slice_qp_y = (int32_t)q;  // (PreCtxState clips to 0..51 anyway)
+            const int64_t t5 = (h.slice_type >= 0 && h.slice_type <= 9) ? h.slice_type % 5 : -1;
+            const bool intra = t5 == 2 || t5 == 4;  // I, SI: no cabac_init_idc in the header -> the I / SI column
+            const int64_t idc = h.cabac_init_idc;
+            p.cabac_init_idc = intra ? -1 : (int32_t)(idc < -2 ? -2 : (idc > 1000 ? 1000 : idc));
+            const uint64_t skip = (h.header_bits + 7u) / 8u;
+            const uint64_t l = len[s];
+            off[s] += skip < l ? skip : l;
+            len[s] = (uint32_t)(skip < l ? l - skip : 0u);
+        }
+        qp[s] = p;
+    }
+}
+
+int launch_stream_slice_headers(h264b_ctx *ctx, const h264b_param_sets *params, const uint8_t *d_rbsp, uint64_t total,
+                                const h264b_nal *d_nals, const uint32_t *d_slice_nal, const uint32_t *d_n_slices,
+                                uint32_t max_slices, h264b_slice_header *d_hdr, uint64_t *d_off, uint32_t *d_len,
+                                h264b_slice_qp *d_qp);
+
 int launch_slice_headers(h264b_ctx *ctx, const SliceHeaderArgs &a) {
     if (!a.n_slices) return H264B_OK;
     slice_header_kernel<<<(a.n_slices + 127) / 128, 128, 0, ctx->stream>>>(a);
     H264B_LAUNCH_CHECK(ctx, "slice_header_kernel");
+    return H264B_OK;
+}
+
+int launch_stream_slice_headers(h264b_ctx *ctx, const h264b_param_sets *params, const uint8_t *d_rbsp, uint64_t total,
+                                const h264b_nal *d_nals, const uint32_t *d_slice_nal, const uint32_t *d_n_slices,
+                                uint32_t max_slices, h264b_slice_header *d_hdr, uint64_t *d_off, uint32_t *d_len,
+                                h264b_slice_qp *d_qp) {
+    if (!max_slices) return H264B_OK;
+    SliceHeaderArgs a;
+    a.ps = *params;
+    a.bytes = d_rbsp;
+    a.total_bytes = total;
+    a.off = nullptr;
+    a.len = nullptr;
+    a.nal_type = a.nal_ref_idc = nullptr;
+    a.nals = d_nals;
+    a.slice_nal = d_slice_nal;
+    a.n_slices = max_slices;
+    a.n_slices_dev = d_n_slices;
+    a.out = d_hdr;
+    int rc = launch_slice_headers(ctx, a);
+    if (rc) return rc;
+    int blocks = (int)((max_slices + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    slice_params_kernel<<<blocks, 256, 0, ctx->stream>>>(d_hdr, d_n_slices, max_slices, d_off, d_len, d_qp);
+    H264B_LAUNCH_CHECK(ctx, "slice_params_kernel");
     return H264B_OK;
 }
 
@@ -77,6 +138,7 @@ extern "C" int32_t h264b_slice_headers_dev(h264b_ctx *ctx, const h264b_param_set
     a.nals = d_nals;
     a.slice_nal = d_slice_nal;
     a.n_slices = n_slices;
+    a.n_slices_dev = nullptr;
     a.out = d_out;
     return launch_slice_headers(ctx, a);
 }

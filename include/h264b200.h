@@ -43,6 +43,12 @@ extern "C" {
 #define H264B_BYPASS_SPEC_OR 0x2u        /* DecodeBypass as (O<<1)|bit (A5); default REF: O<<=1 then O<<=bit */
 #define H264B_CABAC_FINAL_TERMINATE 0x4u /* after a slice's n_ops bins decode one more DecodeTerminate bin */
 #define H264B_STREAM_WANT_RBSP 0x8u      /* h264b_stream_*: also copy the RBSP buffer and the extension headers back */
+#define H264B_STREAM_SLICE_HEADERS 0x10u /* h264b_stream_*: every slice NAL starts with a slice header: parse it on the
+                                            device (job.param_sets) and take SliceQPY, cabac_init_idc (I / SI slices:
+                                            NoCabacInitIdc) and the start of the CABAC data (the byte boundary after
+                                            the header, slice.go:583-587) from it; job.qp and slice_data_offset are
+                                            ignored.  A slice whose header the reference cannot walk is not decoded
+                                            (its final record carries H264B_F_OVERRUN). */
 
 /* per-unit flag bits written by kernels (never abort a batch; SURVEY.md §5 failure handling) */
 #define H264B_F_OVERRUN 0x1u    /* the reference would have panicked reading past the slice's last byte (A10) */
@@ -282,6 +288,7 @@ typedef struct {
     const h264b_slice_qp *qp;     /* [max_slices] */
     uint32_t max_slices;          /* 0: split + strip only (no CABAC stage; ops / n_ops / qp are ignored) */
     uint32_t flags;
+    const h264b_param_sets *param_sets; /* H264B_STREAM_SLICE_HEADERS: the active SPS / PPS fields (host pointer) */
 } h264b_stream_job;
 
 typedef struct {
@@ -297,6 +304,7 @@ typedef struct {
     const uint8_t *rbsp;            /* job.n bytes, indexed by h264b_nal.rbsp_off (H264B_STREAM_WANT_RBSP), else NULL */
     const uint8_t *d_rbsp;          /* the same buffer on the device (for follow-up h264b_*_dev calls) */
     const h264b_nal_ext *ext;       /* [scan.n_nals] (H264B_STREAM_WANT_RBSP), else NULL */
+    const h264b_slice_header *headers; /* [n_slices] (H264B_STREAM_SLICE_HEADERS), else NULL */
 } h264b_stream_result;
 
 int32_t h264b_stream_decode(h264b_ctx *ctx, const h264b_stream_job *job, h264b_stream_result *result);

@@ -71,8 +71,9 @@ class BitWriter:
         return bytes(int("".join(map(str, b[i:i + 8])), 2) for i in range(0, len(b), 8)) + trailing
 
 
-def write_header(rng, ps, nal_type, ref_idc, slice_type):
-    """a header the reference's walk accepts (what it reads, not what the standard says), random field values"""
+def write_header(rng, ps, nal_type, ref_idc, slice_type, qp_delta=None, cabac_init_idc=None, raw=False):
+    """a header the reference's walk accepts (what it reads, not what the standard says), random field values;
+    qp_delta / cabac_init_idc fix those two fields; raw=True returns the BitWriter instead of bytes"""
     w = BitWriter()
     name = ["P", "B", "I", "SP", "SI"][slice_type % 5]
     w.ue(int(rng.integers(0, 400)))
@@ -150,8 +151,11 @@ def write_header(rng, ps, nal_type, ref_idc, slice_type):
         else:
             w.u(1, 0)   # adaptive marking ends in a panic or a hang in the reference: covered by the garbage cases
     if ps["entropy_coding_mode"] == 1 and name not in ("I", "SI"):
-        w.ue(int(rng.integers(0, 3)))
-    w.se_ref(int(rng.integers(0, 50)))
+        w.ue(int(rng.integers(0, 3)) if cabac_init_idc is None else cabac_init_idc)
+    if qp_delta is None:
+        w.se_ref(int(rng.integers(0, 50)))
+    else:   # the reference's se(): codeNum k -> (-1)^(k+1) * floor(k/2)
+        w.se_ref(2 * qp_delta + 1 if qp_delta > 0 else -2 * qp_delta)
     if name in ("SP", "SI"):
         if name == "SP":
             w.u(1, int(rng.integers(0, 2)))
@@ -166,6 +170,8 @@ def write_header(rng, ps, nal_type, ref_idc, slice_type):
         q = ps["pic_size_in_map_units_minus1"] // ps["slice_group_change_rate_minus1"] + 1
         n = int(np.ceil(np.log2(q)))
         w.u(n, int(rng.integers(0, 1 << n)) if n else 0)
+    if raw:
+        return w
     return w.bytes(), len(w.bits)
 
 
@@ -369,3 +375,63 @@ def test_slice_headers_chained_on_device_after_the_scan():
         assert n_ok == len(sl)
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_stream_pipeline_takes_cabac_parameters_from_the_slice_headers():
+    """scan -> slice list -> slice headers -> CABAC in one job (H264B_STREAM_SLICE_HEADERS): SliceQPY, cabac_init_idc
+    and the start of the CABAC data come from the stream.  Each slice = written header, cabac_alignment_one_bits up to
+    the byte boundary, then CABAC data the test encoder produced for exactly those (qp, idc)."""
+    import harness as hz
+    from h264decode_b200 import capi
+    rng = np.random.default_rng(2024)
+    ps = dict(random_param_sets(rng), entropy_coding_mode=1, slice_group_change_rate_minus1=2, pic_init_qp_minus26=-4)
+    n, n_active, n_ctx = 96, 64, 64
+    ops = hz.gen_schedule(2, 2500, n_active)
+    n_ops = rng.integers(50, 2500, n).astype(np.uint32)
+    slice_types = rng.integers(0, 10, n)
+    qp_delta = rng.integers(-20, 21, n)
+    idc_hdr = rng.integers(0, 3, n)
+    qp = (26 + ps["pic_init_qp_minus26"] + qp_delta).astype(np.int32)
+    intra = np.isin(slice_types % 5, (2, 4))
+    idc = np.where(intra, -1, idc_hdr).astype(np.int32)
+    g = hz.gen_cabac_slices(2, ops, n_ops, n_active, n_ctx, qp, idc)
+    payloads, nal_hdr = [], []
+    for s in range(n):
+        nal_type, ref_idc = (5, 3) if s % 7 == 0 else (1, int(rng.integers(0, 4)))
+        w = write_header(rng, ps, nal_type, ref_idc, int(slice_types[s]), qp_delta=int(qp_delta[s]),
+                         cabac_init_idc=int(idc_hdr[s]), raw=True)
+        bits = w.bits + [1] * (-len(w.bits) % 8)     # cabac_alignment_one_bit
+        hdr = bytes(int("".join(map(str, bits[i:i + 8])), 2) for i in range(0, len(bits), 8))
+        data = g["data"][s, :g["lens"][s]]
+        payloads.append(hz.escape(np.concatenate([np.frombuffer(hdr, np.uint8), data])))
+        nal_hdr.append((ref_idc << 5) | nal_type)
+    stream = hz.assemble_annexb(payloads, nal_hdr)
+    ctx = capi.Context(0)
+    try:
+        flags = capi.BYPASS_SPEC_OR | capi.CABAC_FINAL_TERMINATE
+        t = ctx.stream_submit(stream, ops, n_ops, None, None, n_ctx, flags=flags,
+                              param_sets=capi.Context.param_sets(**ps), max_slices=n + 3)
+        r = ctx.stream_wait(*t)
+    finally:
+        ctx.close()
+    assert len(r["final"]) == n and r["headers"] is not None
+    onal, orbsp = orc.read_nal_units_arrays(stream)
+    sl = np.flatnonzero((onal["type"] == 1) | (onal["type"] == 5))
+    term = np.array([orc.make_op(orc.OP_TERMINATE)], np.uint16)
+    for s, k in enumerate(sl):
+        rb = orbsp[int(onal["rbsp_off"][k]):int(onal["rbsp_off"][k]) + int(onal["rbsp_len"][k])]
+        rc, h = oracle_header(ps, int(onal["type"][k]), int(onal["ref_idc"][k]), rb)
+        assert rc == orc.OK
+        compare(r["headers"][s], int(r["headers"][s]["status"]), rc, h, s)
+        assert h["SliceQPy"] == qp[s] and (intra[s] or h["CabacInit"] == idc[s])
+        skip = (h["bits_read"] + 7) // 8
+        init = orc.ctx_init(np.array([h["SliceQPy"]], np.int32), np.array([idc[s]], np.int32), n_ctx)[0]
+        rc, bins, fin, _ = orc.cabac_decode_slice(rb[skip:], np.concatenate([ops[:n_ops[s]], term]), init,
+                                                  orc.BYPASS_SPEC_OR)
+        assert rc == orc.OK
+        nw = (int(n_ops[s]) + 1) // 32
+        assert np.array_equal(r["bins"][s][:nw], bins[:nw]), s
+        assert np.array_equal(r["bins"][s][:nw], g["bins"][s, :nw]), s      # ... which are the bins the encoder coded
+        assert (r["final"]["cod_i_range"][s], r["final"]["cod_i_offset"][s], r["final"]["bits_read"][s]) == (
+            fin["codIRange"], fin["codIOffset"], fin["bitsRead"]), s
