@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libh264b200.so")
+LIB_PATH = os.environ.get("H264B_LIB") or os.path.join(_HERE, "libh264b200.so")  # (H264B_LIB: experiment builds)
 
 OK, E_INVALID, E_CUDA, E_NOMEM, E_CAPACITY, E_NO_DEVICE = range(6)
 TABLES_SPEC, BYPASS_SPEC_OR, CABAC_FINAL_TERMINATE, STREAM_WANT_RBSP, STREAM_SLICE_HEADERS = 1, 2, 4, 8, 16

@@ -17,7 +17,10 @@
 
 namespace h264b {
 
-constexpr int kWarpsPerCta = 2;
+#ifndef H264B_CABAC_WARPS
+#define H264B_CABAC_WARPS 2
+#endif
+constexpr int kWarpsPerCta = H264B_CABAC_WARPS;
 
 struct CabacArgs {
     h264b_cabac_job j;
