@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("H264B_LIB") or os.path.join(_HERE, "libh264b200.so") 
 
 OK, E_INVALID, E_CUDA, E_NOMEM, E_CAPACITY, E_NO_DEVICE = range(6)
 TABLES_SPEC, BYPASS_SPEC_OR, CABAC_FINAL_TERMINATE, STREAM_WANT_RBSP, STREAM_SLICE_HEADERS = 1, 2, 4, 8, 16
+STREAM_PARAM_SETS = 32
 F_OVERRUN, F_HAS_EPB, F_SHORT_NAL = 1, 2, 4
 OP_DECISION, OP_BYPASS, OP_TERMINATE = 0, 1, 2
 
@@ -26,6 +27,8 @@ SYMBOLS = [
     "h264b_state_transition", "h264b_stream_decode", "h264b_stream_submit", "h264b_stream_wait",
     "h264b_slice_headers_dev", "h264b_slice_headers",
     "h264b_slice_select_dev",
+    "h264b_parse_sps", "h264b_parse_pps", "h264b_parse_sps_dev", "h264b_parse_pps_dev", "h264b_make_param_sets",
+    "h264b_param_set_select_dev",
 ]
 
 NAL_DTYPE = np.dtype([("start", "<u8"), ("rbsp_off", "<u8"), ("num_bytes", "<u4"), ("rbsp_len", "<u4"),
@@ -61,13 +64,16 @@ class CabacJob(C.Structure):
 class StreamJob(C.Structure):
     _fields_ = [("stream", C.c_void_p), ("n", C.c_uint64), ("slice_data_offset", C.c_uint32), ("n_ctx", C.c_uint32),
                 ("ops", C.c_void_p), ("n_ops_max", C.c_uint32), ("n_ops", C.c_void_p), ("qp", C.c_void_p),
-                ("max_slices", C.c_uint32), ("flags", C.c_uint32), ("param_sets", C.c_void_p)]
+                ("max_slices", C.c_uint32), ("flags", C.c_uint32), ("param_sets", C.c_void_p),
+                ("max_sps", C.c_uint32), ("max_pps", C.c_uint32)]
 
 
 class StreamResult(C.Structure):
     _fields_ = [("scan", ScanSummary), ("nals", C.c_void_p), ("n_slices", C.c_uint32), ("reserved", C.c_uint32),
                 ("slice_nal", C.c_void_p), ("bins_off", C.c_void_p), ("bins", C.c_void_p), ("final", C.c_void_p),
-                ("total_bins", C.c_uint64), ("rbsp", C.c_void_p), ("d_rbsp", C.c_void_p), ("ext", C.c_void_p), ("headers", C.c_void_p)]
+                ("total_bins", C.c_uint64), ("rbsp", C.c_void_p), ("d_rbsp", C.c_void_p), ("ext", C.c_void_p), ("headers", C.c_void_p),
+                ("n_sps", C.c_uint32), ("n_pps", C.c_uint32), ("sps", C.c_void_p), ("pps", C.c_void_p),
+                ("sps_nal", C.c_void_p), ("pps_nal", C.c_void_p), ("slice_sps", C.c_void_p), ("slice_pps", C.c_void_p)]
 
 
 PARAM_SET_FIELDS = ["use_separate_color_plane", "chroma_format", "frame_mbs_only", "pic_order_count_type",
@@ -79,7 +85,42 @@ PARAM_SET_FIELDS = ["use_separate_color_plane", "chroma_format", "frame_mbs_only
 
 
 class ParamSets(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in PARAM_SET_FIELDS]
+    _fields_ = [(n, C.c_int64) for n in PARAM_SET_FIELDS]
+
+
+SPS_MAX_REF_FRAMES, SPS_MAX_HRD = 256, 64
+SPS_SCALARS = [
+    "profile", "constraint0", "constraint1", "constraint2", "constraint3", "constraint4", "constraint5", "level", "id",
+    "chroma_format", "use_separate_color_plane", "bit_depth_luma_minus8", "bit_depth_chroma_minus8",
+    "qprime_y_zero_transform_bypass", "seq_scaling_matrix_present", "log2_max_frame_num_minus4", "pic_order_count_type",
+    "log2_max_pic_order_cnt_lsb_min4", "delta_pic_order_always_zero", "offset_for_non_ref_pic",
+    "offset_for_top_to_bottom_field", "num_ref_frames_in_pic_order_cnt_cycle", "max_num_ref_frames",
+    "gaps_in_frame_num_value_allowed", "pic_width_in_mbs_minus1", "pic_height_in_map_units_minus1", "frame_mbs_only",
+    "mb_adaptive_frame_field", "direct_8x8_inference", "frame_cropping", "frame_crop_left_offset",
+    "frame_crop_right_offset", "frame_crop_top_offset", "frame_crop_bottom_offset", "vui_parameters_present",
+    "aspect_ratio_info_present", "aspect_ratio", "sar_width", "sar_height", "overscan_info_present",
+    "overscan_appropriate", "video_signal_type_present", "video_format", "video_full_range", "color_description_present",
+    "color_primaries", "transfer_characteristics", "matrix_coefficients", "chroma_loc_info_present",
+    "chroma_sample_loc_type_top_field", "chroma_sample_loc_type_bottom_field", "cpb_cnt_minus1", "bit_rate_scale",
+    "cpb_size_scale", "initial_cpb_removal_delay_length_minus1", "cpb_removal_delay_length_minus1",
+    "dpb_output_delay_length_minus1", "time_offset_length", "timing_info_present", "num_units_in_tick", "time_scale",
+    "nal_hrd_parameters_present", "fixed_frame_rate", "vcl_hrd_parameters_present", "low_hrd_delay", "pic_struct_present",
+    "bitstream_restriction", "motion_vectors_over_pic_boundaries", "max_bytes_per_pic_denom", "max_bits_per_mb_denom",
+    "log2_max_mv_length_horizontal", "log2_max_mv_length_vertical", "max_dec_frame_buffering", "max_num_reorder_frames"]
+SPS_DTYPE = np.dtype([(n, "<i8") for n in SPS_SCALARS] +
+                     [("n_seq_scaling_list", "<i8"), ("seq_scaling_list", "<i8", (12,)),
+                      ("n_offset_for_ref_frame", "<i8"), ("offset_for_ref_frame", "<i8", (SPS_MAX_REF_FRAMES,)),
+                      ("n_hrd", "<i8"), ("bit_rate_value_minus1", "<i8", (SPS_MAX_HRD,)),
+                      ("cpb_size_value_minus1", "<i8", (SPS_MAX_HRD,)), ("cbr", "<i8", (SPS_MAX_HRD,)),
+                      ("bits_read", "<u8"), ("status", "<u4"), ("reserved", "<u4")])
+PPS_SCALARS = [
+    "id", "sps_id", "entropy_coding_mode", "num_slice_groups_minus1", "bottom_field_pic_order_in_frame_present",
+    "slice_group_map_type", "slice_group_change_direction", "slice_group_change_rate_minus1",
+    "pic_size_in_map_units_minus1", "num_ref_idx_l0_default_active_minus1", "num_ref_idx_l1_default_active_minus1",
+    "weighted_pred", "weighted_bipred", "pic_init_qp_minus26", "pic_init_qs_minus26", "chroma_qp_index_offset",
+    "deblocking_filter_control_present", "constrained_intra_pred", "redundant_pic_cnt_present", "transform_8x8_mode",
+    "pic_scaling_matrix_present", "second_chroma_qp_index_offset"]
+PPS_DTYPE = np.dtype([(n, "<i8") for n in PPS_SCALARS] + [("bits_read", "<u8"), ("status", "<u4"), ("reserved", "<u4")])
 
 
 SLICE_HEADER_FIELDS = [
@@ -146,6 +187,12 @@ def load():
         "h264b_slice_headers": (i32, [vp, P(ParamSets), vp, u64, vp, vp, vp, vp, u32, vp]),
         "h264b_stream_wait": (i32, [vp, u64, P(StreamResult)]),
         "h264b_slice_select_dev": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp, vp]),
+        "h264b_parse_sps": (i32, [vp, vp, u64, vp, vp, u32, vp]),
+        "h264b_parse_pps": (i32, [vp, vp, u64, vp, vp, u32, vp]),
+        "h264b_parse_sps_dev": (i32, [vp, vp, u64, vp, vp, vp, vp, u32, vp, vp]),
+        "h264b_parse_pps_dev": (i32, [vp, vp, u64, vp, vp, vp, vp, u32, vp, vp]),
+        "h264b_make_param_sets": (i32, [vp, vp, P(ParamSets)]),
+        "h264b_param_set_select_dev": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -409,6 +456,34 @@ class Context:
             setattr(p, k, int(v))
         return p
 
+    def _parse_psets(self, fn, dtype, data, off, length):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        out = np.zeros(len(off), dtype=dtype)
+        self._check(fn(self.h, data.ctypes.data if len(data) else None, len(data), off.ctypes.data, length.ctypes.data,
+                       len(off), out.ctypes.data))
+        return out
+
+    def parse_sps(self, data, off, length):
+        """NewSPS for every RBSP data[off[i] : off[i] + length[i]] -> SPS_DTYPE[n]"""
+        return self._parse_psets(_lib.h264b_parse_sps, SPS_DTYPE, data, off, length)
+
+    def parse_pps(self, data, off, length):
+        """NewPPS -> PPS_DTYPE[n]"""
+        return self._parse_psets(_lib.h264b_parse_pps, PPS_DTYPE, data, off, length)
+
+    @staticmethod
+    def make_param_sets(sps_rec, pps_rec):
+        """ParamSets (what the slice-header walk reads) from one SPS_DTYPE and one PPS_DTYPE record"""
+        a = np.ascontiguousarray(np.asarray(sps_rec, dtype=SPS_DTYPE).reshape(1))
+        b = np.ascontiguousarray(np.asarray(pps_rec, dtype=PPS_DTYPE).reshape(1))
+        p = ParamSets()
+        rc = _lib.h264b_make_param_sets(a.ctypes.data, b.ctypes.data, C.byref(p))
+        if rc:
+            raise H264BError(rc)
+        return p
+
     def slice_headers(self, params, data, off, length, nal_type, nal_ref_idc):
         """host buffers -> SLICE_HEADER_DTYPE[n]"""
         data = np.ascontiguousarray(data, dtype=np.uint8)
@@ -426,7 +501,7 @@ class Context:
                                                  d_nals, d_slice_nal, n_slices, d_out))
 
     def stream_submit(self, stream, ops, n_ops, qp, idc, n_ctx, slice_data_offset=0, flags=0, param_sets=None,
-                      max_slices=None):
+                      max_slices=None, max_sps=0, max_pps=0):
         """asynchronous form: returns (ticket, keepalive); pass both to stream_wait.  Up to two jobs in flight.
         param_sets (ParamSets): take SliceQPY / cabac_init_idc / the CABAC data offset from the slice headers
         (qp, idc may then be None; max_slices bounds the slice count)."""
@@ -445,7 +520,10 @@ class Context:
         j.qp = p.ctypes.data if p is not None else None
         j.max_slices = len(p) if p is not None else int(max_slices)
         j.flags = flags | (STREAM_SLICE_HEADERS if param_sets is not None else 0)
+        if flags & STREAM_PARAM_SETS:   # the stream's own SPS / PPS NAL units
+            j.flags |= STREAM_SLICE_HEADERS
         j.param_sets = C.addressof(param_sets) if param_sets is not None else None
+        j.max_sps, j.max_pps = max_sps, max_pps
         t = C.c_uint64()
         self._check(_lib.h264b_stream_submit(self.h, C.byref(j), C.byref(t)))
         return t.value, (s, ops, p, nops, j, param_sets)
@@ -464,4 +542,10 @@ class Context:
                     slice_nal=_from_ptr(r.slice_nal, np.uint32, ns), bins_off=boff, bins_flat=flat,
                     bins=[flat[int(boff[i]):int(boff[i + 1])] for i in range(ns)],
                     final=_from_ptr(r.final, FINAL_DTYPE, ns), total_bins=r.total_bins,
-                    headers=_from_ptr(r.headers, SLICE_HEADER_DTYPE, ns) if r.headers else None)
+                    headers=_from_ptr(r.headers, SLICE_HEADER_DTYPE, ns) if r.headers else None,
+                    sps=_from_ptr(r.sps, SPS_DTYPE, r.n_sps) if r.sps else None,
+                    pps=_from_ptr(r.pps, PPS_DTYPE, r.n_pps) if r.pps else None,
+                    sps_nal=_from_ptr(r.sps_nal, np.uint32, r.n_sps) if r.sps else None,
+                    pps_nal=_from_ptr(r.pps_nal, np.uint32, r.n_pps) if r.pps else None,
+                    slice_sps=_from_ptr(r.slice_sps, np.int32, ns) if r.sps else None,
+                    slice_pps=_from_ptr(r.slice_pps, np.int32, ns) if r.sps else None)

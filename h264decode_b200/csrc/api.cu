@@ -471,8 +471,10 @@ int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_
     if (!job || !ticket) return H264B_E_INVALID;
     const h264b_stream_job &j = *job;
     const bool from_headers = (j.flags & H264B_STREAM_SLICE_HEADERS) != 0 && j.max_slices != 0;
+    const bool own_psets = from_headers && (j.flags & H264B_STREAM_PARAM_SETS) != 0;
+    const uint32_t max_sps = j.max_sps ? j.max_sps : 64u, max_pps = j.max_pps ? j.max_pps : 64u;
     if ((!j.stream && j.n) || (j.max_slices && ((!j.qp && !from_headers) || (!j.ops && j.n_ops_max))) ||
-        (from_headers && !j.param_sets))
+        (from_headers && !own_psets && !j.param_sets))
         return set_error(ctx, H264B_E_INVALID, "stream_submit: null pointer in job");
     StreamSlot *sl = ctx->slot[ctx->next_ticket & 1];
     if (sl->busy) return set_error(ctx, H264B_E_INVALID, "stream_submit: two jobs are in flight, wait for one first");
@@ -555,12 +557,34 @@ int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_
     RC(launch_slice_select(ctx, (const h264b_nal *)d_nals, (const h264b_scan_summary *)d_sum, cap,
                            from_headers ? 0u : j.slice_data_offset, j.max_slices, (uint64_t *)d_off, (uint32_t *)d_len,
                            (uint32_t *)d_snal, d_ns));
-    void *d_hdr = nullptr;
+    void *d_hdr = nullptr, *d_psl = nullptr, *d_sps = nullptr, *d_pps = nullptr, *d_sps_of = nullptr;
     if (from_headers) {  // SliceQPY, cabac_init_idc and the start of the CABAC data come from the slices' own headers
         RC(slot_dev(ctx, sl, 14, ms * sizeof(h264b_slice_header), &d_hdr));
+        StreamParamSets sp;
+        if (own_psets) {  // ... and the parameter sets from the stream's SPS / PPS NAL units
+            RC(slot_dev(ctx, sl, 15, ((size_t)max_sps + max_pps + 4) * 4, &d_psl));
+            RC(slot_dev(ctx, sl, 16, (size_t)max_sps * sizeof(h264b_sps), &d_sps));
+            RC(slot_dev(ctx, sl, 17, (size_t)max_pps * sizeof(h264b_pps), &d_pps));
+            RC(slot_dev(ctx, sl, 18, ms * 8, &d_sps_of));
+            uint32_t *counts = (uint32_t *)d_psl, *sps_nal = counts + 4, *pps_nal = sps_nal + max_sps;
+            RC(launch_pset_select(ctx, (const h264b_nal *)d_nals, (const h264b_scan_summary *)d_sum, cap, max_sps, max_pps,
+                                  sps_nal, pps_nal, counts));
+            RC(launch_parse_sps(ctx, (const uint8_t *)d_rbsp, j.n + 16, nullptr, nullptr, (const h264b_nal *)d_nals, sps_nal,
+                                max_sps, counts, (h264b_sps *)d_sps));
+            RC(launch_parse_pps(ctx, (const uint8_t *)d_rbsp, j.n + 16, nullptr, nullptr, (const h264b_nal *)d_nals, pps_nal,
+                                max_pps, counts + 1, (h264b_pps *)d_pps));
+            sp.sps = (const h264b_sps *)d_sps;
+            sp.pps = (const h264b_pps *)d_pps;
+            sp.sps_nal = sps_nal;
+            sp.pps_nal = pps_nal;
+            sp.counts = counts;
+            sp.slice_sps = (int32_t *)d_sps_of;
+            sp.slice_pps = sp.slice_sps + ms;
+        }
         RC(launch_stream_slice_headers(ctx, j.param_sets, (const uint8_t *)d_rbsp, j.n + 16, (const h264b_nal *)d_nals,
                                        (const uint32_t *)d_snal, d_ns, j.max_slices, (h264b_slice_header *)d_hdr,
-                                       (uint64_t *)d_off, (uint32_t *)d_len, (h264b_slice_qp *)d_qp));
+                                       (uint64_t *)d_off, (uint32_t *)d_len, (h264b_slice_qp *)d_qp,
+                                       own_psets ? &sp : nullptr));
     }
     if (j.max_slices) {
         h264b_cabac_job cj;
@@ -597,6 +621,17 @@ int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_
         void *h_hdr;
         RC(slot_pin(ctx, sl, 11, ms * sizeof(h264b_slice_header), &h_hdr));
         H264B_CUDA(ctx, cudaMemcpyAsync(h_hdr, d_hdr, ms * sizeof(h264b_slice_header), cudaMemcpyDeviceToHost, out));
+    }
+    if (own_psets) {
+        void *h_psl, *h_sps, *h_pps, *h_sps_of;
+        RC(slot_pin(ctx, sl, 12, ((size_t)max_sps + max_pps + 4) * 4, &h_psl));
+        RC(slot_pin(ctx, sl, 13, (size_t)max_sps * sizeof(h264b_sps), &h_sps));
+        RC(slot_pin(ctx, sl, 14, (size_t)max_pps * sizeof(h264b_pps), &h_pps));
+        RC(slot_pin(ctx, sl, 15, ms * 8, &h_sps_of));
+        H264B_CUDA(ctx, cudaMemcpyAsync(h_psl, d_psl, ((size_t)max_sps + max_pps + 4) * 4, cudaMemcpyDeviceToHost, out));
+        H264B_CUDA(ctx, cudaMemcpyAsync(h_sps, d_sps, (size_t)max_sps * sizeof(h264b_sps), cudaMemcpyDeviceToHost, out));
+        H264B_CUDA(ctx, cudaMemcpyAsync(h_pps, d_pps, (size_t)max_pps * sizeof(h264b_pps), cudaMemcpyDeviceToHost, out));
+        H264B_CUDA(ctx, cudaMemcpyAsync(h_sps_of, d_sps_of, ms * 8, cudaMemcpyDeviceToHost, out));
     }
     if (j.flags & H264B_STREAM_WANT_RBSP) {  // position-preserving layout: the buffer is as long as the stream
         void *h_rbsp, *h_ext;
@@ -668,6 +703,21 @@ int32_t h264b_stream_wait(h264b_ctx *ctx, uint64_t ticket, h264b_stream_result *
     res->headers = ((sl->job.flags & H264B_STREAM_SLICE_HEADERS) && sl->job.max_slices)
                        ? (const h264b_slice_header *)sl->h[11]
                        : nullptr;
+    if (res->headers && (sl->job.flags & H264B_STREAM_PARAM_SETS)) {
+        const uint32_t max_sps = sl->job.max_sps ? sl->job.max_sps : 64u, max_pps = sl->job.max_pps ? sl->job.max_pps : 64u;
+        const uint32_t *counts = (const uint32_t *)sl->h[12];
+        if (counts[2] > max_sps || counts[3] > max_pps)
+            return set_error(ctx, H264B_E_CAPACITY, "stream: %u SPS / %u PPS NAL units, job.max_sps / max_pps hold %u / %u",
+                             counts[2], counts[3], max_sps, max_pps);
+        res->n_sps = counts[0];
+        res->n_pps = counts[1];
+        res->sps_nal = counts + 4;
+        res->pps_nal = counts + 4 + max_sps;
+        res->sps = (const h264b_sps *)sl->h[13];
+        res->pps = (const h264b_pps *)sl->h[14];
+        res->slice_sps = (const int32_t *)sl->h[15];
+        res->slice_pps = res->slice_sps + (sl->job.max_slices ? sl->job.max_slices : 1);
+    }
     return H264B_OK;
 }
 

@@ -41,7 +41,7 @@ struct h264b_ctx {
     int trace;
 };
 
-enum { kSlotDev = 15, kSlotPin = 12 };
+enum { kSlotDev = 20, kSlotPin = 16 };
 struct StreamSlot {
     void *d[kSlotDev];
     size_t d_bytes[kSlotDev];
@@ -90,10 +90,24 @@ int launch_nal_frames(h264b_ctx *ctx, const uint8_t *d_frames, uint64_t total, c
 int launch_ctx_init(h264b_ctx *ctx, const h264b_slice_qp *d_params, uint32_t n_slices, uint32_t n_ctx,
                     uint8_t *d_states, uint32_t flags);
 int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n_slices = nullptr);
+struct StreamParamSets {  // H264B_STREAM_PARAM_SETS: the stream's own parameter sets, device-resident (param_sets.cu)
+    const h264b_sps *sps;
+    const h264b_pps *pps;
+    const uint32_t *sps_nal, *pps_nal, *counts;
+    int32_t *slice_sps, *slice_pps;
+};
 int launch_stream_slice_headers(h264b_ctx *ctx, const h264b_param_sets *params, const uint8_t *d_rbsp, uint64_t total,
                                 const h264b_nal *d_nals, const uint32_t *d_slice_nal, const uint32_t *d_n_slices,
                                 uint32_t max_slices, h264b_slice_header *d_hdr, uint64_t *d_off, uint32_t *d_len,
-                                h264b_slice_qp *d_qp);
+                                h264b_slice_qp *d_qp, const StreamParamSets *sp = nullptr);
+int launch_pset_select(h264b_ctx *ctx, const h264b_nal *d_nals, const h264b_scan_summary *d_summary, uint32_t nal_cap,
+                       uint32_t max_sps, uint32_t max_pps, uint32_t *d_sps_nal, uint32_t *d_pps_nal, uint32_t *d_counts);
+int launch_parse_sps(h264b_ctx *ctx, const uint8_t *d_bytes, uint64_t total, const uint64_t *d_off, const uint32_t *d_len,
+                     const h264b_nal *d_nals, const uint32_t *d_nal_index, uint32_t n, const uint32_t *d_n,
+                     h264b_sps *d_out);
+int launch_parse_pps(h264b_ctx *ctx, const uint8_t *d_bytes, uint64_t total, const uint64_t *d_off, const uint32_t *d_len,
+                     const h264b_nal *d_nals, const uint32_t *d_nal_index, uint32_t n, const uint32_t *d_n,
+                     h264b_pps *d_out);
 int launch_slice_select(h264b_ctx *ctx, const h264b_nal *d_nals, const h264b_scan_summary *d_summary,
                         uint32_t nal_cap, uint32_t slice_data_offset, uint32_t max_slices, uint64_t *d_off,
                         uint32_t *d_len, uint32_t *d_slice_nal, uint32_t *d_n_slices);

@@ -2,7 +2,7 @@
 // NAL units at once, one thread per slice (the walk is a serial Exp-Golomb parse of a few dozen bits; slices are
 // independent).  The parse itself is slice_header.cuh (shared with the CPU emulation of tests/).
 #include "common.cuh"
-#include "slice_header.cuh"
+#include "param_sets.cuh"
 
 namespace h264b {
 
@@ -18,7 +18,24 @@ struct SliceHeaderArgs {
     uint32_t n_slices;
     const uint32_t *n_slices_dev;  // actual count on the device (n_slices is then the bound), or NULL
     h264b_slice_header *out;
+    // H264B_STREAM_PARAM_SETS: the stream's own parameter sets (param_sets.cu) instead of `ps`
+    const h264b_sps *sps;
+    const h264b_pps *pps;
+    const uint32_t *sps_nal, *pps_nal;  // their NAL ordinals, ascending
+    const uint32_t *ps_counts;          // [0] SPS kept, [1] PPS kept
+    int32_t *slice_sps, *slice_pps;     // out: the sets slice s used (-1: none)
 };
+
+// index of the last entry below `key` in an ascending list, -1 if there is none
+__device__ __forceinline__ int32_t last_below(const uint32_t *list, uint32_t n, uint32_t key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (list[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return (int32_t)lo - 1;
+}
 
 __global__ void __launch_bounds__(128) slice_header_kernel(SliceHeaderArgs a) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -40,7 +57,25 @@ __global__ void __launch_bounds__(128) slice_header_kernel(SliceHeaderArgs a) {
     if (off > a.total_bytes) off = a.total_bytes;
     if (len > a.total_bytes - off) len = a.total_bytes - off;
     h264b_slice_header h;
-    parse_slice_header_record(a.ps, type, ref_idc, a.bytes + off, len, &h);
+    if (a.sps) {
+        // handleConnection (server.go:147-162): a slice belongs to the last VideoStream, i.e. the last SPS before it, and
+        // uses the PPS stored there last, i.e. the last PPS behind that SPS.  No SPS: VideoStreams[-1] panics; no PPS:
+        // NewSliceContext dereferences nil; a parameter set NewSPS / NewPPS panicked on never got that far.
+        const uint32_t k = a.slice_nal[s];
+        const int32_t si = last_below(a.sps_nal, a.ps_counts[0], k);
+        int32_t pi = last_below(a.pps_nal, a.ps_counts[1], k);
+        if (si < 0 || pi < 0 || a.pps_nal[pi] < a.sps_nal[si]) pi = -1;
+        a.slice_sps[s] = si;
+        a.slice_pps[s] = pi;
+        if (si < 0 || pi < 0 || a.sps[si].status != H264B_SH_OK || a.pps[pi].status != H264B_SH_OK) {
+            h = h264b_slice_header{};
+            h.status = H264B_SH_PANIC;
+        } else {
+            parse_slice_header_record(make_param_sets(a.sps[si], a.pps[pi]), type, ref_idc, a.bytes + off, len, &h);
+        }
+    } else {
+        parse_slice_header_record(a.ps, type, ref_idc, a.bytes + off, len, &h);
+    }
     a.out[s] = h;
 }
 
@@ -73,11 +108,6 @@ __global__ void __launch_bounds__(256) slice_params_kernel(const h264b_slice_hea
     }
 }
 
-int launch_stream_slice_headers(h264b_ctx *ctx, const h264b_param_sets *params, const uint8_t *d_rbsp, uint64_t total,
-                                const h264b_nal *d_nals, const uint32_t *d_slice_nal, const uint32_t *d_n_slices,
-                                uint32_t max_slices, h264b_slice_header *d_hdr, uint64_t *d_off, uint32_t *d_len,
-                                h264b_slice_qp *d_qp);
-
 int launch_slice_headers(h264b_ctx *ctx, const SliceHeaderArgs &a) {
     if (!a.n_slices) return H264B_OK;
     slice_header_kernel<<<(a.n_slices + 127) / 128, 128, 0, ctx->stream>>>(a);
@@ -88,10 +118,17 @@ int launch_slice_headers(h264b_ctx *ctx, const SliceHeaderArgs &a) {
 int launch_stream_slice_headers(h264b_ctx *ctx, const h264b_param_sets *params, const uint8_t *d_rbsp, uint64_t total,
                                 const h264b_nal *d_nals, const uint32_t *d_slice_nal, const uint32_t *d_n_slices,
                                 uint32_t max_slices, h264b_slice_header *d_hdr, uint64_t *d_off, uint32_t *d_len,
-                                h264b_slice_qp *d_qp) {
+                                h264b_slice_qp *d_qp, const StreamParamSets *sp) {
     if (!max_slices) return H264B_OK;
     SliceHeaderArgs a;
-    a.ps = *params;
+    a.ps = params ? *params : h264b_param_sets{};
+    a.sps = sp ? sp->sps : nullptr;
+    a.pps = sp ? sp->pps : nullptr;
+    a.sps_nal = sp ? sp->sps_nal : nullptr;
+    a.pps_nal = sp ? sp->pps_nal : nullptr;
+    a.ps_counts = sp ? sp->counts : nullptr;
+    a.slice_sps = sp ? sp->slice_sps : nullptr;
+    a.slice_pps = sp ? sp->slice_pps : nullptr;
     a.bytes = d_rbsp;
     a.total_bytes = total;
     a.off = nullptr;
@@ -140,6 +177,10 @@ extern "C" int32_t h264b_slice_headers_dev(h264b_ctx *ctx, const h264b_param_set
     a.n_slices = n_slices;
     a.n_slices_dev = nullptr;
     a.out = d_out;
+    a.sps = nullptr;
+    a.pps = nullptr;
+    a.sps_nal = a.pps_nal = a.ps_counts = nullptr;
+    a.slice_sps = a.slice_pps = nullptr;
     return launch_slice_headers(ctx, a);
 }
 

@@ -16,6 +16,7 @@
 //   ArithmeticDecoding.{DecodeBypass, DecodeTerminate, RenormD, BinaryDecision}  cabac.go:468-540
 //   (*CABAC).StateTransitionProcess     cabac.go:544-553     h264::CABAC::StateTransitionProcess
 //   NewSliceContext (header part)       slice.go:835-1048    h264::SliceHeaders
+//   NewSPS, NewPPS                      sps.go:192, pps.go:40 h264::NewSPS, h264::NewPPS (+ h264::ParamSets for the walk)
 //   (new, batch)                                             h264::InitContexts, h264::DecodeBins
 #pragma once
 #include <stdint.h>
@@ -393,6 +394,42 @@ inline std::vector<h264b_slice_header> SliceHeaders(const h264b_param_sets &ps, 
     for (const auto &h : out)
         if (h.status == H264B_SH_PANIC) throw Panic("NewSliceContext: the reference panics on this slice header");
     return out;
+}
+
+// ------------------------------------------------------------------------------------------------ parameter sets
+// NewSPS(rbsp, showPacket) (sps.go:192) / NewPPS(sps, rbsp, showPacket) (pps.go:40): field extraction on the device, one
+// thread per parameter set.  A parameter set on which the reference would panic throws h264::Panic (the reference's
+// handleConnection recovers it and exits, server.go:136-143).  showPacket only controlled debug logging.
+using SPS = h264b_sps;
+using PPS = h264b_pps;
+inline SPS NewSPS(const std::vector<uint8_t> &rbsp, bool showPacket = false, Device &dev = Device::Default()) {
+    (void)showPacket;
+    std::vector<uint8_t> buf(rbsp);
+    buf.resize(buf.size() + 8);
+    const uint64_t off = 0;
+    const uint32_t len = (uint32_t)rbsp.size();
+    SPS out;
+    dev.check(h264b_parse_sps(dev.ctx(), buf.data(), buf.size(), &off, &len, 1, &out));
+    if (out.status != H264B_SH_OK) throw Panic("NewSPS: the reference panics on this parameter set");
+    return out;
+}
+inline PPS NewPPS(const SPS *sps, const std::vector<uint8_t> &rbsp, bool showPacket = false, Device &dev = Device::Default()) {
+    (void)sps;  // only read by the reference after it has panicked (pps.go:99-103)
+    (void)showPacket;
+    std::vector<uint8_t> buf(rbsp);
+    buf.resize(buf.size() + 8);
+    const uint64_t off = 0;
+    const uint32_t len = (uint32_t)rbsp.size();
+    PPS out;
+    dev.check(h264b_parse_pps(dev.ctx(), buf.data(), buf.size(), &off, &len, 1, &out));
+    if (out.status != H264B_SH_OK) throw Panic("NewPPS: the reference panics on this parameter set");
+    return out;
+}
+// VideoStream{SPS, PPS} (server.go:149-158) as the slice-header walk needs it
+inline h264b_param_sets ParamSets(const SPS &sps, const PPS &pps) {
+    h264b_param_sets ps;
+    if (h264b_make_param_sets(&sps, &pps, &ps) != H264B_OK) throw std::runtime_error("h264b_make_param_sets");
+    return ps;
 }
 
 // new, batch: the whole engine for many slices at once (see h264b_cabac_job)

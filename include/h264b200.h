@@ -50,6 +50,13 @@ extern "C" {
                                             ignored.  A slice whose header the reference cannot walk is not decoded
                                             (its final record carries H264B_F_OVERRUN). */
 
+#define H264B_STREAM_PARAM_SETS 0x20u   /* h264b_stream_* with H264B_STREAM_SLICE_HEADERS: the parameter sets come from
+                                            the stream's own SPS / PPS NAL units, parsed on the device; a slice uses
+                                            the last SPS before it and the last PPS after that SPS (handleConnection's
+                                            VideoStreams bookkeeping, h264/server.go:147-162).  job.param_sets is
+                                            ignored; a slice without both, or whose parameter sets the reference
+                                            cannot parse, gets header status H264B_SH_PANIC and is not decoded. */
+
 /* per-unit flag bits written by kernels (never abort a batch; SURVEY.md §5 failure handling) */
 #define H264B_F_OVERRUN 0x1u    /* the reference would have panicked reading past the slice's last byte (A10) */
 #define H264B_F_HAS_EPB 0x2u    /* NAL: at least one emulation-prevention byte was removed */
@@ -226,13 +233,13 @@ int32_t h264b_state_transition(h264b_ctx *ctx, uint32_t flags, int32_t *p_state_
  * NAL units at once, one thread per slice: what the CABAC stage needs from the stream instead of from the caller --
  * SliceQPY (SliceQPy, h264/cabac.go:113-115), cabac_init_idc, the slice type and the bit at which slice_data()
  * begins.  The reference's deviations from ITU-T H.264 are reproduced (slice_header.cuh lists them). */
-typedef struct { /* the SPS / PPS fields the walk reads (h264/sps.go, h264/pps.go) */
-    int32_t use_separate_color_plane, chroma_format, frame_mbs_only, pic_order_count_type;
-    int32_t log2_max_pic_order_cnt_lsb_min4, delta_pic_order_always_zero;
-    int32_t bottom_field_pic_order_in_frame_present, redundant_pic_cnt_present, weighted_pred, weighted_bipred;
-    int32_t entropy_coding_mode, deblocking_filter_control_present, num_slice_groups_minus1, slice_group_map_type;
-    int32_t pic_size_in_map_units_minus1, slice_group_change_rate_minus1, pic_init_qp_minus26, reserved;
-} h264b_param_sets; /* 72 bytes */
+typedef struct { /* the SPS / PPS fields the walk reads (h264/sps.go, h264/pps.go); Go ints -> int64 */
+    int64_t use_separate_color_plane, chroma_format, frame_mbs_only, pic_order_count_type;
+    int64_t log2_max_pic_order_cnt_lsb_min4, delta_pic_order_always_zero;
+    int64_t bottom_field_pic_order_in_frame_present, redundant_pic_cnt_present, weighted_pred, weighted_bipred;
+    int64_t entropy_coding_mode, deblocking_filter_control_present, num_slice_groups_minus1, slice_group_map_type;
+    int64_t pic_size_in_map_units_minus1, slice_group_change_rate_minus1, pic_init_qp_minus26, reserved;
+} h264b_param_sets; /* 144 bytes; h264b_make_param_sets fills it from a parsed SPS + PPS */
 
 #define H264B_SH_OK 0u
 #define H264B_SH_PANIC 1u /* the reference would have panicked (read past the end of the RBSP, index out of range,
@@ -271,6 +278,75 @@ int32_t h264b_slice_headers(h264b_ctx *ctx, const h264b_param_sets *params, cons
                             const uint64_t *off, const uint32_t *len, const uint8_t *nal_type,
                             const uint8_t *nal_ref_idc, uint32_t n_slices, h264b_slice_header *out);
 
+/* ------------------------------------------------------------------ parameter sets (rows S1 / f4)
+ * Replaces NewSPS (h264/sps.go:192-437, with scalingList :172-191) and NewPPS (h264/pps.go:40-133): the field
+ * extraction from the RBSP of NAL units of type 7 / 8, one device thread per parameter set, so that the active
+ * parameter sets of a stream stay on the device for the slice-header walk.  The reference's deviations from ITU-T
+ * H.264 are reproduced (param_sets.cuh lists them).  Go ints and bools -> int64; `status` is H264B_SH_OK or
+ * H264B_SH_PANIC (the reference would have panicked: the fields read before that point are set, the rest are 0). */
+#define H264B_SPS_MAX_REF_FRAMES 256 /* entries kept of OffsetForRefFrameList (n_offset_for_ref_frame counts all) */
+#define H264B_SPS_MAX_HRD 64         /* entries kept of BitRateValueMinus1 / CpbSizeValueMinus1 / Cbr (n_hrd counts all) */
+typedef struct { /* SPS, h264/sps.go:13-103 */
+    int64_t profile, constraint0, constraint1, constraint2, constraint3, constraint4, constraint5, level, id;
+    int64_t chroma_format, use_separate_color_plane, bit_depth_luma_minus8, bit_depth_chroma_minus8;
+    int64_t qprime_y_zero_transform_bypass, seq_scaling_matrix_present, log2_max_frame_num_minus4;
+    int64_t pic_order_count_type, log2_max_pic_order_cnt_lsb_min4, delta_pic_order_always_zero;
+    int64_t offset_for_non_ref_pic, offset_for_top_to_bottom_field, num_ref_frames_in_pic_order_cnt_cycle;
+    int64_t max_num_ref_frames, gaps_in_frame_num_value_allowed, pic_width_in_mbs_minus1;
+    int64_t pic_height_in_map_units_minus1, frame_mbs_only, mb_adaptive_frame_field, direct_8x8_inference;
+    int64_t frame_cropping, frame_crop_left_offset, frame_crop_right_offset, frame_crop_top_offset;
+    int64_t frame_crop_bottom_offset, vui_parameters_present, aspect_ratio_info_present, aspect_ratio, sar_width;
+    int64_t sar_height, overscan_info_present, overscan_appropriate, video_signal_type_present, video_format;
+    int64_t video_full_range, color_description_present, color_primaries, transfer_characteristics;
+    int64_t matrix_coefficients, chroma_loc_info_present, chroma_sample_loc_type_top_field;
+    int64_t chroma_sample_loc_type_bottom_field, cpb_cnt_minus1, bit_rate_scale, cpb_size_scale;
+    int64_t initial_cpb_removal_delay_length_minus1, cpb_removal_delay_length_minus1;
+    int64_t dpb_output_delay_length_minus1, time_offset_length, timing_info_present, num_units_in_tick, time_scale;
+    int64_t nal_hrd_parameters_present, fixed_frame_rate, vcl_hrd_parameters_present, low_hrd_delay;
+    int64_t pic_struct_present, bitstream_restriction, motion_vectors_over_pic_boundaries, max_bytes_per_pic_denom;
+    int64_t max_bits_per_mb_denom, log2_max_mv_length_horizontal, log2_max_mv_length_vertical;
+    int64_t max_dec_frame_buffering, max_num_reorder_frames; /* 74 scalars */
+    int64_t n_seq_scaling_list, seq_scaling_list[12];         /* SeqScalingList (the present flags) */
+    int64_t n_offset_for_ref_frame, offset_for_ref_frame[H264B_SPS_MAX_REF_FRAMES];
+    int64_t n_hrd, bit_rate_value_minus1[H264B_SPS_MAX_HRD], cpb_size_value_minus1[H264B_SPS_MAX_HRD],
+        cbr[H264B_SPS_MAX_HRD];
+    uint64_t bits_read; /* BitReader.bitsRead when NewSPS returned (or panicked) */
+    uint32_t status, reserved;
+} h264b_sps;
+
+typedef struct { /* PPS, h264/pps.go:10-38 */
+    int64_t id, sps_id, entropy_coding_mode, num_slice_groups_minus1, bottom_field_pic_order_in_frame_present;
+    int64_t slice_group_map_type, slice_group_change_direction, slice_group_change_rate_minus1;
+    int64_t pic_size_in_map_units_minus1, num_ref_idx_l0_default_active_minus1;
+    int64_t num_ref_idx_l1_default_active_minus1, weighted_pred, weighted_bipred, pic_init_qp_minus26;
+    int64_t pic_init_qs_minus26, chroma_qp_index_offset, deblocking_filter_control_present, constrained_intra_pred;
+    int64_t redundant_pic_cnt_present, transform_8x8_mode, pic_scaling_matrix_present;
+    int64_t second_chroma_qp_index_offset; /* 22 scalars */
+    uint64_t bits_read;
+    uint32_t status, reserved;
+} h264b_pps;
+
+/* Parameter set i = RBSP bytes [off[i], off[i] + len[i]) of `bytes`.  Host pointers; synchronous. */
+int32_t h264b_parse_sps(h264b_ctx *ctx, const uint8_t *bytes, uint64_t total_bytes, const uint64_t *off,
+                        const uint32_t *len, uint32_t n, h264b_sps *out);
+int32_t h264b_parse_pps(h264b_ctx *ctx, const uint8_t *bytes, uint64_t total_bytes, const uint64_t *off,
+                        const uint32_t *len, uint32_t n, h264b_pps *out);
+/* Device pointers; asynchronous.  With d_nals != NULL parameter set i is the RBSP of nals[nal_index[i]] and d_off /
+ * d_len may be NULL; d_n (device, may be NULL) holds the actual count, n is then the bound. */
+int32_t h264b_parse_sps_dev(h264b_ctx *ctx, const uint8_t *d_bytes, uint64_t total_bytes, const uint64_t *d_off,
+                            const uint32_t *d_len, const h264b_nal *d_nals, const uint32_t *d_nal_index, uint32_t n,
+                            const uint32_t *d_n, h264b_sps *d_out);
+int32_t h264b_parse_pps_dev(h264b_ctx *ctx, const uint8_t *d_bytes, uint64_t total_bytes, const uint64_t *d_off,
+                            const uint32_t *d_len, const h264b_nal *d_nals, const uint32_t *d_nal_index, uint32_t n,
+                            const uint32_t *d_n, h264b_pps *d_out);
+/* The fields the slice-header walk reads, from a parsed SPS + PPS (host-side convenience; no device work). */
+int32_t h264b_make_param_sets(const h264b_sps *sps, const h264b_pps *pps, h264b_param_sets *out);
+/* Ordered lists of the NAL units of type 7 and of type 8 of a finished h264b_annexb_scan_dev (handleConnection's
+ * dispatch, h264/server.go:147-158).  Device pointers; d_counts[0] / [1] receive min(count, max_sps / max_pps). */
+int32_t h264b_param_set_select_dev(h264b_ctx *ctx, const h264b_nal *d_nals, const h264b_scan_summary *d_summary,
+                                   uint32_t nal_cap, uint32_t max_sps, uint32_t max_pps, uint32_t *d_sps_nal,
+                                   uint32_t *d_pps_nal, uint32_t *d_counts);
+
 /* ------------------------------------------------------------------ whole front end of one stream
  * split + strip + (slice NALs of type 1 / 5) context init + CABAC bins, the slice data staying on the device
  * between the stages.  The CABAC data of a slice NAL starts at RBSP byte `slice_data_offset` (the reference's
@@ -289,6 +365,7 @@ typedef struct {
     uint32_t max_slices;          /* 0: split + strip only (no CABAC stage; ops / n_ops / qp are ignored) */
     uint32_t flags;
     const h264b_param_sets *param_sets; /* H264B_STREAM_SLICE_HEADERS: the active SPS / PPS fields (host pointer) */
+    uint32_t max_sps, max_pps;    /* H264B_STREAM_PARAM_SETS: bounds on the SPS / PPS NAL units kept (0: 64 each) */
 } h264b_stream_job;
 
 typedef struct {
@@ -305,6 +382,14 @@ typedef struct {
     const uint8_t *d_rbsp;          /* the same buffer on the device (for follow-up h264b_*_dev calls) */
     const h264b_nal_ext *ext;       /* [scan.n_nals] (H264B_STREAM_WANT_RBSP), else NULL */
     const h264b_slice_header *headers; /* [n_slices] (H264B_STREAM_SLICE_HEADERS), else NULL */
+    /* H264B_STREAM_PARAM_SETS (else 0 / NULL): the stream's parameter sets in stream order */
+    uint32_t n_sps, n_pps;
+    const h264b_sps *sps;           /* [n_sps] */
+    const h264b_pps *pps;           /* [n_pps] */
+    const uint32_t *sps_nal;        /* [n_sps] index into nals */
+    const uint32_t *pps_nal;        /* [n_pps] */
+    const int32_t *slice_sps;       /* [n_slices] index into sps of the slice's active SPS, -1: none */
+    const int32_t *slice_pps;       /* [n_slices] index into pps, -1: none after that SPS */
 } h264b_stream_result;
 
 int32_t h264b_stream_decode(h264b_ctx *ctx, const h264b_stream_job *job, h264b_stream_result *result);

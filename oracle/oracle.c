@@ -544,17 +544,24 @@ void orc_ctx_init(uint32_t flags, const int32_t *qp, const int32_t *idc, int64_t
         PANIC_CHECK();                           \
         (dst) = (v_ == 1);                       \
     } while (0)
+/* ue(b.golomb()) / se(b.golomb()) over ALL bits of the code word, however long (sh_golomb / sh_se below) */
+static int sh_golomb(orc_bit_reader *b, int64_t *val);
+static int64_t sh_se(int64_t bitval);
 #define UE(dst)                                        \
     do {                                               \
-        int64_t nb_ = orc_br_golomb(b, gb, GOLOMB_CAP); \
+        int64_t bv_;                                   \
+        (void)gb;                                      \
+        sh_golomb(b, &bv_);                            \
         PANIC_CHECK();                                 \
-        (dst) = orc_ue(gb, nb_ < GOLOMB_CAP ? nb_ : GOLOMB_CAP); \
+        (dst) = (int64_t)((uint64_t)bv_ - 1u);         \
     } while (0)
 #define SE(dst)                                        \
     do {                                               \
-        int64_t nb_ = orc_br_golomb(b, gb, GOLOMB_CAP); \
+        int64_t bv_;                                   \
+        (void)gb;                                      \
+        sh_golomb(b, &bv_);                            \
         PANIC_CHECK();                                 \
-        (dst) = orc_se(gb, nb_ < GOLOMB_CAP ? nb_ : GOLOMB_CAP); \
+        (dst) = sh_se(bv_);                            \
     } while (0)
 
 /* scalingList, sps.go:172-191.  The decoded values land in package-global default lists (sps.go:141-155), which
@@ -564,10 +571,12 @@ static int scaling_list(orc_bit_reader *b, int64_t size) {
     int64_t lastScale = 8, nextScale = 8;
     for (int64_t i = 0; i < size; i++) {
         if (nextScale != 0) {
-            int64_t nb = orc_br_golomb(b, gb, GOLOMB_CAP);
+            int64_t bv;
+            (void)gb;
+            sh_golomb(b, &bv);
             if (b->panicked) return ORC_PANIC;
-            int64_t deltaScale = orc_se(gb, nb < GOLOMB_CAP ? nb : GOLOMB_CAP);
-            nextScale = (lastScale + deltaScale + 256) % 256;
+            int64_t deltaScale = sh_se(bv);
+            nextScale = (int64_t)((uint64_t)lastScale + (uint64_t)deltaScale + 256u) % 256;
         }
         lastScale = (nextScale == 0) ? lastScale : nextScale;
     }
@@ -585,12 +594,12 @@ static int hrd_parameters(orc_bit_reader *b, orc_sps *out) {
         UE(a);
         UE(c);
         FLAG(cbr);
-        if (out->n_hrd < ORC_MAX_LIST) {
+        if (out->n_hrd < ORC_MAX_LIST) { /* n_hrd = len() of the three lists; the first ORC_MAX_LIST are kept */
             out->BitRateValueMinus1[out->n_hrd] = a;
             out->CpbSizeValueMinus1[out->n_hrd] = c;
             out->Cbr[out->n_hrd] = cbr;
-            out->n_hrd++;
         }
+        out->n_hrd++;
         FIELD(out->InitialCpbRemovalDelayLengthMinus1, 5);
         FIELD(out->CpbRemovalDelayLengthMinus1, 5);
         FIELD(out->DpbOutputDelayLengthMinus1, 5);
@@ -666,7 +675,8 @@ int orc_new_sps(const uint8_t *rbsp, int64_t len, orc_sps *out) {
             int64_t v;
             SE(v);
             if (out->n_OffsetForRefFrameList < ORC_MAX_LIST)
-                out->OffsetForRefFrameList[out->n_OffsetForRefFrameList++] = v;
+                out->OffsetForRefFrameList[out->n_OffsetForRefFrameList] = v;
+            out->n_OffsetForRefFrameList++;
         }
     }
     UE(out->MaxNumRefFrames);
@@ -758,8 +768,12 @@ int orc_new_pps(int64_t sps_chroma_format, const uint8_t *rbsp, int64_t len, orc
             /* pps.go:61,65-66,74 assign into nil slices: the first iteration panics (A11).  For type 6 the size
              * field is read first (:72). */
             if (out->SliceGroupMapType == 6) UE(out->PicSizeInMapUnitsMinus1);
-            out->bits_read = b->bitsRead;
-            return ORC_PANIC;
+            /* type 6: the loop `i <= PicSizeInMapUnitsMinus1` (pps.go:73) does not run for a negative size (a code word
+             * of 64 leading zeros or more wraps to -1) */
+            if (out->SliceGroupMapType != 6 || out->PicSizeInMapUnitsMinus1 >= 0) {
+                out->bits_read = b->bitsRead;
+                return ORC_PANIC;
+            }
         } else if (out->SliceGroupMapType > 2 && out->SliceGroupMapType < 6) {
             FLAG(out->SliceGroupChangeDirection);
             UE(out->SliceGroupChangeRateMinus1);

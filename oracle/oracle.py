@@ -88,10 +88,12 @@ class SPS(C.Structure):
     def as_dict(self):
         d = {n: getattr(self, n) for n in _SPS_SCALARS}
         d["SeqScalingList"] = list(self.SeqScalingList[:self.n_SeqScalingList])
-        d["OffsetForRefFrameList"] = list(self.OffsetForRefFrameList[:self.n_OffsetForRefFrameList])
-        d["BitRateValueMinus1"] = list(self.BitRateValueMinus1[:self.n_hrd])
-        d["CpbSizeValueMinus1"] = list(self.CpbSizeValueMinus1[:self.n_hrd])
-        d["Cbr"] = list(self.Cbr[:self.n_hrd])
+        nr, nh = min(self.n_OffsetForRefFrameList, MAX_LIST), min(self.n_hrd, MAX_LIST)
+        d["n_OffsetForRefFrameList"], d["n_hrd"] = self.n_OffsetForRefFrameList, self.n_hrd  # len() of the Go lists
+        d["OffsetForRefFrameList"] = list(self.OffsetForRefFrameList[:nr])                    # (first MAX_LIST kept)
+        d["BitRateValueMinus1"] = list(self.BitRateValueMinus1[:nh])
+        d["CpbSizeValueMinus1"] = list(self.CpbSizeValueMinus1[:nh])
+        d["Cbr"] = list(self.Cbr[:nh])
         d["bits_read"] = self.bits_read
         return d
 
@@ -377,10 +379,12 @@ def new_slice_header(sps_fields, pps_fields, nal_type, nal_ref_idc, rbsp):
     """sps_fields / pps_fields: dicts of the orc_sps / orc_pps scalar names NewSliceContext reads.
     Returns (status, dict of header fields)."""
     sps, pps = SPS(), PPS()
-    for k, v in sps_fields.items():
-        setattr(sps, k, int(v))
+    for k, v in sps_fields.items():      # (whole as_dict() results are fine: lists and counts are skipped)
+        if k in _SPS_SCALARS:
+            setattr(sps, k, int(v))
     for k, v in pps_fields.items():
-        setattr(pps, k, int(v))
+        if k in _PPS_SCALARS:
+            setattr(pps, k, int(v))
     d = _u8(rbsp)
     h = SliceHeader()
     L = lib()

@@ -10,7 +10,7 @@
 
 #include "../../h264decode_b200/csrc/annexb_local.cuh"
 #include "../../h264decode_b200/csrc/cabac_lane.cuh"
-#include "../../h264decode_b200/csrc/slice_header.cuh"
+#include "../../h264decode_b200/csrc/param_sets.cuh"
 #include "../../h264decode_b200/csrc/tables.inc"
 
 using namespace h264b;
@@ -359,6 +359,17 @@ void emul_slice_header(const h264b_param_sets *ps, uint32_t nal_type, uint32_t n
                        uint64_t len, h264b_slice_header *out) {
     parse_slice_header_record(*ps, nal_type, nal_ref_idc, rbsp, len, out);
 }
+
+// NewSPS / NewPPS as parse_sps_kernel / parse_pps_kernel run them, one parameter set
+void emul_parse_sps(const uint8_t *rbsp, uint64_t len, h264b_sps *out) {
+    memset(out, 0, sizeof(*out));
+    out->status = parse_sps(rbsp, len, out);
+}
+void emul_parse_pps(const uint8_t *rbsp, uint64_t len, h264b_pps *out) {
+    memset(out, 0, sizeof(*out));
+    out->status = parse_pps(rbsp, len, out);
+}
+void emul_make_param_sets(const h264b_sps *s, const h264b_pps *p, h264b_param_sets *out) { *out = make_param_sets(*s, *p); }
 
 // NewNalUnit on one frame with keep_byte_frame; returns rbsp length
 int64_t emul_frame(const uint8_t *f, int64_t N, uint8_t *rbsp) {

@@ -62,6 +62,35 @@ int main(int argc, char **argv) {
             } catch (const h264::Panic &) {
                 printf("panic\n");
             }
+        } else if (mode == "psets") {  // handleConnection's dispatch (server.go:145-162): NewSPS / NewPPS / slice headers
+            const auto s = slurp(argv[2]);
+            bool have_sps = false, have_pps = false;
+            h264::SPS sps;
+            h264::PPS pps;
+            for (const auto &u : h264::ReadNalUnits(s.data(), s.size())) {
+                try {
+                    if (u.Type == 7) {
+                        sps = h264::NewSPS(u.RBSP());
+                        have_sps = true;
+                        have_pps = false;
+                        printf("sps %lld %lld %lld %lld %lld %lld %llu\n", (long long)sps.profile, (long long)sps.level,
+                               (long long)sps.pic_width_in_mbs_minus1, (long long)sps.pic_height_in_map_units_minus1,
+                               (long long)sps.pic_order_count_type, (long long)sps.n_hrd, (unsigned long long)sps.bits_read);
+                    } else if (u.Type == 8) {
+                        pps = h264::NewPPS(have_sps ? &sps : nullptr, u.RBSP());
+                        have_pps = have_sps;
+                        printf("pps %lld %lld %lld %lld %lld %llu\n", (long long)pps.id, (long long)pps.entropy_coding_mode,
+                               (long long)pps.pic_init_qp_minus26, (long long)pps.chroma_qp_index_offset,
+                               (long long)pps.transform_8x8_mode, (unsigned long long)pps.bits_read);
+                    } else if ((u.Type == 1 || u.Type == 5) && have_sps && have_pps) {
+                        const auto h = h264::SliceHeaders(h264::ParamSets(sps, pps), {u});
+                        printf("slice %lld %lld %lld %llu\n", (long long)h[0].slice_type, (long long)h[0].slice_qp_y,
+                               (long long)h[0].cabac_init_idc, (unsigned long long)h[0].header_bits);
+                    }
+                } catch (const h264::Panic &) {
+                    printf("panic %d\n", u.Type);
+                }
+            }
         } else if (mode == "ctx") {  // PreCtxState / MNVars / InitContexts
             for (int i = 2; i + 2 < argc; i += 3)
                 printf("pre %d\n", h264::PreCtxState(atoi(argv[i]), atoi(argv[i + 1]), atoi(argv[i + 2])));

@@ -160,3 +160,62 @@ def test_engine_methods_per_call(exe, tmp_path):
     assert out[25] == ["core", str(bv), str(r2), str(o2)]
     p2, v2 = orc.state_transition(int(state[0] & 63), int(state[0] >> 6), 1 - int(state[0] >> 6))
     assert out[26] == ["trans", str(p2), str(v2)]
+
+
+@pytest.mark.gpu
+def test_parameter_sets_and_slice_headers_like_handle_connection(exe, tmp_path):
+    """h264::NewSPS / NewPPS / SliceHeaders driven the way handleConnection dispatches NAL units (server.go:145-162)"""
+    from tests.test_param_sets import write_sps, write_pps, H
+    from tests.test_slice_header import write_header, SPS_KEYS, PPS_KEYS
+    import harness as hz
+    rng = np.random.default_rng(5)
+    SC = b"\x00\x00\x00\x01"
+    parts, exp = [], []
+    ps = None
+    for ev in ["sps", "pps", "slice", "slice", "badpps", "slice", "pps", "slice", "sps", "pps", "slice", "slice"]:
+        if ev == "sps":
+            rb = write_sps(rng)[0]
+            parts += [SC, b"\x67", hz.escape(np.frombuffer(rb, np.uint8)).tobytes()]
+        elif ev in ("pps", "badpps"):
+            rb = write_pps(rng, entropy=1)[0] if ev == "pps" else H("EE0F2CC0") + b"\x80"
+            parts += [SC, b"\x68", hz.escape(np.frombuffer(rb, np.uint8)).tobytes()]
+        else:
+            # the header is written against the parameter sets in force (parsed back by the oracle below)
+            onal, orbsp = orc.read_nal_units_arrays(np.frombuffer(b"".join(parts) + SC, np.uint8))
+            rb_of = lambda k: orbsp[int(onal["rbsp_off"][k]):int(onal["rbsp_off"][k]) + int(onal["rbsp_len"][k])]
+            k7, k8 = np.flatnonzero(onal["type"] == 7), np.flatnonzero(onal["type"] == 8)
+            st1, f1 = orc.new_sps(rb_of(k7[-1]))
+            st2, f2 = orc.new_pps(rb_of(k8[-1]))
+            if st1 == orc.OK and st2 == orc.OK and k8[-1] > k7[-1]:
+                ps = {k: f1[v] for k, v in SPS_KEYS.items()}
+                ps.update({k: f2[v] for k, v in PPS_KEYS.items()})
+                hb, _ = write_header(rng, ps, 1, 2, int(rng.integers(0, 10)))
+            else:
+                hb = bytes(rng.integers(1, 255, 10).astype(np.uint8))
+            parts += [SC, b"\x41", hz.escape(np.frombuffer(hb, np.uint8)).tobytes()]
+    stream = np.frombuffer(b"".join(parts) + SC, np.uint8)
+    path = os.path.join(str(tmp_path), "psets.bin")
+    stream.tofile(path)
+    rc, out = run(exe, "psets", path)
+    assert rc == 0, out
+    onal, orbsp = orc.read_nal_units_arrays(stream)
+    sps = pps = None
+    for k in range(len(onal["start"])):
+        rb = orbsp[int(onal["rbsp_off"][k]):int(onal["rbsp_off"][k]) + int(onal["rbsp_len"][k])]
+        t = int(onal["type"][k])
+        if t == 7:
+            st, f = orc.new_sps(rb)
+            sps, pps = (f if st == orc.OK else None), None
+            exp.append(["sps"] + [str(f[n]) for n in ("Profile", "Level", "PicWidthInMbsMinus1", "PicHeightInMapUnitsMinus1",
+                                                      "PicOrderCountType", "n_hrd", "bits_read")] if st == orc.OK else ["panic", "7"])
+        elif t == 8:
+            st, f = orc.new_pps(rb)
+            pps = f if (st == orc.OK and sps is not None) else None
+            exp.append(["pps"] + [str(f[n]) for n in ("ID", "EntropyCodingMode", "PicInitQpMinus26", "ChromaQpIndexOffset",
+                                                      "Transform8x8Mode", "bits_read")] if st == orc.OK else ["panic", "8"])
+        elif t in (1, 5) and sps is not None and pps is not None:
+            st, h = orc.new_slice_header(sps, pps, t, int(onal["ref_idc"][k]), rb)
+            exp.append(["slice", str(h["SliceType"]), str(h["SliceQPy"]), str(h["CabacInit"]), str(h["bits_read"])]
+                       if st == orc.OK else ["panic", str(t)])
+    assert out == exp
+    assert sum(l[0] == "slice" for l in out) >= 4 and ["panic", "8"] in out
