@@ -87,8 +87,10 @@ int main(int argc, char **argv) {
                         printf("slice %lld %lld %lld %llu\n", (long long)h[0].slice_type, (long long)h[0].slice_qp_y,
                                (long long)h[0].cabac_init_idc, (unsigned long long)h[0].header_bits);
                     }
-                } catch (const h264::Panic &) {
+                } catch (const h264::Panic &) {  // (the reference exits here; going on, the failed set is not usable)
                     printf("panic %d\n", u.Type);
+                    if (u.Type == 7) have_sps = have_pps = false;
+                    if (u.Type == 8) have_pps = false;
                 }
             }
         } else if (mode == "ctx") {  // PreCtxState / MNVars / InitContexts
