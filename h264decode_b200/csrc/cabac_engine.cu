@@ -21,6 +21,32 @@ namespace h264b {
 #define H264B_CABAC_WARPS 2
 #endif
 constexpr int kWarpsPerCta = H264B_CABAC_WARPS;
+constexpr int kTabBytes = 1024 + 2048;  // engine table + its fast-loop form, in front of the context states
+
+// explicit shared-memory accesses (32-bit shared addresses: no generic-address arithmetic in the inner loop)
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u32x2(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {  // (no masking of the selector)
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ uint32_t opaque(uint32_t x) {  // keeps an address in a register instead of re-deriving it
+    asm volatile("mov.b32 %0, %0;" : "+r"(x));
+    return x;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 
 struct CabacArgs {
     h264b_cabac_job j;
@@ -106,9 +132,15 @@ __device__ __forceinline__ int clip3_dev(int x, int y, int z) { return z < x ? x
 __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *s_tab = reinterpret_cast<uint64_t *>(smem);                  // 128 x 8 B
-    uint8_t *s_state_all = smem + 1024;                                    // [warp][n_ctx][32]
+    uint64_t *s_tab_fast = reinterpret_cast<uint64_t *>(smem + 1024);      // 256 x 8 B: the fast loop's form
+    uint8_t *s_state_all = smem + kTabBytes;                               // [warp][n_ctx][32]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 128; i += kWarpsPerCta * 32) s_tab[i] = a.tab[i];
+    for (int i = tid; i < 256; i += kWarpsPerCta * 32) {
+        const uint64_t e = a.tab[i & 127];
+        if (i < 128) s_tab[i] = e;
+        // bins from bit 0 to bit 7 of their bytes (bits 40 -> 47, 56 -> 63); entries 128..255 repeat 0..127
+        s_tab_fast[i] = (e & 0x00FF00FFFFFFFFFFull) | ((e & 0x0100010000000000ull) << 7);
+    }
     __syncthreads();
     const h264b_cabac_job &j = a.j;
     const uint32_t n_ctx = j.n_ctx;
@@ -160,65 +192,106 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
     uint32_t word = 0;
     uint32_t i = 0;
     // ---- fast loop: blocks of 32 ops (one word of bins) while every lane of the warp is active and on the window
-    // engine -- the usual case for all but the tail of a length bundle.  Nothing is predicated: the 32 ops of a block
-    // are fetched with one coalesced load and handed out by shuffle, bins are funnel-shifted into the word, the table
-    // fields are picked with byte permutes.  Same arithmetic as CabacLane::decision / bypass / terminate.
-    uint32_t warp_min = valid ? my_ops : 0u;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) warp_min = min(warp_min, __shfl_xor_sync(0xFFFFFFFFu, warp_min, d));
-    if (warp_min >= 32u && !__any_sync(0xFFFFFFFFu, eng.lit)) {
+    // engine -- the usual case for all but the tail of a length bundle.  Same arithmetic as CabacLane::decision /
+    // bypass / terminate, arranged for the fewest issue slots per bin:
+    //   * the op kinds of a block are two ballots, so every branch on them is warp-uniform (no convergence barriers);
+    //   * shared memory is addressed with explicit 32-bit shared addresses (ld/st.shared), not generic pointers;
+    //   * codIRange is kept as R << 22, aligned with codIOffset in the window: (R22 >> 28) is 4 + qCodIRangeIdx, which as
+    //     a byte-permute selector picks rangeTabLPS[state][q] out of the table word directly; the renormalisation
+    //     shift is clz(R22) - 1;
+    //   * the fast table (256 entries, no masking of the state byte) carries the bin in bit 7 of its byte, so one
+    //     byte permute yields (next state -> byte 0, bin -> bit 31) and one funnel shift appends the bin; the word is
+    //     bit-reversed once per 32 bins;
+    //   * refills are checked once per two ops (16 bits cover two decisions).
+    // (every condition that steers the loop is a vote result: the compiler then knows the warp stays converged and
+    //  emits the shuffles and votes inside without divergence checks)
+    if (__all_sync(0xFFFFFFFFu, my_ops >= 32u && !eng.lit)) {
         CabacLane &w = eng.w;
+        const uint32_t st_lane = opaque(smem_addr(s_state) + (uint32_t)lane);  // &state[0][lane]
+        const uint32_t tab_fast = opaque(smem_addr(s_tab_fast));
+        const uint32_t sel_mps = opaque(0x1440u), sel_lps = opaque(0x3442u);  // byte-permute selectors, kept in registers
+        uint32_t R22 = w.R << 22, hi = w.hi, lo = w.lo;
+        int32_t fbits = w.fbits;
         bool left = false;
-        while (i + 32u <= warp_min && !left) {
-            uint32_t my_op = j.ops[i + (uint32_t)lane];
-            if ((my_op >> 14) == H264B_OP_DECISION && (my_op & 0x3FFu) >= n_ctx) my_op &= ~0x3FFu;  // as below: ctx 0
+        while (!left && __all_sync(0xFFFFFFFFu, i + 32u <= my_ops)) {
+            const uint32_t my_op = j.ops[i + (uint32_t)lane];
+            const uint32_t my_kind = my_op >> 14;
+            const uint32_t dec_mask = __ballot_sync(0xFFFFFFFFu, my_kind == H264B_OP_DECISION);
+            const uint32_t byp_mask = __ballot_sync(0xFFFFFFFFu, my_kind == H264B_OP_BYPASS);
+            uint32_t my_row = ((my_op & 0x3FFu) < n_ctx ? (my_op & 0x3FFu) : 0u) * 32u;  // as below: ctx 0
             uint32_t k = 0;
 #pragma unroll 1
-            for (; k < 32u; k++) {
-                const uint32_t op = __shfl_sync(0xFFFFFFFFu, my_op, (int)k);
-                if (__builtin_expect(__any_sync(0xFFFFFFFFu, w.must_refill()), 0)) {
-                    if (w.can_refill()) w.refill();
-                }
-                const uint32_t kind = op >> 14;
-                uint32_t sel;  // the bin in bit 8
-                if (kind == H264B_OP_DECISION) {
-                    uint8_t *sp = s_state + (op & 0x3FFu) * 32u + (uint32_t)lane;
-                    const uint64_t e = s_tab[*sp & 127u];
-                    const uint32_t tlo = (uint32_t)e, thi = (uint32_t)(e >> 32);
-                    const uint32_t lps = __byte_perm(tlo, 0u, ((w.R >> 6) & 3u) | 0x4440u);  // rangeTabLPS[state][q]
-                    const uint32_t rm = w.R - lps, x = rm << 22;
-                    const bool is_lps = w.hi >= x;
-                    w.hi = is_lps ? w.hi - x : w.hi;
-                    const uint32_t r = is_lps ? lps : rm;
-                    sel = __byte_perm(thi, 0u, is_lps ? 0x4432u : 0x4410u);  // (next state, bin) of the path taken
-                    *sp = (uint8_t)sel;
-                    const uint32_t sh = clz32(r) - 23u;
-                    w.R = r << sh;
-                    w.shift(sh);
-                } else if (kind == H264B_OP_BYPASS) {
-                    sel = w.bypass() << 8;
-                } else {
-                    const uint32_t bin = w.terminate();
-                    sel = bin << 8;
-                    if (__any_sync(0xFFFFFFFFu, bin)) {  // a slice that goes on after its end: the generic loop takes over
-                        if (bin) eng.to_literal();
-                        left = true;
+            for (uint32_t k8 = 0; k8 < 32u && !left; k8 += 8u) {
+                // lanes 0..7 hold the rows of this chunk's ops (the rows rotate by 8 lanes per chunk), so the shuffles
+                // below have constant source lanes
+                const uint32_t dm = dec_mask >> k8, bm = byp_mask >> k8;
+                const uint32_t row8 = my_row;
+                my_row = __shfl_sync(0xFFFFFFFFu, my_row, (lane + 8) & 31);
+#pragma unroll
+                for (uint32_t u = 0; u < 8u; u++) {
+                    if ((u & 1u) == 0u) {
+                        if (__builtin_expect(__any_sync(0xFFFFFFFFu, fbits < 16), 0)) {
+                            __syncwarp();  // (also keeps this rare block a branch instead of 20 predicated instructions)
+                            if (fbits <= 22) {
+                                w.hi = hi, w.lo = lo, w.fbits = fbits;
+                                w.refill();
+                                hi = w.hi, lo = w.lo, fbits = w.fbits;
+                            }
+                        }
+                    }
+                    if (dm & (1u << u)) {
+                        const uint32_t addr = __shfl_sync(0xFFFFFFFFu, row8, (int)u) + st_lane;
+                        const uint32_t st = lds_u8(addr);
+                        const uint2 e = lds_u32x2(tab_fast + st * 8u);
+                        const uint32_t lps22 = prmt(0u, e.x, R22 >> 28) << 22;  // rangeTabLPS[state][q] << 22
+                        const uint32_t rm22 = R22 - lps22;
+                        const bool is_lps = hi >= rm22;
+                        const uint32_t r22 = is_lps ? lps22 : rm22;
+                        const uint32_t hi_lps = hi - rm22;
+                        hi = is_lps ? hi_lps : hi;
+                        const uint32_t sel = prmt(e.y, 0u, is_lps ? sel_lps : sel_mps);  // next state | bin << 31
+                        sts_u8(addr, sel);
+                        const uint32_t sh = (uint32_t)__clz((int)r22) - 1u;
+                        R22 = r22 << sh;
+                        hi = __funnelshift_l(lo, hi, sh);
+                        lo <<= sh;
+                        fbits -= (int32_t)sh;
+                        word = __funnelshift_l(sel, word, 1);
+                    } else if (bm & (1u << u)) {
+                        hi = __funnelshift_l(lo, hi, 1);
+                        lo <<= 1;
+                        fbits -= 1;
+                        const bool one = hi >= R22;
+                        if (one) hi -= R22;
+                        word = (word << 1) | (one ? 1u : 0u);
+                    } else {
+                        w.R = R22 >> 22, w.hi = hi, w.lo = lo, w.fbits = fbits;
+                        const uint32_t bin = w.terminate();
+                        R22 = w.R << 22, hi = w.hi, lo = w.lo, fbits = w.fbits;
+                        word = (word << 1) | bin;
+                        if (__any_sync(0xFFFFFFFFu, bin)) {  // a slice that goes on after its end: the generic loop takes over
+                            if (bin) eng.to_literal();
+                            left = true;
+                            k = k8 + u + 1u;
+                            break;
+                        }
                     }
                 }
-                word = __funnelshift_r(word, sel >> 8, 1);  // bin k of the block ends up in bit k
-                if (left) {
-                    k++;
-                    break;
-                }
             }
-            i += k;
-            if (k == 32u) {
-                if (own) bins[(i >> 5) - 1u] = word;
+            if (!left) {
+                i += 32u;
+                if (own) bins[(i >> 5) - 1u] = __brev(word);
                 word = 0;
             } else {
-                word >>= 32u - k;  // a partial block: bins 0..k-1 in bits 0..k-1, the generic loop goes on from there
+                i += k;
+                word = k < 32u ? __brev(word) >> (32u - k) : __brev(word);  // bins 0..k-1 in bits 0..k-1
+                if (k == 32u) {
+                    if (own) bins[(i >> 5) - 1u] = word;
+                    word = 0;
+                }
             }
         }
+        if (!eng.lit) w.R = R22 >> 22, w.hi = hi, w.lo = lo, w.fbits = fbits;
     }
     // ---- generic loop: lanes that have finished, lanes on the literal engine
     uint32_t next_op = i < warp_ops ? j.ops[i] : 0;
@@ -325,7 +398,7 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
         H264B_LAUNCH_CHECK(ctx, "sort_scatter_kernel");
         a.order = order;
     }
-    const size_t smem = 1024 + (size_t)kWarpsPerCta * j.n_ctx * 32;
+    const size_t smem = kTabBytes + (size_t)kWarpsPerCta * j.n_ctx * 32;
     const int blocks = (int)((a.n_warps + kWarpsPerCta - 1) / kWarpsPerCta);
     H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cabac_decode_kernel<<<blocks, kWarpsPerCta * 32, smem, ctx->stream>>>(a);
