@@ -915,17 +915,19 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
         return set_error(ctx, H264B_E_INVALID, "annexb_scan: d_stream and d_rbsp must be 16-byte aligned");
     if (n >= (1ull << 42)) return set_error(ctx, H264B_E_INVALID, "annexb_scan: stream too long");
     const ScratchOffsets so = scratch_layout(n, nal_cap);
-    if (so.total > ctx->scan_scratch_bytes) {
-        if (ctx->scan_scratch) {
+    void *&scratch = ctx->scan_scratch[ctx->bank];
+    size_t &scratch_bytes = ctx->scan_scratch_bytes[ctx->bank];
+    if (so.total > scratch_bytes) {
+        if (scratch) {
             H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            cudaFree(ctx->scan_scratch);
+            cudaFree(scratch);
         }
-        ctx->scan_scratch = nullptr;
-        ctx->scan_scratch_bytes = 0;
-        H264B_CUDA(ctx, cudaMalloc(&ctx->scan_scratch, so.total));
-        ctx->scan_scratch_bytes = so.total;
+        scratch = nullptr;
+        scratch_bytes = 0;
+        H264B_CUDA(ctx, cudaMalloc(&scratch, so.total));
+        scratch_bytes = so.total;
     }
-    uint8_t *s = (uint8_t *)ctx->scan_scratch;
+    uint8_t *s = (uint8_t *)scratch;
     const uint64_t n_chunks = (n + kChunk - 1) / kChunk;
     ScanArgs a;
     a.in = d_stream;

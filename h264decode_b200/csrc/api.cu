@@ -20,19 +20,21 @@ int set_error(h264b_ctx *ctx, int code, const char *fmt, ...) {
 
 int ensure_dev(h264b_ctx *ctx, int slot, size_t bytes, void **out) {
     if (bytes < 256) bytes = 256;
-    if (ctx->d_buf_bytes[slot] < bytes) {
-        if (ctx->d_buf[slot]) {
+    void *&buf = ctx->d_buf[ctx->bank][slot];
+    size_t &have = ctx->d_buf_bytes[ctx->bank][slot];
+    if (have < bytes) {
+        if (buf) {
             H264B_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            cudaFree(ctx->d_buf[slot]);
-            ctx->d_buf[slot] = nullptr;
-            ctx->d_buf_bytes[slot] = 0;
+            cudaFree(buf);
+            buf = nullptr;
+            have = 0;
         }
         const size_t want = bytes + bytes / 8;
-        cudaError_t e = cudaMalloc(&ctx->d_buf[slot], want);
+        cudaError_t e = cudaMalloc(&buf, want);
         if (e != cudaSuccess) return set_error(ctx, H264B_E_NOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
-        ctx->d_buf_bytes[slot] = want;
+        have = want;
     }
-    *out = ctx->d_buf[slot];
+    *out = buf;
     return H264B_OK;
 }
 
@@ -103,7 +105,8 @@ int32_t h264b_create(int32_t device, h264b_ctx **out) {
               cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < 2 && ok; i++) {
         StreamSlot *sl = (StreamSlot *)calloc(1, sizeof(StreamSlot));
-        ok = sl && cudaEventCreate(&sl->e_in) == cudaSuccess && cudaEventCreate(&sl->e_compute) == cudaSuccess &&
+        ok = sl && cudaStreamCreateWithFlags(&sl->cs, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreate(&sl->e_in) == cudaSuccess && cudaEventCreate(&sl->e_compute) == cudaSuccess &&
              cudaEventCreate(&sl->e_out) == cudaSuccess && cudaEventCreate(&sl->t_in0) == cudaSuccess &&
              cudaEventCreate(&sl->t_c0) == cudaSuccess && cudaEventCreate(&sl->t_o0) == cudaSuccess;
         ctx->slot[i] = sl;
@@ -136,16 +139,19 @@ void h264b_destroy(h264b_ctx *ctx) {
         cudaFree(ctx->d_mn[v]);
         cudaFree(ctx->d_state_lut[v]);
     }
-    for (int i = 0; i < 20; i++) cudaFree(ctx->d_buf[i]);
+    for (int b = 0; b < 3; b++) {
+        for (int i = 0; i < 20; i++) cudaFree(ctx->d_buf[b][i]);
+        cudaFree(ctx->scan_scratch[b]);
+    }
     for (int i = 0; i < 8; i++)
         if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
-    cudaFree(ctx->scan_scratch);
     for (int i = 0; i < 2; i++) {
         StreamSlot *sl = ctx->slot[i];
         if (!sl) continue;
         for (int k = 0; k < kSlotDev; k++) cudaFree(sl->d[k]);
         for (int k = 0; k < kSlotPin; k++)
             if (sl->h[k]) cudaFreeHost(sl->h[k]);
+        if (sl->cs) cudaStreamDestroy(sl->cs);
         if (sl->e_in) cudaEventDestroy(sl->e_in);
         if (sl->e_compute) cudaEventDestroy(sl->e_compute);
         if (sl->e_out) cudaEventDestroy(sl->e_out);
@@ -466,9 +472,23 @@ static int slot_pin(h264b_ctx *ctx, StreamSlot *sl, int i, size_t bytes, void **
     return H264B_OK;
 }
 
+static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job, uint64_t *ticket);
+
 int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_t *ticket) {
     CHECK_CTX(ctx);
     if (!job || !ticket) return H264B_E_INVALID;
+    // the job's kernels go to its slot's own stream and scratch bank (restored whatever happens)
+    const cudaStream_t saved_stream = ctx->stream;
+    const int saved_bank = ctx->bank;
+    ctx->stream = ctx->slot[ctx->next_ticket & 1]->cs;
+    ctx->bank = 1 + (int)(ctx->next_ticket & 1);
+    const int32_t rc = stream_submit_on_slot(ctx, job, ticket);
+    ctx->stream = saved_stream;
+    ctx->bank = saved_bank;
+    return rc;
+}
+
+static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job, uint64_t *ticket) {
     const h264b_stream_job &j = *job;
     const bool from_headers = (j.flags & H264B_STREAM_SLICE_HEADERS) != 0 && j.max_slices != 0;
     const bool own_psets = from_headers && (j.flags & H264B_STREAM_PARAM_SETS) != 0;

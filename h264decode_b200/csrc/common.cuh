@@ -16,9 +16,11 @@ struct h264b_ctx {
     char err[512];
     uint64_t launches;
 
-    // grow-only device scratch
-    void *scan_scratch;
-    size_t scan_scratch_bytes;
+    // grow-only device scratch, in three banks: [0] the direct ("_dev" and host-pointer) entry points, [1] and [2] the
+    // two stream-job slots, whose kernels run on their own streams and may overlap each other
+    int bank;
+    void *scan_scratch[3];
+    size_t scan_scratch_bytes[3];
 
     // constant device tables, built once in h264b_create: [0] = REF, [1] = SPEC
     uint64_t *d_cabac_tab[2];   // 128 entries, see cabac_engine.cu
@@ -30,8 +32,8 @@ struct h264b_ctx {
     // host-level (pinned) staging, grow-only
     void *h_pin[8];
     size_t h_pin_bytes[8];
-    void *d_buf[20];
-    size_t d_buf_bytes[20];
+    void *d_buf[3][20];
+    size_t d_buf_bytes[3][20];
 
     // h264b_stream_submit / h264b_stream_wait: two jobs in flight, each with its own buffers and events
     cudaStream_t s_in, s_out;  // copy streams (host -> device, device -> host)
@@ -47,6 +49,7 @@ struct StreamSlot {
     size_t d_bytes[kSlotDev];
     void *h[kSlotPin];
     size_t h_bytes[kSlotPin];
+    cudaStream_t cs;     // the slot's compute stream: the tail of one job's CABAC kernel overlaps the next job's kernels
     cudaEvent_t e_in, e_compute, e_out;
     cudaEvent_t t_in0, t_c0, t_o0;  // H264B_TRACE=1: phase starts (timing events)
     uint64_t ticket;     // job occupying the slot
