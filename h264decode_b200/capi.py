@@ -29,6 +29,7 @@ SYMBOLS = [
     "h264b_slice_select_dev",
     "h264b_parse_sps", "h264b_parse_pps", "h264b_parse_sps_dev", "h264b_parse_pps_dev", "h264b_make_param_sets",
     "h264b_param_set_select_dev",
+    "h264b_ctx_idx", "h264b_new_binarization", "h264b_init_cabac", "h264b_mb_bin_string", "h264b_bin_string_match",
 ]
 
 NAL_DTYPE = np.dtype([("start", "<u8"), ("rbsp_off", "<u8"), ("num_bytes", "<u4"), ("rbsp_len", "<u4"),
@@ -123,6 +124,12 @@ PPS_SCALARS = [
 PPS_DTYPE = np.dtype([(n, "<i8") for n in PPS_SCALARS] + [("bits_read", "<u8"), ("status", "<u4"), ("reserved", "<u4")])
 
 
+BINARIZATION_FIELDS = ["syntax_element", "prefix_suffix", "fixed_length", "unary", "truncated_unary", "cmax", "uegk",
+                       "cmax_value", "max_is_prefix_suffix", "max_prefix", "max_suffix", "off_is_prefix_suffix",
+                       "off_prefix", "off_suffix", "use_decode_bypass", "reserved"]
+BINARIZATION_DTYPE = np.dtype([(n, "<i4") for n in BINARIZATION_FIELDS])
+NA_CTX_ID = 10000
+
 SLICE_HEADER_FIELDS = [
     "first_mb_in_slice", "slice_type", "pps_id", "color_plane_id", "field_pic", "bottom_field", "idr_pic_id",
     "pic_order_cnt_lsb", "delta_pic_order_cnt_bottom", "delta_pic_order_cnt0", "delta_pic_order_cnt1",
@@ -193,6 +200,11 @@ def load():
         "h264b_parse_pps_dev": (i32, [vp, vp, u64, vp, vp, vp, vp, u32, vp, vp]),
         "h264b_make_param_sets": (i32, [vp, vp, P(ParamSets)]),
         "h264b_param_set_select_dev": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp]),
+        "h264b_ctx_idx": (i32, [vp, u32, vp, vp, vp, vp]),
+        "h264b_new_binarization": (i32, [vp, u32, vp, vp, vp]),
+        "h264b_init_cabac": (i32, [vp, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "h264b_mb_bin_string": (i32, [vp, u32, vp, vp, vp, vp, vp]),
+        "h264b_bin_string_match": (i32, [vp, u32, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -483,6 +495,45 @@ class Context:
         if rc:
             raise H264BError(rc)
         return p
+
+    # ---- syntax-element glue (rows I5 / f3): batches of queries, one device thread each
+    def ctx_idx(self, bin_idx, max_bin_idx_ctx, ctx_idx_offset):
+        a, b, c = (np.ascontiguousarray(x, dtype=np.int64) for x in (bin_idx, max_bin_idx_ctx, ctx_idx_offset))
+        out = np.zeros(len(a), np.int64)
+        self._check(_lib.h264b_ctx_idx(self.h, len(a), a.ctypes.data, b.ctypes.data, c.ctypes.data, out.ctypes.data))
+        return out
+
+    def new_binarization(self, syntax_element, slice_type_name):
+        a, b = (np.ascontiguousarray(x, dtype=np.int32) for x in (syntax_element, slice_type_name))
+        out = np.zeros(len(a), BINARIZATION_DTYPE)
+        self._check(_lib.h264b_new_binarization(self.h, len(a), a.ctypes.data, b.ctypes.data, out.ctypes.data))
+        return out
+
+    def init_cabac(self, bin_idx, max_prefix, off_prefix, pic_init_qp_minus26, slice_qp_delta, flags=0):
+        arrs = [np.ascontiguousarray(x, dtype=np.int64) for x in (bin_idx, max_prefix, off_prefix, pic_init_qp_minus26,
+                                                                   slice_qp_delta)]
+        n = len(arrs[0])
+        p, v, c = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int64)
+        self._check(_lib.h264b_init_cabac(self.h, flags, n, *[a.ctypes.data for a in arrs], p.ctypes.data, v.ctypes.data,
+                                          c.ctypes.data))
+        return p, v, c
+
+    def mb_bin_string(self, slice_type_name, mb_type, sub_mb):
+        a = np.ascontiguousarray(slice_type_name, dtype=np.int32)
+        b = np.ascontiguousarray(mb_type, dtype=np.int64)
+        c = np.ascontiguousarray(sub_mb, dtype=np.uint8)
+        ln, bits = np.zeros(len(a), np.int32), np.zeros(len(a), np.uint32)
+        self._check(_lib.h264b_mb_bin_string(self.h, len(a), a.ctypes.data, b.ctypes.data, c.ctypes.data, ln.ctypes.data,
+                                             bits.ctypes.data))
+        return ln, bits
+
+    def bin_string_match(self, bin_len, bin_bits, n_bits, bits):
+        a, c = (np.ascontiguousarray(x, dtype=np.int32) for x in (bin_len, n_bits))
+        b, d = (np.ascontiguousarray(x, dtype=np.uint32) for x in (bin_bits, bits))
+        out = np.zeros(len(a), np.int32)
+        self._check(_lib.h264b_bin_string_match(self.h, len(a), a.ctypes.data, b.ctypes.data, c.ctypes.data, d.ctypes.data,
+                                                out.ctypes.data))
+        return out
 
     def slice_headers(self, params, data, off, length, nal_type, nal_ref_idc):
         """host buffers -> SLICE_HEADER_DTYPE[n]"""

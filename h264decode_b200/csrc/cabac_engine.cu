@@ -17,9 +17,6 @@
 
 namespace h264b {
 
-#ifndef H264B_CABAC_PIPELINE
-#define H264B_CABAC_PIPELINE 1  // fast loop: load context state / table entry of a decision ahead of time
-#endif
 #ifndef H264B_CABAC_WARPS
 #define H264B_CABAC_WARPS 2
 #endif
@@ -46,12 +43,6 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 __device__ __forceinline__ uint32_t opaque(uint32_t x) {  // keeps an address in a register instead of re-deriving it
     asm volatile("mov.b32 %0, %0;" : "+r"(x));
     return x;
-}
-__device__ __forceinline__ uint32_t ldg_if(const uint32_t *p, bool take, uint32_t otherwise) {  // predicated load
-    asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p ld.global.nc.u32 %0, [%1]; }"
-                 : "+r"(otherwise)
-                 : "l"(p), "r"((uint32_t)take));
-    return otherwise;
 }
 __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
@@ -147,18 +138,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
     for (int i = tid; i < 256; i += kWarpsPerCta * 32) {
         const uint64_t e = a.tab[i & 127];
         if (i < 128) s_tab[i] = e;
-        // bins from bit 0 to bit 7 of their bytes (bits 40 -> 47, 56 -> 63); entries 128..253 repeat 0..125.
-        // 254 / 255: the pseudo states of DecodeTerminate / DecodeBypass (rangeLPS 2 / 0 in every column, bin = "LPS"
-        // path taken, self transition)
-        uint64_t f = (e & 0x00FF00FFFFFFFFFFull) | ((e & 0x0100010000000000ull) << 7);
-        if (i == 254) f = 0x80FE00FE02020202ull;
-        if (i == 255) f = 0x80FF00FF00000000ull;
-        s_tab_fast[i] = f;
+        // bins from bit 0 to bit 7 of their bytes (bits 40 -> 47, 56 -> 63); entries 128..255 repeat 0..127
+        s_tab_fast[i] = (e & 0x00FF00FFFFFFFFFFull) | ((e & 0x0100010000000000ull) << 7);
     }
     __syncthreads();
     const h264b_cabac_job &j = a.j;
     const uint32_t n_ctx = j.n_ctx;
-    uint8_t *s_state = s_state_all + (size_t)warp * (n_ctx + 2) * 32;  // (+ 2 pseudo contexts, see the fast loop)
+    uint8_t *s_state = s_state_all + (size_t)warp * n_ctx * 32;
 
     const uint32_t gw = blockIdx.x * kWarpsPerCta + warp;
     if (gw >= a.n_warps) return;
@@ -182,7 +168,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
         off = j.off[slice];
         len = j.len[slice];
     }
-    bool pseudo_clash = false;
     // initial context states: given, or the K4 rule (state LUT row of this slice's (idc class, clipped qp))
     if (valid) {
         const uint8_t *src;
@@ -192,13 +177,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
             const h264b_slice_qp p = j.qp[slice];
             src = a.lut + ((size_t)idc_class_dev(p.cabac_init_idc) * 52 + clip3_dev(0, 51, p.slice_qp_y)) * 1024;
         }
-        for (uint32_t c = 0; c < n_ctx; c++) {
-            const uint8_t b = src[c];
-            s_state[c * 32 + lane] = b;
-            pseudo_clash |= b >= 254;  // (only a caller's init_states can hold such bytes)
-        }
-        s_state[n_ctx * 32 + lane] = 255;        // pseudo context of DecodeBypass (fast loop)
-        s_state[(n_ctx + 1) * 32 + lane] = 254;  // ... of DecodeTerminate
+        for (uint32_t c = 0; c < n_ctx; c++) s_state[c * 32 + lane] = src[c];
     }
     __syncwarp();
 
@@ -214,148 +193,94 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
     uint32_t i = 0;
     // ---- fast loop: blocks of 32 ops (one word of bins) while every lane of the warp is active and on the window
     // engine -- the usual case for all but the tail of a length bundle.  Same arithmetic as CabacLane::decision /
-    // bypass / terminate.  A warp's time is the serial dependency chain codIRange / codIOffset -> next bin, plus every
-    // taken branch (tens of cycles for a warp that has its scheduler to itself, as the long slices at the end of a
-    // launch do), so the loop is straight-line code with nothing but that chain on the critical path:
-    //   * every op is a decision: DecodeBypass and DecodeTerminate are decisions on two pseudo contexts whose state
-    //     bytes (255, 254) select table entries with rangeLPS = 0 resp. 2 in every column and a self transition.
-    //     What remains kind-specific is data, not control: a shift count (bypass consumes its bit before the
-    //     comparison) and a flag (only a real LPS path replaces codIRange by the LPS range);
-    //   * the op schedule is known ahead, only the states are data: the context state of the op after next and the
-    //     table entry of the next op are loaded ahead of time, with the state just written forwarded to them when the
-    //     contexts coincide (two ballots per block);
+    // bypass / terminate, arranged for the fewest issue slots per bin:
+    //   * the op kinds of a block are two ballots, so every branch on them is warp-uniform (no convergence barriers);
     //   * shared memory is addressed with explicit 32-bit shared addresses (ld/st.shared), not generic pointers;
     //   * codIRange is kept as R << 22, aligned with codIOffset in the window: (R22 >> 28) is 4 + qCodIRangeIdx, which as
     //     a byte-permute selector picks rangeTabLPS[state][q] out of the table word directly; the renormalisation
     //     shift is clz(R22) - 1;
-    //   * the fast table carries the bin in bit 7 of its byte, so one byte permute yields (next state -> byte 0, bin ->
-    //     bit 31) and one funnel shift appends the bin; the word is bit-reversed once per 32 bins;
-    //   * refills are per lane and branch-free: every third op a lane with room for 32 more bits takes them, which
-    //     keeps at least 21 bits (three decisions) in the window;
-    //   * the only branches are the chunk loop and, in chunks that hold a terminate op, the end-of-slice test.
-    // (every condition that steers the loop is a vote result: the compiler then knows the warp stays converged)
-    if (__all_sync(0xFFFFFFFFu, my_ops >= 32u && !eng.lit && !pseudo_clash) && j.total_bytes < (1ull << 33)) {
+    //   * the fast table (256 entries, no masking of the state byte) carries the bin in bit 7 of its byte, so one
+    //     byte permute yields (next state -> byte 0, bin -> bit 31) and one funnel shift appends the bin; the word is
+    //     bit-reversed once per 32 bins;
+    //   * refills are checked once per two ops (16 bits cover two decisions).
+    // (every condition that steers the loop is a vote result: the compiler then knows the warp stays converged and
+    //  emits the shuffles and votes inside without divergence checks)
+    if (__all_sync(0xFFFFFFFFu, my_ops >= 32u && !eng.lit)) {
         CabacLane &w = eng.w;
         const uint32_t st_lane = opaque(smem_addr(s_state) + (uint32_t)lane);  // &state[0][lane]
         const uint32_t tab_fast = opaque(smem_addr(s_tab_fast));
-        const uint32_t row_byp = n_ctx * 32u, row_term = (n_ctx + 1u) * 32u;  // the pseudo contexts' rows
+        const uint32_t sel_mps = opaque(0x1440u), sel_lps = opaque(0x3442u);  // byte-permute selectors, kept in registers
         uint32_t R22 = w.R << 22, hi = w.hi, lo = w.lo;
         int32_t fbits = w.fbits;
-        // bit feed with 32-bit word indices
-        const uint32_t *words = reinterpret_cast<const uint32_t *>(j.bytes);
-        const uint32_t last_idx = (uint32_t)(w.feed.last_word - words);
-        uint32_t next_idx = (uint32_t)(w.feed.next - words), cur = w.feed.cur, pf = w.feed.pf;
-        const uint32_t entry_idx = next_idx, mis8 = w.feed.mis8;
-        const auto op_row = [&](uint32_t op) {
-            const uint32_t kind = op >> 14, c = op & 0x3FFu;
-            return kind == H264B_OP_DECISION ? (c < n_ctx ? c : 0u) * 32u : (kind == H264B_OP_BYPASS ? row_byp : row_term);
-        };
-        const auto load_op = [&](uint32_t at) { return at < j.n_ops_max ? (uint32_t)j.ops[at] : (uint32_t)(H264B_OP_BYPASS << 14); };
-        uint32_t next_op = load_op(i + (uint32_t)lane);
-        // the pipeline: (address, table entry) of the op about to run, (address, state) of the one after it
-        uint32_t a_cur, a1, s1;
-        uint2 e_cur;
-        {
-            const uint32_t r = op_row(next_op);
-            a_cur = __shfl_sync(0xFFFFFFFFu, r, 0) + st_lane;
-            a1 = __shfl_sync(0xFFFFFFFFu, r, 1) + st_lane;
-            e_cur = lds_u32x2(tab_fast + lds_u8(a_cur) * 8u);
-            s1 = lds_u8(a1);
-        }
-        // snapshot of the engine in front of a terminate op (restored by the lanes whose terminate bin is 1)
-        uint32_t snap_R22 = 0, snap_hi = 0, snap_lo = 0;
-        int32_t snap_fbits = 0;
-        uint32_t k = 0;
         bool left = false;
+        // the ops of a block are loaded one block ahead (a global load per 32 ops that is never waited for)
+        uint32_t next_op = i + (uint32_t)lane < j.n_ops_max ? (uint32_t)j.ops[i + (uint32_t)lane] : 0u;
         while (!left && __all_sync(0xFFFFFFFFu, i + 32u <= my_ops)) {
             const uint32_t my_op = next_op;
-            next_op = load_op(i + 32u + (uint32_t)lane);  // one block ahead: a global load per 32 ops, never waited for
+            next_op = i + 32u + (uint32_t)lane < j.n_ops_max ? (uint32_t)j.ops[i + 32u + (uint32_t)lane] : 0u;
             const uint32_t my_kind = my_op >> 14;
             const uint32_t dec_mask = __ballot_sync(0xFFFFFFFFu, my_kind == H264B_OP_DECISION);
             const uint32_t byp_mask = __ballot_sync(0xFFFFFFFFu, my_kind == H264B_OP_BYPASS);
-            const uint32_t term_mask = ~(dec_mask | byp_mask);
-            const uint32_t my_row = op_row(my_op), nx_row = op_row(next_op);
-            // rows of the ops at +1 and +2 (into the next block for the last lanes): same context -> forward the state
-            const uint32_t c1 = __shfl_sync(0xFFFFFFFFu, my_row, (lane + 1) & 31), n1 = __shfl_sync(0xFFFFFFFFu, nx_row, (lane + 1) & 31);
-            const uint32_t c2 = __shfl_sync(0xFFFFFFFFu, my_row, (lane + 2) & 31), n2 = __shfl_sync(0xFFFFFFFFu, nx_row, (lane + 2) & 31);
-            const uint32_t same1_mask = __ballot_sync(0xFFFFFFFFu, my_row == (lane < 31 ? c1 : n1));
-            const uint32_t same2_mask = __ballot_sync(0xFFFFFFFFu, my_row == (lane < 30 ? c2 : n2));
-            uint32_t rowx = my_row;  // lane l: row of the op at chunk position l (running on into the next block)
-
-#define H264B_FAST_OP(u, WITH_TERM)                                                                                    \
-    {                                                                                                                  \
-        if ((u) % 3 == 0) { /* u = 0, 3, 6: at most three ops between two refill points, also across chunks */        \
-            const bool need = fbits <= 22;                                                                             \
-            const uint32_t nxt = __byte_perm(pf, 0u, 0x0123u);                                                         \
-            const uint32_t v = __funnelshift_l(nxt, cur, mis8);                                                        \
-            const uint32_t sft = (uint32_t)(22 - fbits) & 31u;                                                         \
-            hi |= need ? __funnelshift_l(v, 0u, sft) : 0u; /* v >> (32 - sft), 0 for sft == 0 */                       \
-            lo |= need ? v << sft : 0u;                                                                                \
-            fbits += need ? 32 : 0;                                                                                    \
-            cur = need ? nxt : cur;                                                                                    \
-            next_idx += need ? 1u : 0u;                                                                                \
-            pf = ldg_if(words + min(next_idx, last_idx), need, pf);                                                    \
-        }                                                                                                              \
-        const uint32_t a2 = __shfl_sync(0xFFFFFFFFu, rowx, (u) + 2) + st_lane;                                         \
-        const uint32_t s2 = lds_u8(a2);                                                                                \
-        if (WITH_TERM) {                                                                                               \
-            if (tm & (1u << (u))) snap_R22 = R22, snap_hi = hi, snap_lo = lo, snap_fbits = fbits;                      \
-        }                                                                                                              \
-        const uint32_t pre = (bm >> (u)) & 1u; /* bypass: (O << 1) | bit first */                                      \
-        hi = __funnelshift_l(lo, hi, pre);                                                                             \
-        lo <<= pre;                                                                                                    \
-        fbits -= (int32_t)pre;                                                                                         \
-        const uint32_t lps22 = prmt(0u, e_cur.x, R22 >> 28) << 22; /* rangeTabLPS[state][q] << 22 */                   \
-        const uint32_t rm22 = R22 - lps22;                                                                             \
-        const bool is_lps = hi >= rm22;                                                                                \
-        const bool to_lps_range = is_lps && ((dm >> (u)) & 1u);                                                        \
-        const uint32_t r22 = to_lps_range ? lps22 : rm22;                                                              \
-        const uint32_t hi_lps = hi - rm22;                                                                             \
-        hi = is_lps ? hi_lps : hi;                                                                                     \
-        const uint32_t sel = prmt(e_cur.y, 0u, is_lps ? 0x3442u : 0x1440u); /* next state | bin << 31 */               \
-        sts_u8(a_cur, sel);                                                                                            \
-        word = __funnelshift_l(sel, word, 1);                                                                          \
-        const uint32_t sh = (uint32_t)__clz((int)r22) - 1u;                                                            \
-        R22 = r22 << sh;                                                                                               \
-        hi = __funnelshift_l(lo, hi, sh);                                                                              \
-        lo <<= sh;                                                                                                     \
-        fbits -= (int32_t)sh;                                                                                          \
-        const uint32_t st_new = sel & 0xFFu;                                                                           \
-        const uint32_t s1f = (s1m & (1u << (u))) ? st_new : s1;                                                        \
-        s1 = (s2m & (1u << (u))) ? st_new : s2;                                                                        \
-        e_cur = lds_u32x2(tab_fast + s1f * 8u);                                                                        \
-        a_cur = a1;                                                                                                    \
-        a1 = a2;                                                                                                       \
-        if (WITH_TERM) {                                                                                               \
-            if ((tm & (1u << (u))) && __any_sync(0xFFFFFFFFu, is_lps)) { /* a slice ends here: leave */                \
-                if (is_lps) R22 = snap_R22 - (2u << 22), hi = snap_hi, lo = snap_lo, fbits = snap_fbits;               \
-                left = true;                                                                                           \
-                k = k8 + (u) + 1u;                                                                                     \
-                break;                                                                                                 \
-            }                                                                                                          \
-        }                                                                                                              \
-    }
-
+            uint32_t my_row = ((my_op & 0x3FFu) < n_ctx ? (my_op & 0x3FFu) : 0u) * 32u;  // as below: ctx 0
+            uint32_t k = 0;
 #pragma unroll 1
-            for (uint32_t k8 = 0; k8 < 32u; k8 += 8u) {
-                const uint32_t dm = dec_mask >> k8, bm = byp_mask >> k8, tm = (term_mask >> k8) & 0xFFu;
-                const uint32_t s1m = same1_mask >> k8, s2m = same2_mask >> k8;
-                if (tm == 0u) {
-                    H264B_FAST_OP(0, false) H264B_FAST_OP(1, false) H264B_FAST_OP(2, false) H264B_FAST_OP(3, false)
-                    H264B_FAST_OP(4, false) H264B_FAST_OP(5, false) H264B_FAST_OP(6, false) H264B_FAST_OP(7, false)
-                } else {
-                    do {
-                        H264B_FAST_OP(0, true) H264B_FAST_OP(1, true) H264B_FAST_OP(2, true) H264B_FAST_OP(3, true)
-                        H264B_FAST_OP(4, true) H264B_FAST_OP(5, true) H264B_FAST_OP(6, true) H264B_FAST_OP(7, true)
-                    } while (false);
-                    if (left) break;
+            for (uint32_t k8 = 0; k8 < 32u && !left; k8 += 8u) {
+                // lanes 0..7 hold the rows of this chunk's ops (the rows rotate by 8 lanes per chunk), so the shuffles
+                // below have constant source lanes
+                const uint32_t dm = dec_mask >> k8, bm = byp_mask >> k8;
+                const uint32_t row8 = my_row;
+                my_row = __shfl_sync(0xFFFFFFFFu, my_row, (lane + 8) & 31);
+#pragma unroll
+                for (uint32_t u = 0; u < 8u; u++) {
+                    if ((u & 1u) == 0u) {
+                        if (__builtin_expect(__any_sync(0xFFFFFFFFu, fbits < 16), 0)) {
+                            __syncwarp();  // (also keeps this rare block a branch instead of 20 predicated instructions)
+                            if (fbits <= 22) {
+                                w.hi = hi, w.lo = lo, w.fbits = fbits;
+                                w.refill();
+                                hi = w.hi, lo = w.lo, fbits = w.fbits;
+                            }
+                        }
+                    }
+                    if (dm & (1u << u)) {
+                        const uint32_t addr = __shfl_sync(0xFFFFFFFFu, row8, (int)u) + st_lane;
+                        const uint32_t st = lds_u8(addr);
+                        const uint2 e = lds_u32x2(tab_fast + st * 8u);
+                        const uint32_t lps22 = prmt(0u, e.x, R22 >> 28) << 22;  // rangeTabLPS[state][q] << 22
+                        const uint32_t rm22 = R22 - lps22;
+                        const bool is_lps = hi >= rm22;
+                        const uint32_t r22 = is_lps ? lps22 : rm22;
+                        const uint32_t hi_lps = hi - rm22;
+                        hi = is_lps ? hi_lps : hi;
+                        const uint32_t sel = prmt(e.y, 0u, is_lps ? sel_lps : sel_mps);  // next state | bin << 31
+                        sts_u8(addr, sel);
+                        const uint32_t sh = (uint32_t)__clz((int)r22) - 1u;
+                        R22 = r22 << sh;
+                        hi = __funnelshift_l(lo, hi, sh);
+                        lo <<= sh;
+                        fbits -= (int32_t)sh;
+                        word = __funnelshift_l(sel, word, 1);
+                    } else if (bm & (1u << u)) {
+                        hi = __funnelshift_l(lo, hi, 1);
+                        lo <<= 1;
+                        fbits -= 1;
+                        const bool one = hi >= R22;
+                        if (one) hi -= R22;
+                        word = (word << 1) | (one ? 1u : 0u);
+                    } else {
+                        w.R = R22 >> 22, w.hi = hi, w.lo = lo, w.fbits = fbits;
+                        const uint32_t bin = w.terminate();
+                        R22 = w.R << 22, hi = w.hi, lo = w.lo, fbits = w.fbits;
+                        word = (word << 1) | bin;
+                        if (__any_sync(0xFFFFFFFFu, bin)) {  // a slice that goes on after its end: the generic loop takes over
+                            if (bin) eng.to_literal();
+                            left = true;
+                            k = k8 + u + 1u;
+                            break;
+                        }
+                    }
                 }
-                // next chunk: rotate the rows by 8 lanes, the last lanes take the next block's
-                const uint32_t rot = __shfl_sync(0xFFFFFFFFu, rowx, (lane + 8) & 31);
-                const uint32_t nxt_rows = __shfl_sync(0xFFFFFFFFu, nx_row, (lane + 8 + (int)k8) & 31);
-                rowx = (uint32_t)lane + 8u + k8 < 32u ? rot : nxt_rows;
             }
-#undef H264B_FAST_OP
             if (!left) {
                 i += 32u;
                 if (own) bins[(i >> 5) - 1u] = __brev(word);
@@ -369,12 +294,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
                 }
             }
         }
-        w.R = R22 >> 22, w.hi = hi, w.lo = lo, w.fbits = fbits;
-        w.refills += next_idx - entry_idx;
-        w.feed.next = words + next_idx;
-        w.feed.cur = cur;
-        w.feed.pf = pf;
-        if (left && w.hi >= (w.R << 22)) eng.to_literal();  // this lane's terminate bin was 1: O >= R from here on
+        if (!eng.lit) w.R = R22 >> 22, w.hi = hi, w.lo = lo, w.fbits = fbits;
     }
     // ---- generic loop: lanes that have finished, lanes on the literal engine
     uint32_t next_op = i < warp_ops ? j.ops[i] : 0;
@@ -481,7 +401,7 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
         H264B_LAUNCH_CHECK(ctx, "sort_scatter_kernel");
         a.order = order;
     }
-    const size_t smem = kTabBytes + (size_t)kWarpsPerCta * (j.n_ctx + 2) * 32;
+    const size_t smem = kTabBytes + (size_t)kWarpsPerCta * j.n_ctx * 32;
     const int blocks = (int)((a.n_warps + kWarpsPerCta - 1) / kWarpsPerCta);
     H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cabac_decode_kernel<<<blocks, kWarpsPerCta * 32, smem, ctx->stream>>>(a);

@@ -16,6 +16,7 @@
 //   ArithmeticDecoding.{DecodeBypass, DecodeTerminate, RenormD, BinaryDecision}  cabac.go:468-540
 //   (*CABAC).StateTransitionProcess     cabac.go:544-553     h264::CABAC::StateTransitionProcess
 //   NewSliceContext (header part)       slice.go:835-1048    h264::SliceHeaders
+//   CtxIdx, NewBinarization, initCabac  cabac.go:557, :340, :148  h264::CtxIdx, NewBinarization, InitCabac
 //   NewSPS, NewPPS                      sps.go:192, pps.go:40 h264::NewSPS, h264::NewPPS (+ h264::ParamSets for the walk)
 //   (new, batch)                                             h264::InitContexts, h264::DecodeBins
 #pragma once
@@ -430,6 +431,33 @@ inline h264b_param_sets ParamSets(const SPS &sps, const PPS &pps) {
     h264b_param_sets ps;
     if (h264b_make_param_sets(&sps, &pps, &ps) != H264B_OK) throw std::runtime_error("h264b_make_param_sets");
     return ps;
+}
+
+// ------------------------------------------------------------------------------------------------ syntax-element glue
+constexpr int NaCtxId = H264B_NA_CTX_ID;  // cabac.go:4
+// CtxIdx(binIdx, maxBinIdxCtx, ctxIdxOffset) (cabac.go:557): Table 9-39 as the reference has it
+inline int64_t CtxIdx(int64_t binIdx, int64_t maxBinIdxCtx, int64_t ctxIdxOffset, Device &dev = Device::Default()) {
+    int64_t out = 0;
+    dev.check(h264b_ctx_idx(dev.ctx(), 1, &binIdx, &maxBinIdxCtx, &ctxIdxOffset, &out));
+    return out;
+}
+// NewBinarization(syntaxElement, data) (cabac.go:340): the name as an H264B_SE_* value, data.SliceTypeName as H264B_ST_*
+using Binarization = h264b_binarization;
+inline Binarization NewBinarization(int32_t syntaxElement, int32_t sliceTypeName, Device &dev = Device::Default()) {
+    Binarization b;
+    dev.check(h264b_new_binarization(dev.ctx(), 1, &syntaxElement, &sliceTypeName, &b));
+    return b;
+}
+// initCabac(binarization, context) (cabac.go:148): the binarization's private binIdx is always 0 in the reference
+inline CABAC InitCabac(const Binarization &b, int64_t picInitQpMinus26, int64_t sliceQpDelta, int64_t binIdx = 0,
+                       uint32_t flags = 0, Device &dev = Device::Default()) {
+    const int64_t maxp = b.max_prefix, offp = b.off_prefix;
+    int32_t p = 0, v = 0;
+    dev.check(h264b_init_cabac(dev.ctx(), flags, 1, &binIdx, &maxp, &offp, &picInitQpMinus26, &sliceQpDelta, &p, &v, nullptr));
+    CABAC c;
+    c.PStateIdx = p;
+    c.ValMPS = v;
+    return c;
 }
 
 // new, batch: the whole engine for many slices at once (see h264b_cabac_job)

@@ -347,6 +347,45 @@ int32_t h264b_param_set_select_dev(h264b_ctx *ctx, const h264b_nal *d_nals, cons
                                    uint32_t nal_cap, uint32_t max_sps, uint32_t max_pps, uint32_t *d_sps_nal,
                                    uint32_t *d_pps_nal, uint32_t *d_counts);
 
+/* ------------------------------------------------------------------ syntax-element glue (rows I5 / f3)
+ * Replaces, for batches of queries (one device thread each; host pointers, synchronous):
+ *   CtxIdx            h264/cabac.go:557-758   (Table 9-39 as the reference has it; maxBinIdxCtx is never read)
+ *   NewBinarization   h264/cabac.go:340-427   (Table 9-34 rows)
+ *   initCabac         h264/cabac.go:148-174   (CtxIdx -> MNVars[ctxIdx][0] -> PreCtxState(SliceQPy) -> state split)
+ *   binIdxMbMap / binIdxSubMbMap, (*Binarization).IsBinStringMatch   h264/cabac.go:180-303, :429-436 */
+#define H264B_NA_CTX_ID 10000 /* NaCtxId, cabac.go:4 */
+#define H264B_NA_SUFFIX (-1)  /* NA_SUFFIX, cabac.go:5 */
+enum { /* syntax element names NewBinarization knows (anything else gives the zero value) */
+    H264B_SE_CODED_BLOCK_PATTERN, H264B_SE_INTRA_CHROMA_PRED_MODE, H264B_SE_MB_QP_DELTA, H264B_SE_MVD_LN_END0,
+    H264B_SE_MVD_LN_END1, H264B_SE_MB_TYPE, H264B_SE_MB_FIELD_DECODING_FLAG, H264B_SE_PREV_INTRA4X4_PRED_MODE_FLAG,
+    H264B_SE_PREV_INTRA8X8_PRED_MODE_FLAG, H264B_SE_REF_IDX_L0, H264B_SE_REF_IDX_L1, H264B_SE_REM_INTRA4X4_PRED_MODE,
+    H264B_SE_REM_INTRA8X8_PRED_MODE, H264B_SE_TRANSFORM_SIZE_8X8_FLAG, H264B_SE_OTHER
+};
+enum { H264B_ST_P, H264B_ST_B, H264B_ST_I, H264B_ST_SP, H264B_ST_SI, H264B_ST_NONE }; /* sliceTypeMap names, slice.go:105 */
+typedef struct { /* Binarization, cabac.go:318-338 (its private binIdx / binString travel separately) */
+    int32_t syntax_element;
+    int32_t prefix_suffix, fixed_length, unary, truncated_unary, cmax, uegk, cmax_value; /* BinarizationType */
+    int32_t max_is_prefix_suffix, max_prefix, max_suffix;                                /* MaxBinIdxCtx */
+    int32_t off_is_prefix_suffix, off_prefix, off_suffix;                                /* CtxIdxOffset */
+    int32_t use_decode_bypass, reserved;
+} h264b_binarization; /* 64 bytes */
+int32_t h264b_ctx_idx(h264b_ctx *ctx, uint32_t n, const int64_t *bin_idx, const int64_t *max_bin_idx_ctx,
+                      const int64_t *ctx_idx_offset, int64_t *out);
+int32_t h264b_new_binarization(h264b_ctx *ctx, uint32_t n, const int32_t *syntax_element, const int32_t *slice_type_name,
+                               h264b_binarization *out);
+/* initCabac for query i: binarization fields (bin_idx, max_prefix, off_prefix) and the slice's qp terms ->
+ * (PStateIdx, ValMPS); ctx_idx_out (may be NULL) receives the CtxIdx result it used */
+int32_t h264b_init_cabac(h264b_ctx *ctx, uint32_t flags, uint32_t n, const int64_t *bin_idx, const int64_t *max_prefix,
+                         const int64_t *off_prefix, const int64_t *pic_init_qp_minus26, const int64_t *slice_qp_delta,
+                         int32_t *p_state_idx, int32_t *val_mps, int64_t *ctx_idx_out);
+/* bin string of mb_type (sub_mb == 0) / sub_mb_type (sub_mb != 0): len[i] elements, element k in bit k of bits[i] */
+int32_t h264b_mb_bin_string(h264b_ctx *ctx, uint32_t n, const int32_t *slice_type_name, const int64_t *mb_type,
+                            const uint8_t *sub_mb, int32_t *len, uint32_t *bits);
+/* IsBinStringMatch(bits): 1 match, 0 no match, 2 the reference panics (more bits than the bin string holds after a
+ * matching prefix) */
+int32_t h264b_bin_string_match(h264b_ctx *ctx, uint32_t n, const int32_t *bin_len, const uint32_t *bin_bits,
+                               const int32_t *n_bits, const uint32_t *bits, int32_t *out);
+
 /* ------------------------------------------------------------------ whole front end of one stream
  * split + strip + (slice NALs of type 1 / 5) context init + CABAC bins, the slice data staying on the device
  * between the stages.  The CABAC data of a slice NAL starts at RBSP byte `slice_data_offset` (the reference's

@@ -1049,3 +1049,266 @@ panic:
     h->bits_read = b->bitsRead;
     return ORC_PANIC;
 }
+
+/* ================================================================================ syntax-element glue (rows I5 / f3)
+ * Literal restatements, TEST INFRASTRUCTURE: CtxIdx (cabac.go:557-758), NewBinarization (:340-427), initCabac
+ * (:148-174), binIdxMbMap / binIdxSubMbMap (:180-303), IsBinStringMatch (:429-436). */
+#define NA_CTX_ID 10000
+
+int64_t orc_ctx_idx(int64_t binIdx, int64_t maxBinIdxCtx, int64_t ctxIdxOffset) {
+    int64_t ctxIdx = NA_CTX_ID;
+    (void)maxBinIdxCtx;
+    switch (ctxIdxOffset) {
+        case 0:
+            if (binIdx != 0) return NA_CTX_ID;
+            break;
+        case 3:
+            switch (binIdx) {
+                case 0: break;
+                case 1: ctxIdx = 276; break;
+                case 2: ctxIdx = 3; break;
+                case 3: ctxIdx = 4; break;
+                case 4: break;
+                case 5: break;
+                default: ctxIdx = 7;
+            }
+            break;
+        case 11:
+            if (binIdx != 0) return NA_CTX_ID;
+            break;
+        case 14:
+            if (binIdx == 0) ctxIdx = 0;
+            if (binIdx == 1) ctxIdx = 1;
+            if (binIdx == 2) { /* 9.3.3.1.2 */ }
+            if (binIdx > 2) return NA_CTX_ID;
+            break;
+        case 17:
+            switch (binIdx) {
+                case 0: ctxIdx = 0; break;
+                case 1: ctxIdx = 276; break;
+                case 2: ctxIdx = 1; break;
+                case 3: ctxIdx = 2; break;
+                case 4: break;
+                default: ctxIdx = 3;
+            }
+            break;
+        case 21:
+            if (binIdx < 3) ctxIdx = binIdx;
+            else return NA_CTX_ID;
+            break;
+        case 24:
+            if (binIdx != 0) return NA_CTX_ID;
+            break;
+        case 27:
+            switch (binIdx) {
+                case 0: break;
+                case 1: ctxIdx = 3; break;
+                case 2: break;
+                default: ctxIdx = 5;
+            }
+            break;
+        case 32:
+            switch (binIdx) {
+                case 0: ctxIdx = 0; break;
+                case 1: ctxIdx = 276; break;
+                case 2: ctxIdx = 1; break;
+                case 3: ctxIdx = 2; break;
+                case 4: break;
+                default: ctxIdx = 3;
+            }
+            break;
+        case 36:
+            if (binIdx == 0 || binIdx == 1) ctxIdx = binIdx;
+            if (binIdx == 2) { /* 9.3.3.1.2 */ }
+            if (binIdx > 2 && binIdx < 6) ctxIdx = 3;
+            break;
+        case 40: /* fallthrough */
+        case 47:
+            switch (binIdx) {
+                case 0: break;
+                case 1: ctxIdx = 3; break;
+                case 2: ctxIdx = 4; break;
+                case 3: ctxIdx = 5; break;
+                default: ctxIdx = 6;
+            }
+            break;
+        case 54:
+            if (binIdx == 1) ctxIdx = 4;
+            if (binIdx > 1) ctxIdx = 5;
+            break;
+        case 60:
+            if (binIdx == 1) ctxIdx = 2;
+            if (binIdx > 1) ctxIdx = 3;
+            break;
+        case 64:
+            if (binIdx == 0) { /* 9.3.3.1.1.8 */
+            } else if (binIdx == 1 || binIdx == 2) {
+                ctxIdx = 3;
+            } else {
+                return NA_CTX_ID;
+            }
+            break;
+        case 68:
+            if (binIdx != 0) return NA_CTX_ID;
+            ctxIdx = 0;
+            break;
+        case 69:
+            if (binIdx >= 0 && binIdx < 3) ctxIdx = 0;
+            return NA_CTX_ID; /* :714-718: unconditional */
+        case 70:
+            if (binIdx != 0) return NA_CTX_ID;
+            break;
+        case 73:
+            switch (binIdx) {
+                case 0: case 1: case 2: case 3: break;
+                default: return NA_CTX_ID;
+            }
+            break;
+        case 77:
+            if (binIdx == 0) {
+            } else if (binIdx == 1) {
+            } else {
+                return NA_CTX_ID;
+            }
+            break;
+        case 276:
+            if (binIdx != 0) return NA_CTX_ID;
+            ctxIdx = 0;
+            break;
+        case 399:
+            if (binIdx != 0) return NA_CTX_ID;
+            break;
+    }
+    return ctxIdx;
+}
+
+/* NewBinarization(syntaxElement, data): se = index into the names below (anything else: no case), st = sliceTypeMap
+ * name index (0 P, 1 B, 2 I, 3 SP, 4 SI).  out[16]: SyntaxElement, PrefixSuffix, FixedLength, Unary, TruncatedUnary, CMax,
+ * UEGk, CMaxValue, MaxBinIdxCtx{IsPrefixSuffix, Prefix, Suffix}, CtxIdxOffset{IsPrefixSuffix, Prefix, Suffix},
+ * UseDecodeBypass, 0 */
+static const char *const se_names[] = {"CodedBlockPattern", "IntraChromaPredMode", "MbQpDelta", "MvdLnEnd0", "MvdLnEnd1",
+                                       "MbType", "MbFieldDecodingFlag", "PrevIntra4x4PredModeFlag",
+                                       "PrevIntra8x8PredModeFlag", "RefIdxL0", "RefIdxL1", "RemIntra4x4PredMode",
+                                       "RemIntra8x8PredMode", "TransformSize8x8Flag"};
+void orc_new_binarization(int32_t se, int32_t st, int32_t *out) {
+    enum { SE, PS, FL, UN, TU, CM, UEGK, CMV, MAX_PS, MAX_P, MAX_S, OFF_PS, OFF_P, OFF_S, BYP };
+    const char *name = (se >= 0 && se < 14) ? se_names[se] : "";
+    memset(out, 0, 16 * sizeof(int32_t));
+    out[SE] = se;
+#define IS(s) (strcmp(name, s) == 0)
+    if (IS("CodedBlockPattern")) {
+        out[PS] = 1;
+        out[MAX_PS] = 1, out[MAX_P] = 3, out[MAX_S] = 1;
+        out[OFF_PS] = 1, out[OFF_P] = 73, out[OFF_S] = 77;
+    } else if (IS("IntraChromaPredMode")) {
+        out[TU] = 1, out[CM] = 1, out[CMV] = 3;
+        out[MAX_P] = 1;
+        out[OFF_P] = 64;
+    } else if (IS("MbQpDelta")) {
+        out[MAX_P] = 2;
+        out[OFF_P] = 60;
+    } else if (IS("MvdLnEnd0") || IS("MvdLnEnd1")) {
+        out[BYP] = 1;
+        out[UEGK] = 1;
+        out[MAX_PS] = 1, out[MAX_P] = 4, out[MAX_S] = -1;
+        out[OFF_PS] = 1, out[OFF_P] = IS("MvdLnEnd0") ? 40 : 47, out[OFF_S] = -1;
+    } else if (IS("MbType")) {
+        if (st == 4) { /* SI */
+            out[PS] = 1;
+            out[MAX_PS] = 1, out[MAX_P] = 0, out[MAX_S] = 6;
+            out[OFF_PS] = 1, out[OFF_P] = 0, out[OFF_S] = 3;
+        } else if (st == 2) { /* I */
+            out[MAX_P] = 6;
+            out[OFF_P] = 3;
+        } else if (st == 3 || st == 0) { /* SP falls through to P */
+            out[PS] = 1;
+            out[MAX_PS] = 1, out[MAX_P] = 2, out[MAX_S] = 5;
+            out[OFF_PS] = 1, out[OFF_P] = 14, out[OFF_S] = 17;
+        }
+    } else if (IS("MbFieldDecodingFlag")) {
+        out[FL] = 1, out[CM] = 1, out[CMV] = 1;
+        out[OFF_P] = 70;
+    } else if (IS("PrevIntra4x4PredModeFlag") || IS("PrevIntra8x8PredModeFlag")) {
+        out[FL] = 1, out[CM] = 1, out[CMV] = 1;
+        out[OFF_P] = 68;
+    } else if (IS("RefIdxL0") || IS("RefIdxL1")) {
+        out[UN] = 1;
+        out[MAX_P] = 2;
+        out[OFF_P] = 54;
+    } else if (IS("RemIntra4x4PredMode") || IS("RemIntra8x8PredMode")) {
+        out[FL] = 1, out[CM] = 1, out[CMV] = 7;
+        out[OFF_P] = 69;
+    } else if (IS("TransformSize8x8Flag")) {
+        out[FL] = 1, out[CM] = 1, out[CMV] = 1;
+        out[OFF_P] = 399;
+    }
+#undef IS
+}
+
+/* initCabac: mn := MNVars[ctxIdx]; mn[0] -- the MNVars map only (keys 0..39), column cabac_init_idc 0 */
+void orc_init_cabac(uint32_t flags, int64_t binIdx, int64_t maxPrefix, int64_t offPrefix, int64_t picInitQpMinus26,
+                    int64_t sliceQpDelta, int64_t *pStateIdx, int64_t *valMPS, int64_t *ctxIdxOut) {
+    int64_t ctxIdx = orc_ctx_idx(binIdx, maxPrefix, offPrefix);
+    int64_t m = 0, n = 0;
+    if (ctxIdx >= 0 && ctxIdx <= 39) orc_mn(flags, ctxIdx, 0, &m, &n);
+    int64_t sliceQPy = (int64_t)((uint64_t)26 + (uint64_t)picInitQpMinus26 + (uint64_t)sliceQpDelta);
+    int64_t pre = orc_pre_ctx_state(m, n, sliceQPy);
+    if (pre <= 63) {
+        *pStateIdx = 63 - pre;
+        *valMPS = 0;
+    } else {
+        *pStateIdx = pre - 64;
+        *valMPS = 1;
+    }
+    if (ctxIdxOut) *ctxIdxOut = ctxIdx;
+}
+
+/* binIdxMbMap / binIdxSubMbMap, written out as in the reference; returns the length, bits[k] = element k */
+static const int8_t mb_I[26][8] = {
+    {1, 0}, {6, 1, 0, 0, 0, 0, 0}, {6, 1, 0, 0, 0, 0, 1}, {6, 1, 0, 0, 0, 1, 0}, {6, 1, 0, 0, 0, 1, 1},
+    {7, 1, 0, 0, 1, 0, 0, 0}, {7, 1, 0, 0, 1, 0, 0, 1}, {7, 1, 0, 0, 1, 0, 1, 0}, {7, 1, 0, 0, 1, 0, 1, 1},
+    {7, 1, 0, 0, 1, 1, 0, 0}, {7, 1, 0, 0, 1, 1, 0, 1}, {7, 1, 0, 0, 1, 1, 1, 0}, {7, 1, 0, 0, 1, 1, 1, 1},
+    {6, 1, 0, 1, 0, 0, 0}, {6, 1, 0, 1, 0, 0, 1}, {6, 1, 0, 1, 0, 1, 0}, {6, 1, 0, 1, 0, 1, 1},
+    {7, 1, 0, 1, 1, 0, 0, 0}, {7, 1, 0, 1, 1, 0, 0, 1}, {7, 1, 0, 1, 1, 0, 1, 0}, {7, 1, 0, 1, 1, 0, 1, 1},
+    {7, 1, 0, 1, 1, 1, 0, 0}, {7, 1, 0, 1, 1, 1, 0, 1}, {7, 1, 0, 1, 1, 1, 1, 0}, {7, 1, 0, 1, 1, 1, 1, 1},
+    {2, 1, 1}};
+int32_t orc_mb_bin_string(int32_t st, int64_t mbType, int32_t sub, int32_t *bits /* [8] */) {
+    memset(bits, 0, 8 * sizeof(int32_t));
+    if (sub) {
+        if (!(st == 0 || st == 3)) return 0;
+        switch (mbType) {
+            case 0: bits[0] = 1; return 1;
+            case 1: return 2;
+            case 2: bits[1] = 1, bits[2] = 1; return 3;
+            case 3: bits[1] = 1; return 3;
+        }
+        return 0;
+    }
+    if (st == 2) {
+        if (mbType < 0 || mbType > 25) return 0;
+        for (int k = 0; k < mb_I[mbType][0]; k++) bits[k] = mb_I[mbType][1 + k];
+        return mb_I[mbType][0];
+    }
+    if (st == 0 || st == 3) {
+        if (mbType < 0 || mbType > 30) return 0;
+        switch (mbType) {
+            case 0: return 3;
+            case 1: bits[1] = 1, bits[2] = 1; return 3;
+            case 2: bits[1] = 1; return 3;
+            case 3: bits[2] = 1; return 3;
+            case 4: return 0;
+        }
+        bits[0] = 1;
+        return 1;
+    }
+    return 0;
+}
+
+/* IsBinStringMatch: 1 / 0, ORC_HANG + 0 = 2 for the index-out-of-range panic */
+int32_t orc_bin_string_match(const int32_t *binString, int32_t len, const int32_t *bits, int32_t n) {
+    for (int32_t i = 0; i < n; i++) {
+        if (i >= len) return 2;
+        if (binString[i] != bits[i]) return 0;
+    }
+    return len == n;
+}

@@ -186,6 +186,15 @@ int orc_new_slice_header(const orc_sps *sps, const orc_pps *pps, int64_t nal_typ
 int orc_new_sps(const uint8_t *rbsp, int64_t len, orc_sps *out);                         /* sps.go:192-437 */
 int orc_new_pps(int64_t sps_chroma_format, const uint8_t *rbsp, int64_t len, orc_pps *out); /* pps.go:40-133 */
 
+/* ---- syntax-element glue (rows I5 / f3): CtxIdx cabac.go:557-758, NewBinarization :340-427, initCabac :148-174,
+ * binIdxMbMap / binIdxSubMbMap :180-303, IsBinStringMatch :429-436 */
+int64_t orc_ctx_idx(int64_t binIdx, int64_t maxBinIdxCtx, int64_t ctxIdxOffset);
+void orc_new_binarization(int32_t se, int32_t st, int32_t *out /* [16] */);
+void orc_init_cabac(uint32_t flags, int64_t binIdx, int64_t maxPrefix, int64_t offPrefix, int64_t picInitQpMinus26,
+                    int64_t sliceQpDelta, int64_t *pStateIdx, int64_t *valMPS, int64_t *ctxIdxOut);
+int32_t orc_mb_bin_string(int32_t st, int64_t mbType, int32_t sub, int32_t *bits /* [8] */);
+int32_t orc_bin_string_match(const int32_t *binString, int32_t len, const int32_t *bits, int32_t n);
+
 #ifdef __cplusplus
 }
 #endif

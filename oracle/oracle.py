@@ -392,3 +392,54 @@ def new_slice_header(sps_fields, pps_fields, nal_type, nal_ref_idc, rbsp):
     rc = L.orc_new_slice_header(C.byref(sps), C.byref(pps), int(nal_type), int(nal_ref_idc), d.ctypes.data, len(d),
                                 C.byref(h))
     return rc, {n: getattr(h, n) for n in _SLICE_HEADER_FIELDS}
+
+
+# ------------------------------------------------------------------ syntax-element glue (rows I5 / f3)
+NA_CTX_ID = 10000
+BINARIZATION_FIELDS = ["syntax_element", "prefix_suffix", "fixed_length", "unary", "truncated_unary", "cmax", "uegk",
+                       "cmax_value", "max_is_prefix_suffix", "max_prefix", "max_suffix", "off_is_prefix_suffix",
+                       "off_prefix", "off_suffix", "use_decode_bypass", "reserved"]
+
+
+def ctx_idx(bin_idx, max_bin_idx_ctx, ctx_idx_offset):
+    L = lib()
+    L.orc_ctx_idx.restype = C.c_int64
+    L.orc_ctx_idx.argtypes = [C.c_int64] * 3
+    return L.orc_ctx_idx(int(bin_idx), int(max_bin_idx_ctx), int(ctx_idx_offset))
+
+
+def new_binarization(se, st):
+    out = (C.c_int32 * 16)()
+    L = lib()
+    L.orc_new_binarization.restype = None
+    L.orc_new_binarization.argtypes = [C.c_int32, C.c_int32, C.c_void_p]
+    L.orc_new_binarization(int(se), int(st), out)
+    return dict(zip(BINARIZATION_FIELDS, list(out)))
+
+
+def init_cabac(bin_idx, max_prefix, off_prefix, pic_init_qp_minus26, slice_qp_delta, flags=0):
+    L = lib()
+    L.orc_init_cabac.restype = None
+    L.orc_init_cabac.argtypes = [C.c_uint32] + [C.c_int64] * 5 + [C.POINTER(C.c_int64)] * 3
+    p, v, c = C.c_int64(), C.c_int64(), C.c_int64()
+    L.orc_init_cabac(flags, int(bin_idx), int(max_prefix), int(off_prefix), int(pic_init_qp_minus26), int(slice_qp_delta),
+                     C.byref(p), C.byref(v), C.byref(c))
+    return p.value, v.value, c.value
+
+
+def mb_bin_string(st, mb_type, sub=False):
+    bits = (C.c_int32 * 8)()
+    L = lib()
+    L.orc_mb_bin_string.restype = C.c_int32
+    L.orc_mb_bin_string.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_void_p]
+    n = L.orc_mb_bin_string(int(st), int(mb_type), int(bool(sub)), bits)
+    return list(bits)[:n]
+
+
+def bin_string_match(bin_string, bits):
+    a = (C.c_int32 * max(len(bin_string), 1))(*bin_string)
+    b = (C.c_int32 * max(len(bits), 1))(*bits)
+    L = lib()
+    L.orc_bin_string_match.restype = C.c_int32
+    L.orc_bin_string_match.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+    return L.orc_bin_string_match(a, len(bin_string), b, len(bits))

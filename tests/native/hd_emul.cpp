@@ -10,6 +10,7 @@
 
 #include "../../h264decode_b200/csrc/annexb_local.cuh"
 #include "../../h264decode_b200/csrc/cabac_lane.cuh"
+#include "../../h264decode_b200/csrc/ctx_glue.cuh"
 #include "../../h264decode_b200/csrc/param_sets.cuh"
 #include "../../h264decode_b200/csrc/tables.inc"
 
@@ -370,6 +371,14 @@ void emul_parse_pps(const uint8_t *rbsp, uint64_t len, h264b_pps *out) {
     out->status = parse_pps(rbsp, len, out);
 }
 void emul_make_param_sets(const h264b_sps *s, const h264b_pps *p, h264b_param_sets *out) { *out = make_param_sets(*s, *p); }
+
+// the syntax-element glue as ctx_glue_kernel evaluates it
+int64_t emul_ctx_idx(int64_t bin_idx, int64_t max_bin_idx_ctx, int64_t off) { return ctx_idx_ref(bin_idx, max_bin_idx_ctx, off); }
+void emul_new_binarization(int32_t se, int32_t st, h264b_binarization *out) { *out = new_binarization_ref(se, st); }
+void emul_mb_bin_string(int32_t st, int64_t mb_type, int32_t sub, int32_t *len, uint32_t *bits) {
+    mb_bin_string_ref(st, mb_type, sub != 0, len, bits);
+}
+int32_t emul_bin_string_match(int32_t len, uint32_t bin, int32_t n, uint32_t bits) { return bin_string_match_ref(len, bin, n, bits); }
 
 // NewNalUnit on one frame with keep_byte_frame; returns rbsp length
 int64_t emul_frame(const uint8_t *f, int64_t N, uint8_t *rbsp) {

@@ -93,6 +93,18 @@ int main(int argc, char **argv) {
                     if (u.Type == 8) have_pps = false;
                 }
             }
+        } else if (mode == "glue") {  // CtxIdx / NewBinarization / InitCabac, one call each like the Go functions
+            for (int off : {3, 17, 21, 69, 276})
+                for (int b : {-1, 0, 1, 2, 5, 9}) printf("ctxidx %d %d %lld\n", b, off, (long long)h264::CtxIdx(b, 6, off));
+            for (int se = 0; se < 15; se++)
+                for (int st : {H264B_ST_P, H264B_ST_I, H264B_ST_SI, H264B_ST_B}) {
+                    const auto bz = h264::NewBinarization(se, st);
+                    const auto c = h264::InitCabac(bz, -3, 5);
+                    printf("bin %d %d %d %d %d %d %d %d\n", se, st, bz.prefix_suffix, bz.max_prefix, bz.off_prefix,
+                           bz.use_decode_bypass, c.PStateIdx, c.ValMPS);
+                }
+            const auto c = h264::InitCabac(h264::NewBinarization(H264B_SE_MB_TYPE, H264B_ST_P), 4, -9, 2);
+            printf("init %d %d\n", c.PStateIdx, c.ValMPS);
         } else if (mode == "ctx") {  // PreCtxState / MNVars / InitContexts
             for (int i = 2; i + 2 < argc; i += 3)
                 printf("pre %d\n", h264::PreCtxState(atoi(argv[i]), atoi(argv[i + 1]), atoi(argv[i + 2])));

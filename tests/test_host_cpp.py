@@ -219,3 +219,23 @@ def test_parameter_sets_and_slice_headers_like_handle_connection(exe, tmp_path):
                        if st == orc.OK else ["panic", str(t)])
     assert out == exp
     assert sum(l[0] == "slice" for l in out) >= 4 and ["panic", "8"] in out
+
+
+@pytest.mark.gpu
+def test_glue_functions_per_call(exe):
+    """h264::CtxIdx / NewBinarization / InitCabac, one call at a time like the Go functions they mirror"""
+    rc, out = run(exe, "glue")
+    assert rc == 0, out
+    it = iter(out)
+    for off in (3, 17, 21, 69, 276):
+        for b in (-1, 0, 1, 2, 5, 9):
+            assert next(it) == ["ctxidx", str(b), str(off), str(orc.ctx_idx(b, 6, off))]
+    for se in range(15):
+        for st in (0, 2, 4, 1):
+            bz = orc.new_binarization(se, st)
+            p, v, _ = orc.init_cabac(0, bz["max_prefix"], bz["off_prefix"], -3, 5)
+            assert next(it) == ["bin", str(se), str(st), str(bz["prefix_suffix"]), str(bz["max_prefix"]),
+                                str(bz["off_prefix"]), str(bz["use_decode_bypass"]), str(p), str(v)]
+    bz = orc.new_binarization(5, 0)
+    p, v, _ = orc.init_cabac(2, bz["max_prefix"], bz["off_prefix"], 4, -9)
+    assert next(it) == ["init", str(p), str(v)]
