@@ -112,3 +112,64 @@ def test_gpu_ctx_init_matches_fixture(ctx):
     g = load("ctx_init_sweep.npz")
     assert np.array_equal(ctx.ctx_init(g["qp"], g["idc"], 1024, 0), g["states_ref"])
     assert np.array_equal(ctx.ctx_init(g["qp"], g["idc"], 1024, 1), g["states_spec"])
+
+
+# ------------------------------------------------------------------------------------------------ rows S1 / f1 / f3 / f4 / I5
+def _records_equal(got, exp, dtype, what):
+    """field-wise comparison of two structured arrays where the reference did not panic (after a panic only `status` is
+    specified)"""
+    assert np.array_equal(got["status"], exp["status"]), what
+    ok = exp["status"] == 0
+    for name in dtype.names:
+        if name in ("status", "reserved"):
+            continue
+        assert np.array_equal(got[name][ok], exp[name][ok]), (what, name)
+
+
+def test_oracle_reproduces_param_set_and_glue_fixtures():
+    from oracle import oracle as orc
+    from h264decode_b200 import capi
+    g = load("param_sets_headers.npz")
+    for name, fn, mine, theirs in (("sps", orc.new_sps, capi.SPS_SCALARS, orc._SPS_SCALARS),
+                                   ("pps", orc.new_pps, capi.PPS_SCALARS, orc._PPS_SCALARS)):
+        for i in range(len(g[name])):
+            rb = g[name + "_data"][int(g[name + "_off"][i]):int(g[name + "_off"][i]) + int(g[name + "_len"][i])]
+            st, f = fn(rb)
+            assert st == g[name][i]["status"], (name, i)
+            if st == orc.OK:
+                assert [f[b] for a, b in zip(mine, theirs)] == [int(g[name][i][a]) for a, b in zip(mine, theirs)], (name, i)
+                assert f["bits_read"] == int(g[name][i]["bits_read"])
+    q = load("ctx_glue.npz")
+    assert [orc.ctx_idx(int(b), 7, int(o)) for b, o in zip(q["bin_idx"], q["offset"])] == list(q["ctx_idx"])
+    for i in range(len(q["se"])):
+        bz = orc.new_binarization(int(q["se"][i]), int(q["st"][i]))
+        assert [bz[k] for k in orc.BINARIZATION_FIELDS] == list(q["binarization"][i])
+    # a few values read by hand from the reference's tables
+    at = {(int(b), int(o)): int(c) for b, o, c in zip(q["bin_idx"], q["offset"], q["ctx_idx"])}
+    assert at[(1, 3)] == 276 and at[(6, 3)] == 7 and at[(2, 69)] == 10000 and at[(-2, 21)] == -2 and at[(3, 40)] == 5
+
+
+@pytest.mark.gpu
+def test_gpu_param_sets_headers_and_glue_match_fixtures(ctx):
+    from h264decode_b200 import capi
+    g = load("param_sets_headers.npz")
+    _records_equal(ctx.parse_sps(g["sps_data"], g["sps_off"], g["sps_len"]), g["sps"], capi.SPS_DTYPE, "sps")
+    _records_equal(ctx.parse_pps(g["pps_data"], g["pps_off"], g["pps_len"]), g["pps"], capi.PPS_DTYPE, "pps")
+    assert (g["sps"]["status"] == 0).sum() > 30 and (g["sps"]["status"] != 0).sum() > 10
+    hdr = g["hdr"]
+    got = np.zeros(len(hdr), capi.SLICE_HEADER_DTYPE)
+    for i in range(len(hdr)):   # every header has its own parameter sets: one call each
+        ps = capi.Context.param_sets(**dict(zip(capi.PARAM_SET_FIELDS, [int(x) for x in g["hdr_param_sets"][i]])))
+        got[i] = ctx.slice_headers(ps, g["hdr_data"], g["hdr_off"][i:i + 1], g["hdr_len"][i:i + 1], g["hdr_nal_type"][i:i + 1],
+                                   g["hdr_ref_idc"][i:i + 1])[0]
+    assert np.array_equal(got["status"], hdr["status"])
+    ok = hdr["status"] == 0
+    for name in capi.SLICE_HEADER_DTYPE.names:
+        if name not in ("status", "reserved"):
+            assert np.array_equal(got[name][ok], hdr[name][ok]), name
+    q = load("ctx_glue.npz")
+    assert np.array_equal(ctx.ctx_idx(q["bin_idx"], np.full(len(q["bin_idx"]), 7), q["offset"]), q["ctx_idx"])
+    bz = ctx.new_binarization(q["se"], q["st"])
+    assert np.array_equal(np.stack([bz[k] for k in capi.BINARIZATION_FIELDS], 1), q["binarization"])
+    ln, bits = ctx.mb_bin_string(q["mb_st"], q["mb_type"], q["mb_sub"])
+    assert np.array_equal(ln, q["mb_len"]) and np.array_equal(bits, q["mb_bits"])
