@@ -37,6 +37,7 @@ TRAFFIC_PER_ALG_BYTE = 1.0024
 TRAFFIC_SOURCE = "ncu dram__bytes_read.sum + dram__bytes_write.sum per pass (profiles/r1_ncu_launch_list_bench.csv)"
 MEAN_BINS = 455_000      # ~50 KB of CABAC data per slice at ~0.88 bit/bin
 N_ACTIVE = 64
+IN_FLIGHT = 3            # H264B_STREAM_JOBS_IN_FLIGHT
 N_CTX = 64
 SLICES_PER_FRAME = 8
 FRAMES_PER_PARAMS = 250
@@ -303,19 +304,21 @@ def run_gpu(args, rank, world, local_rank):
         h_stream = ctx.host_alloc(n)
         ctx.d2h(h_stream, d_stream.data_ptr())
         ctx.sync()
-        # warm-up: both job slots grow their pinned / device buffers
-        tk = [_stream_submit_raw(ctx, capi, h_stream, ops, n_ops, p, flags) for _ in range(2)]
+        # warm-up: every job slot grows its pinned / device buffers
+        tk = [_stream_submit_raw(ctx, capi, h_stream, ops, n_ops, p, flags) for _ in range(IN_FLIGHT)]
         for t in tk:
             r = _stream_wait_raw(ctx, capi, t)
         barrier()
-        # timed: every step copies its stream in and its results out; consecutive steps overlap (two jobs in flight:
+        # timed: every step copies its stream in and its results out; consecutive steps overlap (three jobs in flight:
         # H2D of step k+1 | kernels of step k | D2H of step k-1), which is how an ingest loop drives the library
         t0 = time.perf_counter()
-        pending = [_stream_submit_raw(ctx, capi, h_stream, ops, n_ops, p, flags)]
-        for k in range(1, e2e_steps):
+        pending = []
+        for k in range(e2e_steps):
+            if len(pending) == IN_FLIGHT:
+                r = _stream_wait_raw(ctx, capi, pending.pop(0))
             pending.append(_stream_submit_raw(ctx, capi, h_stream, ops, n_ops, p, flags))
+        while pending:
             r = _stream_wait_raw(ctx, capi, pending.pop(0))
-        r = _stream_wait_raw(ctx, capi, pending.pop(0))
         torch.cuda.synchronize()
         t_e2e = (time.perf_counter() - t0) / e2e_steps
         e2e_ok = r["n_slices"] == n_slices and r["total_bins"] == total_bins
@@ -369,7 +372,7 @@ def run_gpu(args, rank, world, local_rank):
             "e2e": {"value": (bins_all / t_e2e_max) if e2e_error is None else None, "error": e2e_error,
                     "unit": "bins/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": t_e2e_max * 1e3, "steps": e2e_steps,
-                    "api": "h264b_stream_submit / h264b_stream_wait, two jobs in flight (pinned host stream in; NAL index, "
+                    "api": "h264b_stream_submit / h264b_stream_wait, three jobs in flight (pinned host stream in; NAL index, "
                            "packed bins, final states out; copies of consecutive steps overlap kernels)"},
             "gpu_launches": int(launches), "clocks": clocks,
         }

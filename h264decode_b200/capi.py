@@ -553,7 +553,7 @@ class Context:
 
     def stream_submit(self, stream, ops, n_ops, qp, idc, n_ctx, slice_data_offset=0, flags=0, param_sets=None,
                       max_slices=None, max_sps=0, max_pps=0):
-        """asynchronous form: returns (ticket, keepalive); pass both to stream_wait.  Up to two jobs in flight.
+        """asynchronous form: returns (ticket, keepalive); pass both to stream_wait.  Up to three jobs in flight (H264B_STREAM_JOBS_IN_FLIGHT).
         param_sets (ParamSets): take SliceQPY / cabac_init_idc / the CABAC data offset from the slice headers
         (qp, idc may then be None; max_slices bounds the slice count)."""
         s = np.ascontiguousarray(stream, dtype=np.uint8)

@@ -103,7 +103,7 @@ int32_t h264b_create(int32_t device, h264b_ctx **out) {
     ctx->stream = ctx->own_stream;
     bool ok = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; i < 2 && ok; i++) {
+    for (int i = 0; i < kStreamSlots && ok; i++) {
         StreamSlot *sl = (StreamSlot *)calloc(1, sizeof(StreamSlot));
         ok = sl && cudaStreamCreateWithFlags(&sl->cs, cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreate(&sl->e_in) == cudaSuccess && cudaEventCreate(&sl->e_compute) == cudaSuccess &&
@@ -139,13 +139,13 @@ void h264b_destroy(h264b_ctx *ctx) {
         cudaFree(ctx->d_mn[v]);
         cudaFree(ctx->d_state_lut[v]);
     }
-    for (int b = 0; b < 3; b++) {
+    for (int b = 0; b < 1 + kStreamSlots; b++) {
         for (int i = 0; i < 20; i++) cudaFree(ctx->d_buf[b][i]);
         cudaFree(ctx->scan_scratch[b]);
     }
     for (int i = 0; i < 8; i++)
         if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kStreamSlots; i++) {
         StreamSlot *sl = ctx->slot[i];
         if (!sl) continue;
         for (int k = 0; k < kSlotDev; k++) cudaFree(sl->d[k]);
@@ -430,7 +430,7 @@ int32_t h264b_cabac_decode(h264b_ctx *ctx, const h264b_cabac_job *job) {
     return H264B_OK;
 }
 
-// ---- the whole front end of one stream, asynchronously: two jobs in flight per context -------------------------
+// ---- the whole front end of one stream, asynchronously: kStreamSlots jobs in flight per context -------------------------
 // device buffers of a slot: 0 stream  1 rbsp  2 nals  3 summary + slice count  4 off  5 len  6 slice_nal  7 ops
 //                           8 n_ops  9 qp  10 bins_off  11 bins  12 final  13 ext  14 slice headers
 // pinned buffers of a slot: 0 nals  1 bins_off  2 bins  3 final  4 slice_nal  5 summary + slice count
@@ -480,8 +480,8 @@ int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_
     // the job's kernels go to its slot's own stream and scratch bank (restored whatever happens)
     const cudaStream_t saved_stream = ctx->stream;
     const int saved_bank = ctx->bank;
-    ctx->stream = ctx->slot[ctx->next_ticket & 1]->cs;
-    ctx->bank = 1 + (int)(ctx->next_ticket & 1);
+    ctx->stream = ctx->slot[ctx->next_ticket % kStreamSlots]->cs;
+    ctx->bank = 1 + (int)(ctx->next_ticket % kStreamSlots);
     const int32_t rc = stream_submit_on_slot(ctx, job, ticket);
     ctx->stream = saved_stream;
     ctx->bank = saved_bank;
@@ -496,8 +496,9 @@ static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job
     if ((!j.stream && j.n) || (j.max_slices && ((!j.qp && !from_headers) || (!j.ops && j.n_ops_max))) ||
         (from_headers && !own_psets && !j.param_sets))
         return set_error(ctx, H264B_E_INVALID, "stream_submit: null pointer in job");
-    StreamSlot *sl = ctx->slot[ctx->next_ticket & 1];
-    if (sl->busy) return set_error(ctx, H264B_E_INVALID, "stream_submit: two jobs are in flight, wait for one first");
+    StreamSlot *sl = ctx->slot[ctx->next_ticket % kStreamSlots];
+    if (sl->busy)
+        return set_error(ctx, H264B_E_INVALID, "stream_submit: %d jobs are in flight, wait for one first", kStreamSlots);
     // the slot's previous results may still be on their way out: reuse its buffers only after that
     H264B_CUDA(ctx, cudaEventSynchronize(sl->e_out));
     const size_t ms = j.max_slices ? j.max_slices : 1;
@@ -674,7 +675,7 @@ static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job
 int32_t h264b_stream_wait(h264b_ctx *ctx, uint64_t ticket, h264b_stream_result *res) {
     CHECK_CTX(ctx);
     if (!res) return H264B_E_INVALID;
-    StreamSlot *sl = ctx->slot[ticket & 1];
+    StreamSlot *sl = ctx->slot[ticket % kStreamSlots];
     if (!sl->busy || sl->ticket != ticket) return set_error(ctx, H264B_E_INVALID, "stream_wait: unknown ticket");
     H264B_CUDA(ctx, cudaEventSynchronize(sl->e_out));
     sl->busy = false;

@@ -8,6 +8,9 @@
 #include "../../include/h264b200.h"
 
 struct StreamSlot;
+// Jobs in flight per context.  Three: in the steady state one job copies in, one runs its kernels and one copies out, so
+// the slowest of the three stages paces the pipeline (with two, H2D + kernels + D2H of one job span two periods).
+constexpr int kStreamSlots = 3;
 struct h264b_ctx {
     int device;
     int sm_count;
@@ -16,11 +19,11 @@ struct h264b_ctx {
     char err[512];
     uint64_t launches;
 
-    // grow-only device scratch, in three banks: [0] the direct ("_dev" and host-pointer) entry points, [1] and [2] the
-    // two stream-job slots, whose kernels run on their own streams and may overlap each other
+    // grow-only device scratch, in banks: [0] the direct ("_dev" and host-pointer) entry points, [1 + s] stream-job slot
+    // s, whose kernels run on their own stream and may overlap the other slots'
     int bank;
-    void *scan_scratch[3];
-    size_t scan_scratch_bytes[3];
+    void *scan_scratch[1 + kStreamSlots];
+    size_t scan_scratch_bytes[1 + kStreamSlots];
 
     // constant device tables, built once in h264b_create: [0] = REF, [1] = SPEC
     uint64_t *d_cabac_tab[2];   // 128 entries, see cabac_engine.cu
@@ -32,12 +35,12 @@ struct h264b_ctx {
     // host-level (pinned) staging, grow-only
     void *h_pin[8];
     size_t h_pin_bytes[8];
-    void *d_buf[3][20];
-    size_t d_buf_bytes[3][20];
+    void *d_buf[1 + kStreamSlots][20];
+    size_t d_buf_bytes[1 + kStreamSlots][20];
 
-    // h264b_stream_submit / h264b_stream_wait: two jobs in flight, each with its own buffers and events
+    // h264b_stream_submit / h264b_stream_wait: kStreamSlots jobs in flight, each with its own buffers, stream and events
     cudaStream_t s_in, s_out;  // copy streams (host -> device, device -> host)
-    struct StreamSlot *slot[2];
+    struct StreamSlot *slot[kStreamSlots];
     uint64_t next_ticket;
     cudaEvent_t t_ref;  // H264B_TRACE=1: time origin
     int trace;

@@ -433,12 +433,14 @@ typedef struct {
 
 int32_t h264b_stream_decode(h264b_ctx *ctx, const h264b_stream_job *job, h264b_stream_result *result);
 
-/* The same, asynchronously ("batch submit + wait"): up to two jobs in flight per context, so that the host -> device
+/* The same, asynchronously ("batch submit + wait"): up to H264B_STREAM_JOBS_IN_FLIGHT (3) jobs per context, each with
+ * its own buffers and compute stream, so that the host -> device
  * copy of job k+1, the kernels of job k and the device -> host copy of job k-1 overlap -- what an ingest loop that
  * batches NAL units into pinned buffers (the modified handleConnection, h264/server.go:113-166) needs.  The job's
  * host buffers must stay valid and unchanged until h264b_stream_wait returns for its ticket (they should be pinned:
- * h264b_host_alloc).  A result stays valid until the second-next submit on ctx.  h264b_stream_decode is
+ * h264b_host_alloc).  A result stays valid until H264B_STREAM_JOBS_IN_FLIGHT further submits on ctx.  h264b_stream_decode is
  * submit + wait. */
+#define H264B_STREAM_JOBS_IN_FLIGHT 3
 int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_t *ticket);
 int32_t h264b_stream_wait(h264b_ctx *ctx, uint64_t ticket, h264b_stream_result *result);
 

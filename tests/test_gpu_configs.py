@@ -40,7 +40,7 @@ def test_config2_ctx_init_sweep_one_million_slices():
 
 def test_config4_multi_camera_batch_rank_share():
     """configs[4], scaled to what one test can generate: many independent streams with skewed sizes, dealt to 8 ranks
-    by LPT; this GPU plays rank 0 and pushes its share through the asynchronous stream API (two jobs in flight).
+    by LPT; this GPU plays rank 0 and pushes its share through the asynchronous stream API (three jobs in flight).
     NAL / slice counts, bin totals and every decoded bin (vs what the test encoder coded) must match."""
     from h264decode_b200 import capi, sharding
     rng = np.random.default_rng(4096)
@@ -59,7 +59,7 @@ def test_config4_multi_camera_batch_rank_share():
                                       slices_per_frame=4, frames_per_params=2, id_base=100 * int(i)) for i in mine]
         pending, results = [], []
         for b in jobs:
-            if len(pending) == 2:
+            if len(pending) == 3:
                 results.append(ctx.stream_wait(*pending.pop(0)))
             pending.append(ctx.stream_submit(b["stream"], b["ops"], b["n_ops"], b["qp"], b["idc"], b["n_ctx"], flags=flags))
         while pending:

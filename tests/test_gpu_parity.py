@@ -404,12 +404,12 @@ def test_stream_decode_matches_oracle_pipeline(ctx, capi):
         assert np.array_equal(r["bins"][i][:nw], b["bins"][i, :nw])
 
 
-def test_stream_submit_wait_two_jobs_in_flight(ctx, capi):
-    """h264b_stream_submit / h264b_stream_wait: jobs overlap (two in flight), results stay per job and match the
-    oracle; a third submit without a wait is refused; max_slices larger than the slices the stream holds is fine"""
+def test_stream_submit_wait_jobs_in_flight(ctx, capi):
+    """h264b_stream_submit / h264b_stream_wait: jobs overlap (three in flight), results stay per job and match the
+    oracle; a fourth submit without a wait is refused; max_slices larger than the slices the stream holds is fine"""
     flags = capi.BYPASS_SPEC_OR | capi.CABAC_FINAL_TERMINATE
     jobs = [hz.build_stream_cabac(n, 1500 + 100 * k, n_active=64, n_ctx=64, slices_per_frame=4, frames_per_params=3,
-                                  id_base=7000 * k) for k, n in enumerate([40, 9, 64, 1, 33])]
+                                  id_base=7000 * k) for k, n in enumerate([40, 9, 64, 1, 33, 17])]
 
     def check(b, r):
         onal, orbsp = orc.read_nal_units_arrays(b["stream"])
@@ -431,15 +431,17 @@ def test_stream_submit_wait_two_jobs_in_flight(ctx, capi):
 
     t0 = submit(jobs[0])
     t1 = submit(jobs[1], extra=5)
-    with pytest.raises(capi.H264BError):
-        submit(jobs[2])
-    check(jobs[0], ctx.stream_wait(*t0))
     t2 = submit(jobs[2])
-    check(jobs[1], ctx.stream_wait(*t1))
+    with pytest.raises(capi.H264BError):
+        submit(jobs[3])
+    check(jobs[0], ctx.stream_wait(*t0))
     t3 = submit(jobs[3], extra=2)
-    check(jobs[2], ctx.stream_wait(*t2))
+    check(jobs[1], ctx.stream_wait(*t1))
     t4 = submit(jobs[4])
+    check(jobs[2], ctx.stream_wait(*t2))
+    t5 = submit(jobs[5])
     check(jobs[3], ctx.stream_wait(*t3))
     check(jobs[4], ctx.stream_wait(*t4))
+    check(jobs[5], ctx.stream_wait(*t5))
     with pytest.raises(capi.H264BError):
-        ctx.stream_wait(*t4)
+        ctx.stream_wait(*t5)
