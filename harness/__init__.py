@@ -237,11 +237,11 @@ def slice_bins_normal(n_slices, mean_bins, config, id_base=0, sigma_frac=0.2, lo
 
 
 def gpu_build_stream_cabac(torch, device, n_slices, mean_bins, config=4, n_active=64, n_ctx=64, slices_per_frame=8,
-                           frames_per_params=250, flags=0, id_base=0, want_bins=False):
+                           frames_per_params=250, flags=0, id_base=0, want_bins=False, n_bins=None):
     """C4-shaped stream generated on the GPU (torch tensors for memory only).  Returns dict with device tensors
     stream (uint8, padded), n (int), ops, n_ops, qp, idc (host numpy + device), bins (device or None), payload lens."""
     L = gpu_lib()
-    nb = slice_bins_normal(n_slices, mean_bins, config, id_base)
+    nb = slice_bins_normal(n_slices, mean_bins, config, id_base) if n_bins is None else np.asarray(n_bins, np.uint32)
     ops = gen_schedule(config, int(nb.max()), n_active)
     qp, idc = slice_params(n_slices, first=id_base)
     dev = torch.device(device)
