@@ -741,14 +741,70 @@ __device__ __forceinline__ void move_left(uint8_t *out, uint64_t ps, uint64_t le
 }
 
 constexpr int kFixWindow = 1024;  // parts staged at a time (2 MiB of a NAL)
+constexpr int kFixSub = 6;        // parts walked per step: their runs (<= kFixSub + 1, 12 KiB + edges) move together
+constexpr int kMoveBatch = 8;
+
+// The walk over a NAL's parts is serial bookkeeping: warp 0 does it, kFixSub parts at a time, and publishes the runs;
+// then the whole CTA moves them.  Short runs (an EPB-dense NAL has one per 2 KiB part) move together, 16 KiB of
+// destination per step: all sources of a batch are read before any of its destinations is written, and batches go left
+// to right, so a batch never reads what an earlier one wrote.  A long run (untouched parts that slide as one) moves on
+// its own in steps of 16 KiB (move_left).
+struct MoveBatch {
+    uint64_t d0[kMoveBatch], G[kMoveBatch], len[kMoveBatch];
+    int n;
+};
+constexpr uint64_t kLongRun = 8192;  // bytes
+
+__device__ __forceinline__ void move_short_runs(uint8_t *out, const MoveBatch *mb, int r0, int r1) {
+    // granule slots of runs r0 .. r1-1, dealt to the threads round-robin (at most kMoveGran per thread)
+    uint32_t y[kMoveGran][4];
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+#pragma unroll
+        for (int q = 0; q < kMoveGran; q++) {
+            uint32_t slot = (uint32_t)(q * 256 + (int)threadIdx.x);
+            int r = r0;
+            uint64_t d0 = 0, d1 = 0, g = 0;
+            for (; r < r1; r++) {
+                d0 = mb->d0[r];
+                d1 = d0 + mb->len[r];
+                g = ((d1 + 15) >> 4) - (d0 >> 4);
+                if (slot < g) break;
+                slot -= (uint32_t)g;
+            }
+            if (r == r1) continue;
+            const uint64_t G = mb->G[r];
+            const uint64_t D = (d0 & ~15ull) + (uint64_t)slot * 16u;
+            if (pass == 0) {
+                const uint64_t src = D + G;
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(out + (src & ~3ull));
+                const uint32_t sh = (uint32_t)(src & 3u) * 8u;
+                const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = sh ? wp[4] : 0u;
+                y[q][0] = __funnelshift_r(w0, w1, sh);
+                y[q][1] = __funnelshift_r(w1, w2, sh);
+                y[q][2] = __funnelshift_r(w2, w3, sh);
+                y[q][3] = __funnelshift_r(w3, w4, sh);
+            } else if (D >= d0 && D + 16 <= d1) {
+                *reinterpret_cast<uint4 *>(out + D) = make_uint4(y[q][0], y[q][1], y[q][2], y[q][3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    if (D + j >= d0 && D + j < d1) out[D + j] = (uint8_t)granule_byte(y[q], j);
+            }
+        }
+        __syncthreads();
+    }
+}
 
 __global__ void __launch_bounds__(256) nal_fixup_kernel(ScanArgs a, h264b_scan_summary *summary) {
     __shared__ uint32_t sh_tail[kFixWindow], sh_S[kFixWindow];
+    __shared__ MoveBatch mb;
     const uint32_t n_fix = a.hdr->n_fix;
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // totals of scan_finalize_kernel (complete: previous launch)
         summary->n_epb = a.hdr->n_epb;
         summary->rbsp_bytes = a.hdr->total_kept;  // RBSP bytes of all emitted NAL units
     }
+    const bool walker = threadIdx.x < 32;
     for (uint32_t f = blockIdx.x; f < n_fix; f += gridDim.x) {
         const uint64_t k = a.fix_list[f];
         const uint4 r0 = a.nal_rec[k], r1 = a.nal_rec[k + 1];
@@ -756,9 +812,17 @@ __global__ void __launch_bounds__(256) nal_fixup_kernel(ScanArgs a, h264b_scan_s
         const uint32_t H = nal_header_bytes(r0.z & 0xFFu, (r0.z >> 8) & 0xFFu);
         const uint64_t Tq = (st - 1) / kChunk, Tb = (next - 1) / kChunk;
         const uint32_t S_Tq = a.piece_S[Tq];
-        MoveRun run = {0, 0, 0};
-        const auto move = [&](uint64_t ps, uint64_t len, uint64_t G) { move_left(a.out, ps, len, G); };
-        for (uint64_t t0 = Tq + 1; t0 <= Tb; t0 += kFixWindow) {  // every thread walks the same parts (CTA-uniform)
+        MoveRun run = {0, 0, 0};  // (warp 0's)
+        int n = 0;
+        const auto publish = [&](uint64_t ps, uint64_t len, uint64_t G) {  // (n <= kFixSub + 1 <= kMoveBatch per step)
+            if (threadIdx.x == 0) {
+                mb.d0[n] = ps - G;
+                mb.G[n] = G;
+                mb.len[n] = len;
+            }
+            n++;
+        };
+        for (uint64_t t0 = Tq + 1; t0 <= Tb; t0 += kFixWindow) {
             const uint64_t t1 = t0 + kFixWindow <= Tb + 1 ? t0 + kFixWindow : Tb + 1;
             __syncthreads();
             for (uint64_t t = t0 + threadIdx.x; t < t1; t += 256) {
@@ -766,9 +830,34 @@ __global__ void __launch_bounds__(256) nal_fixup_kernel(ScanArgs a, h264b_scan_s
                 sh_S[t - t0] = a.piece_S[t];
             }
             __syncthreads();
-            nal_pieces_window(st, next, H, r1.w & 0xFFFFu, sh_tail, sh_S, t0, S_Tq, (uint64_t)kChunk, t0, t1, run, move);
+            for (uint64_t s0 = t0; s0 < t1; s0 += kFixSub) {
+                const uint64_t s1 = s0 + kFixSub < t1 ? s0 + kFixSub : t1;
+                if (walker) {
+                    n = 0;
+                    nal_pieces_window(st, next, H, r1.w & 0xFFFFu, sh_tail, sh_S, t0, S_Tq, (uint64_t)kChunk, s0, s1, run, publish);
+                    if (s1 == Tb + 1) nal_pieces_flush(run, publish);
+                    if (threadIdx.x == 0) mb.n = n;
+                }
+                __syncthreads();
+                const int nr = mb.n;
+                for (int a0 = 0; a0 < nr;) {  // groups in stream order: a long run alone, short runs together
+                    if (mb.len[a0] >= kLongRun) {
+                        move_left(a.out, mb.d0[a0] + mb.G[a0], mb.len[a0], mb.G[a0]);
+                        a0++;
+                        continue;
+                    }
+                    int a1 = a0;
+                    uint64_t bytes = 0;
+                    while (a1 < nr && mb.len[a1] < kLongRun && bytes + mb.len[a1] <= (uint64_t)kMoveGran * 256 * 16 - 16 * (kMoveBatch + 1)) {
+                        bytes += mb.len[a1];
+                        a1++;
+                    }
+                    move_short_runs(a.out, &mb, a0, a1);
+                    a0 = a1;
+                }
+                __syncthreads();
+            }
         }
-        nal_pieces_flush(run, move);
     }
 }
 
