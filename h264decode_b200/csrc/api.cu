@@ -490,7 +490,8 @@ int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_
 
 static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job, uint64_t *ticket) {
     const h264b_stream_job &j = *job;
-    const bool from_headers = (j.flags & H264B_STREAM_SLICE_HEADERS) != 0 && j.max_slices != 0;
+    // (H264B_STREAM_PARAM_SETS implies H264B_STREAM_SLICE_HEADERS)
+    const bool from_headers = (j.flags & (H264B_STREAM_SLICE_HEADERS | H264B_STREAM_PARAM_SETS)) != 0 && j.max_slices != 0;
     const bool own_psets = from_headers && (j.flags & H264B_STREAM_PARAM_SETS) != 0;
     const uint32_t max_sps = j.max_sps ? j.max_sps : 64u, max_pps = j.max_pps ? j.max_pps : 64u;
     if ((!j.stream && j.n) || (j.max_slices && ((!j.qp && !from_headers) || (!j.ops && j.n_ops_max))) ||
@@ -721,7 +722,7 @@ int32_t h264b_stream_wait(h264b_ctx *ctx, uint64_t ticket, h264b_stream_result *
     res->rbsp = (sl->job.flags & H264B_STREAM_WANT_RBSP) ? (const uint8_t *)sl->h[9] : nullptr;
     res->d_rbsp = (const uint8_t *)sl->d[1];
     res->ext = (sl->job.flags & H264B_STREAM_WANT_RBSP) ? (const h264b_nal_ext *)sl->h[10] : nullptr;
-    res->headers = ((sl->job.flags & H264B_STREAM_SLICE_HEADERS) && sl->job.max_slices)
+    res->headers = ((sl->job.flags & (H264B_STREAM_SLICE_HEADERS | H264B_STREAM_PARAM_SETS)) && sl->job.max_slices)
                        ? (const h264b_slice_header *)sl->h[11]
                        : nullptr;
     if (res->headers && (sl->job.flags & H264B_STREAM_PARAM_SETS)) {

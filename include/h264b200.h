@@ -50,7 +50,7 @@ extern "C" {
                                             ignored.  A slice whose header the reference cannot walk is not decoded
                                             (its final record carries H264B_F_OVERRUN). */
 
-#define H264B_STREAM_PARAM_SETS 0x20u   /* h264b_stream_* with H264B_STREAM_SLICE_HEADERS: the parameter sets come from
+#define H264B_STREAM_PARAM_SETS 0x20u   /* h264b_stream_* (implies H264B_STREAM_SLICE_HEADERS): the parameter sets come from
                                             the stream's own SPS / PPS NAL units, parsed on the device; a slice uses
                                             the last SPS before it and the last PPS after that SPS (handleConnection's
                                             VideoStreams bookkeeping, h264/server.go:147-162).  job.param_sets is

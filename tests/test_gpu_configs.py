@@ -81,3 +81,75 @@ def test_config4_multi_camera_batch_rank_share():
         assert np.array_equal(r["nals"]["rbsp_len"].astype(np.int64), onal["rbsp_len"])
     finally:
         ctx.close()
+
+
+def test_raw_stream_pipeline_at_scale():
+    """H264B_STREAM_PARAM_SETS on a configs[3]-shaped stream (8000 slice NAL units, SPS + PPS every 25 frames): parameter
+    sets, the sets each slice uses, every slice header (the payload bytes read as a header: arbitrary bits, so all three
+    outcomes of the reference's walk occur) and, for the slices whose header the reference can walk, the engine's final
+    state -- all against the oracle, through the asynchronous job API with three jobs in flight."""
+    from h264decode_b200 import capi
+    from tests.test_param_sets import compare_sps, compare_pps
+    from tests.test_slice_header import compare as compare_header
+    n_slices = 8000
+    b = hz.build_stream_cabac(n_slices, 600, config=3, n_active=64, n_ctx=64, slices_per_frame=8, frames_per_params=25,
+                              id_base=31)
+    stream = b["stream"]
+    flags = capi.BYPASS_SPEC_OR | capi.CABAC_FINAL_TERMINATE | capi.STREAM_PARAM_SETS
+    ctx = capi.Context(0)
+    try:
+        tks = [ctx.stream_submit(stream, b["ops"], b["n_ops"], None, None, 64, flags=flags, max_slices=n_slices + 5,
+                                 max_sps=64, max_pps=64) for _ in range(3)]
+        rs = [ctx.stream_wait(*t) for t in tks]
+    finally:
+        ctx.close()
+    onal, orbsp = orc.read_nal_units_arrays(stream)
+    rb_of = lambda k: orbsp[int(onal["rbsp_off"][k]):int(onal["rbsp_off"][k]) + int(onal["rbsp_len"][k])]  # noqa: E731
+    i_sps, i_pps = np.flatnonzero(onal["type"] == 7), np.flatnonzero(onal["type"] == 8)
+    sl = np.flatnonzero((onal["type"] == 1) | (onal["type"] == 5))
+    assert len(i_sps) == 40 and len(i_pps) == 40 and len(sl) == n_slices
+    sps_f = [orc.new_sps(rb_of(k)) for k in i_sps]
+    pps_f = [orc.new_pps(rb_of(k)) for k in i_pps]
+    term = np.array([orc.make_op(orc.OP_TERMINATE)], np.uint16)
+    for r in rs:
+        assert np.array_equal(r["sps_nal"], i_sps) and np.array_equal(r["pps_nal"], i_pps)
+        assert np.array_equal(r["slice_nal"], sl)
+    r = rs[2]
+    for j in range(40):
+        compare_sps(r["sps"][j], *sps_f[j], j)
+        compare_pps(r["pps"][j], *pps_f[j], j)
+    exp_sps = np.searchsorted(i_sps, sl) - 1
+    exp_pps = np.searchsorted(i_pps, sl) - 1
+    assert np.array_equal(r["slice_sps"], exp_sps) and np.array_equal(r["slice_pps"], exp_pps)
+    counts = {0: 0, 1: 0, 2: 0}
+    decoded = 0
+    for s, k in enumerate(sl):
+        rc, h = orc.new_slice_header(sps_f[exp_sps[s]][1], pps_f[exp_pps[s]][1], int(onal["type"][k]), int(onal["ref_idc"][k]),
+                                     rb_of(k))
+        hdr = r["headers"][s]
+        compare_header(hdr, int(hdr["status"]), rc, h, s)
+        counts[rc] += 1
+        if rc != orc.OK:
+            assert r["final"]["flags"][s] & capi.F_OVERRUN, s   # not decoded: no data
+            continue
+        if decoded < 150:   # the engine on what follows the "header": same op schedule, (SliceQPY, idc) from the header
+            t5 = h["SliceType"] % 5 if 0 <= h["SliceType"] <= 9 else -1
+            idc = -1 if t5 in (2, 4) else max(min(h["CabacInit"], 1000), -2)
+            qp = max(min(h["SliceQPy"], 1000000), -1000000)
+            init = orc.ctx_init(np.array([qp], np.int32), np.array([idc], np.int32), 64)[0]
+            skip = min((h["bits_read"] + 7) // 8, len(rb_of(k)))
+            rc2, bins, fin, _ = orc.cabac_decode_slice(rb_of(k)[skip:], np.concatenate([b["ops"][:b["n_ops"][s]], term]), init,
+                                                       orc.BYPASS_SPEC_OR)
+            if rc2 == orc.OK:
+                nw = (int(b["n_ops"][s]) + 1) // 32
+                assert np.array_equal(r["bins"][s][:nw], bins[:nw]), s
+                assert (r["final"]["cod_i_range"][s], r["final"]["cod_i_offset"][s], r["final"]["bits_read"][s]) == (
+                    fin["codIRange"], fin["codIOffset"], fin["bitsRead"]), s
+            else:
+                assert r["final"]["flags"][s] & capi.F_OVERRUN, s
+            decoded += 1
+    assert counts[0] > 100 and counts[1] + counts[2] > 10 and decoded == 150, counts
+    # the three jobs in flight saw the same stream: same results
+    for other in rs[:2]:
+        assert np.array_equal(other["headers"], r["headers"]) and np.array_equal(other["final"], r["final"])
+        assert np.array_equal(other["bins_flat"], r["bins_flat"])
