@@ -296,6 +296,49 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
         }
         if (!eng.lit) w.R = R22 >> 22, w.hi = hi, w.lo = lo, w.fbits = fbits;
     }
+    // ---- the same block structure for warps whose lanes are all on the literal engine (the reference's own bypass form,
+    // H264B_BYPASS_SPEC_OR clear): uniform op kinds by ballot, ops one block ahead, explicit shared addresses; the
+    // arithmetic is LiteralLane's (64-bit codIOffset, stream bits from its window).  A terminate bin of 1 does not end
+    // anything here: the literal engine simply goes on, like the reference.
+    if ((i & 31u) == 0u && __all_sync(0xFFFFFFFFu, eng.lit && i + 32u <= my_ops)) {  // (i: warp-uniform)
+        LiteralLane &l = eng.l;
+        const uint32_t st_lane = opaque(smem_addr(s_state) + (uint32_t)lane);
+        const uint32_t tab = opaque(smem_addr(s_tab));
+        uint32_t next_op = i + (uint32_t)lane < j.n_ops_max ? (uint32_t)j.ops[i + (uint32_t)lane] : 0u;
+        while (__all_sync(0xFFFFFFFFu, i + 32u <= my_ops)) {
+            const uint32_t my_op = next_op;
+            next_op = i + 32u + (uint32_t)lane < j.n_ops_max ? (uint32_t)j.ops[i + 32u + (uint32_t)lane] : 0u;
+            const uint32_t my_kind = my_op >> 14;
+            const uint32_t dec_mask = __ballot_sync(0xFFFFFFFFu, my_kind == H264B_OP_DECISION);
+            const uint32_t byp_mask = __ballot_sync(0xFFFFFFFFu, my_kind == H264B_OP_BYPASS);
+            uint32_t my_row = ((my_op & 0x3FFu) < n_ctx ? (my_op & 0x3FFu) : 0u) * 32u;
+#pragma unroll 1
+            for (uint32_t k8 = 0; k8 < 32u; k8 += 8u) {
+                const uint32_t dm = dec_mask >> k8, bm = byp_mask >> k8;
+                const uint32_t row8 = my_row;
+                my_row = __shfl_sync(0xFFFFFFFFu, my_row, (lane + 8) & 31);
+#pragma unroll
+                for (uint32_t u = 0; u < 8u; u++) {
+                    uint32_t bin;
+                    if (dm & (1u << u)) {
+                        const uint32_t addr = __shfl_sync(0xFFFFFFFFu, row8, (int)u) + st_lane;
+                        const uint2 e = lds_u32x2(tab + (lds_u8(addr) & 127u) * 8u);
+                        uint8_t ns;
+                        bin = l.decision(((uint64_t)e.y << 32) | e.x, &ns);
+                        sts_u8(addr, ns);
+                    } else if (bm & (1u << u)) {
+                        bin = l.bypass();
+                    } else {
+                        bin = l.terminate();
+                    }
+                    word = (word << 1) | bin;
+                }
+            }
+            i += 32u;
+            if (own) bins[(i >> 5) - 1u] = __brev(word);
+            word = 0;
+        }
+    }
     // ---- generic loop: lanes that have finished, lanes on the literal engine
     uint32_t next_op = i < warp_ops ? j.ops[i] : 0;
     for (; i < warp_ops; i++) {

@@ -161,34 +161,40 @@ struct CabacLane {
 struct LiteralLane {
     int64_t R, O;
     uint64_t bitpos;  // bits consumed from the slice start
-    const uint8_t *buf;
-    uint64_t total_bytes, off;
+    // the stream bits that follow, left-aligned in `win` (`avail` of them, <= 64), behind them the slice's bit feed
+    uint64_t win;
+    uint32_t avail;
+    BitFeed feed;
     bool spec_or;
 
-    H264B_HDM uint32_t read_bit() {
-        uint64_t byte = off + (bitpos >> 3);
-        if (byte >= total_bytes) byte = total_bytes ? total_bytes - 1 : 0;
-        const uint32_t b = (buf[byte] >> (7u - (uint32_t)(bitpos & 7u))) & 1u;
-        bitpos++;
-        return b;
+    // next k bits of the slice (k <= 32), MSB first; bytes past the buffer repeat its last word (don't-care: the slice
+    // is flagged H264B_F_OVERRUN long before)
+    H264B_HDM uint32_t read_bits(uint32_t k) {
+        if (avail < k) {  // avail < 32: room for 32 more
+            win |= (uint64_t)feed.get32() << (32u - avail);
+            avail += 32u;
+        }
+        const uint32_t v = k ? (uint32_t)(win >> (64u - k)) : 0u;
+        win = k ? win << k : win;
+        avail -= k;
+        bitpos += k;
+        return v;
     }
-    H264B_HDM void attach(const uint8_t *b, uint64_t total, uint64_t o, bool spec_or_bypass) {
-        buf = b;
-        total_bytes = total;
-        off = o;
-        spec_or = spec_or_bypass;
-    }
-    H264B_HDM void init() {  // initDecodingEngine, cabac.go:439-446
+    H264B_HDM void attach(const uint8_t *, uint64_t, uint64_t, bool spec_or_bypass) { spec_or = spec_or_bypass; }
+    H264B_HDM void init(const uint8_t *b, uint64_t total, uint64_t o) {  // initDecodingEngine, cabac.go:439-446
+        feed.init(b, total, o);
+        win = 0;
+        avail = 0;
         bitpos = 0;
         R = 510;
-        O = 0;
-        for (int i = 0; i < 9; i++) O = (O << 1) | (int64_t)read_bit();
+        O = (int64_t)read_bits(9);
     }
-    H264B_HDM void renorm() {  // RenormD, cabac.go:503-511
-        while (R < 256) {
-            R <<= 1;
-            O = (int64_t)(((uint64_t)O << 1) | (uint64_t)read_bit());
-        }
+    H264B_HDM void renorm() {  // RenormD, cabac.go:503-511: R doubles until >= 256, O takes one stream bit per step
+        // R is in [2, 510] whenever this runs (a range-table value or R minus one, R >= 256 before): at most 7 steps
+        uint32_t k = 0;
+        while (k < 9u && (R << k) < 256) k++;
+        R <<= k;
+        O = (int64_t)(((uint64_t)O << k) | (uint64_t)read_bits(k));
     }
     H264B_HDM uint32_t decision(uint64_t tab_entry, uint8_t *state_out) {
         const uint32_t tlo = (uint32_t)tab_entry, thi = (uint32_t)(tab_entry >> 32);
@@ -209,7 +215,7 @@ struct LiteralLane {
     }
     H264B_HDM uint32_t bypass() {  // cabac.go:468-481
         uint64_t o = (uint64_t)O << 1;
-        const uint32_t b = read_bit();
+        const uint32_t b = read_bits(1);
         o = spec_or ? (o | b) : (o << b);
         O = (int64_t)o;
         if (O >= R) {
@@ -232,17 +238,20 @@ struct LaneDecoder {
     LiteralLane l;
     bool lit;
 
-    H264B_HDM void to_literal() {
+    H264B_HDM void to_literal() {  // the window engine's look-ahead bits and bit feed go on where they are
         l.R = (int64_t)w.R;
         l.O = w.cod_i_offset();
         l.bitpos = w.bits_read();
+        l.win = ((((uint64_t)w.hi << 32) | w.lo) << 10);
+        l.avail = w.fbits > 0 ? (uint32_t)w.fbits : 0u;
+        l.feed = w.feed;
         lit = true;
     }
     H264B_HDM void init(const uint8_t *buf, uint64_t total_bytes, uint64_t off, bool spec_or_bypass) {
         l.attach(buf, total_bytes, off, spec_or_bypass);
         if (!spec_or_bypass) {
             lit = true;
-            l.init();
+            l.init(buf, total_bytes, off);
             return;
         }
         lit = false;
