@@ -66,7 +66,7 @@ class StreamJob(C.Structure):
     _fields_ = [("stream", C.c_void_p), ("n", C.c_uint64), ("slice_data_offset", C.c_uint32), ("n_ctx", C.c_uint32),
                 ("ops", C.c_void_p), ("n_ops_max", C.c_uint32), ("n_ops", C.c_void_p), ("qp", C.c_void_p),
                 ("max_slices", C.c_uint32), ("flags", C.c_uint32), ("param_sets", C.c_void_p),
-                ("max_sps", C.c_uint32), ("max_pps", C.c_uint32)]
+                ("max_sps", C.c_uint32), ("max_pps", C.c_uint32), ("initial_sps", C.c_void_p), ("initial_pps", C.c_void_p)]
 
 
 class StreamResult(C.Structure):
@@ -552,7 +552,7 @@ class Context:
                                                  d_nals, d_slice_nal, n_slices, d_out))
 
     def stream_submit(self, stream, ops, n_ops, qp, idc, n_ctx, slice_data_offset=0, flags=0, param_sets=None,
-                      max_slices=None, max_sps=0, max_pps=0):
+                      max_slices=None, max_sps=0, max_pps=0, initial_sps=None, initial_pps=None):
         """asynchronous form: returns (ticket, keepalive); pass both to stream_wait.  Up to three jobs in flight (H264B_STREAM_JOBS_IN_FLIGHT).
         param_sets (ParamSets): take SliceQPY / cabac_init_idc / the CABAC data offset from the slice headers
         (qp, idc may then be None; max_slices bounds the slice count)."""
@@ -575,9 +575,15 @@ class Context:
             j.flags |= STREAM_SLICE_HEADERS
         j.param_sets = C.addressof(param_sets) if param_sets is not None else None
         j.max_sps, j.max_pps = max_sps, max_pps
+        keep = []
+        for name, rec, dt in (("initial_sps", initial_sps, SPS_DTYPE), ("initial_pps", initial_pps, PPS_DTYPE)):
+            if rec is not None:   # the sets in force when the batch begins (one SPS_DTYPE / PPS_DTYPE record each)
+                a = np.ascontiguousarray(np.asarray(rec, dtype=dt).reshape(1))
+                keep.append(a)
+                setattr(j, name, a.ctypes.data)
         t = C.c_uint64()
         self._check(_lib.h264b_stream_submit(self.h, C.byref(j), C.byref(t)))
-        return t.value, (s, ops, p, nops, j, param_sets)
+        return t.value, (s, ops, p, nops, j, param_sets, keep)
 
     def stream_wait(self, ticket, keepalive=None):
         r = StreamResult()

@@ -549,7 +549,7 @@ static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job
     void *h_ops, *h_nops, *h_qp;
     RC(slot_pin(ctx, sl, 6, (size_t)j.n_ops_max * 2, &h_ops));
     RC(slot_pin(ctx, sl, 7, ms * 4, &h_nops));
-    RC(slot_pin(ctx, sl, 8, ms * sizeof(h264b_slice_qp), &h_qp));
+    RC(slot_pin(ctx, sl, 8, ms * sizeof(h264b_slice_qp) + sizeof(h264b_sps) + sizeof(h264b_pps), &h_qp));  // (+ initial sets)
     if (j.n_ops_max && j.max_slices) {
         memcpy(h_ops, j.ops, (size_t)j.n_ops_max * 2);
         H264B_CUDA(ctx, cudaMemcpyAsync(d_ops, h_ops, (size_t)j.n_ops_max * 2, cudaMemcpyHostToDevice, in));
@@ -585,8 +585,8 @@ static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job
         StreamParamSets sp;
         if (own_psets) {  // ... and the parameter sets from the stream's SPS / PPS NAL units
             RC(slot_dev(ctx, sl, 15, ((size_t)max_sps + max_pps + 4) * 4, &d_psl));
-            RC(slot_dev(ctx, sl, 16, (size_t)max_sps * sizeof(h264b_sps), &d_sps));
-            RC(slot_dev(ctx, sl, 17, (size_t)max_pps * sizeof(h264b_pps), &d_pps));
+            RC(slot_dev(ctx, sl, 16, ((size_t)max_sps + 1) * sizeof(h264b_sps), &d_sps));  // (+ 1: job.initial_sps)
+            RC(slot_dev(ctx, sl, 17, ((size_t)max_pps + 1) * sizeof(h264b_pps), &d_pps));
             RC(slot_dev(ctx, sl, 18, ms * 8, &d_sps_of));
             uint32_t *counts = (uint32_t *)d_psl, *sps_nal = counts + 4, *pps_nal = sps_nal + max_sps;
             RC(launch_pset_select(ctx, (const h264b_nal *)d_nals, (const h264b_scan_summary *)d_sum, cap, max_sps, max_pps,
@@ -602,6 +602,20 @@ static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job
             sp.counts = counts;
             sp.slice_sps = (int32_t *)d_sps_of;
             sp.slice_pps = sp.slice_sps + ms;
+            sp.initial_sps = nullptr;
+            sp.initial_pps = nullptr;
+            if (j.initial_sps) {  // the sets the batch inherits: staged through the slot's pinned memory
+                uint8_t *hp = (uint8_t *)h_qp + ms * sizeof(h264b_slice_qp);  // (behind the slot's qp staging area)
+                memcpy(hp, j.initial_sps, sizeof(h264b_sps));
+                H264B_CUDA(ctx, cudaMemcpyAsync((h264b_sps *)d_sps + max_sps, hp, sizeof(h264b_sps), cudaMemcpyHostToDevice, cs));
+                sp.initial_sps = (const h264b_sps *)d_sps + max_sps;
+                if (j.initial_pps) {
+                    memcpy(hp + sizeof(h264b_sps), j.initial_pps, sizeof(h264b_pps));
+                    H264B_CUDA(ctx, cudaMemcpyAsync((h264b_pps *)d_pps + max_pps, hp + sizeof(h264b_sps), sizeof(h264b_pps),
+                                                    cudaMemcpyHostToDevice, cs));
+                    sp.initial_pps = (const h264b_pps *)d_pps + max_pps;
+                }
+            }
         }
         RC(launch_stream_slice_headers(ctx, j.param_sets, (const uint8_t *)d_rbsp, j.n + 16, (const h264b_nal *)d_nals,
                                        (const uint32_t *)d_snal, d_ns, j.max_slices, (h264b_slice_header *)d_hdr,

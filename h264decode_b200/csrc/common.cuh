@@ -101,6 +101,8 @@ struct StreamParamSets {  // H264B_STREAM_PARAM_SETS: the stream's own parameter
     const h264b_pps *pps;
     const uint32_t *sps_nal, *pps_nal, *counts;
     int32_t *slice_sps, *slice_pps;
+    const h264b_sps *initial_sps;  // device copies of job.initial_sps / initial_pps, or NULL
+    const h264b_pps *initial_pps;
 };
 int launch_stream_slice_headers(h264b_ctx *ctx, const h264b_param_sets *params, const uint8_t *d_rbsp, uint64_t total,
                                 const h264b_nal *d_nals, const uint32_t *d_slice_nal, const uint32_t *d_n_slices,

@@ -23,7 +23,9 @@ struct SliceHeaderArgs {
     const h264b_pps *pps;
     const uint32_t *sps_nal, *pps_nal;  // their NAL ordinals, ascending
     const uint32_t *ps_counts;          // [0] SPS kept, [1] PPS kept
-    int32_t *slice_sps, *slice_pps;     // out: the sets slice s used (-1: none)
+    int32_t *slice_sps, *slice_pps;     // out: the sets slice s used (-1: none, -2: the initial set)
+    const h264b_sps *initial_sps;       // the sets in force when the batch begins (batched ingest), or NULL
+    const h264b_pps *initial_pps;
 };
 
 // index of the last entry below `key` in an ascending list, -1 if there is none
@@ -62,16 +64,29 @@ __global__ void __launch_bounds__(128) slice_header_kernel(SliceHeaderArgs a) {
         // uses the PPS stored there last, i.e. the last PPS behind that SPS.  No SPS: VideoStreams[-1] panics; no PPS:
         // NewSliceContext dereferences nil; a parameter set NewSPS / NewPPS panicked on never got that far.
         const uint32_t k = a.slice_nal[s];
-        const int32_t si = last_below(a.sps_nal, a.ps_counts[0], k);
+        int32_t si = last_below(a.sps_nal, a.ps_counts[0], k);
         int32_t pi = last_below(a.pps_nal, a.ps_counts[1], k);
-        if (si < 0 || pi < 0 || a.pps_nal[pi] < a.sps_nal[si]) pi = -1;
+        const h264b_sps *sps = nullptr;
+        const h264b_pps *pps = nullptr;
+        if (si >= 0) {  // a VideoStream of this batch: its PPS must come behind its SPS
+            sps = a.sps + si;
+            if (pi >= 0 && a.pps_nal[pi] > a.sps_nal[si]) pps = a.pps + pi;
+            else pi = -1;
+        } else if (a.initial_sps) {  // the VideoStream the batch inherited: a PPS of this batch replaces the inherited one
+            si = -2;
+            sps = a.initial_sps;
+            if (pi >= 0) pps = a.pps + pi;
+            else if (a.initial_pps) pps = a.initial_pps, pi = -2;
+        } else {
+            pi = -1;
+        }
         a.slice_sps[s] = si;
         a.slice_pps[s] = pi;
-        if (si < 0 || pi < 0 || a.sps[si].status != H264B_SH_OK || a.pps[pi].status != H264B_SH_OK) {
+        if (!sps || !pps || sps->status != H264B_SH_OK || pps->status != H264B_SH_OK) {
             h = h264b_slice_header{};
             h.status = H264B_SH_PANIC;
         } else {
-            parse_slice_header_record(make_param_sets(a.sps[si], a.pps[pi]), type, ref_idc, a.bytes + off, len, &h);
+            parse_slice_header_record(make_param_sets(*sps, *pps), type, ref_idc, a.bytes + off, len, &h);
         }
     } else {
         parse_slice_header_record(a.ps, type, ref_idc, a.bytes + off, len, &h);
@@ -129,6 +144,8 @@ int launch_stream_slice_headers(h264b_ctx *ctx, const h264b_param_sets *params, 
     a.ps_counts = sp ? sp->counts : nullptr;
     a.slice_sps = sp ? sp->slice_sps : nullptr;
     a.slice_pps = sp ? sp->slice_pps : nullptr;
+    a.initial_sps = sp ? sp->initial_sps : nullptr;
+    a.initial_pps = sp ? sp->initial_pps : nullptr;
     a.bytes = d_rbsp;
     a.total_bytes = total;
     a.off = nullptr;
@@ -181,6 +198,8 @@ extern "C" int32_t h264b_slice_headers_dev(h264b_ctx *ctx, const h264b_param_set
     a.pps = nullptr;
     a.sps_nal = a.pps_nal = a.ps_counts = nullptr;
     a.slice_sps = a.slice_pps = nullptr;
+    a.initial_sps = nullptr;
+    a.initial_pps = nullptr;
     return launch_slice_headers(ctx, a);
 }
 

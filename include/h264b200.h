@@ -405,6 +405,12 @@ typedef struct {
     uint32_t flags;
     const h264b_param_sets *param_sets; /* H264B_STREAM_SLICE_HEADERS: the active SPS / PPS fields (host pointer) */
     uint32_t max_sps, max_pps;    /* H264B_STREAM_PARAM_SETS: bounds on the SPS / PPS NAL units kept (0: 64 each) */
+    /* H264B_STREAM_PARAM_SETS, batched ingest: the parameter sets in force when this batch begins (host pointers or
+     * NULL), i.e. the last SPS of the batches before and the last PPS behind it.  Slices in front of the batch's first
+     * SPS use them (slice_sps / slice_pps then read -2); a PPS of this batch in front of its first SPS replaces
+     * initial_pps, as handleConnection stores it into the current VideoStream (h264/server.go:153-155). */
+    const h264b_sps *initial_sps;
+    const h264b_pps *initial_pps;
 } h264b_stream_job;
 
 typedef struct {
@@ -427,8 +433,8 @@ typedef struct {
     const h264b_pps *pps;           /* [n_pps] */
     const uint32_t *sps_nal;        /* [n_sps] index into nals */
     const uint32_t *pps_nal;        /* [n_pps] */
-    const int32_t *slice_sps;       /* [n_slices] index into sps of the slice's active SPS, -1: none */
-    const int32_t *slice_pps;       /* [n_slices] index into pps, -1: none after that SPS */
+    const int32_t *slice_sps;       /* [n_slices] index into sps of the slice's active SPS, -1: none, -2: job.initial_sps */
+    const int32_t *slice_pps;       /* [n_slices] index into pps, -1: none after that SPS, -2: job.initial_pps */
 } h264b_stream_result;
 
 int32_t h264b_stream_decode(h264b_ctx *ctx, const h264b_stream_job *job, h264b_stream_result *result);

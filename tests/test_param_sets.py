@@ -571,3 +571,75 @@ def test_c1_stream_parameter_sets_on_the_device():
     compare_sps(sps, *orc.new_sps(rb(k7[0])), "c1 sps")
     compare_pps(pps, *orc.new_pps(rb(k8[0])), "c1 pps")
     assert int(sps["profile"]) == 100 and int(sps["pic_width_in_mbs_minus1"]) == 119 and int(pps["pic_init_qp_minus26"]) == -3
+
+
+@pytest.mark.gpu
+def test_parameter_sets_carry_across_batches():
+    """Batched ingest: a stream cut at any NAL boundary into two jobs, the second one inheriting the sets in force
+    (job.initial_sps / initial_pps), yields the slice headers of the uncut stream -- including a PPS that arrives in the
+    second batch for an SPS of the first, and slices with no parameter sets at all.  (No CABAC ops: headers only.)"""
+    import harness as hz
+    from h264decode_b200 import capi
+    rng = np.random.default_rng(99)
+    SC = b"\x00\x00\x00\x01"
+    nal_list, ps = [], None
+    cur_sps = cur_pps = None
+    for ev in ["slice", "sps", "slice", "pps", "slice", "slice", "pps", "slice", "sps", "pps", "slice", "slice", "slice"]:
+        if ev == "sps":
+            while True:
+                rb, nb = write_sps(rng)
+                if nb is not None and orc.new_sps(np.frombuffer(rb, np.uint8))[0] == orc.OK:
+                    break
+            cur_sps, cur_pps = orc.new_sps(np.frombuffer(rb, np.uint8))[1], None
+            nal_list.append(b"\x67" + hz.escape(np.frombuffer(rb, np.uint8)).tobytes())
+        elif ev == "pps":
+            rb = write_pps(rng, entropy=1)[0]
+            esc = hz.escape(np.frombuffer(rb, np.uint8)).tobytes()
+            if cur_sps is not None:
+                cur_pps = orc.new_pps(np.frombuffer(_unescape(esc), np.uint8))[1]
+            nal_list.append(b"\x68" + esc)
+        else:
+            if cur_sps is not None and cur_pps is not None:
+                p = _ps_dict(cur_sps, cur_pps)
+                hb, _ = write_header(rng, p, 1, 2, int(rng.integers(0, 10)))
+            else:
+                hb = bytes(rng.integers(1, 255, 9).astype(np.uint8))
+            nal_list.append(b"\x41" + hz.escape(np.frombuffer(hb, np.uint8)).tobytes())
+    whole = np.frombuffer(b"".join(SC + x for x in nal_list) + SC, np.uint8)
+    empty_ops = np.zeros(0, np.uint16)
+    flags = capi.STREAM_PARAM_SETS
+
+    def run(ctx, stream, **kw):
+        return ctx.stream_wait(*ctx.stream_submit(stream, empty_ops, None, None, None, 64, flags=flags, max_slices=32,
+                                                  max_sps=8, max_pps=8, **kw))
+
+    ctx = capi.Context(0)
+    try:
+        ref = run(ctx, whole)
+        n_slices_all = len(ref["headers"])
+        assert n_slices_all == 8 and int(ref["headers"]["status"][0]) == capi.SH_PANIC
+        assert (ref["headers"]["status"] == capi.SH_OK).sum() >= 6
+        n_inherited = 0
+        for cut in range(1, len(nal_list)):
+            a = np.frombuffer(b"".join(SC + x for x in nal_list[:cut]) + SC, np.uint8)
+            b = np.frombuffer(b"".join(SC + x for x in nal_list[cut:]) + SC, np.uint8)
+            r1 = run(ctx, a)
+            init_sps = init_pps = None
+            if len(r1["sps"]):
+                init_sps = r1["sps"][-1].copy()
+                later = np.flatnonzero(r1["pps_nal"] > r1["sps_nal"][-1])
+                if len(later):
+                    init_pps = r1["pps"][later[-1]].copy()
+            r2 = run(ctx, b, initial_sps=init_sps, initial_pps=init_pps)
+            got = np.concatenate([r1["headers"], r2["headers"]])
+            assert len(got) == n_slices_all, cut
+            assert np.array_equal(got["status"], ref["headers"]["status"]), cut
+            ok = got["status"] == capi.SH_OK
+            for name in capi.SLICE_HEADER_DTYPE.names:
+                if name not in ("reserved",):
+                    assert np.array_equal(got[name][ok], ref["headers"][name][ok]), (cut, name)
+            n_inherited += int((r2["slice_sps"] == -2).sum())
+            assert np.all((r2["slice_pps"] != -2) | (r2["slice_sps"] == -2))
+        assert n_inherited > 10
+    finally:
+        ctx.close()
