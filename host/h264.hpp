@@ -154,6 +154,17 @@ inline std::vector<NalUnit> ReadNalUnits(const uint8_t *stream, size_t n, Device
 }
 
 // ------------------------------------------------------------------------------------------------ ingest
+using SPS = h264b_sps;  // (NewSPS / NewPPS further down)
+using PPS = h264b_pps;
+// What handleConnection does with each NAL unit (server.go:145-162), as callbacks: every unit, then by type NewSPS, NewPPS,
+// and the header part of NewSliceContext with the parameter sets in force.  A record whose status is H264B_SH_PANIC is
+// one the reference would have panicked on (its handleConnection recovers and exits, server.go:136-143).
+struct IngestHandlers {
+    std::function<void(const NalUnit &)> on_nal;
+    std::function<void(const SPS &)> on_sps;
+    std::function<void(const PPS &)> on_pps;
+    std::function<void(const NalUnit &, const h264b_slice_header &)> on_slice;
+};
 // The reference's handleConnection (server.go:113-166) appends one byte at a time to a growing []byte
 // (bit_reader.go:27-39) and re-tests isStartSequence after every byte.  Here the connection is read straight into
 // pinned, device-bound buffers; whole batches go through h264b_stream_submit / h264b_stream_wait with two batches in
@@ -171,6 +182,18 @@ class ByteStreamReader {
     }
     // Reads fd until end of file; on_nal is called for every NAL unit in stream order.  Returns the number of units.
     uint64_t Run(int fd, const std::function<void(const NalUnit &)> &on_nal) {
+        IngestHandlers h;
+        h.on_nal = on_nal;
+        return Run(fd, h);
+    }
+    // The same with handleConnection's dispatch: parameter sets and slice headers are parsed on the device in the same
+    // job as the split (H264B_STREAM_PARAM_SETS); the sets in force carry over from batch to batch.  max_slices bounds
+    // the slice NAL units of one batch.
+    uint64_t Run(int fd, const IngestHandlers &hd, uint32_t max_slices = 1u << 16) {
+        const bool dispatch = (bool)hd.on_sps || (bool)hd.on_pps || (bool)hd.on_slice;
+        bool have_sps = false, have_pps = false;
+        SPS cur_sps;
+        PPS cur_pps;
         uint64_t n_units = 0, consumed = 0;  // consumed: stream offset of the first byte of the pending batch's new data
         int cur = 0;
         bool eof = false, in_flight = false;
@@ -197,9 +220,38 @@ class ByteStreamReader {
             if (in_flight) {
                 h264b_stream_result res;
                 dev_.check(h264b_stream_wait(dev_.ctx(), ticket, &res));
+                uint32_t i_sps = 0, i_pps = 0, i_slice = 0;
                 for (uint64_t i = 0; i < res.scan.n_nals; i++) {
-                    on_nal(make_nal_unit(res.nals[i], res.ext ? &res.ext[i] : nullptr, res.rbsp, flight_base));
+                    const NalUnit u = make_nal_unit(res.nals[i], res.ext ? &res.ext[i] : nullptr, res.rbsp, flight_base);
+                    if (hd.on_nal) hd.on_nal(u);
                     n_units++;
+                    if (!dispatch) continue;
+                    if (u.Type == 7 && i_sps < res.n_sps) {
+                        if (hd.on_sps) hd.on_sps(res.sps[i_sps]);
+                        i_sps++;
+                    } else if (u.Type == 8 && i_pps < res.n_pps) {
+                        if (hd.on_pps) hd.on_pps(res.pps[i_pps]);
+                        i_pps++;
+                    } else if (u.Type == 1 || u.Type == 5) {
+                        if (i_slice >= res.n_slices)
+                            throw std::runtime_error("ByteStreamReader: more slice NAL units in a batch than max_slices");
+                        if (hd.on_slice) hd.on_slice(u, res.headers[i_slice]);
+                        i_slice++;
+                    }
+                }
+                if (dispatch && res.n_sps) {  // the sets in force behind this batch: its last SPS and the last PPS behind it
+                    cur_sps = res.sps[res.n_sps - 1];
+                    have_sps = true;
+                    have_pps = false;
+                    for (uint32_t q = res.n_pps; q-- > 0;)
+                        if (res.pps_nal[q] > res.sps_nal[res.n_sps - 1]) {
+                            cur_pps = res.pps[q];
+                            have_pps = true;
+                            break;
+                        }
+                } else if (dispatch && res.n_pps && have_sps) {  // a PPS for the VideoStream the batch inherited
+                    cur_pps = res.pps[res.n_pps - 1];
+                    have_pps = true;
                 }
                 // everything from the last start code on is carried over (none found: a start code may still straddle
                 // the batch boundary, keep the last 3 bytes)
@@ -227,6 +279,13 @@ class ByteStreamReader {
             job.stream = buf_[cur] + room_ - carry;
             job.n = carry + fill;
             job.flags = H264B_STREAM_WANT_RBSP;
+            if (dispatch) {  // (no CABAC ops: headers only)
+                job.flags |= H264B_STREAM_PARAM_SETS;
+                job.max_slices = max_slices;
+                job.n_ctx = 1;
+                job.initial_sps = have_sps ? &cur_sps : nullptr;
+                job.initial_pps = have_sps && have_pps ? &cur_pps : nullptr;
+            }
             dev_.check(h264b_stream_submit(dev_.ctx(), &job, &ticket));
             in_flight = true;
             flight_begin = room_ - carry;
@@ -401,8 +460,6 @@ inline std::vector<h264b_slice_header> SliceHeaders(const h264b_param_sets &ps, 
 // NewSPS(rbsp, showPacket) (sps.go:192) / NewPPS(sps, rbsp, showPacket) (pps.go:40): field extraction on the device, one
 // thread per parameter set.  A parameter set on which the reference would panic throws h264::Panic (the reference's
 // handleConnection recovers it and exits, server.go:136-143).  showPacket only controlled debug logging.
-using SPS = h264b_sps;
-using PPS = h264b_pps;
 inline SPS NewSPS(const std::vector<uint8_t> &rbsp, bool showPacket = false, Device &dev = Device::Default()) {
     (void)showPacket;
     std::vector<uint8_t> buf(rbsp);

@@ -93,6 +93,53 @@ int main(int argc, char **argv) {
                     if (u.Type == 8) have_pps = false;
                 }
             }
+        } else if (mode == "ingest_psets") {  // handleConnection's dispatch inside the batched ingest (sets carry over)
+            const auto s = slurp(argv[2]);
+            const size_t batch = strtoull(argv[3], nullptr, 10), chunk = strtoull(argv[4], nullptr, 10);
+            int fds[2];
+            if (pipe(fds)) return 3;
+            std::thread writer([&] {
+                size_t off = 0;
+                while (off < s.size()) {
+                    size_t n = chunk < s.size() - off ? chunk : s.size() - off;
+                    const ssize_t w = write(fds[1], s.data() + off, n);
+                    if (w <= 0) break;
+                    off += (size_t)w;
+                }
+                close(fds[1]);
+            });
+            h264::IngestHandlers hd;
+            hd.on_sps = [](const h264::SPS &sps) {
+                if (sps.status != H264B_SH_OK) {
+                    printf("panic 7\n");
+                    return;
+                }
+                printf("sps %lld %lld %lld %lld %lld %lld %llu\n", (long long)sps.profile, (long long)sps.level,
+                       (long long)sps.pic_width_in_mbs_minus1, (long long)sps.pic_height_in_map_units_minus1,
+                       (long long)sps.pic_order_count_type, (long long)sps.n_hrd, (unsigned long long)sps.bits_read);
+            };
+            hd.on_pps = [](const h264::PPS &pps) {
+                if (pps.status != H264B_SH_OK) {
+                    printf("panic 8\n");
+                    return;
+                }
+                printf("pps %lld %lld %lld %lld %lld %llu\n", (long long)pps.id, (long long)pps.entropy_coding_mode,
+                       (long long)pps.pic_init_qp_minus26, (long long)pps.chroma_qp_index_offset,
+                       (long long)pps.transform_8x8_mode, (unsigned long long)pps.bits_read);
+            };
+            hd.on_slice = [](const h264::NalUnit &u, const h264b_slice_header &h) {
+                if (h.status != H264B_SH_OK) {
+                    printf("panic %d\n", u.Type);
+                    return;
+                }
+                printf("slice %lld %lld %lld %llu\n", (long long)h.slice_type, (long long)h.slice_qp_y,
+                       (long long)h.cabac_init_idc, (unsigned long long)h.header_bits);
+            };
+            h264::ByteStreamReader reader(h264::Device::Default(), batch, 4096);
+            const uint64_t n = reader.Run(fds[0], hd, 64);
+            writer.join();
+            close(fds[0]);
+            printf("units %llu\n", (unsigned long long)n);
         } else if (mode == "glue") {  // CtxIdx / NewBinarization / InitCabac, one call each like the Go functions
             for (int off : {3, 17, 21, 69, 276})
                 for (int b : {-1, 0, 1, 2, 5, 9}) printf("ctxidx %d %d %lld\n", b, off, (long long)h264::CtxIdx(b, 6, off));

@@ -239,3 +239,57 @@ def test_glue_functions_per_call(exe):
     bz = orc.new_binarization(5, 0)
     p, v, _ = orc.init_cabac(2, bz["max_prefix"], bz["off_prefix"], 4, -9)
     assert next(it) == ["init", str(p), str(v)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch,chunk", [(1 << 20, 65536), (700, 97), (257, 31)])
+def test_batched_ingest_with_handle_connection_dispatch(exe, tmp_path, batch, chunk):
+    """ByteStreamReader::Run with IngestHandlers: NewSPS / NewPPS / slice headers come out of the same device job as the
+    split, and the parameter sets in force carry from batch to batch -- whatever the batch size, the lines are those of
+    one pass over the whole stream"""
+    from tests.test_param_sets import write_sps, write_pps, H, _unescape
+    from tests.test_slice_header import write_header, SPS_KEYS, PPS_KEYS
+    rng = np.random.default_rng(8)
+    SC = b"\x00\x00\x00\x01"
+    parts, exp = [], []
+    sps = pps = None
+    for ev in ["slice", "sps", "slice", "pps", "slice", "slice", "badpps", "slice", "pps", "slice", "sps", "pps"] + ["slice"] * 6:
+        if ev == "sps":
+            while True:
+                rb, nb = write_sps(rng)
+                st, f = orc.new_sps(np.frombuffer(rb, np.uint8))
+                if nb is not None and st == orc.OK:
+                    break
+            sps, pps = f, None
+            parts += [SC, b"\x67", hz.escape(np.frombuffer(rb, np.uint8)).tobytes()]
+            exp.append(["sps"] + [str(f[n]) for n in ("Profile", "Level", "PicWidthInMbsMinus1", "PicHeightInMapUnitsMinus1",
+                                                      "PicOrderCountType", "n_hrd", "bits_read")])
+        elif ev in ("pps", "badpps"):
+            rb = write_pps(rng, entropy=1)[0] if ev == "pps" else H("EE0F2CC0") + b"\x80"
+            esc = hz.escape(np.frombuffer(rb, np.uint8)).tobytes()
+            st, f = orc.new_pps(np.frombuffer(_unescape(esc), np.uint8))
+            pps = f if (st == orc.OK and sps is not None) else None
+            parts += [SC, b"\x68", esc]
+            exp.append(["pps"] + [str(f[n]) for n in ("ID", "EntropyCodingMode", "PicInitQpMinus26", "ChromaQpIndexOffset",
+                                                      "Transform8x8Mode", "bits_read")] if st == orc.OK else ["panic", "8"])
+        else:
+            if sps is not None and pps is not None:
+                ps = {k: sps[v] for k, v in SPS_KEYS.items()}
+                ps.update({k: pps[v] for k, v in PPS_KEYS.items()})
+                hb, _ = write_header(rng, ps, 1, 2, int(rng.integers(0, 10)))
+                esc = hz.escape(np.frombuffer(hb, np.uint8)).tobytes()
+                st, h = orc.new_slice_header(sps, pps, 1, 2, np.frombuffer(_unescape(esc), np.uint8))
+                exp.append(["slice", str(h["SliceType"]), str(h["SliceQPy"]), str(h["CabacInit"]), str(h["bits_read"])]
+                           if st == orc.OK else ["panic", "1"])
+            else:
+                esc = bytes(rng.integers(1, 255, 10).astype(np.uint8))
+                exp.append(["panic", "1"])
+            parts += [SC, b"\x41", esc]
+    stream = np.frombuffer(b"".join(parts) + SC, np.uint8)
+    path = os.path.join(str(tmp_path), "ingest_psets.bin")
+    stream.tofile(path)
+    rc, out = run(exe, "ingest_psets", path, batch, chunk)
+    assert rc == 0, out[-3:]
+    assert out[-1] == ["units", str(len(exp))]
+    assert out[:-1] == exp
+    assert sum(l[0] == "slice" for l in exp) >= 8
