@@ -297,7 +297,7 @@ def run_gpu(args, rank, world, local_rank):
     # ---- e2e through the host-buffer entry point
     del d_bins, d_rbsp
     torch.cuda.empty_cache()
-    e2e_steps = max(2, min(args.steps, 8))
+    e2e_steps = max(IN_FLIGHT, min(args.steps, 12))
     e2e_error = None
     t_e2e, e2e_ok, h_stream = 0.0, True, None
     try:
