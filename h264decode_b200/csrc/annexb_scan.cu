@@ -796,7 +796,7 @@ __device__ __forceinline__ void move_short_runs(uint8_t *out, const MoveBatch *m
     }
 }
 
-__global__ void __launch_bounds__(256) nal_fixup_kernel(ScanArgs a, h264b_scan_summary *summary) {
+__global__ void __launch_bounds__(256, 6) nal_fixup_kernel(ScanArgs a, h264b_scan_summary *summary) {
     __shared__ uint32_t sh_tail[kFixWindow], sh_S[kFixWindow];
     __shared__ MoveBatch mb;
     const uint32_t n_fix = a.hdr->n_fix;
@@ -805,7 +805,13 @@ __global__ void __launch_bounds__(256) nal_fixup_kernel(ScanArgs a, h264b_scan_s
         summary->rbsp_bytes = a.hdr->total_kept;  // RBSP bytes of all emitted NAL units
     }
     const bool walker = threadIdx.x < 32;
-    for (uint32_t f = blockIdx.x; f < n_fix; f += gridDim.x) {
+    __shared__ uint32_t sh_next;
+    for (;;) {  // NAL units are handed out first come first served (their sizes differ by orders of magnitude)
+        __syncthreads();
+        if (threadIdx.x == 0) sh_next = (uint32_t)atomicAdd(&a.hdr->reserved[0], 1ull);
+        __syncthreads();
+        const uint32_t f = sh_next;
+        if (f >= n_fix) break;
         const uint64_t k = a.fix_list[f];
         const uint4 r0 = a.nal_rec[k], r1 = a.nal_rec[k + 1];
         const uint64_t st = rec_start(r0), next = rec_start(r1);
@@ -1058,7 +1064,7 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     }
     scan_finalize_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a, d_nals, d_ext, d_summary);
     H264B_LAUNCH_CHECK(ctx, "scan_finalize_kernel");
-    nal_fixup_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(a, d_summary);
+    nal_fixup_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(a, d_summary);
     H264B_LAUNCH_CHECK(ctx, "nal_fixup_kernel");
     return H264B_OK;
 }
