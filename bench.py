@@ -38,6 +38,7 @@ TRAFFIC_SOURCE = "ncu dram__bytes_read.sum + dram__bytes_write.sum per pass (pro
 MEAN_BINS = 455_000      # ~50 KB of CABAC data per slice at ~0.88 bit/bin
 N_ACTIVE = 64
 IN_FLIGHT = 3            # H264B_STREAM_JOBS_IN_FLIGHT
+CABAC_WARP_INST_PER_OP = 30.2   # ncu: 34.4 G warp instructions / 1.137 G warp-ops (profiles/r1_ncu_cabac_v4_summary.txt)
 N_CTX = 64
 SLICES_PER_FRAME = 8
 FRAMES_PER_PARAMS = 250
@@ -201,6 +202,7 @@ def run_gpu(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     ctx = capi.Context(local_rank)
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     # a dedicated (non-default) stream: torch's events and the library's launches must be on the same one, and a NULL
     # handle would mean "the context's own stream" to h264b_set_stream
     stream = torch.cuda.Stream(device=dev)
@@ -368,7 +370,17 @@ def run_gpu(args, rank, world, local_rank):
                          "traffic_source": TRAFFIC_SOURCE, "peak_source": peak_src, "algorithmic_bytes": alg_bytes},
             "roofline_cabac": {"bound": "issue/latency (serial integer chain; not HBM, not tensor)",
                                "bins_per_s_per_gpu": total_bins / (t_cabac_ms * 1e-3),
-                               "lanes": n_slices, "hbm_gbs_implied": total_bins * 0.235 / (t_cabac_ms * 1e-3) / 1e9},
+                               "lanes": n_slices, "hbm_gbs_implied": total_bins * 0.235 / (t_cabac_ms * 1e-3) / 1e9,
+                               # issue model: warp instructions per op from ncu (smsp__inst_executed.sum / warp-ops,
+                               # profiles/r1_ncu_cabac_v4_summary.txt); one scheduler issues <= 1 per cycle and the
+                               # ALU pipe most of these instructions use takes 2 cycles per warp instruction
+                               "warp_inst_per_bin": CABAC_WARP_INST_PER_OP,
+                               "issue_ipc_per_scheduler": (total_bins / 32.0) * CABAC_WARP_INST_PER_OP / (
+                                   sm_count * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6 * t_cabac_ms * 1e-3),
+                               "alu_pipe_ipc_peak": 0.5,
+                               "equal_length_bins_per_s": 648e9,
+                               "note": "bounded by its longest bundle: 1.92 x mean ops x ~197 cycles for a warp on its own "
+                                       "(DESIGN.md section 4, K3; tools/cabac_balance_exp.py)"},
             "e2e": {"value": (bins_all / t_e2e_max) if e2e_error is None else None, "error": e2e_error,
                     "unit": "bins/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": t_e2e_max * 1e3, "steps": e2e_steps,
