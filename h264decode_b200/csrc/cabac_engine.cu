@@ -17,6 +17,9 @@
 
 namespace h264b {
 
+#ifndef H264B_CABAC_PIPELINE
+#define H264B_CABAC_PIPELINE 1  // fast loop: context state / table entry of a decision requested ahead of time
+#endif
 #ifndef H264B_CABAC_WARPS
 #define H264B_CABAC_WARPS 2
 #endif
@@ -43,6 +46,16 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 __device__ __forceinline__ uint32_t opaque(uint32_t x) {  // keeps an address in a register instead of re-deriving it
     asm volatile("mov.b32 %0, %0;" : "+r"(x));
     return x;
+}
+// table[state at addr], out of line on purpose: called only for a hazard (warp-uniform, rare).  Inlined, the two loads
+// would be predicated, and a predicated-off load still holds its scoreboard: the load latency would be back on the
+// common path.
+__device__ __noinline__ uint2 reload_entry(uint32_t addr, uint32_t tab) {
+    uint32_t st;
+    uint2 e;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(st) : "r"(addr) : "memory");
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(tab + st * 8u));
+    return e;
 }
 __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
@@ -213,6 +226,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
         uint32_t R22 = w.R << 22, hi = w.hi, lo = w.lo;
         int32_t fbits = w.fbits;
         bool left = false;
+#if H264B_CABAC_PIPELINE
+        uint2 e_cur = make_uint2(0u, 0u);  // table entry of the next decision (unless it is a hazard)
+        uint32_t s1 = 0;                   // state byte of the decision after that
+#endif
         // the ops of a block are loaded one block ahead (a global load per 32 ops that is never waited for)
         uint32_t next_op = i + (uint32_t)lane < j.n_ops_max ? (uint32_t)j.ops[i + (uint32_t)lane] : 0u;
         while (!left && __all_sync(0xFFFFFFFFu, i + 32u <= my_ops)) {
@@ -222,6 +239,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
             const uint32_t dec_mask = __ballot_sync(0xFFFFFFFFu, my_kind == H264B_OP_DECISION);
             const uint32_t byp_mask = __ballot_sync(0xFFFFFFFFu, my_kind == H264B_OP_BYPASS);
             uint32_t my_row = ((my_op & 0x3FFu) < n_ctx ? (my_op & 0x3FFu) : 0u) * 32u;  // as below: ctx 0
+#if H264B_CABAC_PIPELINE
+            // Loads ahead of the arithmetic: at a decision, the state byte of the second decision after it and the table
+            // entry of the next one are requested (the schedule is known, only the states are data).  A decision whose
+            // context was written by one of the two decisions before it, or that is among the first two of the block,
+            // loads in place instead (hazard ballot: a warp-uniform, rarely taken branch).
+            const uint32_t below = dec_mask & ((1u << lane) - 1u);
+            const uint32_t q1 = 31u - (uint32_t)__clz((int)(below | 1u));
+            const uint32_t below2 = below & ~(1u << q1);
+            const uint32_t q2 = 31u - (uint32_t)__clz((int)(below2 | 1u));
+            const uint32_t r1 = __shfl_sync(0xFFFFFFFFu, my_row, (int)q1), r2 = __shfl_sync(0xFFFFFFFFu, my_row, (int)q2);
+            const uint32_t haz_mask = __ballot_sync(0xFFFFFFFFu, below2 == 0u || my_row == r1 || my_row == r2);
+            const uint32_t above = dec_mask & ~((2u << lane) - 1u);
+            const uint32_t above2 = above & (above - 1u);
+            uint32_t my_nn = __shfl_sync(0xFFFFFFFFu, my_row, above2 ? __ffs((int)above2) - 1 : lane);
+            if (!above2) my_nn = 0u;  // (no second decision behind this op in the block: a harmless load of row 0)
+#endif
             uint32_t k = 0;
 #pragma unroll 1
             for (uint32_t k8 = 0; k8 < 32u && !left; k8 += 8u) {
@@ -230,6 +263,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
                 const uint32_t dm = dec_mask >> k8, bm = byp_mask >> k8;
                 const uint32_t row8 = my_row;
                 my_row = __shfl_sync(0xFFFFFFFFu, my_row, (lane + 8) & 31);
+#if H264B_CABAC_PIPELINE
+                const uint32_t hm = haz_mask >> k8, nn8 = my_nn;
+                my_nn = __shfl_sync(0xFFFFFFFFu, my_nn, (lane + 8) & 31);
+#endif
 #pragma unroll
                 for (uint32_t u = 0; u < 8u; u++) {
                     if ((u & 1u) == 0u) {
@@ -243,9 +280,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
                         }
                     }
                     if (dm & (1u << u)) {
+#if H264B_CABAC_PIPELINE
+                        const uint2 e_next = lds_u32x2(tab_fast + s1 * 8u);                           // next decision's entry
+                        const uint32_t s2 = lds_u8(__shfl_sync(0xFFFFFFFFu, nn8, (int)u) + st_lane);  // state of the one after
+                        const uint32_t addr = __shfl_sync(0xFFFFFFFFu, row8, (int)u) + st_lane;
+                        uint2 e = e_cur;
+                        if (hm & (1u << u)) e = reload_entry(addr, tab_fast);  // (a call: see reload_entry)
+                        e_cur = e_next;
+                        s1 = s2;
+#else
                         const uint32_t addr = __shfl_sync(0xFFFFFFFFu, row8, (int)u) + st_lane;
                         const uint32_t st = lds_u8(addr);
                         const uint2 e = lds_u32x2(tab_fast + st * 8u);
+#endif
                         const uint32_t lps22 = prmt(0u, e.x, R22 >> 28) << 22;  // rangeTabLPS[state][q] << 22
                         const uint32_t rm22 = R22 - lps22;
                         const bool is_lps = hi >= rm22;
