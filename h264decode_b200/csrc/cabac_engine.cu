@@ -47,16 +47,6 @@ __device__ __forceinline__ uint32_t opaque(uint32_t x) {  // keeps an address in
     asm volatile("mov.b32 %0, %0;" : "+r"(x));
     return x;
 }
-// table[state at addr], out of line on purpose: called only for a hazard (warp-uniform, rare).  Inlined, the two loads
-// would be predicated, and a predicated-off load still holds its scoreboard: the load latency would be back on the
-// common path.
-__device__ __noinline__ uint2 reload_entry(uint32_t addr, uint32_t tab) {
-    uint32_t st;
-    uint2 e;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(st) : "r"(addr) : "memory");
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(tab + st * 8u));
-    return e;
-}
 __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
@@ -227,7 +217,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
         int32_t fbits = w.fbits;
         bool left = false;
 #if H264B_CABAC_PIPELINE
-        uint2 e_cur = make_uint2(0u, 0u);  // table entry of the next decision (unless it is a hazard)
+        uint2 e_cur = make_uint2(0u, 0u);  // table entry of the next decision
         uint32_t s1 = 0;                   // state byte of the decision after that
 #endif
         // the ops of a block are loaded one block ahead (a global load per 32 ops that is never waited for)
@@ -240,20 +230,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
             const uint32_t byp_mask = __ballot_sync(0xFFFFFFFFu, my_kind == H264B_OP_BYPASS);
             uint32_t my_row = ((my_op & 0x3FFu) < n_ctx ? (my_op & 0x3FFu) : 0u) * 32u;  // as below: ctx 0
 #if H264B_CABAC_PIPELINE
-            // Loads ahead of the arithmetic: at a decision, the state byte of the second decision after it and the table
-            // entry of the next one are requested (the schedule is known, only the states are data).  A decision whose
-            // context was written by one of the two decisions before it, or that is among the first two of the block,
-            // loads in place instead (hazard ballot: a warp-uniform, rarely taken branch).
-            const uint32_t below = dec_mask & ((1u << lane) - 1u);
-            const uint32_t q1 = 31u - (uint32_t)__clz((int)(below | 1u));
-            const uint32_t below2 = below & ~(1u << q1);
-            const uint32_t q2 = 31u - (uint32_t)__clz((int)(below2 | 1u));
-            const uint32_t r1 = __shfl_sync(0xFFFFFFFFu, my_row, (int)q1), r2 = __shfl_sync(0xFFFFFFFFu, my_row, (int)q2);
-            const uint32_t haz_mask = __ballot_sync(0xFFFFFFFFu, below2 == 0u || my_row == r1 || my_row == r2);
+            // Loads ahead of the arithmetic (the schedule is known, only the states are data): a decision requests the
+            // state byte of the second decision after it and, once its own new state is known, the table entry of the
+            // next one.  The new state is forwarded into both when they use the same context (two ballots per block), so
+            // there is no hazard path and no branch; the pipeline restarts at every block.
             const uint32_t above = dec_mask & ~((2u << lane) - 1u);
             const uint32_t above2 = above & (above - 1u);
+            const uint32_t nrow1 = __shfl_sync(0xFFFFFFFFu, my_row, above ? __ffs((int)above) - 1 : lane);
             uint32_t my_nn = __shfl_sync(0xFFFFFFFFu, my_row, above2 ? __ffs((int)above2) - 1 : lane);
+            // the state a decision writes is forwarded to the loads already made for the next two decisions when they
+            // use the same context
+            const uint32_t fwd1_mask = __ballot_sync(0xFFFFFFFFu, above != 0u && nrow1 == my_row);
+            const uint32_t fwd2_mask = __ballot_sync(0xFFFFFFFFu, above2 != 0u && my_nn == my_row);
             if (!above2) my_nn = 0u;  // (no second decision behind this op in the block: a harmless load of row 0)
+            {   // the block's first two decisions: entry of the first, state of the second (once per block, in place)
+                const uint32_t rest = dec_mask & (dec_mask - 1u);
+                const uint32_t row_d0 = __shfl_sync(0xFFFFFFFFu, my_row, dec_mask ? __ffs((int)dec_mask) - 1 : 0);
+                const uint32_t row_d1 = __shfl_sync(0xFFFFFFFFu, my_row, rest ? __ffs((int)rest) - 1 : 0);
+                e_cur = lds_u32x2(tab_fast + lds_u8(row_d0 + st_lane) * 8u);
+                s1 = lds_u8(row_d1 + st_lane);
+            }
 #endif
             uint32_t k = 0;
 #pragma unroll 1
@@ -264,7 +260,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
                 const uint32_t row8 = my_row;
                 my_row = __shfl_sync(0xFFFFFFFFu, my_row, (lane + 8) & 31);
 #if H264B_CABAC_PIPELINE
-                const uint32_t hm = haz_mask >> k8, nn8 = my_nn;
+                const uint32_t f1m = fwd1_mask >> k8, f2m = fwd2_mask >> k8, nn8 = my_nn;
                 my_nn = __shfl_sync(0xFFFFFFFFu, my_nn, (lane + 8) & 31);
 #endif
 #pragma unroll
@@ -281,13 +277,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
                     }
                     if (dm & (1u << u)) {
 #if H264B_CABAC_PIPELINE
-                        const uint2 e_next = lds_u32x2(tab_fast + s1 * 8u);                           // next decision's entry
-                        const uint32_t s2 = lds_u8(__shfl_sync(0xFFFFFFFFu, nn8, (int)u) + st_lane);  // state of the one after
+                        const uint32_t s2 = lds_u8(__shfl_sync(0xFFFFFFFFu, nn8, (int)u) + st_lane);  // state of the one after next
                         const uint32_t addr = __shfl_sync(0xFFFFFFFFu, row8, (int)u) + st_lane;
-                        uint2 e = e_cur;
-                        if (hm & (1u << u)) e = reload_entry(addr, tab_fast);  // (a call: see reload_entry)
-                        e_cur = e_next;
-                        s1 = s2;
+                        const uint2 e = e_cur;
 #else
                         const uint32_t addr = __shfl_sync(0xFFFFFFFFu, row8, (int)u) + st_lane;
                         const uint32_t st = lds_u8(addr);
@@ -307,6 +299,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
                         lo <<= sh;
                         fbits -= (int32_t)sh;
                         word = __funnelshift_l(sel, word, 1);
+#if H264B_CABAC_PIPELINE
+                        const uint32_t st_new = sel & 0xFFu;
+                        e_cur = lds_u32x2(tab_fast + ((f1m & (1u << u)) ? st_new : s1) * 8u);  // next decision's entry
+                        s1 = (f2m & (1u << u)) ? st_new : s2;
+#endif
                     } else if (bm & (1u << u)) {
                         hi = __funnelshift_l(lo, hi, 1);
                         lo <<= 1;
