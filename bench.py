@@ -38,7 +38,7 @@ TRAFFIC_SOURCE = "ncu dram__bytes_read.sum + dram__bytes_write.sum per pass (pro
 MEAN_BINS = 455_000      # ~50 KB of CABAC data per slice at ~0.88 bit/bin
 N_ACTIVE = 64
 IN_FLIGHT = 3            # H264B_STREAM_JOBS_IN_FLIGHT
-CABAC_WARP_INST_PER_OP = 36.9   # ncu: 41.9 G warp instructions / 1.137 G warp-ops (profiles/r1_ncu_cabac_final_summary.txt)
+CABAC_WARP_INST_PER_OP = 37.0   # ncu: 42.1 G warp instructions / 1.137 G warp-ops (profiles/r1_ncu_cabac_final_summary.txt)
 N_CTX = 64
 SLICES_PER_FRAME = 8
 FRAMES_PER_PARAMS = 250
@@ -378,8 +378,8 @@ def run_gpu(args, rank, world, local_rank):
                                "issue_ipc_per_scheduler": (total_bins / 32.0) * CABAC_WARP_INST_PER_OP / (
                                    sm_count * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6 * t_cabac_ms * 1e-3),
                                "alu_pipe_ipc_peak": 0.5,
-                               "equal_length_bins_per_s": 648e9,
-                               "note": "bounded by its longest bundle: 1.92 x mean ops x ~197 cycles for a warp on its own "
+                               "equal_length_bins_per_s": 665e9,
+                               "note": "bounded by its longest bundle: 1.92 x mean ops x ~157 cycles for a warp on its own "
                                        "(DESIGN.md section 4, K3; tools/cabac_balance_exp.py)"},
             "e2e": {"value": (bins_all / t_e2e_max) if e2e_error is None else None, "error": e2e_error,
                     "unit": "bins/s", "h2d_bytes_per_step": h2d_bytes,
