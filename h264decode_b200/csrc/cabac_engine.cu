@@ -196,8 +196,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
     uint32_t i = 0;
     // ---- fast loop: blocks of 32 ops (one word of bins) while every lane of the warp is active and on the window
     // engine -- the usual case for all but the tail of a length bundle.  Same arithmetic as CabacLane::decision /
-    // bypass / terminate, arranged for the fewest issue slots per bin:
+    // bypass / terminate.  A warp's time is its serial chain codIRange / codIOffset -> next bin plus every taken branch
+    // (tens of cycles for a warp that has its scheduler to itself, as the long slices at the end of a launch do), so:
     //   * the op kinds of a block are two ballots, so every branch on them is warp-uniform (no convergence barriers);
+    //   * the context state and the table entry of a decision are requested ahead of the arithmetic, with the state a
+    //     decision writes forwarded into those requests when the contexts coincide (no hazard branch; see below);
     //   * shared memory is addressed with explicit 32-bit shared addresses (ld/st.shared), not generic pointers;
     //   * codIRange is kept as R << 22, aligned with codIOffset in the window: (R22 >> 28) is 4 + qCodIRangeIdx, which as
     //     a byte-permute selector picks rangeTabLPS[state][q] out of the table word directly; the renormalisation
