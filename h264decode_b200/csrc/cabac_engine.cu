@@ -303,9 +303,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
                         fbits -= (int32_t)sh;
                         word = __funnelshift_l(sel, word, 1);
 #if H264B_CABAC_PIPELINE
-                        const uint32_t st_new = sel & 0xFFu;
-                        e_cur = lds_u32x2(tab_fast + ((f1m & (1u << u)) ? st_new : s1) * 8u);  // next decision's entry
-                        s1 = (f2m & (1u << u)) ? st_new : s2;
+                        // forwarding as one bitwise select each: the masks are 0xFF or 0 (warp-uniform), states are bytes
+                        const uint32_t m1 = (0u - ((f1m >> u) & 1u)) & 0xFFu, m2 = (0u - ((f2m >> u) & 1u)) & 0xFFu;
+                        e_cur = lds_u32x2(tab_fast + ((sel & m1) | (s1 & ~m1)) * 8u);  // next decision's entry
+                        s1 = (sel & m2) | (s2 & ~m2);
 #endif
                     } else if (bm & (1u << u)) {
                         hi = __funnelshift_l(lo, hi, 1);
