@@ -177,7 +177,7 @@ def config_dict(args):
                         "payloads (shared op schedule, 64 active contexts), SPS+PPS every %d frames; split + EPB strip "
                         "+ CABAC bins; one stream per GPU" % (args.frames, SLICES_PER_FRAME, FRAMES_PER_PARAMS),
             "frames": args.frames, "slices_per_stream": args.frames * SLICES_PER_FRAME, "mean_bins_per_slice": MEAN_BINS,
-            "n_ctx": N_CTX, "bypass_form": "SPEC_OR", "tables": "REF",
+            "n_ctx": N_CTX, "bypass_form": os.environ.get("H264B_BENCH_BYPASS_FORM", "SPEC_OR"), "tables": "REF",
             "l2": "inputs (GBs per step) far exceed the 126 MB L2; no explicit flush needed",
             "parallelism": "stream-sharded, no collective"}
 
@@ -210,6 +210,8 @@ def run_gpu(args, rank, world, local_rank):
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     flags = capi.BYPASS_SPEC_OR | capi.CABAC_FINAL_TERMINATE
+    if os.environ.get("H264B_BENCH_BYPASS_FORM") == "REF_SHIFT":  # diagnostic: the literal int64 engine on the same input
+        flags = capi.CABAC_FINAL_TERMINATE
 
     # ---- synthetic input, generated on the GPU by the harness (outside every timed region)
     n_slices = args.frames * SLICES_PER_FRAME

@@ -348,10 +348,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
     // H264B_BYPASS_SPEC_OR clear): uniform op kinds by ballot, ops one block ahead, explicit shared addresses; the
     // arithmetic is LiteralLane's (64-bit codIOffset, stream bits from its window).  A terminate bin of 1 does not end
     // anything here: the literal engine simply goes on, like the reference.
-    if ((i & 31u) == 0u && __all_sync(0xFFFFFFFFu, eng.lit && i + 32u <= my_ops)) {  // (i: warp-uniform)
+    if (__all_sync(0xFFFFFFFFu, (i & 31u) == 0u && eng.lit && i + 32u <= my_ops)) {  // (i is warp-uniform; a vote says so)
         LiteralLane &l = eng.l;
         const uint32_t st_lane = opaque(smem_addr(s_state) + (uint32_t)lane);
-        const uint32_t tab = opaque(smem_addr(s_tab));
+        const uint32_t tab_fast = opaque(smem_addr(s_tab_fast));
         uint32_t next_op = i + (uint32_t)lane < j.n_ops_max ? (uint32_t)j.ops[i + (uint32_t)lane] : 0u;
         while (__all_sync(0xFFFFFFFFu, i + 32u <= my_ops)) {
             const uint32_t my_op = next_op;
@@ -360,26 +360,55 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
             const uint32_t dec_mask = __ballot_sync(0xFFFFFFFFu, my_kind == H264B_OP_DECISION);
             const uint32_t byp_mask = __ballot_sync(0xFFFFFFFFu, my_kind == H264B_OP_BYPASS);
             uint32_t my_row = ((my_op & 0x3FFu) < n_ctx ? (my_op & 0x3FFu) : 0u) * 32u;
+            // the same load pipeline as the window loop above: entry of the next decision and state of the one after it
+            // in flight, the state a decision writes forwarded into them where the contexts coincide
+            const uint32_t above = dec_mask & ~((2u << lane) - 1u);
+            const uint32_t above2 = above & (above - 1u);
+            const uint32_t nrow1 = __shfl_sync(0xFFFFFFFFu, my_row, above ? __ffs((int)above) - 1 : lane);
+            uint32_t my_nn = __shfl_sync(0xFFFFFFFFu, my_row, above2 ? __ffs((int)above2) - 1 : lane);
+            const uint32_t fwd1_mask = __ballot_sync(0xFFFFFFFFu, above != 0u && nrow1 == my_row);
+            const uint32_t fwd2_mask = __ballot_sync(0xFFFFFFFFu, above2 != 0u && my_nn == my_row);
+            if (!above2) my_nn = 0u;
+            uint2 e_cur;
+            uint32_t s1;
+            {
+                const uint32_t rest = dec_mask & (dec_mask - 1u);
+                const uint32_t row_d0 = __shfl_sync(0xFFFFFFFFu, my_row, dec_mask ? __ffs((int)dec_mask) - 1 : 0);
+                const uint32_t row_d1 = __shfl_sync(0xFFFFFFFFu, my_row, rest ? __ffs((int)rest) - 1 : 0);
+                e_cur = lds_u32x2(tab_fast + lds_u8(row_d0 + st_lane) * 8u);
+                s1 = lds_u8(row_d1 + st_lane);
+            }
 #pragma unroll 1
             for (uint32_t k8 = 0; k8 < 32u; k8 += 8u) {
                 const uint32_t dm = dec_mask >> k8, bm = byp_mask >> k8;
-                const uint32_t row8 = my_row;
+                const uint32_t f1m = fwd1_mask >> k8, f2m = fwd2_mask >> k8;
+                const uint32_t row8 = my_row, nn8 = my_nn;
                 my_row = __shfl_sync(0xFFFFFFFFu, my_row, (lane + 8) & 31);
+                my_nn = __shfl_sync(0xFFFFFFFFu, my_nn, (lane + 8) & 31);
 #pragma unroll
                 for (uint32_t u = 0; u < 8u; u++) {
-                    uint32_t bin;
                     if (dm & (1u << u)) {
+                        const uint32_t s2 = lds_u8(__shfl_sync(0xFFFFFFFFu, nn8, (int)u) + st_lane);
                         const uint32_t addr = __shfl_sync(0xFFFFFFFFu, row8, (int)u) + st_lane;
-                        const uint2 e = lds_u32x2(tab + (lds_u8(addr) & 127u) * 8u);
-                        uint8_t ns;
-                        bin = l.decision(((uint64_t)e.y << 32) | e.x, &ns);
-                        sts_u8(addr, ns);
+                        const uint2 e = e_cur;
+                        // LiteralLane::decision on the fast table's form (bin in bit 7 of the state bytes)
+                        const int64_t lps = (int64_t)prmt(e.x, 0u, 0x4440u | ((uint32_t)(l.R >> 6) & 3u));
+                        l.R -= lps;
+                        const bool is_lps = l.O >= l.R;
+                        l.O = is_lps ? (int64_t)((uint64_t)l.O - (uint64_t)l.R) : l.O;
+                        l.R = is_lps ? lps : l.R;
+                        const uint32_t sel = prmt(e.y, 0u, is_lps ? 0x3442u : 0x1440u);  // next state | bin << 31
+                        sts_u8(addr, sel);
+                        const uint32_t m1 = (0u - ((f1m >> u) & 1u)) & 0xFFu, m2 = (0u - ((f2m >> u) & 1u)) & 0xFFu;
+                        e_cur = lds_u32x2(tab_fast + ((sel & m1) | (s1 & ~m1)) * 8u);
+                        s1 = (sel & m2) | (s2 & ~m2);
+                        l.renorm();
+                        word = __funnelshift_l(sel, word, 1);
                     } else if (bm & (1u << u)) {
-                        bin = l.bypass();
+                        word = (word << 1) | l.bypass();
                     } else {
-                        bin = l.terminate();
+                        word = (word << 1) | l.terminate();
                     }
-                    word = (word << 1) | bin;
                 }
             }
             i += 32u;

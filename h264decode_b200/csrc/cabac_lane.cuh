@@ -190,10 +190,12 @@ struct LiteralLane {
         O = (int64_t)read_bits(9);
     }
     H264B_HDM void renorm() {  // RenormD, cabac.go:503-511: R doubles until >= 256, O takes one stream bit per step
-        // R is in [2, 510] whenever this runs (a range-table value or R minus one, R >= 256 before): at most 7 steps
-        uint32_t k = 0;
-        while (k < 9u && (R << k) < 256) k++;
-        R <<= k;
+        // k = the number of doublings: 0 for R >= 256, clz32(R) - 23 for R in [1, 255] (9 - bit length), and the cap of 9
+        // steps for R <= 0 (a state only stream garbage reaches; the reference would spin there).  No loop: a chain of
+        // compare-and-branch steps costs a lone warp tens of cycles each.
+        const uint32_t rc = R >= 256 ? 256u : (R <= 0 ? 0u : (uint32_t)R);  // clz32(256) = 23, clz32(0) = 32
+        const uint32_t k = clz32(rc) - 23u;
+        R = (int64_t)((uint64_t)R << k);
         O = (int64_t)(((uint64_t)O << k) | (uint64_t)read_bits(k));
     }
     H264B_HDM uint32_t decision(uint64_t tab_entry, uint8_t *state_out) {
