@@ -387,6 +387,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
                 my_nn = __shfl_sync(0xFFFFFFFFu, my_nn, (lane + 8) & 31);
 #pragma unroll
                 for (uint32_t u = 0; u < 8u; u++) {
+                    if ((u & 1u) == 0u) {  // two ops take at most 2 x 9 stream bits
+                        if (__any_sync(0xFFFFFFFFu, l.avail < 18u)) {
+                            __syncwarp();
+                            if (l.avail <= 32u) l.top_up();
+                        }
+                    }
                     if (dm & (1u << u)) {
                         const uint32_t s2 = lds_u8(__shfl_sync(0xFFFFFFFFu, nn8, (int)u) + st_lane);
                         const uint32_t addr = __shfl_sync(0xFFFFFFFFu, row8, (int)u) + st_lane;
@@ -402,12 +408,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
                         const uint32_t m1 = (0u - ((f1m >> u) & 1u)) & 0xFFu, m2 = (0u - ((f2m >> u) & 1u)) & 0xFFu;
                         e_cur = lds_u32x2(tab_fast + ((sel & m1) | (s1 & ~m1)) * 8u);
                         s1 = (sel & m2) | (s2 & ~m2);
-                        l.renorm();
+                        l.renorm<false>();
                         word = __funnelshift_l(sel, word, 1);
                     } else if (bm & (1u << u)) {
-                        word = (word << 1) | l.bypass();
+                        word = (word << 1) | l.bypass<false>();
                     } else {
-                        word = (word << 1) | l.terminate();
+                        word = (word << 1) | l.terminate<false>();
                     }
                 }
             }

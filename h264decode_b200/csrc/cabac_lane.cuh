@@ -169,11 +169,15 @@ struct LiteralLane {
 
     // next k bits of the slice (k <= 32), MSB first; bytes past the buffer repeat its last word (don't-care: the slice
     // is flagged H264B_F_OVERRUN long before)
+    // kRefill = false: the caller has made sure that avail >= k (cabac_decode_kernel's block loop tops the window up by
+    // a warp vote every two ops)
+    H264B_HDM void top_up() {  // avail <= 32: room for 32 more
+        win |= (uint64_t)feed.get32() << (32u - avail);
+        avail += 32u;
+    }
+    template <bool kRefill = true>
     H264B_HDM uint32_t read_bits(uint32_t k) {
-        if (avail < k) {  // avail < 32: room for 32 more
-            win |= (uint64_t)feed.get32() << (32u - avail);
-            avail += 32u;
-        }
+        if (kRefill && avail < k) top_up();
         const uint32_t v = k ? (uint32_t)(win >> (64u - k)) : 0u;
         win = k ? win << k : win;
         avail -= k;
@@ -189,6 +193,7 @@ struct LiteralLane {
         R = 510;
         O = (int64_t)read_bits(9);
     }
+    template <bool kRefill = true>
     H264B_HDM void renorm() {  // RenormD, cabac.go:503-511: R doubles until >= 256, O takes one stream bit per step
         // k = the number of doublings: 0 for R >= 256, clz32(R) - 23 for R in [1, 255] (9 - bit length), and the cap of 9
         // steps for R <= 0 (a state only stream garbage reaches; the reference would spin there).  No loop: a chain of
@@ -196,7 +201,7 @@ struct LiteralLane {
         const uint32_t rc = R >= 256 ? 256u : (R <= 0 ? 0u : (uint32_t)R);  // clz32(256) = 23, clz32(0) = 32
         const uint32_t k = clz32(rc) - 23u;
         R = (int64_t)((uint64_t)R << k);
-        O = (int64_t)(((uint64_t)O << k) | (uint64_t)read_bits(k));
+        O = (int64_t)(((uint64_t)O << k) | (uint64_t)read_bits<kRefill>(k));
     }
     H264B_HDM uint32_t decision(uint64_t tab_entry, uint8_t *state_out) {
         const uint32_t tlo = (uint32_t)tab_entry, thi = (uint32_t)(tab_entry >> 32);
@@ -215,9 +220,10 @@ struct LiteralLane {
         renorm();
         return (sel >> 8) & 1u;
     }
+    template <bool kRefill = true>
     H264B_HDM uint32_t bypass() {  // cabac.go:468-481
         uint64_t o = (uint64_t)O << 1;
-        const uint32_t b = read_bits(1);
+        const uint32_t b = read_bits<kRefill>(1);
         o = spec_or ? (o | b) : (o << b);
         O = (int64_t)o;
         if (O >= R) {
@@ -226,10 +232,11 @@ struct LiteralLane {
         }
         return 0u;
     }
+    template <bool kRefill = true>
     H264B_HDM uint32_t terminate() {  // cabac.go:486-499
         R -= 2;
         if (O >= R) return 1u;
-        renorm();
+        renorm<kRefill>();
         return 0u;
     }
 };
