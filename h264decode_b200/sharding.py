@@ -25,6 +25,42 @@ def lpt_assign(sizes, n_ranks):
     return [np.array(sorted(x), dtype=np.int64) for x in out]
 
 
+START_CODE = b"\x00\x00\x00\x01"
+
+
+def cut_byte_ranges(stream, n_shards):
+    """One long Annex-B stream cut into n_shards byte ranges that can be scanned independently ("a
+    single long stream may instead be cut into byte ranges").  Every cut is moved forward from its nominal position
+    k * len / n_shards to the next start code 00 00 00 01 (server.go:19, :28-39: the only boundary the reference
+    knows), and a range keeps the 4 bytes of the start code that opens the next one, because the reference's NAL is
+    "payload plus the following start code" (server.go:64-111) and K start codes yield K - 1 NAL units.  The pattern
+    cannot overlap itself, so the NAL units of range r are exactly those of the whole stream whose start code lies in
+    [cut_r, cut_{r+1}); positions in a range's results are relative to its begin.  Ranges can be empty (fewer NAL
+    units than shards).  Only the bytes between a nominal cut and the next start code are looked at: O(n_shards x NAL
+    size) host work, no pass over the stream.
+
+    -> list of (begin, end) with stream[begin:end] the input of shard r; deterministic, identical on every rank."""
+    buf = stream if isinstance(stream, (bytes, bytearray, memoryview)) else memoryview(np.ascontiguousarray(stream, np.uint8))
+    buf = bytes(buf) if isinstance(buf, bytearray) else buf
+    n = len(buf)
+    find = buf.find if isinstance(buf, bytes) else None
+    cuts = [0]
+    for k in range(1, n_shards):
+        nominal = max(cuts[-1], (k * n) // n_shards)
+        lo = max(nominal - 3, cuts[-1])  # a start code that straddles the nominal cut belongs to this shard
+        if find is not None:
+            p = find(START_CODE, lo)
+        else:  # memoryview over a numpy array: search window by window without copying the stream
+            p, w = -1, lo
+            while w < n and p < 0:
+                q = bytes(buf[w:w + (1 << 20) + 3]).find(START_CODE)
+                p = w + q if q >= 0 else -1
+                w += 1 << 20
+        cuts.append(n if p < 0 else p)
+    cuts.append(n)
+    return [(cuts[r], min(n, cuts[r + 1] + 4) if r + 1 < n_shards else n) for r in range(n_shards)]
+
+
 def my_share(sizes, rank, world):
     return lpt_assign(sizes, world)[rank]
 

@@ -227,6 +227,29 @@ def test_scan_large_properties(ctx, capi):
     assert summ["n_epb"] > 0
 
 
+def test_scan_byte_ranges_of_one_stream(ctx, capi):
+    """§8e: one stream cut at start codes into byte ranges (h264decode_b200/sharding.py), each range scanned on its own
+    through the C ABI: the concatenation is the whole stream's scan, NAL by NAL, RBSP byte by byte"""
+    from h264decode_b200 import sharding
+    s = np.ascontiguousarray(hz.build_stream_c1(1 << 20), np.uint8)
+    _, wn, wx, wr = ctx.annexb_scan(s)
+    wn, wr = wn.copy(), wr.copy()
+    for n_shards in (2, 8, 5):
+        ranges = sharding.cut_byte_ranges(s, n_shards)
+        k = 0
+        for b, e in ranges:
+            _, nals, _, rbsp = ctx.annexb_scan(s[b:e])
+            for j in range(len(nals)):
+                assert int(nals["start"][j]) + b == int(wn["start"][k])
+                for f in ("num_bytes", "type", "ref_idc", "header_bytes", "rbsp_len"):
+                    assert nals[f][j] == wn[f][k]
+                assert np.array_equal(rbsp[nals["rbsp_off"][j]:nals["rbsp_off"][j] + nals["rbsp_len"][j]],
+                                      wr[wn["rbsp_off"][k]:wn["rbsp_off"][k] + wn["rbsp_len"][k]])
+                k += 1
+        assert k == len(wn)
+        assert max(e - b for b, e in ranges) < len(s) // n_shards + (1 << 17)   # balanced up to one NAL
+
+
 # =========================================================================================== NewNalUnit (frames)
 def test_nal_units_frames(ctx, capi):
     from tests.test_hd_logic import random_stream
