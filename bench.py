@@ -38,7 +38,7 @@ TRAFFIC_SOURCE = "ncu dram__bytes_read.sum + dram__bytes_write.sum per pass (pro
 MEAN_BINS = 455_000      # ~50 KB of CABAC data per slice at ~0.88 bit/bin
 N_ACTIVE = 64
 IN_FLIGHT = 3            # H264B_STREAM_JOBS_IN_FLIGHT
-CABAC_WARP_INST_PER_OP = 37.0   # ncu: 42.1 G warp instructions / 1.137 G warp-ops (profiles/r1_ncu_cabac_final_summary.txt)
+CABAC_WARP_INST_PER_OP = 38.9   # ncu: 44.26 G warp instructions / 1.137 G warp-ops (profiles/r1_ncu_cabac_final2_summary.txt)
 N_CTX = 64
 SLICES_PER_FRAME = 8
 FRAMES_PER_PARAMS = 250
@@ -374,7 +374,7 @@ def run_gpu(args, rank, world, local_rank):
                                "bins_per_s_per_gpu": total_bins / (t_cabac_ms * 1e-3),
                                "lanes": n_slices, "hbm_gbs_implied": total_bins * 0.235 / (t_cabac_ms * 1e-3) / 1e9,
                                # issue model: warp instructions per op from ncu (smsp__inst_executed.sum / warp-ops,
-                               # profiles/r1_ncu_cabac_final_summary.txt); one scheduler issues <= 1 per cycle and the
+                               # profiles/r1_ncu_cabac_final2_summary.txt); one scheduler issues <= 1 per cycle and the
                                # ALU pipe most of these instructions use takes 2 cycles per warp instruction
                                "warp_inst_per_bin": CABAC_WARP_INST_PER_OP,
                                "issue_ipc_per_scheduler": (total_bins / 32.0) * CABAC_WARP_INST_PER_OP / (
