@@ -24,6 +24,7 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <functional>
 #include <stdexcept>
 #include <string>
@@ -140,8 +141,31 @@ inline NalUnit NewNalUnit(const uint8_t *frame, int numBytesInNal, Device &dev =
     return NewNalUnits({std::vector<uint8_t>(frame, frame + numBytesInNal)}, dev)[0];
 }
 
-// Every NalUnit the readNalUnit loop (server.go:64-111) produces from a byte stream held in memory.
-inline std::vector<NalUnit> ReadNalUnits(const uint8_t *stream, size_t n, Device &dev = Device::Default()) {
+// One long stream as byte ranges that can be scanned independently, e.g. one per GPU (the C++ twin of
+// h264decode_b200/sharding.py cut_byte_ranges): every nominal cut k * n / n_ranges moves forward to the next start code
+// 00 00 00 01 (server.go:19, :28-39) and a range keeps the start code that opens the next one, because the reference's
+// NAL unit is payload plus the following start code (server.go:64-111).  The NAL units of range r are exactly those of
+// the whole stream whose start code lies in [begin_r, begin_{r+1}); ReadNalUnits(stream + begin, end - begin, dev,
+// begin) yields them with whole-stream offsets.  Host work is O(n_ranges x NAL size): no pass over the stream.
+inline std::vector<std::pair<size_t, size_t>> CutByteRanges(const uint8_t *stream, size_t n, unsigned n_ranges) {
+    static const uint8_t kStart[4] = {0, 0, 0, 1};
+    std::vector<size_t> cuts(1, 0);
+    for (unsigned k = 1; k < n_ranges; k++) {
+        const size_t nominal = std::max(cuts.back(), (size_t)(((unsigned __int128)k * n) / n_ranges));
+        const size_t lo = std::max(nominal >= 3 ? nominal - 3 : (size_t)0, cuts.back());  // a start code across the cut
+        const uint8_t *hit = std::search(stream + lo, stream + n, kStart, kStart + 4);
+        cuts.push_back((size_t)(hit - stream));
+    }
+    cuts.push_back(n);
+    std::vector<std::pair<size_t, size_t>> out;
+    for (unsigned r = 0; r < n_ranges; r++)
+        out.emplace_back(cuts[r], r + 1 < n_ranges ? std::min(n, cuts[r + 1] + 4) : n);
+    return out;
+}
+
+// Every NalUnit the readNalUnit loop (server.go:64-111) produces from a byte stream held in memory (`base`: offset of
+// `stream` in a longer stream, added to startOffset).
+inline std::vector<NalUnit> ReadNalUnits(const uint8_t *stream, size_t n, Device &dev = Device::Default(), uint64_t base = 0) {
     const h264b_nal *nals = nullptr;
     const h264b_nal_ext *ext = nullptr;
     const uint8_t *rbsp = nullptr;
@@ -149,7 +173,7 @@ inline std::vector<NalUnit> ReadNalUnits(const uint8_t *stream, size_t n, Device
     dev.check(h264b_annexb_scan(dev.ctx(), stream, n, 0, 1, &nals, &ext, &sum, &rbsp, nullptr));
     std::vector<NalUnit> out;
     out.reserve(sum.n_nals);
-    for (uint64_t i = 0; i < sum.n_nals; i++) out.push_back(make_nal_unit(nals[i], &ext[i], rbsp, 0));
+    for (uint64_t i = 0; i < sum.n_nals; i++) out.push_back(make_nal_unit(nals[i], &ext[i], rbsp, base));
     return out;
 }
 

@@ -33,6 +33,15 @@ int main(int argc, char **argv) {
         if (mode == "nals") {  // readNalUnit loop over a whole buffer
             const auto s = slurp(argv[2]);
             for (const auto &u : h264::ReadNalUnits(s.data(), s.size())) print_nal(u);
+        } else if (mode == "ranges") {  // CutByteRanges alone (no device call)
+            const auto s = slurp(argv[2]);
+            for (const auto &r : h264::CutByteRanges(s.data(), s.size(), (unsigned)atoi(argv[3])))
+                printf("range %zu %zu\n", r.first, r.second);
+        } else if (mode == "nals_ranges") {  // the stream as n byte ranges, each scanned on its own
+            const auto s = slurp(argv[2]);
+            for (const auto &r : h264::CutByteRanges(s.data(), s.size(), (unsigned)atoi(argv[3])))
+                for (const auto &u : h264::ReadNalUnits(s.data() + r.first, r.second - r.first, h264::Device::Default(), r.first))
+                    print_nal(u);
         } else if (mode == "ingest") {  // the same stream through a pipe in odd-sized writes, batched ingest
             const auto s = slurp(argv[2]);
             const size_t batch = strtoull(argv[3], nullptr, 10), chunk = strtoull(argv[4], nullptr, 10),

@@ -293,3 +293,30 @@ def test_batched_ingest_with_handle_connection_dispatch(exe, tmp_path, batch, ch
     assert out[-1] == ["units", str(len(exp))]
     assert out[:-1] == exp
     assert sum(l[0] == "slice" for l in exp) >= 8
+
+
+def test_cut_byte_ranges_matches_the_python_twin(exe, tmp_path):
+    """host/h264.hpp CutByteRanges == h264decode_b200.sharding.cut_byte_ranges (pure host logic: runs without a GPU)"""
+    from h264decode_b200 import sharding
+    rng = np.random.default_rng(5)
+    for t in range(12):
+        n = int(rng.integers(0, 40000))
+        s = rng.integers(0, 256, n, dtype=np.uint8)
+        s[rng.random(n) < 0.4] = 0
+        for pos in rng.integers(0, max(1, n - 4), max(1, n // 700)):
+            s[pos:pos + 4] = [0, 0, 0, 1]
+        path = os.path.join(str(tmp_path), "r%d.bin" % t)
+        s.tofile(path)
+        for n_ranges in (1, 2, 7):
+            rc, out = run(exe, "ranges", path, n_ranges)
+            assert rc == 0
+            assert [(int(a), int(b)) for _, a, b in out] == sharding.cut_byte_ranges(s, n_ranges)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_ranges", [2, 5])
+def test_read_nal_units_by_byte_ranges(exe, tmp_path, n_ranges):
+    s, path = make_stream(tmp_path)
+    rc, out = run(exe, "nals_ranges", path, n_ranges)
+    assert rc == 0
+    assert out == expect_nal_lines(s)
