@@ -20,7 +20,7 @@ OP_DECISION, OP_BYPASS, OP_TERMINATE = 0, 1, 2
 # every symbol include/h264b200.h declares (tests check that the library exports exactly these)
 SYMBOLS = [
     "h264b_version", "h264b_device_count", "h264b_create", "h264b_destroy", "h264b_last_error", "h264b_set_stream",
-    "h264b_sync", "h264b_host_alloc", "h264b_host_free", "h264b_dev_alloc", "h264b_dev_free", "h264b_memcpy_h2d",
+    "h264b_sync", "h264b_host_alloc", "h264b_host_free", "h264b_cut_byte_ranges", "h264b_dev_alloc", "h264b_dev_free", "h264b_memcpy_h2d",
     "h264b_memcpy_d2h", "h264b_launch_count", "h264b_annexb_scratch_bytes", "h264b_annexb_scan_dev",
     "h264b_annexb_scan", "h264b_nal_units", "h264b_ctx_init_dev", "h264b_ctx_init", "h264b_pre_ctx_state", "h264b_mn",
     "h264b_cabac_decode_dev", "h264b_cabac_decode", "h264b_engine_step", "h264b_binary_decision",
@@ -170,6 +170,7 @@ def load():
         "h264b_sync": (i32, [vp]),
         "h264b_host_alloc": (i32, [vp, C.c_size_t, P(vp)]),
         "h264b_host_free": (i32, [vp, vp]),
+        "h264b_cut_byte_ranges": (i32, [vp, C.c_uint64, C.c_uint32, vp, vp]),
         "h264b_dev_alloc": (i32, [vp, C.c_size_t, P(vp)]),
         "h264b_dev_free": (i32, [vp, vp]),
         "h264b_memcpy_h2d": (i32, [vp, vp, vp, C.c_size_t]),
@@ -222,6 +223,17 @@ def lib():
 
 def make_op(kind, ctx=0):
     return (kind << 14) | (ctx & 0x3FF)
+
+
+def cut_byte_ranges(stream, n_ranges):
+    """h264b_cut_byte_ranges (host-only planner, needs no context / GPU) -> [(begin, end)] * n_ranges"""
+    s = np.ascontiguousarray(stream, dtype=np.uint8)
+    b, e = np.zeros(n_ranges, np.uint64), np.zeros(n_ranges, np.uint64)
+    rc = _lib.h264b_cut_byte_ranges(C.c_void_p(s.ctypes.data), len(s), n_ranges, C.c_void_p(b.ctypes.data),
+                                    C.c_void_p(e.ctypes.data))
+    if rc:
+        raise H264BError(rc, "h264b_cut_byte_ranges")
+    return [(int(x), int(y)) for x, y in zip(b, e)]
 
 
 def _from_ptr(ptr, dtype, count):

@@ -193,6 +193,25 @@ int32_t h264b_host_free(h264b_ctx *ctx, void *p) {
     if (p) H264B_CUDA(ctx, cudaFreeHost(p));
     return H264B_OK;
 }
+int32_t h264b_cut_byte_ranges(const uint8_t *stream, uint64_t n, uint32_t n_ranges, uint64_t *begin, uint64_t *end) {
+    if (!n_ranges || !begin || !end || (n && !stream)) return H264B_E_INVALID;
+    uint64_t cut = 0;  // begin of the range being closed
+    for (uint32_t k = 1; k <= n_ranges; k++) {
+        uint64_t next = n;
+        if (k < n_ranges) {
+            const uint64_t nominal = (uint64_t)(((unsigned __int128)k * n) / n_ranges);
+            uint64_t p = nominal >= 3 ? nominal - 3 : 0;  // a start code that straddles the nominal cut counts
+            if (p < cut) p = cut;
+            for (; p + 4 <= n; p++)
+                if (stream[p] == 0 && stream[p + 1] == 0 && stream[p + 2] == 0 && stream[p + 3] == 1) break;
+            next = p + 4 <= n ? p : n;
+        }
+        begin[k - 1] = cut;
+        end[k - 1] = k < n_ranges ? (next + 4 < n ? next + 4 : n) : n;
+        cut = next;
+    }
+    return H264B_OK;
+}
 int32_t h264b_dev_alloc(h264b_ctx *ctx, size_t bytes, void **out) {
     CHECK_CTX(ctx);
     if (!out) return H264B_E_INVALID;

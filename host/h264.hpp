@@ -141,25 +141,18 @@ inline NalUnit NewNalUnit(const uint8_t *frame, int numBytesInNal, Device &dev =
     return NewNalUnits({std::vector<uint8_t>(frame, frame + numBytesInNal)}, dev)[0];
 }
 
-// One long stream as byte ranges that can be scanned independently, e.g. one per GPU (the C++ twin of
-// h264decode_b200/sharding.py cut_byte_ranges): every nominal cut k * n / n_ranges moves forward to the next start code
+// One long stream as byte ranges that can be scanned independently, e.g. one per GPU (h264b_cut_byte_ranges; the same
+// rule as h264decode_b200/sharding.py cut_byte_ranges): every nominal cut k * n / n_ranges moves forward to the next start code
 // 00 00 00 01 (server.go:19, :28-39) and a range keeps the start code that opens the next one, because the reference's
 // NAL unit is payload plus the following start code (server.go:64-111).  The NAL units of range r are exactly those of
 // the whole stream whose start code lies in [begin_r, begin_{r+1}); ReadNalUnits(stream + begin, end - begin, dev,
 // begin) yields them with whole-stream offsets.  Host work is O(n_ranges x NAL size): no pass over the stream.
 inline std::vector<std::pair<size_t, size_t>> CutByteRanges(const uint8_t *stream, size_t n, unsigned n_ranges) {
-    static const uint8_t kStart[4] = {0, 0, 0, 1};
-    std::vector<size_t> cuts(1, 0);
-    for (unsigned k = 1; k < n_ranges; k++) {
-        const size_t nominal = std::max(cuts.back(), (size_t)(((unsigned __int128)k * n) / n_ranges));
-        const size_t lo = std::max(nominal >= 3 ? nominal - 3 : (size_t)0, cuts.back());  // a start code across the cut
-        const uint8_t *hit = std::search(stream + lo, stream + n, kStart, kStart + 4);
-        cuts.push_back((size_t)(hit - stream));
-    }
-    cuts.push_back(n);
+    std::vector<uint64_t> b(n_ranges), e(n_ranges);
+    if (h264b_cut_byte_ranges(stream, n, n_ranges, b.data(), e.data()) != H264B_OK)
+        throw std::invalid_argument("CutByteRanges");
     std::vector<std::pair<size_t, size_t>> out;
-    for (unsigned r = 0; r < n_ranges; r++)
-        out.emplace_back(cuts[r], r + 1 < n_ranges ? std::min(n, cuts[r + 1] + 4) : n);
+    for (unsigned r = 0; r < n_ranges; r++) out.emplace_back((size_t)b[r], (size_t)e[r]);
     return out;
 }
 

@@ -77,6 +77,14 @@ int32_t h264b_sync(h264b_ctx *ctx);
  * H264Reader.BufferToReader, h264/bit_reader.go:27-39). */
 int32_t h264b_host_alloc(h264b_ctx *ctx, size_t bytes, void **out);
 int32_t h264b_host_free(h264b_ctx *ctx, void *p);
+/* Host-side planner, no device work: cut one long Annex-B stream held in host memory into n_ranges byte ranges that
+ * can be scanned independently (one per GPU / context).  Each nominal cut k * n / n_ranges moves forward to
+ * the next start code 00 00 00 01 (h264/server.go:19, :28-39: the only boundary the reference knows) and a range keeps
+ * the 4 bytes that open the next one, because the reference's NAL unit is payload plus the following start code
+ * (h264/server.go:64-111).  The NAL units of range r are exactly those of the whole stream whose start code lies in
+ * [begin[r], begin[r+1]); offsets in a range's results are relative to begin[r].  Ranges may be empty.  Only the bytes
+ * between a nominal cut and the next start code are read (O(n_ranges x NAL size)). */
+int32_t h264b_cut_byte_ranges(const uint8_t *stream, uint64_t n, uint32_t n_ranges, uint64_t *begin, uint64_t *end);
 int32_t h264b_dev_alloc(h264b_ctx *ctx, size_t bytes, void **out);
 int32_t h264b_dev_free(h264b_ctx *ctx, void *p);
 int32_t h264b_memcpy_h2d(h264b_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async on the stream */

@@ -67,3 +67,25 @@ def test_generated_tables_match_reference_when_present():
     if not os.path.isdir("/root/reference/h264"):
         pytest.skip("reference not mounted (GPU box)")
     subprocess.check_call(["python", os.path.join(ROOT, "tools", "extract_tables.py"), "--check"])
+
+
+def test_cut_byte_ranges_c_abi_matches_python_twin():
+    """h264b_cut_byte_ranges is host-only (no context, no GPU): same ranges as sharding.cut_byte_ranges, bad arguments
+    rejected"""
+    import ctypes as C
+    import numpy as np
+    from h264decode_b200 import capi, sharding
+    rng = np.random.default_rng(21)
+    for t in range(60):
+        n = int(rng.integers(0, 9000))
+        s = rng.integers(0, 256, n, dtype=np.uint8)
+        s[rng.random(n) < 0.5] = 0
+        for pos in rng.integers(0, max(1, n - 4), max(1, n // 150)) if n >= 4 else []:
+            s[pos:pos + 4] = [0, 0, 0, 1]
+        for n_ranges in (1, 2, 3, 8, 13):
+            assert capi.cut_byte_ranges(s, n_ranges) == sharding.cut_byte_ranges(s, n_ranges)
+    lib = capi.lib()
+    one = (C.c_uint64 * 1)()
+    assert lib.h264b_cut_byte_ranges(None, 10, 1, one, one) != 0      # bytes announced, no buffer
+    assert lib.h264b_cut_byte_ranges(None, 0, 0, one, one) != 0       # no ranges asked for
+    assert lib.h264b_cut_byte_ranges(None, 0, 1, one, one) == 0 and one[0] == 0

@@ -303,7 +303,7 @@ def test_cut_byte_ranges_matches_the_python_twin(exe, tmp_path):
         n = int(rng.integers(0, 40000))
         s = rng.integers(0, 256, n, dtype=np.uint8)
         s[rng.random(n) < 0.4] = 0
-        for pos in rng.integers(0, max(1, n - 4), max(1, n // 700)):
+        for pos in rng.integers(0, max(1, n - 4), max(1, n // 700)) if n >= 4 else []:
             s[pos:pos + 4] = [0, 0, 0, 1]
         path = os.path.join(str(tmp_path), "r%d.bin" % t)
         s.tofile(path)

@@ -104,7 +104,7 @@ def _nal_list(stream_bytes, base=0):
 def _random_stream(rng, n, p_zero, every):
     s = rng.integers(0, 256, n, dtype=np.uint8)
     s[rng.random(n) < p_zero] = 0
-    for pos in rng.integers(0, max(1, n - 4), max(1, n // every)):
+    for pos in rng.integers(0, max(1, n - 4), max(1, n // every)) if n >= 4 else []:
         s[pos:pos + 4] = [0, 0, 0, 1]
     return s
 
