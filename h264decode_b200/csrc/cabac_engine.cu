@@ -14,17 +14,16 @@
 // refill ahead, which hides the (uncoalesced, L2-resident) load completely; bitstream traffic is ~0.11 B per bin.
 #include "cabac_lane.cuh"
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace h264b {
 
 #ifndef H264B_CABAC_PIPELINE
 #define H264B_CABAC_PIPELINE 1  // fast loop: context state / table entry of a decision requested ahead of time
 #endif
-#ifndef H264B_CABAC_WARPS
-#define H264B_CABAC_WARPS 2
-#endif
-constexpr int kWarpsPerCta = H264B_CABAC_WARPS;
-constexpr int kTabBytes = 1024 + 2048;  // engine table + its fast-loop form, in front of the context states
+constexpr int kMaxWarpsPerCta = 20;            // one CTA per SM, five warps per scheduler
+constexpr int kTab16Bytes = 128 * 8 * 16;      // the fast loop's table: 128 states x 8 copies x 16 bytes
+constexpr size_t kMaxSmemPerCta = 227 * 1024;  // opt-in maximum of dynamic shared memory per CTA on sm_100
 
 // explicit shared-memory accesses (32-bit shared addresses: no generic-address arithmetic in the inner loop)
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -36,6 +35,11 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
 __device__ __forceinline__ uint2 lds_u32x2(uint32_t a) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u32x4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {  // (no masking of the selector)
@@ -58,7 +62,8 @@ struct CabacArgs {
     const uint32_t *order; // slices sorted by length (longest first) or NULL: lane -> slice = order[index]
     const uint32_t *d_n;   // actual slice count on the device (<= j.n_slices, which then is only the bound) or NULL
     uint32_t lanes_per_warp;
-    uint32_t n_warps;
+    uint32_t n_warps;      // bundles of lanes_per_warp slices
+    uint32_t map_mode;     // 0: warp 0 of a CTA takes its longest bundle, 1: the highest warp does, 2: launch order
 };
 
 // ---------------------------------------------------------------------------------------------- length bundles
@@ -132,47 +137,80 @@ __global__ void __launch_bounds__(256) sort_scatter_kernel(const uint32_t *n_ops
 __device__ __forceinline__ int idc_class_dev(int idc) { return (idc >= -1 && idc <= 2) ? idc + 1 : 4; }
 __device__ __forceinline__ int clip3_dev(int x, int y, int z) { return z < x ? x : (z > y ? y : z); }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacArgs a) {
+// 16-byte form of an engine-table entry for the pipelined fast loop (kLoop 1):
+//   x  rangeTabLPS[state][0..3]                      (as in the 8-byte entry)
+//   y  renormalisation shift after an LPS, per q:    clz(rangeLPS) - 23  (RenormD's step count for codIRange = rangeLPS)
+//   z  next state after an MPS | bin << 15 | next state after an LPS << 16 | bin << 31   (the r1 "fast" form)
+// Kept 8 times in shared memory, copy c in the 16-byte column c of every 128-byte row: lane l reads copy l & 7, so the
+// 8 lanes of a quarter warp (one LDS.128 wavefront) always hit 8 different bank groups -- no conflicts for any states.
+__device__ __forceinline__ uint4 entry16(uint64_t e) {
+    uint4 r;
+    r.x = (uint32_t)e;
+    uint32_t y = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t lps = (r.x >> (8 * q)) & 0xFFu;
+        y |= ((lps ? (uint32_t)__clz((int)lps) - 23u : 9u) & 0xFFu) << (8 * q);
+    }
+    r.y = y;
+    const uint64_t f = (e & 0x00FF00FFFFFFFFFFull) | ((e & 0x0100010000000000ull) << 7);
+    r.z = (uint32_t)(f >> 32);
+    r.w = 0u;
+    return r;
+}
+
+template <int kLoop>
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(CabacArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint64_t *s_tab = reinterpret_cast<uint64_t *>(smem);                  // 128 x 8 B
-    uint64_t *s_tab_fast = reinterpret_cast<uint64_t *>(smem + 1024);      // 256 x 8 B: the fast loop's form
-    uint8_t *s_state_all = smem + kTabBytes;                               // [warp][n_ctx][32]
+    uint64_t *s_tab = reinterpret_cast<uint64_t *>(smem);                  // 128 x 8 B (generic loop)
+    uint64_t *s_tab_fast = reinterpret_cast<uint64_t *>(smem + 1024);      // kLoop 0: 256 x 8 B, the r1 fast loop's form
+    uint4 *s_tab16 = reinterpret_cast<uint4 *>(smem + 1024);               // kLoop 1: 128 x 8 x 16 B
+    uint8_t *s_state_all = smem + 1024 + (kLoop ? kTab16Bytes : 2048);     // [warp][n_ctx][32]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 256; i += kWarpsPerCta * 32) {
-        const uint64_t e = a.tab[i & 127];
-        if (i < 128) s_tab[i] = e;
-        // bins from bit 0 to bit 7 of their bytes (bits 40 -> 47, 56 -> 63); entries 128..255 repeat 0..127
-        s_tab_fast[i] = (e & 0x00FF00FFFFFFFFFFull) | ((e & 0x0100010000000000ull) << 7);
+    const uint32_t W = blockDim.x >> 5;
+    for (int i = tid; i < 128; i += blockDim.x) s_tab[i] = a.tab[i];
+    if (kLoop == 0) {
+        for (int i = tid; i < 256; i += blockDim.x) {
+            const uint64_t e = a.tab[i & 127];
+            // bins from bit 0 to bit 7 of their bytes (bits 40 -> 47, 56 -> 63); entries 128..255 repeat 0..127
+            s_tab_fast[i] = (e & 0x00FF00FFFFFFFFFFull) | ((e & 0x0100010000000000ull) << 7);
+        }
+    } else {
+        for (int i = tid; i < 1024; i += blockDim.x) s_tab16[i] = entry16(a.tab[i >> 3]);
     }
     __syncthreads();
     const h264b_cabac_job &j = a.j;
     const uint32_t n_ctx = j.n_ctx;
     uint8_t *s_state = s_state_all + (size_t)warp * n_ctx * 32;
-
-    const uint32_t gw = blockIdx.x * kWarpsPerCta + warp;
-    if (gw >= a.n_warps) return;
-    const uint32_t index = gw * a.lanes_per_warp + lane;
     const uint32_t n_slices = a.d_n && *a.d_n < j.n_slices ? *a.d_n : j.n_slices;
-    if (gw * a.lanes_per_warp >= n_slices) return;
+    const uint32_t n_bundles = (n_slices + a.lanes_per_warp - 1) / a.lanes_per_warp;
+
+    // Bundle (lanes_per_warp slices of similar length, longest bundles first) -> warp.  One wave: the CTAs are spread over
+    // the SMs and the position of a warp is  rank of the warp inside its CTA x CTAs + CTA,  so the longest bundles are
+    // spread over all SMs and sit on the warps the issue arbiter prefers (map_mode 1: the highest warp of a CTA takes
+    // its longest bundle).  More bundles than one wave holds: small CTAs in launch order.
+    const uint32_t rank = a.map_mode == 1 ? (W - 1u - (uint32_t)warp) : (uint32_t)warp;
+    const uint32_t gw = a.map_mode == 2 ? blockIdx.x * W + (uint32_t)warp : rank * gridDim.x + blockIdx.x;
+    if (gw >= n_bundles) return;
+    const uint32_t index = gw * a.lanes_per_warp + lane;
     // Lanes without a slice of their own (a partly filled warp) shadow the warp's first lane: they decode the same
     // slice and store nothing, so the loops below never have to predicate on "is there a slice in this lane".
     const bool own = lane < (int)a.lanes_per_warp && index < n_slices;
-    const bool valid = true;
     const uint32_t src_index = own ? index : gw * a.lanes_per_warp;
     const uint32_t slice = a.order ? a.order[src_index] : src_index;
 
     // ---- per-lane setup
-    uint32_t my_ops = 0;
-    uint64_t off = 0;
-    uint32_t len = 0;
-    if (valid) {
-        my_ops = j.n_ops ? j.n_ops[slice] : j.n_ops_max;
-        if (my_ops > j.n_ops_max) my_ops = j.n_ops_max;
-        off = j.off[slice];
-        len = j.len[slice];
-    }
+    uint32_t my_ops = j.n_ops ? j.n_ops[slice] : j.n_ops_max;
+    if (my_ops > j.n_ops_max) my_ops = j.n_ops_max;
+    uint64_t off = j.off[slice];
+    uint32_t len = j.len[slice];
+    // a slice that does not lie inside the buffer (a caller's bad offset) decodes the buffer's last bytes and is flagged
+    bool bad_range = false;
+    if (off > j.total_bytes) off = j.total_bytes, bad_range = true;
+    if ((uint64_t)len > j.total_bytes - off) len = (uint32_t)(j.total_bytes - off), bad_range = true;
     // initial context states: given, or the K4 rule (state LUT row of this slice's (idc class, clipped qp))
-    if (valid) {
+    uint32_t st_or = 0;
+    {
         const uint8_t *src;
         if (j.init_states) {
             src = j.init_states + (size_t)slice * n_ctx;
@@ -180,12 +218,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
             const h264b_slice_qp p = j.qp[slice];
             src = a.lut + ((size_t)idc_class_dev(p.cabac_init_idc) * 52 + clip3_dev(0, 51, p.slice_qp_y)) * 1024;
         }
-        for (uint32_t c = 0; c < n_ctx; c++) s_state[c * 32 + lane] = src[c];
+        for (uint32_t c = 0; c < n_ctx; c++) {
+            const uint8_t v = src[c];
+            st_or |= v;
+            s_state[c * 32 + lane] = v;
+        }
     }
     __syncwarp();
 
     LaneDecoder eng = {};
-    if (valid) eng.init(j.bytes, j.total_bytes, off, (j.flags & H264B_BYPASS_SPEC_OR) != 0);
+    eng.init(j.bytes, j.total_bytes, off, (j.flags & H264B_BYPASS_SPEC_OR) != 0);
 
     uint32_t warp_ops = my_ops;
 #pragma unroll
@@ -199,18 +241,143 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
     // bypass / terminate.  A warp's time is its serial chain codIRange / codIOffset -> next bin plus every taken branch
     // (tens of cycles for a warp that has its scheduler to itself, as the long slices at the end of a launch do), so:
     //   * the op kinds of a block are two ballots, so every branch on them is warp-uniform (no convergence barriers);
-    //   * the context state and the table entry of a decision are requested ahead of the arithmetic, with the state a
-    //     decision writes forwarded into those requests when the contexts coincide (no hazard branch; see below);
+    //   * the context state and the table entry of a decision are requested ahead of the arithmetic;
     //   * shared memory is addressed with explicit 32-bit shared addresses (ld/st.shared), not generic pointers;
     //   * codIRange is kept as R << 22, aligned with codIOffset in the window: (R22 >> 28) is 4 + qCodIRangeIdx, which as
-    //     a byte-permute selector picks rangeTabLPS[state][q] out of the table word directly; the renormalisation
-    //     shift is clz(R22) - 1;
-    //   * the fast table (256 entries, no masking of the state byte) carries the bin in bit 7 of its byte, so one
-    //     byte permute yields (next state -> byte 0, bin -> bit 31) and one funnel shift appends the bin; the word is
-    //     bit-reversed once per 32 bins;
+    //     a byte-permute selector picks rangeTabLPS[state][q] out of the table word directly;
+    //   * the table carries the bin in bit 7 of its byte, so one byte permute yields (next state -> byte 0, bin ->
+    //     bit 31) and one funnel shift appends the bin; the word is bit-reversed once per 32 bins;
     //   * refills are checked once per two ops (16 bits cover two decisions).
     // (every condition that steers the loop is a vote result: the compiler then knows the warp stays converged and
     //  emits the shuffles and votes inside without divergence checks)
+    if (kLoop == 1) {
+      // kLoop 1.  The serial chain of a decision is  codIRange -> rangeLPS -> compare -> new codIRange: nothing else may
+      // sit on it.  (1) The entry of the next decision is requested before this decision's arithmetic, from the state
+      // byte fetched one decision earlier; only when the next decision (or the one after it) uses this decision's own
+      // context -- known from the schedule: two ballots per block -- a rare, warp-uniform branch re-requests it from the
+      // state just written.  (2) The renormalisation shift comes from the table (LPS: static per state and q) or from
+      // bit 30 of the MPS range, not from a count-leading-zeros (XU pipe, ~25 cycles).  (3) The table is replicated so
+      // that its reads are bank-conflict free for any combination of states (entry16()).
+      if (__all_sync(0xFFFFFFFFu, my_ops >= 32u && !eng.lit && !(st_or & 0x80u))) {
+        CabacLane &w = eng.w;
+        const uint32_t st_lane = opaque(smem_addr(s_state) + (uint32_t)lane);  // &state[0][lane]
+        const uint32_t tabl = opaque(smem_addr(s_tab16) + (uint32_t)(lane & 7) * 16u);
+        const uint32_t sel_mps = opaque(0x1440u), sel_lps = opaque(0x3442u);  // byte-permute selectors, kept in registers
+        uint32_t R22 = w.R << 22, hi = w.hi, lo = w.lo;
+        int32_t fbits = w.fbits;
+        bool left = false;
+        uint4 e_cur = make_uint4(0u, 0u, 0u, 0u);  // table entry of the next decision
+        uint32_t s1 = 0;                           // state byte of the decision after that
+        uint32_t next_op = i + (uint32_t)lane < j.n_ops_max ? (uint32_t)j.ops[i + (uint32_t)lane] : 0u;
+        while (!left && __all_sync(0xFFFFFFFFu, i + 32u <= my_ops)) {
+            const uint32_t my_op = next_op;
+            next_op = i + 32u + (uint32_t)lane < j.n_ops_max ? (uint32_t)j.ops[i + 32u + (uint32_t)lane] : 0u;
+            const uint32_t my_kind = my_op >> 14;
+            const uint32_t dec_mask = __ballot_sync(0xFFFFFFFFu, my_kind == H264B_OP_DECISION);
+            const uint32_t byp_mask = __ballot_sync(0xFFFFFFFFu, my_kind == H264B_OP_BYPASS);
+            uint32_t my_row = ((my_op & 0x3FFu) < n_ctx ? (my_op & 0x3FFu) : 0u) * 32u;  // as below: ctx 0
+            const uint32_t above = dec_mask & ~((2u << lane) - 1u);
+            const uint32_t above2 = above & (above - 1u);
+            const uint32_t nrow1 = __shfl_sync(0xFFFFFFFFu, my_row, above ? __ffs((int)above) - 1 : lane);
+            uint32_t my_nn = __shfl_sync(0xFFFFFFFFu, my_row, above2 ? __ffs((int)above2) - 1 : lane);
+            const uint32_t fwd1_mask = __ballot_sync(0xFFFFFFFFu, above != 0u && nrow1 == my_row);
+            const uint32_t fwd2_mask = __ballot_sync(0xFFFFFFFFu, above2 != 0u && my_nn == my_row);
+            if (!above2) my_nn = 0u;  // (no second decision behind this op in the block: a harmless load of row 0)
+            {   // the block's first two decisions: entry of the first, state of the second (once per block, in place)
+                const uint32_t rest = dec_mask & (dec_mask - 1u);
+                const uint32_t row_d0 = __shfl_sync(0xFFFFFFFFu, my_row, dec_mask ? __ffs((int)dec_mask) - 1 : 0);
+                const uint32_t row_d1 = __shfl_sync(0xFFFFFFFFu, my_row, rest ? __ffs((int)rest) - 1 : 0);
+                e_cur = lds_u32x4(tabl + lds_u8(row_d0 + st_lane) * 128u);
+                s1 = lds_u8(row_d1 + st_lane);
+            }
+            uint32_t k = 0;
+#pragma unroll 1
+            for (uint32_t k8 = 0; k8 < 32u && !left; k8 += 8u) {
+                // lanes 0..7 hold the rows of this chunk's ops (the rows rotate by 8 lanes per chunk), so the shuffles
+                // below have constant source lanes
+                const uint32_t dm = dec_mask >> k8, bm = byp_mask >> k8;
+                const uint32_t row8 = my_row;
+                my_row = __shfl_sync(0xFFFFFFFFu, my_row, (lane + 8) & 31);
+                const uint32_t f1m = fwd1_mask >> k8, f2m = fwd2_mask >> k8, nn8 = my_nn;
+                const uint32_t hzm = f1m | f2m;
+                my_nn = __shfl_sync(0xFFFFFFFFu, my_nn, (lane + 8) & 31);
+#pragma unroll
+                for (uint32_t u = 0; u < 8u; u++) {
+                    if ((u & 1u) == 0u) {
+                        if (__builtin_expect(__any_sync(0xFFFFFFFFu, fbits < 16), 0)) {
+                            __syncwarp();  // (also keeps this rare block a branch instead of 20 predicated instructions)
+                            if (fbits <= 22) {
+                                w.hi = hi, w.lo = lo, w.fbits = fbits;
+                                w.refill();
+                                hi = w.hi, lo = w.lo, fbits = w.fbits;
+                            }
+                        }
+                    }
+                    if (dm & (1u << u)) {
+                        const uint32_t s2 = lds_u8(__shfl_sync(0xFFFFFFFFu, nn8, (int)u) + st_lane);  // state of the one after next
+                        const uint32_t addr = __shfl_sync(0xFFFFFFFFu, row8, (int)u) + st_lane;
+                        const uint4 e = e_cur;
+                        e_cur = lds_u32x4(tabl + s1 * 128u);  // the next decision's entry, ahead of this one's arithmetic
+                        const uint32_t q4 = R22 >> 28;
+                        const uint32_t lps22 = prmt(0u, e.x, q4) << 22;  // rangeTabLPS[state][q] << 22
+                        const uint32_t sh_lps = prmt(0u, e.y, q4);
+                        const uint32_t rm22 = R22 - lps22;
+                        const bool is_lps = hi >= rm22;
+                        const uint32_t sh_mps = (rm22 >> 30) ^ 1u;  // codIRange - rangeLPS >= 128: at most one doubling
+                        const uint32_t r22 = is_lps ? lps22 : rm22;
+                        const uint32_t sh = is_lps ? sh_lps : sh_mps;
+                        const uint32_t hi_lps = hi - rm22;
+                        hi = is_lps ? hi_lps : hi;
+                        const uint32_t sel = prmt(e.z, 0u, is_lps ? sel_lps : sel_mps);  // next state | bin << 31
+                        sts_u8(addr, sel);
+                        R22 = r22 << sh;
+                        hi = __funnelshift_l(lo, hi, sh);
+                        lo <<= sh;
+                        fbits -= (int32_t)sh;
+                        word = __funnelshift_l(sel, word, 1);
+                        s1 = s2;
+                        if (__builtin_expect((hzm >> u) & 1u, 0)) {  // this context again within two decisions
+                            __syncwarp();
+                            if ((f1m >> u) & 1u) e_cur = lds_u32x4(tabl + (sel & 0xFFu) * 128u);
+                            if ((f2m >> u) & 1u) s1 = sel & 0xFFu;
+                        }
+                    } else if (bm & (1u << u)) {
+                        hi = __funnelshift_l(lo, hi, 1);
+                        lo <<= 1;
+                        fbits -= 1;
+                        const bool one = hi >= R22;
+                        if (one) hi -= R22;
+                        word = (word << 1) | (one ? 1u : 0u);
+                    } else {
+                        w.R = R22 >> 22, w.hi = hi, w.lo = lo, w.fbits = fbits;
+                        const uint32_t bin = w.terminate();
+                        R22 = w.R << 22, hi = w.hi, lo = w.lo, fbits = w.fbits;
+                        word = (word << 1) | bin;
+                        if (__any_sync(0xFFFFFFFFu, bin)) {  // a slice that goes on after its end: the generic loop takes over
+                            if (bin) eng.to_literal();
+                            left = true;
+                            k = k8 + u + 1u;
+                            break;
+                        }
+                    }
+                }
+            }
+            if (!left) {
+                i += 32u;
+                if (own) bins[(i >> 5) - 1u] = __brev(word);
+                word = 0;
+            } else {
+                i += k;
+                word = k < 32u ? __brev(word) >> (32u - k) : __brev(word);  // bins 0..k-1 in bits 0..k-1
+                if (k == 32u) {
+                    if (own) bins[(i >> 5) - 1u] = word;
+                    word = 0;
+                }
+            }
+        }
+        if (!eng.lit) w.R = R22 >> 22, w.hi = hi, w.lo = lo, w.fbits = fbits;
+      }
+    } else
     if (__all_sync(0xFFFFFFFFu, my_ops >= 32u && !eng.lit)) {
         CabacLane &w = eng.w;
         const uint32_t st_lane = opaque(smem_addr(s_state) + (uint32_t)lane);  // &state[0][lane]
@@ -472,7 +639,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
         f.cod_i_range = eng.cod_i_range();
         f.cod_i_offset = eng.cod_i_offset();
         f.bits_read = bits_read;
-        f.flags = bits_read > 8ull * len ? H264B_F_OVERRUN : 0u;
+        f.flags = (bits_read > 8ull * len || bad_range) ? H264B_F_OVERRUN : 0u;
         f.n_bins = n_bins;
         j.final[slice] = f;
         if (j.final_states) {
@@ -480,6 +647,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) cabac_decode_kernel(CabacAr
             for (uint32_t c = 0; c < n_ctx; c++) dst[c] = s_state[c * 32 + lane];
         }
     }
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
 }
 
 int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n_slices) {
@@ -492,6 +664,9 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
     if (!j.bins_off && j.bins_stride_words < (j.n_ops_max + 1 + 31) / 32)
         return set_error(ctx, H264B_E_INVALID, "cabac: bins_stride_words too small");
     if ((uintptr_t)j.bytes & 3) return set_error(ctx, H264B_E_INVALID, "cabac: bytes must be 4-byte aligned");
+    // measurement knobs (tools/cabac_balance_exp.py); the defaults are the shipped configuration
+    const int k_loop = env_int("H264B_CABAC_LOOP", 1), k_w = env_int("H264B_CABAC_W", 0),
+              k_map = env_int("H264B_CABAC_MAP", 1);
     const int v = (j.flags & H264B_TABLES_SPEC) ? 1 : 0;
     CabacArgs a;
     a.j = j;
@@ -499,7 +674,8 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
     a.lut = ctx->d_state_lut[v];
     // Few slices: spread them one (or a few) per warp so every slice gets its own scheduler slot and no lane waits on
     // a neighbour's bank conflict; many slices: 32 per warp.
-    const uint32_t target_warps = (uint32_t)ctx->sm_count * 4;  // one warp per scheduler before lanes are doubled up
+    const uint32_t sms = (uint32_t)ctx->sm_count;
+    const uint32_t target_warps = sms * 4;  // one warp per scheduler before lanes are doubled up
     uint32_t lpw = (j.n_slices + target_warps - 1) / target_warps;
     if (lpw < 1) lpw = 1;
     if (lpw > 32) lpw = 32;
@@ -507,6 +683,21 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
     a.n_warps = (j.n_slices + lpw - 1) / lpw;
     a.order = nullptr;
     a.d_n = d_n_slices;
+    a.map_mode = (uint32_t)k_map;
+    // One wave of one CTA per SM with W warps, each warp with its own n_ctx x 32 bytes of context rows; what does not fit
+    // one wave runs as small CTAs in launch order (the hardware hands them out as earlier ones finish).
+    const size_t tab_bytes = 1024 + (k_loop ? kTab16Bytes : 2048);
+    uint32_t w_fit = (uint32_t)((kMaxSmemPerCta - tab_bytes) / ((size_t)j.n_ctx * 32));
+    if (w_fit > (uint32_t)kMaxWarpsPerCta) w_fit = kMaxWarpsPerCta;
+    uint32_t W = (a.n_warps + sms - 1) / sms;
+    if (k_w > 0) W = (uint32_t)k_w;
+    if (W > w_fit || (k_w > 0 && k_w < 4)) {
+        W = w_fit < 4 ? w_fit : 4;
+        if (k_w > 0 && k_w < 4) W = (uint32_t)k_w;
+        a.map_mode = 2;
+    }
+    if (W < 1) W = 1;
+    const uint32_t grid = (a.n_warps + W - 1) / W;
     if (lpw > 1 && j.n_ops) {  // bundles of equally long slices
         void *d_sort;
         int rc = ensure_dev(ctx, 16, sizeof(SortScratch) + (size_t)j.n_slices * 4, &d_sort);
@@ -515,8 +706,7 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
         uint32_t *order = (uint32_t *)(ss + 1);
         H264B_CUDA(ctx, cudaMemsetAsync(ss, 0, sizeof(SortScratch), ctx->stream));
         H264B_CUDA(ctx, cudaMemsetAsync(&ss->min_ops, 0xFF, 4, ctx->stream));
-        const int sb = (int)((j.n_slices + 255) / 256 < (uint32_t)ctx->sm_count * 4 ? (j.n_slices + 255) / 256
-                                                                                   : (uint32_t)ctx->sm_count * 4);
+        const int sb = (int)((j.n_slices + 255) / 256 < sms * 4 ? (j.n_slices + 255) / 256 : sms * 4);
         sort_minmax_kernel<<<sb, 256, 0, ctx->stream>>>(j.n_ops, j.n_slices, d_n_slices, j.n_ops_max, ss);
         H264B_LAUNCH_CHECK(ctx, "sort_minmax_kernel");
         sort_hist_kernel<<<sb, 256, 0, ctx->stream>>>(j.n_ops, j.n_slices, d_n_slices, j.n_ops_max, ss);
@@ -527,10 +717,14 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
         H264B_LAUNCH_CHECK(ctx, "sort_scatter_kernel");
         a.order = order;
     }
-    const size_t smem = kTabBytes + (size_t)kWarpsPerCta * j.n_ctx * 32;
-    const int blocks = (int)((a.n_warps + kWarpsPerCta - 1) / kWarpsPerCta);
-    H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cabac_decode_kernel<<<blocks, kWarpsPerCta * 32, smem, ctx->stream>>>(a);
+    const size_t smem = tab_bytes + (size_t)W * j.n_ctx * 32;
+    if (k_loop) {
+        H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cabac_decode_kernel<1><<<grid, W * 32, smem, ctx->stream>>>(a);
+    } else {
+        H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cabac_decode_kernel<0><<<grid, W * 32, smem, ctx->stream>>>(a);
+    }
     H264B_LAUNCH_CHECK(ctx, "cabac_decode_kernel");
     return H264B_OK;
 }
