@@ -938,12 +938,13 @@ __global__ void __launch_bounds__(256) nal_frames_kernel(const uint8_t *in, uint
 __global__ void __launch_bounds__(1024) slice_select_kernel(const h264b_nal *nals, const h264b_scan_summary *summary,
                                                             uint32_t nal_cap, uint32_t data_off, uint32_t max_slices,
                                                             uint64_t *s_off, uint32_t *s_len, uint32_t *s_nal,
-                                                            uint32_t *n_out) {
+                                                            uint32_t *n_out, uint32_t *n_found) {
     __shared__ uint32_t warp_cnt[32];
     __shared__ uint32_t base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint64_t n = summary->n_nals;
     if (n > nal_cap) n = nal_cap;
+    if (summary->status != H264B_OK) n = 0;  // an incomplete index holds no records at all (scan_finalize_kernel)
     if (tid == 0) base = 0;
     __syncthreads();
     for (uint64_t k0 = 0; k0 < n; k0 += 1024) {
@@ -975,7 +976,10 @@ __global__ void __launch_bounds__(1024) slice_select_kernel(const h264b_nal *nal
         if (tid == 0) base += tot;
         __syncthreads();
     }
-    if (tid == 0) *n_out = base < max_slices ? base : max_slices;
+    if (tid == 0) {
+        *n_out = base < max_slices ? base : max_slices;
+        if (n_found) *n_found = base;  // all slice NAL units, whatever the list holds
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
@@ -1081,9 +1085,9 @@ int launch_nal_frames(h264b_ctx *ctx, const uint8_t *d_frames, uint64_t total, c
 
 int launch_slice_select(h264b_ctx *ctx, const h264b_nal *d_nals, const h264b_scan_summary *d_summary,
                         uint32_t nal_cap, uint32_t slice_data_offset, uint32_t max_slices, uint64_t *d_off,
-                        uint32_t *d_len, uint32_t *d_slice_nal, uint32_t *d_n_slices) {
+                        uint32_t *d_len, uint32_t *d_slice_nal, uint32_t *d_n_slices, uint32_t *d_n_found) {
     slice_select_kernel<<<1, 1024, 0, ctx->stream>>>(d_nals, d_summary, nal_cap, slice_data_offset, max_slices, d_off,
-                                                     d_len, d_slice_nal, d_n_slices);
+                                                     d_len, d_slice_nal, d_n_slices, d_n_found);
     H264B_LAUNCH_CHECK(ctx, "slice_select_kernel");
     return H264B_OK;
 }

@@ -491,23 +491,35 @@ static int slot_pin(h264b_ctx *ctx, StreamSlot *sl, int i, size_t bytes, void **
     return H264B_OK;
 }
 
-static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job, uint64_t *ticket);
+static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job, int slot_idx, uint32_t nal_cap);
 
 int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_t *ticket) {
     CHECK_CTX(ctx);
     if (!job || !ticket) return H264B_E_INVALID;
     // the job's kernels go to its slot's own stream and scratch bank (restored whatever happens)
+    const int slot_idx = (int)(ctx->next_ticket % kStreamSlots);
+    StreamSlot *sl = ctx->slot[slot_idx];
+    if (sl->busy)
+        return set_error(ctx, H264B_E_INVALID, "stream_submit: %d jobs are in flight, wait for one first", kStreamSlots);
     const cudaStream_t saved_stream = ctx->stream;
     const int saved_bank = ctx->bank;
-    ctx->stream = ctx->slot[ctx->next_ticket % kStreamSlots]->cs;
-    ctx->bank = 1 + (int)(ctx->next_ticket % kStreamSlots);
-    const int32_t rc = stream_submit_on_slot(ctx, job, ticket);
+    ctx->stream = sl->cs;
+    ctx->bank = 1 + slot_idx;
+    const int32_t rc = stream_submit_on_slot(ctx, job, slot_idx, default_nal_cap(job->n));
     ctx->stream = saved_stream;
     ctx->bank = saved_bank;
+    if (rc == H264B_OK) {
+        sl->busy = true;
+        sl->ticket = ctx->next_ticket;
+        *ticket = ctx->next_ticket++;
+    }
     return rc;
 }
 
-static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job, uint64_t *ticket) {
+// Enqueues the job on slot slot_idx (its copies and kernels; ctx->stream / ctx->bank are the slot's).  nal_cap: records of
+// the NAL index.  h264b_stream_wait calls this again, with the bounds the first run reported, when one of them was too
+// small (the job's host buffers are still valid then: they have to be until the wait returns).
+static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job, int slot_idx, uint32_t nal_cap) {
     const h264b_stream_job &j = *job;
     // (H264B_STREAM_PARAM_SETS implies H264B_STREAM_SLICE_HEADERS)
     const bool from_headers = (j.flags & (H264B_STREAM_SLICE_HEADERS | H264B_STREAM_PARAM_SETS)) != 0 && j.max_slices != 0;
@@ -516,13 +528,11 @@ static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job
     if ((!j.stream && j.n) || (j.max_slices && ((!j.qp && !from_headers) || (!j.ops && j.n_ops_max))) ||
         (from_headers && !own_psets && !j.param_sets))
         return set_error(ctx, H264B_E_INVALID, "stream_submit: null pointer in job");
-    StreamSlot *sl = ctx->slot[ctx->next_ticket % kStreamSlots];
-    if (sl->busy)
-        return set_error(ctx, H264B_E_INVALID, "stream_submit: %d jobs are in flight, wait for one first", kStreamSlots);
+    StreamSlot *sl = ctx->slot[slot_idx];
     // the slot's previous results may still be on their way out: reuse its buffers only after that
     H264B_CUDA(ctx, cudaEventSynchronize(sl->e_out));
     const size_t ms = j.max_slices ? j.max_slices : 1;
-    const uint32_t cap = default_nal_cap(j.n);
+    const uint32_t cap = nal_cap;
     void *d_stream, *d_rbsp, *d_nals, *d_sum, *d_off, *d_len, *d_snal, *d_ops, *d_nops = nullptr, *d_qp, *d_boff, *d_bins,
         *d_fin, *h_boff;
     // bins layout: fixed by the caller's op counts, so it is known before the device knows how many slices there are
@@ -561,7 +571,7 @@ static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job
 
     // 1. inputs: host -> device on the copy-in stream (overlaps the kernels of the job before)
     cudaStream_t in = ctx->s_in, out = ctx->s_out, cs = ctx->stream;
-    if (ctx->trace && ctx->next_ticket == 0) cudaEventRecord(ctx->t_ref, in);
+    if (ctx->trace && ctx->next_ticket == 0 && !sl->busy) cudaEventRecord(ctx->t_ref, in);
     H264B_CUDA(ctx, cudaStreamWaitEvent(in, sl->e_compute, 0));  // the slot's previous kernels have read its inputs
     if (ctx->trace) cudaEventRecord(sl->t_in0, in);
     if (j.n) H264B_CUDA(ctx, cudaMemcpyAsync(d_stream, j.stream, j.n, cudaMemcpyHostToDevice, in));
@@ -597,7 +607,7 @@ static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job
                           (h264b_nal_ext *)d_ext, cap, (h264b_scan_summary *)d_sum, j.flags));
     RC(launch_slice_select(ctx, (const h264b_nal *)d_nals, (const h264b_scan_summary *)d_sum, cap,
                            from_headers ? 0u : j.slice_data_offset, j.max_slices, (uint64_t *)d_off, (uint32_t *)d_len,
-                           (uint32_t *)d_snal, d_ns));
+                           (uint32_t *)d_snal, d_ns, d_ns + 1));
     void *d_hdr = nullptr, *d_psl = nullptr, *d_sps = nullptr, *d_pps = nullptr, *d_sps_of = nullptr;
     if (from_headers) {  // SliceQPY, cabac_init_idc and the start of the CABAC data come from the slices' own headers
         RC(slot_dev(ctx, sl, 14, ms * sizeof(h264b_slice_header), &d_hdr));
@@ -700,9 +710,6 @@ static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job
     sl->nal_cap = cap;
     sl->nal_prefix = nal_prefix;
     sl->total_words = total_words;
-    sl->busy = true;
-    sl->ticket = ctx->next_ticket;
-    *ticket = ctx->next_ticket++;
     return H264B_OK;
 }
 
@@ -724,11 +731,50 @@ int32_t h264b_stream_wait(h264b_ctx *ctx, uint64_t ticket, h264b_stream_result *
         fprintf(stderr, "h264b trace: job %llu  H2D %.1f..%.1f  kernels %.1f..%.1f  D2H %.1f..%.1f ms\n",
                 (unsigned long long)ticket, a, b, c, d, e, f);
     }
-    memset(res, 0, sizeof(*res));
-    memcpy(&res->scan, sl->h[5], sizeof(res->scan));
-    if (res->scan.status != H264B_OK)
-        return set_error(ctx, H264B_E_CAPACITY, "stream: more NAL units (%llu) than the index holds (%u)",
-                         (unsigned long long)res->scan.n_nals, sl->nal_cap);
+    // A bound of the job that turned out too small -- the NAL index (streams of very short NAL units), the SPS / PPS
+    // lists, the slice list of a job whose per-slice inputs all come from the stream -- is raised to what the run
+    // reported and the job runs once more on its slot (its host buffers are still valid: the wait has not returned).
+    for (int attempt = 0;; attempt++) {
+        memset(res, 0, sizeof(*res));
+        memcpy(&res->scan, sl->h[5], sizeof(res->scan));
+        h264b_stream_job jr = sl->job;
+        uint32_t cap = sl->nal_cap;
+        bool again = false;
+        if (res->scan.status != H264B_OK) {
+            if (res->scan.n_start_codes + 1 > 0xFFFFFFFFull)
+                return set_error(ctx, H264B_E_CAPACITY, "stream: %llu NAL units", (unsigned long long)res->scan.n_nals);
+            cap = (uint32_t)(res->scan.n_start_codes + 1);
+            again = true;
+        } else {
+            const bool headers = (jr.flags & (H264B_STREAM_SLICE_HEADERS | H264B_STREAM_PARAM_SETS)) != 0 && jr.max_slices;
+            const uint32_t slices_found = *(const uint32_t *)((const uint8_t *)sl->h[5] + 68);
+            if (headers && (jr.flags & H264B_STREAM_PARAM_SETS) && !jr.n_ops && slices_found > jr.max_slices) {
+                jr.max_slices = slices_found;
+                again = true;
+            }
+            if (headers && (jr.flags & H264B_STREAM_PARAM_SETS)) {
+                const uint32_t max_sps = jr.max_sps ? jr.max_sps : 64u, max_pps = jr.max_pps ? jr.max_pps : 64u;
+                const uint32_t *counts = (const uint32_t *)sl->h[12];
+                if (counts[2] > max_sps || counts[3] > max_pps) {
+                    jr.max_sps = counts[2] > max_sps ? counts[2] : max_sps;
+                    jr.max_pps = counts[3] > max_pps ? counts[3] : max_pps;
+                    again = true;
+                }
+            }
+        }
+        if (!again) break;
+        if (attempt >= 2) return set_error(ctx, H264B_E_CAPACITY, "stream: the job's bounds keep falling short");
+        const cudaStream_t saved_stream = ctx->stream;
+        const int saved_bank = ctx->bank;
+        const int slot_idx = (int)(ticket % kStreamSlots);
+        ctx->stream = sl->cs;
+        ctx->bank = 1 + slot_idx;
+        const int32_t rc = stream_submit_on_slot(ctx, &jr, slot_idx, cap);
+        ctx->stream = saved_stream;
+        ctx->bank = saved_bank;
+        if (rc != H264B_OK) return rc;
+        H264B_CUDA(ctx, cudaEventSynchronize(sl->e_out));
+    }
     uint32_t n_slices = *(const uint32_t *)((const uint8_t *)sl->h[5] + 64);
     if (n_slices > sl->job.max_slices) n_slices = sl->job.max_slices;
     void *h_nals = sl->h[0];
@@ -759,11 +805,8 @@ int32_t h264b_stream_wait(h264b_ctx *ctx, uint64_t ticket, h264b_stream_result *
                        ? (const h264b_slice_header *)sl->h[11]
                        : nullptr;
     if (res->headers && (sl->job.flags & H264B_STREAM_PARAM_SETS)) {
-        const uint32_t max_sps = sl->job.max_sps ? sl->job.max_sps : 64u, max_pps = sl->job.max_pps ? sl->job.max_pps : 64u;
+        const uint32_t max_sps = sl->job.max_sps ? sl->job.max_sps : 64u;
         const uint32_t *counts = (const uint32_t *)sl->h[12];
-        if (counts[2] > max_sps || counts[3] > max_pps)
-            return set_error(ctx, H264B_E_CAPACITY, "stream: %u SPS / %u PPS NAL units, job.max_sps / max_pps hold %u / %u",
-                             counts[2], counts[3], max_sps, max_pps);
         res->n_sps = counts[0];
         res->n_pps = counts[1];
         res->sps_nal = counts + 4;

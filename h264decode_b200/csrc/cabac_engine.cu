@@ -22,7 +22,8 @@ namespace h264b {
 #define H264B_CABAC_PIPELINE 1  // fast loop: context state / table entry of a decision requested ahead of time
 #endif
 constexpr int kMaxWarpsPerCta = 20;            // one CTA per SM, five warps per scheduler
-constexpr int kTab16Bytes = 128 * 8 * 16;      // the fast loop's table: 128 states x 8 copies x 16 bytes
+constexpr int kTab16Rows = 130;                // 128 states + the bypass pseudo state 128 (+ 1 spare)
+constexpr int kTab16Bytes = kTab16Rows * 8 * 16; // the fast loops' table: rows x 8 copies x 16 bytes
 constexpr size_t kMaxSmemPerCta = 227 * 1024;  // opt-in maximum of dynamic shared memory per CTA on sm_100
 
 // explicit shared-memory accesses (32-bit shared addresses: no generic-address arithmetic in the inner loop)
@@ -63,7 +64,9 @@ struct CabacArgs {
     const uint32_t *d_n;   // actual slice count on the device (<= j.n_slices, which then is only the bound) or NULL
     uint32_t lanes_per_warp;
     uint32_t n_warps;      // bundles of lanes_per_warp slices
-    uint32_t map_mode;     // 0: warp 0 of a CTA takes its longest bundle, 1: the highest warp does, 2: launch order
+    uint32_t map_mode;     // 0: warp 0 of a CTA takes its longest bundle, 1: the highest warp does, 2: launch order,
+                           // 3: slot_bundle[CTA x warps + warp] (bundle_assign_kernel), -1: none
+    const int32_t *slot_bundle;
 };
 
 // ---------------------------------------------------------------------------------------------- length bundles
@@ -134,6 +137,74 @@ __global__ void __launch_bounds__(256) sort_scatter_kernel(const uint32_t *n_ops
         order[atomicAdd(&s->hist[len_bucket(n_ops[i] < cap ? n_ops[i] : cap, lo, hi)], 1u)] = i;
 }
 
+// ---------------------------------------------------------------------------------------------- bundles -> schedulers
+// One wave of one CTA per SM: warp w of CTA b runs on scheduler (b, w & 3) from start to end, so which bundles share a
+// scheduler decides when the launch ends.  A scheduler is saturated by ~2.2 warps of the fast loop (a lone warp needs
+// ~115 cycles per op, the issue port ~52), so its time is  max(longest bundle x 115, all its ops x 52)  and a few bundles
+// -- the 32 longest slices of 80 000 are 1.9 x the mean -- want a scheduler (almost) to themselves.  Greedy "longest
+// first onto the least loaded scheduler" with such bundles weighted up does that (tools/cabac_assign_model.py has the
+// model next to the measurements: 80 ms -> 62 ms for BASELINE configs[3]).  One warp, ~0.2 ms for 2 500 bundles.
+constexpr int kSlotsMax = 5;  // warps per scheduler = kMaxWarpsPerCta / 4
+
+__global__ void __launch_bounds__(1024) bundle_assign_kernel(const uint32_t *n_ops, const uint32_t *order, uint32_t n_bound,
+                                                             const uint32_t *d_n, uint32_t cap_ops, uint32_t lpw,
+                                                             uint32_t n_sched, uint32_t slots, uint32_t W,
+                                                             int32_t *slot_bundle) {
+    extern __shared__ uint32_t sm_u32[];
+    uint32_t *len = sm_u32;                       // [n_bundles] ops of each bundle (its longest slice)
+    uint32_t *sum = len + n_sched * slots;        // [n_sched] weighted ops placed so far
+    uint32_t *cnt = sum + n_sched;                // [n_sched] bundles placed so far
+    __shared__ unsigned long long total_s;
+    const uint32_t n_slices = d_n && *d_n < n_bound ? *d_n : n_bound;
+    const uint32_t n_bundles = (n_slices + lpw - 1) / lpw;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) total_s = 0;
+    for (uint32_t k = tid; k < n_sched * slots; k += blockDim.x) slot_bundle[k] = -1;
+    for (uint32_t k = tid; k < n_sched; k += blockDim.x) sum[k] = 0, cnt[k] = 0;
+    __syncthreads();
+    unsigned long long part = 0;
+    for (uint32_t g = tid; g < n_bundles; g += blockDim.x) {
+        uint32_t m = 0;
+        for (uint32_t l = 0; l < lpw && g * lpw + l < n_slices; l++) {
+            const uint32_t v = n_ops[order[g * lpw + l]];
+            m = max(m, v < cap_ops ? v : cap_ops);
+        }
+        len[g] = m;
+        part += m;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, d);
+    if (lane == 0 && part) atomicAdd(&total_s, part);
+    __syncthreads();
+    if (tid >= 32) return;
+    // a bundle whose own chain (x 2.2) comes near the balanced load of a scheduler counts 1.5 times
+    const unsigned long long critical = total_s * 4 / (5ull * n_sched);  // 0.8 x total / schedulers
+    uint32_t my_min = 0xFFFFFFFFu, my_arg = 0;  // least loaded scheduler among this lane's (lane, lane + 32, ...)
+    for (uint32_t k = lane; k < n_sched; k += 32)
+        if (my_min == 0xFFFFFFFFu) my_min = 0, my_arg = k;
+    for (uint32_t g = 0; g < n_bundles; g++) {  // bundles come longest first
+        // least loaded scheduler of all (ties: the lowest index)
+        unsigned long long key = ((unsigned long long)my_min << 32) | my_arg;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, d);
+            key = o < key ? o : key;
+        }
+        const uint32_t sidx = (uint32_t)key;
+        const uint32_t L = len[g];
+        if ((sidx & 31u) == (uint32_t)lane) {  // its owner places the bundle and looks for its new minimum
+            const uint32_t kpos = cnt[sidx];
+            slot_bundle[(sidx >> 2) * W + kpos * 4 + (sidx & 3u)] = (int32_t)g;
+            cnt[sidx] = kpos + 1;
+            const uint32_t wgt = ((unsigned long long)L * 11 / 5 > critical) ? L + L / 2 : L;
+            sum[sidx] = kpos + 1 >= slots ? 0xFFFFFFF0u : sum[sidx] + wgt;
+            my_min = 0xFFFFFFFFu;
+            for (uint32_t k = lane; k < n_sched; k += 32)
+                if (sum[k] < my_min) my_min = sum[k], my_arg = k;
+        }
+    }
+}
+
 __device__ __forceinline__ int idc_class_dev(int idc) { return (idc >= -1 && idc <= 2) ? idc + 1 : 4; }
 __device__ __forceinline__ int clip3_dev(int x, int y, int z) { return z < x ? x : (z > y ? y : z); }
 
@@ -176,12 +247,15 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(C
             s_tab_fast[i] = (e & 0x00FF00FFFFFFFFFFull) | ((e & 0x0100010000000000ull) << 7);
         }
     } else {
-        for (int i = tid; i < 1024; i += blockDim.x) s_tab16[i] = entry16(a.tab[i >> 3]);
+        for (int i = tid; i < kTab16Rows * 8; i += blockDim.x) {
+            // rows 128..: the bypass pseudo state (kLoop 2): rangeLPS 0, shift 0, next state 128 either way, bins (0, 1)
+            s_tab16[i] = (i >> 3) < 128 ? entry16(a.tab[i >> 3]) : make_uint4(0u, 0u, 0x80800080u, 0xFFFFFFFFu);
+        }
     }
     __syncthreads();
     const h264b_cabac_job &j = a.j;
     const uint32_t n_ctx = j.n_ctx;
-    uint8_t *s_state = s_state_all + (size_t)warp * n_ctx * 32;
+    uint8_t *s_state = s_state_all + (size_t)warp * (n_ctx + 2) * 32;  // (+ 2: kLoop 2's bypass pseudo contexts)
     const uint32_t n_slices = a.d_n && *a.d_n < j.n_slices ? *a.d_n : j.n_slices;
     const uint32_t n_bundles = (n_slices + a.lanes_per_warp - 1) / a.lanes_per_warp;
 
@@ -190,7 +264,8 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(C
     // spread over all SMs and sit on the warps the issue arbiter prefers (map_mode 1: the highest warp of a CTA takes
     // its longest bundle).  More bundles than one wave holds: small CTAs in launch order.
     const uint32_t rank = a.map_mode == 1 ? (W - 1u - (uint32_t)warp) : (uint32_t)warp;
-    const uint32_t gw = a.map_mode == 2 ? blockIdx.x * W + (uint32_t)warp : rank * gridDim.x + blockIdx.x;
+    uint32_t gw = a.map_mode == 2 ? blockIdx.x * W + (uint32_t)warp : rank * gridDim.x + blockIdx.x;
+    if (a.map_mode == 3) gw = (uint32_t)a.slot_bundle[blockIdx.x * W + (uint32_t)warp];  // (-1 -> no bundle)
     if (gw >= n_bundles) return;
     const uint32_t index = gw * a.lanes_per_warp + lane;
     // Lanes without a slice of their own (a partly filled warp) shadow the warp's first lane: they decode the same
@@ -210,6 +285,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(C
     if ((uint64_t)len > j.total_bytes - off) len = (uint32_t)(j.total_bytes - off), bad_range = true;
     // initial context states: given, or the K4 rule (state LUT row of this slice's (idc class, clipped qp))
     uint32_t st_or = 0;
+    bool st_63 = false;  // a caller-given pStateIdx 63 (rangeLPS 2: seven renormalisation shifts; unreachable otherwise)
     {
         const uint8_t *src;
         if (j.init_states) {
@@ -221,6 +297,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(C
         for (uint32_t c = 0; c < n_ctx; c++) {
             const uint8_t v = src[c];
             st_or |= v;
+            st_63 |= (v & 63u) == 63u;
             s_state[c * 32 + lane] = v;
         }
     }
@@ -236,6 +313,62 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(C
     uint32_t *bins = j.bins + (j.bins_off ? (size_t)j.bins_off[slice] : (size_t)slice * j.bins_stride_words);
     uint32_t word = 0;
     uint32_t i = 0;
+    bool live = true;  // this lane's slice is not finished (kLoop 2 finishes lanes one by one, see below)
+    // one op of the generic form (any engine, any lane state) for the lanes that ask for it
+    const auto generic_op = [&](uint32_t at, uint32_t op, bool active) {
+        if (__any_sync(0xFFFFFFFFu, active && eng.must_refill())) {
+            if (active) eng.refill_if_room();
+        }
+        const uint32_t kind = op >> 14;
+        uint32_t bin = 0;
+        if (kind == H264B_OP_DECISION) {
+            uint32_t c = op & 0x3FFu;
+            if (c >= n_ctx) c = 0;
+            uint8_t *sp = s_state + c * 32 + lane;
+            if (active) {
+                const uint64_t e = s_tab[*sp & 127u];
+                uint8_t ns;
+                bin = eng.decision(e, &ns);
+                *sp = ns;
+            }
+        } else if (kind == H264B_OP_BYPASS) {
+            if (active) bin = eng.bypass();
+        } else {
+            if (active) bin = eng.terminate();
+        }
+        if (active) {  // a lane that has finished keeps its last partial word for finish_lane()
+            word |= bin << (at & 31u);
+            if ((at & 31u) == 31u) {
+                if (own) bins[at >> 5] = word;
+                word = 0;
+            }
+        }
+    };
+    // the end of a lane's slice: optional final DecodeTerminate, flush, final record
+    const auto finish_lane = [&]() {
+        if (!own) return;
+        uint32_t n_bins = my_ops;
+        if (j.flags & H264B_CABAC_FINAL_TERMINATE) {
+            if (eng.must_refill()) eng.refill_if_room();
+            const uint32_t bin = eng.terminate();
+            word |= bin << (my_ops & 31u);  // `word` holds bins (my_ops & ~31) .. my_ops-1 (empty after a flush)
+            n_bins++;
+        }
+        if (n_bins & 31u) bins[n_bins >> 5] = word;
+        else if ((j.flags & H264B_CABAC_FINAL_TERMINATE) && (n_bins & 31u) == 0) bins[(n_bins - 1) >> 5] = word;
+        h264b_cabac_final f;
+        const uint64_t bits_read = eng.bits_read();
+        f.cod_i_range = eng.cod_i_range();
+        f.cod_i_offset = eng.cod_i_offset();
+        f.bits_read = bits_read;
+        f.flags = (bits_read > 8ull * len || bad_range) ? H264B_F_OVERRUN : 0u;
+        f.n_bins = n_bins;
+        j.final[slice] = f;
+        if (j.final_states) {
+            uint8_t *dst = j.final_states + (size_t)slice * n_ctx;
+            for (uint32_t c = 0; c < n_ctx; c++) dst[c] = s_state[c * 32 + lane];
+        }
+    };
     // ---- fast loop: blocks of 32 ops (one word of bins) while every lane of the warp is active and on the window
     // engine -- the usual case for all but the tail of a length bundle.  Same arithmetic as CabacLane::decision /
     // bypass / terminate.  A warp's time is its serial chain codIRange / codIOffset -> next bin plus every taken branch
@@ -250,6 +383,273 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(C
     //   * refills are checked once per two ops (16 bits cover two decisions).
     // (every condition that steers the loop is a vote result: the compiler then knows the warp stays converged and
     //  emits the shuffles and votes inside without divergence checks)
+    if (kLoop == 2) {
+      // kLoop 2: no branch inside a chunk of 8 ops, and as few instructions as the arithmetic allows.  A lone warp -- the
+      // long slices at the end of a launch, or a launch of a few slices -- pays ~28 cycles for every predicate -> taken
+      // branch and the static waits of predicated-off code all the same (ncu: profiles/r2_lone_*_sass.txt), and the
+      // op-kind dispatch plus the refill vote of the branchy loops take 2 - 3 branches per op.  Here
+      //  * a bypass is a decision on a pseudo context: its row holds the state byte 128 for ever, table entry 128 has
+      //    rangeLPS 0, shift 0, bins (0, 1) and an all-ones word w that keeps codIRange on the "LPS" side; the window's
+      //    bypass shift rides on the renormalisation shift of the op BEFORE it (bit 7 of the next op's state byte);
+      //    nothing in the straight line asks for the op kind;
+      //  * the window is 96 bits (codIOffset + up to 86 stream bits), so one warp vote per chunk covers its refills:
+      //    8 ops take at most 8 x 6 + 1 bits (pStateIdx 63, rangeLPS 2, is unreachable: such caller-given states stay
+      //    with the other loops), a lane holding fewer than 49 refills, and with it every lane that has room;
+      //  * row addresses are broadcast three ops ahead (for the state byte fetched two ops ahead) and reused for the
+      //    store; a chunk in which a context comes back within two ops (known from the schedule) runs the variant that
+      //    re-requests what the store has overtaken;
+      //  * the selects on the decision's outcome are written as selp (a predicate used as a guard costs ~10 cycles more
+      //    than one used as data).
+      // Chunks with a terminate op (1 in 48) run op by op.
+      if (__all_sync(0xFFFFFFFFu, !eng.lit && !(st_or & 0x80u) && !st_63) && j.total_bytes < (1ull << 33)) {
+        CabacLane &w = eng.w;
+        const uint32_t st_lane = opaque(smem_addr(s_state) + (uint32_t)lane);  // &state[0][lane]
+        const uint32_t tabl = opaque(smem_addr(s_tab16) + (uint32_t)(lane & 7) * 16u);
+        const uint32_t sel_mps = opaque(0x1440u), sel_lps = opaque(0x3442u);  // byte-permute selectors, kept in registers
+        // two bypass rows, for ops at even / odd positions: neighbouring bypass ops never look like one context
+        sts_u8(st_lane + n_ctx * 32u, 128u);
+        sts_u8(st_lane + n_ctx * 32u + 32u, 128u);
+        // window: hi = codIOffset (10 bits) | 22 stream bits, mid, lo = the next 64; fbits of them are valid
+        uint32_t R22, hi, mid, lo;
+        int32_t fbits;
+        // the bit feed as a word index, two words ahead: pf0 = words[widx], pf1 = words[widx + 1] (indices clamped)
+        const uint32_t *words = reinterpret_cast<const uint32_t *>(j.bytes);
+        const uint32_t last_idx = (uint32_t)(w.feed.last_word - words);
+        const uint32_t mis8 = w.feed.mis8;
+        uint32_t widx, widx0, refills0, cur, pf0, pf1;
+        const auto enter = [&]() {  // CabacLane -> registers of this loop
+            R22 = w.R << 22, hi = w.hi, mid = w.lo, lo = 0u, fbits = w.fbits;
+            widx = (uint32_t)(w.feed.next - words);
+            widx0 = widx, refills0 = w.refills;
+            cur = w.feed.cur, pf0 = w.feed.pf, pf1 = words[widx + 1u < last_idx ? widx + 1u : last_idx];
+        };
+        const auto leave = [&]() {  // ... and back: a lane holding more than 54 stream bits gives the last 32 back
+            if (fbits > 54) {
+                const uint32_t keep = (uint32_t)(fbits - 32 - 22);  // valid bits that stay in mid (1 .. 32)
+                mid = keep >= 32u ? mid : (mid & ~(0xFFFFFFFFu >> keep));
+                fbits -= 32;
+                widx--;
+            }
+            w.R = R22 >> 22, w.hi = hi, w.lo = mid, w.fbits = fbits;
+            w.refills = refills0 + (widx - widx0);
+            w.feed.next = words + widx;
+            const uint32_t prev = widx ? widx - 1u : 0u;
+            w.feed.cur = bswap32(words[prev < last_idx ? prev : last_idx]);
+            w.feed.pf = words[widx < last_idx ? widx : last_idx];
+        };
+        const auto next32 = [&]() -> uint32_t {  // the next 32 stream bits; the feed moves on one word
+            const uint32_t nxt = bswap32(pf0);
+            const uint32_t v = funnel_l(nxt, cur, mis8);
+            cur = nxt;
+            pf0 = pf1;
+            widx++;
+            pf1 = words[widx + 1u < last_idx ? widx + 1u : last_idx];
+            return v;
+        };
+        const auto refill_chunk = [&]() {  // every lane that has room; a lane below 23 twice (rare)
+            if (fbits <= 22) {
+                const uint32_t v = next32();
+                const uint32_t s = (uint32_t)(22 - fbits);
+                hi |= funnel_l(v, 0u, s);  // v >> (32 - s), 0 for s == 0
+                mid |= v << s;
+                fbits += 32;
+            }
+            if (fbits <= 54) {  // (> 22 here)
+                const uint32_t v = next32();
+                const uint32_t t = (uint32_t)(fbits - 22);  // 1 .. 32
+                mid |= __funnelshift_rc(v, 0u, t);          // v >> t, 0 for t == 32
+                lo |= __funnelshift_rc(0u, v, t);           // v << (32 - t)
+                fbits += 32;
+            }
+        };
+        const auto shift3 = [&](uint32_t k) {
+            hi = __funnelshift_l(mid, hi, k);
+            mid = __funnelshift_l(lo, mid, k);
+            lo <<= k;
+            fbits -= (int32_t)k;
+        };
+        bool left = false;
+        uint4 e_cur = make_uint4(0u, 0u, 0u, 0u);  // table entry of the op at hand
+        uint32_t s1 = 0;                           // state byte of the op after it
+        uint32_t a0 = 0, a1 = 0, a2 = 0;           // state addresses of the op at hand and of the two after it
+        // A lane whose slice ends before the warp's longest one finishes on its own (the < 32 ops that do not fill a block
+        // op by op, then its final record) and rides along from there, decoding on without storing anything: the block
+        // loop goes on for the other lanes.  (The 32 longest slices of a launch differ by tens of per cent.)
+        for (;;) {
+        enter();
+        uint32_t next_op = i + (uint32_t)lane < j.n_ops_max ? (uint32_t)j.ops[i + (uint32_t)lane] : 0u;
+        while (!left && __all_sync(0xFFFFFFFFu, !live || i + 32u <= my_ops) && __any_sync(0xFFFFFFFFu, live)) {
+            const uint32_t my_op = next_op;
+            next_op = i + 32u + (uint32_t)lane < j.n_ops_max ? (uint32_t)j.ops[i + 32u + (uint32_t)lane] : 0u;
+            const uint32_t my_kind = my_op >> 14;
+            const uint32_t dec_mask = __ballot_sync(0xFFFFFFFFu, my_kind == H264B_OP_DECISION);
+            const uint32_t byp_mask = __ballot_sync(0xFFFFFFFFu, my_kind == H264B_OP_BYPASS);
+            const uint32_t trm_mask = ~(dec_mask | byp_mask);
+            uint32_t my_row = (my_kind == H264B_OP_DECISION ? ((my_op & 0x3FFu) < n_ctx ? (my_op & 0x3FFu) : 0u)
+                                                            : n_ctx + ((uint32_t)lane & 1u)) * 32u;
+            // op p stores the state that the requests already made for op p + 1 / p + 2 have read
+            const uint32_t r1 = __shfl_down_sync(0xFFFFFFFFu, my_row, 1), r2 = __shfl_down_sync(0xFFFFFFFFu, my_row, 2);
+            const uint32_t haz_mask = __ballot_sync(0xFFFFFFFFu, my_kind == H264B_OP_DECISION &&
+                                                                     ((lane < 31 && r1 == my_row) || (lane < 30 && r2 == my_row)));
+            // per chunk c: bit c = holds a terminate op (runs op by op), bit 4 + c = a context comes back within two ops
+            uint32_t chunk_flags = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                chunk_flags |= (((trm_mask >> (8 * c)) & 0xFFu) ? 1u << c : 0u) | (((haz_mask >> (8 * c)) & 0xFFu) ? 16u << c : 0u);
+            bool primed = false;  // e_cur / s1 / a0 / a1 / a2 are those of the op at hand (straight-line chunks hand them on)
+            uint32_t k = 0;
+#pragma unroll 1
+            for (uint32_t k8 = 0; k8 < 32u && !left; k8 += 8u) {
+                const uint32_t row8 = my_row;  // lanes 0..7: this chunk's ops, lanes 8..10: the next chunk's first three
+                my_row = __shfl_sync(0xFFFFFFFFu, my_row, (lane + 8) & 31);
+                const uint32_t cf = chunk_flags >> (k8 >> 3);
+                if (__any_sync(0xFFFFFFFFu, fbits < 49)) {
+                    __syncwarp();  // (keeps this block a branch: predicated off it would still pay its static waits)
+                    refill_chunk();
+                }
+                if (cf & 1u) {  // ---- a chunk with a terminate op: op by op, nothing in flight
+                    const uint32_t dm = dec_mask >> k8, bm = byp_mask >> k8;
+#pragma unroll 1
+                    for (uint32_t u = 0; u < 8u; u++) {
+                        const uint32_t row = __shfl_sync(0xFFFFFFFFu, row8, (int)u);
+                        if ((dm >> u) & 1u) {
+                            const uint32_t addr = row + st_lane;
+                            const uint4 e = lds_u32x4(tabl + lds_u8(addr) * 128u);
+                            const uint32_t q4 = R22 >> 28;
+                            const uint32_t lps22 = prmt(0u, e.x, q4) << 22;
+                            const uint32_t sh_lps = prmt(0u, e.y, q4);
+                            const uint32_t rm22 = R22 - lps22;
+                            const bool is_lps = hi >= rm22;
+                            const uint32_t sh = is_lps ? sh_lps : ((rm22 >> 30) ^ 1u);
+                            const uint32_t r22 = is_lps ? lps22 : rm22;
+                            hi = is_lps ? hi - rm22 : hi;
+                            const uint32_t sel = prmt(e.z, 0u, is_lps ? sel_lps : sel_mps);
+                            sts_u8(addr, sel);
+                            R22 = r22 << sh;
+                            shift3(sh);
+                            word = __funnelshift_l(sel, word, 1);
+                        } else if ((bm >> u) & 1u) {
+                            shift3(1u);
+                            const bool one = hi >= R22;
+                            if (one) hi -= R22;
+                            word = (word << 1) | (one ? 1u : 0u);
+                        } else {  // DecodeTerminate (CabacLane::terminate on this window)
+                            R22 -= 2u << 22;
+                            const uint32_t bin = (hi >= R22 && live) ? 1u : 0u;  // (a lane that rides along: whatever)
+                            if (!bin) {
+                                const uint32_t sh = (uint32_t)__clz((int)R22) - 1u;
+                                R22 <<= sh;
+                                shift3(sh);
+                            }
+                            word = (word << 1) | bin;
+                            if (__any_sync(0xFFFFFFFFu, bin)) {  // a slice that goes on after its end: the generic loop takes over
+                                left = true;
+                                k = k8 + u + 1u;
+                                break;
+                            }
+                        }
+                    }
+                    primed = false;
+                    continue;
+                }
+                // ---- the straight line
+                const bool hand_on = k8 < 24u && !((cf >> 1) & 1u);  // the next chunk of this block runs here too
+                const uint32_t pre_mask = hand_on ? 1u : 0u;
+                if (!primed) {
+                    // the first op's own bypass shift (the op before it ran elsewhere), its entry, and the state byte of
+                    // the second op
+                    shift3((byp_mask >> k8) & 1u);
+                    a0 = __shfl_sync(0xFFFFFFFFu, row8, 0) + st_lane;
+                    a1 = __shfl_sync(0xFFFFFFFFu, row8, 1) + st_lane;
+                    a2 = __shfl_sync(0xFFFFFFFFu, row8, 2) + st_lane;
+                    e_cur = lds_u32x4(tabl + lds_u8(a0) * 128u);
+                    s1 = lds_u8(a1);
+                    primed = true;
+                }
+#define H264B_UNIFIED_OP(u, kHaz)                                                                                        \
+    {                                                                                                                    \
+        const uint32_t a3 = __shfl_sync(0xFFFFFFFFu, row8, (u) + 3) + st_lane; /* address of op u + 3's state */         \
+        uint32_t s2 = lds_u8(a2);                                              /* state byte of op u + 2 */              \
+        const uint4 e = e_cur;                                                                                           \
+        e_cur = lds_u32x4(tabl + s1 * 128u); /* entry of op u + 1, ahead of this op's arithmetic */                      \
+        const uint32_t q4 = R22 >> 28;                                                                                   \
+        const uint32_t lps22 = prmt(0u, e.x, q4) << 22; /* rangeTabLPS[state][q] << 22; bypass: 0 */                     \
+        const uint32_t sh_lps = prmt(0u, e.y, q4);      /* bypass: 0 */                                                  \
+        const uint32_t rm22 = R22 - lps22;                                                                               \
+        const uint32_t r_lps = lps22 | (R22 & e.w);     /* a bypass keeps codIRange either way */                        \
+        const uint32_t sh_mps = (rm22 >> 30) ^ 1u;      /* codIRange - rangeLPS >= 128: at most one doubling */           \
+        const uint32_t hi_lps = hi - rm22;                                                                               \
+        uint32_t r22, sh, selr;                                                                                          \
+        asm("{\n\t.reg .pred p;\n\t"                                                                                     \
+            "setp.ge.u32 p, %3, %4;\n\t"                                                                                 \
+            "selp.u32 %0, %5, %4, p;\n\t"                                                                                \
+            "selp.u32 %1, %6, %7, p;\n\t"                                                                                \
+            "selp.u32 %2, %8, %9, p;\n\t"                                                                                \
+            "selp.u32 %3, %10, %3, p;\n\t}"                                                                              \
+            : "=r"(r22), "=r"(sh), "=r"(selr), "+r"(hi)                                                                  \
+            : "r"(rm22), "r"(r_lps), "r"(sh_lps), "r"(sh_mps), "r"(sel_lps), "r"(sel_mps), "r"(hi_lps));                 \
+        const uint32_t sel = prmt(e.z, 0u, selr); /* next state | bin << 31 */                                           \
+        sts_u8(a0, sel);                                                                                                 \
+        if (kHaz) { /* this context again within two ops: what the store has overtaken is asked for again */             \
+            if (a1 == a0) e_cur = lds_u32x4(tabl + (sel & 0xFFu) * 128u);                                                \
+            if (a2 == a0) s2 = sel & 0xFFu;                                                                              \
+        }                                                                                                                \
+        R22 = r22 << sh;                                                                                                 \
+        /* + the bypass shift of the op that follows (state byte 128) */                                                 \
+        const uint32_t sht = sh + ((u) == 7 ? ((s1 >> 7) & pre_mask) : (s1 >> 7));                                       \
+        shift3(sht);                                                                                                     \
+        word = __funnelshift_l(sel, word, 1);                                                                            \
+        s1 = s2;                                                                                                         \
+        a0 = a1;                                                                                                         \
+        a1 = a2;                                                                                                         \
+        a2 = a3;                                                                                                         \
+    }
+                if (!(cf & 16u)) {
+                    H264B_UNIFIED_OP(0, false) H264B_UNIFIED_OP(1, false) H264B_UNIFIED_OP(2, false)
+                    H264B_UNIFIED_OP(3, false) H264B_UNIFIED_OP(4, false) H264B_UNIFIED_OP(5, false)
+                    H264B_UNIFIED_OP(6, false) H264B_UNIFIED_OP(7, false)
+                } else {
+                    H264B_UNIFIED_OP(0, true) H264B_UNIFIED_OP(1, true) H264B_UNIFIED_OP(2, true)
+                    H264B_UNIFIED_OP(3, true) H264B_UNIFIED_OP(4, true) H264B_UNIFIED_OP(5, true)
+                    H264B_UNIFIED_OP(6, true) H264B_UNIFIED_OP(7, true)
+                }
+#undef H264B_UNIFIED_OP
+                primed = hand_on;
+            }
+            if (!left) {
+                i += 32u;
+                if (own && live) bins[(i >> 5) - 1u] = __brev(word);
+                word = 0;
+            } else {
+                i += k;
+                word = k < 32u ? __brev(word) >> (32u - k) : __brev(word);  // bins 0..k-1 in bits 0..k-1
+                if (k == 32u) {
+                    if (own && live) bins[(i >> 5) - 1u] = word;
+                    word = 0;
+                }
+            }
+        }
+        leave();
+        if (left) {
+            if (live && hi >= R22) eng.to_literal();  // the terminate bin of 1: codIOffset >= codIRange from here on
+            break;
+        }
+        // lanes whose slice ends inside the next block: their last ops one by one, then their final record
+        const bool ending = live && my_ops < i + 32u;
+        if (!__any_sync(0xFFFFFFFFu, ending)) break;  // (no lane is live any more)
+        uint32_t end_at = ending ? my_ops : 0u;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) end_at = max(end_at, __shfl_xor_sync(0xFFFFFFFFu, end_at, d));
+        for (uint32_t at = i; at < end_at; at++) generic_op(at, j.ops[at], ending && at < my_ops);
+        if (ending) {
+            finish_lane();
+            live = false;
+            word = 0;
+        }
+        if (!__any_sync(0xFFFFFFFFu, live) || __any_sync(0xFFFFFFFFu, live && eng.lit)) break;
+        }
+      }
+    } else
     if (kLoop == 1) {
       // kLoop 1.  The serial chain of a decision is  codIRange -> rangeLPS -> compare -> new codIRange: nothing else may
       // sit on it.  (1) The entry of the next decision is requested before this decision's arithmetic, from the state
@@ -518,7 +918,16 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(C
     if (__all_sync(0xFFFFFFFFu, (i & 31u) == 0u && eng.lit && i + 32u <= my_ops)) {  // (i is warp-uniform; a vote says so)
         LiteralLane &l = eng.l;
         const uint32_t st_lane = opaque(smem_addr(s_state) + (uint32_t)lane);
-        const uint32_t tab_fast = opaque(smem_addr(s_tab_fast));
+        // (entry of a state byte: rangeLPS word, next-state word; kLoop 1 keeps them in the replicated 16-byte table, whose
+        //  128 rows need the state byte without a stray bit 7 of caller-given initial states)
+        const uint32_t tab_fast = opaque(kLoop ? smem_addr(s_tab16) + (uint32_t)(lane & 7) * 16u : smem_addr(s_tab_fast));
+        const auto entry_of = [&](uint32_t st) -> uint2 {
+            if (kLoop) {
+                const uint4 v = lds_u32x4(tab_fast + (st & 127u) * 128u);
+                return make_uint2(v.x, v.z);
+            }
+            return lds_u32x2(tab_fast + st * 8u);
+        };
         uint32_t next_op = i + (uint32_t)lane < j.n_ops_max ? (uint32_t)j.ops[i + (uint32_t)lane] : 0u;
         while (__all_sync(0xFFFFFFFFu, i + 32u <= my_ops)) {
             const uint32_t my_op = next_op;
@@ -542,7 +951,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(C
                 const uint32_t rest = dec_mask & (dec_mask - 1u);
                 const uint32_t row_d0 = __shfl_sync(0xFFFFFFFFu, my_row, dec_mask ? __ffs((int)dec_mask) - 1 : 0);
                 const uint32_t row_d1 = __shfl_sync(0xFFFFFFFFu, my_row, rest ? __ffs((int)rest) - 1 : 0);
-                e_cur = lds_u32x2(tab_fast + lds_u8(row_d0 + st_lane) * 8u);
+                e_cur = entry_of(lds_u8(row_d0 + st_lane));
                 s1 = lds_u8(row_d1 + st_lane);
             }
 #pragma unroll 1
@@ -573,7 +982,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(C
                         const uint32_t sel = prmt(e.y, 0u, is_lps ? 0x3442u : 0x1440u);  // next state | bin << 31
                         sts_u8(addr, sel);
                         const uint32_t m1 = (0u - ((f1m >> u) & 1u)) & 0xFFu, m2 = (0u - ((f2m >> u) & 1u)) & 0xFFu;
-                        e_cur = lds_u32x2(tab_fast + ((sel & m1) | (s1 & ~m1)) * 8u);
+                        e_cur = entry_of((sel & m1) | (s1 & ~m1));
                         s1 = (sel & m2) | (s2 & ~m2);
                         l.renorm<false>();
                         word = __funnelshift_l(sel, word, 1);
@@ -590,63 +999,16 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(C
         }
     }
     // ---- generic loop: lanes that have finished, lanes on the literal engine
+    warp_ops = live ? my_ops : 0u;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) warp_ops = max(warp_ops, __shfl_xor_sync(0xFFFFFFFFu, warp_ops, d));
     uint32_t next_op = i < warp_ops ? j.ops[i] : 0;
     for (; i < warp_ops; i++) {
         const uint32_t op = next_op;
         if (i + 1 < warp_ops) next_op = j.ops[i + 1];
-        const bool active = i < my_ops;
-        if (__any_sync(0xFFFFFFFFu, active && eng.must_refill())) {
-            if (active) eng.refill_if_room();
-        }
-        const uint32_t kind = op >> 14;
-        uint32_t bin = 0;
-        if (kind == H264B_OP_DECISION) {
-            uint32_t c = op & 0x3FFu;
-            if (c >= n_ctx) c = 0;
-            uint8_t *sp = s_state + c * 32 + lane;
-            if (active) {
-                const uint64_t e = s_tab[*sp & 127u];
-                uint8_t ns;
-                bin = eng.decision(e, &ns);
-                *sp = ns;
-            }
-        } else if (kind == H264B_OP_BYPASS) {
-            if (active) bin = eng.bypass();
-        } else {
-            if (active) bin = eng.terminate();
-        }
-        if (active) {  // a lane that has finished keeps its last partial word for the tail below
-            word |= bin << (i & 31u);
-            if ((i & 31u) == 31u) {
-                if (own) bins[i >> 5] = word;
-                word = 0;
-            }
-        }
+        generic_op(i, op, live && i < my_ops);
     }
-    // ---- tail: optional final DecodeTerminate, flush, final record
-    if (own) {
-        uint32_t n_bins = my_ops;
-        if (j.flags & H264B_CABAC_FINAL_TERMINATE) {
-            if (eng.must_refill()) eng.refill_if_room();
-            const uint32_t bin = eng.terminate();
-            word |= bin << (my_ops & 31u);  // `word` holds bins (my_ops & ~31) .. my_ops-1 (empty after a flush)
-            n_bins++;
-        }
-        if (n_bins & 31u) bins[n_bins >> 5] = word;
-        else if ((j.flags & H264B_CABAC_FINAL_TERMINATE) && (n_bins & 31u) == 0) bins[(n_bins - 1) >> 5] = word;
-        h264b_cabac_final f;
-        const uint64_t bits_read = eng.bits_read();
-        f.cod_i_range = eng.cod_i_range();
-        f.cod_i_offset = eng.cod_i_offset();
-        f.bits_read = bits_read;
-        f.flags = (bits_read > 8ull * len || bad_range) ? H264B_F_OVERRUN : 0u;
-        f.n_bins = n_bins;
-        j.final[slice] = f;
-        if (j.final_states) {
-            uint8_t *dst = j.final_states + (size_t)slice * n_ctx;
-            for (uint32_t c = 0; c < n_ctx; c++) dst[c] = s_state[c * 32 + lane];
-        }
-    }
+    if (live) finish_lane();
 }
 
 static int env_int(const char *name, int dflt) {
@@ -665,8 +1027,8 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
         return set_error(ctx, H264B_E_INVALID, "cabac: bins_stride_words too small");
     if ((uintptr_t)j.bytes & 3) return set_error(ctx, H264B_E_INVALID, "cabac: bytes must be 4-byte aligned");
     // measurement knobs (tools/cabac_balance_exp.py); the defaults are the shipped configuration
-    const int k_loop = env_int("H264B_CABAC_LOOP", 1), k_w = env_int("H264B_CABAC_W", 0),
-              k_map = env_int("H264B_CABAC_MAP", 1);
+    const int k_loop = env_int("H264B_CABAC_LOOP", 2), k_w = env_int("H264B_CABAC_W", 0),
+              k_map = env_int("H264B_CABAC_MAP", 3);
     const int v = (j.flags & H264B_TABLES_SPEC) ? 1 : 0;
     CabacArgs a;
     a.j = j;
@@ -687,7 +1049,7 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
     // One wave of one CTA per SM with W warps, each warp with its own n_ctx x 32 bytes of context rows; what does not fit
     // one wave runs as small CTAs in launch order (the hardware hands them out as earlier ones finish).
     const size_t tab_bytes = 1024 + (k_loop ? kTab16Bytes : 2048);
-    uint32_t w_fit = (uint32_t)((kMaxSmemPerCta - tab_bytes) / ((size_t)j.n_ctx * 32));
+    uint32_t w_fit = (uint32_t)((kMaxSmemPerCta - tab_bytes) / ((size_t)(j.n_ctx + 2) * 32));
     if (w_fit > (uint32_t)kMaxWarpsPerCta) w_fit = kMaxWarpsPerCta;
     uint32_t W = (a.n_warps + sms - 1) / sms;
     if (k_w > 0) W = (uint32_t)k_w;
@@ -697,10 +1059,22 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
         a.map_mode = 2;
     }
     if (W < 1) W = 1;
-    const uint32_t grid = (a.n_warps + W - 1) / W;
+    uint32_t grid = (a.n_warps + W - 1) / W;
+    // bundles -> schedulers by bundle_assign_kernel: one wave of full CTAs with a slot to spare on every scheduler
+    uint32_t slots = (a.n_warps + sms * 4 - 1) / (sms * 4) + 1;
+    if (slots > (uint32_t)kSlotsMax) slots = kSlotsMax;
+    const bool assign = a.map_mode == 3 && lpw > 1 && j.n_ops && slots * 4 <= w_fit && a.n_warps <= (uint64_t)sms * 4 * slots &&
+                        a.n_warps > sms * 4;
+    if (a.map_mode == 3 && !assign) a.map_mode = 1;
+    if (assign) {
+        W = slots * 4;
+        grid = sms;
+    }
+    a.slot_bundle = nullptr;
     if (lpw > 1 && j.n_ops) {  // bundles of equally long slices
         void *d_sort;
-        int rc = ensure_dev(ctx, 16, sizeof(SortScratch) + (size_t)j.n_slices * 4, &d_sort);
+        const size_t order_bytes = ((size_t)j.n_slices * 4 + 15) & ~(size_t)15;
+        int rc = ensure_dev(ctx, 16, sizeof(SortScratch) + order_bytes + (size_t)sms * 4 * kSlotsMax * 4, &d_sort);
         if (rc) return rc;
         SortScratch *ss = (SortScratch *)d_sort;
         uint32_t *order = (uint32_t *)(ss + 1);
@@ -716,9 +1090,20 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
         sort_scatter_kernel<<<sb, 256, 0, ctx->stream>>>(j.n_ops, j.n_slices, d_n_slices, j.n_ops_max, ss, order);
         H264B_LAUNCH_CHECK(ctx, "sort_scatter_kernel");
         a.order = order;
+        if (assign) {
+            int32_t *slot_bundle = (int32_t *)((uint8_t *)order + order_bytes);
+            const size_t sm_assign = ((size_t)sms * 4 * slots + 2 * (size_t)sms * 4) * 4;
+            bundle_assign_kernel<<<1, 1024, sm_assign, ctx->stream>>>(j.n_ops, order, j.n_slices, d_n_slices, j.n_ops_max, lpw,
+                                                                     sms * 4, slots, W, slot_bundle);
+            H264B_LAUNCH_CHECK(ctx, "bundle_assign_kernel");
+            a.slot_bundle = slot_bundle;
+        }
     }
-    const size_t smem = tab_bytes + (size_t)W * j.n_ctx * 32;
-    if (k_loop) {
+    const size_t smem = tab_bytes + (size_t)W * (j.n_ctx + 2) * 32;
+    if (k_loop == 2) {
+        H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cabac_decode_kernel<2><<<grid, W * 32, smem, ctx->stream>>>(a);
+    } else if (k_loop) {
         H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cabac_decode_kernel<1><<<grid, W * 32, smem, ctx->stream>>>(a);
     } else {

@@ -118,6 +118,6 @@ int launch_parse_pps(h264b_ctx *ctx, const uint8_t *d_bytes, uint64_t total, con
                      h264b_pps *d_out);
 int launch_slice_select(h264b_ctx *ctx, const h264b_nal *d_nals, const h264b_scan_summary *d_summary,
                         uint32_t nal_cap, uint32_t slice_data_offset, uint32_t max_slices, uint64_t *d_off,
-                        uint32_t *d_len, uint32_t *d_slice_nal, uint32_t *d_n_slices);
+                        uint32_t *d_len, uint32_t *d_slice_nal, uint32_t *d_n_slices, uint32_t *d_n_found = nullptr);
 
 }  // namespace h264b

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(1024) pset_select_kernel(const h264b_nal *nals
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint64_t n = summary->n_nals;
     if (n > nal_cap) n = nal_cap;
+    if (summary->status != H264B_OK) n = 0;  // an incomplete index holds no records at all
     if (tid < 2) base[tid] = 0;
     __syncthreads();
     for (uint64_t k0 = 0; k0 < n; k0 += 1024) {

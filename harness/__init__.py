@@ -208,7 +208,7 @@ def build_gpu(force=False):
     os.makedirs(os.path.dirname(_GPU_LIB_PATH), exist_ok=True)
     nvcc = "/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc"
     subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-                           "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared", "-o", _GPU_LIB_PATH,
+                           "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared", "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-o", _GPU_LIB_PATH,
                            srcs[0]])
     return _GPU_LIB_PATH
 

@@ -153,3 +153,84 @@ def test_raw_stream_pipeline_at_scale():
     for other in rs[:2]:
         assert np.array_equal(other["headers"], r["headers"]) and np.array_equal(other["final"], r["final"])
         assert np.array_equal(other["bins_flat"], r["bins_flat"])
+
+
+@pytest.mark.parametrize("bypass_spec_or", [True, False])
+@pytest.mark.parametrize("tables_spec", [False, True])
+def test_config1_full_size_64_slices_x_100k_bins(bypass_spec_or, tables_spec):
+    """configs[1] at its stated size: 64 independent slices x 100 000 bins (test-encoder generated, one shared op
+    schedule of mixed decision / bypass / terminate ops, 64 active contexts), every bin, every final
+    (codIRange, codIOffset, bitsRead) and every final context state against the oracle, for both bypass forms and both
+    table sets.  (The encoder codes for the SPEC_OR bypass form; under the reference's own bypass form the same bytes are
+    just bytes, which the literal engine and the oracle must still decode alike, overruns included.)"""
+    from h264decode_b200 import capi
+    n_slices, n_bins, n_active, n_ctx = 64, 100_000, 64, 64
+    fo = (orc.BYPASS_SPEC_OR if bypass_spec_or else 0) | (orc.TABLES_SPEC if tables_spec else 0)
+    fg = (capi.BYPASS_SPEC_OR if bypass_spec_or else 0) | (capi.TABLES_SPEC if tables_spec else 0) | capi.CABAC_FINAL_TERMINATE
+    ops = hz.gen_schedule(2, n_bins, n_active)
+    n_ops = np.full(n_slices, n_bins, np.uint32)
+    qp, idc = hz.slice_params(n_slices, first=7)
+    g = hz.gen_cabac_slices(2, ops, n_ops, n_active, n_ctx, qp, idc, flags=hz.TABLES_SPEC if tables_spec else 0)
+    stride = g["data"].shape[1]
+    data = np.concatenate([g["data"].reshape(-1), np.zeros(64, np.uint8)])
+    off = np.arange(n_slices, dtype=np.uint64) * stride
+    length = g["lens"].astype(np.uint32)
+    ctx = capi.Context(0)
+    try:
+        bins, fin, fst = ctx.cabac_decode(data, off, length, ops, n_ops, n_ctx, qp=qp, idc=idc, flags=fg)
+    finally:
+        ctx.close()
+    init = orc.ctx_init(qp, idc, n_ctx, fo & orc.TABLES_SPEC)
+    term = np.array([orc.make_op(orc.OP_TERMINATE)], np.uint16)
+    full_ops = np.concatenate([ops, term])
+    nw = (n_bins + 1 + 31) // 32
+    for s in range(n_slices):
+        rc, obins, ofin, ost = orc.cabac_decode_slice(data[int(off[s]):int(off[s]) + int(length[s])], full_ops, init[s], fo)
+        assert bool(fin["flags"][s] & capi.F_OVERRUN) == (rc == orc.PANIC), s
+        if rc == orc.PANIC:
+            for w in range(ofin["n_bins"] // 32):
+                assert bins[s][w] == obins[w], (s, w)
+            continue
+        got = bins[s][:nw].copy()
+        got[-1] &= np.uint32((1 << ((n_bins + 1) % 32)) - 1)
+        assert np.array_equal(got, obins[:nw]), "slice %d bins" % s
+        assert (fin["cod_i_range"][s], fin["cod_i_offset"][s], fin["bits_read"][s], fin["n_bins"][s]) == (
+            ofin["codIRange"], ofin["codIOffset"], ofin["bitsRead"], ofin["n_bins"]), s
+        assert np.array_equal(fst[s], ost), "slice %d states" % s
+        if bypass_spec_or:   # self-check: the decoder returns what the encoder coded
+            assert np.array_equal(got, g["bins"][s, :nw]), s
+
+
+def test_streams_of_very_short_nal_units_and_many_parameter_sets():
+    """A stream whose NAL units average far less than 64 bytes (the NAL index of a stream job starts at n / 64 + 1024
+    records) and one with more SPS / PPS NAL units than a job's default bound of 64: both entry points must deliver the
+    oracle's units -- the job re-runs with the bounds its first pass reported -- instead of failing with E_CAPACITY."""
+    from h264decode_b200 import capi
+    rng = np.random.default_rng(77)
+    parts = []
+    for k in range(40000):   # 8- to 11-byte units: start code + header + 3..6 payload bytes
+        parts.append(b"\x00\x00\x00\x01" + bytes([0x41 if k % 3 else 0x65]) + bytes(rng.integers(4, 255, int(rng.integers(3, 7))).astype(np.uint8)))
+    short = np.frombuffer(b"".join(parts) + b"\x00\x00\x00\x01", np.uint8)
+    sps, pps = hz.SPS_NAL, hz.PPS_NAL   # SURVEY.md Appendix B.3: sets the reference parses
+    many = []
+    for k in range(150):
+        many.append(b"\x00\x00\x00\x01" + sps + b"\x00\x00\x00\x01" + pps + b"\x00\x00\x00\x01\x65" + bytes(rng.integers(4, 255, 40).astype(np.uint8)))
+    many = np.frombuffer(b"".join(many) + b"\x00\x00\x00\x01", np.uint8)
+    ctx = capi.Context(0)
+    try:
+        for stream in (short, many):
+            onal, orbsp = orc.read_nal_units_arrays(stream)
+            summ, nals, ext, rbsp = ctx.annexb_scan(stream)
+            assert summ["n_nals"] == len(onal["start"])
+            assert np.array_equal(nals["start"].astype(np.int64), onal["start"])
+            r = ctx.stream_decode(stream, np.zeros(0, np.uint16), None, np.zeros(1, np.int32), np.zeros(1, np.int32), 1)
+            assert r["scan"]["n_nals"] == len(onal["start"])
+            assert np.array_equal(r["nals"]["start"].astype(np.int64), onal["start"])
+            assert np.array_equal(r["nals"]["rbsp_len"].astype(np.int64), onal["rbsp_len"])
+        # the stream's own parameter sets, with the default bounds (64 SPS / 64 PPS) and a slice bound that is too small
+        t = ctx.stream_submit(many, np.zeros(0, np.uint16), None, None, None, 1, flags=capi.STREAM_PARAM_SETS, max_slices=10)
+        r = ctx.stream_wait(*t)
+        assert len(r["sps"]) == 150 and len(r["pps"]) == 150 and len(r["headers"]) == 150
+        assert np.array_equal(r["slice_sps"], np.arange(150)) and np.array_equal(r["slice_pps"], np.arange(150))
+    finally:
+        ctx.close()

@@ -488,10 +488,12 @@ def test_stream_pipeline_takes_parameter_sets_from_the_stream():
         flags = capi.BYPASS_SPEC_OR | capi.CABAC_FINAL_TERMINATE | capi.STREAM_PARAM_SETS
         t = ctx.stream_submit(stream, ops, n_ops, None, None, n_ctx, flags=flags, max_slices=n + 2, max_sps=8, max_pps=8)
         r = ctx.stream_wait(*t)
-        # the bounds are enforced
-        with pytest.raises(capi.H264BError):
-            ctx.stream_wait(*ctx.stream_submit(stream, ops, n_ops, None, None, n_ctx, flags=flags, max_slices=n + 2,
-                                               max_sps=2, max_pps=8))
+        # bounds that fall short are raised to what the run reported and the job runs again: same result
+        r2 = ctx.stream_wait(*ctx.stream_submit(stream, ops, n_ops, None, None, n_ctx, flags=flags, max_slices=n + 2,
+                                                max_sps=2, max_pps=1))
+        assert np.array_equal(r2["sps"], r["sps"]) and np.array_equal(r2["pps"], r["pps"])
+        assert np.array_equal(r2["slice_sps"], r["slice_sps"]) and np.array_equal(r2["slice_pps"], r["slice_pps"])
+        assert np.array_equal(r2["final"], r["final"]) and np.array_equal(r2["bins_flat"], r["bins_flat"])
     finally:
         ctx.close()
     onal, orbsp = orc.read_nal_units_arrays(stream)
