@@ -30,15 +30,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# DRAM bytes (read + write) per algorithmic byte of the Annex-B pass, from the ncu capture of this command line
-# (profiles/r1_ncu_launch_list_bench.csv: dram__bytes_read.sum + dram__bytes_write.sum of the seven kernels of one pass,
-# 7.885 GB against 7.866 GB algorithmic; annexb_copy_kernel alone 7.826 GB, profiles/r1_ncu_copy_kernel_summary.txt)
-TRAFFIC_PER_ALG_BYTE = 1.0024
-TRAFFIC_SOURCE = "ncu dram__bytes_read.sum + dram__bytes_write.sum per pass (profiles/r1_ncu_launch_list_bench.csv)"
 MEAN_BINS = 455_000      # ~50 KB of CABAC data per slice at ~0.88 bit/bin
 N_ACTIVE = 64
 IN_FLIGHT = 3            # H264B_STREAM_JOBS_IN_FLIGHT
-CABAC_WARP_INST_PER_OP = 38.9   # ncu: 44.26 G warp instructions / 1.137 G warp-ops (profiles/r1_ncu_cabac_final2_summary.txt)
 N_CTX = 64
 SLICES_PER_FRAME = 8
 FRAMES_PER_PARAMS = 250
@@ -183,10 +177,104 @@ def config_dict(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def measured_constants():
+    """Numbers this file quotes from ncu captures: profiles/r2_constants.json, written by tools/ncu_constants.py from
+    the committed .ncu-rep summaries together with the commit they were measured at (no constants pasted here)."""
+    p = os.path.join(ROOT, "profiles", "r2_constants.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
+class StepBuffers:
+    """Device buffers of one step in flight and the context (own CUDA stream) that runs it."""
+
+    def __init__(self, torch, capi, dev, local_rank, n, nal_cap, n_slices, total_words):
+        self.ctx = capi.Context(local_rank)
+        self.stream = torch.cuda.Stream(device=dev)
+        assert self.stream.cuda_stream != 0  # (a NULL handle would mean "the context's own stream" to h264b_set_stream)
+        self.ctx.set_stream(self.stream.cuda_stream)
+        self.rbsp = torch.empty(n + 64, dtype=torch.uint8, device=dev)
+        self.nals = torch.empty(nal_cap * 32, dtype=torch.uint8, device=dev)
+        self.sum = torch.zeros(64, dtype=torch.uint8, device=dev)
+        self.off = torch.empty(n_slices, dtype=torch.int64, device=dev)
+        self.len = torch.empty(n_slices, dtype=torch.int32, device=dev)
+        self.snal = torch.empty(n_slices, dtype=torch.int32, device=dev)
+        self.ns = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.bins = torch.zeros(total_words, dtype=torch.int32, device=dev)
+        self.fin = torch.empty(n_slices * 32, dtype=torch.uint8, device=dev)
+
+
+def verify_slices(torch, capi, orc, buf, d_stream, which, ops, n_ops, qp, idc, boff, flags, threads):
+    """Full comparison of the chosen slices with the oracle: the NAL unit's RBSP bytes (NewNalUnit on the unit's own
+    stream bytes), every bin, the final (codIRange, codIOffset, bitsRead).  Returns the number of slices that agree."""
+    from concurrent.futures import ThreadPoolExecutor
+    nals = np.frombuffer(buf.nals.cpu().numpy().tobytes(), dtype=capi.NAL_DTYPE)
+    snal = buf.snal.cpu().numpy()
+    fin = np.frombuffer(buf.fin.cpu().numpy().tobytes(), dtype=capi.FINAL_DTYPE)
+    term = np.array([orc.make_op(orc.OP_TERMINATE)], np.uint16)
+    fo = orc.BYPASS_SPEC_OR if flags & capi.BYPASS_SPEC_OR else 0
+    jobs = []
+    for s in which:
+        u = nals[snal[s]]
+        unit = d_stream[int(u["start"]):int(u["start"]) + int(u["num_bytes"])].cpu().numpy()
+        rb = buf.rbsp[int(u["rbsp_off"]):int(u["rbsp_off"]) + int(u["rbsp_len"])].cpu().numpy()
+        bins = buf.bins[int(boff[s]):int(boff[s + 1])].cpu().numpy().view(np.uint32)
+        jobs.append((int(s), unit, rb, bins))
+
+    def check(job):
+        s, unit, rb, bins = job
+        st, _, orb = orc.new_nal_unit(unit)
+        if st != orc.OK or orb != rb.tobytes():
+            return False
+        init = orc.ctx_init(qp[s:s + 1], idc[s:s + 1], N_CTX)[0]
+        rc, obins, ofin, _ = orc.cabac_decode_slice(rb, np.concatenate([ops[:n_ops[s]], term]), init, fo)
+        nb = int(n_ops[s]) + 1
+        nw = (nb + 31) // 32
+        got = bins[:nw].copy()
+        if nb % 32:
+            got[-1] &= np.uint32((1 << (nb % 32)) - 1)
+        f = fin[s]
+        return bool(rc == orc.OK and np.array_equal(got, obins[:nw]) and
+                    (int(f["cod_i_range"]), int(f["cod_i_offset"]), int(f["bits_read"]), int(f["n_bins"])) ==
+                    (ofin["codIRange"], ofin["codIOffset"], ofin["bitsRead"], ofin["n_bins"]))
+
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:
+        return int(sum(ex.map(check, jobs)))
+
+
+def copy_probe(torch, dev, h2d_bytes, d2h_bytes, reps, barrier):
+    """What this box can copy: plain pinned cudaMemcpyAsync of one step's bytes host -> device and device -> host at
+    once (two streams), every rank at the same time.  The time per repetition is the floor of an end-to-end step."""
+    h_in = torch.empty(h2d_bytes, dtype=torch.uint8, pin_memory=True)
+    h_out = torch.empty(d2h_bytes, dtype=torch.uint8, pin_memory=True)
+    d_in = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    res = {}
+    for mode in ("h2d", "d2h", "both"):
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if mode != "d2h":
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if mode != "h2d":
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+        res[mode] = (time.perf_counter() - t0) / reps
+    del h_in, h_out, d_in, d_out
+    return res
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import harness as hz
     from h264decode_b200 import capi
+    from oracle import oracle as orc
 
     torch.cuda.set_device(local_rank)
     dev = "cuda:%d" % local_rank
@@ -201,14 +289,7 @@ def run_gpu(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    ctx = capi.Context(local_rank)
     sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
-    # a dedicated (non-default) stream: torch's events and the library's launches must be on the same one, and a NULL
-    # handle would mean "the context's own stream" to h264b_set_stream
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    ctx.set_stream(stream.cuda_stream)
     flags = capi.BYPASS_SPEC_OR | capi.CABAC_FINAL_TERMINATE
     if os.environ.get("H264B_BENCH_BYPASS_FORM") == "REF_SHIFT":  # diagnostic: the literal int64 engine on the same input
         flags = capi.CABAC_FINAL_TERMINATE
@@ -227,15 +308,6 @@ def run_gpu(args, rank, world, local_rank):
     nal_cap = n_nals + 16
     ops, n_ops, qp, idc = g["ops"], g["n_ops"], g["qp"], g["idc"]
     total_bins = int(n_ops.astype(np.int64).sum()) + n_slices
-
-    # ---- device buffers of one step
-    d_rbsp = torch.empty(n + 64, dtype=torch.uint8, device=dev)
-    d_nals = torch.empty(nal_cap * 32, dtype=torch.uint8, device=dev)
-    d_sum = torch.zeros(64, dtype=torch.uint8, device=dev)
-    d_off = torch.empty(n_slices, dtype=torch.int64, device=dev)
-    d_len = torch.empty(n_slices, dtype=torch.int32, device=dev)
-    d_snal = torch.empty(n_slices, dtype=torch.int32, device=dev)
-    d_ns = torch.zeros(4, dtype=torch.int32, device=dev)
     d_ops = torch.from_numpy(ops.view(np.int16)).to(dev)
     d_nops = torch.from_numpy(n_ops.view(np.int32)).to(dev)
     p = capi.Context.slice_qp(qp, idc)
@@ -243,63 +315,121 @@ def run_gpu(args, rank, world, local_rank):
     boff = np.zeros(n_slices + 1, dtype=np.uint64)
     boff[1:] = np.cumsum((n_ops.astype(np.uint64) + 1 + 31) // 32)
     d_boff = torch.from_numpy(boff.view(np.int64)).to(dev)
-    d_bins = torch.empty(int(boff[-1]), dtype=torch.int32, device=dev)
-    d_fin = torch.empty(n_slices * 32, dtype=torch.uint8, device=dev)
 
+    # ---- two steps' worth of device buffers: steps alternate between two contexts (two CUDA streams), so the tail of
+    # one step's CABAC launch -- its longest slices, alone on their schedulers -- overlaps the next step's kernels
+    bufs = [StepBuffers(torch, capi, dev, local_rank, n, nal_cap, n_slices, int(boff[-1])) for _ in range(2)]
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
-    def step(events=None):
+    def step(b, events=None):
+        c, st = b.ctx, b.stream
         if events:
-            events[0].record(stream)
-        ctx.annexb_scan_dev(d_stream.data_ptr(), n, d_rbsp.data_ptr(), d_nals.data_ptr(), None, nal_cap,
-                            d_sum.data_ptr(), 0)
+            events[0].record(st)
+        c.annexb_scan_dev(d_stream.data_ptr(), n, b.rbsp.data_ptr(), b.nals.data_ptr(), None, nal_cap, b.sum.data_ptr(), 0)
         if events:
-            events[1].record(stream)
-        ctx.slice_select_dev(d_nals.data_ptr(), d_sum.data_ptr(), nal_cap, 0, n_slices, d_off.data_ptr(),
-                             d_len.data_ptr(), d_snal.data_ptr(), d_ns.data_ptr())
-        ctx.cabac_decode_dev(bytes=d_rbsp.data_ptr(), total_bytes=n + 16, off=d_off.data_ptr(), len=d_len.data_ptr(),
-                             n_slices=n_slices, n_ctx=N_CTX, ops=d_ops.data_ptr(), n_ops_max=len(ops),
-                             n_ops=d_nops.data_ptr(), qp=d_qp.data_ptr(), init_states=None, bins=d_bins.data_ptr(),
-                             bins_off=d_boff.data_ptr(), bins_stride_words=0, final=d_fin.data_ptr(),
-                             final_states=None, flags=flags)
+            events[1].record(st)
+        c.slice_select_dev(b.nals.data_ptr(), b.sum.data_ptr(), nal_cap, 0, n_slices, b.off.data_ptr(), b.len.data_ptr(),
+                           b.snal.data_ptr(), b.ns.data_ptr())
+        c.cabac_decode_dev(bytes=b.rbsp.data_ptr(), total_bytes=n + 16, off=b.off.data_ptr(), len=b.len.data_ptr(),
+                           n_slices=n_slices, n_ctx=N_CTX, ops=d_ops.data_ptr(), n_ops_max=len(ops),
+                           n_ops=d_nops.data_ptr(), qp=d_qp.data_ptr(), init_states=None, bins=b.bins.data_ptr(),
+                           bins_off=d_boff.data_ptr(), bins_stride_words=0, final=b.fin.data_ptr(), final_states=None,
+                           flags=flags)
         if events:
-            events[2].record(stream)
+            events[2].record(st)
 
-    # ---- warm-up (also: result sanity outside the timed region)
-    for _ in range(max(args.warmup, 1)):
-        step()
+    # ---- warm-up, then the results are checked outside the timed regions
+    for k in range(max(args.warmup, 1)):
+        step(bufs[k & 1])
+    step(bufs[0])
+    step(bufs[1])
     torch.cuda.synchronize()
-    summ = np.frombuffer(d_sum.cpu().numpy().tobytes()[:48], dtype=np.uint64, count=5)
-    fin = np.frombuffer(d_fin.cpu().numpy().tobytes(), dtype=capi.FINAL_DTYPE)
-    ok = (int(summ[1]) == n_nals and int(d_ns.cpu()[0]) == n_slices and int(fin["n_bins"].astype(np.int64).sum())
-          == total_bins and not (fin["flags"] & capi.F_OVERRUN).any()
-          and np.array_equal(fin["n_bins"], n_ops + 1))
-    # last bin of every slice is the terminate bin the encoder wrote (1), a cheap whole-workload self-check
-    last_word = d_bins[torch.from_numpy((boff[1:] - 1).astype(np.int64)).to(dev)].cpu().numpy().view(np.uint32)
-    ok = ok and bool(np.all((last_word >> (n_ops & 31).astype(np.uint32)) & 1 == 1))
-    rbsp_bytes = int(summ[2])
+    ok = True
+    for b in bufs:   # whole-workload properties: counts, no overrun, and the terminate bin the encoder wrote last
+        summ = np.frombuffer(b.sum.cpu().numpy().tobytes()[:48], dtype=np.uint64, count=5)
+        fin = np.frombuffer(b.fin.cpu().numpy().tobytes(), dtype=capi.FINAL_DTYPE)
+        ok = ok and (int(summ[1]) == n_nals and int(b.ns.cpu()[0]) == n_slices and
+                     int(fin["n_bins"].astype(np.int64).sum()) == total_bins and not (fin["flags"] & capi.F_OVERRUN).any()
+                     and np.array_equal(fin["n_bins"], n_ops + 1))
+        last_word = b.bins[torch.from_numpy((boff[1:] - 1).astype(np.int64)).to(dev)].cpu().numpy().view(np.uint32)
+        ok = ok and bool(np.all((last_word >> (n_ops & 31).astype(np.uint32)) & 1 == 1))
+        rbsp_bytes = int(summ[2])
+    # every bin, final engine state and RBSP byte of the 32 longest slices and of randomly chosen ones, against the oracle
+    rng = np.random.default_rng(0x48323634 + rank)
+    longest = np.argsort(n_ops)[::-1][:min(32, n_slices)]
+    sample = rng.choice(n_slices, size=min(args.verify_slices, n_slices), replace=False)
+    which = np.unique(np.concatenate([longest, sample]))
+    t_ver = time.perf_counter()
+    verified = verify_slices(torch, capi, orc, bufs[0], d_stream, which, ops, n_ops, qp, idc, boff, flags,
+                             os.cpu_count() or 1) if len(which) else 0
+    t_ver = time.perf_counter() - t_ver
+    ok = ok and verified == len(which)
+    ok = ok and bool(torch.equal(bufs[0].bins, bufs[1].bins) and torch.equal(bufs[0].fin, bufs[1].fin))
 
-    # ---- timed region: exactly K steps
+    # ---- timed region 1: exactly K steps, one after the other on one stream
     sampler = ClockSampler(local_rank)
     evs = [[ev(), ev(), ev()] for _ in range(args.steps)]
-    launches0 = ctx.launch_count()
+    launches0 = bufs[0].ctx.launch_count() + bufs[1].ctx.launch_count()
     barrier()
     sampler.start()
     e_beg, e_end = ev(), ev()
-    e_beg.record(stream)
+    e_beg.record(bufs[0].stream)
     for k in range(args.steps):
-        step(evs[k])
-    e_end.record(stream)
+        step(bufs[0], evs[k])
+    e_end.record(bufs[0].stream)
+    torch.cuda.synchronize()
+    barrier()
+    t_serial_ms = e_beg.elapsed_time(e_end)
+    launches = bufs[0].ctx.launch_count() + bufs[1].ctx.launch_count() - launches0
+    t_scan_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    t_cabac_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    # ---- timed region 2: exactly K steps, two in flight (alternating contexts); timed on the device from the first
+    # step's start to the end of whichever step ends last
+    join = ev()
+    barrier()
+    o_beg, o_end = ev(), ev()
+    o_beg.record(bufs[0].stream)
+    bufs[1].stream.wait_event(o_beg)
+    for k in range(args.steps):
+        step(bufs[k & 1])
+    join.record(bufs[1].stream)
+    bufs[0].stream.wait_event(join)
+    o_end.record(bufs[0].stream)
     torch.cuda.synchronize()
     barrier()
     clocks = sampler.stop()
-    launches = ctx.launch_count() - launches0
-    t_total_ms = e_beg.elapsed_time(e_end)
-    t_scan_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
-    t_cabac_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    t_overlap_ms = o_beg.elapsed_time(o_end)
+
+    # ---- the EPB-dense stream of SURVEY.md 8(d) C1 (one emulation-prevention byte per ~200 bytes), 512 MiB: the
+    # scan / strip kernels' other regime
+    dense = None
+    if rank == 0 and not args.no_dense:
+        try:
+            c1 = np.ascontiguousarray(hz.build_stream_c1(1 << 20), dtype=np.uint8)
+            reps = 512
+            d_c1 = torch.from_numpy(c1.copy()).to(dev).repeat(reps)
+            nd = int(d_c1.numel())
+            capd = nd // 64 + 4096
+            db = StepBuffers(torch, capi, dev, local_rank, nd, capd, 1, 1)
+            for _ in range(2):
+                db.ctx.annexb_scan_dev(d_c1.data_ptr(), nd, db.rbsp.data_ptr(), db.nals.data_ptr(), None, capd, db.sum.data_ptr(), 0)
+            d0, d1 = ev(), ev()
+            d0.record(db.stream)
+            for _ in range(3):
+                db.ctx.annexb_scan_dev(d_c1.data_ptr(), nd, db.rbsp.data_ptr(), db.nals.data_ptr(), None, capd, db.sum.data_ptr(), 0)
+            d1.record(db.stream)
+            torch.cuda.synchronize()
+            sd = np.frombuffer(db.sum.cpu().numpy().tobytes()[:48], dtype=np.uint64, count=5)
+            dense = {"ms": d0.elapsed_time(d1) / 3, "bytes": nd, "n_nals": int(sd[1]), "rbsp_bytes": int(sd[2]), "n_epb": int(sd[4])}
+            db.ctx.close()
+            del db, d_c1
+        except Exception as ex:
+            dense = {"error": "%s: %s" % (type(ex).__name__, ex)}
 
     # ---- e2e through the host-buffer entry point
-    del d_bins, d_rbsp
+    ctx = bufs[0].ctx
+    for b in bufs:
+        del b.bins, b.rbsp
     torch.cuda.empty_cache()
     e2e_steps = max(IN_FLIGHT, min(args.steps, 12))
     e2e_error = None
@@ -335,17 +465,42 @@ def run_gpu(args, rank, world, local_rank):
                 pass
     d2h_bytes = int(boff[-1]) * 4 + n_slices * 32 + n_slices * 4 + n_nals * 32 + 48 + 4
     h2d_bytes = n + len(ops) * 2 + n_slices * (8 + 4) + (n_slices + 1) * 8
+    if h_stream is not None:
+        ctx.host_free(h_stream)
+        h_stream = None
+    probe = None
+    if not args.no_probe:
+        try:
+            probe = copy_probe(torch, dev, h2d_bytes, d2h_bytes, 3, barrier)
+        except Exception as ex:
+            probe = {"error": "%s: %s" % (type(ex).__name__, ex)}
+            if dist is not None:
+                try:
+                    barrier()
+                except Exception:
+                    pass
 
     # ---- reduce over ranks
-    t_max_ms, t_e2e_max, bins_all, bytes_all = t_total_ms, t_e2e, total_bins, n
+    per_rank = None
+    t_ser_max, t_ovl_max, t_e2e_max, bins_all, bytes_all = t_serial_ms, t_overlap_ms, t_e2e, total_bins, n
+    probe_max = dict(probe) if probe and "error" not in probe else None
     if dist is not None:
-        t = torch.tensor([t_total_ms, t_e2e], dtype=torch.float64, device=dev)
+        t = torch.tensor([t_serial_ms, t_overlap_ms, t_e2e] + ([probe[k] for k in ("h2d", "d2h", "both")] if probe_max else [0, 0, 0]),
+                         dtype=torch.float64, device=dev)
+        mine = torch.tensor([t_serial_ms / args.steps, t_overlap_ms / args.steps, t_cabac_ms, float(n_ops.max()),
+                             float(total_bins)], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[float(x) for x in r_] for r_ in allr]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_max_ms, t_e2e_max = float(t[0]), float(t[1])
-        c = torch.tensor([total_bins, n, int(ok and e2e_ok), int(e2e_error is not None)], dtype=torch.int64, device=dev)
+        t_ser_max, t_ovl_max, t_e2e_max = float(t[0]), float(t[1]), float(t[2])
+        if probe_max:
+            probe_max = {"h2d": float(t[3]), "d2h": float(t[4]), "both": float(t[5])}
+        c = torch.tensor([total_bins, n, int(ok and e2e_ok), int(e2e_error is not None), verified], dtype=torch.int64, device=dev)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         bins_all, bytes_all = int(c[0]), int(c[1])
         ok = int(c[2]) == world
+        verified = int(c[4])
         if int(c[3]) and e2e_error is None:
             e2e_error = "the end-to-end leg failed on %d other rank(s)" % int(c[3])
     else:
@@ -353,36 +508,47 @@ def run_gpu(args, rank, world, local_rank):
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        alg_bytes = n + rbsp_bytes + 20 * n_nals          # SURVEY.md §8(d): N_in + N_rbsp + index
+        k = measured_constants()
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        alg_bytes = n + rbsp_bytes + 20 * n_nals          # SURVEY.md 8(d): N_in + N_rbsp + index
         achieved = alg_bytes / (t_scan_ms * 1e-3) / 1e9
-        value = bins_all * args.steps / (t_max_ms * 1e-3)
+        value = bins_all * args.steps / (t_ovl_max * 1e-3)
+        serial = bins_all * args.steps / (t_ser_max * 1e-3)
+        cabac_rate = total_bins / (t_cabac_ms * 1e-3)
+        inst_per_bin = k.get("cabac_warp_inst_per_bin")
+        issue_bound = (sm_count * 4 * 32 * sm_mhz * 1e6 / inst_per_bin) if inst_per_bin else None
         out = {
             "metric": "cabac_bins_per_s", "value": value, "unit": "bins/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t_max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": t_ovl_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/u32 integer", "data": "synthetic (harness GPU encoder, %.1f s)" % t_gen,
             "config": config_dict(args), "results_verified": bool(ok),
+            "value_mode": "K steps on resident input, two in flight (two contexts = two CUDA streams; the tail of one "
+                          "step's CABAC launch overlaps the next step's kernels), device-timed first start -> last end",
+            "serialized": {"value": serial, "ms_per_step": t_ser_max / args.steps,
+                           "note": "the same K steps one after the other on one stream"},
+            "verified_slices": {"compared_with_oracle": int(verified), "chosen": int(len(which)) * world,
+                                "what": "RBSP bytes (NewNalUnit on the unit's stream bytes), every bin, final codIRange / "
+                                        "codIOffset / bitsRead; the 32 longest slices + %d random ones per rank" % args.verify_slices,
+                                "seconds": t_ver},
             "annexb_gbps": bytes_all / 1e9 / (t_scan_ms * 1e-3),
-            "stage_ms": {"annexb_scan": t_scan_ms, "slice_select+cabac": t_cabac_ms},
+            "stage_ms": {"annexb_scan": t_scan_ms, "slice_select+sort+assign+cabac": t_cabac_ms},
             "stream_bytes_per_gpu": n, "bins_per_gpu": total_bins, "nals_per_gpu": n_nals,
-            "roofline": {"bound": "hbm", "kernel": "annexb_copy_kernel + the six small launches of one Annex-B pass "
-                                                   "(memset, dirty chunks, ordinal scan x2, permute, finalize, fixup), "
-                                                   "timed together with CUDA events on the launching stream",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": TRAFFIC_PER_ALG_BYTE * alg_bytes if TRAFFIC_PER_ALG_BYTE else None,
-                         "traffic_source": TRAFFIC_SOURCE, "peak_source": peak_src, "algorithmic_bytes": alg_bytes},
-            "roofline_cabac": {"bound": "issue/latency (serial integer chain; not HBM, not tensor)",
-                               "bins_per_s_per_gpu": total_bins / (t_cabac_ms * 1e-3),
-                               "lanes": n_slices, "hbm_gbs_implied": total_bins * 0.235 / (t_cabac_ms * 1e-3) / 1e9,
-                               # issue model: warp instructions per op from ncu (smsp__inst_executed.sum / warp-ops,
-                               # profiles/r1_ncu_cabac_final2_summary.txt); one scheduler issues <= 1 per cycle and the
-                               # ALU pipe most of these instructions use takes 2 cycles per warp instruction
-                               "warp_inst_per_bin": CABAC_WARP_INST_PER_OP,
-                               "issue_ipc_per_scheduler": (total_bins / 32.0) * CABAC_WARP_INST_PER_OP / (
-                                   sm_count * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6 * t_cabac_ms * 1e-3),
-                               "alu_pipe_ipc_peak": 0.5,
-                               "equal_length_bins_per_s": 665e9,
-                               "note": "bounded by its longest bundle: 1.92 x mean ops x ~157 cycles for a warp on its own "
-                                       "(DESIGN.md section 4, K3; tools/cabac_balance_exp.py)"},
+            # the dominant kernel (98 % of a step): cabac_decode_kernel.  Serial integer work: neither HBM nor tensor
+            # bound; its roofline is the warp schedulers' issue rate
+            "roofline": {"bound": "issue (integer pipes; not hbm, not tensor)", "kernel": "cabac_decode_kernel",
+                         "achieved": cabac_rate / 1e9, "peak": issue_bound / 1e9 if issue_bound else None, "unit": "Gbins/s",
+                         "frac": cabac_rate / issue_bound if issue_bound else None,
+                         "peak_source": "SMs x 4 schedulers x 32 lanes x %.0f MHz / %s warp instructions per bin (ncu "
+                                        "smsp__inst_executed.sum / warp-bins, %s)" % (sm_mhz, inst_per_bin, k.get("source")),
+                         "traffic": k.get("cabac_dram_bytes_per_launch"), "algorithmic_bytes": int(total_bins * 0.235),
+                         "hbm_frac": total_bins * 0.235 / (t_cabac_ms * 1e-3) / 1e9 / peak,
+                         "longest_slice_ops": int(n_ops.max()), "mean_slice_ops": float(n_ops.mean()),
+                         "constants": k},
+            "roofline_scan": {"bound": "hbm", "kernel": "annexb_copy_kernel + the small launches of one Annex-B pass, timed "
+                                                        "together with CUDA events on the launching stream",
+                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                              "traffic": k.get("scan_dram_bytes_per_alg_byte", 0) * alg_bytes or None,
+                              "peak_source": peak_src, "algorithmic_bytes": alg_bytes},
             "e2e": {"value": (bins_all / t_e2e_max) if e2e_error is None else None, "error": e2e_error,
                     "unit": "bins/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": t_e2e_max * 1e3, "steps": e2e_steps,
@@ -390,6 +556,27 @@ def run_gpu(args, rank, world, local_rank):
                            "packed bins, final states out; copies of consecutive steps overlap kernels)"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if dense and "error" not in dense:
+            d_alg = dense["bytes"] + dense["rbsp_bytes"] + 20 * dense["n_nals"]
+            out["roofline_scan_dense"] = {"bound": "hbm", "workload": "512 copies of the configs[0] stream: %d EPBs in %.0f MB"
+                                          % (dense["n_epb"], dense["bytes"] / 1e6), "ms": dense["ms"],
+                                          "achieved": d_alg / (dense["ms"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                          "frac": d_alg / (dense["ms"] * 1e-3) / 1e9 / peak, "algorithmic_bytes": d_alg}
+        elif dense:
+            out["roofline_scan_dense"] = dense
+        if probe_max:
+            out["e2e"]["copy_probe"] = {
+                "what": "plain pinned cudaMemcpyAsync of one step's bytes, host -> device and device -> host at once, "
+                        "all %d ranks at the same time (max over ranks)" % world,
+                "h2d_gbs": h2d_bytes / probe_max["h2d"] / 1e9, "d2h_gbs": d2h_bytes / probe_max["d2h"] / 1e9,
+                "both_ms": probe_max["both"] * 1e3,
+                "e2e_roofline_bins_per_s": bins_all / probe_max["both"],
+                "e2e_frac_of_copy_floor": (probe_max["both"] / t_e2e_max) if e2e_error is None and t_e2e_max else None}
+        elif probe:
+            out["e2e"]["copy_probe"] = probe
+        if per_rank:
+            out["per_rank"] = {"columns": ["serialized ms/step", "overlapped ms/step", "cabac stage ms", "longest slice ops",
+                                           "bins"], "rows": per_rank}
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             # bounded sample: ~10-20 s of CPU work in all (all-core pass on `ns` slices, one-core pass on 1/8 of them)
@@ -409,12 +596,124 @@ def run_gpu(args, rank, world, local_rank):
             if b1:
                 out["cpu_baseline"]["single_core_bins_per_s"] = b1 / s1
                 out["cpu_baseline"]["cabac_bins_per_s_1core"] = b1 / s1_cabac
+            # how to read value / cpu_baseline.value: 70 % of the CPU pass is its one-thread byte-at-a-time scan
+            out["cpu_baseline"]["gpu_over_cpu"] = {
+                "whole_pass_all_cores": value / (bN / sN), "cabac_only_all_cores": cabac_rate / (bN / sN_cabac),
+                "cabac_only_one_core": (cabac_rate / (b1 / s1_cabac)) if b1 else None}
         print(json.dumps(out))
-    if h_stream is not None:
-        ctx.host_free(h_stream)
-    ctx.close()
+    for b in bufs:
+        b.ctx.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ configs[4]
+def run_config4(args):
+    """BASELINE configs[4], "multi-camera batch": 4096 concurrent synthetic streams x 16 slices, slice sizes
+    1 KB * 2^(10 u^3) (1 KB .. 1 MB, skewed towards small), through h264b_scheduler on --gpus devices
+    of ONE process: LPT by bytes over the devices, device jobs with the longest slices first, three jobs in flight per
+    device.  Prints makespan, per-slice completion percentiles (tail latency) and the devices' busy-time imbalance."""
+    import torch
+    import harness as hz
+    from h264decode_b200 import capi
+    from oracle import oracle as orc
+
+    n_dev = args.gpus
+    n_streams, per = args.streams, 16
+    rs = np.random.default_rng(4096)
+    size_bytes = 1024.0 * 2.0 ** (10.0 * rs.random((n_streams, per)) ** 3)
+    nb_all = np.maximum((size_bytes.reshape(-1) * 8 / 0.88).astype(np.int64), 32).astype(np.uint32)   # ~0.88 bit per bin
+    dev = "cuda:0"
+    torch.cuda.set_device(0)
+    streams, n_ops, qp, idc, ops = [], [], [], [], None
+    t_gen = time.perf_counter()
+    part = max(1, min(n_streams, 256))   # streams generated at a time (the generator's scratch is slices x longest slice)
+    pre_len = len(hz.SC + hz.SPS_NAL + hz.SC + hz.PPS_NAL)
+    sc = np.frombuffer(hz.SC, np.uint8)
+    for k0 in range(0, n_streams, part):
+        k1 = min(k0 + part, n_streams)
+        nb = nb_all[k0 * per:k1 * per]
+        g = hz.gpu_build_stream_cabac(torch, dev, len(nb), 0, config=5, n_active=N_ACTIVE, n_ctx=N_CTX, slices_per_frame=per,
+                                      frames_per_params=1, id_base=k0 * per, n_bins=nb)
+        torch.cuda.synchronize()
+        h = g["stream"][:g["n"]].cpu().numpy()
+        sizes = (g["payload_lens"] + 5).reshape(-1, per).sum(1) + pre_len
+        at = np.concatenate([[0], np.cumsum(sizes)])
+        for i in range(k1 - k0):
+            streams.append(np.concatenate([h[at[i]:at[i + 1]], sc]))
+        n_ops.append(g["n_ops"])
+        qp.append(g["qp"])
+        idc.append(g["idc"])
+        if ops is None or len(g["ops"]) > len(ops):
+            ops = g["ops"]
+        del g
+        torch.cuda.empty_cache()
+    n_ops, qp, idc = np.concatenate(n_ops), np.concatenate(qp), np.concatenate(idc)
+    t_gen = time.perf_counter() - t_gen
+    total_bytes = int(sum(len(x) for x in streams))
+    flags = capi.BYPASS_SPEC_OR | capi.CABAC_FINAL_TERMINATE
+    sch = capi.Scheduler(list(range(n_dev)))
+    runs = []
+    try:
+        for rnd in range(args.warmup if args.warmup < 2 else 1):   # buffer growth
+            sch.run(streams, [per] * n_streams, ops, n_ops, qp, idc, N_CTX, flags=flags, group_bytes=args.group_mb << 20)
+        for rnd in range(args.steps):
+            r = sch.run(streams, [per] * n_streams, ops, n_ops, qp, idc, N_CTX, flags=flags, group_bytes=args.group_mb << 20)
+            runs.append(r)
+    finally:
+        sch.close()
+    r = min(runs, key=lambda x: x["makespan_ms"])
+    fin = r["final"]
+    ok = bool(np.array_equal(fin["n_bins"], n_ops + 1)) and not (fin["flags"] & capi.F_OVERRUN).any()
+    last = np.array([int(r["bins_flat"][int(r["bins_off"][s + 1]) - 1]) for s in range(len(n_ops))], dtype=np.uint64)
+    ok = ok and bool(np.all((last >> (n_ops & 31).astype(np.uint64)) & 1 == 1))
+    # a sample of slices against the oracle, bin by bin (the oracle strips the stream itself)
+    rng = np.random.default_rng(44)
+    check = np.unique(np.concatenate([rng.choice(len(n_ops), 64, replace=False), np.argsort(n_ops)[-4:]]))
+    term = np.array([orc.make_op(orc.OP_TERMINATE)], np.uint16)
+    verified = 0
+    for s in check:
+        st, k = divmod(int(s), per)
+        onal, orbsp = orc.read_nal_units_arrays(streams[st])
+        sl = np.flatnonzero((onal["type"] == 1) | (onal["type"] == 5))[k]
+        data = orbsp[onal["rbsp_off"][sl]:onal["rbsp_off"][sl] + onal["rbsp_len"][sl]]
+        init = orc.ctx_init(qp[s:s + 1], idc[s:s + 1], N_CTX)[0]
+        rc, obins, ofin, _ = orc.cabac_decode_slice(data, np.concatenate([ops[:n_ops[s]], term]), init, orc.BYPASS_SPEC_OR)
+        nbits = int(n_ops[s]) + 1
+        nw = (nbits + 31) // 32
+        got = np.array(r["bins"][s][:nw], dtype=np.uint32)
+        if nbits % 32:
+            got[-1] &= np.uint32((1 << (nbits % 32)) - 1)
+        verified += int(rc == orc.OK and np.array_equal(got, obins[:nw]) and
+                        (int(fin[s]["cod_i_range"]), int(fin[s]["cod_i_offset"]), int(fin[s]["bits_read"])) ==
+                        (ofin["codIRange"], ofin["codIOffset"], ofin["bitsRead"]))
+    ok = ok and verified == len(check)
+    done = np.sort(r["slice_done_ms"])
+    busy = r["device_busy_ms"]
+    total_bins = int(n_ops.astype(np.int64).sum()) + len(n_ops)
+    out = {
+        "metric": "cabac_bins_per_s", "value": total_bins / (r["makespan_ms"] * 1e-3), "unit": "bins/s", "n_gpus": n_dev,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["makespan_ms"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8/u32 integer",
+        "data": "synthetic (harness GPU encoder, %.1f s)" % t_gen,
+        "config": {"workload": "configs[4]: multi-camera batch, %d streams x %d slices, slice sizes 1 KB * 2^(10 u^3); one "
+                               "process, h264b_scheduler over %d device(s): LPT by bytes, jobs of ~%d MiB with the longest "
+                               "slices first, three in flight per device; host buffers in and out" % (
+                                   n_streams, per, n_dev, args.group_mb),
+                   "streams": n_streams, "slices": int(len(n_ops)), "stream_bytes": total_bytes, "n_ctx": N_CTX,
+                   "longest_slice_bins": int(n_ops.max()), "mean_slice_bins": float(n_ops.mean())},
+        "results_verified": bool(ok), "verified_slices": {"compared_with_oracle": int(verified), "chosen": int(len(check))},
+        "makespan_ms": r["makespan_ms"], "makespan_ms_all_runs": [x["makespan_ms"] for x in runs],
+        "slice_completion_ms": {"p50": float(done[len(done) // 2]), "p90": float(done[int(len(done) * 0.9)]),
+                                "p99": float(done[int(len(done) * 0.99)]), "max": float(done[-1])},
+        "device_busy_ms": [float(x) for x in busy], "device_busy_imbalance_max_over_mean": float(busy.max() / busy.mean()),
+        "device_bytes": [int(x) for x in r["device_bytes"]], "device_jobs": [int(x) for x in r["device_jobs"]],
+        "lpt_imbalance_bytes_max_over_mean": float(r["device_bytes"].max() / r["device_bytes"].mean()),
+        "longest_slice_floor_ms": float(n_ops.max()) * 119.0 / 1.965e6,
+        "e2e": {"value": total_bins / (r["makespan_ms"] * 1e-3), "unit": "bins/s", "h2d_bytes_per_step": total_bytes,
+                "d2h_bytes_per_step": int(r["bins_off"][-1]) * 4 + len(n_ops) * 32},
+    }
+    print(json.dumps(out))
 
 
 def _stream_submit_raw(ctx, capi, h_stream, ops, n_ops, p, flags):
@@ -454,12 +753,23 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-single", action="store_true", default=True)
     ap.add_argument("--cpu-slices", type=int, default=0, help="slices in the bounded CPU sample (default 16 x cores)")
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4], help="BASELINE.json configs[] index: 3 (default, the "
+                    "headline workload) or 4 (multi-camera batch through the in-process multi-GPU scheduler)")
+    ap.add_argument("--streams", type=int, default=4096, help="configs[4]: number of streams")
+    ap.add_argument("--group-mb", type=int, default=16, help="configs[4]: stream bytes per device job")
+    ap.add_argument("--verify-slices", type=int, default=256, help="random slices per rank compared bin by bin with the oracle")
+    ap.add_argument("--no-probe", action="store_true", help="skip the pinned-copy probe (the end-to-end floor of this box)")
+    ap.add_argument("--no-dense", action="store_true", help="skip the EPB-dense Annex-B stream (roofline_scan_dense)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.config == 4:   # one process drives all --gpus devices (under torchrun: rank 0 alone)
+        if rank == 0:
+            run_config4(args)
         return
     run_gpu(args, rank, world, local_rank)
 

@@ -30,6 +30,7 @@ SYMBOLS = [
     "h264b_parse_sps", "h264b_parse_pps", "h264b_parse_sps_dev", "h264b_parse_pps_dev", "h264b_make_param_sets",
     "h264b_param_set_select_dev",
     "h264b_ctx_idx", "h264b_new_binarization", "h264b_init_cabac", "h264b_mb_bin_string", "h264b_bin_string_match",
+    "h264b_scheduler_create", "h264b_scheduler_destroy", "h264b_scheduler_last_error", "h264b_scheduler_run",
 ]
 
 NAL_DTYPE = np.dtype([("start", "<u8"), ("rbsp_off", "<u8"), ("num_bytes", "<u4"), ("rbsp_len", "<u4"),
@@ -67,6 +68,24 @@ class StreamJob(C.Structure):
                 ("ops", C.c_void_p), ("n_ops_max", C.c_uint32), ("n_ops", C.c_void_p), ("qp", C.c_void_p),
                 ("max_slices", C.c_uint32), ("flags", C.c_uint32), ("param_sets", C.c_void_p),
                 ("max_sps", C.c_uint32), ("max_pps", C.c_uint32), ("initial_sps", C.c_void_p), ("initial_pps", C.c_void_p)]
+
+
+class BatchStream(C.Structure):
+    _fields_ = [("stream", C.c_void_p), ("n", C.c_uint64), ("first_slice", C.c_uint32), ("n_slices", C.c_uint32)]
+
+
+class BatchJob(C.Structure):
+    _fields_ = [("streams", C.c_void_p), ("n_streams", C.c_uint32), ("total_slices", C.c_uint32), ("n_ctx", C.c_uint32),
+                ("n_ops_max", C.c_uint32), ("ops", C.c_void_p), ("n_ops", C.c_void_p), ("qp", C.c_void_p),
+                ("slice_data_offset", C.c_uint32), ("flags", C.c_uint32), ("group_bytes", C.c_uint64)]
+
+
+class BatchResult(C.Structure):
+    _fields_ = [("stream_device", C.c_void_p), ("stream_job", C.c_void_p), ("stream_nal_off", C.c_void_p),
+                ("nals", C.c_void_p), ("final", C.c_void_p), ("bins_off", C.c_void_p), ("bins", C.c_void_p),
+                ("slice_done_ms", C.c_void_p), ("n_devices", C.c_uint32), ("reserved", C.c_uint32),
+                ("device_busy_ms", C.c_void_p), ("device_bytes", C.c_void_p), ("device_jobs", C.c_void_p),
+                ("makespan_ms", C.c_double), ("total_bins", C.c_uint64), ("total_nals", C.c_uint64)]
 
 
 class StreamResult(C.Structure):
@@ -206,6 +225,10 @@ def load():
         "h264b_init_cabac": (i32, [vp, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp]),
         "h264b_mb_bin_string": (i32, [vp, u32, vp, vp, vp, vp, vp]),
         "h264b_bin_string_match": (i32, [vp, u32, vp, vp, vp, vp, vp]),
+        "h264b_scheduler_create": (i32, [vp, u32, P(vp)]),
+        "h264b_scheduler_destroy": (None, [vp]),
+        "h264b_scheduler_last_error": (C.c_char_p, [vp]),
+        "h264b_scheduler_run": (i32, [vp, P(BatchJob), P(BatchResult)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -618,3 +641,77 @@ class Context:
                     pps_nal=_from_ptr(r.pps_nal, np.uint32, r.n_pps) if r.pps else None,
                     slice_sps=_from_ptr(r.slice_sps, np.int32, ns) if r.sps else None,
                     slice_pps=_from_ptr(r.slice_pps, np.int32, ns) if r.sps else None)
+
+
+class Scheduler:
+    """h264b_scheduler: a batch of independent streams over several GPUs of this process (one worker thread and one
+    context per device, LPT by bytes, device jobs with the longest slices first, three in flight per device)."""
+
+    def __init__(self, devices):
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        rc = _lib.h264b_scheduler_create(C.c_void_p(devs.ctypes.data), len(devs), C.byref(h))
+        if rc != OK:
+            raise H264BError(rc, "h264b_scheduler_create failed" + (": no usable CUDA device" if rc == E_NO_DEVICE else ""))
+        self.h = h
+        self.n_devices = len(devs)
+
+    def close(self):
+        if self.h:
+            _lib.h264b_scheduler_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, streams, slices_per_stream, ops, n_ops, qp, idc, n_ctx, flags=0, slice_data_offset=0, group_bytes=0):
+        """streams: list of uint8 arrays; slices_per_stream[i]: slice NAL units of stream i (rows of n_ops / qp / idc in
+        stream order).  -> dict(stream_device, stream_job, nals (list per stream), final, bins (list per slice),
+        slice_done_ms, device_busy_ms, device_bytes, device_jobs, makespan_ms, total_bins, total_nals)"""
+        arrs = [np.ascontiguousarray(s, dtype=np.uint8) for s in streams]
+        per = np.asarray(slices_per_stream, dtype=np.int64)
+        first = np.concatenate([[0], np.cumsum(per)]).astype(np.int64)
+        total = int(first[-1])
+        bs = (BatchStream * max(len(arrs), 1))()
+        for i, a in enumerate(arrs):
+            bs[i].stream = a.ctypes.data if len(a) else None
+            bs[i].n = len(a)
+            bs[i].first_slice = int(first[i])
+            bs[i].n_slices = int(per[i])
+        ops = np.ascontiguousarray(ops, dtype=np.uint16)
+        nops = None if n_ops is None else np.ascontiguousarray(n_ops, dtype=np.uint32)
+        p = Context.slice_qp(qp, idc)
+        j = BatchJob()
+        j.streams = C.addressof(bs)
+        j.n_streams = len(arrs)
+        j.total_slices = total
+        j.n_ctx = n_ctx
+        j.n_ops_max = len(ops)
+        j.ops = ops.ctypes.data if len(ops) else None
+        j.n_ops = nops.ctypes.data if nops is not None else None
+        j.qp = p.ctypes.data
+        j.slice_data_offset = slice_data_offset
+        j.flags = flags
+        j.group_bytes = group_bytes
+        r = BatchResult()
+        rc = _lib.h264b_scheduler_run(self.h, C.byref(j), C.byref(r))
+        if rc != OK:
+            raise H264BError(rc, (_lib.h264b_scheduler_last_error(self.h) or b"").decode(errors="replace"))
+        ns = len(arrs)
+        noff = _from_ptr(r.stream_nal_off, np.uint64, ns + 1).copy()
+        nals = _from_ptr(r.nals, NAL_DTYPE, int(noff[-1]) if ns else 0).copy()
+        boff = _from_ptr(r.bins_off, np.uint64, total + 1).copy()
+        flat = _from_ptr(r.bins, np.uint32, int(boff[-1]) if total else 0)
+        return dict(stream_device=_from_ptr(r.stream_device, np.int32, ns).copy(),
+                    stream_job=_from_ptr(r.stream_job, np.uint32, ns).copy(),
+                    nals=[nals[int(noff[i]):int(noff[i + 1])] for i in range(ns)],
+                    final=_from_ptr(r.final, FINAL_DTYPE, total).copy(), bins_off=boff, bins_flat=flat,
+                    bins=[flat[int(boff[i]):int(boff[i + 1])] for i in range(total)],
+                    slice_done_ms=_from_ptr(r.slice_done_ms, np.float64, total).copy(),
+                    device_busy_ms=_from_ptr(r.device_busy_ms, np.float64, r.n_devices).copy(),
+                    device_bytes=_from_ptr(r.device_bytes, np.uint64, r.n_devices).copy(),
+                    device_jobs=_from_ptr(r.device_jobs, np.uint32, r.n_devices).copy(),
+                    makespan_ms=r.makespan_ms, total_bins=r.total_bins, total_nals=r.total_nals)

@@ -179,28 +179,22 @@ __global__ void __launch_bounds__(1024) bundle_assign_kernel(const uint32_t *n_o
     if (tid >= 32) return;
     // a bundle whose own chain (x 2.2) comes near the balanced load of a scheduler counts 1.5 times
     const unsigned long long critical = total_s * 4 / (5ull * n_sched);  // 0.8 x total / schedulers
-    uint32_t my_min = 0xFFFFFFFFu, my_arg = 0;  // least loaded scheduler among this lane's (lane, lane + 32, ...)
-    for (uint32_t k = lane; k < n_sched; k += 32)
-        if (my_min == 0xFFFFFFFFu) my_min = 0, my_arg = k;
+    // key of a scheduler: weighted ops / 2 (22 bits are plenty: 5 bundles of < 2^20 ops, weighted 1.5) << 10 | its index; the
+    // least loaded one (ties: the lowest index) is the minimum key -- one warp reduction per bundle
+    const auto key_of = [&](uint32_t k) { return sum[k] >= 0xFFFFFFF0u ? 0xFFFFFFFFu : ((sum[k] >> 1) << 10) | k; };
+    uint32_t my_key = 0xFFFFFFFFu;  // least loaded scheduler among this lane's (lane, lane + 32, ...)
+    for (uint32_t k = lane; k < n_sched; k += 32) my_key = min(my_key, key_of(k));
     for (uint32_t g = 0; g < n_bundles; g++) {  // bundles come longest first
-        // least loaded scheduler of all (ties: the lowest index)
-        unsigned long long key = ((unsigned long long)my_min << 32) | my_arg;
-#pragma unroll
-        for (int d = 16; d; d >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, d);
-            key = o < key ? o : key;
-        }
-        const uint32_t sidx = (uint32_t)key;
-        const uint32_t L = len[g];
+        const uint32_t sidx = __reduce_min_sync(0xFFFFFFFFu, my_key) & 1023u;
         if ((sidx & 31u) == (uint32_t)lane) {  // its owner places the bundle and looks for its new minimum
+            const uint32_t L = len[g];
             const uint32_t kpos = cnt[sidx];
             slot_bundle[(sidx >> 2) * W + kpos * 4 + (sidx & 3u)] = (int32_t)g;
             cnt[sidx] = kpos + 1;
             const uint32_t wgt = ((unsigned long long)L * 11 / 5 > critical) ? L + L / 2 : L;
             sum[sidx] = kpos + 1 >= slots ? 0xFFFFFFF0u : sum[sidx] + wgt;
-            my_min = 0xFFFFFFFFu;
-            for (uint32_t k = lane; k < n_sched; k += 32)
-                if (sum[k] < my_min) my_min = sum[k], my_arg = k;
+            my_key = 0xFFFFFFFFu;
+            for (uint32_t k = lane; k < n_sched; k += 32) my_key = min(my_key, key_of(k));
         }
     }
 }

@@ -466,6 +466,67 @@ int32_t h264b_slice_select_dev(h264b_ctx *ctx, const h264b_nal *d_nals, const h2
                                uint32_t nal_cap, uint32_t slice_data_offset, uint32_t max_slices, uint64_t *d_off,
                                uint32_t *d_len, uint32_t *d_slice_nal, uint32_t *d_n_slices);
 
+/* ------------------------------------------------------------------ many streams over the GPUs of one box
+ * The reference's unit of concurrency is a connection: main.go:16-21 starts one goroutine per accepted connection,
+ * each running ByteStreamReader -> handleConnection (h264/server.go:113-166) on its own stream.  Here a scheduler owns
+ * one context and one worker thread per device and takes a whole batch of independent streams ("multi-camera batch",
+ * BASELINE configs[4]):
+ *   - streams are dealt to the devices longest first onto the least loaded one (LPT by bytes);
+ *   - on its device a stream joins a job of ~group_bytes: the streams holding the longest slices go first (a slice is
+ *     serial work: the job with the longest slices starts at once and runs beside the jobs that follow it), jobs run
+ *     through h264b_stream_submit / h264b_stream_wait with three in flight per device;
+ *   - every slice's result carries the time at which it reached host memory (tail latency), every device the time it
+ *     was busy.
+ * No collective, no exchange between devices: slices share nothing.
+ * A stream is taken from its first to its last start code 00 00 00 01 (what comes before and after yields no NAL unit
+ * in the reference either: h264/server.go:64-111); its results are those of h264b_stream_decode on it alone. */
+typedef struct h264b_scheduler h264b_scheduler;
+int32_t h264b_scheduler_create(const int32_t *devices, uint32_t n_devices, h264b_scheduler **out);
+void h264b_scheduler_destroy(h264b_scheduler *s);
+const char *h264b_scheduler_last_error(const h264b_scheduler *s);
+
+typedef struct {
+    const uint8_t *stream;  /* host memory */
+    uint64_t n;
+    uint32_t first_slice;   /* its slice NAL units (type 1 / 5, in stream order) are rows first_slice .. + n_slices - 1 */
+    uint32_t n_slices;      /* of the batch's per-slice arrays */
+} h264b_batch_stream;
+
+typedef struct {
+    const h264b_batch_stream *streams;
+    uint32_t n_streams;
+    uint32_t total_slices;
+    uint32_t n_ctx;
+    uint32_t n_ops_max;
+    const uint16_t *ops;       /* shared op schedule */
+    const uint32_t *n_ops;     /* [total_slices] or NULL */
+    const h264b_slice_qp *qp;  /* [total_slices] */
+    uint32_t slice_data_offset;
+    uint32_t flags;            /* H264B_TABLES_SPEC | H264B_BYPASS_SPEC_OR | H264B_CABAC_FINAL_TERMINATE */
+    uint64_t group_bytes;      /* stream bytes per device job; 0: 16 MiB */
+} h264b_batch_job;
+
+typedef struct {
+    const int32_t *stream_device;    /* [n_streams] index into the scheduler's devices */
+    const uint32_t *stream_job;      /* [n_streams] job of that device the stream ran in */
+    const uint64_t *stream_nal_off;  /* [n_streams + 1] the stream's NAL units are nals[stream_nal_off[i] .. [i + 1]) */
+    const h264b_nal *nals;           /* start / rbsp_off relative to the stream's own first byte */
+    const h264b_cabac_final *final;  /* [total_slices] */
+    const uint64_t *bins_off;        /* [total_slices + 1] word offsets into bins */
+    const uint32_t *bins;
+    const double *slice_done_ms;     /* [total_slices] from the start of the run to the slice's result in host memory */
+    uint32_t n_devices;
+    uint32_t reserved;
+    const double *device_busy_ms;    /* [n_devices] first submit to last wait */
+    const uint64_t *device_bytes;    /* [n_devices] stream bytes dealt to the device */
+    const uint32_t *device_jobs;     /* [n_devices] */
+    double makespan_ms;
+    uint64_t total_bins, total_nals;
+} h264b_batch_result;
+
+/* Synchronous; the result stays valid until the next run or the scheduler's destruction. */
+int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264b_batch_result *res);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

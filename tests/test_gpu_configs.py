@@ -234,3 +234,57 @@ def test_streams_of_very_short_nal_units_and_many_parameter_sets():
         assert np.array_equal(r["slice_sps"], np.arange(150)) and np.array_equal(r["slice_pps"], np.arange(150))
     finally:
         ctx.close()
+
+
+def test_scheduler_batch_of_streams_over_several_workers():
+    """h264b_scheduler: a batch of independent streams (skewed sizes, some with bytes in front of their first start code
+    or without a closing start code) dealt to two workers -- here two contexts on the one GPU -- in many small device
+    jobs.  Every stream's NAL units must be the oracle's for that stream on its own, every slice's bins the ones the
+    test encoder coded, whatever job and worker the stream landed in."""
+    from h264decode_b200 import capi
+    rng = np.random.default_rng(5)
+    n_streams = 40
+    mean_bins = (1024 * 2 ** (6 * rng.random(n_streams) ** 3) * 8 / 0.88).astype(np.int64)
+    per = rng.integers(1, 7, n_streams)
+    built = [hz.build_stream_cabac(int(per[i]), int(mean_bins[i]), config=5, n_active=64, n_ctx=64, slices_per_frame=3,
+                                   frames_per_params=2, id_base=1000 * i) for i in range(n_streams)]
+    ops = max((b["ops"] for b in built), key=len)   # the schedules are prefixes of one another (same generator)
+    for b in built:
+        assert np.array_equal(b["ops"], ops[:len(b["ops"])])
+    streams = []
+    for i, b in enumerate(built):
+        s = b["stream"]
+        if i % 5 == 1:
+            s = np.concatenate([np.array([7, 0, 0, 1, 9], np.uint8), s])          # junk in front of the first start code
+        if i % 7 == 2:
+            s = np.concatenate([s, np.array([0x65, 1, 2, 3, 4, 5], np.uint8)])    # an unterminated unit at the end
+        streams.append(s)
+    streams.append(np.array([1, 2, 3], np.uint8))                                 # no start code at all
+    per = np.concatenate([per, [0]])
+    n_ops = np.concatenate([b["n_ops"] for b in built])
+    qp = np.concatenate([b["qp"] for b in built])
+    idc = np.concatenate([b["idc"] for b in built])
+    flags = capi.BYPASS_SPEC_OR | capi.CABAC_FINAL_TERMINATE
+    sch = capi.Scheduler([0, 0])
+    try:
+        r = sch.run(streams, per, ops, n_ops, qp, idc, 64, flags=flags, group_bytes=96 << 10)
+    finally:
+        sch.close()
+    assert r["device_jobs"].sum() > 6 and set(r["stream_device"][:n_streams]) == {0, 1} and r["stream_device"][-1] == -1
+    assert abs(int(r["device_bytes"][0]) - int(r["device_bytes"][1])) < 0.25 * r["device_bytes"].sum()
+    row = 0
+    for i, b in enumerate(built):
+        onal, _ = orc.read_nal_units_arrays(streams[i])
+        got = r["nals"][i]
+        assert np.array_equal(got["start"].astype(np.int64), onal["start"]), i
+        assert np.array_equal(got["rbsp_len"].astype(np.int64), onal["rbsp_len"]), i
+        assert np.array_equal(got["type"].astype(np.int64), onal["type"]), i
+        for s in range(int(per[i])):
+            f = r["final"][row]
+            assert f["n_bins"] == b["n_ops"][s] + 1 and not (f["flags"] & capi.F_OVERRUN)
+            nw = (int(b["n_ops"][s]) + 1) // 32
+            assert np.array_equal(r["bins"][row][:nw], b["bins"][s, :nw]), (i, s)
+            assert 0 < r["slice_done_ms"][row] <= r["makespan_ms"]
+            row += 1
+    assert row == len(n_ops) and r["total_bins"] == int(n_ops.sum()) + len(n_ops)
+    assert len(r["nals"][-1]) == 0
