@@ -697,9 +697,9 @@ def run_config4(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "u8/u32 integer",
         "data": "synthetic (harness GPU encoder, %.1f s)" % t_gen,
         "config": {"workload": "configs[4]: multi-camera batch, %d streams x %d slices, slice sizes 1 KB * 2^(10 u^3); one "
-                               "process, h264b_scheduler over %d device(s): LPT by bytes, jobs of ~%d MiB with the longest "
-                               "slices first, three in flight per device; host buffers in and out" % (
-                                   n_streams, per, n_dev, args.group_mb),
+                               "process, h264b_scheduler over %d device(s): LPT by bytes, one split + strip pass and five "
+                               "CABAC launches by slice length (longest first, side by side) per device; host buffers in "
+                               "and out" % (n_streams, per, n_dev),
                    "streams": n_streams, "slices": int(len(n_ops)), "stream_bytes": total_bytes, "n_ctx": N_CTX,
                    "longest_slice_bins": int(n_ops.max()), "mean_slice_bins": float(n_ops.mean())},
         "results_verified": bool(ok), "verified_slices": {"compared_with_oracle": int(verified), "chosen": int(len(check))},

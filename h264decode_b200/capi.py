@@ -9,6 +9,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# h264b_scheduler runs several launches side by side on one device: more hardware queues than CUDA's default of 8, so that
+# no two of its streams share one (read when the process initialises CUDA, which importing this module does not do)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 LIB_PATH = os.environ.get("H264B_LIB") or os.path.join(_HERE, "libh264b200.so")  # (H264B_LIB: experiment builds)
 
 OK, E_INVALID, E_CUDA, E_NOMEM, E_CAPACITY, E_NO_DEVICE = range(6)

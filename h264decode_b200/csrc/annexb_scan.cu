@@ -1009,6 +1009,7 @@ static ScratchOffsets scratch_layout(uint64_t n, uint32_t nal_cap) {
 
 int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint8_t *d_rbsp, h264b_nal *d_nals,
                        h264b_nal_ext *d_ext, uint32_t nal_cap, h264b_scan_summary *d_summary, uint32_t flags) {
+    TraceRange trace_range("h264b:annexb_scan");
     (void)flags;
     if (((uintptr_t)d_stream & 15) || ((uintptr_t)d_rbsp & 15))
         return set_error(ctx, H264B_E_INVALID, "annexb_scan: d_stream and d_rbsp must be 16-byte aligned");

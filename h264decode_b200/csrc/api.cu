@@ -520,6 +520,7 @@ int32_t h264b_stream_submit(h264b_ctx *ctx, const h264b_stream_job *job, uint64_
 // the NAL index.  h264b_stream_wait calls this again, with the bounds the first run reported, when one of them was too
 // small (the job's host buffers are still valid then: they have to be until the wait returns).
 static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job, int slot_idx, uint32_t nal_cap) {
+    TraceRange trace_range("h264b:stream_submit");
     const h264b_stream_job &j = *job;
     // (H264B_STREAM_PARAM_SETS implies H264B_STREAM_SLICE_HEADERS)
     const bool from_headers = (j.flags & (H264B_STREAM_SLICE_HEADERS | H264B_STREAM_PARAM_SETS)) != 0 && j.max_slices != 0;
@@ -716,6 +717,7 @@ static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job
 int32_t h264b_stream_wait(h264b_ctx *ctx, uint64_t ticket, h264b_stream_result *res) {
     CHECK_CTX(ctx);
     if (!res) return H264B_E_INVALID;
+    TraceRange trace_range("h264b:stream_wait");
     StreamSlot *sl = ctx->slot[ticket % kStreamSlots];
     if (!sl->busy || sl->ticket != ticket) return set_error(ctx, H264B_E_INVALID, "stream_wait: unknown ticket");
     H264B_CUDA(ctx, cudaEventSynchronize(sl->e_out));

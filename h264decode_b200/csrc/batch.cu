@@ -5,6 +5,8 @@
 // worker thread and one h264b context per device, streams dealt to devices longest first (LPT by bytes), grouped into
 // device jobs with the longest slices first, three jobs in flight per device through the same h264b_stream_submit /
 // h264b_stream_wait any single-stream caller uses.  Host code only: no kernel lives here.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdarg>
@@ -41,20 +43,20 @@ bool trim(const uint8_t *s, uint64_t n, uint64_t *begin, uint64_t *end) {
     return true;
 }
 
-struct DeviceJob {
-    std::vector<uint32_t> streams;        // indices into the batch, staging order
-    std::vector<uint64_t> base;           // offset of each stream in the staged buffer
-    uint64_t bytes = 0;
-    uint32_t n_slices = 0;
+constexpr int kClasses = 5;  // slice-length classes of a device's share: their CABAC launches run side by side
+
+struct Grown {  // grow-only raw buffers (pinned host or device)
+    void *p = nullptr;
+    size_t bytes = 0;
 };
 
 struct Worker {
     int device = 0;
-    h264b_ctx *ctx = nullptr;
-    uint8_t *stage[kStreamSlots] = {nullptr, nullptr, nullptr};
-    size_t stage_bytes[kStreamSlots] = {0, 0, 0};
-    std::vector<uint32_t> j_nops[kStreamSlots];
-    std::vector<h264b_slice_qp> j_qp[kStreamSlots];
+    h264b_ctx *ctx[kClasses] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [0] also runs the split + strip pass
+    cudaEvent_t e_scan = nullptr, e_done[kClasses] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    Grown h_stream, h_bins, h_fin, h_nals, h_small;                      // pinned
+    Grown d_stream, d_rbsp, d_nals, d_sum, d_off, d_len, d_snal, d_offp, d_lenp, d_perm, d_nops, d_qp, d_boff, d_bins, d_fin,
+        d_ops;                                                           // device
     std::string err;
     int rc = H264B_OK;
 };
@@ -79,6 +81,15 @@ struct h264b_scheduler {
     std::vector<uint32_t> device_jobs;
 };
 
+// slice lists in class order: (off, len) of slice perm[k] -> position k
+__global__ void __launch_bounds__(256) gather_slices_kernel(const uint64_t *off, const uint32_t *len, const uint32_t *perm,
+                                                            uint32_t n, uint64_t *off_p, uint32_t *len_p) {
+    for (uint32_t k = blockIdx.x * 256 + threadIdx.x; k < n; k += gridDim.x * 256) {
+        off_p[k] = off[perm[k]];
+        len_p[k] = len[perm[k]];
+    }
+}
+
 static int sched_error(h264b_scheduler *s, int code, const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -92,14 +103,30 @@ extern "C" {
 int32_t h264b_scheduler_create(const int32_t *devices, uint32_t n_devices, h264b_scheduler **out) {
     if (!out || !devices || !n_devices) return H264B_E_INVALID;
     *out = nullptr;
+    // The classes' launches must not queue behind one another: CUDA maps a process's streams onto 8 hardware queues by
+    // default, and two streams on one queue serialise.  (Read when the process initialises CUDA: set it before that.)
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     h264b_scheduler *s = new h264b_scheduler;
     s->workers.resize(n_devices);
     for (uint32_t d = 0; d < n_devices; d++) {
-        s->workers[d].device = devices[d];
-        const int32_t rc = h264b_create(devices[d], &s->workers[d].ctx);
-        if (rc != H264B_OK) {
+        Worker &w = s->workers[d];
+        w.device = devices[d];
+        for (int c = 0; c < kClasses; c++) {
+            const int32_t rc = h264b_create(devices[d], &w.ctx[c]);
+            if (rc != H264B_OK) {
+                h264b_scheduler_destroy(s);
+                return rc;
+            }
+            // several launches share the device: small CTAs, so that the short classes find room beside the long ones
+            w.ctx[c]->cabac_max_warps = 8;
+            if (cudaEventCreateWithFlags(&w.e_done[c], cudaEventDisableTiming) != cudaSuccess) {
+                h264b_scheduler_destroy(s);
+                return H264B_E_CUDA;
+            }
+        }
+        if (cudaEventCreateWithFlags(&w.e_scan, cudaEventDisableTiming) != cudaSuccess) {
             h264b_scheduler_destroy(s);
-            return rc;
+            return H264B_E_CUDA;
         }
     }
     *out = s;
@@ -109,10 +136,19 @@ int32_t h264b_scheduler_create(const int32_t *devices, uint32_t n_devices, h264b
 void h264b_scheduler_destroy(h264b_scheduler *s) {
     if (!s) return;
     for (Worker &w : s->workers) {
-        if (!w.ctx) continue;
-        for (int k = 0; k < kStreamSlots; k++)
-            if (w.stage[k]) h264b_host_free(w.ctx, w.stage[k]);
-        h264b_destroy(w.ctx);
+        if (!w.ctx[0]) continue;
+        cudaSetDevice(w.device);
+        cudaDeviceSynchronize();
+        for (Grown *g : {&w.h_stream, &w.h_bins, &w.h_fin, &w.h_nals, &w.h_small})
+            if (g->p) cudaFreeHost(g->p);
+        for (Grown *g : {&w.d_stream, &w.d_rbsp, &w.d_nals, &w.d_sum, &w.d_off, &w.d_len, &w.d_snal, &w.d_offp, &w.d_lenp,
+                         &w.d_perm, &w.d_nops, &w.d_qp, &w.d_boff, &w.d_bins, &w.d_fin, &w.d_ops})
+            if (g->p) cudaFree(g->p);
+        if (w.e_scan) cudaEventDestroy(w.e_scan);
+        for (int c = 0; c < kClasses; c++) {
+            if (w.e_done[c]) cudaEventDestroy(w.e_done[c]);
+            if (w.ctx[c]) h264b_destroy(w.ctx[c]);
+        }
     }
     delete s;
 }
@@ -172,134 +208,230 @@ int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264
         s->device_bytes[best] += ts[k].end - ts[k].begin;
         s->stream_device[ts[k].index] = (int32_t)best;
     }
-    // ---- per device: streams with the longest slices first, cut into jobs of ~group_bytes
-    std::vector<std::vector<DeviceJob>> jobs(nd);
-    for (uint32_t d = 0; d < nd; d++) {
-        std::stable_sort(mine[d].begin(), mine[d].end(), [&](uint32_t a, uint32_t b) { return ts[a].longest > ts[b].longest; });
-        DeviceJob cur;
-        for (uint32_t k : mine[d]) {
-            const uint64_t len = ts[k].end - ts[k].begin;
-            if (!cur.streams.empty() && cur.bytes + len > group_bytes) {
-                jobs[d].push_back(std::move(cur));
-                cur = DeviceJob();
-            }
-            cur.base.push_back(cur.bytes);
-            cur.streams.push_back(k);
-            cur.bytes += len;
-            cur.n_slices += J.streams[ts[k].index].n_slices;
-            s->stream_job[ts[k].index] = (uint32_t)jobs[d].size();
-        }
-        if (!cur.streams.empty()) jobs[d].push_back(std::move(cur));
-        s->device_jobs[d] = (uint32_t)jobs[d].size();
-    }
-
-    // ---- one worker thread per device
+    (void)group_bytes;
+    // ---- one worker thread per device.  The device's share goes through ONE split + strip pass; its slices then run in
+    // kClasses launches by length (longest class first, each on its own context = CUDA stream, side by side): a slice is
+    // serial work, so the launch holding the 1 MB slices lasts two orders of magnitude longer than the one holding the
+    // 1 KB slices, whose results are on the host long before (per-slice completion times: tail latency).
     const Clock::time_point t_start = Clock::now();
     auto ms_since = [&](Clock::time_point t) { return std::chrono::duration<double, std::milli>(t - t_start).count(); };
     std::vector<std::thread> threads;
     for (uint32_t d = 0; d < nd; d++) {
         threads.emplace_back([&, d]() {
+            h264b::TraceRange trace_range("h264b:scheduler_worker");
             Worker &w = s->workers[d];
             w.rc = H264B_OK;
             w.err.clear();
-            const std::vector<DeviceJob> &dj = jobs[d];
-            auto fail = [&](int rc, const char *what) {
+            cudaSetDevice(w.device);
+            auto fail = [&](int rc, const std::string &what) {
                 w.rc = rc;
-                w.err = std::string(what) + ": " + h264b_last_error(w.ctx);
+                w.err = what;
             };
-            uint64_t ticket[kStreamSlots] = {0, 0, 0};
-            Clock::time_point first_submit;
-            bool any = false;
-            auto collect = [&](size_t q) -> bool {  // wait for device job q and scatter its results
-                const DeviceJob &g = dj[q];
-                h264b_stream_result r;
-                const int32_t rc = h264b_stream_wait(w.ctx, ticket[q % kStreamSlots], &r);
-                const double t_done = ms_since(Clock::now());
-                if (rc != H264B_OK) {
-                    fail(rc, "stream_wait");
-                    return false;
-                }
-                if (r.n_slices != g.n_slices) {
-                    w.rc = H264B_E_INVALID;
-                    w.err = "a device job found " + std::to_string(r.n_slices) + " slice NAL units, its streams announce " +
-                            std::to_string(g.n_slices);
-                    return false;
-                }
-                // slices: job row -> batch row
-                uint32_t row = 0;
-                for (size_t k = 0; k < g.streams.size(); k++) {
-                    const h264b_batch_stream &b = J.streams[ts[g.streams[k]].index];
-                    for (uint32_t x = 0; x < b.n_slices; x++, row++) {
-                        const uint32_t br = b.first_slice + x;
-                        s->fin[br] = r.final[row];
-                        s->slice_done_ms[br] = t_done;
-                        const uint64_t words = r.bins_off[row + 1] - r.bins_off[row];
-                        memcpy(s->bins.data() + s->bins_off[br], r.bins + r.bins_off[row], (size_t)words * 4);
-                    }
-                }
-                // NAL units: those that lie inside one stream's staged extent (the 4-byte unit that the next stream's
-                // leading start code forms is nobody's)
-                size_t k = 0;
-                for (uint64_t i = 0; i < r.scan.n_nals; i++) {
-                    const h264b_nal &u = r.nals[i];
-                    while (k + 1 < g.streams.size() && u.start >= g.base[k + 1]) k++;
-                    const TrimmedStream &t = ts[g.streams[k]];
-                    const uint64_t lo = g.base[k], hi = g.base[k] + (t.end - t.begin);
-                    if (u.start < lo + 4 || u.start + u.num_bytes > hi) continue;
-                    h264b_nal v = u;
-                    v.start = u.start - lo + t.begin;
-                    v.rbsp_off = u.rbsp_off - lo + t.begin;
-                    s->stream_nals[t.index].push_back(v);
-                }
+            auto grow_pin = [&](Grown &g, size_t bytes) -> bool {
+                if (bytes < 256) bytes = 256;
+                if (g.bytes >= bytes) return true;
+                if (g.p) cudaFreeHost(g.p);
+                g.p = nullptr, g.bytes = 0;
+                if (cudaHostAlloc(&g.p, bytes + bytes / 8, cudaHostAllocDefault) != cudaSuccess) return false;
+                g.bytes = bytes + bytes / 8;
                 return true;
             };
-            for (size_t q = 0; q < dj.size(); q++) {
-                if (q >= (size_t)kStreamSlots && !collect(q - kStreamSlots)) return;
-                const DeviceJob &g = dj[q];
-                const int slot = (int)(q % kStreamSlots);
-                if (w.stage_bytes[slot] < g.bytes + 64) {
-                    if (w.stage[slot]) h264b_host_free(w.ctx, w.stage[slot]);
-                    w.stage[slot] = nullptr;
-                    void *p = nullptr;
-                    const size_t want = (size_t)(g.bytes + 64) + (size_t)(g.bytes / 8);
-                    if (h264b_host_alloc(w.ctx, want, &p) != H264B_OK) return fail(H264B_E_NOMEM, "host_alloc");
-                    w.stage[slot] = (uint8_t *)p;
-                    w.stage_bytes[slot] = want;
-                }
-                w.j_nops[slot].clear();
-                w.j_qp[slot].clear();
-                for (size_t k = 0; k < g.streams.size(); k++) {
-                    const TrimmedStream &t = ts[g.streams[k]];
-                    const h264b_batch_stream &b = J.streams[t.index];
-                    memcpy(w.stage[slot] + g.base[k], b.stream + t.begin, (size_t)(t.end - t.begin));
-                    for (uint32_t x = 0; x < b.n_slices; x++) {
-                        if (J.n_ops) w.j_nops[slot].push_back(J.n_ops[b.first_slice + x]);
-                        w.j_qp[slot].push_back(J.qp[b.first_slice + x]);
-                    }
-                }
-                h264b_stream_job sj;
-                memset(&sj, 0, sizeof(sj));
-                sj.stream = w.stage[slot];
-                sj.n = g.bytes;
-                sj.slice_data_offset = J.slice_data_offset;
-                sj.n_ctx = J.n_ctx;
-                sj.ops = J.ops;
-                sj.n_ops_max = J.n_ops_max;
-                sj.n_ops = J.n_ops ? w.j_nops[slot].data() : nullptr;
-                sj.qp = w.j_qp[slot].data();
-                sj.max_slices = g.n_slices;
-                sj.flags = J.flags & (H264B_TABLES_SPEC | H264B_BYPASS_SPEC_OR | H264B_CABAC_FINAL_TERMINATE);
-                if (!any) {
-                    first_submit = Clock::now();
-                    any = true;
-                }
-                if (g.n_slices == 0) sj.qp = nullptr;
-                const int32_t rc = h264b_stream_submit(w.ctx, &sj, &ticket[slot]);
-                if (rc != H264B_OK) return fail(rc, "stream_submit");
+            auto grow_dev = [&](Grown &g, size_t bytes) -> bool {
+                if (bytes < 256) bytes = 256;
+                if (g.bytes >= bytes) return true;
+                if (g.p) cudaFree(g.p);
+                g.p = nullptr, g.bytes = 0;
+                if (cudaMalloc(&g.p, bytes + bytes / 8) != cudaSuccess) return false;
+                g.bytes = bytes + bytes / 8;
+                return true;
+            };
+            const std::vector<uint32_t> &my = mine[d];
+            if (my.empty()) return;
+            s->device_jobs[d] = 1;
+            // streams in stream-index order (so that a device's slice rows ascend), staged back to back
+            std::vector<uint32_t> order(my);
+            std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return ts[x].index < ts[y].index; });
+            std::vector<uint64_t> base(order.size() + 1, 0);
+            uint32_t n_sl = 0;
+            for (size_t k = 0; k < order.size(); k++) {
+                base[k + 1] = base[k] + (ts[order[k]].end - ts[order[k]].begin);
+                n_sl += J.streams[ts[order[k]].index].n_slices;
+                s->stream_job[ts[order[k]].index] = 0;
             }
-            for (size_t q = dj.size() > (size_t)kStreamSlots ? dj.size() - kStreamSlots : 0; q < dj.size(); q++)
-                if (!collect(q)) return;
-            if (any) s->device_busy_ms[d] = std::chrono::duration<double, std::milli>(Clock::now() - first_submit).count();
+            const uint64_t n = base.back();
+            const Clock::time_point t_first = Clock::now();
+            if (!grow_pin(w.h_stream, n + 64) || !grow_dev(w.d_stream, n + 64) || !grow_dev(w.d_rbsp, n + 64))
+                return fail(H264B_E_NOMEM, "out of memory staging the device's streams");
+            for (size_t k = 0; k < order.size(); k++) {
+                const TrimmedStream &t = ts[order[k]];
+                memcpy((uint8_t *)w.h_stream.p + base[k], J.streams[t.index].stream + t.begin, (size_t)(t.end - t.begin));
+            }
+            // the device's slice rows, and their order by length (longest first; ties: the lower row)
+            std::vector<uint32_t> rows;
+            rows.reserve(n_sl);
+            for (uint32_t k : order) {
+                const h264b_batch_stream &b = J.streams[ts[k].index];
+                for (uint32_t x = 0; x < b.n_slices; x++) rows.push_back(b.first_slice + x);
+            }
+            auto ops_of = [&](uint32_t row) { return J.n_ops ? std::min(J.n_ops[row], J.n_ops_max) : J.n_ops_max; };
+            std::vector<uint32_t> perm(n_sl);
+            for (uint32_t k = 0; k < n_sl; k++) perm[k] = k;
+            std::stable_sort(perm.begin(), perm.end(), [&](uint32_t x, uint32_t y) { return ops_of(rows[x]) > ops_of(rows[y]); });
+            // classes: more than 1/2, 1/8, 1/32, 1/128 of the longest slice, and the rest
+            uint32_t cls_begin[kClasses + 1];
+            {
+                const uint64_t top = n_sl ? ops_of(rows[perm[0]]) : 0;
+                const uint64_t thr[kClasses - 1] = {top / 2, top / 8, top / 32, top / 128};
+                uint32_t k = 0;
+                for (int c = 0; c < kClasses - 1; c++) {
+                    cls_begin[c] = k;
+                    while (k < n_sl && ops_of(rows[perm[k]]) > thr[c]) k++;
+                }
+                cls_begin[kClasses - 1] = k;
+                cls_begin[kClasses] = n_sl;
+            }
+            const uint32_t nal_cap = (uint32_t)std::min<uint64_t>(n / 64 + 1024 + 2 * (uint64_t)order.size(), 0xFFFFFFF0ull);
+            const size_t ms = n_sl ? n_sl : 1;
+            // per-slice inputs in class order
+            if (!grow_pin(w.h_small, ms * (4 + 4 + sizeof(h264b_slice_qp) + 8) + 8 + 256))
+                return fail(H264B_E_NOMEM, "out of pinned memory");
+            uint32_t *h_perm = (uint32_t *)w.h_small.p;
+            uint32_t *h_nops = h_perm + ms;
+            h264b_slice_qp *h_qp = (h264b_slice_qp *)(h_nops + ms);
+            uint64_t *h_boff = (uint64_t *)(h_qp + ms);
+            h_boff[0] = 0;
+            for (uint32_t k = 0; k < n_sl; k++) {
+                const uint32_t row = rows[perm[k]];
+                h_perm[k] = perm[k];
+                h_nops[k] = ops_of(row);
+                h_qp[k] = J.qp[row];
+                h_boff[k + 1] = h_boff[k] + ((uint64_t)h_nops[k] + 1 + 31) / 32;
+            }
+            const size_t total_words = (size_t)h_boff[n_sl];
+            if (!grow_dev(w.d_nals, (size_t)nal_cap * sizeof(h264b_nal)) || !grow_dev(w.d_sum, 256) ||
+                !grow_dev(w.d_off, ms * 8) || !grow_dev(w.d_len, ms * 4) || !grow_dev(w.d_snal, ms * 4 + 16) ||
+                !grow_dev(w.d_offp, ms * 8) || !grow_dev(w.d_lenp, ms * 4) || !grow_dev(w.d_perm, ms * 4) ||
+                !grow_dev(w.d_nops, ms * 4) || !grow_dev(w.d_qp, ms * sizeof(h264b_slice_qp)) ||
+                !grow_dev(w.d_boff, (ms + 1) * 8) || !grow_dev(w.d_bins, total_words * 4 + 16) ||
+                !grow_dev(w.d_fin, ms * sizeof(h264b_cabac_final)) || !grow_dev(w.d_ops, (size_t)J.n_ops_max * 2 + 16) ||
+                !grow_pin(w.h_bins, total_words * 4 + 16) || !grow_pin(w.h_fin, ms * sizeof(h264b_cabac_final)) ||
+                !grow_pin(w.h_nals, (size_t)nal_cap * sizeof(h264b_nal) + 256))
+                return fail(H264B_E_NOMEM, "out of memory for the device's slice arrays");
+            // ---- split + strip, slice list, class order (context 0's stream)
+            h264b_ctx *c0 = w.ctx[0];
+            cudaStream_t s0 = c0->stream;
+            bool ok = cudaMemcpyAsync(w.d_stream.p, w.h_stream.p, n, cudaMemcpyHostToDevice, s0) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(w.d_perm.p, h_perm, ms * 4, cudaMemcpyHostToDevice, s0) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(w.d_nops.p, h_nops, ms * 4, cudaMemcpyHostToDevice, s0) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(w.d_qp.p, h_qp, ms * sizeof(h264b_slice_qp), cudaMemcpyHostToDevice, s0) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(w.d_boff.p, h_boff, (ms + 1) * 8, cudaMemcpyHostToDevice, s0) == cudaSuccess;
+            if (J.n_ops_max)
+                ok = ok && cudaMemcpyAsync(w.d_ops.p, J.ops, (size_t)J.n_ops_max * 2, cudaMemcpyHostToDevice, s0) == cudaSuccess;
+            if (!ok) return fail(H264B_E_CUDA, "copying the device's share in failed");
+            uint32_t *d_ns = (uint32_t *)((uint8_t *)w.d_sum.p + 64);
+            int rc = h264b_annexb_scan_dev(c0, (const uint8_t *)w.d_stream.p, n, (uint8_t *)w.d_rbsp.p, (h264b_nal *)w.d_nals.p,
+                                           nullptr, nal_cap, (h264b_scan_summary *)w.d_sum.p, 0);
+            if (rc == H264B_OK)
+                rc = h264b_slice_select_dev(c0, (const h264b_nal *)w.d_nals.p, (const h264b_scan_summary *)w.d_sum.p, nal_cap,
+                                            J.slice_data_offset, n_sl, (uint64_t *)w.d_off.p, (uint32_t *)w.d_len.p,
+                                            (uint32_t *)w.d_snal.p, d_ns);
+            if (rc != H264B_OK) return fail(rc, std::string("split + strip: ") + h264b_last_error(c0));
+            if (n_sl)
+                gather_slices_kernel<<<(n_sl + 255) / 256, 256, 0, s0>>>((const uint64_t *)w.d_off.p, (const uint32_t *)w.d_len.p,
+                                                                        (const uint32_t *)w.d_perm.p, n_sl, (uint64_t *)w.d_offp.p,
+                                                                        (uint32_t *)w.d_lenp.p);
+            cudaEventRecord(w.e_scan, s0);
+            if (getenv("H264B_SCHED_TRACE")) {
+                cudaStreamSynchronize(s0);
+                fprintf(stderr, "h264b scheduler: device %d: %.1f MB staged, split + strip done at %.1f ms\n", w.device, n / 1e6,
+                        ms_since(Clock::now()));
+            }
+            // ---- the classes' CABAC launches and their results, each on its own stream
+            bool launched[kClasses] = {false, false, false, false, false};
+            for (int c = 0; c < kClasses; c++) {
+                const uint32_t k0 = cls_begin[c], k1 = cls_begin[c + 1];
+                if (k1 == k0) continue;
+                h264b_ctx *cc = w.ctx[c];
+                cudaStream_t sc = cc->stream;
+                cudaStreamWaitEvent(sc, w.e_scan, 0);
+                h264b_cabac_job cj;
+                memset(&cj, 0, sizeof(cj));
+                cj.bytes = (const uint8_t *)w.d_rbsp.p;
+                cj.total_bytes = n + 16;
+                cj.off = (const uint64_t *)w.d_offp.p + k0;
+                cj.len = (const uint32_t *)w.d_lenp.p + k0;
+                cj.n_slices = k1 - k0;
+                cj.n_ctx = J.n_ctx;
+                cj.ops = (const uint16_t *)w.d_ops.p;
+                cj.n_ops_max = J.n_ops_max;
+                cj.n_ops = (const uint32_t *)w.d_nops.p + k0;
+                cj.qp = (const h264b_slice_qp *)w.d_qp.p + k0;
+                cj.bins = (uint32_t *)w.d_bins.p;
+                cj.bins_off = (const uint64_t *)w.d_boff.p + k0;
+                cj.final = (h264b_cabac_final *)w.d_fin.p + k0;
+                cj.flags = J.flags & (H264B_TABLES_SPEC | H264B_BYPASS_SPEC_OR | H264B_CABAC_FINAL_TERMINATE);
+                rc = h264b_cabac_decode_dev(cc, &cj);
+                if (rc != H264B_OK) return fail(rc, std::string("cabac: ") + h264b_last_error(cc));
+                const size_t w0 = (size_t)h_boff[k0], w1 = (size_t)h_boff[k1];
+                cudaMemcpyAsync((uint32_t *)w.h_bins.p + w0, (const uint32_t *)w.d_bins.p + w0, (w1 - w0) * 4, cudaMemcpyDeviceToHost, sc);
+                cudaMemcpyAsync((h264b_cabac_final *)w.h_fin.p + k0, (const h264b_cabac_final *)w.d_fin.p + k0,
+                                (size_t)(k1 - k0) * sizeof(h264b_cabac_final), cudaMemcpyDeviceToHost, sc);
+                cudaEventRecord(w.e_done[c], sc);
+                launched[c] = true;
+            }
+            // the NAL index (context 0's stream, behind its class launch)
+            cudaMemcpyAsync(w.h_nals.p, w.d_sum.p, 128, cudaMemcpyDeviceToHost, s0);
+            cudaMemcpyAsync((uint8_t *)w.h_nals.p + 256, w.d_nals.p, (size_t)nal_cap * sizeof(h264b_nal), cudaMemcpyDeviceToHost, s0);
+            // ---- collect the classes as they finish
+            int pending = 0;
+            for (int c = 0; c < kClasses; c++) pending += launched[c] ? 1 : 0;
+            while (pending) {
+                bool progressed = false;
+                for (int c = 0; c < kClasses; c++) {
+                    if (!launched[c]) continue;
+                    const cudaError_t q = cudaEventQuery(w.e_done[c]);
+                    if (q == cudaErrorNotReady) continue;
+                    if (q != cudaSuccess) return fail(H264B_E_CUDA, std::string("a class launch failed: ") + cudaGetErrorString(q));
+                    const double t_done = ms_since(Clock::now());
+                    if (getenv("H264B_SCHED_TRACE"))
+                        fprintf(stderr, "h264b scheduler: device %d class %d: %u slices (longest %u ops) done at %.1f ms\n", w.device,
+                                c, cls_begin[c + 1] - cls_begin[c], ops_of(rows[perm[cls_begin[c]]]), t_done);
+                    for (uint32_t k = cls_begin[c]; k < cls_begin[c + 1]; k++) {
+                        const uint32_t row = rows[perm[k]];
+                        s->fin[row] = ((const h264b_cabac_final *)w.h_fin.p)[k];
+                        s->slice_done_ms[row] = t_done;
+                        memcpy(s->bins.data() + s->bins_off[row], (const uint32_t *)w.h_bins.p + h_boff[k],
+                               (size_t)(h_boff[k + 1] - h_boff[k]) * 4);
+                    }
+                    launched[c] = false;
+                    pending--;
+                    progressed = true;
+                }
+                if (!progressed) std::this_thread::sleep_for(std::chrono::microseconds(50));
+            }
+            if (cudaStreamSynchronize(s0) != cudaSuccess) return fail(H264B_E_CUDA, "the NAL index did not arrive");
+            const h264b_scan_summary *sum = (const h264b_scan_summary *)w.h_nals.p;
+            const uint32_t found = *(const uint32_t *)((const uint8_t *)w.h_nals.p + 64);
+            if (sum->status != H264B_OK) return fail(H264B_E_CAPACITY, "more NAL units than the index holds");
+            if (found != n_sl)
+                return fail(H264B_E_INVALID, "the device's streams hold " + std::to_string(found) + " slice NAL units, the batch announces " +
+                                                 std::to_string(n_sl));
+            // NAL units: those that lie inside one stream's staged extent (the 4-byte unit that the next stream's leading
+            // start code forms is nobody's)
+            const h264b_nal *un = (const h264b_nal *)((const uint8_t *)w.h_nals.p + 256);
+            size_t k = 0;
+            for (uint64_t i = 0; i < sum->n_nals; i++) {
+                const h264b_nal &u = un[i];
+                while (k + 1 < order.size() && u.start >= base[k + 1]) k++;
+                const TrimmedStream &t = ts[order[k]];
+                const uint64_t lo = base[k], hi = base[k + 1];
+                if (u.start < lo + 4 || u.start + u.num_bytes > hi) continue;
+                h264b_nal v = u;
+                v.start = u.start - lo + t.begin;
+                v.rbsp_off = u.rbsp_off - lo + t.begin;
+                s->stream_nals[t.index].push_back(v);
+            }
+            s->device_busy_ms[d] = std::chrono::duration<double, std::milli>(Clock::now() - t_first).count();
         });
     }
     for (std::thread &t : threads) t.join();

@@ -67,6 +67,7 @@ struct CabacArgs {
     uint32_t map_mode;     // 0: warp 0 of a CTA takes its longest bundle, 1: the highest warp does, 2: launch order,
                            // 3: slot_bundle[CTA x warps + warp] (bundle_assign_kernel), -1: none
     const int32_t *slot_bundle;
+    uint32_t rounds;       // map_mode 3: bundles per slot (else 1)
 };
 
 // ---------------------------------------------------------------------------------------------- length bundles
@@ -148,18 +149,18 @@ constexpr int kSlotsMax = 5;  // warps per scheduler = kMaxWarpsPerCta / 4
 
 __global__ void __launch_bounds__(1024) bundle_assign_kernel(const uint32_t *n_ops, const uint32_t *order, uint32_t n_bound,
                                                              const uint32_t *d_n, uint32_t cap_ops, uint32_t lpw,
-                                                             uint32_t n_sched, uint32_t slots, uint32_t W,
+                                                             uint32_t n_sched, uint32_t slots, uint32_t rounds, uint32_t W,
                                                              int32_t *slot_bundle) {
     extern __shared__ uint32_t sm_u32[];
     uint32_t *len = sm_u32;                       // [n_bundles] ops of each bundle (its longest slice)
-    uint32_t *sum = len + n_sched * slots;        // [n_sched] weighted ops placed so far
+    uint32_t *sum = len + n_sched * slots * rounds;  // [n_sched] weighted ops placed so far
     uint32_t *cnt = sum + n_sched;                // [n_sched] bundles placed so far
     __shared__ unsigned long long total_s;
     const uint32_t n_slices = d_n && *d_n < n_bound ? *d_n : n_bound;
     const uint32_t n_bundles = (n_slices + lpw - 1) / lpw;
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) total_s = 0;
-    for (uint32_t k = tid; k < n_sched * slots; k += blockDim.x) slot_bundle[k] = -1;
+    for (uint32_t k = tid; k < n_sched * slots * rounds; k += blockDim.x) slot_bundle[k] = -1;
     for (uint32_t k = tid; k < n_sched; k += blockDim.x) sum[k] = 0, cnt[k] = 0;
     __syncthreads();
     unsigned long long part = 0;
@@ -179,9 +180,9 @@ __global__ void __launch_bounds__(1024) bundle_assign_kernel(const uint32_t *n_o
     if (tid >= 32) return;
     // a bundle whose own chain (x 2.2) comes near the balanced load of a scheduler counts 1.5 times
     const unsigned long long critical = total_s * 4 / (5ull * n_sched);  // 0.8 x total / schedulers
-    // key of a scheduler: weighted ops / 2 (22 bits are plenty: 5 bundles of < 2^20 ops, weighted 1.5) << 10 | its index; the
+    // key of a scheduler: weighted ops / 8 (22 bits: 2^25 ops; more saturate) << 10 | its index; the
     // least loaded one (ties: the lowest index) is the minimum key -- one warp reduction per bundle
-    const auto key_of = [&](uint32_t k) { return sum[k] >= 0xFFFFFFF0u ? 0xFFFFFFFFu : ((sum[k] >> 1) << 10) | k; };
+    const auto key_of = [&](uint32_t k) { return sum[k] >= 0xFFFFFFF0u ? 0xFFFFFFFFu : sum[k] >= (1u << 25) ? (0x3FFFFEu << 10) | k : ((sum[k] >> 3) << 10) | k; };
     uint32_t my_key = 0xFFFFFFFFu;  // least loaded scheduler among this lane's (lane, lane + 32, ...)
     for (uint32_t k = lane; k < n_sched; k += 32) my_key = min(my_key, key_of(k));
     for (uint32_t g = 0; g < n_bundles; g++) {  // bundles come longest first
@@ -189,10 +190,12 @@ __global__ void __launch_bounds__(1024) bundle_assign_kernel(const uint32_t *n_o
         if ((sidx & 31u) == (uint32_t)lane) {  // its owner places the bundle and looks for its new minimum
             const uint32_t L = len[g];
             const uint32_t kpos = cnt[sidx];
-            slot_bundle[(sidx >> 2) * W + kpos * 4 + (sidx & 3u)] = (int32_t)g;
+            // the scheduler's bundles fill its warps round by round: the longest ones run side by side first
+            const uint32_t round = kpos / slots, slot = kpos % slots;
+            slot_bundle[(round * (n_sched >> 2) + (sidx >> 2)) * W + slot * 4 + (sidx & 3u)] = (int32_t)g;
             cnt[sidx] = kpos + 1;
             const uint32_t wgt = ((unsigned long long)L * 11 / 5 > critical) ? L + L / 2 : L;
-            sum[sidx] = kpos + 1 >= slots ? 0xFFFFFFF0u : sum[sidx] + wgt;
+            sum[sidx] = kpos + 1 >= slots * rounds ? 0xFFFFFFF0u : sum[sidx] + wgt;
             my_key = 0xFFFFFFFFu;
             for (uint32_t k = lane; k < n_sched; k += 32) my_key = min(my_key, key_of(k));
         }
@@ -259,8 +262,11 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(C
     // its longest bundle).  More bundles than one wave holds: small CTAs in launch order.
     const uint32_t rank = a.map_mode == 1 ? (W - 1u - (uint32_t)warp) : (uint32_t)warp;
     uint32_t gw = a.map_mode == 2 ? blockIdx.x * W + (uint32_t)warp : rank * gridDim.x + blockIdx.x;
-    if (a.map_mode == 3) gw = (uint32_t)a.slot_bundle[blockIdx.x * W + (uint32_t)warp];  // (-1 -> no bundle)
-    if (gw >= n_bundles) return;
+    // map_mode 3: the warp runs the bundles of its slot one after the other (rounds: as many as the launch needs for all
+    // bundles to have a slot: one, unless the context rows leave room for few warps); -1: no bundle
+    for (uint32_t round = 0; round < a.rounds; round++) {
+    if (a.map_mode == 3) gw = (uint32_t)a.slot_bundle[(round * gridDim.x + blockIdx.x) * W + (uint32_t)warp];
+    if (__all_sync(0xFFFFFFFFu, gw >= n_bundles)) continue;  // (a vote: gw is the same in every lane)
     const uint32_t index = gw * a.lanes_per_warp + lane;
     // Lanes without a slice of their own (a partly filled warp) shadow the warp's first lane: they decode the same
     // slice and store nothing, so the loops below never have to predicate on "is there a slice in this lane".
@@ -1003,6 +1009,8 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(C
         generic_op(i, op, live && i < my_ops);
     }
     if (live) finish_lane();
+    __syncwarp();  // every lane is done with the context rows before the next bundle's states go there
+    }
 }
 
 static int env_int(const char *name, int dflt) {
@@ -1011,6 +1019,7 @@ static int env_int(const char *name, int dflt) {
 }
 
 int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n_slices) {
+    TraceRange trace_range("h264b:cabac_decode");
     const h264b_cabac_job &j = *job;
     if (j.n_ctx < 1 || j.n_ctx > 1024) return set_error(ctx, H264B_E_INVALID, "cabac: n_ctx must be 1..1024");
     if (!j.n_slices) return H264B_OK;
@@ -1045,30 +1054,37 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
     const size_t tab_bytes = 1024 + (k_loop ? kTab16Bytes : 2048);
     uint32_t w_fit = (uint32_t)((kMaxSmemPerCta - tab_bytes) / ((size_t)(j.n_ctx + 2) * 32));
     if (w_fit > (uint32_t)kMaxWarpsPerCta) w_fit = kMaxWarpsPerCta;
-    uint32_t W = (a.n_warps + sms - 1) / sms;
-    if (k_w > 0) W = (uint32_t)k_w;
-    if (W > w_fit || (k_w > 0 && k_w < 4)) {
-        W = w_fit < 4 ? w_fit : 4;
-        if (k_w > 0 && k_w < 4) W = (uint32_t)k_w;
-        a.map_mode = 2;
-    }
-    if (W < 1) W = 1;
-    uint32_t grid = (a.n_warps + W - 1) / W;
-    // bundles -> schedulers by bundle_assign_kernel: one wave of full CTAs with a slot to spare on every scheduler
+    if (ctx->cabac_max_warps > 0 && w_fit > (uint32_t)ctx->cabac_max_warps) w_fit = (uint32_t)ctx->cabac_max_warps;
+    // bundles -> schedulers by bundle_assign_kernel: one wave of full CTAs with a slot to spare on every scheduler; when
+    // the context rows leave room for fewer warps than there are bundles, every warp runs several bundles in turn
     uint32_t slots = (a.n_warps + sms * 4 - 1) / (sms * 4) + 1;
     if (slots > (uint32_t)kSlotsMax) slots = kSlotsMax;
-    const bool assign = a.map_mode == 3 && lpw > 1 && j.n_ops && slots * 4 <= w_fit && a.n_warps <= (uint64_t)sms * 4 * slots &&
-                        a.n_warps > sms * 4;
+    if (slots * 4 > w_fit) slots = w_fit / 4;
+    uint32_t rounds = slots ? (uint32_t)((a.n_warps + (uint64_t)sms * 4 * slots - 1) / ((uint64_t)sms * 4 * slots)) : 0;
+    const bool assign = a.map_mode == 3 && k_w <= 0 && lpw > 1 && j.n_ops && slots >= 1 && rounds >= 1 && rounds <= 64 &&
+                        a.n_warps > sms * 4 && ((uint64_t)sms * 4 * slots * rounds + 2ull * sms * 4) * 4 <= 200 * 1024;
     if (a.map_mode == 3 && !assign) a.map_mode = 1;
+    uint32_t W, grid;
     if (assign) {
         W = slots * 4;
         grid = sms;
+    } else {
+        W = (a.n_warps + sms - 1) / sms;
+        if (k_w > 0) W = (uint32_t)k_w;
+        if (W > w_fit || (k_w > 0 && k_w < 4)) {
+            W = w_fit < 4 ? w_fit : 4;
+            if (k_w > 0 && k_w < 4) W = (uint32_t)k_w;
+            a.map_mode = 2;
+        }
+        if (W < 1) W = 1;
+        grid = (a.n_warps + W - 1) / W;
     }
     a.slot_bundle = nullptr;
+    a.rounds = 1;
     if (lpw > 1 && j.n_ops) {  // bundles of equally long slices
         void *d_sort;
         const size_t order_bytes = ((size_t)j.n_slices * 4 + 15) & ~(size_t)15;
-        int rc = ensure_dev(ctx, 16, sizeof(SortScratch) + order_bytes + (size_t)sms * 4 * kSlotsMax * 4, &d_sort);
+        int rc = ensure_dev(ctx, 16, sizeof(SortScratch) + order_bytes + (size_t)sms * 4 * (assign ? slots * rounds : 1) * 4, &d_sort);
         if (rc) return rc;
         SortScratch *ss = (SortScratch *)d_sort;
         uint32_t *order = (uint32_t *)(ss + 1);
@@ -1086,16 +1102,28 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
         a.order = order;
         if (assign) {
             int32_t *slot_bundle = (int32_t *)((uint8_t *)order + order_bytes);
-            const size_t sm_assign = ((size_t)sms * 4 * slots + 2 * (size_t)sms * 4) * 4;
+            const size_t sm_assign = ((size_t)sms * 4 * slots * rounds + 2 * (size_t)sms * 4) * 4;
+            if (sm_assign > 48 * 1024)
+                H264B_CUDA(ctx, cudaFuncSetAttribute(bundle_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_assign));
             bundle_assign_kernel<<<1, 1024, sm_assign, ctx->stream>>>(j.n_ops, order, j.n_slices, d_n_slices, j.n_ops_max, lpw,
-                                                                     sms * 4, slots, W, slot_bundle);
+                                                                     sms * 4, slots, rounds, W, slot_bundle);
             H264B_LAUNCH_CHECK(ctx, "bundle_assign_kernel");
             a.slot_bundle = slot_bundle;
+            a.rounds = rounds;
         }
     }
     const size_t smem = tab_bytes + (size_t)W * (j.n_ctx + 2) * 32;
     if (k_loop == 2) {
-        H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // (one carveout for every launch of this kernel: launches that differ in their shared-memory split cannot share an SM,
+        //  and h264b_scheduler runs several side by side)
+        static bool carveout_set[64] = {false};
+        if (ctx->device < 64 && !carveout_set[ctx->device]) {
+            H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                 cudaSharedmemCarveoutMaxShared));
+            H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)kMaxSmemPerCta));
+            carveout_set[ctx->device] = true;
+        }
         cabac_decode_kernel<2><<<grid, W * 32, smem, ctx->stream>>>(a);
     } else if (k_loop) {
         H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

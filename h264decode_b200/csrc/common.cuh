@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges show up in Nsight Systems / ncu timelines, no library to link
+
 #include "../../include/h264b200.h"
 
 struct StreamSlot;
@@ -18,6 +20,7 @@ struct h264b_ctx {
     cudaStream_t stream;  // the one "_dev" work goes to (own_stream unless h264b_set_stream was called)
     char err[512];
     uint64_t launches;
+    int cabac_max_warps;  // 0: as many warps per CTA as fit; else a cap (launches that share the GPU: h264b_scheduler)
 
     // grow-only device scratch, in banks: [0] the direct ("_dev" and host-pointer) entry points, [1 + s] stream-job slot
     // s, whose kernels run on their own stream and may overlap the other slots'
@@ -64,6 +67,14 @@ struct StreamSlot {
 };
 
 namespace h264b {
+
+// a named range on the calling host thread for the lifetime of the object (tracing: SURVEY.md section 5)
+struct TraceRange {
+    explicit TraceRange(const char *name) { nvtxRangePushA(name); }
+    ~TraceRange() { nvtxRangePop(); }
+    TraceRange(const TraceRange &) = delete;
+    TraceRange &operator=(const TraceRange &) = delete;
+};
 
 int set_error(h264b_ctx *ctx, int code, const char *fmt, ...);
 int ensure_dev(h264b_ctx *ctx, int slot, size_t bytes, void **out);   // grow-only device buffer per slot

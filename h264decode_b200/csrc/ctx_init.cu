@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(256) ctx_init_bytes_kernel(const h264b_slice_q
 
 int launch_ctx_init(h264b_ctx *ctx, const h264b_slice_qp *d_params, uint32_t n_slices, uint32_t n_ctx,
                     uint8_t *d_states, uint32_t flags) {
+    TraceRange trace_range("h264b:ctx_init");
     if (n_ctx < 1 || n_ctx > kCtxMax) return set_error(ctx, H264B_E_INVALID, "ctx_init: n_ctx must be 1..1024");
     if (!n_slices) return H264B_OK;
     const uint8_t *lut = ctx->d_state_lut[(flags & H264B_TABLES_SPEC) ? 1 : 0];

@@ -472,9 +472,10 @@ int32_t h264b_slice_select_dev(h264b_ctx *ctx, const h264b_nal *d_nals, const h2
  * one context and one worker thread per device and takes a whole batch of independent streams ("multi-camera batch",
  * BASELINE configs[4]):
  *   - streams are dealt to the devices longest first onto the least loaded one (LPT by bytes);
- *   - on its device a stream joins a job of ~group_bytes: the streams holding the longest slices go first (a slice is
- *     serial work: the job with the longest slices starts at once and runs beside the jobs that follow it), jobs run
- *     through h264b_stream_submit / h264b_stream_wait with three in flight per device;
+ *   - a device's share goes through one split + strip pass; its slices then run in five CABAC launches by length
+ *     (more than 1/2, 1/8, 1/32, 1/128 of the longest slice, and the rest), the longest class first, side by side on
+ *     streams of their own: a slice is serial work, so the launch with the 1 MB slices lasts two orders of magnitude
+ *     longer than the one with the 1 KB slices, whose results reach the host long before;
  *   - every slice's result carries the time at which it reached host memory (tail latency), every device the time it
  *     was busy.
  * No collective, no exchange between devices: slices share nothing.
@@ -503,12 +504,12 @@ typedef struct {
     const h264b_slice_qp *qp;  /* [total_slices] */
     uint32_t slice_data_offset;
     uint32_t flags;            /* H264B_TABLES_SPEC | H264B_BYPASS_SPEC_OR | H264B_CABAC_FINAL_TERMINATE */
-    uint64_t group_bytes;      /* stream bytes per device job; 0: 16 MiB */
+    uint64_t group_bytes;      /* reserved (0) */
 } h264b_batch_job;
 
 typedef struct {
     const int32_t *stream_device;    /* [n_streams] index into the scheduler's devices */
-    const uint32_t *stream_job;      /* [n_streams] job of that device the stream ran in */
+    const uint32_t *stream_job;      /* [n_streams] pass of that device the stream ran in (0: a share is one pass) */
     const uint64_t *stream_nal_off;  /* [n_streams + 1] the stream's NAL units are nals[stream_nal_off[i] .. [i + 1]) */
     const h264b_nal *nals;           /* start / rbsp_off relative to the stream's own first byte */
     const h264b_cabac_final *final;  /* [total_slices] */
@@ -519,7 +520,7 @@ typedef struct {
     uint32_t reserved;
     const double *device_busy_ms;    /* [n_devices] first submit to last wait */
     const uint64_t *device_bytes;    /* [n_devices] stream bytes dealt to the device */
-    const uint32_t *device_jobs;     /* [n_devices] */
+    const uint32_t *device_jobs;     /* [n_devices] passes (1, or 0 for a device without a stream) */
     double makespan_ms;
     uint64_t total_bins, total_nals;
 } h264b_batch_result;

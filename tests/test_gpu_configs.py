@@ -238,9 +238,10 @@ def test_streams_of_very_short_nal_units_and_many_parameter_sets():
 
 def test_scheduler_batch_of_streams_over_several_workers():
     """h264b_scheduler: a batch of independent streams (skewed sizes, some with bytes in front of their first start code
-    or without a closing start code) dealt to two workers -- here two contexts on the one GPU -- in many small device
-    jobs.  Every stream's NAL units must be the oracle's for that stream on its own, every slice's bins the ones the
-    test encoder coded, whatever job and worker the stream landed in."""
+    or without a closing start code) dealt to two workers -- here both on the one GPU -- each of which runs its share
+    through one split + strip pass and five CABAC launches by slice length.  Every stream's NAL units must be the
+    oracle's for that stream on its own, every slice's bins the ones the test encoder coded, whatever worker and launch
+    they landed in."""
     from h264decode_b200 import capi
     rng = np.random.default_rng(5)
     n_streams = 40
@@ -270,7 +271,7 @@ def test_scheduler_batch_of_streams_over_several_workers():
         r = sch.run(streams, per, ops, n_ops, qp, idc, 64, flags=flags, group_bytes=96 << 10)
     finally:
         sch.close()
-    assert r["device_jobs"].sum() > 6 and set(r["stream_device"][:n_streams]) == {0, 1} and r["stream_device"][-1] == -1
+    assert set(r["stream_device"][:n_streams]) == {0, 1} and r["stream_device"][-1] == -1
     assert abs(int(r["device_bytes"][0]) - int(r["device_bytes"][1])) < 0.25 * r["device_bytes"].sum()
     row = 0
     for i, b in enumerate(built):
