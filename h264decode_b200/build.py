@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libh264b200.so")
-SOURCES = ["api.cu", "annexb_scan.cu", "cabac_engine.cu", "ctx_init.cu", "slice_header.cu", "param_sets.cu", "ctx_glue.cu", "batch.cu"]
+SOURCES = ["api.cu", "annexb_scan.cu", "cabac_engine.cu", "ctx_init.cu", "slice_header.cu", "param_sets.cu", "ctx_glue.cu", "batch.cu", "mb_type.cu"]
 HEADERS = ["common.cuh", "annexb_local.cuh", "cabac_lane.cuh", "slice_header.cuh", "param_sets.cuh", "ctx_glue.cuh", "tables.inc", "../../include/h264b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

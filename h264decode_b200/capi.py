@@ -33,6 +33,7 @@ SYMBOLS = [
     "h264b_parse_sps", "h264b_parse_pps", "h264b_parse_sps_dev", "h264b_parse_pps_dev", "h264b_make_param_sets",
     "h264b_param_set_select_dev",
     "h264b_ctx_idx", "h264b_new_binarization", "h264b_init_cabac", "h264b_mb_bin_string", "h264b_bin_string_match",
+    "h264b_mb_type_decode_dev", "h264b_mb_type_decode",
     "h264b_scheduler_create", "h264b_scheduler_destroy", "h264b_scheduler_last_error", "h264b_scheduler_run",
 ]
 
@@ -71,6 +72,17 @@ class StreamJob(C.Structure):
                 ("ops", C.c_void_p), ("n_ops_max", C.c_uint32), ("n_ops", C.c_void_p), ("qp", C.c_void_p),
                 ("max_slices", C.c_uint32), ("flags", C.c_uint32), ("param_sets", C.c_void_p),
                 ("max_sps", C.c_uint32), ("max_pps", C.c_uint32), ("initial_sps", C.c_void_p), ("initial_pps", C.c_void_p)]
+
+
+class MbTypeJob(C.Structure):
+    _fields_ = [("bytes", C.c_void_p), ("total_bytes", C.c_uint64), ("off", C.c_void_p), ("len", C.c_void_p),
+                ("n_slices", C.c_uint32), ("n_ctx", C.c_uint32), ("slice_kind", C.c_void_p), ("n_mb", C.c_void_p),
+                ("n_mb_max", C.c_uint32), ("flags", C.c_uint32), ("qp", C.c_void_p), ("init_states", C.c_void_p),
+                ("mb_type", C.c_void_p), ("final", C.c_void_p), ("final_states", C.c_void_p)]
+
+
+MB_FINAL_DTYPE = np.dtype([("cod_i_range", "<i8"), ("cod_i_offset", "<i8"), ("bits_read", "<u8"), ("flags", "<u4"),
+                           ("n_bins", "<u4"), ("n_mb", "<u4"), ("reserved", "<u4")])
 
 
 class BatchStream(C.Structure):
@@ -228,6 +240,8 @@ def load():
         "h264b_init_cabac": (i32, [vp, u32, u32, vp, vp, vp, vp, vp, vp, vp, vp]),
         "h264b_mb_bin_string": (i32, [vp, u32, vp, vp, vp, vp, vp]),
         "h264b_bin_string_match": (i32, [vp, u32, vp, vp, vp, vp, vp]),
+        "h264b_mb_type_decode_dev": (i32, [vp, P(MbTypeJob)]),
+        "h264b_mb_type_decode": (i32, [vp, P(MbTypeJob)]),
         "h264b_scheduler_create": (i32, [vp, u32, P(vp)]),
         "h264b_scheduler_destroy": (None, [vp]),
         "h264b_scheduler_last_error": (C.c_char_p, [vp]),
@@ -588,6 +602,41 @@ class Context:
     def slice_headers_dev(self, params, d_bytes, total_bytes, d_nals, d_slice_nal, n_slices, d_out):
         self._check(_lib.h264b_slice_headers_dev(self.h, C.byref(params), d_bytes, total_bytes, None, None, None, None,
                                                  d_nals, d_slice_nal, n_slices, d_out))
+
+    def mb_type_decode(self, data, off, length, slice_kind, n_mb, n_ctx, qp=None, idc=None, init_states=None, flags=0,
+                       want_states=True):
+        """mb_type as a syntax element for every slice (slice_kind 0: I, 1: P / SP) -> (mb_type uint8[n_slices][n_mb_max],
+        final MB_FINAL_DTYPE[n_slices], final states | None)"""
+        d = np.ascontiguousarray(data, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        kind = np.ascontiguousarray(slice_kind, dtype=np.uint8)
+        n_mb = np.ascontiguousarray(n_mb, dtype=np.uint32)
+        ns = len(off)
+        n_max = int(n_mb.max()) if ns else 0
+        p = self.slice_qp(qp, idc) if qp is not None else None
+        init = None if init_states is None else np.ascontiguousarray(init_states, dtype=np.uint8)
+        out = np.zeros((ns, max(n_max, 1)), dtype=np.uint8)
+        fin = np.zeros(ns, dtype=MB_FINAL_DTYPE)
+        fst = np.zeros((ns, n_ctx), dtype=np.uint8) if want_states else None
+        j = MbTypeJob()
+        j.bytes, j.total_bytes = d.ctypes.data, len(d)
+        j.off, j.len, j.n_slices, j.n_ctx = off.ctypes.data, length.ctypes.data, ns, n_ctx
+        j.slice_kind, j.n_mb, j.n_mb_max, j.flags = kind.ctypes.data, n_mb.ctypes.data, max(n_max, 1), flags
+        j.qp = p.ctypes.data if p is not None else None
+        j.init_states = init.ctypes.data if init is not None else None
+        j.mb_type, j.final = out.ctypes.data, fin.ctypes.data
+        j.final_states = fst.ctypes.data if fst is not None else None
+        self._check(_lib.h264b_mb_type_decode(self.h, C.byref(j)))
+        return out, fin, fst
+
+    def mb_type_decode_dev(self, **kw):
+        """device pointers (ints): bytes, total_bytes, off, len, n_slices, n_ctx, slice_kind, n_mb, n_mb_max, flags, qp,
+        init_states, mb_type, final, final_states"""
+        j = MbTypeJob()
+        for k, v in kw.items():
+            setattr(j, k, v)
+        self._check(_lib.h264b_mb_type_decode_dev(self.h, C.byref(j)))
 
     def stream_submit(self, stream, ops, n_ops, qp, idc, n_ctx, slice_data_offset=0, flags=0, param_sets=None,
                       max_slices=None, max_sps=0, max_pps=0, initial_sps=None, initial_pps=None):

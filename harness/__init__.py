@@ -49,6 +49,9 @@ def lib():
                                           C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                           C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
         L.hz_gen_cabac_slices.restype = C.c_int
+        L.hz_encode_explicit.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                         C.c_int64]
+        L.hz_encode_explicit.restype = C.c_int64
         L.hz_random_payload.argtypes = [C.c_uint32, C.c_uint64, C.c_int64, C.c_void_p]
         L.hz_random_payload.restype = None
         L.hz_escape.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
@@ -104,6 +107,20 @@ def gen_cabac_slices(config, ops, n_ops, n_active, n_ctx, qp, idc, flags=0, id_b
     if ov:
         raise RuntimeError("slice did not fit its stride")
     return dict(data=data, lens=lens, bins=bins, final_states=fst, stride=stride)
+
+
+def encode_explicit(ops, bins, states, flags=0):
+    """Encode an explicit list of (op word, bin) pairs -- data-dependent op sequences such as syntax elements -- plus the
+    final terminate(1).  states: initial context states (uint8[n_ctx]).  -> (data uint8[], final states uint8[n_ctx])"""
+    ops = np.ascontiguousarray(ops, dtype=np.uint16)
+    bins = np.ascontiguousarray(bins, dtype=np.uint8)
+    st = np.ascontiguousarray(states, dtype=np.uint8).copy()
+    out = np.zeros(len(ops) * 2 + 64, dtype=np.uint8)
+    n = lib().hz_encode_explicit(flags, ops.ctypes.data, bins.ctypes.data, len(ops), st.ctypes.data, len(st), out.ctypes.data,
+                                 len(out))
+    if n <= 0:
+        raise RuntimeError("hz_encode_explicit: output too small")
+    return out[:n].copy(), st
 
 
 def random_payload(config, ident, n):

@@ -156,3 +156,33 @@ int64_t hz_escape(const uint8_t *in, int64_t n, uint8_t *out) {
     hz_sink_finish(&s);
     return s.n;
 }
+
+/* Encode an explicit list of (op, bin) pairs -- decision bins on the ctxIdx of the op word, bypass bins, terminate bins --
+ * then the final terminate(1).  For data-dependent op sequences (syntax elements), where the schedule is the caller's.
+ * states[n_ctx]: initial context states, updated in place.  Returns the bytes written (0: out too small). */
+int64_t hz_encode_explicit(uint32_t flags, const uint16_t *ops, const uint8_t *bins, int64_t n, uint8_t *states, int64_t n_ctx,
+                           uint8_t *out, int64_t cap) {
+    const hz_tables t = tables_for(flags);
+    hz_sink sink;
+    hz_sink_init(&sink, out, cap, (flags & HZ_ESCAPE) ? 1 : 0);
+    hz_enc e;
+    hz_enc_init(&e, &sink);
+    for (int64_t i = 0; i < n; i++) {
+        uint32_t kind = ops[i] >> 14, ctx = ops[i] & 0x3FFu;
+        if (kind == HZ_OP_DECISION) {
+            if ((int64_t)ctx >= n_ctx) ctx = 0;
+            hz_enc_decision(&e, &t, &states[ctx], bins[i] & 1u);
+        } else if (kind == HZ_OP_BYPASS) {
+            hz_enc_bypass(&e, bins[i] & 1u);
+        } else {
+            hz_enc_terminate(&e, bins[i] & 1u);
+            if (bins[i] & 1u) { /* the slice's data ends here (I_PCM / end of slice): nothing may follow */
+                hz_sink_finish(&sink);
+                return sink.overflow ? 0 : sink.n;
+            }
+        }
+    }
+    hz_enc_terminate(&e, 1);
+    hz_sink_finish(&sink);
+    return sink.overflow ? 0 : sink.n;
+}

@@ -466,6 +466,53 @@ int32_t h264b_slice_select_dev(h264b_ctx *ctx, const h264b_nal *d_nals, const h2
                                uint32_t nal_cap, uint32_t slice_data_offset, uint32_t max_slices, uint64_t *d_off,
                                uint32_t *d_len, uint32_t *d_slice_nal, uint32_t *d_n_slices);
 
+/* ------------------------------------------------------------------ mb_type as a syntax element (row f3)
+ * The walk the reference sketches at h264/slice.go:639-672: NewBinarization("MbType") (h264/cabac.go:340-427), then bin
+ * after bin  CtxIdx(binIdx, MaxBinIdxCtx.Prefix, CtxIdxOffset.Prefix) (:557-758) -> decode -> IsBinStringMatch against
+ * binIdxMbMap[sliceTypeName] (:180-303, :429-436), composed with the engine (the reference reads raw bits there and
+ * never decodes).  Unlike h264b_cabac_decode, where every slice follows one shared op schedule, each lane's sequence of
+ * (context, decision | terminate) ops depends on the bins it has decoded: the binarisation is a trie in shared memory
+ * (built once per context from the reference's tables), a lane's position in it names the next context.
+ * Where CtxIdx leaves a binIdx to a "9.3.3.1.x" comment and answers NaCtxId the rule of that clause is used:
+ *   I slices (ctxIdxOffset 3): binIdx 0 -> ctxIdxInc = 1 if a macroblock was decoded before this one in the slice and it
+ *   was not I_NxN, else 0 (neighbour A = the previous macroblock, B not available); binIdx 1 -> 276 = DecodeTerminate;
+ *   binIdx 4 -> b3 != 0 ? 5 : 6; binIdx 5 -> b3 != 0 ? 6 : 7.   P / SP slices (prefix offset 14): binIdx 2 -> b1 != 1 ?
+ *   2 : 3; the prefix bin 1 is followed by the I-slice bin string on the suffix offset 17 (binIdx 4 -> b3 != 0 ? 2 : 3)
+ *   and mb_type = 5 + that value.
+ * I_PCM (the terminate bin of 1) ends a slice's walk after that element (pcm samples follow, not CABAC data). */
+typedef struct {
+    int64_t cod_i_range;
+    int64_t cod_i_offset;
+    uint64_t bits_read;
+    uint32_t flags;     /* H264B_F_OVERRUN */
+    uint32_t n_bins;    /* bins decoded */
+    uint32_t n_mb;      /* mb_type elements decoded */
+    uint32_t reserved;
+} h264b_mb_final;       /* 40 bytes */
+
+typedef struct {
+    const uint8_t *bytes;          /* slice data; slice s = bytes[off[s] .. off[s]+len[s]), 4-byte aligned base */
+    uint64_t total_bytes;
+    const uint64_t *off;           /* [n_slices] */
+    const uint32_t *len;           /* [n_slices] */
+    uint32_t n_slices;
+    uint32_t n_ctx;                /* context variables per slice, 21..1024 (mb_type uses ctxIdx 3..10 and 14..20) */
+    const uint8_t *slice_kind;     /* [n_slices] 0: I slice (Table 9-36), 1: P / SP slice (Table 9-37 + the I suffix) */
+    const uint32_t *n_mb;          /* [n_slices] mb_type elements to decode, each <= n_mb_max */
+    uint32_t n_mb_max;
+    uint32_t flags;                /* H264B_TABLES_SPEC */
+    const h264b_slice_qp *qp;      /* [n_slices]: initial states by the K4 rule; used when init_states == NULL */
+    const uint8_t *init_states;    /* [n_slices][n_ctx] or NULL */
+    uint8_t *mb_type;              /* [n_slices][n_mb_max] */
+    h264b_mb_final *final;         /* [n_slices] */
+    uint8_t *final_states;         /* [n_slices][n_ctx] or NULL */
+} h264b_mb_type_job;
+
+/* all pointers in job are DEVICE pointers; asynchronous */
+int32_t h264b_mb_type_decode_dev(h264b_ctx *ctx, const h264b_mb_type_job *job);
+/* all pointers in job are HOST pointers; synchronous */
+int32_t h264b_mb_type_decode(h264b_ctx *ctx, const h264b_mb_type_job *job);
+
 /* ------------------------------------------------------------------ many streams over the GPUs of one box
  * The reference's unit of concurrency is a connection: main.go:16-21 starts one goroutine per accepted connection,
  * each running ByteStreamReader -> handleConnection (h264/server.go:113-166) on its own stream.  Here a scheduler owns

@@ -1312,3 +1312,116 @@ int32_t orc_bin_string_match(const int32_t *binString, int32_t len, const int32_
     }
     return len == n;
 }
+
+/* ======================================================================= mb_type as a syntax element (row f3)
+ * The walk the reference sketches at h264/slice.go:639-672 -- NewBinarization("MbType") (cabac.go:340-427), then bin
+ * after bin: CtxIdx(binIdx, MaxBinIdxCtx.Prefix, CtxIdxOffset.Prefix) (cabac.go:557-758), decode, IsBinStringMatch
+ * against binIdxMbMap[sliceTypeName] (cabac.go:180-303, :429-436) -- composed with the engine the way the reference's
+ * section comments point to (the reference itself reads raw bits there and never decodes: A6, A16).  Where CtxIdx
+ * leaves a binIdx to a "9.3.3.1.x" comment and answers NaCtxId, the rule of that clause is used:
+ *   I slices, ctxIdxOffset 3:  binIdx 0 -> ctxIdxInc = condTermFlagA + condTermFlagB (9.3.3.1.1.3) with A the macroblock
+ *     decoded before this one in the slice (1 unless there is none or it was I_NxN) and B not available;
+ *     binIdx 1 -> 276: DecodeTerminate; binIdx 4 -> b3 != 0 ? 5 : 6; binIdx 5 -> b3 != 0 ? 6 : 7 (9.3.3.1.2); the other
+ *     increments are the values CtxIdx returns (Table 9-39 as the reference has it);
+ *   P / SP slices, prefix ctxIdxOffset 14: binIdx 2 -> b1 != 1 ? 2 : 3; the prefix bin 1 (binIdxMbMap gives {1} for every
+ *     mb_type 5..30) is followed by the I-slice bin string decoded with the suffix offset 17 (binIdx 4 -> b3 != 0 ? 2 : 3)
+ *     and mb_type = 5 + that I-slice value (Table 9-37 of the standard).
+ * A bin string no mb_type matches ends the walk (the reference's loop would spin): ORC_PANIC.  I_PCM (the terminate
+ * bin of 1) ends the slice's walk after that element: pcm samples follow, not CABAC data. */
+static int64_t mbt_ctx_inc(int64_t offset, int64_t binIdx, const int32_t *bits, int64_t prev_not_nxn) {
+    int64_t v = orc_ctx_idx(binIdx, 0, offset);
+    if (v != NA_CTX_ID) return v;
+    if (offset == 3) {
+        if (binIdx == 0) return prev_not_nxn;
+        if (binIdx == 4) return bits[3] != 0 ? 5 : 6;
+        if (binIdx == 5) return bits[3] != 0 ? 6 : 7;
+    } else if (offset == 14) {
+        if (binIdx == 2) return bits[1] != 1 ? 2 : 3;
+    } else if (offset == 17) {
+        if (binIdx == 4) return bits[3] != 0 ? 2 : 3;
+    }
+    return NA_CTX_ID;
+}
+
+/* one bin string against binIdxMbMap[st]: the mb_type whose string it is, -1: a proper prefix of some string,
+ * -2: of none */
+static int64_t mbt_match(int32_t st, const int32_t *bits, int32_t n, int64_t n_types) {
+    int64_t prefix_of_some = 0;
+    for (int64_t t = 0; t < n_types; t++) {
+        int32_t bs[8];
+        int32_t len = orc_mb_bin_string(st, t, 0, bs);
+        if (len == 0) continue; /* nil / empty string: never matches a decoded bin */
+        if (len == n && orc_bin_string_match(bs, len, bits, n) == 1) return t;
+        if (len > n) {
+            int same = 1;
+            for (int32_t k = 0; k < n; k++) same = same && bs[k] == bits[k];
+            prefix_of_some |= same;
+        }
+    }
+    return prefix_of_some ? -1 : -2;
+}
+
+/* kind 0: I slice, 1: P / SP slice.  Decodes up to n_mb mb_type elements; out_types[k] receives element k.
+ * fin->n_bins = bins decoded, *n_done = elements decoded.  Status as orc_cabac_decode_slice (a bin that runs off the
+ * data leaves everything as it was before that bin). */
+int orc_decode_mb_types(uint32_t flags, int32_t kind, const uint8_t *bytes, int64_t len, int64_t n_mb, uint8_t *ctx_state,
+                        int64_t n_ctx, uint8_t *out_types, int64_t *n_done, orc_cabac_final *fin) {
+    orc_bit_reader br;
+    orc_br_init(&br, bytes, len);
+    int64_t R, O, done = 0, bins = 0;
+    int status = ORC_OK;
+    orc_init_decoding_engine(&br, &R, &O);
+    int64_t prev_not_nxn = 0;
+    while (!br.panicked && done < n_mb) {
+        int32_t bits[16];
+        int32_t n = 0;
+        int64_t offset = kind == 0 ? 3 : 14;
+        int32_t st = kind == 0 ? 2 : 0; /* sliceTypeName I / P */
+        int64_t base_type = 0, found = -1;
+        int stop = 0;
+        for (;;) {
+            int64_t inc = mbt_ctx_inc(offset, n, bits, prev_not_nxn);
+            int64_t bin = 0, R0 = R, O0 = O, bits0 = br.bitsRead;
+            if (inc == 276) {
+                orc_decode_terminate(&br, &R, &O, &bin);
+            } else {
+                int64_t ctx = offset + inc;
+                if (inc == NA_CTX_ID || ctx >= n_ctx) ctx = 0;
+                uint8_t s0 = ctx_state[ctx];
+                orc_decode_decision(flags, &br, &ctx_state[ctx], &R, &O, &bin);
+                if (br.panicked) ctx_state[ctx] = s0;
+            }
+            if (br.panicked) {
+                R = R0, O = O0, br.bitsRead = bits0;
+                break;
+            }
+            bins++;
+            bits[n++] = (int32_t)bin;
+            if (kind == 1 && offset == 14 && n == 1 && bin == 1) { /* the prefix {1}: an intra macroblock in a P slice */
+                offset = 17, st = 2, base_type = 5, n = 0;
+                continue;
+            }
+            int64_t t = mbt_match(st, bits, n, st == 2 ? 26 : 5);
+            if (t >= 0) {
+                found = base_type + t;
+                break;
+            }
+            if (t == -2 || n >= 15) {
+                status = ORC_PANIC;
+                stop = 1;
+                break;
+            }
+        }
+        if (br.panicked || stop) break;
+        out_types[done++] = (uint8_t)found;
+        if (kind == 0) prev_not_nxn = found != 0;
+        if (found == 25 + base_type && st == 2) break; /* I_PCM */
+    }
+    fin->codIRange = R;
+    fin->codIOffset = O;
+    fin->bitsRead = br.bitsRead;
+    fin->flags = br.panicked ? 1u : 0u;
+    fin->n_bins = (uint32_t)bins;
+    *n_done = done;
+    return br.panicked ? ORC_PANIC : status;
+}

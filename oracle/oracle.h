@@ -194,6 +194,9 @@ void orc_init_cabac(uint32_t flags, int64_t binIdx, int64_t maxPrefix, int64_t o
                     int64_t sliceQpDelta, int64_t *pStateIdx, int64_t *valMPS, int64_t *ctxIdxOut);
 int32_t orc_mb_bin_string(int32_t st, int64_t mbType, int32_t sub, int32_t *bits /* [8] */);
 int32_t orc_bin_string_match(const int32_t *binString, int32_t len, const int32_t *bits, int32_t n);
+/* mb_type as a syntax element: h264/slice.go:639-672, h264/cabac.go:180-303, :340-436, :557-758 */
+int orc_decode_mb_types(uint32_t flags, int32_t kind, const uint8_t *bytes, int64_t len, int64_t n_mb, uint8_t *ctx_state,
+                        int64_t n_ctx, uint8_t *out_types, int64_t *n_done, orc_cabac_final *fin);
 
 #ifdef __cplusplus
 }

@@ -157,6 +157,9 @@ def lib():
     L.orc_cabac_decode_slice.argtypes = [C.c_uint32, u8p, i64, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p,
                                          C.POINTER(CabacFinal)]
     L.orc_cabac_decode_slice.restype = C.c_int
+    L.orc_decode_mb_types.argtypes = [C.c_uint32, C.c_int32, u8p, i64, i64, C.c_void_p, i64, C.c_void_p, i64p,
+                                      C.POINTER(CabacFinal)]
+    L.orc_decode_mb_types.restype = C.c_int
     L.orc_clip3.argtypes = [i64, i64, i64]
     L.orc_clip3.restype = i64
     L.orc_pre_ctx_state.argtypes = [i64, i64, i64]
@@ -317,6 +320,19 @@ def cabac_decode_slice(data, ops, ctx_state, flags=0):
                                       bins.ctypes.data, C.byref(fin))
     return rc, bins[:(len(ops) + 31) // 32], dict(codIRange=fin.codIRange, codIOffset=fin.codIOffset,
                                                   bitsRead=fin.bitsRead, flags=fin.flags, n_bins=fin.n_bins), st
+
+
+def decode_mb_types(data, kind, n_mb, ctx_state, flags=0):
+    """The mb_type walk (kind 0: I slice, 1: P / SP slice) -> (status, mb_types uint8[n_done], final dict, ctx_state after)"""
+    d = _u8(data)
+    st = np.ascontiguousarray(ctx_state, dtype=np.uint8).copy()
+    out = np.zeros(max(n_mb, 1), dtype=np.uint8)
+    fin = CabacFinal()
+    nd = C.c_int64(0)
+    rc = lib().orc_decode_mb_types(flags, kind, d.ctypes.data, len(d), n_mb, st.ctypes.data, len(st), out.ctypes.data,
+                                   C.byref(nd), C.byref(fin))
+    return rc, out[:nd.value], dict(codIRange=fin.codIRange, codIOffset=fin.codIOffset, bitsRead=fin.bitsRead,
+                                    flags=fin.flags, n_bins=fin.n_bins), st
 
 
 # ------------------------------------------------------------------ context init
