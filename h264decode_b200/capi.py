@@ -64,7 +64,7 @@ class CabacJob(C.Structure):
                 ("n_slices", C.c_uint32), ("n_ctx", C.c_uint32), ("ops", C.c_void_p), ("n_ops_max", C.c_uint32),
                 ("n_ops", C.c_void_p), ("qp", C.c_void_p), ("init_states", C.c_void_p), ("bins", C.c_void_p),
                 ("bins_off", C.c_void_p), ("bins_stride_words", C.c_uint32), ("final", C.c_void_p), ("final_states", C.c_void_p),
-                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("flags", C.c_uint32), ("n_ctx_used", C.c_uint32)]
 
 
 class StreamJob(C.Structure):

@@ -669,6 +669,11 @@ static int32_t stream_submit_on_slot(h264b_ctx *ctx, const h264b_stream_job *job
         cj.bins_off = (const uint64_t *)d_boff;
         cj.final = (h264b_cabac_final *)d_fin;
         cj.flags = j.flags;
+        // the schedule's context working set: only those rows have to live in shared memory
+        uint32_t top = 0;
+        for (uint32_t k = 0; k < j.n_ops_max; k++)
+            if ((j.ops[k] >> 14) == H264B_OP_DECISION && (j.ops[k] & 0x3FFu) > top) top = j.ops[k] & 0x3FFu;
+        cj.n_ctx_used = top + 1 < j.n_ctx ? top + 1 : 0;
         RC(launch_cabac(ctx, &cj, d_ns));
     }
     H264B_CUDA(ctx, cudaEventRecord(sl->e_compute, cs));

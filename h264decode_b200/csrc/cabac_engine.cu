@@ -68,6 +68,7 @@ struct CabacArgs {
                            // 3: slot_bundle[CTA x warps + warp] (bundle_assign_kernel), -1: none
     const int32_t *slot_bundle;
     uint32_t rounds;       // map_mode 3: bundles per slot (else 1)
+    uint32_t n_rows;       // context rows per slice in shared memory
 };
 
 // ---------------------------------------------------------------------------------------------- length bundles
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(256) sort_scatter_kernel(const uint32_t *n_ops
 // model next to the measurements: 80 ms -> 62 ms for BASELINE configs[3]).  One warp, ~0.2 ms for 2 500 bundles.
 constexpr int kSlotsMax = 5;  // warps per scheduler = kMaxWarpsPerCta / 4
 
-__global__ void __launch_bounds__(1024) bundle_assign_kernel(const uint32_t *n_ops, const uint32_t *order, uint32_t n_bound,
+__global__ void __launch_bounds__(256) bundle_assign_kernel(const uint32_t *n_ops, const uint32_t *order, uint32_t n_bound,
                                                              const uint32_t *d_n, uint32_t cap_ops, uint32_t lpw,
                                                              uint32_t n_sched, uint32_t slots, uint32_t rounds, uint32_t W,
                                                              int32_t *slot_bundle) {
@@ -180,24 +181,38 @@ __global__ void __launch_bounds__(1024) bundle_assign_kernel(const uint32_t *n_o
     if (tid >= 32) return;
     // a bundle whose own chain (x 2.2) comes near the balanced load of a scheduler counts 1.5 times
     const unsigned long long critical = total_s * 4 / (5ull * n_sched);  // 0.8 x total / schedulers
-    // key of a scheduler: weighted ops / 8 (22 bits: 2^25 ops; more saturate) << 10 | its index; the
-    // least loaded one (ties: the lowest index) is the minimum key -- one warp reduction per bundle
-    const auto key_of = [&](uint32_t k) { return sum[k] >= 0xFFFFFFF0u ? 0xFFFFFFFFu : sum[k] >= (1u << 25) ? (0x3FFFFEu << 10) | k : ((sum[k] >> 3) << 10) | k; };
-    uint32_t my_key = 0xFFFFFFFFu;  // least loaded scheduler among this lane's (lane, lane + 32, ...)
-    for (uint32_t k = lane; k < n_sched; k += 32) my_key = min(my_key, key_of(k));
+    // key of a scheduler: weighted ops / 8 (22 bits: 2^25 ops; more saturate) << 10 | its index; the least loaded one
+    // (ties: the lowest index) is the minimum key -- one warp reduction per bundle.  Lane l keeps the keys of schedulers
+    // l, l + 32, ... in registers (kKeys of them: 640 schedulers = 160 SMs).
+    constexpr int kKeys = 20;
+    uint32_t key[kKeys], load[kKeys], filled[kKeys];
+#pragma unroll
+    for (int q = 0; q < kKeys; q++) {
+        const uint32_t k = (uint32_t)lane + 32u * q;
+        load[q] = 0, filled[q] = 0;
+        key[q] = k < n_sched ? k : 0xFFFFFFFFu;
+    }
     for (uint32_t g = 0; g < n_bundles; g++) {  // bundles come longest first
+        uint32_t my_key = key[0];
+#pragma unroll
+        for (int q = 1; q < kKeys; q++) my_key = min(my_key, key[q]);
         const uint32_t sidx = __reduce_min_sync(0xFFFFFFFFu, my_key) & 1023u;
-        if ((sidx & 31u) == (uint32_t)lane) {  // its owner places the bundle and looks for its new minimum
+        if ((sidx & 31u) == (uint32_t)lane) {  // its owner places the bundle
             const uint32_t L = len[g];
-            const uint32_t kpos = cnt[sidx];
-            // the scheduler's bundles fill its warps round by round: the longest ones run side by side first
-            const uint32_t round = kpos / slots, slot = kpos % slots;
-            slot_bundle[(round * (n_sched >> 2) + (sidx >> 2)) * W + slot * 4 + (sidx & 3u)] = (int32_t)g;
-            cnt[sidx] = kpos + 1;
             const uint32_t wgt = ((unsigned long long)L * 11 / 5 > critical) ? L + L / 2 : L;
-            sum[sidx] = kpos + 1 >= slots * rounds ? 0xFFFFFFF0u : sum[sidx] + wgt;
-            my_key = 0xFFFFFFFFu;
-            for (uint32_t k = lane; k < n_sched; k += 32) my_key = min(my_key, key_of(k));
+            const uint32_t mine = sidx >> 5;
+#pragma unroll
+            for (int q = 0; q < kKeys; q++) {
+                if ((uint32_t)q == mine) {
+                    // the scheduler's bundles fill its warps round by round: the longest ones run side by side first
+                    const uint32_t kpos = filled[q], round = kpos / slots, slot = kpos % slots;
+                    slot_bundle[(round * (n_sched >> 2) + (sidx >> 2)) * W + slot * 4 + (sidx & 3u)] = (int32_t)g;
+                    filled[q] = kpos + 1;
+                    load[q] += wgt;
+                    key[q] = kpos + 1 >= slots * rounds ? 0xFFFFFFFFu
+                                                        : ((load[q] >= (1u << 25) ? 0x3FFFFEu : load[q] >> 3) << 10) | sidx;
+                }
+            }
         }
     }
 }
@@ -251,7 +266,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(C
     }
     __syncthreads();
     const h264b_cabac_job &j = a.j;
-    const uint32_t n_ctx = j.n_ctx;
+    const uint32_t n_ctx = a.n_rows;  // context rows kept in shared memory (j.n_ctx, or the caller's n_ctx_used)
     uint8_t *s_state = s_state_all + (size_t)warp * (n_ctx + 2) * 32;  // (+ 2: kLoop 2's bypass pseudo contexts)
     const uint32_t n_slices = a.d_n && *a.d_n < j.n_slices ? *a.d_n : j.n_slices;
     const uint32_t n_bundles = (n_slices + a.lanes_per_warp - 1) / a.lanes_per_warp;
@@ -289,7 +304,7 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(C
     {
         const uint8_t *src;
         if (j.init_states) {
-            src = j.init_states + (size_t)slice * n_ctx;
+            src = j.init_states + (size_t)slice * j.n_ctx;
         } else {
             const h264b_slice_qp p = j.qp[slice];
             src = a.lut + ((size_t)idc_class_dev(p.cabac_init_idc) * 52 + clip3_dev(0, 51, p.slice_qp_y)) * 1024;
@@ -365,8 +380,18 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(C
         f.n_bins = n_bins;
         j.final[slice] = f;
         if (j.final_states) {
-            uint8_t *dst = j.final_states + (size_t)slice * n_ctx;
+            uint8_t *dst = j.final_states + (size_t)slice * j.n_ctx;
             for (uint32_t c = 0; c < n_ctx; c++) dst[c] = s_state[c * 32 + lane];
+            if (n_ctx < j.n_ctx) {  // contexts the schedule never touches: as they were initialised
+                const uint8_t *src;
+                if (j.init_states) {
+                    src = j.init_states + (size_t)slice * j.n_ctx;
+                } else {
+                    const h264b_slice_qp p = j.qp[slice];
+                    src = a.lut + ((size_t)idc_class_dev(p.cabac_init_idc) * 52 + clip3_dev(0, 51, p.slice_qp_y)) * 1024;
+                }
+                for (uint32_t c = n_ctx; c < j.n_ctx; c++) dst[c] = src[c];
+            }
         }
     };
     // ---- fast loop: blocks of 32 ops (one word of bins) while every lane of the warp is active and on the window
@@ -1052,7 +1077,10 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
     // One wave of one CTA per SM with W warps, each warp with its own n_ctx x 32 bytes of context rows; what does not fit
     // one wave runs as small CTAs in launch order (the hardware hands them out as earlier ones finish).
     const size_t tab_bytes = 1024 + (k_loop ? kTab16Bytes : 2048);
-    uint32_t w_fit = (uint32_t)((kMaxSmemPerCta - tab_bytes) / ((size_t)(j.n_ctx + 2) * 32));
+    // the schedule's context working set, when the caller names it: only those rows live in shared memory
+    const uint32_t n_rows = j.n_ctx_used && j.n_ctx_used < j.n_ctx ? j.n_ctx_used : j.n_ctx;
+    a.n_rows = n_rows;
+    uint32_t w_fit = (uint32_t)((kMaxSmemPerCta - tab_bytes) / ((size_t)(n_rows + 2) * 32));
     if (w_fit > (uint32_t)kMaxWarpsPerCta) w_fit = kMaxWarpsPerCta;
     if (ctx->cabac_max_warps > 0 && w_fit > (uint32_t)ctx->cabac_max_warps) w_fit = (uint32_t)ctx->cabac_max_warps;
     // bundles -> schedulers by bundle_assign_kernel: one wave of full CTAs with a slot to spare on every scheduler; when
@@ -1062,7 +1090,7 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
     if (slots * 4 > w_fit) slots = w_fit / 4;
     uint32_t rounds = slots ? (uint32_t)((a.n_warps + (uint64_t)sms * 4 * slots - 1) / ((uint64_t)sms * 4 * slots)) : 0;
     const bool assign = a.map_mode == 3 && k_w <= 0 && lpw > 1 && j.n_ops && slots >= 1 && rounds >= 1 && rounds <= 64 &&
-                        a.n_warps > sms * 4 && ((uint64_t)sms * 4 * slots * rounds + 2ull * sms * 4) * 4 <= 200 * 1024;
+                        a.n_warps > sms * 4 && sms * 4 <= 640 && ((uint64_t)sms * 4 * slots * rounds + 2ull * sms * 4) * 4 <= 200 * 1024;
     if (a.map_mode == 3 && !assign) a.map_mode = 1;
     uint32_t W, grid;
     if (assign) {
@@ -1105,14 +1133,14 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
             const size_t sm_assign = ((size_t)sms * 4 * slots * rounds + 2 * (size_t)sms * 4) * 4;
             if (sm_assign > 48 * 1024)
                 H264B_CUDA(ctx, cudaFuncSetAttribute(bundle_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_assign));
-            bundle_assign_kernel<<<1, 1024, sm_assign, ctx->stream>>>(j.n_ops, order, j.n_slices, d_n_slices, j.n_ops_max, lpw,
+            bundle_assign_kernel<<<1, 256, sm_assign, ctx->stream>>>(j.n_ops, order, j.n_slices, d_n_slices, j.n_ops_max, lpw,
                                                                      sms * 4, slots, rounds, W, slot_bundle);
             H264B_LAUNCH_CHECK(ctx, "bundle_assign_kernel");
             a.slot_bundle = slot_bundle;
             a.rounds = rounds;
         }
     }
-    const size_t smem = tab_bytes + (size_t)W * (j.n_ctx + 2) * 32;
+    const size_t smem = tab_bytes + (size_t)W * (n_rows + 2) * 32;
     if (k_loop == 2) {
         // (one carveout for every launch of this kernel: launches that differ in their shared-memory split cannot share an SM,
         //  and h264b_scheduler runs several side by side)

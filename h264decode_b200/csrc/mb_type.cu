@@ -19,7 +19,7 @@
 
 namespace h264b {
 
-// node: leaf  = 0x80000000 | mb_type
+// node: leaf  = 0x80000000 | I_PCM << 8 | mb_type   (I_PCM: the walk of the slice ends with this element)
 //       inner = terminate << 30 | add_prev << 29 | ctxIdx << 16 | child(bin 1) << 8 | child(bin 0); child 0xFF: no mb_type
 //       has this bin string (the reference's loop would never end)
 constexpr uint32_t kLeaf = 0x80000000u, kNoChild = 0xFFu;
@@ -75,7 +75,7 @@ struct TrieBuilder {
             const int st = classify(n + 1, nb, &type);
             if (st == 2) {
                 child[b] = (uint32_t)nodes.size();
-                nodes.push_back(kLeaf | (uint32_t)(base + type));
+                nodes.push_back(kLeaf | (type == 25 ? 0x100u : 0u) | (uint32_t)(base + type));  // (I table only: 25 = I_PCM)
             } else if (st == 1) {
                 child[b] = (uint32_t)node(offset, base, root_adds_prev, n + 1, nb, classify);
             } else {
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kMbWarps * 32) mb_type_kernel(MbArgs a) {
                         done++;
                         prev = t != 0u ? 1u : 0u;
                         idx = 0;
-                        if (done >= want || t == 25u || t == 30u) active = false;  // (25 / 30: I_PCM)
+                        if (done >= want || (nn & 0x100u)) active = false;  // (I_PCM)
                     } else {
                         idx = child;
                     }

@@ -216,7 +216,10 @@ typedef struct {
     h264b_cabac_final *final;      /* [n_slices] */
     uint8_t *final_states;         /* [n_slices][n_ctx] or NULL */
     uint32_t flags;
-    uint32_t reserved;
+    uint32_t n_ctx_used;           /* 0, or a promise: the schedule's decisions only use ctxIdx < n_ctx_used (<= n_ctx).  Only
+                                      those context rows are then kept in shared memory (32 bytes per context and warp: what
+                                      decides how many slices an SM decodes at once); the others pass from init to final
+                                      untouched.  A ctxIdx >= n_ctx_used in the schedule is treated like one >= n_ctx: as 0. */
 } h264b_cabac_job;
 
 /* all pointers in job are DEVICE pointers; asynchronous */

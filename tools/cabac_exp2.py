@@ -9,7 +9,9 @@ from h264decode_b200 import capi
 dev = "cuda:0"
 N = int(os.environ.get("EXP_SLICES", "80000"))
 MEAN = int(os.environ.get("EXP_MEAN_BINS", "455000"))
-g = hz.gpu_build_stream_cabac(torch, dev, N, MEAN, config=4, n_active=64, n_ctx=64, slices_per_frame=8,
+N_ACTIVE = int(os.environ.get("EXP_ACTIVE", "64"))      # active contexts of the schedule (64, repeat with 460)
+N_CTX = int(os.environ.get("EXP_NCTX", str(N_ACTIVE)))   # context rows per slice
+g = hz.gpu_build_stream_cabac(torch, dev, N, MEAN, config=4, n_active=N_ACTIVE, n_ctx=N_CTX, slices_per_frame=8,
                               frames_per_params=250, id_base=0, want_bins=False)
 torch.cuda.synchronize()
 n, d_stream, n_nals = g["n"], g["stream"], g["n_nals"]
@@ -41,7 +43,7 @@ def run(ns, nops_arr, label, reps=3, check_key=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         ctx.cabac_decode_dev(bytes=d_rbsp.data_ptr(), total_bytes=n + 16, off=d_off.data_ptr(), len=d_len.data_ptr(),
-                             n_slices=ns, n_ctx=64, ops=d_ops.data_ptr(), n_ops_max=len(ops), n_ops=d_nops.data_ptr(),
+                             n_slices=ns, n_ctx=N_CTX, ops=d_ops.data_ptr(), n_ops_max=len(ops), n_ops=d_nops.data_ptr(),
                              qp=d_qp.data_ptr(), init_states=None, bins=d_bins.data_ptr(), bins_off=d_boff.data_ptr(),
                              bins_stride_words=0, final=d_fin.data_ptr(), final_states=None, flags=flags)
         e1.record(stream); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
@@ -62,7 +64,7 @@ only = os.environ.get("EXP_ONLY")   # "ns": one equal-length configuration only 
 for v in variants:
     loop, w, mp = v.split(":")
     os.environ["H264B_CABAC_LOOP"], os.environ["H264B_CABAC_W"], os.environ["H264B_CABAC_MAP"] = loop, w, mp
-    print("--- loop %s, warps/CTA %s (0 = one wave), map %s" % (loop, w, mp), flush=True)
+    print("--- loop %s, warps/CTA %s (0 = one wave), map %s, %d active contexts, %d context rows" % (loop, w, mp, N_ACTIVE, N_CTX), flush=True)
     if only:
         run(int(only), np.full(int(only), K), "equal length %d ops" % K, reps=1)
         continue
