@@ -431,7 +431,8 @@ def run_gpu(args, rank, world, local_rank):
     for b in bufs:
         del b.bins, b.rbsp
     torch.cuda.empty_cache()
-    e2e_steps = max(IN_FLIGHT, min(args.steps, 12))
+    # (at least 12 steps: with three jobs in flight a shorter run is mostly pipeline fill and drain)
+    e2e_steps = max(12, args.steps)
     e2e_error = None
     t_e2e, e2e_ok, h_stream = 0.0, True, None
     try:

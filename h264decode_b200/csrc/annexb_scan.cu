@@ -28,6 +28,8 @@
 //
 // (Measured alternatives -- 16 KiB CTA tiles with decoupled look-back, warp-private TMA rings with bulk stores,
 // register pipelines over 128 KiB pieces -- are in the git history and profiles/r1_scan_*; DESIGN.md has the numbers.)
+#include <stdlib.h>
+
 #include "annexb_local.cuh"
 #include "common.cuh"
 
@@ -1045,32 +1047,95 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     a.nal_cap = nal_cap;
     a.n_chunks = (uint32_t)n_chunks;
 
-    // header + per-chunk (start codes | EPBs) array: all zero
-    H264B_CUDA(ctx, cudaMemsetAsync(s, 0, so.piece + n_chunks * 4, ctx->stream));
-    if (n_chunks) {
-        annexb_copy_kernel<<<(unsigned)((n_chunks + kWarpsA - 1) / kWarpsA), kWarpsA * 32, 0, ctx->stream>>>(a);
-        H264B_LAUNCH_CHECK(ctx, "annexb_copy_kernel");
-        static int occ_b = 0;  // resident CTAs per SM: the kernel walks the list grid-stride, one wave
-        if (!occ_b) {
-            H264B_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, annexb_dirty_kernel, kWarpsB * 32, 0));
-            if (occ_b < 1) occ_b = 1;
-        }
-        uint64_t grid_b = (n_chunks + kWarpsB - 1) / kWarpsB;  // (the list is at most that long)
-        if (grid_b > (uint64_t)ctx->sm_count * occ_b) grid_b = (uint64_t)ctx->sm_count * occ_b;
-        annexb_dirty_kernel<<<(unsigned)grid_b, kWarpsB * 32, 0, ctx->stream>>>(a);
-        H264B_LAUNCH_CHECK(ctx, "annexb_dirty_kernel");
-        const unsigned tiles = (unsigned)((n_chunks + kOrderTile - 1) / kOrderTile);
-        order_reduce_kernel<<<tiles, 256, 0, ctx->stream>>>(a.piece, a.tile_sum, a.n_chunks);
-        H264B_LAUNCH_CHECK(ctx, "order_reduce_kernel");
-        order_apply_kernel<<<tiles, 256, 0, ctx->stream>>>(a.piece, a.tile_sum, a.piece_ord, a.piece_S, a.n_chunks);
-        H264B_LAUNCH_CHECK(ctx, "order_apply_kernel");
-        nal_permute_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a);
-        H264B_LAUNCH_CHECK(ctx, "nal_permute_kernel");
+    // Small streams are launch bound: the pass is captured once per set of arguments and replayed as one graph launch.
+    static const bool graphs_on = !(getenv("H264B_SCAN_GRAPH") && atoi(getenv("H264B_SCAN_GRAPH")) == 0);
+    static int occ_b = 0;  // resident CTAs per SM of the dirty-chunk kernel: it walks its list grid-stride, one wave
+    if (!occ_b) {
+        H264B_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, annexb_dirty_kernel, kWarpsB * 32, 0));
+        if (occ_b < 1) occ_b = 1;
     }
-    scan_finalize_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a, d_nals, d_ext, d_summary);
-    H264B_LAUNCH_CHECK(ctx, "scan_finalize_kernel");
-    nal_fixup_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(a, d_summary);
-    H264B_LAUNCH_CHECK(ctx, "nal_fixup_kernel");
+    const auto enqueue = [&]() -> int {
+        unsigned launched = 0;
+        // header + per-chunk (start codes | EPBs) array: all zero
+        H264B_CUDA(ctx, cudaMemsetAsync(s, 0, so.piece + n_chunks * 4, ctx->stream));
+        if (n_chunks) {
+            annexb_copy_kernel<<<(unsigned)((n_chunks + kWarpsA - 1) / kWarpsA), kWarpsA * 32, 0, ctx->stream>>>(a);
+            H264B_LAUNCH_CHECK(ctx, "annexb_copy_kernel");
+            uint64_t grid_b = (n_chunks + kWarpsB - 1) / kWarpsB;  // (the list is at most that long)
+            if (grid_b > (uint64_t)ctx->sm_count * occ_b) grid_b = (uint64_t)ctx->sm_count * occ_b;
+            annexb_dirty_kernel<<<(unsigned)grid_b, kWarpsB * 32, 0, ctx->stream>>>(a);
+            H264B_LAUNCH_CHECK(ctx, "annexb_dirty_kernel");
+            const unsigned tiles = (unsigned)((n_chunks + kOrderTile - 1) / kOrderTile);
+            order_reduce_kernel<<<tiles, 256, 0, ctx->stream>>>(a.piece, a.tile_sum, a.n_chunks);
+            H264B_LAUNCH_CHECK(ctx, "order_reduce_kernel");
+            order_apply_kernel<<<tiles, 256, 0, ctx->stream>>>(a.piece, a.tile_sum, a.piece_ord, a.piece_S, a.n_chunks);
+            H264B_LAUNCH_CHECK(ctx, "order_apply_kernel");
+            nal_permute_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a);
+            H264B_LAUNCH_CHECK(ctx, "nal_permute_kernel");
+            launched += 5;
+        }
+        scan_finalize_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a, d_nals, d_ext, d_summary);
+        H264B_LAUNCH_CHECK(ctx, "scan_finalize_kernel");
+        nal_fixup_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(a, d_summary);
+        H264B_LAUNCH_CHECK(ctx, "nal_fixup_kernel");
+        (void)launched;
+        return H264B_OK;
+    };
+    if (!graphs_on || n > (8ull << 20)) return enqueue();
+    ScanGraph key;
+    memset(&key, 0, sizeof(key));
+    {
+        unsigned char *k = key.key;
+        const void *ptrs[6] = {d_stream, d_rbsp, d_nals, d_ext, d_summary, s};
+        memcpy(k, ptrs, sizeof(ptrs));
+        memcpy(k + 48, &n, 8);
+        memcpy(k + 56, &nal_cap, 4);
+        const void *st = (const void *)ctx->stream;
+        memcpy(k + 64, &st, 8);
+    }
+    ScanGraph *hit = nullptr, *victim = nullptr;  // victim: an empty entry, else the least recently used one
+    for (int i = 0; i < kScanGraphs; i++) {
+        ScanGraph &g = ctx->scan_graph[i];
+        if (g.exec && memcmp(g.key, key.key, sizeof(key.key)) == 0) hit = &g;
+        if (!g.exec) {
+            if (!victim || victim->exec) victim = &g;
+        } else if (!victim || (victim->exec && g.used < victim->used)) {
+            victim = &g;
+        }
+    }
+    if (!hit) {
+        const uint64_t launches_before = ctx->launches;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            return enqueue();  // (a stream that cannot be captured: the legacy default stream, or one already capturing)
+        }
+        const int rc = enqueue();
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc != H264B_OK || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            ctx->launches = launches_before;
+            return rc != H264B_OK ? rc : enqueue();
+        }
+        cudaGraphExec_t exec = nullptr;
+        if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+            cudaGraphDestroy(graph);
+            cudaGetLastError();
+            ctx->launches = launches_before;
+            return enqueue();
+        }
+        cudaGraphDestroy(graph);
+        if (victim->exec) cudaGraphExecDestroy(victim->exec);
+        memcpy(victim->key, key.key, sizeof(key.key));
+        victim->exec = exec;
+        victim->nodes = (unsigned)(ctx->launches - launches_before);
+        ctx->launches = launches_before;
+        hit = victim;
+    }
+    hit->used = ++ctx->scan_graph_tick;
+    H264B_CUDA(ctx, cudaGraphLaunch(hit->exec, ctx->stream));
+    ctx->launches += hit->nodes;
     return H264B_OK;
 }
 

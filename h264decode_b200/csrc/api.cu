@@ -143,6 +143,8 @@ void h264b_destroy(h264b_ctx *ctx) {
         for (int i = 0; i < 20; i++) cudaFree(ctx->d_buf[b][i]);
         cudaFree(ctx->scan_scratch[b]);
     }
+    for (int i = 0; i < kScanGraphs; i++)
+        if (ctx->scan_graph[i].exec) cudaGraphExecDestroy(ctx->scan_graph[i].exec);
     for (int i = 0; i < 8; i++)
         if (ctx->h_pin[i]) cudaFreeHost(ctx->h_pin[i]);
     for (int i = 0; i < kStreamSlots; i++) {

@@ -279,9 +279,16 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(C
     uint32_t gw = a.map_mode == 2 ? blockIdx.x * W + (uint32_t)warp : rank * gridDim.x + blockIdx.x;
     // map_mode 3: the warp runs the bundles of its slot one after the other (rounds: as many as the launch needs for all
     // bundles to have a slot: one, unless the context rows leave room for few warps); -1: no bundle
+#ifdef H264B_EXP_NO_ROUNDS
+    {
+    const uint32_t round = 0;
+    if (a.map_mode == 3) gw = (uint32_t)a.slot_bundle[(round * gridDim.x + blockIdx.x) * W + (uint32_t)warp];
+    if (gw >= n_bundles) return;
+#else
     for (uint32_t round = 0; round < a.rounds; round++) {
     if (a.map_mode == 3) gw = (uint32_t)a.slot_bundle[(round * gridDim.x + blockIdx.x) * W + (uint32_t)warp];
     if (__all_sync(0xFFFFFFFFu, gw >= n_bundles)) continue;  // (a vote: gw is the same in every lane)
+#endif
     const uint32_t index = gw * a.lanes_per_warp + lane;
     // Lanes without a slice of their own (a partly filled warp) shadow the warp's first lane: they decode the same
     // slice and store nothing, so the loops below never have to predicate on "is there a slice in this lane".
@@ -1146,8 +1153,10 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
         //  and h264b_scheduler runs several side by side)
         static bool carveout_set[64] = {false};
         if (ctx->device < 64 && !carveout_set[ctx->device]) {
+            // (half of the SM's 228 KB: room for every launch shape at 64 contexts, and an L1 for the op schedule and the
+            //  bitstream words; launches that need more get more)
             H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                 cudaSharedmemCarveoutMaxShared));
+                                                 env_int("H264B_CABAC_CARVEOUT", 50)));
             H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)kMaxSmemPerCta));
             carveout_set[ctx->device] = true;

@@ -10,6 +10,15 @@
 #include "../../include/h264b200.h"
 
 struct StreamSlot;
+// A captured Annex-B pass (annexb_scan.cu): small streams are launch bound (8 stream operations for 1 MB of input), a
+// graph of the same operations replays with one launch.  Keyed by every argument of the pass.
+struct ScanGraph {
+    unsigned char key[96];
+    cudaGraphExec_t exec;
+    uint64_t used;     // tick of the last replay (least recently used goes first)
+    unsigned nodes;    // kernels in the graph (for the launch counter)
+};
+constexpr int kScanGraphs = 8;
 // Jobs in flight per context.  Three: in the steady state one job copies in, one runs its kernels and one copies out, so
 // the slowest of the three stages paces the pipeline (with two, H2D + kernels + D2H of one job span two periods).
 constexpr int kStreamSlots = 3;
@@ -20,6 +29,8 @@ struct h264b_ctx {
     cudaStream_t stream;  // the one "_dev" work goes to (own_stream unless h264b_set_stream was called)
     char err[512];
     uint64_t launches;
+    ScanGraph scan_graph[kScanGraphs];
+    uint64_t scan_graph_tick;
     int cabac_max_warps;  // 0: as many warps per CTA as fit; else a cap (launches that share the GPU: h264b_scheduler)
 
     // grow-only device scratch, in banks: [0] the direct ("_dev" and host-pointer) entry points, [1 + s] stream-job slot

@@ -45,7 +45,8 @@ def run(ns, nops_arr, label, reps=3, check_key=None):
         ctx.cabac_decode_dev(bytes=d_rbsp.data_ptr(), total_bytes=n + 16, off=d_off.data_ptr(), len=d_len.data_ptr(),
                              n_slices=ns, n_ctx=N_CTX, ops=d_ops.data_ptr(), n_ops_max=len(ops), n_ops=d_nops.data_ptr(),
                              qp=d_qp.data_ptr(), init_states=None, bins=d_bins.data_ptr(), bins_off=d_boff.data_ptr(),
-                             bins_stride_words=0, final=d_fin.data_ptr(), final_states=None, flags=flags)
+                             bins_stride_words=0, final=d_fin.data_ptr(), final_states=None, flags=flags,
+                             n_ctx_used=N_ACTIVE if N_ACTIVE < N_CTX else 0)
         e1.record(stream); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     t = float(np.median(ts[1:])); bins = float(nops_arr.astype(np.int64).sum())
     ok = ""
