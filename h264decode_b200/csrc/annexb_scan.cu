@@ -49,10 +49,15 @@ constexpr int kSlotBytes = kHalo + kChunk + kHalo; // 2080
 constexpr int kWarpsA = H264B_SCAN_WARPS;          // chunks per CTA of the copy kernel
 constexpr int kWarpsB = 4;                         // warps per CTA of the dirty-chunk kernel (32 chunk flags each)
 constexpr int kOrderTile = 4096;                   // chunks per CTA of the ordinal scan
+// piece[] word of a chunk
+constexpr uint32_t kPieceEpb = 0x7FFFu;            // bits 14:0   EPBs (<= 683 per chunk)
+constexpr uint32_t kPieceDirty = 0x8000u;          // bit 15      the copy kernel left the chunk to the dirty-chunk kernel
+constexpr uint32_t kPieceNscShift = 16;            // bits 28:16  start codes (<= 512 per chunk)
+constexpr uint32_t kPieceNsc = 0x1FFFu;
+constexpr uint32_t kPieceReady = 0x80000000u;      // bit 31      (dirty chunks) the fields above are final
 
-struct ScanScratchHeader {   // device scratch; zeroed (together with the piece array) before every pass
-    unsigned int n_dirty;          // entries of dirty_list
-    unsigned int n_fix;            // entries of fix_list
+struct ScanScratchHeader {   // device scratch; zeroed (together with the two per-chunk arrays behind it) before every pass
+    unsigned int reserved0[2];
     unsigned long long first_inv;  // max over NAL starts of ~start (0: no start code): first_start = ~first_inv
     unsigned long long total_sc;   // start codes found = slots handed out of the NAL record buffer
     unsigned long long total_kept;
@@ -65,13 +70,15 @@ struct ScanArgs {
     uint64_t n;
     uint8_t *out;
     ScanScratchHeader *hdr;
-    uint32_t *piece;           // per chunk: start codes << 16 | EPBs after its last NAL start (or in the whole chunk
-                               // when it has none); stays 0 for the chunks the copy kernel handled
-    uint32_t *dirty_list;      // chunks left to the dirty-chunk kernel, any order
+    uint32_t *piece;           // per chunk, see kPiece*: start codes << 16 | EPBs after its last NAL start (or in the
+                               // whole chunk when it has none) | flags; stays 0 for a chunk the copy kernel stored
+                               // verbatim and found no start code in
+    uint32_t *piece_carry;     // per dirty chunk: kPieceReady | EPBs removed from the NAL open at the END of the chunk
+                               // since that NAL's start (the look-back's short cut)
     uint32_t *piece_ord;       // per chunk: ordinal of its first start code (exclusive scan of the counts)
-    uint32_t *piece_S;         // per chunk: exclusive scan of the EPB fields (see nal_pieces)
-    uint2 *tile_sum;           // per kOrderTile chunks: (start codes, EPB fields): first phase of those scans
-    uint32_t *fix_list;        // NAL ordinals whose later parts must slide left (written by scan_finalize_kernel)
+    uint32_t *piece_S;         // per chunk: exclusive scan of the EPB fields
+    uint32_t *piece_M;         // per chunk: 1 + the last earlier chunk that holds a start code (0: none)
+    uint4 *tile_sum;           // per kOrderTile chunks: (start codes, EPB fields, last chunk with a start code + 1)
     // One 16-byte record per start code: .x/.y = offset of the byte after it (the next NAL's first byte), .z = that
     // NAL's first 4 bytes, .w = EPBs removed (within the start code's chunk) from the NAL that ENDS at this start code
     // | rank of the start code inside its chunk << 16.
@@ -147,7 +154,7 @@ __global__ void __launch_bounds__(kWarpsA * 32) annexb_copy_kernel(ScanArgs a) {
     const uint64_t pos = (uint64_t)chunk * kChunk;
     // chunks that touch the ends of the stream always take the general path (it blanks the bytes outside)
     if (pos == 0 || pos + kChunk + kHalo > a.n) {
-        if (lane == 0) a.dirty_list[atomicAdd(&a.hdr->n_dirty, 1u)] = chunk;
+        if (lane == 0) a.piece[chunk] = kPieceDirty;
         return;
     }
     const uint8_t *src = a.in + pos + lane * 16;
@@ -174,7 +181,7 @@ __global__ void __launch_bounds__(kWarpsA * 32) annexb_copy_kernel(ScanArgs a) {
 #endif
     }
     if (__any_sync(0xFFFFFFFFu, any_e != 0)) {
-        if (lane == 0) a.dirty_list[atomicAdd(&a.hdr->n_dirty, 1u)] = chunk;
+        if (lane == 0) a.piece[chunk] = kPieceDirty;
         return;
     }
 #ifndef H264B_EXP_NOSTORE
@@ -247,7 +254,7 @@ __device__ __noinline__ void compact_row_in_place(uint8_t *row, const uint8_t *s
 // NAL header can reach (header bytes are dropped bytes: their rows are never "EPB-only")
 __device__ __noinline__ void store_boundary_granule(const ScanArgs &a, const uint8_t *tile_in, uint64_t pos, int gi,
                                                     uint32_t k16, uint32_t ee, uint32_t sc, uint64_t c, uint64_t k,
-                                                    uint32_t rank, bool first_of_chunk) {
+                                                    uint32_t rank, bool first_of_chunk, uint32_t carry_in) {
     const uint64_t gpos = pos + (uint64_t)gi * 16;
     const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
     if (k16 == 0xFFFFu && sc == 0 && ((gpos - c) & 15u) == 0) {  // an ordinary granule of such a row (ee is 0 then)
@@ -257,6 +264,9 @@ __device__ __noinline__ void store_boundary_granule(const ScanArgs &a, const uin
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     store_granule_bytes(a.out, gpos, w, k16, ee, sc, c, [&](int j, uint64_t c_end) {
         const uint64_t st = gpos + (uint64_t)j + 1;  // the new NAL's first byte
+        // the record keeps the count since the start of the chunk for a NAL that was open when the chunk began (the
+        // chunks before it are added from S[] by nal_removed)
+        const uint32_t c_local = (uint32_t)c_end - (first_of_chunk ? carry_in : 0u);
         if (first_of_chunk) {
             atomicMax(&a.hdr->first_inv, ~(unsigned long long)st);
             first_of_chunk = false;
@@ -264,7 +274,7 @@ __device__ __noinline__ void store_boundary_granule(const ScanArgs &a, const uin
         if (k < a.nal_cap) {
             const uint8_t *hb = tile_in + gi * 16 + j + 1;  // its first 4 bytes (0xFF past the end of the stream)
             const uint32_t h = (uint32_t)hb[0] | ((uint32_t)hb[1] << 8) | ((uint32_t)hb[2] << 16) | ((uint32_t)hb[3] << 24);
-            a.rec[k] = make_uint4((uint32_t)st, (uint32_t)(st >> 32), h, (uint32_t)c_end | (rank << 16));
+            a.rec[k] = make_uint4((uint32_t)st, (uint32_t)(st >> 32), h, c_local | (rank << 16));
         }
         k++;
         rank++;
@@ -286,16 +296,59 @@ __device__ __noinline__ void store_row(uint8_t *out, uint64_t o, uint32_t len, c
     store_row_lane(out, o, len, wp, w, lane, prev_tail, next_joins);
 }
 
+// EPBs removed so far from the NAL that is open at the first byte of `chunk`: the chunks before it are walked
+// backwards, 32 at a time, up to the nearest one that holds a NAL start or has published its own carry.  A dirty chunk
+// that has not published its counts yet is waited for; it never waits itself before publishing them, and the warp that
+// owns it is running (chunks are dealt to the warps of one wave in ascending order), so the wait ends.
+__device__ __noinline__ uint32_t lookback_carry(const ScanArgs &a, uint32_t chunk, int lane) {
+    uint32_t carry = 0;
+    const volatile uint32_t *piece = a.piece, *pc = a.piece_carry;
+    for (int64_t base = (int64_t)chunk; base > 0; base -= 32) {
+        const int64_t idx = base - 1 - lane;  // lane 0: the nearest chunk
+        uint32_t w, c, term, pending;
+        for (;;) {
+            if (idx < 0) {  // in front of the stream: nothing is open there
+                w = 0;
+                c = 0;
+                term = 1;
+                pending = 0;
+            } else {
+                w = piece[idx];
+                c = (w & kPieceDirty) ? pc[idx] : 0u;
+                pending = (w & kPieceDirty) && !(w & kPieceReady);
+                term = !pending && ((((w >> kPieceNscShift) & kPieceNsc) != 0) || (c & kPieceReady));
+            }
+            const uint32_t tmask = __ballot_sync(0xFFFFFFFFu, term), pmask = __ballot_sync(0xFFFFFFFFu, pending);
+            const uint32_t need = tmask ? ((tmask & (0u - tmask)) - 1u) : 0xFFFFFFFFu;  // the lanes nearer than the first stop
+            if ((pmask & need) == 0) {
+                uint32_t x = 0;
+                if (tmask) {
+                    const int first = __ffs((int)tmask) - 1;
+                    if (lane < first) x = w & kPieceEpb;
+                    // a chunk with a NAL start: the EPBs after its last start; else its published carry
+                    if (lane == first) x = idx < 0 ? 0u : (((w >> kPieceNscShift) & kPieceNsc) ? (w & kPieceEpb) : (c & kPieceEpb));
+                } else {
+                    x = w & kPieceEpb;
+                }
+                carry += __reduce_add_sync(0xFFFFFFFFu, x);
+                if (tmask) return carry;
+                break;
+            }
+            __nanosleep(40);
+        }
+    }
+    return carry;
+}
+
 struct ChunkResult {
-    uint32_t carry_epb;  // EPBs removed from the open NAL since its start / the start of the piece
-    uint32_t piece_nsc;  // start codes of the piece so far
     uint32_t clean;      // nothing to remove after all and nothing shifted: the caller bulk-stores the chunk
 };
 
 // General path of one chunk (whole warp).  tile_in[i] = s[pos + i] for i in [-16, kChunk + 16), bytes outside the
 // stream read as 0xFF.
 __device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, uint16_t *scbits, uint8_t *buf, uint64_t pos,
-                                                  uint32_t carry_epb, uint32_t piece_nsc, int lane) {
+                                                  uint32_t chunk, int lane) {
+    const uint32_t piece_nsc = 0;
     uint8_t *tile_in = buf + kHalo;
     if (pos == 0 || pos + kChunk + kHalo > a.n) {  // bytes outside the stream read as 0xFF (they match no predicate)
         const uint64_t n16 = (a.n + 15) & ~15ull;
@@ -386,17 +439,21 @@ __device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, uint16_t *s
         incl[r] = x;
         rp[r + 1] = seg_combine(rp[r], __shfl_sync(0xFFFFFFFFu, x, 31));
     }
+    const uint32_t total = rp[kRows];
+    const uint32_t n_sc = (total >> 16) & 0x1FFFu;  // == n_sc_raw
+    // The chunk's own counts are final: publish them, then ask the chunks before this one how far the NAL that is open
+    // at its first byte has shifted (nobody is kept waiting while this warp waits).
+    if (lane == 0)
+        *(volatile uint32_t *)&a.piece[chunk] = kPieceReady | kPieceDirty | (n_sc << kPieceNscShift) | (total & kPieceEpb);
+    const uint32_t carry_epb = lookback_carry(a, chunk, lane);
+    if (lane == 0) *(volatile uint32_t *)&a.piece_carry[chunk] = kPieceReady | seg_apply(total, carry_epb);
     ChunkResult res;
-    res.carry_epb = carry_epb;
-    res.piece_nsc = piece_nsc;
     res.clean = 0;
     if (cls == 0 && carry_epb == 0) {  // false alarm (00 00 xx with xx > 3): a verbatim copy after all
         res.clean = 1;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // (the fills above)
         return res;
     }
-    const uint32_t total = rp[kRows];
-    const uint32_t n_sc = (total >> 16) & 0x1FFFu;  // == n_sc_raw
 
     // ---------------------------------------------------------------- rows with boundaries: bytes + NAL records
     if (n_sc) slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
@@ -410,7 +467,7 @@ __device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, uint16_t *s
         const uint64_t c = seg_apply(pre, carry_epb);
         const uint32_t before = (pre >> 16) & 0x1FFFu;  // start codes of the chunk before this granule
         store_boundary_granule(a, tile_in, pos, gi, ks[r] & 0xFFFFu, ee[r], ks[r] >> 16, c, slot0 + before,
-                               piece_nsc + before, before == 0);
+                               piece_nsc + before, before == 0, carry_epb);
     }
     __syncwarp();
 
@@ -443,15 +500,15 @@ __device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, uint16_t *s
         const bool next_joins = r < kRows - 1 && ((cls >> (2 * r + 2)) & 3u) != 2u;
         store_row(a.out, o, 512u - removed, tile_in + gi * 16, lane, prev_tail, next_joins);
     }
-    res.carry_epb = seg_apply(total, carry_epb);
-    res.piece_nsc = piece_nsc + n_sc;
     // generic-proxy writes to the slot (fills, compaction) are ordered before the TMA writes that will reuse it
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     return res;
 }
 
-// One warp per listed chunk (grid-stride over the list): the TMA stages the chunk (the next one is already on its way
-// while this one is walked), the whole warp walks it.
+// The dirty chunks, in ascending order over the warps of one resident wave: warp g looks at chunks g, g + W, g + 2W, ...
+// (W = warps of the grid; 32 flags per load, one per lane) and walks those the copy kernel flagged.  The TMA stages a
+// chunk while the one before it is walked.  Ascending order is what the look-back of general_chunk relies on: every
+// chunk a warp can wait for belongs to a warp that is running and not behind it.
 __global__ void __launch_bounds__(kWarpsB * 32) annexb_dirty_kernel(ScanArgs a) {
     __shared__ WarpStage stage[kWarpsB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -462,9 +519,8 @@ __global__ void __launch_bounds__(kWarpsB * 32) annexb_dirty_kernel(ScanArgs a) 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    const uint32_t n_dirty = a.hdr->n_dirty;
     const uint64_t n16 = (a.n + 15) & ~15ull;
-    const uint32_t stride = gridDim.x * kWarpsB;
+    const uint64_t W = (uint64_t)gridDim.x * kWarpsB, g = (uint64_t)blockIdx.x * kWarpsB + (uint64_t)warp;
     auto stage_chunk = [&](uint32_t chunk, int b) {  // lane 0: TMA bulk load of the chunk and its halos, clipped to the stream
         const uint64_t pos = (uint64_t)chunk * kChunk;
         const uint64_t lo = pos ? pos - kHalo : 0;
@@ -478,29 +534,42 @@ __global__ void __launch_bounds__(kWarpsB * 32) annexb_dirty_kernel(ScanArgs a) 
             "l"(a.in + lo), "r"(bytes), "r"(bar)
             : "memory");
     };
-    uint32_t i = blockIdx.x * kWarpsB + (uint32_t)warp;
-    if (i >= n_dirty) return;
-    uint32_t chunk = a.dirty_list[i];
-    uint32_t chunk_next = i + stride < n_dirty ? a.dirty_list[i + stride] : 0u;
-    if (lane == 0) stage_chunk(chunk, 0);
+    // the warp's dirty chunks, 32 candidates at a time: lane l of batch t holds chunk g + (32 t + l) W
+    uint64_t batch = 0;
+    uint32_t mask = 0;
+    bool more = true;  // batches left
+    const auto next_dirty = [&]() -> int64_t {  // the warp's next dirty chunk, -1: none left (warp-uniform)
+        while (!mask && more) {
+            const uint64_t c = g + (batch * 32 + (uint64_t)lane) * W;
+            const uint32_t w = c < a.n_chunks ? a.piece[c] : 0u;
+            mask = __ballot_sync(0xFFFFFFFFu, (w & kPieceDirty) != 0);
+            more = g + (batch + 1) * 32 * W < a.n_chunks;
+            batch++;
+        }
+        if (!mask) return -1;
+        const int l = __ffs((int)mask) - 1;
+        mask &= mask - 1;
+        return (int64_t)(g + ((batch - 1) * 32 + (uint64_t)l) * W);
+    };
+    int64_t chunk = next_dirty();
+    if (chunk < 0) return;
+    if (lane == 0) stage_chunk((uint32_t)chunk, 0);
     uint32_t parity = 0;  // bit b: phase parity of buffer b's barrier
-    for (int b = 0; i < n_dirty; i += stride, b ^= 1) {
-        const uint32_t chunk_after = i + 2 * stride < n_dirty ? a.dirty_list[i + 2 * stride] : 0u;  // two ahead
-        if (lane == 0 && i + stride < n_dirty) stage_chunk(chunk_next, b ^ 1);
+    for (int b = 0; chunk >= 0; b ^= 1) {
+        const int64_t chunk_next = next_dirty();
+        if (lane == 0 && chunk_next >= 0) stage_chunk((uint32_t)chunk_next, b ^ 1);
         mbar_wait(smem_u32(&st.mbar[b]), (parity >> b) & 1u);
         parity ^= 1u << b;
         const uint64_t pos = (uint64_t)chunk * kChunk;
-        const ChunkResult res = general_chunk(a, st.scbits, st.buf[b], pos, 0u, 0u, lane);
+        const ChunkResult res = general_chunk(a, st.scbits, st.buf[b], pos, (uint32_t)chunk, lane);
         if (res.clean) {  // a false alarm (00 00 03 whose zeros are header bytes, ...): the verbatim copy after all
 #pragma unroll
             for (int r = 0; r < kRows; r++)
                 *reinterpret_cast<uint4 *>(a.out + pos + (uint32_t)(r * 32 + lane) * 16u) =
                     *reinterpret_cast<const uint4 *>(st.buf[b] + kHalo + (r * 32 + lane) * 16);
         }
-        if (lane == 0) a.piece[chunk] = (res.piece_nsc << 16) | res.carry_epb;
         __syncwarp();  // every lane is done with this buffer before (next iteration) a bulk load is aimed at it
         chunk = chunk_next;
-        chunk_next = chunk_after;
     }
 }
 
@@ -551,89 +620,96 @@ __device__ __forceinline__ void decode_nal_header(uint32_t hdr4, h264b_nal &o, h
 }
 
 // Post-pass 1: exclusive scans over the chunks of (a) the start-code counts -> ordinal of every chunk's first start
-// code and (b) the EPB fields -> S of nal_pieces(); in two phases over tiles of kOrderTile chunks: tile totals, then
-// every CTA adds up the totals of the tiles before its own (a few hundred values for a 4 GB stream) and scans its tile.
-__device__ __forceinline__ uint2 block_sum2_256(uint2 x, uint2 *warp_sum, int tid) {
+// code, (b) the EPB fields -> S[] and (c) "1 + index of the last chunk with a start code" (a running maximum) -> M[];
+// in two phases over tiles of kOrderTile chunks: tile totals, then every CTA combines the totals of the tiles before its
+// own (a few hundred values for a 4 GB stream) and scans its tile.
+struct Ord3 {
+    uint32_t nsc, epb, last;
+};
+__device__ __forceinline__ Ord3 ord3_of(uint32_t p, uint32_t i) {
+    const uint32_t nsc = (p >> kPieceNscShift) & kPieceNsc;
+    return Ord3{nsc, p & kPieceEpb, nsc ? i + 1u : 0u};
+}
+__device__ __forceinline__ Ord3 ord3_add(Ord3 a, Ord3 b) { return Ord3{a.nsc + b.nsc, a.epb + b.epb, a.last > b.last ? a.last : b.last}; }
+
+__device__ __forceinline__ Ord3 block_sum3_256(Ord3 x, Ord3 *warp_sum, int tid) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
-        x.x += __shfl_xor_sync(0xFFFFFFFFu, x.x, d);
-        x.y += __shfl_xor_sync(0xFFFFFFFFu, x.y, d);
+        Ord3 y;
+        y.nsc = __shfl_xor_sync(0xFFFFFFFFu, x.nsc, d);
+        y.epb = __shfl_xor_sync(0xFFFFFFFFu, x.epb, d);
+        y.last = __shfl_xor_sync(0xFFFFFFFFu, x.last, d);
+        x = ord3_add(x, y);
     }
     if ((tid & 31) == 0) warp_sum[tid >> 5] = x;
     __syncthreads();
-    uint2 t = make_uint2(0, 0);
+    Ord3 t = {0, 0, 0};
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
-        t.x += warp_sum[w].x;
-        t.y += warp_sum[w].y;
-    }
+    for (int w = 0; w < 8; w++) t = ord3_add(t, warp_sum[w]);
     __syncthreads();
     return t;
 }
 
-__global__ void __launch_bounds__(256) order_reduce_kernel(const uint32_t *piece, uint2 *tile_sum, uint32_t n_chunks) {
-    __shared__ uint2 warp_sum[8];
+__global__ void __launch_bounds__(256) order_reduce_kernel(const uint32_t *piece, uint4 *tile_sum, uint32_t n_chunks) {
+    __shared__ Ord3 warp_sum[8];
     const int tid = threadIdx.x;
     const uint32_t base = blockIdx.x * kOrderTile;
-    uint2 x = make_uint2(0, 0);
+    Ord3 x = {0, 0, 0};
 #pragma unroll
     for (int k = 0; k < kOrderTile / 256; k++) {
         const uint32_t i = base + (uint32_t)(k * 256 + tid);
-        if (i < n_chunks) {
-            const uint32_t p = piece[i];
-            x.x += p >> 16;
-            x.y += p & 0xFFFFu;
-        }
+        if (i < n_chunks) x = ord3_add(x, ord3_of(piece[i], i));
     }
-    x = block_sum2_256(x, warp_sum, tid);
-    if (tid == 0) tile_sum[blockIdx.x] = x;
+    x = block_sum3_256(x, warp_sum, tid);
+    if (tid == 0) tile_sum[blockIdx.x] = make_uint4(x.nsc, x.epb, x.last, 0u);
 }
 
-__global__ void __launch_bounds__(256) order_apply_kernel(const uint32_t *piece, const uint2 *tile_sum,
-                                                           uint32_t *piece_ord, uint32_t *piece_S, uint32_t n_chunks) {
-    __shared__ uint2 warp_sum[8];
+__global__ void __launch_bounds__(256) order_apply_kernel(const uint32_t *piece, const uint4 *tile_sum,
+                                                           uint32_t *piece_ord, uint32_t *piece_S, uint32_t *piece_M,
+                                                           uint32_t n_chunks) {
+    __shared__ Ord3 warp_sum[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint2 before = make_uint2(0, 0);  // totals of the tiles before this one
+    Ord3 before = {0, 0, 0};  // totals of the tiles before this one
     for (uint32_t t = (uint32_t)tid; t < blockIdx.x; t += 256) {
-        const uint2 s = tile_sum[t];
-        before.x += s.x;
-        before.y += s.y;
+        const uint4 s = tile_sum[t];
+        before = ord3_add(before, Ord3{s.x, s.y, s.z});
     }
-    before = block_sum2_256(before, warp_sum, tid);
+    before = block_sum3_256(before, warp_sum, tid);
     constexpr int kPer = kOrderTile / 256;  // contiguous chunks per thread
     const uint32_t first = blockIdx.x * kOrderTile + (uint32_t)tid * kPer;
-    uint32_t c[kPer];
-    uint2 own = make_uint2(0, 0);
+    Ord3 c[kPer];
+    Ord3 own = {0, 0, 0};
 #pragma unroll
     for (int k = 0; k < kPer; k++) {
-        c[k] = first + k < n_chunks ? piece[first + k] : 0u;
-        own.x += c[k] >> 16;
-        own.y += c[k] & 0xFFFFu;
+        c[k] = first + k < n_chunks ? ord3_of(piece[first + k], first + (uint32_t)k) : Ord3{0, 0, 0};
+        own = ord3_add(own, c[k]);
     }
-    uint2 x = own;
+    Ord3 x = own;  // inclusive over the warp's threads
+    Ord3 ex = {0, 0, 0};  // exclusive
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t yx = __shfl_up_sync(0xFFFFFFFFu, x.x, d), yy = __shfl_up_sync(0xFFFFFFFFu, x.y, d);
-        if (lane >= d) {
-            x.x += yx;
-            x.y += yy;
-        }
+        Ord3 y;
+        y.nsc = __shfl_up_sync(0xFFFFFFFFu, x.nsc, d);
+        y.epb = __shfl_up_sync(0xFFFFFFFFu, x.epb, d);
+        y.last = __shfl_up_sync(0xFFFFFFFFu, x.last, d);
+        if (lane >= d) x = ord3_add(y, x);
     }
+    ex.nsc = __shfl_up_sync(0xFFFFFFFFu, x.nsc, 1);
+    ex.epb = __shfl_up_sync(0xFFFFFFFFu, x.epb, 1);
+    ex.last = __shfl_up_sync(0xFFFFFFFFu, x.last, 1);
+    if (lane == 0) ex = Ord3{0, 0, 0};
     if (lane == 31) warp_sum[warp] = x;
     __syncthreads();
-    uint2 run = make_uint2(before.x + x.x - own.x, before.y + x.y - own.y);
-    for (int w = 0; w < warp; w++) {
-        run.x += warp_sum[w].x;
-        run.y += warp_sum[w].y;
-    }
+    Ord3 run = ord3_add(before, ex);
+    for (int w = 0; w < warp; w++) run = ord3_add(run, warp_sum[w]);
 #pragma unroll
     for (int k = 0; k < kPer; k++) {
         if (first + k < n_chunks) {
-            piece_ord[first + k] = run.x;
-            piece_S[first + k] = run.y;
+            piece_ord[first + k] = run.nsc;
+            piece_S[first + k] = run.epb;
+            piece_M[first + k] = run.last;
         }
-        run.x += c[k] >> 16;
-        run.y += c[k] & 0xFFFFu;
+        run = ord3_add(run, c[k]);
     }
 }
 
@@ -650,7 +726,7 @@ __global__ void __launch_bounds__(256) nal_permute_kernel(ScanArgs a) {
     }
 }
 
-// Post-pass 3: the h264b_nal records; NALs whose later parts have to slide left are queued for post-pass 4.
+// Post-pass 3: the h264b_nal records.
 __global__ void __launch_bounds__(256) scan_finalize_kernel(ScanArgs a, h264b_nal *nals, h264b_nal_ext *ext,
                                                              h264b_scan_summary *summary) {
     const uint64_t K = a.hdr->total_sc;
@@ -669,7 +745,6 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(ScanArgs a, h264b_na
         decode_nal_header(r0.z, o, ext ? &ext[k] : nullptr);
         uint32_t later_shift;
         const uint64_t removed = nal_removed(o.start, next, r1.w & 0xFFFFu, a.piece_S, (uint64_t)kChunk, &later_shift);
-        if (later_shift) a.fix_list[atomicAdd(&a.hdr->n_fix, 1u)] = (uint32_t)k;
         // body = NumBytes - HeaderBytes - 2 bytes (a NAL shorter than that has no body); its RBSP sits at the body's
         // own position in the output buffer
         const int64_t body = (int64_t)o.num_bytes - (int64_t)o.header_bytes - 2;
@@ -698,173 +773,75 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(ScanArgs a, h264b_na
     }
 }
 
-// Post-pass 4: slide the later parts of the queued NALs left (one CTA per NAL, runs in stream order).  A run moves in
-// steps of 16 KiB: every thread assembles up to four destination-aligned 16-byte granules from aligned source words
-// (funnel shifts) in registers, the CTA synchronises, then stores -- the move overlaps itself, reads come first.
-constexpr int kMoveGran = 4;                         // granules per thread and step
-constexpr uint64_t kMoveStep = 256 * 16 * kMoveGran;  // 16 KiB
-
-__device__ __forceinline__ void move_left(uint8_t *out, uint64_t ps, uint64_t len, uint64_t G) {
-    const uint64_t d0 = ps - G, d1 = d0 + len;  // destination range
-    const uint32_t s8 = (uint32_t)((d0 + G) & 3u) * 8u;  // (the same for every granule: D is a multiple of 16)
-    (void)s8;
-    for (uint64_t base = d0 & ~15ull; base < d1; base += kMoveStep) {
-        uint32_t y[kMoveGran][4];
+// Post-pass 4: chunks the copy kernel stored verbatim although the NAL open at their first byte had lost emulation-
+// prevention bytes in an earlier chunk (G > 0 of them): that NAL's bytes of the chunk are copied again from the input
+// stream, G bytes to the left.  Every such chunk is independent of every other (the dirty-chunk kernel has written its
+// own chunks at their final place already), and real streams have few: a warp looks at 32 chunks, then copies the
+// flagged ones, one destination-aligned 16-byte granule per lane and step, assembled from aligned source words.
+__device__ __forceinline__ void shifted_copy_warp(const uint8_t *in, uint8_t *out, uint64_t ps, uint64_t pe, uint64_t G,
+                                                  int lane) {
+    const uint64_t d0 = ps - G, d1 = pe - G;  // destination range
+    for (uint64_t D = (d0 & ~15ull) + (uint64_t)lane * 16u; D < d1; D += 512u) {
+        const uint64_t src = D + G;
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(in + (src & ~3ull));
+        const uint32_t sh = (uint32_t)(src & 3u) * 8u;
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = sh ? wp[4] : 0u;
+        const uint32_t y[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                               __funnelshift_r(w3, w4, sh)};
+        if (D >= d0 && D + 16 <= d1) {
+            *reinterpret_cast<uint4 *>(out + D) = make_uint4(y[0], y[1], y[2], y[3]);
+        } else {
 #pragma unroll
-        for (int q = 0; q < kMoveGran; q++) {
-            const uint64_t D = base + (uint64_t)(q * 256 + (int)threadIdx.x) * 16u;
-            if (D < d1) {
-                const uint64_t src = D + G;
-                const uint32_t *wp = reinterpret_cast<const uint32_t *>(out + (src & ~3ull));
-                const uint32_t sh = (uint32_t)(src & 3u) * 8u;
-                const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = sh ? wp[4] : 0u;
-                y[q][0] = __funnelshift_r(w0, w1, sh);
-                y[q][1] = __funnelshift_r(w1, w2, sh);
-                y[q][2] = __funnelshift_r(w2, w3, sh);
-                y[q][3] = __funnelshift_r(w3, w4, sh);
-            }
+            for (int j = 0; j < 16; j++)
+                if (D + j >= d0 && D + j < d1) out[D + j] = (uint8_t)granule_byte(y, j);
         }
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < kMoveGran; q++) {
-            const uint64_t D = base + (uint64_t)(q * 256 + (int)threadIdx.x) * 16u;
-            if (D < d1) {
-                if (D >= d0 && D + 16 <= d1) {
-                    *reinterpret_cast<uint4 *>(out + D) = make_uint4(y[q][0], y[q][1], y[q][2], y[q][3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; j++)
-                        if (D + j >= d0 && D + j < d1) out[D + j] = (uint8_t)granule_byte(y[q], j);
-                }
-            }
-        }
-        __syncthreads();
     }
 }
 
-constexpr int kFixWindow = 1024;  // parts staged at a time (2 MiB of a NAL)
-constexpr int kFixSub = 6;        // parts walked per step: their runs (<= kFixSub + 1, 12 KiB + edges) move together
-constexpr int kMoveBatch = 8;
-
-// The walk over a NAL's parts is serial bookkeeping: warp 0 does it, kFixSub parts at a time, and publishes the runs;
-// then the whole CTA moves them.  Short runs (an EPB-dense NAL has one per 2 KiB part) move together, 16 KiB of
-// destination per step: all sources of a batch are read before any of its destinations is written, and batches go left
-// to right, so a batch never reads what an earlier one wrote.  A long run (untouched parts that slide as one) moves on
-// its own in steps of 16 KiB (move_left).
-struct MoveBatch {
-    uint64_t d0[kMoveBatch], G[kMoveBatch], len[kMoveBatch];
-    int n;
-};
-constexpr uint64_t kLongRun = 8192;  // bytes
-
-__device__ __forceinline__ void move_short_runs(uint8_t *out, const MoveBatch *mb, int r0, int r1) {
-    // granule slots of runs r0 .. r1-1, dealt to the threads round-robin (at most kMoveGran per thread)
-    uint32_t y[kMoveGran][4];
-#pragma unroll
-    for (int pass = 0; pass < 2; pass++) {
-#pragma unroll
-        for (int q = 0; q < kMoveGran; q++) {
-            uint32_t slot = (uint32_t)(q * 256 + (int)threadIdx.x);
-            int r = r0;
-            uint64_t d0 = 0, d1 = 0, g = 0;
-            for (; r < r1; r++) {
-                d0 = mb->d0[r];
-                d1 = d0 + mb->len[r];
-                g = ((d1 + 15) >> 4) - (d0 >> 4);
-                if (slot < g) break;
-                slot -= (uint32_t)g;
-            }
-            if (r == r1) continue;
-            const uint64_t G = mb->G[r];
-            const uint64_t D = (d0 & ~15ull) + (uint64_t)slot * 16u;
-            if (pass == 0) {
-                const uint64_t src = D + G;
-                const uint32_t *wp = reinterpret_cast<const uint32_t *>(out + (src & ~3ull));
-                const uint32_t sh = (uint32_t)(src & 3u) * 8u;
-                const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = sh ? wp[4] : 0u;
-                y[q][0] = __funnelshift_r(w0, w1, sh);
-                y[q][1] = __funnelshift_r(w1, w2, sh);
-                y[q][2] = __funnelshift_r(w2, w3, sh);
-                y[q][3] = __funnelshift_r(w3, w4, sh);
-            } else if (D >= d0 && D + 16 <= d1) {
-                *reinterpret_cast<uint4 *>(out + D) = make_uint4(y[q][0], y[q][1], y[q][2], y[q][3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; j++)
-                    if (D + j >= d0 && D + j < d1) out[D + j] = (uint8_t)granule_byte(y[q], j);
-            }
-        }
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(256, 6) nal_fixup_kernel(ScanArgs a, h264b_scan_summary *summary) {
-    __shared__ uint32_t sh_tail[kFixWindow], sh_S[kFixWindow];
-    __shared__ MoveBatch mb;
-    const uint32_t n_fix = a.hdr->n_fix;
+__global__ void __launch_bounds__(256) chunk_shift_kernel(ScanArgs a, h264b_scan_summary *summary) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // totals of scan_finalize_kernel (complete: previous launch)
         summary->n_epb = a.hdr->n_epb;
         summary->rbsp_bytes = a.hdr->total_kept;  // RBSP bytes of all emitted NAL units
     }
-    const bool walker = threadIdx.x < 32;
-    __shared__ uint32_t sh_next;
-    for (;;) {  // NAL units are handed out first come first served (their sizes differ by orders of magnitude)
-        __syncthreads();
-        if (threadIdx.x == 0) sh_next = (uint32_t)atomicAdd(&a.hdr->reserved[0], 1ull);
-        __syncthreads();
-        const uint32_t f = sh_next;
-        if (f >= n_fix) break;
-        const uint64_t k = a.fix_list[f];
-        const uint4 r0 = a.nal_rec[k], r1 = a.nal_rec[k + 1];
-        const uint64_t st = rec_start(r0), next = rec_start(r1);
-        const uint32_t H = nal_header_bytes(r0.z & 0xFFu, (r0.z >> 8) & 0xFFu);
-        const uint64_t Tq = (st - 1) / kChunk, Tb = (next - 1) / kChunk;
-        const uint32_t S_Tq = a.piece_S[Tq];
-        MoveRun run = {0, 0, 0};  // (warp 0's)
-        int n = 0;
-        const auto publish = [&](uint64_t ps, uint64_t len, uint64_t G) {  // (n <= kFixSub + 1 <= kMoveBatch per step)
-            if (threadIdx.x == 0) {
-                mb.d0[n] = ps - G;
-                mb.G[n] = G;
-                mb.len[n] = len;
-            }
-            n++;
-        };
-        for (uint64_t t0 = Tq + 1; t0 <= Tb; t0 += kFixWindow) {
-            const uint64_t t1 = t0 + kFixWindow <= Tb + 1 ? t0 + kFixWindow : Tb + 1;
-            __syncthreads();
-            for (uint64_t t = t0 + threadIdx.x; t < t1; t += 256) {
-                sh_tail[t - t0] = a.piece[t];
-                sh_S[t - t0] = a.piece_S[t];
-            }
-            __syncthreads();
-            for (uint64_t s0 = t0; s0 < t1; s0 += kFixSub) {
-                const uint64_t s1 = s0 + kFixSub < t1 ? s0 + kFixSub : t1;
-                if (walker) {
-                    n = 0;
-                    nal_pieces_window(st, next, H, r1.w & 0xFFFFu, sh_tail, sh_S, t0, S_Tq, (uint64_t)kChunk, s0, s1, run, publish);
-                    if (s1 == Tb + 1) nal_pieces_flush(run, publish);
-                    if (threadIdx.x == 0) mb.n = n;
-                }
-                __syncthreads();
-                const int nr = mb.n;
-                for (int a0 = 0; a0 < nr;) {  // groups in stream order: a long run alone, short runs together
-                    if (mb.len[a0] >= kLongRun) {
-                        move_left(a.out, mb.d0[a0] + mb.G[a0], mb.len[a0], mb.G[a0]);
-                        a0++;
-                        continue;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = (uint64_t)gridDim.x * 8u, warp_id = (uint64_t)blockIdx.x * 8u + (threadIdx.x >> 5);
+    for (uint64_t t0 = warp_id * 32u; t0 < a.n_chunks; t0 += warps * 32u) {
+        const uint64_t t = t0 + (uint64_t)lane;
+        uint64_t ps = 0, pe = 0;
+        uint32_t G = 0;
+        if (t < a.n_chunks && t > 0) {
+            const uint32_t p = a.piece[t], M = a.piece_M[t];
+            if (!(p & kPieceDirty) && M) {  // stored verbatim, and some NAL is open at its first byte
+                const uint32_t Tq = M - 1u;  // the chunk where that NAL starts (after its last start code)
+                G = a.piece_S[t] - a.piece_S[Tq];
+                if (G) {
+                    const uint32_t pq = a.piece[Tq];
+                    const uint64_t k = (uint64_t)a.piece_ord[Tq] + ((pq >> kPieceNscShift) & kPieceNsc) - 1u;  // the NAL's ordinal
+                    const uint64_t lo = t * (uint64_t)kChunk;
+                    ps = lo;
+                    pe = lo + kChunk;
+                    if (k + 1 < a.nal_cap) {  // (an index too small for the stream is reported as such: nothing to do)
+                        const uint4 r0 = a.nal_rec[k];
+                        const uint64_t body = rec_start(r0) + nal_header_bytes(r0.z & 0xFFu, (r0.z >> 8) & 0xFFu);
+                        if (body > ps) ps = body;
+                        if ((p >> kPieceNscShift) & kPieceNsc) {  // the NAL ends in this chunk: its last two bytes stay out
+                            const uint64_t b = rec_start(a.nal_rec[k + 1]);
+                            pe = b - 2;
+                        }
+                    } else {
+                        G = 0;
                     }
-                    int a1 = a0;
-                    uint64_t bytes = 0;
-                    while (a1 < nr && mb.len[a1] < kLongRun && bytes + mb.len[a1] <= (uint64_t)kMoveGran * 256 * 16 - 16 * (kMoveBatch + 1)) {
-                        bytes += mb.len[a1];
-                        a1++;
-                    }
-                    move_short_runs(a.out, &mb, a0, a1);
-                    a0 = a1;
+                    if (pe <= ps) G = 0;
                 }
-                __syncthreads();
             }
+        }
+        uint32_t todo = __ballot_sync(0xFFFFFFFFu, G != 0);
+        while (todo) {
+            const int l = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            const uint64_t ps_l = __shfl_sync(0xFFFFFFFFu, ps, l), pe_l = __shfl_sync(0xFFFFFFFFu, pe, l);
+            const uint32_t G_l = __shfl_sync(0xFFFFFFFFu, G, l);
+            shifted_copy_warp(a.in, a.out, ps_l, pe_l, (uint64_t)G_l, lane);
         }
     }
 }
@@ -986,7 +963,7 @@ __global__ void __launch_bounds__(1024) slice_select_kernel(const h264b_nal *nal
 
 // ------------------------------------------------------------------------------------------------ launchers
 struct ScratchOffsets {
-    uint64_t piece, dirty_list, piece_ord, piece_S, tile_sum, fix_list, rec, nal_rec, total;
+    uint64_t piece, piece_carry, piece_ord, piece_S, piece_M, tile_sum, rec, nal_rec, total;
 };
 static ScratchOffsets scratch_layout(uint64_t n, uint32_t nal_cap) {
     const uint64_t n_chunks = (n + kChunk - 1) / kChunk;
@@ -997,12 +974,12 @@ static ScratchOffsets scratch_layout(uint64_t n, uint32_t nal_cap) {
         p = (p + bytes + 15) & ~15ull;
         return at;
     };
-    o.piece = take(n_chunks * 4);  // directly behind the header: one memset clears both
-    o.dirty_list = take(n_chunks * 4);
+    o.piece = take(n_chunks * 4);  // directly behind the header, then piece_carry: one memset clears all three
+    o.piece_carry = take(n_chunks * 4);
     o.piece_ord = take(n_chunks * 4);
     o.piece_S = take(n_chunks * 4);
-    o.tile_sum = take((n_chunks + kOrderTile - 1) / kOrderTile * 8);
-    o.fix_list = take((uint64_t)nal_cap * 4);
+    o.piece_M = take(n_chunks * 4);
+    o.tile_sum = take((n_chunks + kOrderTile - 1) / kOrderTile * 16);
     o.rec = take((uint64_t)nal_cap * 16);
     o.nal_rec = take((uint64_t)nal_cap * 16);
     o.total = (p + 255) & ~255ull;
@@ -1037,11 +1014,11 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     a.out = d_rbsp;
     a.hdr = (ScanScratchHeader *)s;
     a.piece = (uint32_t *)(s + so.piece);
-    a.dirty_list = (uint32_t *)(s + so.dirty_list);
+    a.piece_carry = (uint32_t *)(s + so.piece_carry);
     a.piece_ord = (uint32_t *)(s + so.piece_ord);
     a.piece_S = (uint32_t *)(s + so.piece_S);
-    a.tile_sum = (uint2 *)(s + so.tile_sum);
-    a.fix_list = (uint32_t *)(s + so.fix_list);
+    a.piece_M = (uint32_t *)(s + so.piece_M);
+    a.tile_sum = (uint4 *)(s + so.tile_sum);
     a.rec = (uint4 *)(s + so.rec);
     a.nal_rec = (uint4 *)(s + so.nal_rec);
     a.nal_cap = nal_cap;
@@ -1056,8 +1033,8 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     }
     const auto enqueue = [&]() -> int {
         unsigned launched = 0;
-        // header + per-chunk (start codes | EPBs) array: all zero
-        H264B_CUDA(ctx, cudaMemsetAsync(s, 0, so.piece + n_chunks * 4, ctx->stream));
+        // header + the per-chunk counts and carries: all zero
+        H264B_CUDA(ctx, cudaMemsetAsync(s, 0, so.piece_ord, ctx->stream));
         if (n_chunks) {
             annexb_copy_kernel<<<(unsigned)((n_chunks + kWarpsA - 1) / kWarpsA), kWarpsA * 32, 0, ctx->stream>>>(a);
             H264B_LAUNCH_CHECK(ctx, "annexb_copy_kernel");
@@ -1068,7 +1045,8 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
             const unsigned tiles = (unsigned)((n_chunks + kOrderTile - 1) / kOrderTile);
             order_reduce_kernel<<<tiles, 256, 0, ctx->stream>>>(a.piece, a.tile_sum, a.n_chunks);
             H264B_LAUNCH_CHECK(ctx, "order_reduce_kernel");
-            order_apply_kernel<<<tiles, 256, 0, ctx->stream>>>(a.piece, a.tile_sum, a.piece_ord, a.piece_S, a.n_chunks);
+            order_apply_kernel<<<tiles, 256, 0, ctx->stream>>>(a.piece, a.tile_sum, a.piece_ord, a.piece_S, a.piece_M,
+                                                               a.n_chunks);
             H264B_LAUNCH_CHECK(ctx, "order_apply_kernel");
             nal_permute_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a);
             H264B_LAUNCH_CHECK(ctx, "nal_permute_kernel");
@@ -1076,8 +1054,13 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
         }
         scan_finalize_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a, d_nals, d_ext, d_summary);
         H264B_LAUNCH_CHECK(ctx, "scan_finalize_kernel");
-        nal_fixup_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(a, d_summary);
-        H264B_LAUNCH_CHECK(ctx, "nal_fixup_kernel");
+        {
+            uint64_t grid_s = (n_chunks + 255) / 256;  // 32 chunks per warp and step
+            if (grid_s > (uint64_t)ctx->sm_count * 8) grid_s = (uint64_t)ctx->sm_count * 8;
+            if (grid_s < 1) grid_s = 1;
+            chunk_shift_kernel<<<(unsigned)grid_s, 256, 0, ctx->stream>>>(a, d_summary);
+            H264B_LAUNCH_CHECK(ctx, "chunk_shift_kernel");
+        }
         (void)launched;
         return H264B_OK;
     };
