@@ -193,9 +193,11 @@ __global__ void __launch_bounds__(kWarpsA * 32) annexb_copy_kernel(ScanArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ K1b: dirty chunks
+constexpr int kStageBufs = 3;  // chunk being written, chunk whose counts are being taken, chunk on its way
 struct __align__(16) WarpStage {
-    uint8_t buf[2][kSlotBytes];           // double buffer; each: [0,16) low halo, [16,16+kChunk) chunk, high halo
-    unsigned long long mbar[2];           // "bytes have landed"
+    uint8_t buf[kStageBufs][kSlotBytes];  // each: [0,16) low halo, [16,16+kChunk) chunk, high halo
+    unsigned long long mbar[kStageBufs];  // "bytes have landed"
+    unsigned long long pad0;
     uint16_t scbits[kChunkGran + 2];      // start-code-end bits per granule, [0] = halo granule before the chunk
     uint16_t pad[(8 - (kChunkGran + 2) % 8) % 8];
 };
@@ -223,77 +225,11 @@ __device__ __forceinline__ uint32_t warp_seg_scan(uint32_t x, int lane) {  // in
     return x;
 }
 
-// The general path is rare for real streams; its pieces are kept out of line so that the hot loop stays small.
+// Pieces that few lanes need are kept out of line so that the walk of a chunk stays small.
 __device__ __noinline__ uint32_t keep_near_sc(const uint8_t *tile_in, uint64_t base, uint64_t gpos, uint32_t e16,
                                               uint32_t sc_prev, uint32_t sc_own, uint32_t sc_next, uint32_t *epb_eff) {
     auto get = [&](int64_t p) -> uint32_t { return tile_in[p - (int64_t)base]; };
     return keep_mask_near_sc(get, (int64_t)gpos, e16, sc_prev, sc_own, sc_next, epb_eff);
-}
-
-__device__ __noinline__ void compact_row_in_place(uint8_t *row, const uint8_t *src, uint32_t k16, uint32_t loff) {
-    const uint4 v = *reinterpret_cast<const uint4 *>(src);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    __syncwarp();  // every lane has its bytes in registers before anyone overwrites the span
-    if (k16 == 0xFFFFu && (loff & 3u) == 0) {
-        uint32_t *d = reinterpret_cast<uint32_t *>(row + loff);
-        d[0] = w[0];
-        d[1] = w[1];
-        d[2] = w[2];
-        d[3] = w[3];
-    } else {
-#pragma unroll
-        for (int j = 0; j < 16; j++)
-            if (k16 & (1u << j)) row[loff++] = (uint8_t)(w[j >> 2] >> ((j & 3) * 8));
-    }
-}
-
-// one lane's granule of a row with NAL boundaries: kept bytes one by one, one record per start-code end
-//   c     EPBs removed so far (in this chunk) from the NAL open at the granule's first byte
-//   k     record slot of the first start code of the granule;  rank: its rank inside the chunk
-// tile_in is the staged chunk (tile_in[i] = s[pos + i]); the row has not been compacted, and neither has any byte a
-// NAL header can reach (header bytes are dropped bytes: their rows are never "EPB-only")
-__device__ __noinline__ void store_boundary_granule(const ScanArgs &a, const uint8_t *tile_in, uint64_t pos, int gi,
-                                                    uint32_t k16, uint32_t ee, uint32_t sc, uint64_t c, uint64_t k,
-                                                    uint32_t rank, bool first_of_chunk, uint32_t carry_in) {
-    const uint64_t gpos = pos + (uint64_t)gi * 16;
-    const uint4 v = *reinterpret_cast<const uint4 *>(tile_in + gi * 16);
-    if (k16 == 0xFFFFu && sc == 0 && ((gpos - c) & 15u) == 0) {  // an ordinary granule of such a row (ee is 0 then)
-        *reinterpret_cast<uint4 *>(a.out + gpos - c) = v;
-        return;
-    }
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    store_granule_bytes(a.out, gpos, w, k16, ee, sc, c, [&](int j, uint64_t c_end) {
-        const uint64_t st = gpos + (uint64_t)j + 1;  // the new NAL's first byte
-        // the record keeps the count since the start of the chunk for a NAL that was open when the chunk began (the
-        // chunks before it are added from S[] by nal_removed)
-        const uint32_t c_local = (uint32_t)c_end - (first_of_chunk ? carry_in : 0u);
-        if (first_of_chunk) {
-            atomicMax(&a.hdr->first_inv, ~(unsigned long long)st);
-            first_of_chunk = false;
-        }
-        if (k < a.nal_cap) {
-            const uint8_t *hb = tile_in + gi * 16 + j + 1;  // its first 4 bytes (0xFF past the end of the stream)
-            const uint32_t h = (uint32_t)hb[0] | ((uint32_t)hb[1] << 8) | ((uint32_t)hb[2] << 16) | ((uint32_t)hb[3] << 24);
-            a.rec[k] = make_uint4((uint32_t)st, (uint32_t)(st >> 32), h, c_local | (rank << 16));
-        }
-        k++;
-        rank++;
-    });
-}
-
-__device__ __noinline__ void store_row(uint8_t *out, uint64_t o, uint32_t len, const uint8_t *src, int lane,
-                                       const uint8_t *prev_tail, bool next_joins) {
-    const uint4 v = *reinterpret_cast<const uint4 *>(src);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t wp[4];
-    if ((uint32_t)o & 15u) {  // warp-uniform: only shifted rows need the neighbour's bytes
-#pragma unroll
-        for (int k = 0; k < 4; k++) wp[k] = __shfl_up_sync(0xFFFFFFFFu, w[k], 1);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; k++) wp[k] = 0;
-    }
-    store_row_lane(out, o, len, wp, w, lane, prev_tail, next_joins);
 }
 
 // EPBs removed so far from the NAL that is open at the first byte of `chunk`: the chunks before it are walked
@@ -334,21 +270,22 @@ __device__ __noinline__ uint32_t lookback_carry(const ScanArgs &a, uint32_t chun
                 if (tmask) return carry;
                 break;
             }
-            __nanosleep(40);
+            __nanosleep(20);
         }
     }
     return carry;
 }
 
-struct ChunkResult {
-    uint32_t clean;      // nothing to remove after all and nothing shifted: the caller bulk-stores the chunk
+// What the first walk over a staged chunk leaves for the second one (per lane: its granule of every row).
+struct ChunkMasks {
+    uint32_t es[kRows];   // emulation-prevention bytes really removed | start-code-end mask << 16
+    uint32_t pre[kRows];  // segmented count in front of the granule (inside the chunk): seg_combine format
+    uint32_t total;       // ... of the whole chunk (warp-uniform)
 };
 
-// General path of one chunk (whole warp).  tile_in[i] = s[pos + i] for i in [-16, kChunk + 16), bytes outside the
-// stream read as 0xFF.
-__device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, uint16_t *scbits, uint8_t *buf, uint64_t pos,
-                                                  uint32_t chunk, int lane) {
-    const uint32_t piece_nsc = 0;
+// First walk (whole warp).  tile_in[i] = s[pos + i] for i in [-16, kChunk + 16); bytes outside the stream are made 0xFF
+// here.  Exact masks, start-code bitmap, the bit-domain fix-up near start codes and the segmented counts.
+__device__ __forceinline__ ChunkMasks chunk_masks(const ScanArgs &a, uint16_t *scbits, uint8_t *buf, uint64_t pos, int lane) {
     uint8_t *tile_in = buf + kHalo;
     if (pos == 0 || pos + kChunk + kHalo > a.n) {  // bytes outside the stream read as 0xFF (they match no predicate)
         const uint64_t n16 = (a.n + 15) & ~15ull;
@@ -364,7 +301,6 @@ __device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, uint16_t *s
         }
         __syncwarp();
     }
-    // ---------------------------------------------------------------- exact masks + start-code bitmap
     uint32_t em[kRows];  // raw EPB mask | start-code mask << 16
 #pragma unroll
     for (int r = 0; r < kRows; r++) {
@@ -383,139 +319,295 @@ __device__ __noinline__ ChunkResult general_chunk(const ScanArgs &a, uint16_t *s
         const uint32_t prev = lane ? *reinterpret_cast<const uint32_t *>(tile_in + gi * 16 - 4) : 0xFFFFFFFFu;
         scbits[gi + 1] = (uint16_t)granule_masks(w, prev).sc;
     }
-    // Record slots for the chunk's start codes: the atomic is issued now, its result is only needed by the stores
-    // below.  (Bytes past the end of the stream are 0xFF in the slot, so no start code is counted there.)
-    uint32_t n_sc_raw = 0;
-#pragma unroll
-    for (int r = 0; r < kRows; r++) n_sc_raw += bits_popc(em[r] >> 16);
-    n_sc_raw = __reduce_add_sync(0xFFFFFFFFu, n_sc_raw);
-    unsigned long long slot0 = 0;
-    if (n_sc_raw && lane == 0) slot0 = atomicAdd(&a.hdr->total_sc, (unsigned long long)n_sc_raw);
     __syncwarp();
-
-    // ---------------------------------------------------------------- adjust + classify + per-row segmented scan
     const bool has_end = pos + kChunk > a.n;  // some granules reach past the stream
-    uint32_t ks[kRows];    // keep mask | start-code mask << 16
-    uint32_t ee[kRows];    // emulation-prevention bytes really removed
-    uint32_t incl[kRows];  // inclusive segmented scan inside the row
-    uint32_t rp[kRows + 1];  // exclusive prefix of each row inside the chunk (warp-uniform); [kRows] = chunk total
-    uint32_t cls = 0;        // 2 bits per row, warp-uniform: 0 untouched, 1 only EPBs removed, 2 boundaries / stream end
-    rp[0] = 0;
+    ChunkMasks cm;
+    uint32_t rp = 0;  // segmented count in front of the row (warp-uniform)
 #pragma unroll
     for (int r = 0; r < kRows; r++) {
         const int gi = r * 32 + lane;
         const uint64_t gpos = pos + (uint64_t)gi * 16;
         uint32_t e16 = em[r] & 0xFFFFu;
-        uint32_t k16 = ~e16 & 0xFFFFu;
         // start-code ends q in [g-6, g+16] change what this granule keeps
         const uint32_t near = ((uint32_t)scbits[gi] >> 10) | scbits[gi + 1] | (scbits[gi + 2] & 1u);
         if (near)  // header bytes, the 2-byte tail rule and the EPB guard, all in the bit domain
-            k16 = keep_near_sc(tile_in, pos, gpos, e16, scbits[gi], scbits[gi + 1], scbits[gi + 2], &e16);
+            (void)keep_near_sc(tile_in, pos, gpos, e16, scbits[gi], scbits[gi + 1], scbits[gi + 2], &e16);
         uint32_t sc = em[r] >> 16;
         if (has_end) {
             if (gpos >= a.n) {
-                k16 = 0;
                 sc = 0;
                 e16 = 0;
             } else if (gpos + 16 > a.n) {
                 const uint32_t valid = (1u << (uint32_t)(a.n - gpos)) - 1u;
-                k16 &= valid;
                 sc &= valid;
                 e16 &= valid;
             }
         }
-        ks[r] = k16 | (sc << 16);
-        ee[r] = e16;
-        uint32_t x;
-        if (__all_sync(0xFFFFFFFFu, k16 == 0xFFFFu)) {  // nothing removed
+        cm.es[r] = e16 | (sc << 16);
+        uint32_t x;  // inclusive segmented scan inside the row
+        if (__all_sync(0xFFFFFFFFu, (e16 | sc) == 0)) {
             x = 0;
-        } else if (__all_sync(0xFFFFFFFFu, (k16 | e16) == 0xFFFFu && sc == 0)) {  // only EPBs removed
-            cls |= 1u << (2 * r);
-            x = warp_seg_scan(bits_popc(e16), lane);
+        } else if (__all_sync(0xFFFFFFFFu, sc == 0)) {
+            x = bits_popc(e16);
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+                if (lane >= d) x += y;
+            }
         } else {
-            cls |= 2u << (2 * r);
             x = warp_seg_scan(seg_element(e16, sc), lane);
         }
-        incl[r] = x;
-        rp[r + 1] = seg_combine(rp[r], __shfl_sync(0xFFFFFFFFu, x, 31));
-    }
-    const uint32_t total = rp[kRows];
-    const uint32_t n_sc = (total >> 16) & 0x1FFFu;  // == n_sc_raw
-    // The chunk's own counts are final: publish them, then ask the chunks before this one how far the NAL that is open
-    // at its first byte has shifted (nobody is kept waiting while this warp waits).
-    if (lane == 0)
-        *(volatile uint32_t *)&a.piece[chunk] = kPieceReady | kPieceDirty | (n_sc << kPieceNscShift) | (total & kPieceEpb);
-    const uint32_t carry_epb = lookback_carry(a, chunk, lane);
-    if (lane == 0) *(volatile uint32_t *)&a.piece_carry[chunk] = kPieceReady | seg_apply(total, carry_epb);
-    ChunkResult res;
-    res.clean = 0;
-    if (cls == 0 && carry_epb == 0) {  // false alarm (00 00 xx with xx > 3): a verbatim copy after all
-        res.clean = 1;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // (the fills above)
-        return res;
-    }
-
-    // ---------------------------------------------------------------- rows with boundaries: bytes + NAL records
-    if (n_sc) slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
-#pragma unroll
-    for (int r = 0; r < kRows; r++) {
-        if (((cls >> (2 * r)) & 3u) != 2u) continue;  // warp-uniform
-        const int gi = r * 32 + lane;
-        uint32_t ex = __shfl_up_sync(0xFFFFFFFFu, incl[r], 1);
+        uint32_t ex = __shfl_up_sync(0xFFFFFFFFu, x, 1);
         if (lane == 0) ex = 0;
-        const uint32_t pre = seg_combine(rp[r], ex);
-        const uint64_t c = seg_apply(pre, carry_epb);
-        const uint32_t before = (pre >> 16) & 0x1FFFu;  // start codes of the chunk before this granule
-        store_boundary_granule(a, tile_in, pos, gi, ks[r] & 0xFFFFu, ee[r], ks[r] >> 16, c, slot0 + before,
-                               piece_nsc + before, before == 0, carry_epb);
+        cm.pre[r] = seg_combine(rp, ex);
+        rp = seg_combine(rp, __shfl_sync(0xFFFFFFFFu, x, 31));
     }
-    __syncwarp();
+    cm.total = rp;
+    return cm;
+}
 
-    // ---------------------------------------------------------------- in-place compaction of EPB-only rows
-    // inside their own 512-byte span of the slot: afterwards they are `len` contiguous bytes like untouched rows
-#pragma unroll
-    for (int r = 0; r < kRows; r++) {
-        if (((cls >> (2 * r)) & 3u) != 1u) continue;  // warp-uniform
-        const int gi = r * 32 + lane;
-        const uint32_t loff = 16u * (uint32_t)lane - (incl[r] - bits_popc(ee[r]));  // kept bytes of the lanes before
-        compact_row_in_place(tile_in + r * 512, tile_in + gi * 16, ks[r] & 0xFFFFu, loff);
-    }
-    __syncwarp();
-
-    // ---------------------------------------------------------------- the other rows: shuffle-aligned 16-byte stores
-#pragma unroll
-    for (int r = 0; r < kRows; r++) {
-        const int gi = r * 32 + lane;
-        const uint32_t c2 = (cls >> (2 * r)) & 3u;
-        if (c2 == 2u) continue;
-        // one contiguous run of len bytes, shifted left by the EPBs removed from its NAL so far in this chunk
-        const uint64_t c_row = seg_apply(rp[r], carry_epb);
-        const uint32_t removed = c2 ? ((rp[r + 1] - rp[r]) & 0x7FFFu) : 0u;
-        const uint64_t o = pos + 512u * (uint32_t)r - c_row;
-        const uint8_t *prev_tail = nullptr;
-        if (r > 0 && ((cls >> (2 * r - 2)) & 3u) != 2u) {
-            const uint32_t prev_removed = (rp[r] - rp[r - 1]) & 0x7FFFu;
-            prev_tail = tile_in + 512 * r - prev_removed;
+// NAL records of the start-code ends in one lane's granule (few lanes have any).  hdr4 bytes are read from the staged
+// chunk, so this runs before the chunk is rewritten in place.
+__device__ __noinline__ void emit_dirty_records(const ScanArgs &a, const uint8_t *tile_in, uint64_t pos, int gi, uint32_t ee,
+                                                uint32_t sc, uint32_t pre, uint64_t slot0) {
+    uint32_t rank = (pre >> 16) & 0x1FFFu;  // start codes of the chunk in front of this granule
+    uint32_t c = pre & 0x7FFFu;             // EPBs since the last NAL start / the start of the chunk
+    int prev = -1;
+    while (sc) {
+        const int j = __ffs((int)sc) - 1;
+        sc &= sc - 1;
+        const uint32_t between = (ee >> (prev + 1)) & ((1u << (j - prev - 1)) - 1u);  // (no EPB at a start-code end)
+        c += bits_popc(between);
+        const uint64_t st = pos + (uint64_t)gi * 16 + (uint64_t)j + 1;  // the new NAL's first byte
+        if (rank == 0) atomicMax(&a.hdr->first_inv, ~(unsigned long long)st);
+        if (slot0 + rank < a.nal_cap) {
+            const uint8_t *hb = tile_in + gi * 16 + j + 1;  // its first 4 bytes (0xFF past the end of the stream)
+            const uint32_t h = (uint32_t)hb[0] | ((uint32_t)hb[1] << 8) | ((uint32_t)hb[2] << 16) | ((uint32_t)hb[3] << 24);
+            // .w: EPBs the NAL that ends here lost inside this chunk (nal_removed adds the chunks before from S[])
+            a.rec[slot0 + rank] = make_uint4((uint32_t)st, (uint32_t)(st >> 32), h, c | (rank << 16));
         }
-        const bool next_joins = r < kRows - 1 && ((cls >> (2 * r + 2)) & 3u) != 2u;
-        store_row(a.out, o, 512u - removed, tile_in + gi * 16, lane, prev_tail, next_joins);
+        rank++;
+        c = 0;
+        prev = j;
     }
-    // generic-proxy writes to the slot (fills, compaction) are ordered before the TMA writes that will reuse it
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    return res;
+}
+
+// A granule with start-code ends, byte by byte into the image (few lanes).  x0 = image offset of the granule's first
+// byte if nothing had been removed so far; c = EPBs removed so far from the open NAL (plus the sub-granule part of
+// the carry while that NAL is the one open at the chunk's first byte); after a start-code end the count restarts.
+__device__ __noinline__ void image_boundary_granule(uint8_t *tile_in, int gi, uint4 v4, uint32_t ee, uint32_t sc,
+                                                    uint32_t c) {
+    const uint32_t v[4] = {v4.x, v4.y, v4.z, v4.w};
+    for (int j = 0; j < 16; j++) {
+        const uint32_t bit = 1u << j;
+        if (ee & bit) {
+            c++;
+        } else {
+            tile_in[gi * 16 + j - (int)c] = (uint8_t)granule_byte(v, j);  // (dropped bytes land between two RBSPs)
+        }
+        if (sc & bit) c = 0;
+    }
+}
+
+// 16-byte granules [x0, x1) of the image (offsets relative to tile_in, which is 16-byte aligned like `base`) to
+// out[base + x]: aligned 16-byte stores inside, single bytes at the two ragged ends (neighbouring chunks own the
+// bytes beyond them).
+__device__ __forceinline__ void store_image(uint8_t *out, uint64_t base, const uint8_t *tile_in, int x0, int x1, int lane) {
+    if (x1 <= x0) return;
+    const int g0 = x0 >> 4, g1 = (x1 + 15) >> 4;  // (arithmetic shift: x0 may be negative)
+    const bool head = (x0 & 15) != 0, tail = (x1 & 15) != 0 && (g1 - 1 > g0 || !head);
+    for (int g = g0 + (head ? 1 : 0) + lane; g < g1 - ((x1 & 15) ? 1 : 0); g += 32)
+        *reinterpret_cast<uint4 *>(out + base + (int64_t)g * 16) = *reinterpret_cast<const uint4 *>(tile_in + g * 16);
+    // lanes 0..15: the head granule's bytes; lanes 16..31: the tail granule's
+    if (lane < 16) {
+        const int x = g0 * 16 + lane;
+        if (head && x >= x0 && x < x1) out[base + (int64_t)x] = tile_in[x];
+    } else {
+        const int x = (g1 - 1) * 16 + (lane - 16);
+        if (tail && x >= x0 && x < x1) out[base + (int64_t)x] = tile_in[x];
+    }
+}
+
+// Second walk (whole warp): the chunk's output image is built in place in the staging buffer -- every byte that is
+// not an emulation-prevention byte moves left by the number of those removed from its NAL so far -- and stored with
+// aligned 16-byte stores.  Bytes the reference drops around a start code (its last two bytes, the NAL header) are
+// carried along: they land between two RBSPs of the position-preserving layout, where the buffer is unspecified.
+//   image offset x <-> out[pos - (carry & ~15) + x] for the NAL open at the chunk's first byte (its bytes start at
+//   x = -(carry & 15), inside the low halo), out[pos + x] for everything behind the chunk's first start code.
+// Lanes exchange the 0..3 bytes that straddle a 32-bit word so that the image is written with word stores.
+__device__ __forceinline__ void chunk_store(const ScanArgs &a, uint8_t *buf, uint64_t pos, const ChunkMasks &cm,
+                                            uint32_t carry, int lane) {
+    uint8_t *tile_in = buf + kHalo;
+    uint32_t *tile_w = reinterpret_cast<uint32_t *>(tile_in);
+    const uint32_t total = cm.total;
+    const uint32_t n_sc = (total >> 16) & 0x1FFFu;
+    const uint32_t cb = carry & 15u;
+    const uint64_t base_a = pos - (uint64_t)(carry & ~15u);
+    const int64_t limit = (int64_t)a.n - (int64_t)pos;  // image offsets (second mapping) stay below this
+    if ((total & 0x7FFFu) == 0 && n_sc == 0 && cb == 0) {  // nothing removed, nothing to restart: an aligned copy
+        store_image(a.out, base_a, tile_in, 0, (int)(limit < kChunk ? limit : kChunk), lane);
+        return;
+    }
+    // start codes: records first (they read the staged bytes)
+    uint32_t any_sc = 0;
+#pragma unroll
+    for (int r = 0; r < kRows; r++) any_sc |= cm.es[r] >> 16;
+    int first_end = 0;  // (n_sc != 0) image offsets of the first start code: x of its 01 byte + 1 in the second mapping,
+    int first_a_end = 0;  // and the end of the first NAL's bytes in the first mapping
+    if (n_sc) {
+        unsigned long long slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(&a.hdr->total_sc, (unsigned long long)n_sc);
+        slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+        int fe = 0x7FFFFFFF, fa = 0;
+#pragma unroll
+        for (int r = 0; r < kRows; r++) {
+            const uint32_t sc = cm.es[r] >> 16;
+            if (!sc) continue;
+            const int gi = r * 32 + lane;
+            emit_dirty_records(a, tile_in, pos, gi, cm.es[r] & 0xFFFFu, sc, cm.pre[r], slot0);
+            if (((cm.pre[r] >> 16) & 0x1FFFu) == 0 && fe == 0x7FFFFFFF) {  // the chunk's first start code is here
+                const int j = __ffs((int)sc) - 1;
+                fe = gi * 16 + j + 1;
+                // its NAL's bytes end two bytes earlier; they have moved by cb + the EPBs in front of them
+                fa = fe - 2 - (int)cb - (int)((cm.pre[r] & 0x7FFFu) + bits_popc(cm.es[r] & ((1u << j) - 1u)));
+            }
+        }
+        const uint32_t who = __ballot_sync(0xFFFFFFFFu, fe != 0x7FFFFFFF);
+        const int src = __ffs((int)who) - 1;  // (row-major order: the lowest row wins inside a lane, but another lane may
+        // hold an earlier row) -> take the minimum
+        int fe_min = fe;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int o = __shfl_xor_sync(0xFFFFFFFFu, fe_min, d);
+            fe_min = o < fe_min ? o : fe_min;
+        }
+        (void)src;
+        const uint32_t owner = __ballot_sync(0xFFFFFFFFu, fe == fe_min);
+        first_end = fe_min;
+        first_a_end = __shfl_sync(0xFFFFFFFFu, fa, __ffs((int)owner) - 1);
+    }
+    // every lane's granules into registers before anything is rewritten
+    uint32_t v[kRows][4];
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+        const uint4 t = *reinterpret_cast<const uint4 *>(tile_in + (r * 32 + lane) * 16);
+        v[r][0] = t.x;
+        v[r][1] = t.y;
+        v[r][2] = t.z;
+        v[r][3] = t.w;
+    }
+    __syncwarp();
+    uint32_t spill_prev_row = 0;  // lane 31's spill of the previous row
+    bool reg_prev_row = false;    // ... and whether it feeds this row's lane 0
+    uint32_t late_word[kRows];    // bytes this lane has to write itself once the words are in place
+    int late_x[kRows], late_n[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+        const int gi = r * 32 + lane;
+        uint32_t ee = cm.es[r] & 0xFFFFu;
+        const uint32_t sc = cm.es[r] >> 16;
+        const bool regular = sc == 0;
+        const uint32_t pre = cm.pre[r];
+        const int shift = (int)(pre & 0x7FFFu) + ((pre >> 31) ? 0 : (int)cb);
+        const int q = gi * 16 - shift;  // image offset of the granule's first byte
+        const int n = 16 - (int)bits_popc(ee);
+        // drop the emulation-prevention bytes (highest first: the lower positions stay put)
+        uint32_t w0 = v[r][0], w1 = v[r][1], w2 = v[r][2], w3 = v[r][3];
+        if (regular) {
+            while (ee) {
+                const int j = bits_msb(ee);
+                ee &= ~(1u << j);
+                const uint32_t s0 = __funnelshift_r(w0, w1, 8), s1 = __funnelshift_r(w1, w2, 8),
+                               s2 = __funnelshift_r(w2, w3, 8), s3 = w3 >> 8;
+                const uint32_t m = (1u << ((j & 3) * 8)) - 1u;  // bytes of word j>>2 that stay
+                const int wj = j >> 2;
+                w0 = wj > 0 ? w0 : (w0 & m) | (s0 & ~m);
+                w1 = wj > 1 ? w1 : (wj == 1 ? (w1 & m) | (s1 & ~m) : s1);
+                w2 = wj > 2 ? w2 : (wj == 2 ? (w2 & m) | (s2 & ~m) : s2);
+                w3 = wj == 3 ? (w3 & m) | (s3 & ~m) : s3;
+            }
+        }
+        // shifted by the byte offset inside the first word: x0 .. x4 are the image words q>>2 ..
+        const uint32_t a8 = (uint32_t)(q & 3) * 8u;
+        const uint32_t x0 = w0 << a8, x1 = __funnelshift_l(w0, w1, a8), x2 = __funnelshift_l(w1, w2, a8),
+                       x3 = __funnelshift_l(w2, w3, a8), x4 = __funnelshift_l(w3, 0u, a8);
+        const int wq = q >> 2;                       // first word (arithmetic shift)
+        const int cnt = ((q + n) >> 2) - wq;         // words whose last byte is this lane's: 2 .. 4
+        const int rem = (q + n) & 3;                 // bytes of the word behind them: the next lane completes it
+        const uint32_t spill = cnt == 2 ? x2 : (cnt == 3 ? x3 : x4);
+        // the lane in front (the previous row's last lane for lane 0) hands over its spill if it is a regular granule
+        uint32_t sp = __shfl_up_sync(0xFFFFFFFFu, spill, 1);
+        uint32_t rg = __shfl_up_sync(0xFFFFFFFFu, (uint32_t)regular, 1);
+        if (lane == 0) {
+            sp = spill_prev_row;
+            rg = reg_prev_row ? 1u : 0u;
+        }
+        spill_prev_row = __shfl_sync(0xFFFFFFFFu, spill, 31);
+        reg_prev_row = __shfl_sync(0xFFFFFFFFu, (uint32_t)regular, 31) != 0;
+        uint32_t rn = __shfl_down_sync(0xFFFFFFFFu, (uint32_t)regular, 1);  // does the next lane take this lane's spill?
+        if (lane == 31) rn = r + 1 < kRows ? 2u : 0u;                       // (2: decided below, from the next row)
+        if (regular) {
+            tile_w[wq] = x0 | (rg ? sp : 0u);
+            tile_w[wq + 1] = x1;
+            if (cnt > 2) tile_w[wq + 2] = x2;
+            if (cnt > 3) tile_w[wq + 3] = x3;
+        }
+        late_word[r] = spill;
+        late_x[r] = (wq + cnt) * 4;
+        late_n[r] = regular ? (rn == 1u ? 0 : (rn == 2u ? -rem : rem)) : -100;  // -100: a boundary granule; < 0: see below
+    }
+    // lane 31's spill is taken by the next row's lane 0 if that one is regular
+#pragma unroll
+    for (int r = 0; r + 1 < kRows; r++) {
+        const uint32_t next_reg = __shfl_sync(0xFFFFFFFFu, (uint32_t)((cm.es[r + 1] >> 16) == 0), 0);
+        if (lane == 31 && late_n[r] > -100 && late_n[r] <= 0) late_n[r] = next_reg ? 0 : -late_n[r];
+    }
+    __syncwarp();
+    // single bytes: spills nobody took, and the granules with start codes
+#pragma unroll
+    for (int r = 0; r < kRows; r++) {
+        if (late_n[r] == -100) {
+            const uint32_t pre = cm.pre[r];
+            const uint32_t c = (pre & 0x7FFFu) + ((pre >> 31) ? 0u : cb);
+            image_boundary_granule(tile_in, r * 32 + lane, make_uint4(v[r][0], v[r][1], v[r][2], v[r][3]), cm.es[r] & 0xFFFFu,
+                                   cm.es[r] >> 16, c);
+        } else {
+            for (int k = 0; k < late_n[r]; k++) tile_in[late_x[r] + k] = (uint8_t)(late_word[r] >> (8 * k));
+        }
+    }
+    __syncwarp();
+    // the image to the output buffer
+    const int removed_end = (int)(total & 0x7FFFu);  // EPBs of the NAL open at the chunk's end, since its start / the chunk's
+    if (n_sc == 0) {
+        int x1 = kChunk - (int)cb - removed_end;
+        const int64_t lim = limit - (int64_t)cb;  // (first mapping: out[base_a + x] with base_a + x < n - carry)
+        if ((int64_t)x1 > lim) x1 = (int)lim;
+        store_image(a.out, base_a, tile_in, -(int)cb, x1, lane);
+    } else {
+        int xb1 = kChunk - removed_end;
+        if ((int64_t)xb1 > limit) xb1 = (int)limit;
+        if (base_a == pos) {  // one mapping: one run, the gap at the start code included
+            store_image(a.out, pos, tile_in, -(int)cb, xb1, lane);
+        } else {
+            store_image(a.out, base_a, tile_in, -(int)cb, first_a_end, lane);
+            store_image(a.out, pos, tile_in, first_end, xb1, lane);
+        }
+    }
 }
 
 // The dirty chunks, in ascending order over the warps of one resident wave: warp g looks at chunks g, g + W, g + 2W, ...
-// (W = warps of the grid; 32 flags per load, one per lane) and walks those the copy kernel flagged.  The TMA stages a
-// chunk while the one before it is walked.  Ascending order is what the look-back of general_chunk relies on: every
-// chunk a warp can wait for belongs to a warp that is running and not behind it.
+// (W = warps of the grid; 32 flags per load, one per lane) and walks those the copy kernel flagged.  Per chunk: the
+// TMA stages it; first walk (chunk_masks), after which its counts are published; look-back for the carry; second walk
+// (chunk_store).  The first walk of the warp's NEXT chunk runs before the look-back of the current one, so the counts a
+// neighbour waits for are out a whole chunk early.  Ascending order is what the look-back relies on: every chunk a warp
+// can wait for belongs to a warp that is running and not behind it.
 __global__ void __launch_bounds__(kWarpsB * 32) annexb_dirty_kernel(ScanArgs a) {
     __shared__ WarpStage stage[kWarpsB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpStage &st = stage[warp];
     if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&st.mbar[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&st.mbar[1])));
+#pragma unroll
+        for (int b = 0; b < kStageBufs; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&st.mbar[b])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -551,25 +643,53 @@ __global__ void __launch_bounds__(kWarpsB * 32) annexb_dirty_kernel(ScanArgs a) 
         mask &= mask - 1;
         return (int64_t)(g + ((batch - 1) * 32 + (uint64_t)l) * W);
     };
-    int64_t chunk = next_dirty();
-    if (chunk < 0) return;
-    if (lane == 0) stage_chunk((uint32_t)chunk, 0);
+    // c_cur: counted and published, waits for its second walk (buffer b_cur); c_nxt: staged (buffer b_cur + 1);
+    // c_far: staged (buffer b_cur + 2)
+    int64_t c_cur = -1, c_nxt = next_dirty(), c_far = -1;
+    if (c_nxt < 0) return;
+    int b_cur = kStageBufs - 1;  // so that c_nxt sits in buffer 0
+    if (lane == 0) stage_chunk((uint32_t)c_nxt, 0);
+    c_far = next_dirty();
+    if (lane == 0 && c_far >= 0) stage_chunk((uint32_t)c_far, 1);
     uint32_t parity = 0;  // bit b: phase parity of buffer b's barrier
-    for (int b = 0; chunk >= 0; b ^= 1) {
-        const int64_t chunk_next = next_dirty();
-        if (lane == 0 && chunk_next >= 0) stage_chunk((uint32_t)chunk_next, b ^ 1);
-        mbar_wait(smem_u32(&st.mbar[b]), (parity >> b) & 1u);
-        parity ^= 1u << b;
-        const uint64_t pos = (uint64_t)chunk * kChunk;
-        const ChunkResult res = general_chunk(a, st.scbits, st.buf[b], pos, (uint32_t)chunk, lane);
-        if (res.clean) {  // a false alarm (00 00 03 whose zeros are header bytes, ...): the verbatim copy after all
-#pragma unroll
-            for (int r = 0; r < kRows; r++)
-                *reinterpret_cast<uint4 *>(a.out + pos + (uint32_t)(r * 32 + lane) * 16u) =
-                    *reinterpret_cast<const uint4 *>(st.buf[b] + kHalo + (r * 32 + lane) * 16);
+    ChunkMasks cm_cur, cm_nxt;
+    while (c_cur >= 0 || c_nxt >= 0) {
+        const int b_nxt = b_cur + 1 == kStageBufs ? 0 : b_cur + 1;
+        if (c_nxt >= 0) {
+            mbar_wait(smem_u32(&st.mbar[b_nxt]), (parity >> b_nxt) & 1u);
+            parity ^= 1u << b_nxt;
+            cm_nxt = chunk_masks(a, st.scbits, st.buf[b_nxt], (uint64_t)c_nxt * kChunk, lane);
+            // the chunk's own counts are final: out they go, nobody is kept waiting while this warp waits
+            if (lane == 0)
+                *(volatile uint32_t *)&a.piece[c_nxt] = kPieceReady | kPieceDirty | (cm_nxt.total & 0x1FFF0000u) | (cm_nxt.total & kPieceEpb);
         }
-        __syncwarp();  // every lane is done with this buffer before (next iteration) a bulk load is aimed at it
-        chunk = chunk_next;
+        if (c_cur >= 0) {
+            const uint32_t carry = lookback_carry(a, (uint32_t)c_cur, lane);
+            if (lane == 0) *(volatile uint32_t *)&a.piece_carry[c_cur] = kPieceReady | seg_apply(cm_cur.total, carry);
+            chunk_store(a, st.buf[b_cur], (uint64_t)c_cur * kChunk, cm_cur, carry, lane);
+            // generic-proxy writes to the buffer are ordered before the TMA write that reuses it
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            // this buffer is free: the chunk after c_far goes there (c_far stays in its own)
+            const int64_t c_new = next_dirty();
+            if (c_nxt >= 0 && c_far >= 0) {
+                // (buffers: b_nxt = c_nxt, b_nxt + 1 = c_far, b_cur = free)
+            }
+            if (lane == 0 && c_new >= 0) stage_chunk((uint32_t)c_new, b_cur);
+            // rotate
+            c_cur = c_nxt;
+            cm_cur = cm_nxt;
+            c_nxt = c_far;
+            c_far = c_new;
+            b_cur = b_nxt;
+        } else {  // first round: nothing to store yet
+            c_cur = c_nxt;
+            cm_cur = cm_nxt;
+            c_nxt = c_far;
+            c_far = next_dirty();
+            b_cur = b_nxt;
+            if (lane == 0 && c_far >= 0) stage_chunk((uint32_t)c_far, 2);
+        }
     }
 }
 
