@@ -57,7 +57,8 @@ constexpr uint32_t kPieceNsc = 0x1FFFu;
 constexpr uint32_t kPieceReady = 0x80000000u;      // bit 31      (dirty chunks) the fields above are final
 
 struct ScanScratchHeader {   // device scratch; zeroed (together with the two per-chunk arrays behind it) before every pass
-    unsigned int reserved0[2];
+    unsigned int n_shift;          // entries of shift_list
+    unsigned int reserved0;
     unsigned long long first_inv;  // max over NAL starts of ~start (0: no start code): first_start = ~first_inv
     unsigned long long total_sc;   // start codes found = slots handed out of the NAL record buffer
     unsigned long long total_kept;
@@ -77,8 +78,9 @@ struct ScanArgs {
                                // since that NAL's start (the look-back's short cut)
     uint32_t *piece_ord;       // per chunk: ordinal of its first start code (exclusive scan of the counts)
     uint32_t *piece_S;         // per chunk: exclusive scan of the EPB fields
-    uint32_t *piece_M;         // per chunk: 1 + the last earlier chunk that holds a start code (0: none)
-    uint4 *tile_sum;           // per kOrderTile chunks: (start codes, EPB fields, last chunk with a start code + 1)
+    uint2 *shift_list;         // (chunk, G): chunks the copy kernel stored verbatim although the NAL open at their first
+                               // byte had lost G emulation-prevention bytes in earlier chunks (order_apply_kernel)
+    uint4 *tile_sum;           // per kOrderTile chunks: (start codes, EPB fields, segmented EPB count: flag, count)
     // One 16-byte record per start code: .x/.y = offset of the byte after it (the next NAL's first byte), .z = that
     // NAL's first 4 bytes, .w = EPBs removed (within the start code's chunk) from the NAL that ENDS at this start code
     // | rank of the start code inside its chunk << 16.
@@ -249,8 +251,8 @@ __device__ __noinline__ uint32_t lookback_carry(const ScanArgs &a, uint32_t chun
                 term = 1;
                 pending = 0;
             } else {
-                w = piece[idx];
-                c = (w & kPieceDirty) ? pc[idx] : 0u;
+                w = piece[idx];  // (both loads in flight together)
+                c = pc[idx];
                 pending = (w & kPieceDirty) && !(w & kPieceReady);
                 term = !pending && ((((w >> kPieceNscShift) & kPieceNsc) != 0) || (c & kPieceReady));
             }
@@ -262,7 +264,7 @@ __device__ __noinline__ uint32_t lookback_carry(const ScanArgs &a, uint32_t chun
                     const int first = __ffs((int)tmask) - 1;
                     if (lane < first) x = w & kPieceEpb;
                     // a chunk with a NAL start: the EPBs after its last start; else its published carry
-                    if (lane == first) x = idx < 0 ? 0u : (((w >> kPieceNscShift) & kPieceNsc) ? (w & kPieceEpb) : (c & kPieceEpb));
+                    if (lane == first) x = idx < 0 ? 0u : (((w >> kPieceNscShift) & kPieceNsc) ? (w & kPieceEpb) : (c & ~kPieceReady));
                 } else {
                     x = w & kPieceEpb;
                 }
@@ -601,7 +603,10 @@ __device__ __forceinline__ void chunk_store(const ScanArgs &a, uint8_t *buf, uin
 // (chunk_store).  The first walk of the warp's NEXT chunk runs before the look-back of the current one, so the counts a
 // neighbour waits for are out a whole chunk early.  Ascending order is what the look-back relies on: every chunk a warp
 // can wait for belongs to a warp that is running and not behind it.
-__global__ void __launch_bounds__(kWarpsB * 32) annexb_dirty_kernel(ScanArgs a) {
+#ifndef H264B_DIRTY_MIN_CTAS
+#define H264B_DIRTY_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(kWarpsB * 32, H264B_DIRTY_MIN_CTAS) annexb_dirty_kernel(ScanArgs a) {
     __shared__ WarpStage stage[kWarpsB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpStage &st = stage[warp];
@@ -626,22 +631,38 @@ __global__ void __launch_bounds__(kWarpsB * 32) annexb_dirty_kernel(ScanArgs a) 
             "l"(a.in + lo), "r"(bytes), "r"(bar)
             : "memory");
     };
-    // the warp's dirty chunks, 32 candidates at a time: lane l of batch t holds chunk g + (32 t + l) W
-    uint64_t batch = 0;
-    uint32_t mask = 0;
-    bool more = true;  // batches left
+    // the warp's dirty chunks: lane l of batch t holds chunk g + (32 t + l) W; the flags of kAhead batches are loaded
+    // together (a warp of a sparse stream only ever sees flags, so the loads should not queue up behind each other)
+    constexpr int kAhead = 4;
+    uint64_t batch = 0;      // first batch of the current round
+    uint32_t masks[kAhead];  // dirty lanes of the round's batches (consumed lowest batch, lowest lane first)
+#pragma unroll
+    for (int i = 0; i < kAhead; i++) masks[i] = 0;
+    bool more = true;  // rounds left
+    bool fresh = true;  // no round loaded yet
     const auto next_dirty = [&]() -> int64_t {  // the warp's next dirty chunk, -1: none left (warp-uniform)
-        while (!mask && more) {
-            const uint64_t c = g + (batch * 32 + (uint64_t)lane) * W;
-            const uint32_t w = c < a.n_chunks ? a.piece[c] : 0u;
-            mask = __ballot_sync(0xFFFFFFFFu, (w & kPieceDirty) != 0);
-            more = g + (batch + 1) * 32 * W < a.n_chunks;
-            batch++;
+        for (;;) {
+#pragma unroll
+            for (int i = 0; i < kAhead; i++) {
+                if (masks[i]) {
+                    const int l = __ffs((int)masks[i]) - 1;
+                    masks[i] &= masks[i] - 1;
+                    return (int64_t)(g + ((batch + i) * 32 + (uint64_t)l) * W);
+                }
+            }
+            if (!more) return -1;
+            if (!fresh) batch += kAhead;
+            fresh = false;
+            uint32_t w[kAhead];
+#pragma unroll
+            for (int i = 0; i < kAhead; i++) {
+                const uint64_t c = g + ((batch + i) * 32 + (uint64_t)lane) * W;
+                w[i] = c < a.n_chunks ? a.piece[c] : 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < kAhead; i++) masks[i] = __ballot_sync(0xFFFFFFFFu, (w[i] & kPieceDirty) != 0);
+            more = g + (batch + kAhead) * 32 * W < a.n_chunks;
         }
-        if (!mask) return -1;
-        const int l = __ffs((int)mask) - 1;
-        mask &= mask - 1;
-        return (int64_t)(g + ((batch - 1) * 32 + (uint64_t)l) * W);
     };
     // c_cur: counted and published, waits for its second walk (buffer b_cur); c_nxt: staged (buffer b_cur + 1);
     // c_far: staged (buffer b_cur + 2)
@@ -740,96 +761,131 @@ __device__ __forceinline__ void decode_nal_header(uint32_t hdr4, h264b_nal &o, h
 }
 
 // Post-pass 1: exclusive scans over the chunks of (a) the start-code counts -> ordinal of every chunk's first start
-// code, (b) the EPB fields -> S[] and (c) "1 + index of the last chunk with a start code" (a running maximum) -> M[];
-// in two phases over tiles of kOrderTile chunks: tile totals, then every CTA combines the totals of the tiles before its
-// own (a few hundred values for a 4 GB stream) and scans its tile.
-struct Ord3 {
-    uint32_t nsc, epb, last;
+// code, (b) the EPB fields -> S[] and (c) the SEGMENTED EPB count (it restarts in every chunk with a NAL start) -> G, the
+// bytes the NAL open at a chunk's first byte has lost so far; a chunk the copy kernel stored verbatim with G > 0 goes
+// on the list of post-pass 4.  Two phases over tiles of kOrderTile chunks: tile totals, then every CTA combines the
+// totals of the tiles before its own (a few hundred values for a 4 GB stream) and scans its tile.  Every thread owns
+// kOrderTile / 256 consecutive chunks, so that (c), which does not commute, can be folded in order.
+struct SegCount {
+    uint32_t f, c;  // a NAL start inside the span; EPBs since the last one (since the start of the span without one)
 };
-__device__ __forceinline__ Ord3 ord3_of(uint32_t p, uint32_t i) {
-    const uint32_t nsc = (p >> kPieceNscShift) & kPieceNsc;
-    return Ord3{nsc, p & kPieceEpb, nsc ? i + 1u : 0u};
+__device__ __forceinline__ SegCount segc_combine(SegCount a, SegCount b) {  // a: earlier span, b: later span
+    return SegCount{a.f | b.f, b.f ? b.c : a.c + b.c};
 }
-__device__ __forceinline__ Ord3 ord3_add(Ord3 a, Ord3 b) { return Ord3{a.nsc + b.nsc, a.epb + b.epb, a.last > b.last ? a.last : b.last}; }
+struct Ord3 {
+    uint32_t nsc, epb;
+    SegCount seg;
+};
+__device__ __forceinline__ Ord3 ord3_of(uint32_t p) {
+    const uint32_t nsc = (p >> kPieceNscShift) & kPieceNsc, epb = p & kPieceEpb;
+    return Ord3{nsc, epb, SegCount{nsc ? 1u : 0u, epb}};
+}
+__device__ __forceinline__ Ord3 ord3_combine(Ord3 a, Ord3 b) {
+    return Ord3{a.nsc + b.nsc, a.epb + b.epb, segc_combine(a.seg, b.seg)};
+}
+__device__ __forceinline__ Ord3 ord3_shfl_up(Ord3 x, int d) {
+    Ord3 y;
+    y.nsc = __shfl_up_sync(0xFFFFFFFFu, x.nsc, d);
+    y.epb = __shfl_up_sync(0xFFFFFFFFu, x.epb, d);
+    y.seg.f = __shfl_up_sync(0xFFFFFFFFu, x.seg.f, d);
+    y.seg.c = __shfl_up_sync(0xFFFFFFFFu, x.seg.c, d);
+    return y;
+}
+constexpr Ord3 kOrd3Zero = {0u, 0u, {0u, 0u}};
 
-__device__ __forceinline__ Ord3 block_sum3_256(Ord3 x, Ord3 *warp_sum, int tid) {
+// In-order scan over the 256 threads of a CTA (thread t's value covers the span right after thread t-1's):
+// returns the exclusive prefix of this thread; *total receives the CTA's total.
+__device__ __forceinline__ Ord3 block_scan3_256(Ord3 own, Ord3 *warp_sum, int tid, Ord3 *total) {
+    const int lane = tid & 31, warp = tid >> 5;
+    Ord3 x = own;  // inclusive over the warp
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        Ord3 y;
-        y.nsc = __shfl_xor_sync(0xFFFFFFFFu, x.nsc, d);
-        y.epb = __shfl_xor_sync(0xFFFFFFFFu, x.epb, d);
-        y.last = __shfl_xor_sync(0xFFFFFFFFu, x.last, d);
-        x = ord3_add(x, y);
+    for (int d = 1; d < 32; d <<= 1) {
+        const Ord3 y = ord3_shfl_up(x, d);
+        if (lane >= d) x = ord3_combine(y, x);
     }
-    if ((tid & 31) == 0) warp_sum[tid >> 5] = x;
+    Ord3 ex = ord3_shfl_up(x, 1);
+    if (lane == 0) ex = kOrd3Zero;
+    if (lane == 31) warp_sum[warp] = x;
     __syncthreads();
-    Ord3 t = {0, 0, 0};
+    Ord3 before = kOrd3Zero, all = kOrd3Zero;
 #pragma unroll
-    for (int w = 0; w < 8; w++) t = ord3_add(t, warp_sum[w]);
+    for (int w = 0; w < 8; w++) {
+        if (w < warp) before = ord3_combine(before, warp_sum[w]);
+        all = ord3_combine(all, warp_sum[w]);
+    }
     __syncthreads();
-    return t;
+    *total = all;
+    return ord3_combine(before, ex);
 }
 
 __global__ void __launch_bounds__(256) order_reduce_kernel(const uint32_t *piece, uint4 *tile_sum, uint32_t n_chunks) {
     __shared__ Ord3 warp_sum[8];
     const int tid = threadIdx.x;
-    const uint32_t base = blockIdx.x * kOrderTile;
-    Ord3 x = {0, 0, 0};
+    constexpr int kPer = kOrderTile / 256;
+    const uint32_t first = blockIdx.x * kOrderTile + (uint32_t)tid * kPer;
+    Ord3 own = kOrd3Zero;
 #pragma unroll
-    for (int k = 0; k < kOrderTile / 256; k++) {
-        const uint32_t i = base + (uint32_t)(k * 256 + tid);
-        if (i < n_chunks) x = ord3_add(x, ord3_of(piece[i], i));
-    }
-    x = block_sum3_256(x, warp_sum, tid);
-    if (tid == 0) tile_sum[blockIdx.x] = make_uint4(x.nsc, x.epb, x.last, 0u);
+    for (int k = 0; k < kPer; k++)
+        if (first + k < n_chunks) own = ord3_combine(own, ord3_of(piece[first + k]));
+    Ord3 total;
+    (void)block_scan3_256(own, warp_sum, tid, &total);
+    if (tid == 0) tile_sum[blockIdx.x] = make_uint4(total.nsc, total.epb, total.seg.f, total.seg.c);
 }
 
-__global__ void __launch_bounds__(256) order_apply_kernel(const uint32_t *piece, const uint4 *tile_sum,
-                                                           uint32_t *piece_ord, uint32_t *piece_S, uint32_t *piece_M,
-                                                           uint32_t n_chunks) {
+__global__ void __launch_bounds__(256) order_apply_kernel(ScanArgs a) {
     __shared__ Ord3 warp_sum[8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    Ord3 before = {0, 0, 0};  // totals of the tiles before this one
-    for (uint32_t t = (uint32_t)tid; t < blockIdx.x; t += 256) {
-        const uint4 s = tile_sum[t];
-        before = ord3_add(before, Ord3{s.x, s.y, s.z});
+    const int tid = threadIdx.x, lane = tid & 31;
+    // the tiles before this one, in order: thread t folds tiles [t m, (t + 1) m)
+    const uint32_t nb = blockIdx.x, m = (nb + 255u) / 256u;
+    Ord3 mine = kOrd3Zero;
+    for (uint32_t t = (uint32_t)tid * m; t < (uint32_t)(tid + 1) * m && t < nb; t++) {
+        const uint4 s = a.tile_sum[t];
+        mine = ord3_combine(mine, Ord3{s.x, s.y, SegCount{s.z, s.w}});
     }
-    before = block_sum3_256(before, warp_sum, tid);
-    constexpr int kPer = kOrderTile / 256;  // contiguous chunks per thread
+    Ord3 before;
+    (void)block_scan3_256(mine, warp_sum, tid, &before);
+    constexpr int kPer = kOrderTile / 256;  // consecutive chunks per thread
     const uint32_t first = blockIdx.x * kOrderTile + (uint32_t)tid * kPer;
-    Ord3 c[kPer];
-    Ord3 own = {0, 0, 0};
+    uint32_t p[kPer];
+    Ord3 own = kOrd3Zero;
 #pragma unroll
     for (int k = 0; k < kPer; k++) {
-        c[k] = first + k < n_chunks ? ord3_of(piece[first + k], first + (uint32_t)k) : Ord3{0, 0, 0};
-        own = ord3_add(own, c[k]);
+        p[k] = first + k < a.n_chunks ? a.piece[first + k] : 0u;
+        own = ord3_combine(own, ord3_of(p[k]));
     }
-    Ord3 x = own;  // inclusive over the warp's threads
-    Ord3 ex = {0, 0, 0};  // exclusive
+    Ord3 total;
+    Ord3 run = ord3_combine(before, block_scan3_256(own, warp_sum, tid, &total));
+    uint32_t G[kPer];
+    uint32_t n_mine = 0;  // chunks of this thread for the list
+#pragma unroll
+    for (int k = 0; k < kPer; k++) {
+        G[k] = 0;
+        if (first + k < a.n_chunks) {
+            a.piece_ord[first + k] = run.nsc;
+            a.piece_S[first + k] = run.epb;
+            // stored verbatim, some NAL is open at its first byte, and that NAL has lost bytes already
+            if (!(p[k] & kPieceDirty) && run.nsc && run.seg.c) {
+                G[k] = run.seg.c;
+                n_mine++;
+            }
+        }
+        run = ord3_combine(run, ord3_of(p[k]));
+    }
+    // one slot reservation per warp
+    uint32_t incl = n_mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        Ord3 y;
-        y.nsc = __shfl_up_sync(0xFFFFFFFFu, x.nsc, d);
-        y.epb = __shfl_up_sync(0xFFFFFFFFu, x.epb, d);
-        y.last = __shfl_up_sync(0xFFFFFFFFu, x.last, d);
-        if (lane >= d) x = ord3_add(y, x);
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += y;
     }
-    ex.nsc = __shfl_up_sync(0xFFFFFFFFu, x.nsc, 1);
-    ex.epb = __shfl_up_sync(0xFFFFFFFFu, x.epb, 1);
-    ex.last = __shfl_up_sync(0xFFFFFFFFu, x.last, 1);
-    if (lane == 0) ex = Ord3{0, 0, 0};
-    if (lane == 31) warp_sum[warp] = x;
-    __syncthreads();
-    Ord3 run = ord3_add(before, ex);
-    for (int w = 0; w < warp; w++) run = ord3_add(run, warp_sum[w]);
+    const uint32_t warp_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (warp_total) {
+        uint32_t slot = 0;
+        if (lane == 31) slot = atomicAdd(&a.hdr->n_shift, warp_total);
+        slot = __shfl_sync(0xFFFFFFFFu, slot, 31) + incl - n_mine;
 #pragma unroll
-    for (int k = 0; k < kPer; k++) {
-        if (first + k < n_chunks) {
-            piece_ord[first + k] = run.nsc;
-            piece_S[first + k] = run.epb;
-            piece_M[first + k] = run.last;
-        }
-        run = ord3_add(run, c[k]);
+        for (int k = 0; k < kPer; k++)
+            if (G[k]) a.shift_list[slot++] = make_uint2(first + (uint32_t)k, G[k]);
     }
 }
 
@@ -900,20 +956,35 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(ScanArgs a, h264b_na
 // flagged ones, one destination-aligned 16-byte granule per lane and step, assembled from aligned source words.
 __device__ __forceinline__ void shifted_copy_warp(const uint8_t *in, uint8_t *out, uint64_t ps, uint64_t pe, uint64_t G,
                                                   int lane) {
-    const uint64_t d0 = ps - G, d1 = pe - G;  // destination range
-    for (uint64_t D = (d0 & ~15ull) + (uint64_t)lane * 16u; D < d1; D += 512u) {
-        const uint64_t src = D + G;
-        const uint32_t *wp = reinterpret_cast<const uint32_t *>(in + (src & ~3ull));
-        const uint32_t sh = (uint32_t)(src & 3u) * 8u;
-        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = sh ? wp[4] : 0u;
-        const uint32_t y[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
-                               __funnelshift_r(w3, w4, sh)};
-        if (D >= d0 && D + 16 <= d1) {
-            *reinterpret_cast<uint4 *>(out + D) = make_uint4(y[0], y[1], y[2], y[3]);
-        } else {
+    const uint64_t d0 = ps - G, d1 = pe - G;  // destination range: at most kChunk bytes, kChunk / 512 + 1 rounds of the warp
+    constexpr int kSteps = kChunk / 512 + 1;
+    const uint64_t Dl = (d0 & ~15ull) + (uint64_t)lane * 16u;
+    uint32_t y[kSteps][4];
 #pragma unroll
-            for (int j = 0; j < 16; j++)
-                if (D + j >= d0 && D + j < d1) out[D + j] = (uint8_t)granule_byte(y, j);
+    for (int k = 0; k < kSteps; k++) {  // all loads first
+        const uint64_t D = Dl + (uint64_t)k * 512u;
+        if (D < d1) {
+            const uint64_t src = D + G;
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(in + (src & ~3ull));
+            const uint32_t sh = (uint32_t)(src & 3u) * 8u;
+            const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = sh ? wp[4] : 0u;
+            y[k][0] = __funnelshift_r(w0, w1, sh);
+            y[k][1] = __funnelshift_r(w1, w2, sh);
+            y[k][2] = __funnelshift_r(w2, w3, sh);
+            y[k][3] = __funnelshift_r(w3, w4, sh);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kSteps; k++) {
+        const uint64_t D = Dl + (uint64_t)k * 512u;
+        if (D < d1) {
+            if (D >= d0 && D + 16 <= d1) {
+                *reinterpret_cast<uint4 *>(out + D) = make_uint4(y[k][0], y[k][1], y[k][2], y[k][3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                    if (D + j >= d0 && D + j < d1) out[D + j] = (uint8_t)granule_byte(y[k], j);
+            }
         }
     }
 }
@@ -924,45 +995,22 @@ __global__ void __launch_bounds__(256) chunk_shift_kernel(ScanArgs a, h264b_scan
         summary->rbsp_bytes = a.hdr->total_kept;  // RBSP bytes of all emitted NAL units
     }
     const int lane = threadIdx.x & 31;
-    const uint64_t warps = (uint64_t)gridDim.x * 8u, warp_id = (uint64_t)blockIdx.x * 8u + (threadIdx.x >> 5);
-    for (uint64_t t0 = warp_id * 32u; t0 < a.n_chunks; t0 += warps * 32u) {
-        const uint64_t t = t0 + (uint64_t)lane;
-        uint64_t ps = 0, pe = 0;
-        uint32_t G = 0;
-        if (t < a.n_chunks && t > 0) {
-            const uint32_t p = a.piece[t], M = a.piece_M[t];
-            if (!(p & kPieceDirty) && M) {  // stored verbatim, and some NAL is open at its first byte
-                const uint32_t Tq = M - 1u;  // the chunk where that NAL starts (after its last start code)
-                G = a.piece_S[t] - a.piece_S[Tq];
-                if (G) {
-                    const uint32_t pq = a.piece[Tq];
-                    const uint64_t k = (uint64_t)a.piece_ord[Tq] + ((pq >> kPieceNscShift) & kPieceNsc) - 1u;  // the NAL's ordinal
-                    const uint64_t lo = t * (uint64_t)kChunk;
-                    ps = lo;
-                    pe = lo + kChunk;
-                    if (k + 1 < a.nal_cap) {  // (an index too small for the stream is reported as such: nothing to do)
-                        const uint4 r0 = a.nal_rec[k];
-                        const uint64_t body = rec_start(r0) + nal_header_bytes(r0.z & 0xFFu, (r0.z >> 8) & 0xFFu);
-                        if (body > ps) ps = body;
-                        if ((p >> kPieceNscShift) & kPieceNsc) {  // the NAL ends in this chunk: its last two bytes stay out
-                            const uint64_t b = rec_start(a.nal_rec[k + 1]);
-                            pe = b - 2;
-                        }
-                    } else {
-                        G = 0;
-                    }
-                    if (pe <= ps) G = 0;
-                }
-            }
-        }
-        uint32_t todo = __ballot_sync(0xFFFFFFFFu, G != 0);
-        while (todo) {
-            const int l = __ffs((int)todo) - 1;
-            todo &= todo - 1;
-            const uint64_t ps_l = __shfl_sync(0xFFFFFFFFu, ps, l), pe_l = __shfl_sync(0xFFFFFFFFu, pe, l);
-            const uint32_t G_l = __shfl_sync(0xFFFFFFFFu, G, l);
-            shifted_copy_warp(a.in, a.out, ps_l, pe_l, (uint64_t)G_l, lane);
-        }
+    const uint32_t n = a.hdr->n_shift;
+    const uint32_t warps = gridDim.x * 8u;
+    for (uint32_t i = blockIdx.x * 8u + (threadIdx.x >> 5); i < n; i += warps) {  // one warp per listed chunk
+        const uint2 e = a.shift_list[i];
+        const uint64_t t = e.x, G = e.y;
+        const uint32_t p = a.piece[t];
+        const uint64_t k = (uint64_t)a.piece_ord[t] - 1u;  // the NAL open at the chunk's first byte
+        if (k + 1 >= a.nal_cap) continue;  // (an index too small for the stream is reported as such: nothing to do)
+        const uint64_t lo = t * (uint64_t)kChunk;
+        uint64_t ps = lo, pe = lo + kChunk;
+        const uint4 r0 = a.nal_rec[k];
+        const uint64_t body = rec_start(r0) + nal_header_bytes(r0.z & 0xFFu, (r0.z >> 8) & 0xFFu);
+        if (body > ps) ps = body;
+        if ((p >> kPieceNscShift) & kPieceNsc)  // the NAL ends in this chunk: its last two bytes stay out
+            pe = rec_start(a.nal_rec[k + 1]) - 2;
+        if (pe > ps) shifted_copy_warp(a.in, a.out, ps, pe, G, lane);
     }
 }
 
@@ -1083,7 +1131,7 @@ __global__ void __launch_bounds__(1024) slice_select_kernel(const h264b_nal *nal
 
 // ------------------------------------------------------------------------------------------------ launchers
 struct ScratchOffsets {
-    uint64_t piece, piece_carry, piece_ord, piece_S, piece_M, tile_sum, rec, nal_rec, total;
+    uint64_t piece, piece_carry, piece_ord, piece_S, shift_list, tile_sum, rec, nal_rec, total;
 };
 static ScratchOffsets scratch_layout(uint64_t n, uint32_t nal_cap) {
     const uint64_t n_chunks = (n + kChunk - 1) / kChunk;
@@ -1098,7 +1146,7 @@ static ScratchOffsets scratch_layout(uint64_t n, uint32_t nal_cap) {
     o.piece_carry = take(n_chunks * 4);
     o.piece_ord = take(n_chunks * 4);
     o.piece_S = take(n_chunks * 4);
-    o.piece_M = take(n_chunks * 4);
+    o.shift_list = take(n_chunks * 8);
     o.tile_sum = take((n_chunks + kOrderTile - 1) / kOrderTile * 16);
     o.rec = take((uint64_t)nal_cap * 16);
     o.nal_rec = take((uint64_t)nal_cap * 16);
@@ -1137,7 +1185,7 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     a.piece_carry = (uint32_t *)(s + so.piece_carry);
     a.piece_ord = (uint32_t *)(s + so.piece_ord);
     a.piece_S = (uint32_t *)(s + so.piece_S);
-    a.piece_M = (uint32_t *)(s + so.piece_M);
+    a.shift_list = (uint2 *)(s + so.shift_list);
     a.tile_sum = (uint4 *)(s + so.tile_sum);
     a.rec = (uint4 *)(s + so.rec);
     a.nal_rec = (uint4 *)(s + so.nal_rec);
@@ -1165,8 +1213,7 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
             const unsigned tiles = (unsigned)((n_chunks + kOrderTile - 1) / kOrderTile);
             order_reduce_kernel<<<tiles, 256, 0, ctx->stream>>>(a.piece, a.tile_sum, a.n_chunks);
             H264B_LAUNCH_CHECK(ctx, "order_reduce_kernel");
-            order_apply_kernel<<<tiles, 256, 0, ctx->stream>>>(a.piece, a.tile_sum, a.piece_ord, a.piece_S, a.piece_M,
-                                                               a.n_chunks);
+            order_apply_kernel<<<tiles, 256, 0, ctx->stream>>>(a);
             H264B_LAUNCH_CHECK(ctx, "order_apply_kernel");
             nal_permute_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a);
             H264B_LAUNCH_CHECK(ctx, "nal_permute_kernel");
@@ -1175,7 +1222,7 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
         scan_finalize_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a, d_nals, d_ext, d_summary);
         H264B_LAUNCH_CHECK(ctx, "scan_finalize_kernel");
         {
-            uint64_t grid_s = (n_chunks + 255) / 256;  // 32 chunks per warp and step
+            uint64_t grid_s = (n_chunks + 7) / 8;  // one warp per listed chunk, grid-stride
             if (grid_s > (uint64_t)ctx->sm_count * 8) grid_s = (uint64_t)ctx->sm_count * 8;
             if (grid_s < 1) grid_s = 1;
             chunk_shift_kernel<<<(unsigned)grid_s, 256, 0, ctx->stream>>>(a, d_summary);

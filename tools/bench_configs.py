@@ -128,6 +128,8 @@ for label, fl in (("REF tables", 0), ("SPEC tables", 1)):
           flush=True)
 del d_st
 
+if os.environ.get("BENCH_CONFIGS_SKIP_C4"):
+    sys.exit(0)
 print("== configs[4]: multi-camera batch, rank 0's LPT share of 4096 streams x 16 slices (slice size 1 KB * 2^(10 u^3))")
 rs = np.random.default_rng(4096)
 n_streams, per = 4096, 16

@@ -34,7 +34,7 @@ def line_table(lib, filt):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
     for f in sorted(os.listdir(tmp)):
-        txt = subprocess.run(["nvdisasm", "-g", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+        txt = subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, f)], capture_output=True, text=True).stdout
         m = re.search(r"^\.text\.\S*%s\S*:$" % re.escape(filt), txt, re.M)
         if not m:
             continue
@@ -47,6 +47,10 @@ def line_table(lib, filt):
                 mm = re.match(r'//## File "([^"]+)", line (\d+)(.*)', s)
                 cur = (os.path.basename(mm.group(1)), int(mm.group(2)))
                 stack = mm.group(3)
+                if OUTER:  # attribute to the outermost call site instead of the innermost line
+                    chain = re.findall(r'inlined at "([^"]+)", line (\d+)', stack)
+                    if chain:
+                        cur = (os.path.basename(chain[-1][0]), int(chain[-1][1]))
                 continue
             if s.startswith(".section") or s.startswith("//-----"):
                 break
@@ -55,6 +59,9 @@ def line_table(lib, filt):
                 lines.append((cur, stack, mm.group(2)))
         return lines
     raise SystemExit("kernel not in library")
+
+
+OUTER = bool(int(os.environ.get("NCU_LINES_OUTER", "0")))
 
 
 def main():
