@@ -92,6 +92,12 @@ H264B_HD uint32_t zero_bytes(uint32_t w) { return ~(((w & 0x7F7F7F7Fu) + 0x7F7F7
 // gather bit 7 of each byte into bits 0..3 (byte 0 -> bit 0)
 H264B_HD uint32_t pack_msb4(uint32_t m) { return ((m & 0x80808080u) * 0x00204081u) >> 28; }
 
+// byte b (0..15) of a 16-byte granule held in four words, without dynamic register indexing
+H264B_HD uint32_t granule_byte(const uint32_t y[4], int b) {
+    const uint32_t lo = (b & 4) ? y[1] : y[0], hi = (b & 4) ? y[3] : y[2];
+    return (((b & 8) ? hi : lo) >> ((b & 3) * 8)) & 0xFFu;
+}
+
 // For a 16-byte granule (little-endian words w[0..3], byte j of the granule = byte j&3 of w[j>>2]) and the 4 bytes
 // before it (prev, byte 3 = the byte just before the granule), return per-byte bit masks (bit j = granule byte j):
 //   z  : byte == 0          e : raw emulation-prevention candidate  s[p]==3 && s[p-1]==0 && s[p-2]==0
@@ -111,7 +117,13 @@ H264B_HD GranuleMasks granule_masks(const uint32_t w[4], uint32_t prev) {
     m.z = z;
     m.e = 0;
     m.sc = 0;
-    if ((two & 0xFFFFu) != 0) {  // rare for entropy-coded payloads: only now look for 03 / 01 bytes
+    uint32_t cand = two & 0xFFFFu;  // positions with two zero bytes right before them: rare for entropy-coded payloads
+    if (cand && (cand & (cand - 1u)) == 0u) {  // a single candidate (the usual case): look at that byte alone
+        const int j = bits_msb(cand);
+        const uint32_t b = granule_byte(w, j);
+        if (b == 3u) m.e = cand;
+        if (b == 1u) m.sc = cand & three;
+    } else if (cand) {  // several (runs of zeros): byte-parallel search for 03 / 01
         uint32_t t = pack_msb4(zero_bytes(w[0] ^ 0x03030303u)) | (pack_msb4(zero_bytes(w[1] ^ 0x03030303u)) << 4) |
                      (pack_msb4(zero_bytes(w[2] ^ 0x03030303u)) << 8) |
                      (pack_msb4(zero_bytes(w[3] ^ 0x03030303u)) << 12);
@@ -240,12 +252,6 @@ H264B_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
     return s ? ((lo >> s) | (hi << (32u - s))) : lo;
 }
 #endif
-
-// byte b (0..15) of a 16-byte granule held in four words, without dynamic register indexing
-H264B_HD uint32_t granule_byte(const uint32_t y[4], int b) {
-    const uint32_t lo = (b & 4) ? y[1] : y[0], hi = (b & 4) ? y[3] : y[2];
-    return (((b & 8) ? hi : lo) >> ((b & 3) * 8)) & 0xFFu;
-}
 
 // Store one row of a tile (one lane's part; the kernel calls this for all 32 lanes of the row's warp): `len`
 // (<= 512) contiguous bytes, lane l holding row bytes [16l, 16l+16) in w, to out[o .. o+len).

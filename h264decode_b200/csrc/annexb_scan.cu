@@ -8,26 +8,33 @@
 // a span of the stream that holds neither a start code nor an emulation-prevention byte -- all but a few KiB per MB
 // of entropy-coded data -- is an aligned copy.  The pass is built around that, as two kernels over 2 KiB chunks:
 //
-//   K1a  annexb_copy_kernel   one warp per chunk, no shared memory, ~32 registers, full occupancy: coalesced LDG.128
+//   K1a  annexb_copy_kernel   one warp per chunk, no shared memory, 36 registers, full occupancy: coalesced LDG.128
 //                             (one 16-byte granule per lane and row), word-parallel search for two adjacent zero
 //                             bytes (zero_pair_acc: every 00 00 03 and 00 00 00 01 needs such a pair), and -- for a
-//                             chunk without one -- STG.128 of the same registers: a copy at copy speed.  A chunk
-//                             with a pair (or at an end of the stream) is only flagged.
-//   K1b  annexb_dirty_kernel  the flagged chunks (a few per cent of random data, far fewer really hold anything): the
-//                             chunk + 16-byte halos are staged in shared memory by a TMA 1-D bulk load (cp.async.bulk
-//                             + mbarrier complete_tx); exact masks (granule_masks), start-code bitmap, bit-domain
-//                             fix-up near start codes (keep_mask_near_sc), per-row segmented scan of (EPBs | start
-//                             codes), in-place compaction of rows that only lose EPBs, shuffle-aligned 16-byte row
-//                             stores, byte stores and NAL records (start, EPB count, first 4 bytes, rank in chunk)
-//                             for rows with boundaries.
-// Chunks never talk to each other: no block barrier, no look-back, no ticket.  Inside a chunk a kept byte at stream
-// position p goes to out[p - (EPBs removed from p's NAL earlier in the chunk)]; what a NAL lost in EARLIER chunks is
-// made up for by the post-pass (nal_pieces, annexb_local.cuh): rare, because emulation-prevention bytes are rare.
-// Post-passes (tiny): exclusive scan of the per-chunk start-code counts, permutation of the records into stream
-// order, h264b_nal records (lengths are differences of neighbours), and the slide of NAL parts described above.
+//                             chunk without an emulation-prevention candidate -- STG.128 of the same registers: a copy
+//                             at copy speed (start codes in such a chunk only add records).  A chunk with a candidate
+//                             (or at an end of the stream) is only flagged.
+//   K1b  annexb_dirty_kernel  the flagged chunks (a few per cent of random data, every chunk of an EPB-dense stream):
+//                             the chunk + 16-byte halos are staged in shared memory by a TMA 1-D bulk load
+//                             (cp.async.bulk + mbarrier complete_tx, three buffers per warp).  First walk
+//                             (chunk_masks): exact masks (granule_masks), start-code bitmap, bit-domain fix-up near
+//                             start codes (keep_mask_near_sc), segmented scan of (EPBs | start codes); the chunk's
+//                             counts are published.  Look-back (lookback_carry) over the published counts of the
+//                             chunks before it: how many bytes the NAL open at the chunk's first byte has lost so
+//                             far.  Second walk (chunk_store): the output image of the chunk is built in place
+//                             (emulation-prevention bytes spliced out in registers, 32-bit stores, neighbouring
+//                             lanes hand over the bytes that straddle a word) and stored with aligned 16-byte
+//                             stores at its final position; NAL records for the start codes.
+// A kept byte at stream position p goes to out[p - (EPBs removed from p's NAL before p)].  Dirty chunks are dealt to the
+// warps of one resident wave in ascending order, and a warp takes the counts of its NEXT chunk before it looks back for
+// the current one, so a neighbour rarely waits.  What is left for the post-passes: exclusive scans of the per-chunk
+// counts (NAL ordinals; S[] for the per-NAL totals; the segmented carry that finds the chunks the copy kernel stored
+// verbatim although their NAL had already lost bytes -- those are copied again, shifted, from the input), permutation
+// of the records into stream order, and the h264b_nal records (lengths are differences of neighbours).
 //
 // (Measured alternatives -- 16 KiB CTA tiles with decoupled look-back, warp-private TMA rings with bulk stores,
-// register pipelines over 128 KiB pieces -- are in the git history and profiles/r1_scan_*; DESIGN.md has the numbers.)
+// register pipelines over 128 KiB pieces, chunks compacted on their own plus a per-NAL slide -- are in the git history
+// and profiles/r1_scan_*, profiles/r2_dense_*; DESIGN.md has the numbers.)
 #include <stdlib.h>
 
 #include "annexb_local.cuh"
@@ -631,38 +638,22 @@ __global__ void __launch_bounds__(kWarpsB * 32, H264B_DIRTY_MIN_CTAS) annexb_dir
             "l"(a.in + lo), "r"(bytes), "r"(bar)
             : "memory");
     };
-    // the warp's dirty chunks: lane l of batch t holds chunk g + (32 t + l) W; the flags of kAhead batches are loaded
-    // together (a warp of a sparse stream only ever sees flags, so the loads should not queue up behind each other)
-    constexpr int kAhead = 4;
-    uint64_t batch = 0;      // first batch of the current round
-    uint32_t masks[kAhead];  // dirty lanes of the round's batches (consumed lowest batch, lowest lane first)
-#pragma unroll
-    for (int i = 0; i < kAhead; i++) masks[i] = 0;
-    bool more = true;  // rounds left
-    bool fresh = true;  // no round loaded yet
+    // the warp's dirty chunks, 32 candidates at a time: lane l of batch t holds chunk g + (32 t + l) W
+    uint64_t batch = 0;
+    uint32_t mask = 0;
+    bool more = true;  // batches left
     const auto next_dirty = [&]() -> int64_t {  // the warp's next dirty chunk, -1: none left (warp-uniform)
-        for (;;) {
-#pragma unroll
-            for (int i = 0; i < kAhead; i++) {
-                if (masks[i]) {
-                    const int l = __ffs((int)masks[i]) - 1;
-                    masks[i] &= masks[i] - 1;
-                    return (int64_t)(g + ((batch + i) * 32 + (uint64_t)l) * W);
-                }
-            }
-            if (!more) return -1;
-            if (!fresh) batch += kAhead;
-            fresh = false;
-            uint32_t w[kAhead];
-#pragma unroll
-            for (int i = 0; i < kAhead; i++) {
-                const uint64_t c = g + ((batch + i) * 32 + (uint64_t)lane) * W;
-                w[i] = c < a.n_chunks ? a.piece[c] : 0u;
-            }
-#pragma unroll
-            for (int i = 0; i < kAhead; i++) masks[i] = __ballot_sync(0xFFFFFFFFu, (w[i] & kPieceDirty) != 0);
-            more = g + (batch + kAhead) * 32 * W < a.n_chunks;
+        while (!mask && more) {
+            const uint64_t c = g + (batch * 32 + (uint64_t)lane) * W;
+            const uint32_t w = c < a.n_chunks ? a.piece[c] : 0u;
+            mask = __ballot_sync(0xFFFFFFFFu, (w & kPieceDirty) != 0);
+            more = g + (batch + 1) * 32 * W < a.n_chunks;
+            batch++;
         }
+        if (!mask) return -1;
+        const int l = __ffs((int)mask) - 1;
+        mask &= mask - 1;
+        return (int64_t)(g + ((batch - 1) * 32 + (uint64_t)l) * W);
     };
     // c_cur: counted and published, waits for its second walk (buffer b_cur); c_nxt: staged (buffer b_cur + 1);
     // c_far: staged (buffer b_cur + 2)
