@@ -248,6 +248,8 @@ def load():
         "h264b_scheduler_run": (i32, [vp, P(BatchJob), P(BatchResult)]),
     }
     for name, (res, args) in sig.items():
+        if os.environ.get("H264B_LIB") and not hasattr(L, name):
+            continue  # (an experiment build of an older revision)
         f = getattr(L, name)
         f.restype = res
         f.argtypes = args

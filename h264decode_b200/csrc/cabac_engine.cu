@@ -242,7 +242,11 @@ __device__ __forceinline__ uint4 entry16(uint64_t e) {
     return r;
 }
 
-template <int kLoop>
+// kRounds: a warp may run several bundles in turn (a launch whose context rows leave room for few warps).  The usual
+// launch has one bundle per warp and takes the instantiation without that loop: under it the compiler keeps fewer
+// warp-uniform values on the uniform datapath, which a warp on its own pays with a third more cycles per bin in the
+// older loops (configs[1]: 193 against 138 cycles per bin with kLoop 0, 244 against 177 on the literal engine).
+template <int kLoop, bool kRounds>
 __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(CabacArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *s_tab = reinterpret_cast<uint64_t *>(smem);                  // 128 x 8 B (generic loop)
@@ -279,16 +283,14 @@ __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1) cabac_decode_kernel(C
     uint32_t gw = a.map_mode == 2 ? blockIdx.x * W + (uint32_t)warp : rank * gridDim.x + blockIdx.x;
     // map_mode 3: the warp runs the bundles of its slot one after the other (rounds: as many as the launch needs for all
     // bundles to have a slot: one, unless the context rows leave room for few warps); -1: no bundle
-#ifdef H264B_EXP_NO_ROUNDS
-    {
-    const uint32_t round = 0;
+    const uint32_t n_rounds = kRounds ? a.rounds : 1u;
+    for (uint32_t round = 0; round < n_rounds; round++) {
     if (a.map_mode == 3) gw = (uint32_t)a.slot_bundle[(round * gridDim.x + blockIdx.x) * W + (uint32_t)warp];
-    if (gw >= n_bundles) return;
-#else
-    for (uint32_t round = 0; round < a.rounds; round++) {
-    if (a.map_mode == 3) gw = (uint32_t)a.slot_bundle[(round * gridDim.x + blockIdx.x) * W + (uint32_t)warp];
-    if (__all_sync(0xFFFFFFFFu, gw >= n_bundles)) continue;  // (a vote: gw is the same in every lane)
-#endif
+    if (kRounds) {
+        if (__all_sync(0xFFFFFFFFu, gw >= n_bundles)) continue;  // (a vote: gw is the same in every lane)
+    } else {
+        if (gw >= n_bundles) return;
+    }
     const uint32_t index = gw * a.lanes_per_warp + lane;
     // Lanes without a slice of their own (a partly filled warp) shadow the warp's first lane: they decode the same
     // slice and store nothing, so the loops below never have to predicate on "is there a slice in this lane".
@@ -1062,7 +1064,9 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
         return set_error(ctx, H264B_E_INVALID, "cabac: bins_stride_words too small");
     if ((uintptr_t)j.bytes & 3) return set_error(ctx, H264B_E_INVALID, "cabac: bytes must be 4-byte aligned");
     // measurement knobs (tools/cabac_balance_exp.py); the defaults are the shipped configuration
-    const int k_loop = env_int("H264B_CABAC_LOOP", 2), k_w = env_int("H264B_CABAC_W", 0),
+    // the branch-free loop (2) is the window engine's; jobs in the reference's own bypass form run on the literal engine,
+    // whose block loop is fastest in the instantiation with the 8-byte table (0)
+    const int k_loop = env_int("H264B_CABAC_LOOP", (j.flags & H264B_BYPASS_SPEC_OR) ? 2 : 0), k_w = env_int("H264B_CABAC_W", 0),
               k_map = env_int("H264B_CABAC_MAP", 3);
     const int v = (j.flags & H264B_TABLES_SPEC) ? 1 : 0;
     CabacArgs a;
@@ -1148,27 +1152,30 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
         }
     }
     const size_t smem = tab_bytes + (size_t)W * (n_rows + 2) * 32;
-    if (k_loop == 2) {
-        // (one carveout for every launch of this kernel: launches that differ in their shared-memory split cannot share an SM,
-        //  and h264b_scheduler runs several side by side)
-        static bool carveout_set[64] = {false};
-        if (ctx->device < 64 && !carveout_set[ctx->device]) {
-            // (half of the SM's 228 KB: room for every launch shape at 64 contexts, and an L1 for the op schedule and the
-            //  bitstream words; launches that need more get more)
-            H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    // (one carveout for every launch of these kernels: launches that differ in their shared-memory split cannot share an
+    //  SM, and h264b_scheduler runs several side by side; half of the SM's 228 KB: room for every launch shape at 64
+    //  contexts, and an L1 for the op schedule and the bitstream words; launches that need more get more)
+    const auto launch = [&](auto kernel, int which) -> int {
+        static bool attr_set[6][64] = {{false}};
+        if (ctx->device >= 64 || !attr_set[which][ctx->device]) {
+            H264B_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                                  env_int("H264B_CABAC_CARVEOUT", 50)));
-            H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)kMaxSmemPerCta));
-            carveout_set[ctx->device] = true;
+            H264B_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemPerCta));
+            if (ctx->device < 64) attr_set[which][ctx->device] = true;
         }
-        cabac_decode_kernel<2><<<grid, W * 32, smem, ctx->stream>>>(a);
+        kernel<<<grid, W * 32, smem, ctx->stream>>>(a);
+        return H264B_OK;
+    };
+    int lrc;
+    const bool multi = a.rounds > 1;
+    if (k_loop == 2) {
+        lrc = multi ? launch(cabac_decode_kernel<2, true>, 0) : launch(cabac_decode_kernel<2, false>, 1);
     } else if (k_loop) {
-        H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cabac_decode_kernel<1><<<grid, W * 32, smem, ctx->stream>>>(a);
+        lrc = multi ? launch(cabac_decode_kernel<1, true>, 2) : launch(cabac_decode_kernel<1, false>, 3);
     } else {
-        H264B_CUDA(ctx, cudaFuncSetAttribute(cabac_decode_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cabac_decode_kernel<0><<<grid, W * 32, smem, ctx->stream>>>(a);
+        lrc = multi ? launch(cabac_decode_kernel<0, true>, 4) : launch(cabac_decode_kernel<0, false>, 5);
     }
+    if (lrc) return lrc;
     H264B_LAUNCH_CHECK(ctx, "cabac_decode_kernel");
     return H264B_OK;
 }
