@@ -539,4 +539,44 @@ inline void DecodeBins(const h264b_cabac_job &job, Device &dev = Device::Default
     dev.check(h264b_cabac_decode(dev.ctx(), &job));
 }
 
+// new, batch: mb_type as a syntax element for many slices at once -- the walk of slice.go:639-672 (NewBinarization,
+// CtxIdx per bin, IsBinStringMatch) with every slice on its own, data-dependent sequence of contexts (see
+// h264b_mb_type_job; host pointers)
+inline void DecodeMbTypes(const h264b_mb_type_job &job, Device &dev = Device::Default()) {
+    dev.check(h264b_mb_type_decode(dev.ctx(), &job));
+}
+
+// The reference serves every TCP connection from a goroutine of its own (main.go:16-21 -> ByteStreamReader ->
+// handleConnection, h264/server.go:113-166).  Scheduler is that concurrency for whole streams held in host memory: a
+// batch of independent streams goes over the GPUs of this process (longest processing time first by bytes; per GPU one
+// split + strip pass and the CABAC engine in five launches by slice length, side by side), and comes back as NAL units,
+// bins and final engine states per stream, with the time every slice's result reached host memory.
+class Scheduler {
+   public:
+    // devices: CUDA ordinals; empty = every device of the process
+    explicit Scheduler(std::vector<int32_t> devices = {}) {
+        if (devices.empty()) {
+            int32_t n = 0;
+            h264b_device_count(&n);
+            for (int32_t d = 0; d < n; d++) devices.push_back(d);
+        }
+        const int32_t rc = h264b_scheduler_create(devices.data(), (uint32_t)devices.size(), &s_);
+        if (rc != H264B_OK) throw std::runtime_error("h264b_scheduler_create: status " + std::to_string(rc) + " (no CPU fallback)");
+    }
+    ~Scheduler() { h264b_scheduler_destroy(s_); }
+    Scheduler(const Scheduler &) = delete;
+    Scheduler &operator=(const Scheduler &) = delete;
+    // synchronous; the result's arrays stay valid until the next Run or the scheduler's destruction
+    h264b_batch_result Run(const h264b_batch_job &job) {
+        h264b_batch_result res;
+        const int32_t rc = h264b_scheduler_run(s_, &job, &res);
+        if (rc != H264B_OK)
+            throw std::runtime_error("h264b_scheduler_run: status " + std::to_string(rc) + ": " + h264b_scheduler_last_error(s_));
+        return res;
+    }
+
+   private:
+    h264b_scheduler *s_ = nullptr;
+};
+
 }  // namespace h264

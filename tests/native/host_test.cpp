@@ -205,6 +205,62 @@ int main(int argc, char **argv) {
             printf("core %d %lld %lld\n", std::get<0>(bd), (long long)std::get<1>(bd), (long long)std::get<2>(bd));
             c.StateTransitionProcess(1 - c.ValMPS);
             printf("trans %d %d\n", c.PStateIdx, c.ValMPS);
+        } else if (mode == "sched") {  // a batch of streams through h264::Scheduler; argv[2]: the batch as one file (see test)
+            const auto f = slurp(argv[2]);
+            const uint8_t *p = f.data();
+            auto take = [&](void *dst, size_t n) {
+                memcpy(dst, p, n);
+                p += n;
+            };
+            uint32_t hdr[5];  // n_streams, n_ctx, n_ops_max, flags, workers
+            take(hdr, sizeof(hdr));
+            std::vector<std::vector<uint8_t>> bytes(hdr[0]);
+            std::vector<h264b_batch_stream> streams(hdr[0]);
+            uint32_t total = 0;
+            for (uint32_t i = 0; i < hdr[0]; i++) {
+                uint64_t n;
+                uint32_t ns;
+                take(&n, 8);
+                take(&ns, 4);
+                bytes[i].resize(n);
+                take(bytes[i].data(), n);
+                streams[i].stream = bytes[i].data();
+                streams[i].n = n;
+                streams[i].first_slice = total;
+                streams[i].n_slices = ns;
+                total += ns;
+            }
+            std::vector<uint16_t> ops(hdr[2]);
+            take(ops.data(), ops.size() * 2);
+            std::vector<uint32_t> n_ops(total);
+            take(n_ops.data(), n_ops.size() * 4);
+            std::vector<h264b_slice_qp> qp(total);
+            take(qp.data(), qp.size() * sizeof(h264b_slice_qp));
+            h264b_batch_job job;
+            memset(&job, 0, sizeof(job));
+            job.streams = streams.data();
+            job.n_streams = hdr[0];
+            job.total_slices = total;
+            job.n_ctx = hdr[1];
+            job.n_ops_max = hdr[2];
+            job.ops = ops.data();
+            job.n_ops = n_ops.data();
+            job.qp = qp.data();
+            job.flags = hdr[3];
+            h264::Scheduler sched(std::vector<int32_t>(hdr[4], 0));  // (workers on device 0: the test box has one GPU)
+            const h264b_batch_result r = sched.Run(job);
+            for (uint32_t i = 0; i < hdr[0]; i++)
+                printf("stream %u worker %d nals %llu\n", i, r.stream_device[i],
+                       (unsigned long long)(r.stream_nal_off[i + 1] - r.stream_nal_off[i]));
+            for (uint32_t k = 0; k < total; k++) {
+                uint64_t sum = 0;  // the slice's whole bin words, position-weighted
+                const uint32_t words = r.final[k].n_bins / 32;
+                for (uint32_t w = 0; w < words; w++) sum = sum * 1000003ull + r.bins[r.bins_off[k] + w];
+                printf("slice %u bins %u range %lld offset %lld flags %u sum %llu done %d\n", k, r.final[k].n_bins,
+                       (long long)r.final[k].cod_i_range, (long long)r.final[k].cod_i_offset, r.final[k].flags,
+                       (unsigned long long)sum, r.slice_done_ms[k] > 0 && r.slice_done_ms[k] <= r.makespan_ms);
+            }
+            printf("total bins %llu nals %llu\n", (unsigned long long)r.total_bins, (unsigned long long)r.total_nals);
         } else {
             return 2;
         }

@@ -320,3 +320,50 @@ def test_read_nal_units_by_byte_ranges(exe, tmp_path, n_ranges):
     rc, out = run(exe, "nals_ranges", path, n_ranges)
     assert rc == 0
     assert out == expect_nal_lines(s)
+
+
+@pytest.mark.gpu
+def test_scheduler_wrapper_runs_a_batch_of_streams(exe, tmp_path):
+    """h264::Scheduler (host/h264.hpp) over h264b_scheduler_run: a batch of streams of different sizes over two workers;
+    per stream the oracle's NAL unit count, per slice the bins the test encoder coded and the oracle's final engine state."""
+    import struct
+    from h264decode_b200 import capi
+    rng = np.random.default_rng(11)
+    n_streams = 9
+    mean_bins = (1024 * 2 ** (5 * rng.random(n_streams) ** 3) * 8 / 0.88).astype(np.int64)
+    per = rng.integers(1, 5, n_streams)
+    built = [hz.build_stream_cabac(int(per[i]), int(mean_bins[i]), config=5, n_active=64, n_ctx=64, slices_per_frame=2,
+                                   frames_per_params=2, id_base=100 * i) for i in range(n_streams)]
+    ops = max((b["ops"] for b in built), key=len)
+    flags = capi.BYPASS_SPEC_OR | capi.CABAC_FINAL_TERMINATE
+    blob = [struct.pack("<5I", n_streams, 64, len(ops), flags, 2)]
+    for i, b in enumerate(built):
+        s = np.ascontiguousarray(b["stream"])
+        blob += [struct.pack("<QI", len(s), int(per[i])), s.tobytes()]
+    n_ops = np.concatenate([b["n_ops"] for b in built]).astype(np.uint32)
+    qp = capi.Context.slice_qp(np.concatenate([b["qp"] for b in built]), np.concatenate([b["idc"] for b in built]))
+    blob += [np.ascontiguousarray(ops).astype(np.uint16).tobytes(), n_ops.tobytes(), qp.tobytes()]
+    path = os.path.join(str(tmp_path), "batch.bin")
+    with open(path, "wb") as f:
+        f.write(b"".join(blob))
+    rc, out = run(exe, "sched", path)
+    assert rc == 0, out
+    lines = {(l[0], int(l[1])): l for l in out if l[0] in ("stream", "slice")}
+    row = 0
+    workers = set()
+    for i, b in enumerate(built):
+        onal, _ = orc.read_nal_units_arrays(b["stream"])
+        l = lines[("stream", i)]
+        workers.add(int(l[3]))
+        assert int(l[5]) == len(onal["start"])
+        for s in range(int(per[i])):
+            l = lines[("slice", row)]
+            n = int(b["n_ops"][s]) + 1
+            assert int(l[3]) == n and int(l[9]) == 0 and int(l[13]) == 1
+            acc = 0
+            for w in b["bins"][s, :n // 32]:
+                acc = (acc * 1000003 + int(w)) & 0xFFFFFFFFFFFFFFFF
+            assert int(l[11]) == acc, (i, s)
+            row += 1
+    assert workers == {0, 1}
+    assert out[-1][:3] == ["total", "bins", str(int(n_ops.sum()) + len(n_ops))]
