@@ -356,12 +356,13 @@ H264B_HD void store_granule_bytes(uint8_t *out, uint64_t gpos, const uint32_t w[
 }
 
 // ---- NALs whose body spans several chunks ---------------------------------------------------------------------
-// The main pass treats every chunk ("piece": kChunk bytes of the stream) on its own: inside a chunk a kept byte at
-// stream position p goes to out[p - (EPBs removed from p's NAL earlier IN THIS CHUNK)].  A NAL that continues into
-// further chunks is therefore laid out in parts, one per chunk, each compacted towards its own start; whenever an
-// earlier part lost EPBs the later parts sit too far right by the accumulated count G.  Real streams almost never
-// have that (one EPB per several MB of entropy-coded data), so the hot kernels need no communication between chunks
-// at all and a tiny post-pass slides the few affected parts left (nal_fixup_kernel).
+// Inside a chunk ("piece": kChunk bytes of the stream) a kept byte at stream position p goes to
+// out[p - (EPBs removed from p's NAL earlier in this chunk) - G], G = what the NAL lost in the chunks before.  The
+// device kernels carry G into the chunk (look-back over the per-chunk counts, annexb_scan.cu).  The CPU emulation of
+// the kernels' logic (tests/native/hd_emul.cpp) keeps the round-1 formulation as a second, independent one: every
+// chunk compacted on its own (G = 0), then the later parts of a NAL slide left by their G (nal_pieces below).  Both
+// must produce the oracle's bytes.  nal_removed is shared: the device's scan_finalize_kernel totals a NAL's count
+// with it.
 //   tail[t]   per chunk, low 16 bits: EPBs after the chunk's last NAL start, or in the whole chunk when it holds none
 //   S[t]      exclusive prefix sum of tail[] (mod 2^32): for chunks Tq < t <= Tb of one NAL, G(t) = S[t] - S[Tq]
 //   a, b      first byte of this NAL / of the next one (b-1 is the 01 of the start code that ends it)
