@@ -431,8 +431,10 @@ def run_gpu(args, rank, world, local_rank):
     for b in bufs:
         del b.bins, b.rbsp
     torch.cuda.empty_cache()
-    # (at least 12 steps: with three jobs in flight a shorter run is mostly pipeline fill and drain)
-    e2e_steps = max(12, args.steps)
+    # (at least 24 steps: with three jobs in flight a short run is mostly pipeline fill and drain -- one H2D and one kernel
+    #  stage before the first result, three D2H after the last submit; they stay inside the timed region and the value)
+    e2e_steps = max(24, args.steps)
+    done_at = []
     e2e_error = None
     t_e2e, e2e_ok, h_stream = 0.0, True, None
     try:
@@ -451,9 +453,11 @@ def run_gpu(args, rank, world, local_rank):
         for k in range(e2e_steps):
             if len(pending) == IN_FLIGHT:
                 r = _stream_wait_raw(ctx, capi, pending.pop(0))
+                done_at.append(time.perf_counter())
             pending.append(_stream_submit_raw(ctx, capi, h_stream, ops, n_ops, p, flags))
         while pending:
             r = _stream_wait_raw(ctx, capi, pending.pop(0))
+            done_at.append(time.perf_counter())
         torch.cuda.synchronize()
         t_e2e = (time.perf_counter() - t0) / e2e_steps
         e2e_ok = r["n_slices"] == n_slices and r["total_bins"] == total_bins
@@ -553,6 +557,8 @@ def run_gpu(args, rank, world, local_rank):
             "e2e": {"value": (bins_all / t_e2e_max) if e2e_error is None else None, "error": e2e_error,
                     "unit": "bins/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": t_e2e_max * 1e3, "steps": e2e_steps,
+                    # rank 0's median interval between two results coming home: the pipeline once it is full
+                    "steady_ms_per_step": (float(np.median(np.diff(done_at))) * 1e3) if len(done_at) > 4 else None,
                     "api": "h264b_stream_submit / h264b_stream_wait, three jobs in flight (pinned host stream in; NAL index, "
                            "packed bins, final states out; copies of consecutive steps overlap kernels)"},
             "gpu_launches": int(launches), "clocks": clocks,
