@@ -716,7 +716,8 @@ def run_config4(args):
         "device_busy_ms": [float(x) for x in busy], "device_busy_imbalance_max_over_mean": float(busy.max() / busy.mean()),
         "device_bytes": [int(x) for x in r["device_bytes"]], "device_jobs": [int(x) for x in r["device_jobs"]],
         "lpt_imbalance_bytes_max_over_mean": float(r["device_bytes"].max() / r["device_bytes"].mean()),
-        "longest_slice_floor_ms": float(n_ops.max()) * 119.0 / 1.965e6,
+        # (a warp on its own: 104 cycles per bin at 1965 MHz, configs[1] in profiles/r2_configs_measured.txt)
+        "longest_slice_floor_ms": float(n_ops.max()) * 104.0 / 1.965e6,
         "e2e": {"value": total_bins / (r["makespan_ms"] * 1e-3), "unit": "bins/s", "h2d_bytes_per_step": total_bytes,
                 "d2h_bytes_per_step": int(r["bins_off"][-1]) * 4 + len(n_ops) * 32},
     }

@@ -1080,6 +1080,9 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
     uint32_t lpw = (j.n_slices + target_warps - 1) / target_warps;
     if (lpw < 1) lpw = 1;
     if (lpw > 32) lpw = 32;
+    const bool exclusive = ctx->cabac_exclusive != 0;
+    if (exclusive) lpw = 1;
+    else if (ctx->cabac_pack) lpw = 32;
     a.lanes_per_warp = lpw;
     a.n_warps = (j.n_slices + lpw - 1) / lpw;
     a.order = nullptr;
@@ -1100,11 +1103,16 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
     if (slots > (uint32_t)kSlotsMax) slots = kSlotsMax;
     if (slots * 4 > w_fit) slots = w_fit / 4;
     uint32_t rounds = slots ? (uint32_t)((a.n_warps + (uint64_t)sms * 4 * slots - 1) / ((uint64_t)sms * 4 * slots)) : 0;
-    const bool assign = a.map_mode == 3 && k_w <= 0 && lpw > 1 && j.n_ops && slots >= 1 && rounds >= 1 && rounds <= 64 &&
+    const bool assign = !exclusive && a.map_mode == 3 && k_w <= 0 && lpw > 1 && j.n_ops && slots >= 1 && rounds >= 1 && rounds <= 64 &&
                         a.n_warps > sms * 4 && sms * 4 <= 640 && ((uint64_t)sms * 4 * slots * rounds + 2ull * sms * 4) * 4 <= 200 * 1024;
     if (a.map_mode == 3 && !assign) a.map_mode = 1;
     uint32_t W, grid;
-    if (assign) {
+    if (exclusive) {  // slices in the caller's order, four to an SM, each warp on a scheduler of its own
+        W = w_fit < 4 ? w_fit : 4;
+        if (W < 1) W = 1;
+        grid = (a.n_warps + W - 1) / W;
+        a.map_mode = 2;
+    } else if (assign) {
         W = slots * 4;
         grid = sms;
     } else {
@@ -1151,7 +1159,7 @@ int launch_cabac(h264b_ctx *ctx, const h264b_cabac_job *job, const uint32_t *d_n
             a.rounds = rounds;
         }
     }
-    const size_t smem = tab_bytes + (size_t)W * (n_rows + 2) * 32;
+    const size_t smem = exclusive ? (size_t)kMaxSmemPerCta : tab_bytes + (size_t)W * (n_rows + 2) * 32;
     // (one carveout for every launch of these kernels: launches that differ in their shared-memory split cannot share an
     //  SM, and h264b_scheduler runs several side by side; half of the SM's 228 KB: room for every launch shape at 64
     //  contexts, and an L1 for the op schedule and the bitstream words; launches that need more get more)

@@ -32,6 +32,10 @@ struct h264b_ctx {
     ScanGraph scan_graph[kScanGraphs];
     uint64_t scan_graph_tick;
     int cabac_max_warps;  // 0: as many warps per CTA as fit; else a cap (launches that share the GPU: h264b_scheduler)
+    int cabac_pack;       // 1: 32 slices per warp whatever their number (launches that share the GPU: as few warps as the
+                          // slices need, so that each has a scheduler to itself); 0: spread over the schedulers first
+    int cabac_exclusive;  // 1: one slice per warp, four warps per CTA (one per scheduler), the whole SM's shared memory per
+                          // CTA so that nothing else lands beside it: for the few slices a whole batch waits for
 
     // grow-only device scratch, in banks: [0] the direct ("_dev" and host-pointer) entry points, [1 + s] stream-job slot
     // s, whose kernels run on their own stream and may overlap the other slots'

@@ -522,9 +522,13 @@ int32_t h264b_mb_type_decode(h264b_ctx *ctx, const h264b_mb_type_job *job);
  * one context and one worker thread per device and takes a whole batch of independent streams ("multi-camera batch",
  * BASELINE configs[4]):
  *   - streams are dealt to the devices longest first onto the least loaded one (LPT by bytes);
- *   - a device's share goes through one split + strip pass; its slices then run in five CABAC launches by length
- *     (more than 1/2, 1/8, 1/32, 1/128 of the longest slice, and the rest), the longest class first, side by side on
- *     streams of their own: a slice is serial work, so the launch with the 1 MB slices lasts two orders of magnitude
+ *   - a device's share is taken in up to three passes, the streams with the longest slices first (a twelfth of the
+ *     share's bytes, then up to one half, then the rest): a slice is serial work, so the slices everything waits for are
+ *     staged, copied and started within milliseconds, while the bulk of the share is still being staged;
+ *   - a pass goes through one split + strip pass; its slices then run in up to six CABAC launches by length, the longest
+ *     class first, side by side on streams of their own: the slices longer than 0.7 of the share's longest -- the chains
+ *     the makespan hangs on -- one per warp, four to an SM that they have to themselves; then more than 1/2, 1/8, 1/32,
+ *     1/128 of the pass's longest slice, and the rest: the launch with the 1 MB slices lasts two orders of magnitude
  *     longer than the one with the 1 KB slices, whose results reach the host long before;
  *   - every slice's result carries the time at which it reached host memory (tail latency), every device the time it
  *     was busy.
@@ -554,12 +558,12 @@ typedef struct {
     const h264b_slice_qp *qp;  /* [total_slices] */
     uint32_t slice_data_offset;
     uint32_t flags;            /* H264B_TABLES_SPEC | H264B_BYPASS_SPEC_OR | H264B_CABAC_FINAL_TERMINATE */
-    uint64_t group_bytes;      /* reserved (0) */
+    uint64_t group_bytes;      /* a device's share of at most this many stream bytes is taken in one pass (0: 32 MiB) */
 } h264b_batch_job;
 
 typedef struct {
     const int32_t *stream_device;    /* [n_streams] index into the scheduler's devices */
-    const uint32_t *stream_job;      /* [n_streams] pass of that device the stream ran in (0: a share is one pass) */
+    const uint32_t *stream_job;      /* [n_streams] pass of that device the stream ran in (0: the first) */
     const uint64_t *stream_nal_off;  /* [n_streams + 1] the stream's NAL units are nals[stream_nal_off[i] .. [i + 1]) */
     const h264b_nal *nals;           /* start / rbsp_off relative to the stream's own first byte */
     const h264b_cabac_final *final;  /* [total_slices] */
@@ -570,7 +574,7 @@ typedef struct {
     uint32_t reserved;
     const double *device_busy_ms;    /* [n_devices] first submit to last wait */
     const uint64_t *device_bytes;    /* [n_devices] stream bytes dealt to the device */
-    const uint32_t *device_jobs;     /* [n_devices] passes (1, or 0 for a device without a stream) */
+    const uint32_t *device_jobs;     /* [n_devices] passes (1..3, or 0 for a device without a stream) */
     double makespan_ms;
     uint64_t total_bins, total_nals;
 } h264b_batch_result;

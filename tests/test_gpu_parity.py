@@ -173,6 +173,42 @@ def test_scan_chunk_boundaries(ctx, capi, seed):
         check_scan(ctx, capi, np.concatenate([sc, hdr, b, sc, hdr, body[:5000], sc]))
 
 
+def test_scan_carry_across_many_chunks(ctx, capi):
+    """What a NAL has lost so far travels from chunk to chunk (look-back over the per-chunk counts) and, for chunks the
+    copy kernel stored verbatim, through the segmented scan and the re-copy list.  Cases the random streams do not reach:
+    a NAL that loses more than 2^15 bytes (the per-chunk count field is 15 bits wide, the carry is not), one early EPB
+    in front of a megabyte of clean payload (hundreds of verbatim chunks to shift), dirty and clean chunks in turn,
+    a long NAL whose every chunk is dirty, and the same with start codes sprinkled in."""
+    rng = np.random.default_rng(77)
+    sc, hdr = np.array([0, 0, 0, 1], np.uint8), np.array([0x65], np.uint8)
+    clean = lambda n: rng.integers(4, 256, n).astype(np.uint8)
+    # (a) 70 000 EPBs in one NAL, then clean payload inside the same NAL, then another NAL
+    triples = np.tile(np.array([0, 0, 3], np.uint8), 70000)
+    check_scan(ctx, capi, np.concatenate([sc, hdr, clean(100), triples, clean(50000), sc, hdr, clean(3000), sc]))
+    # (b) one EPB at the front of 1.2 MB of clean payload; the NAL ends in the middle of a chunk
+    b = clean(1200000 + 1234)
+    b[10:13] = [0, 0, 3]
+    check_scan(ctx, capi, np.concatenate([sc, hdr, b, sc, hdr, clean(100), sc]))
+    # (c) an EPB in every fourth chunk only
+    b = clean(64 * 2048 + 321)
+    for k in range(0, 64, 4):
+        at = k * 2048 + int(rng.integers(8, 2000))
+        b[at:at + 3] = [0, 0, 3]
+    check_scan(ctx, capi, np.concatenate([clean(7), sc, hdr, b, sc]))
+    # (d) every chunk of a 300 KB NAL dirty, then the same payload cut into NAL units of odd lengths
+    b = clean(300000)
+    at = np.sort(rng.choice(np.arange(4, 300000 - 4, 97), 2500, replace=False))
+    for p_ in at:
+        b[p_:p_ + 3] = [0, 0, 3]
+    check_scan(ctx, capi, np.concatenate([sc, hdr, b, sc]))
+    parts, pos = [], 0
+    while pos < len(b):
+        ln = int(rng.integers(50, 9000))
+        parts += [sc, hdr, b[pos:pos + ln]]
+        pos += ln
+    check_scan(ctx, capi, np.concatenate(parts + [sc]))
+
+
 @pytest.mark.parametrize("T", [2048, 16384, 131072])
 def test_scan_start_codes_across_tile_boundaries(ctx, capi, T):
     rng = np.random.default_rng(9)
