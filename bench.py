@@ -672,7 +672,7 @@ def run_config4(args):
     r = min(runs, key=lambda x: x["makespan_ms"])
     fin = r["final"]
     ok = bool(np.array_equal(fin["n_bins"], n_ops + 1)) and not (fin["flags"] & capi.F_OVERRUN).any()
-    last = np.array([int(r["bins_flat"][int(r["bins_off"][s + 1]) - 1]) for s in range(len(n_ops))], dtype=np.uint64)
+    last = np.array([int(r["bins"][s][-1]) for s in range(len(n_ops))], dtype=np.uint64)
     ok = ok and bool(np.all((last >> (n_ops & 31).astype(np.uint64)) & 1 == 1))
     # a sample of slices against the oracle, bin by bin (the oracle strips the stream itself)
     rng = np.random.default_rng(44)

@@ -758,12 +758,14 @@ class Scheduler:
         noff = _from_ptr(r.stream_nal_off, np.uint64, ns + 1).copy()
         nals = _from_ptr(r.nals, NAL_DTYPE, int(noff[-1]) if ns else 0).copy()
         boff = _from_ptr(r.bins_off, np.uint64, total + 1).copy()
-        flat = _from_ptr(r.bins, np.uint32, int(boff[-1]) if total else 0)
+        flat = _from_ptr(r.bins, np.uint32, int(boff[-1]) if total else 0).copy()   # (the library's arena lives until the next run)
+        nb = np.minimum(nops, len(ops)) if nops is not None else np.full(total, len(ops), np.uint32)
+        words = (nb.astype(np.int64) + 1 + 31) // 32   # (a slice's words lie where its launch copied them)
         return dict(stream_device=_from_ptr(r.stream_device, np.int32, ns).copy(),
                     stream_job=_from_ptr(r.stream_job, np.uint32, ns).copy(),
                     nals=[nals[int(noff[i]):int(noff[i + 1])] for i in range(ns)],
                     final=_from_ptr(r.final, FINAL_DTYPE, total).copy(), bins_off=boff, bins_flat=flat,
-                    bins=[flat[int(boff[i]):int(boff[i + 1])] for i in range(total)],
+                    bins=[flat[int(boff[i]):int(boff[i]) + int(words[i])] for i in range(total)],
                     slice_done_ms=_from_ptr(r.slice_done_ms, np.float64, total).copy(),
                     device_busy_ms=_from_ptr(r.device_busy_ms, np.float64, r.n_devices).copy(),
                     device_bytes=_from_ptr(r.device_bytes, np.uint64, r.n_devices).copy(),

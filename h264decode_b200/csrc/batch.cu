@@ -58,7 +58,7 @@ constexpr int kPasses = 3;   // of a device's share, by the streams' longest sli
 struct Pass {  // buffers and contexts of one pass; grow-only, reused from run to run
     h264b_ctx *ctx[kClasses] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [1] also runs the split + strip pass
     cudaEvent_t e_scan = nullptr, e_done[kClasses] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    Grown h_stream, h_bins, h_fin, h_nals, h_small;                      // pinned
+    Grown h_stream, h_fin, h_nals, h_small;                              // pinned
     Grown d_stream, d_rbsp, d_nals, d_sum, d_off, d_len, d_snal, d_offp, d_lenp, d_perm, d_nops, d_qp, d_boff, d_bins, d_fin,
         d_ops;                                                           // device
     // the run in progress
@@ -67,6 +67,7 @@ struct Pass {  // buffers and contexts of one pass; grow-only, reused from run t
     std::vector<uint32_t> rows, perm;
     uint32_t cls_begin[kClasses + 1] = {0, 0, 0, 0, 0, 0, 0};
     const uint64_t *h_boff = nullptr;
+    uint64_t arena_base = 0;
     uint64_t n = 0;
     uint32_t n_sl = 0, nal_cap = 0;
     bool launched[kClasses] = {false, false, false, false, false, false};
@@ -92,7 +93,8 @@ struct h264b_scheduler {
     std::vector<h264b_nal> nals;
     std::vector<h264b_cabac_final> fin;
     std::vector<uint64_t> bins_off;
-    std::vector<uint32_t> bins;
+    uint32_t *bins = nullptr;  // pinned, grow-only: every launch copies its bins straight to where the result says they are
+    size_t bins_words = 0;
     std::vector<double> slice_done_ms;
     std::vector<double> device_busy_ms;
     std::vector<uint64_t> device_bytes;
@@ -163,7 +165,7 @@ void h264b_scheduler_destroy(h264b_scheduler *s) {
         cudaSetDevice(w.device);
         cudaDeviceSynchronize();
         for (Pass &ps : w.pass) {
-            for (Grown *g : {&ps.h_stream, &ps.h_bins, &ps.h_fin, &ps.h_nals, &ps.h_small})
+            for (Grown *g : {&ps.h_stream, &ps.h_fin, &ps.h_nals, &ps.h_small})
                 if (g->p) cudaFreeHost(g->p);
             for (Grown *g : {&ps.d_stream, &ps.d_rbsp, &ps.d_nals, &ps.d_sum, &ps.d_off, &ps.d_len, &ps.d_snal, &ps.d_offp,
                              &ps.d_lenp, &ps.d_perm, &ps.d_nops, &ps.d_qp, &ps.d_boff, &ps.d_bins, &ps.d_fin, &ps.d_ops})
@@ -175,6 +177,7 @@ void h264b_scheduler_destroy(h264b_scheduler *s) {
             }
         }
     }
+    if (s->bins) cudaFreeHost(s->bins);
     delete s;
 }
 
@@ -189,13 +192,27 @@ int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264
     const uint64_t group_bytes = J.group_bytes ? J.group_bytes : (32ull << 20);  // a smaller share is taken in one pass
 
     // ---- bins layout (fixed by the op counts) and the streams' extents
-    s->bins_off.assign((size_t)J.total_slices + 1, 0);
-    for (uint32_t r = 0; r < J.total_slices; r++) {
+    // ---- bins: one pinned arena for the whole batch.  A slice's words are fixed by its op count; where they lie is decided
+    // by the device, pass and class the slice lands in (a launch's bins are one block), and reported per slice.
+    auto words_of = [&](uint32_t r) -> uint64_t {
         uint32_t nb = J.n_ops ? J.n_ops[r] : J.n_ops_max;
         if (nb > J.n_ops_max) nb = J.n_ops_max;
-        s->bins_off[r + 1] = s->bins_off[r] + ((uint64_t)nb + 1 + 31) / 32;
+        return ((uint64_t)nb + 1 + 31) / 32;
+    };
+    uint64_t all_words = 0;
+    for (uint32_t r = 0; r < J.total_slices; r++) all_words += words_of(r);
+    s->bins_off.assign((size_t)J.total_slices + 1, ~0ull);
+    s->bins_off[J.total_slices] = all_words;
+    if (all_words + 16 > s->bins_words) {
+        if (s->bins) cudaFreeHost(s->bins);
+        s->bins = nullptr;
+        s->bins_words = 0;
+        cudaSetDevice(s->workers[0].device);
+        const size_t want = (size_t)(all_words + all_words / 16 + 16);
+        if (cudaHostAlloc((void **)&s->bins, want * 4, cudaHostAllocPortable) != cudaSuccess)
+            return sched_error(s, H264B_E_NOMEM, "scheduler_run: no pinned memory for %llu MB of bins", (unsigned long long)(want * 4 >> 20));
+        s->bins_words = want;
     }
-    s->bins.assign((size_t)s->bins_off[J.total_slices], 0u);
     s->fin.assign(J.total_slices, h264b_cabac_final{});
     s->slice_done_ms.assign(J.total_slices, 0.0);
     s->stream_device.assign(J.n_streams, -1);
@@ -232,6 +249,38 @@ int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264
         mine[best].push_back(k);
         s->device_bytes[best] += ts[k].end - ts[k].begin;
         s->stream_device[ts[k].index] = (int32_t)best;
+    }
+    // the devices' regions of the bins arena; slices of streams that go nowhere (no NAL unit in them) get zeroed words
+    // behind them
+    std::vector<uint64_t> device_words(nd + 1, 0);
+    {
+        std::vector<char> placed(J.n_streams, 0);
+        for (uint32_t d = 0; d < nd; d++) {
+            uint64_t wsum = 0;
+            for (uint32_t k : mine[d]) {
+                const h264b_batch_stream &b = J.streams[ts[k].index];
+                placed[ts[k].index] = 1;
+                for (uint32_t x = 0; x < b.n_slices; x++) wsum += words_of(b.first_slice + x);
+            }
+            device_words[d + 1] = device_words[d] + wsum;
+        }
+        uint64_t at = device_words[nd];
+        for (uint32_t i = 0; i < J.n_streams; i++) {
+            if (placed[i]) continue;
+            const h264b_batch_stream &b = J.streams[i];
+            for (uint32_t x = 0; x < b.n_slices; x++) {
+                s->bins_off[b.first_slice + x] = at;
+                const uint64_t wn = words_of(b.first_slice + x);
+                memset(s->bins + at, 0, (size_t)wn * 4);
+                at += wn;
+            }
+        }
+        for (uint32_t r = 0; r < J.total_slices; r++)  // rows no stream claims
+            if (s->bins_off[r] == ~0ull && at + words_of(r) <= all_words) {
+                s->bins_off[r] = at;
+                memset(s->bins + at, 0, (size_t)words_of(r) * 4);
+                at += words_of(r);
+            }
     }
     // ---- one worker thread per device.  The device's share is taken in up to kPasses passes: the streams with the longest
     // slices first (a slice is serial work: the pass that holds the batch's longest slices is small, and its CABAC launch
@@ -301,6 +350,7 @@ int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264
                 }
             }
             uint32_t n_passes = 0;
+            uint64_t arena_at = device_words[d];  // where the next pass's bins go
             uint32_t excl_budget = (uint32_t)w.pass[0].ctx[0]->sm_count * 4u / 3u;  // slices for class 0 (four to an SM)
 
             // ---- the CABAC launches of classes [c_from, c_to) of a pass and their results, each on its own stream
@@ -330,7 +380,7 @@ int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264
                     const int rc = h264b_cabac_decode_dev(cc, &cj);
                     if (rc != H264B_OK) return fail(rc, std::string("cabac: ") + h264b_last_error(cc));
                     const size_t w0 = (size_t)ps.h_boff[k0], w1 = (size_t)ps.h_boff[k1];
-                    cudaMemcpyAsync((uint32_t *)ps.h_bins.p + w0, (const uint32_t *)ps.d_bins.p + w0, (w1 - w0) * 4, cudaMemcpyDeviceToHost, sc);
+                    cudaMemcpyAsync(s->bins + ps.arena_base + w0, (const uint32_t *)ps.d_bins.p + w0, (w1 - w0) * 4, cudaMemcpyDeviceToHost, sc);
                     cudaMemcpyAsync((h264b_cabac_final *)ps.h_fin.p + k0, (const h264b_cabac_final *)ps.d_fin.p + k0,
                                     (size_t)(k1 - k0) * sizeof(h264b_cabac_final), cudaMemcpyDeviceToHost, sc);
                     cudaEventRecord(ps.e_done[c], sc);
@@ -440,13 +490,16 @@ int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264
                     h_boff[k + 1] = h_boff[k] + ((uint64_t)h_nops[k] + 1 + 31) / 32;
                 }
                 const size_t total_words = (size_t)h_boff[n_sl];
+                ps.arena_base = arena_at;  // the pass's bins in the arena, in class order
+                arena_at += total_words;
+                for (uint32_t k = 0; k < n_sl; k++) s->bins_off[rows[perm[k]]] = ps.arena_base + h_boff[k];
                 if (!grow_dev(ps.d_nals, (size_t)nal_cap * sizeof(h264b_nal)) || !grow_dev(ps.d_sum, 256) ||
                     !grow_dev(ps.d_off, ms * 8) || !grow_dev(ps.d_len, ms * 4) || !grow_dev(ps.d_snal, ms * 4 + 16) ||
                     !grow_dev(ps.d_offp, ms * 8) || !grow_dev(ps.d_lenp, ms * 4) || !grow_dev(ps.d_perm, ms * 4) ||
                     !grow_dev(ps.d_nops, ms * 4) || !grow_dev(ps.d_qp, ms * sizeof(h264b_slice_qp)) ||
                     !grow_dev(ps.d_boff, (ms + 1) * 8) || !grow_dev(ps.d_bins, total_words * 4 + 16) ||
                     !grow_dev(ps.d_fin, ms * sizeof(h264b_cabac_final)) || !grow_dev(ps.d_ops, (size_t)J.n_ops_max * 2 + 16) ||
-                    !grow_pin(ps.h_bins, total_words * 4 + 16) || !grow_pin(ps.h_fin, ms * sizeof(h264b_cabac_final)) ||
+                    !grow_pin(ps.h_fin, ms * sizeof(h264b_cabac_final)) ||
                     !grow_pin(ps.h_nals, (size_t)nal_cap * sizeof(h264b_nal) + 256))
                     return fail(H264B_E_NOMEM, "out of memory for the device's slice arrays");
                 // ---- split + strip, slice list, class order (context 0's stream)
@@ -503,8 +556,6 @@ int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264
                             const uint32_t row = ps.rows[ps.perm[k]];
                             s->fin[row] = ((const h264b_cabac_final *)ps.h_fin.p)[k];
                             s->slice_done_ms[row] = t_done;
-                            memcpy(s->bins.data() + s->bins_off[row], (const uint32_t *)ps.h_bins.p + ps.h_boff[k],
-                                   (size_t)(ps.h_boff[k + 1] - ps.h_boff[k]) * 4);
                         }
                         ps.launched[c] = false;
                         *progressed = true;
@@ -596,7 +647,7 @@ int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264
     res->nals = s->nals.data();
     res->final = s->fin.data();
     res->bins_off = s->bins_off.data();
-    res->bins = s->bins.data();
+    res->bins = s->bins;
     res->slice_done_ms = s->slice_done_ms.data();
     res->n_devices = nd;
     res->device_busy_ms = s->device_busy_ms.data();

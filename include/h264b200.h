@@ -567,8 +567,10 @@ typedef struct {
     const uint64_t *stream_nal_off;  /* [n_streams + 1] the stream's NAL units are nals[stream_nal_off[i] .. [i + 1]) */
     const h264b_nal *nals;           /* start / rbsp_off relative to the stream's own first byte */
     const h264b_cabac_final *final;  /* [total_slices] */
-    const uint64_t *bins_off;        /* [total_slices + 1] word offsets into bins */
-    const uint32_t *bins;
+    const uint64_t *bins_off;        /* [total_slices + 1]: slice r owns bins[bins_off[r] .. + (final[r].n_bins + 31) / 32)
+                                        (its launch copied them there; the offsets are in no particular order);
+                                        bins_off[total_slices] = words in all */
+    const uint32_t *bins;            /* pinned host memory */
     const double *slice_done_ms;     /* [total_slices] from the start of the run to the slice's result in host memory */
     uint32_t n_devices;
     uint32_t reserved;
