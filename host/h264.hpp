@@ -548,8 +548,9 @@ inline void DecodeMbTypes(const h264b_mb_type_job &job, Device &dev = Device::De
 
 // The reference serves every TCP connection from a goroutine of its own (main.go:16-21 -> ByteStreamReader ->
 // handleConnection, h264/server.go:113-166).  Scheduler is that concurrency for whole streams held in host memory: a
-// batch of independent streams goes over the GPUs of this process (longest processing time first by bytes; per GPU one
-// split + strip pass and the CABAC engine in five launches by slice length, side by side), and comes back as NAL units,
+// batch of independent streams goes over the GPUs of this process (longest processing time first by bytes; a GPU takes its
+// share in up to three passes, longest slices first, each one split + strip pass and the CABAC engine in up to six
+// launches by slice length, side by side), and comes back as NAL units,
 // bins and final engine states per stream, with the time every slice's result reached host memory.
 class Scheduler {
    public:
