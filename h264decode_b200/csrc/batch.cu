@@ -459,11 +459,13 @@ int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264
                     if (thr[1] > thr[0]) thr[1] = thr[0];
                     uint32_t n_excl = 0;
                     while (n_excl < n_sl && ops_of(rows[perm[n_excl]]) > thr[0]) n_excl++;
-                    // (they take SMs away from everything else: at most a third of the device over the passes of a share)
-                    if (n_excl > excl_budget) thr[0] = ~0ull, n_excl = 0;
+                    // (they take SMs away from everything else: at most a third of the device over the passes of a share;
+                    //  the longest ones if there are more)
+                    if (n_excl > excl_budget) n_excl = excl_budget;
                     excl_budget -= n_excl;
-                    uint32_t k = 0;
-                    for (int c = 0; c < kClasses - 1; c++) {
+                    cls_begin[0] = 0;
+                    uint32_t k = n_excl;
+                    for (int c = 1; c < kClasses - 1; c++) {
                         cls_begin[c] = k;
                         while (k < n_sl && ops_of(rows[perm[k]]) > thr[c]) k++;
                     }
