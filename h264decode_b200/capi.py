@@ -34,7 +34,7 @@ SYMBOLS = [
     "h264b_param_set_select_dev",
     "h264b_ctx_idx", "h264b_new_binarization", "h264b_init_cabac", "h264b_mb_bin_string", "h264b_bin_string_match",
     "h264b_mb_type_decode_dev", "h264b_mb_type_decode",
-    "h264b_scheduler_create", "h264b_scheduler_destroy", "h264b_scheduler_last_error", "h264b_scheduler_run",
+    "h264b_scheduler_create", "h264b_scheduler_destroy", "h264b_scheduler_last_error", "h264b_scheduler_run", "h264b_scheduler_plan",
 ]
 
 NAL_DTYPE = np.dtype([("start", "<u8"), ("rbsp_off", "<u8"), ("num_bytes", "<u4"), ("rbsp_len", "<u4"),
@@ -246,6 +246,7 @@ def load():
         "h264b_scheduler_destroy": (None, [vp]),
         "h264b_scheduler_last_error": (C.c_char_p, [vp]),
         "h264b_scheduler_run": (i32, [vp, P(BatchJob), P(BatchResult)]),
+        "h264b_scheduler_plan": (i32, [P(BatchJob), u32, u32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         if os.environ.get("H264B_LIB") and not hasattr(L, name):
@@ -695,6 +696,36 @@ class Context:
                     pps_nal=_from_ptr(r.pps_nal, np.uint32, r.n_pps) if r.pps else None,
                     slice_sps=_from_ptr(r.slice_sps, np.int32, ns) if r.sps else None,
                     slice_pps=_from_ptr(r.slice_pps, np.int32, ns) if r.sps else None)
+
+
+def scheduler_plan(streams, slices_per_stream, n_ops, n_ops_max, n_devices, sm_count=148, group_bytes=0):
+    """h264b_scheduler_plan: host only (works without a GPU).  -> (stream_device, stream_pass, slice_class)"""
+    arrs = [np.ascontiguousarray(s, dtype=np.uint8) for s in streams]
+    per = np.asarray(slices_per_stream, dtype=np.int64)
+    first = np.concatenate([[0], np.cumsum(per)]).astype(np.int64)
+    total = int(first[-1])
+    bs = (BatchStream * max(len(arrs), 1))()
+    for i, a in enumerate(arrs):
+        bs[i].stream = a.ctypes.data if len(a) else None
+        bs[i].n = len(a)
+        bs[i].first_slice = int(first[i])
+        bs[i].n_slices = int(per[i])
+    nops = None if n_ops is None else np.ascontiguousarray(n_ops, dtype=np.uint32)
+    j = BatchJob()
+    j.streams = C.addressof(bs)
+    j.n_streams = len(arrs)
+    j.total_slices = total
+    j.n_ctx = 64
+    j.n_ops_max = int(n_ops_max)
+    j.n_ops = nops.ctypes.data if nops is not None else None
+    j.group_bytes = group_bytes
+    dev = np.zeros(max(len(arrs), 1), np.int32)
+    pas = np.zeros(max(len(arrs), 1), np.uint32)
+    cls = np.zeros(max(total, 1), np.uint8)
+    rc = _lib.h264b_scheduler_plan(C.byref(j), n_devices, sm_count, dev.ctypes.data, pas.ctypes.data, cls.ctypes.data)
+    if rc != OK:
+        raise H264BError(rc, "h264b_scheduler_plan")
+    return dev[:len(arrs)], pas[:len(arrs)], cls[:total]
 
 
 class Scheduler:

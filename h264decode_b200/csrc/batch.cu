@@ -118,6 +118,101 @@ static int sched_error(h264b_scheduler *s, int code, const char *fmt, ...) {
     return code;
 }
 
+
+// ---------------------------------------------------------------------------------------------- planning (host only)
+// The three decisions of a run -- which device a stream goes to, which pass of that device, which launch class a slice
+// -- are pure functions of the job; h264b_scheduler_run and h264b_scheduler_plan share them.
+
+// Streams with at least one NAL unit, from their first to their last start code.  false: a stream's slice rows are out
+// of range (*bad = its index).
+static bool plan_trim(const h264b_batch_job &J, std::vector<TrimmedStream> &ts, uint32_t *bad) {
+    ts.clear();
+    ts.reserve(J.n_streams);
+    for (uint32_t i = 0; i < J.n_streams; i++) {
+        const h264b_batch_stream &b = J.streams[i];
+        if ((uint64_t)b.first_slice + b.n_slices > J.total_slices) {
+            *bad = i;
+            return false;
+        }
+        TrimmedStream t;
+        t.index = i;
+        if (!b.stream || !trim(b.stream, b.n, &t.begin, &t.end)) continue;  // no NAL unit in it
+        t.longest = 0;
+        for (uint32_t k = 0; k < b.n_slices; k++)
+            t.longest = std::max<uint64_t>(t.longest, J.n_ops ? std::min(J.n_ops[b.first_slice + k], J.n_ops_max) : J.n_ops_max);
+        if (!b.n_slices) t.longest = t.end - t.begin;
+        ts.push_back(t);
+    }
+    return true;
+}
+
+// streams -> devices: longest first onto the least loaded device (ties: lowest device, lowest stream)
+static void plan_devices(const std::vector<TrimmedStream> &ts, uint32_t nd, std::vector<std::vector<uint32_t>> &mine,
+                         std::vector<uint64_t> &device_bytes) {
+    std::vector<uint32_t> by_size(ts.size());
+    for (size_t k = 0; k < ts.size(); k++) by_size[k] = (uint32_t)k;
+    std::stable_sort(by_size.begin(), by_size.end(),
+                     [&](uint32_t a, uint32_t b) { return ts[a].end - ts[a].begin > ts[b].end - ts[b].begin; });
+    mine.assign(nd, {});
+    device_bytes.assign(nd, 0);
+    for (uint32_t k : by_size) {
+        uint32_t best = 0;
+        for (uint32_t d = 1; d < nd; d++)
+            if (device_bytes[d] < device_bytes[best]) best = d;
+        mine[best].push_back(k);
+        device_bytes[best] += ts[k].end - ts[k].begin;
+    }
+}
+
+// A device's streams -> passes: by their longest slice, descending; the first pass takes the streams up to 1/12 of the
+// share's bytes (it is staged and copied in a few ms and holds the slices everything waits for), the second up to one
+// half, the third the rest.  A share of at most group_bytes, or of fewer than 8 streams, is one pass.
+static void plan_passes(const h264b_batch_job &J, const std::vector<TrimmedStream> &ts, const std::vector<uint32_t> &my,
+                        uint64_t share, uint64_t group_bytes, std::vector<uint32_t> order[kPasses]) {
+    for (int p = 0; p < kPasses; p++) order[p].clear();
+    std::vector<uint32_t> by_len(my);
+    std::stable_sort(by_len.begin(), by_len.end(), [&](uint32_t x, uint32_t y) { return ts[x].longest > ts[y].longest; });
+    const bool cut = J.total_slices != 0 && share > group_bytes && by_len.size() >= 8;
+    uint64_t acc = 0;
+    for (uint32_t k : by_len) {
+        const int p = !cut ? 0 : (acc * 12 < share ? 0 : (acc * 2 < share ? 1 : 2));
+        order[p].push_back(k);
+        acc += ts[k].end - ts[k].begin;
+    }
+}
+
+// A pass's slices (ops[k], longest first) -> launch classes [cls_begin[c], cls_begin[c + 1]).
+//   class 0: a slice that shares its scheduler runs at ~74 ns per bin instead of ~53; the bulk's launches start once
+//   every pass is on the device (~0.1 ms per MB of the share), so a slice longer than (longest x 53 ns - that start) /
+//   74 ns would end after the share's longest one does on its own: such slices run one per warp, four to an SM that they
+//   have to themselves.  They take SMs away from everything else: *excl_budget (a third of the device over the passes
+//   of a share) bounds their number; the longest ones are taken if there are more.
+//   classes 1..: more than 1/2, 1/8, 1/32, 1/128 of the pass's longest slice, and the rest.
+static void plan_classes(const std::vector<uint64_t> &ops, uint64_t share_top, uint64_t share_bytes, uint32_t *excl_budget,
+                         uint32_t cls_begin[kClasses + 1]) {
+    const uint32_t n_sl = (uint32_t)ops.size();
+    const uint64_t ptop = n_sl ? ops[0] : 0;
+    const double t_lone = 53e-6, t_shared = 74e-6;  // ms per bin
+    const double start_ms = 0.1 * (double)share_bytes / 1e6;
+    double excl = ((double)share_top * t_lone - start_ms) / t_shared;
+    if (excl < 0.3 * (double)share_top) excl = 0.3 * (double)share_top;
+    uint64_t thr[kClasses - 1] = {(uint64_t)excl, ptop / 2, ptop / 8, ptop / 32, ptop / 128};
+    if (thr[1] > thr[0]) thr[1] = thr[0];
+    uint32_t n_excl = 0;
+    while (n_excl < n_sl && ops[n_excl] > thr[0]) n_excl++;
+    if (n_excl > *excl_budget) n_excl = *excl_budget;
+    *excl_budget -= n_excl;
+    cls_begin[0] = 0;
+    uint32_t k = n_excl;
+    for (int c = 1; c < kClasses - 1; c++) {
+        cls_begin[c] = k;
+        while (k < n_sl && ops[k] > thr[c]) k++;
+    }
+    cls_begin[kClasses - 1] = k;
+    cls_begin[kClasses] = n_sl;
+}
+static uint32_t plan_excl_budget(uint32_t sm_count) { return sm_count * 4u / 3u; }  // slices for class 0 (four to an SM)
+
 extern "C" {
 
 int32_t h264b_scheduler_create(const int32_t *devices, uint32_t n_devices, h264b_scheduler **out) {
@@ -191,7 +286,6 @@ int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264
     const uint32_t nd = (uint32_t)s->workers.size();
     const uint64_t group_bytes = J.group_bytes ? J.group_bytes : (32ull << 20);  // a smaller share is taken in one pass
 
-    // ---- bins layout (fixed by the op counts) and the streams' extents
     // ---- bins: one pinned arena for the whole batch.  A slice's words are fixed by its op count; where they lie is decided
     // by the device, pass and class the slice lands in (a launch's bins are one block), and reported per slice.
     auto words_of = [&](uint32_t r) -> uint64_t {
@@ -222,34 +316,14 @@ int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264
     s->device_bytes.assign(nd, 0);
     s->device_jobs.assign(nd, 0);
     std::vector<TrimmedStream> ts;
-    ts.reserve(J.n_streams);
-    for (uint32_t i = 0; i < J.n_streams; i++) {
-        const h264b_batch_stream &b = J.streams[i];
-        if ((uint64_t)b.first_slice + b.n_slices > J.total_slices)
-            return sched_error(s, H264B_E_INVALID, "scheduler_run: stream %u: slice rows out of range", i);
-        TrimmedStream t;
-        t.index = i;
-        if (!b.stream || !trim(b.stream, b.n, &t.begin, &t.end)) continue;  // no NAL unit in it
-        t.longest = 0;
-        for (uint32_t k = 0; k < b.n_slices; k++)
-            t.longest = std::max<uint64_t>(t.longest, J.n_ops ? J.n_ops[b.first_slice + k] : J.n_ops_max);
-        if (!b.n_slices) t.longest = t.end - t.begin;
-        ts.push_back(t);
+    {
+        uint32_t bad = 0;
+        if (!plan_trim(J, ts, &bad)) return sched_error(s, H264B_E_INVALID, "scheduler_run: stream %u: slice rows out of range", bad);
     }
-    // ---- streams -> devices: longest first onto the least loaded device (ties: lowest device, lowest stream)
-    std::vector<uint32_t> by_size(ts.size());
-    for (size_t k = 0; k < ts.size(); k++) by_size[k] = (uint32_t)k;
-    std::stable_sort(by_size.begin(), by_size.end(),
-                     [&](uint32_t a, uint32_t b) { return ts[a].end - ts[a].begin > ts[b].end - ts[b].begin; });
-    std::vector<std::vector<uint32_t>> mine(nd);
-    for (uint32_t k : by_size) {
-        uint32_t best = 0;
-        for (uint32_t d = 1; d < nd; d++)
-            if (s->device_bytes[d] < s->device_bytes[best]) best = d;
-        mine[best].push_back(k);
-        s->device_bytes[best] += ts[k].end - ts[k].begin;
-        s->stream_device[ts[k].index] = (int32_t)best;
-    }
+    std::vector<std::vector<uint32_t>> mine;
+    plan_devices(ts, nd, mine, s->device_bytes);
+    for (uint32_t d = 0; d < nd; d++)
+        for (uint32_t k : mine[d]) s->stream_device[ts[k].index] = (int32_t)d;
     // the devices' regions of the bins arena; slices of streams that go nowhere (no NAL unit in them) get zeroed words
     // behind them
     std::vector<uint64_t> device_words(nd + 1, 0);
@@ -281,6 +355,8 @@ int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264
                 memset(s->bins + at, 0, (size_t)words_of(r) * 4);
                 at += words_of(r);
             }
+        for (uint32_t r = 0; r < J.total_slices; r++)  // (rows claimed twice leave no room for the others: a caller's error)
+            if (s->bins_off[r] == ~0ull) s->bins_off[r] = 0;
     }
     // ---- one worker thread per device.  The device's share is taken in up to kPasses passes: the streams with the longest
     // slices first (a slice is serial work: the pass that holds the batch's longest slices is small, and its CABAC launch
@@ -326,9 +402,7 @@ int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264
             if (my.empty()) return;
             const Clock::time_point t_first = Clock::now();
             auto ops_of = [&](uint32_t row) { return J.n_ops ? std::min(J.n_ops[row], J.n_ops_max) : J.n_ops_max; };
-            // ---- the share's streams -> passes: by their longest slice, descending; the first pass takes the streams up to
-            // 1/12 of the share's bytes (it is staged and copied in a few ms and holds the slices everything waits for), the
-            // second up to one half, the third the rest.  A share too small to be worth cutting is one pass.
+            // ---- the share's streams -> passes (plan_passes)
             for (Pass &ps : w.pass) {
                 ps.order.clear();
                 ps.n = 0;
@@ -338,20 +412,13 @@ int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264
             uint64_t share_top = 0;  // ops of the share's longest slice
             for (uint32_t k : my) share_top = std::max(share_top, ts[k].longest);
             {
-                std::vector<uint32_t> by_len(my);
-                std::stable_sort(by_len.begin(), by_len.end(), [&](uint32_t x, uint32_t y) { return ts[x].longest > ts[y].longest; });
-                const uint64_t share = s->device_bytes[d];
-                const bool cut = J.total_slices != 0 && share > group_bytes && by_len.size() >= 8;
-                uint64_t acc = 0;
-                for (uint32_t k : by_len) {
-                    const int p = !cut ? 0 : (acc * 12 < share ? 0 : (acc * 2 < share ? 1 : 2));
-                    w.pass[p].order.push_back(k);
-                    acc += ts[k].end - ts[k].begin;
-                }
+                std::vector<uint32_t> order[kPasses];
+                plan_passes(J, ts, my, s->device_bytes[d], group_bytes, order);
+                for (int p = 0; p < kPasses; p++) w.pass[p].order.swap(order[p]);
             }
             uint32_t n_passes = 0;
             uint64_t arena_at = device_words[d];  // where the next pass's bins go
-            uint32_t excl_budget = (uint32_t)w.pass[0].ctx[0]->sm_count * 4u / 3u;  // slices for class 0 (four to an SM)
+            uint32_t excl_budget = plan_excl_budget((uint32_t)w.pass[0].ctx[0]->sm_count);
 
             // ---- the CABAC launches of classes [c_from, c_to) of a pass and their results, each on its own stream
             auto launch_classes = [&](Pass &ps, int c_from, int c_to) -> bool {
@@ -442,35 +509,11 @@ int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264
                 perm.resize(n_sl);
                 for (uint32_t k = 0; k < n_sl; k++) perm[k] = k;
                 std::stable_sort(perm.begin(), perm.end(), [&](uint32_t x, uint32_t y) { return ops_of(rows[x]) > ops_of(rows[y]); });
-                // classes: [0] more than 0.7 of the SHARE's longest slice -- the chains the makespan hangs on: one warp
-                // each, four to an SM that they have to themselves, unless they are too many for that to pay; then more
-                // than 1/2, 1/8, 1/32, 1/128 of the pass's longest slice, and the rest
-                uint32_t *cls_begin = ps.cls_begin;
+                // launch classes (plan_classes)
                 {
-                    const uint64_t ptop = n_sl ? ops_of(rows[perm[0]]) : 0;
-                    // class 0: a slice that shares its scheduler runs at ~74 ns per bin instead of ~53; the bulk's launches
-                    // start once every pass is on the device (~0.1 ms per MB of the share), so a slice longer than
-                    // (longest x 53 ns - that start) / 74 ns would end after the longest one does on its own
-                    const double t_lone = 53e-6, t_shared = 74e-6;  // ms per bin
-                    const double start_ms = 0.1 * (double)s->device_bytes[d] / 1e6;
-                    double excl = ((double)share_top * t_lone - start_ms) / t_shared;
-                    if (excl < 0.3 * (double)share_top) excl = 0.3 * (double)share_top;
-                    uint64_t thr[kClasses - 1] = {(uint64_t)excl, ptop / 2, ptop / 8, ptop / 32, ptop / 128};
-                    if (thr[1] > thr[0]) thr[1] = thr[0];
-                    uint32_t n_excl = 0;
-                    while (n_excl < n_sl && ops_of(rows[perm[n_excl]]) > thr[0]) n_excl++;
-                    // (they take SMs away from everything else: at most a third of the device over the passes of a share;
-                    //  the longest ones if there are more)
-                    if (n_excl > excl_budget) n_excl = excl_budget;
-                    excl_budget -= n_excl;
-                    cls_begin[0] = 0;
-                    uint32_t k = n_excl;
-                    for (int c = 1; c < kClasses - 1; c++) {
-                        cls_begin[c] = k;
-                        while (k < n_sl && ops_of(rows[perm[k]]) > thr[c]) k++;
-                    }
-                    cls_begin[kClasses - 1] = k;
-                    cls_begin[kClasses] = n_sl;
+                    std::vector<uint64_t> sorted_ops(n_sl);
+                    for (uint32_t k = 0; k < n_sl; k++) sorted_ops[k] = ops_of(rows[perm[k]]);
+                    plan_classes(sorted_ops, share_top, s->device_bytes[d], &excl_budget, ps.cls_begin);
                 }
                 const uint32_t nal_cap = (uint32_t)std::min<uint64_t>(n / 64 + 1024 + 2 * (uint64_t)order.size(), 0xFFFFFFF0ull);
                 ps.nal_cap = nal_cap;
@@ -658,6 +701,58 @@ int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264
     res->makespan_ms = makespan;
     res->total_nals = s->nals.size();
     for (uint32_t r = 0; r < J.total_slices; r++) res->total_bins += s->fin[r].n_bins;
+    return H264B_OK;
+}
+
+int32_t h264b_scheduler_plan(const h264b_batch_job *job, uint32_t n_devices, uint32_t sm_count, int32_t *stream_device,
+                             uint32_t *stream_pass, uint8_t *slice_class) {
+    if (!job || !n_devices) return H264B_E_INVALID;
+    const h264b_batch_job &J = *job;
+    if (J.n_streams && !J.streams) return H264B_E_INVALID;
+    const uint64_t group_bytes = J.group_bytes ? J.group_bytes : (32ull << 20);
+    std::vector<TrimmedStream> ts;
+    uint32_t bad = 0;
+    if (!plan_trim(J, ts, &bad)) return H264B_E_INVALID;
+    std::vector<std::vector<uint32_t>> mine;
+    std::vector<uint64_t> device_bytes;
+    plan_devices(ts, n_devices, mine, device_bytes);
+    for (uint32_t i = 0; i < J.n_streams; i++) {
+        if (stream_device) stream_device[i] = -1;
+        if (stream_pass) stream_pass[i] = 0;
+    }
+    if (slice_class) memset(slice_class, 255, J.total_slices);
+    auto ops_of = [&](uint32_t row) { return J.n_ops ? std::min(J.n_ops[row], J.n_ops_max) : J.n_ops_max; };
+    for (uint32_t d = 0; d < n_devices; d++) {
+        const std::vector<uint32_t> &my = mine[d];
+        uint64_t share_top = 0;
+        for (uint32_t k : my) share_top = std::max(share_top, ts[k].longest);
+        std::vector<uint32_t> order[kPasses];
+        plan_passes(J, ts, my, device_bytes[d], group_bytes, order);
+        uint32_t excl_budget = plan_excl_budget(sm_count);
+        uint32_t pass_no = 0;
+        for (int p = 0; p < kPasses; p++) {
+            if (order[p].empty()) continue;
+            std::sort(order[p].begin(), order[p].end(), [&](uint32_t x, uint32_t y) { return ts[x].index < ts[y].index; });
+            std::vector<uint32_t> rows;
+            for (uint32_t k : order[p]) {
+                const h264b_batch_stream &b = J.streams[ts[k].index];
+                if (stream_device) stream_device[ts[k].index] = (int32_t)d;
+                if (stream_pass) stream_pass[ts[k].index] = pass_no;
+                for (uint32_t x = 0; x < b.n_slices; x++) rows.push_back(b.first_slice + x);
+            }
+            std::vector<uint32_t> perm(rows.size());
+            for (uint32_t k = 0; k < perm.size(); k++) perm[k] = k;
+            std::stable_sort(perm.begin(), perm.end(), [&](uint32_t x, uint32_t y) { return ops_of(rows[x]) > ops_of(rows[y]); });
+            std::vector<uint64_t> sorted_ops(rows.size());
+            for (uint32_t k = 0; k < perm.size(); k++) sorted_ops[k] = ops_of(rows[perm[k]]);
+            uint32_t cls_begin[kClasses + 1];
+            plan_classes(sorted_ops, share_top, device_bytes[d], &excl_budget, cls_begin);
+            if (slice_class)
+                for (int c = 0; c < kClasses; c++)
+                    for (uint32_t k = cls_begin[c]; k < cls_begin[c + 1]; k++) slice_class[rows[perm[k]]] = (uint8_t)c;
+            pass_no++;
+        }
+    }
     return H264B_OK;
 }
 

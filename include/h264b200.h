@@ -137,8 +137,9 @@ typedef struct {
 /* Bytes of device scratch h264b_annexb_scan_dev needs for an n-byte stream (the context owns and grows it). */
 uint64_t h264b_annexb_scratch_bytes(uint64_t n);
 
-/* Device-resident scan.  d_stream: n bytes, 16-byte aligned (the 16-byte granule holding byte n-1 must be
- * readable).  d_rbsp: 16-byte aligned, capacity >= n + 16.
+/* Device-resident scan.  d_stream: n bytes, 16-byte aligned, readable up to n + 32 (loads are whole 16-byte granules
+ * and whole words; what lies past n is never used).  d_rbsp: 16-byte aligned, capacity >= n + 32 (the pass itself
+ * writes below n; h264b_cabac_decode_dev on this buffer reads whole words past the end of the last slice).
  * d_nals: nal_cap records.  d_ext: nal_cap records or NULL.  d_summary: one record.  Asynchronous. */
 int32_t h264b_annexb_scan_dev(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint8_t *d_rbsp,
                               h264b_nal *d_nals, h264b_nal_ext *d_ext, uint32_t nal_cap,
@@ -583,6 +584,16 @@ typedef struct {
 
 /* Synchronous; the result stays valid until the next run or the scheduler's destruction. */
 int32_t h264b_scheduler_run(h264b_scheduler *s, const h264b_batch_job *job, h264b_batch_result *res);
+
+/* Host only (no device is touched; the streams' bytes are searched for their first and last start code): how
+ * h264b_scheduler_run deals this batch over n_devices devices of sm_count SMs each -- the same code decides there.
+ * Outputs, each may be NULL:
+ *   stream_device[n_streams]   index of the device, -1: the stream holds no NAL unit
+ *   stream_pass[n_streams]     pass of that device the stream is taken in (0: the first)
+ *   slice_class[total_slices]  launch class inside its pass: 0 = one slice per warp on an SM of their own, 1..5 by
+ *                              length (longest first); 255: the slice's stream goes nowhere */
+int32_t h264b_scheduler_plan(const h264b_batch_job *job, uint32_t n_devices, uint32_t sm_count, int32_t *stream_device,
+                             uint32_t *stream_pass, uint8_t *slice_class);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop
