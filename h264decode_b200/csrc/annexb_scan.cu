@@ -458,42 +458,29 @@ __device__ __forceinline__ void chunk_store(const ScanArgs &a, uint8_t *buf, uin
         return;
     }
     // start codes: records first (they read the staged bytes)
-    uint32_t any_sc = 0;
-#pragma unroll
-    for (int r = 0; r < kRows; r++) any_sc |= cm.es[r] >> 16;
-    int first_end = 0;  // (n_sc != 0) image offsets of the first start code: x of its 01 byte + 1 in the second mapping,
-    int first_a_end = 0;  // and the end of the first NAL's bytes in the first mapping
+    int first_end = 0;    // (n_sc != 0) image offset of the byte behind the chunk's first start code, second mapping,
+    int first_a_end = 0;  // and the end of the bytes of the NAL it ends, first mapping
     if (n_sc) {
         unsigned long long slot0 = 0;
         if (lane == 0) slot0 = atomicAdd(&a.hdr->total_sc, (unsigned long long)n_sc);
         slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
-        int fe = 0x7FFFFFFF, fa = 0;
+        int fe = -1, fa = 0;  // one granule of the chunk holds its first start code: that lane sets these
 #pragma unroll
         for (int r = 0; r < kRows; r++) {
             const uint32_t sc = cm.es[r] >> 16;
             if (!sc) continue;
             const int gi = r * 32 + lane;
             emit_dirty_records(a, tile_in, pos, gi, cm.es[r] & 0xFFFFu, sc, cm.pre[r], slot0);
-            if (((cm.pre[r] >> 16) & 0x1FFFu) == 0 && fe == 0x7FFFFFFF) {  // the chunk's first start code is here
+            if (((cm.pre[r] >> 16) & 0x1FFFu) == 0 && fe < 0) {  // no start code of the chunk in front of this granule
                 const int j = __ffs((int)sc) - 1;
                 fe = gi * 16 + j + 1;
-                // its NAL's bytes end two bytes earlier; they have moved by cb + the EPBs in front of them
+                // the NAL's bytes end two bytes earlier; they have moved by cb + the EPBs in front of them
                 fa = fe - 2 - (int)cb - (int)((cm.pre[r] & 0x7FFFu) + bits_popc(cm.es[r] & ((1u << j) - 1u)));
             }
         }
-        const uint32_t who = __ballot_sync(0xFFFFFFFFu, fe != 0x7FFFFFFF);
-        const int src = __ffs((int)who) - 1;  // (row-major order: the lowest row wins inside a lane, but another lane may
-        // hold an earlier row) -> take the minimum
-        int fe_min = fe;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const int o = __shfl_xor_sync(0xFFFFFFFFu, fe_min, d);
-            fe_min = o < fe_min ? o : fe_min;
-        }
-        (void)src;
-        const uint32_t owner = __ballot_sync(0xFFFFFFFFu, fe == fe_min);
-        first_end = fe_min;
-        first_a_end = __shfl_sync(0xFFFFFFFFu, fa, __ffs((int)owner) - 1);
+        const int owner = __ffs((int)__ballot_sync(0xFFFFFFFFu, fe >= 0)) - 1;
+        first_end = __shfl_sync(0xFFFFFFFFu, fe, owner);
+        first_a_end = __shfl_sync(0xFFFFFFFFu, fa, owner);
     }
     // every lane's granules into registers before anything is rewritten
     uint32_t v[kRows][4];
