@@ -25,9 +25,10 @@
 //                             (emulation-prevention bytes spliced out in registers, 32-bit stores, neighbouring
 //                             lanes hand over the bytes that straddle a word) and stored with aligned 16-byte
 //                             stores at its final position; NAL records for the start codes.
-// A kept byte at stream position p goes to out[p - (EPBs removed from p's NAL before p)].  Dirty chunks are dealt to the
-// warps of one resident wave in ascending order, and a warp takes the counts of its NEXT chunk before it looks back for
-// the current one, so a neighbour rarely waits.  What is left for the post-passes: exclusive scans of the per-chunk
+// A kept byte at stream position p goes to out[p - (EPBs removed from p's NAL before p)].  Dirty chunks are handed out in
+// ascending order by ticket (dirty_list_kernel compacts the flags first), so a chunk that is waited for is always in the
+// hands of a running warp, and a warp takes the counts of its NEXT chunk before it looks back for the current one, so a
+// neighbour rarely waits.  What is left for the post-passes: exclusive scans of the per-chunk
 // counts (NAL ordinals; S[] for the per-NAL totals; the segmented carry that finds the chunks the copy kernel stored
 // verbatim although their NAL had already lost bytes -- those are copied again, shifted, from the input), permutation
 // of the records into stream order, and the h264b_nal records (lengths are differences of neighbours).
@@ -65,12 +66,13 @@ constexpr uint32_t kPieceReady = 0x80000000u;      // bit 31      (dirty chunks)
 
 struct ScanScratchHeader {   // device scratch; zeroed (together with the two per-chunk arrays behind it) before every pass
     unsigned int n_shift;          // entries of shift_list
-    unsigned int reserved0;
+    unsigned int n_dirty;          // entries of dirty_list (dirty_list_kernel)
     unsigned long long first_inv;  // max over NAL starts of ~start (0: no start code): first_start = ~first_inv
     unsigned long long total_sc;   // start codes found = slots handed out of the NAL record buffer
     unsigned long long total_kept;
     unsigned long long n_epb;
-    unsigned long long reserved[3];
+    unsigned long long ticket;     // next entry of dirty_list to hand out (annexb_dirty_kernel)
+    unsigned long long reserved[2];
 };  // 64 bytes
 
 struct ScanArgs {
@@ -83,6 +85,8 @@ struct ScanArgs {
                                // verbatim and found no start code in
     uint32_t *piece_carry;     // per dirty chunk: kPieceReady | EPBs removed from the NAL open at the END of the chunk
                                // since that NAL's start (the look-back's short cut)
+    uint32_t *tile_dirty;      // per kOrderTile chunks: dirty chunks among them (counted by the copy kernel)
+    uint32_t *dirty_list;      // the dirty chunks in ascending order (dirty_list_kernel)
     uint32_t *piece_ord;       // per chunk: ordinal of its first start code (exclusive scan of the counts)
     uint32_t *piece_S;         // per chunk: exclusive scan of the EPB fields
     uint2 *shift_list;         // (chunk, G): chunks the copy kernel stored verbatim although the NAL open at their first
@@ -163,7 +167,10 @@ __global__ void __launch_bounds__(kWarpsA * 32) annexb_copy_kernel(ScanArgs a) {
     const uint64_t pos = (uint64_t)chunk * kChunk;
     // chunks that touch the ends of the stream always take the general path (it blanks the bytes outside)
     if (pos == 0 || pos + kChunk + kHalo > a.n) {
-        if (lane == 0) a.piece[chunk] = kPieceDirty;
+        if (lane == 0) {
+            a.piece[chunk] = kPieceDirty;
+            atomicAdd(&a.tile_dirty[chunk / kOrderTile], 1u);
+        }
         return;
     }
     const uint8_t *src = a.in + pos + lane * 16;
@@ -190,7 +197,10 @@ __global__ void __launch_bounds__(kWarpsA * 32) annexb_copy_kernel(ScanArgs a) {
 #endif
     }
     if (__any_sync(0xFFFFFFFFu, any_e != 0)) {
-        if (lane == 0) a.piece[chunk] = kPieceDirty;
+        if (lane == 0) {
+            a.piece[chunk] = kPieceDirty;
+            atomicAdd(&a.tile_dirty[chunk / kOrderTile], 1u);  // (one address per 8 MiB of stream: no hot spot)
+        }
         return;
     }
 #ifndef H264B_EXP_NOSTORE
@@ -591,12 +601,56 @@ __device__ __forceinline__ void chunk_store(const ScanArgs &a, uint8_t *buf, uin
     }
 }
 
-// The dirty chunks, in ascending order over the warps of one resident wave: warp g looks at chunks g, g + W, g + 2W, ...
-// (W = warps of the grid; 32 flags per load, one per lane) and walks those the copy kernel flagged.  Per chunk: the
-// TMA stages it; first walk (chunk_masks), after which its counts are published; look-back for the carry; second walk
-// (chunk_store).  The first walk of the warp's NEXT chunk runs before the look-back of the current one, so the counts a
-// neighbour waits for are out a whole chunk early.  Ascending order is what the look-back relies on: every chunk a warp
-// can wait for belongs to a warp that is running and not behind it.
+// The dirty chunks in ascending order: one CTA per kOrderTile chunks adds up the counts of the tiles before its own (the
+// copy kernel counted while it flagged) and compacts its tile's flags in order.
+__global__ void __launch_bounds__(256) dirty_list_kernel(ScanArgs a) {
+    __shared__ uint32_t warp_sum[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t before = 0;
+    for (uint32_t t = (uint32_t)tid; t < blockIdx.x; t += 256) before += a.tile_dirty[t];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, d);
+    if (lane == 0) warp_sum[warp] = before;
+    __syncthreads();
+    before = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) before += warp_sum[w];
+    __syncthreads();
+    constexpr int kPer = kOrderTile / 256;  // consecutive chunks per thread
+    const uint32_t first = blockIdx.x * kOrderTile + (uint32_t)tid * kPer;
+    uint32_t flags = 0, own = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; k++)
+        if (first + k < a.n_chunks && (a.piece[first + k] & kPieceDirty)) {
+            flags |= 1u << k;
+            own++;
+        }
+    uint32_t incl = own;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    uint32_t at = before + incl - own, total = before;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        if (w < warp) at += warp_sum[w];
+        total += warp_sum[w];
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; k++)
+        if (flags & (1u << k)) a.dirty_list[at++] = first + (uint32_t)k;
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) a.hdr->n_dirty = total;
+}
+
+// The dirty chunks, handed out in ascending order by ticket (one atomic per chunk; a warp holds the tickets of its next
+// two chunks ahead of time).  Per chunk: the TMA stages it; first walk (chunk_masks), after which its counts are
+// published; look-back for the carry; second walk (chunk_store).  The first walk of the warp's NEXT chunk runs before
+// the look-back of the current one, so the counts a neighbour waits for are out a whole chunk early.  Ascending tickets
+// are what the look-back relies on: a chunk a warp can wait for has a lower ticket, so its warp is running -- whatever
+// part of the grid is resident beside other kernels -- and the warp with the lowest ticket never waits.
 #ifndef H264B_DIRTY_MIN_CTAS
 #define H264B_DIRTY_MIN_CTAS 6
 #endif
@@ -611,7 +665,6 @@ __global__ void __launch_bounds__(kWarpsB * 32, H264B_DIRTY_MIN_CTAS) annexb_dir
     }
     __syncwarp();
     const uint64_t n16 = (a.n + 15) & ~15ull;
-    const uint64_t W = (uint64_t)gridDim.x * kWarpsB, g = (uint64_t)blockIdx.x * kWarpsB + (uint64_t)warp;
     auto stage_chunk = [&](uint32_t chunk, int b) {  // lane 0: TMA bulk load of the chunk and its halos, clipped to the stream
         const uint64_t pos = (uint64_t)chunk * kChunk;
         const uint64_t lo = pos ? pos - kHalo : 0;
@@ -625,22 +678,14 @@ __global__ void __launch_bounds__(kWarpsB * 32, H264B_DIRTY_MIN_CTAS) annexb_dir
             "l"(a.in + lo), "r"(bytes), "r"(bar)
             : "memory");
     };
-    // the warp's dirty chunks, 32 candidates at a time: lane l of batch t holds chunk g + (32 t + l) W
-    uint64_t batch = 0;
-    uint32_t mask = 0;
-    bool more = true;  // batches left
-    const auto next_dirty = [&]() -> int64_t {  // the warp's next dirty chunk, -1: none left (warp-uniform)
-        while (!mask && more) {
-            const uint64_t c = g + (batch * 32 + (uint64_t)lane) * W;
-            const uint32_t w = c < a.n_chunks ? a.piece[c] : 0u;
-            mask = __ballot_sync(0xFFFFFFFFu, (w & kPieceDirty) != 0);
-            more = g + (batch + 1) * 32 * W < a.n_chunks;
-            batch++;
-        }
-        if (!mask) return -1;
-        const int l = __ffs((int)mask) - 1;
-        mask &= mask - 1;
-        return (int64_t)(g + ((batch - 1) * 32 + (uint64_t)l) * W);
+    const uint32_t n_dirty = a.hdr->n_dirty;
+    // (more warps than dirty chunks: the surplus leaves before it adds to the queue at the ticket counter)
+    if ((uint64_t)blockIdx.x * kWarpsB + (uint64_t)warp >= (uint64_t)n_dirty) return;
+    const auto next_dirty = [&]() -> int64_t {  // the next dirty chunk nobody has taken, -1: none left (warp-uniform)
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(&a.hdr->ticket, 1ull);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        return t < (unsigned long long)n_dirty ? (int64_t)a.dirty_list[t] : -1;
     };
     // c_cur: counted and published, waits for its second walk (buffer b_cur); c_nxt: staged (buffer b_cur + 1);
     // c_far: staged (buffer b_cur + 2)
@@ -1109,7 +1154,7 @@ __global__ void __launch_bounds__(1024) slice_select_kernel(const h264b_nal *nal
 
 // ------------------------------------------------------------------------------------------------ launchers
 struct ScratchOffsets {
-    uint64_t piece, piece_carry, piece_ord, piece_S, shift_list, tile_sum, rec, nal_rec, total;
+    uint64_t piece, piece_carry, tile_dirty, zero_end, dirty_list, piece_ord, piece_S, shift_list, tile_sum, rec, nal_rec, total;
 };
 static ScratchOffsets scratch_layout(uint64_t n, uint32_t nal_cap) {
     const uint64_t n_chunks = (n + kChunk - 1) / kChunk;
@@ -1120,8 +1165,11 @@ static ScratchOffsets scratch_layout(uint64_t n, uint32_t nal_cap) {
         p = (p + bytes + 15) & ~15ull;
         return at;
     };
-    o.piece = take(n_chunks * 4);  // directly behind the header, then piece_carry: one memset clears all three
+    o.piece = take(n_chunks * 4);  // directly behind the header, then piece_carry and tile_dirty: one memset clears all
     o.piece_carry = take(n_chunks * 4);
+    o.tile_dirty = take((n_chunks + kOrderTile - 1) / kOrderTile * 4);
+    o.zero_end = p;  // everything up to here is cleared before a pass
+    o.dirty_list = take(n_chunks * 4);
     o.piece_ord = take(n_chunks * 4);
     o.piece_S = take(n_chunks * 4);
     o.shift_list = take(n_chunks * 8);
@@ -1161,6 +1209,8 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     a.hdr = (ScanScratchHeader *)s;
     a.piece = (uint32_t *)(s + so.piece);
     a.piece_carry = (uint32_t *)(s + so.piece_carry);
+    a.tile_dirty = (uint32_t *)(s + so.tile_dirty);
+    a.dirty_list = (uint32_t *)(s + so.dirty_list);
     a.piece_ord = (uint32_t *)(s + so.piece_ord);
     a.piece_S = (uint32_t *)(s + so.piece_S);
     a.shift_list = (uint2 *)(s + so.shift_list);
@@ -1180,10 +1230,13 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
     const auto enqueue = [&]() -> int {
         unsigned launched = 0;
         // header + the per-chunk counts and carries: all zero
-        H264B_CUDA(ctx, cudaMemsetAsync(s, 0, so.piece_ord, ctx->stream));
+        H264B_CUDA(ctx, cudaMemsetAsync(s, 0, so.zero_end, ctx->stream));
         if (n_chunks) {
             annexb_copy_kernel<<<(unsigned)((n_chunks + kWarpsA - 1) / kWarpsA), kWarpsA * 32, 0, ctx->stream>>>(a);
             H264B_LAUNCH_CHECK(ctx, "annexb_copy_kernel");
+            const unsigned tiles_d = (unsigned)((n_chunks + kOrderTile - 1) / kOrderTile);
+            dirty_list_kernel<<<tiles_d, 256, 0, ctx->stream>>>(a);
+            H264B_LAUNCH_CHECK(ctx, "dirty_list_kernel");
             uint64_t grid_b = (n_chunks + kWarpsB - 1) / kWarpsB;  // (the list is at most that long)
             if (grid_b > (uint64_t)ctx->sm_count * occ_b) grid_b = (uint64_t)ctx->sm_count * occ_b;
             annexb_dirty_kernel<<<(unsigned)grid_b, kWarpsB * 32, 0, ctx->stream>>>(a);
@@ -1195,7 +1248,7 @@ int launch_annexb_scan(h264b_ctx *ctx, const uint8_t *d_stream, uint64_t n, uint
             H264B_LAUNCH_CHECK(ctx, "order_apply_kernel");
             nal_permute_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a);
             H264B_LAUNCH_CHECK(ctx, "nal_permute_kernel");
-            launched += 5;
+            launched += 6;
         }
         scan_finalize_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a, d_nals, d_ext, d_summary);
         H264B_LAUNCH_CHECK(ctx, "scan_finalize_kernel");
