@@ -355,6 +355,354 @@ int64_t emul_stream_tiles(const uint8_t *s, int64_t n, uint8_t *out_base, int64_
     return Kall;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The round-2 pipeline of annexb_scan.cu, lane by lane: copy kernel (filter, verbatim chunks, dirty flags), ordered
+// dirty list, per dirty chunk chunk_masks -> published counts -> lookback_carry -> chunk_store (output image built in
+// place with word stores and spill hand-over, boundary granules byte by byte, store_image in two mappings), the
+// segmented carry scan with its re-copy list, chunk_shift_kernel, permutation and nal_removed.  Dirty chunks are taken
+// in ticket (= ascending) order, one at a time: the device's waits are synchronisation only, what is waited for is what
+// is read here.  Same outputs as emul_stream_tiles; `out` must be 16-byte aligned like the device buffer when out_shift
+// is a multiple of 16 (other shifts exercise nothing new here: stores are emulated byte-wise).
+int64_t emul_stream_carry(const uint8_t *s, int64_t n, uint8_t *out_base, int64_t out_shift, uint64_t *nal_start,
+                          uint64_t *nal_epb, uint32_t *nal_hdr, int64_t cap, int64_t *stats) {
+    const int kRows = 4, kGran = 32 * kRows, kChunk = kGran * 16, kHalo = 16;
+    const uint32_t kEpb = 0x7FFFu, kDirty = 0x8000u, kNscShift = 16, kNsc = 0x1FFFu, kReady = 0x80000000u;
+    uint8_t *out = out_base + out_shift;
+    auto gets = [&](int64_t p) -> uint32_t { return (p >= 0 && p < n) ? s[p] : 0xFFu; };
+    const int64_t n_chunks = (n + kChunk - 1) / kChunk;
+    std::vector<uint32_t> piece((size_t)n_chunks + 1, 0), piece_carry((size_t)n_chunks + 1, 0);
+    std::vector<uint64_t> rec_start;
+    std::vector<uint32_t> rec_epb, rec_hdr, rec_rank;
+    int64_t n_verbatim = 0, n_dirty = 0, n_spin_would_wait = 0, n_recopied = 0;
+    std::vector<uint8_t> buf(kHalo + kChunk + kHalo);
+    std::vector<uint16_t> scb(kGran + 2);
+    std::vector<int64_t> dirty_list;
+    auto stage = [&](int64_t pos) {
+        for (int i = 0; i < kHalo + kChunk + kHalo; i++) buf[i] = (uint8_t)gets(pos - kHalo + i);
+    };
+    // ---- annexb_copy_kernel
+    for (int64_t chunk = 0; chunk < n_chunks; chunk++) {
+        const int64_t pos = chunk * kChunk;
+        if (pos == 0 || pos + kChunk + kHalo > n) {
+            piece[chunk] = kDirty;
+            dirty_list.push_back(chunk);
+            continue;
+        }
+        stage(pos);
+        const uint8_t *tile_in = buf.data() + kHalo;
+        uint32_t any_e = 0;
+        std::vector<uint32_t> sc_f(kGran);
+        for (int gi = 0; gi < kGran; gi++) {
+            uint32_t w[4], prev;
+            memcpy(w, tile_in + gi * 16, 16);
+            memcpy(&prev, tile_in + gi * 16 - 4, 4);
+            const GranuleMasks mf = granule_masks_filtered(w, prev);
+            any_e |= mf.e;
+            sc_f[gi] = mf.sc;
+        }
+        if (any_e) {
+            piece[chunk] = kDirty;
+            dirty_list.push_back(chunk);
+            continue;
+        }
+        n_verbatim++;
+        memcpy(out + pos, tile_in, kChunk);
+        uint32_t rank = 0;
+        for (int gi = 0; gi < kGran; gi++)
+            for (int j = 0; j < 16; j++)
+                if (sc_f[gi] & (1u << j)) {
+                    const uint64_t st = (uint64_t)pos + (uint64_t)gi * 16 + j + 1;
+                    uint32_t h = 0;
+                    for (int q = 0; q < 4; q++) h |= gets((int64_t)st + q) << (8 * q);
+                    rec_start.push_back(st);
+                    rec_hdr.push_back(h);
+                    rec_epb.push_back(0);
+                    rec_rank.push_back(rank++);
+                }
+        piece[chunk] = rank << kNscShift;
+    }
+    // ---- annexb_dirty_kernel, tickets in ascending order
+    for (int64_t chunk : dirty_list) {
+        n_dirty++;
+        const int64_t pos = chunk * kChunk;
+        stage(pos);
+        uint8_t *tile_in = buf.data() + kHalo;
+        // chunk_masks
+        std::vector<uint32_t> es(kGran), pre(kGran);
+        {
+            std::vector<uint32_t> em(kGran);
+            auto masks_at = [&](int gi, bool have_prev) {
+                uint32_t w[4];
+                memcpy(w, tile_in + gi * 16, 16);
+                uint32_t prev = 0xFFFFFFFFu;
+                if (have_prev) memcpy(&prev, tile_in + gi * 16 - 4, 4);
+                return granule_masks(w, prev);
+            };
+            for (int gi = 0; gi < kGran; gi++) {
+                const GranuleMasks m = masks_at(gi, true);
+                em[gi] = m.e | (m.sc << 16);
+                scb[gi + 1] = (uint16_t)m.sc;
+            }
+            scb[0] = (uint16_t)masks_at(-1, false).sc;
+            scb[kGran + 1] = (uint16_t)masks_at(kGran, true).sc;
+            auto get = [&](int64_t p) -> uint32_t { return tile_in[p - pos]; };
+            uint32_t rp = 0;
+            for (int r = 0; r < kRows; r++) {
+                uint32_t run = 0;
+                for (int lane = 0; lane < 32; lane++) {
+                    const int gi = r * 32 + lane;
+                    const int64_t gpos = pos + (int64_t)gi * 16;
+                    uint32_t e16 = em[gi] & 0xFFFFu;
+                    const uint32_t near = ((uint32_t)scb[gi] >> 10) | scb[gi + 1] | (scb[gi + 2] & 1u);
+                    if (near) (void)keep_mask_near_sc(get, gpos, e16, scb[gi], scb[gi + 1], scb[gi + 2], &e16);
+                    uint32_t sc = em[gi] >> 16;
+                    if (pos + kChunk > n) {
+                        if (gpos >= n) {
+                            sc = 0;
+                            e16 = 0;
+                        } else if (gpos + 16 > n) {
+                            const uint32_t v = (1u << (uint32_t)(n - gpos)) - 1u;
+                            sc &= v;
+                            e16 &= v;
+                        }
+                    }
+                    es[gi] = e16 | (sc << 16);
+                    pre[gi] = seg_combine(rp, lane ? run : 0u);
+                    const uint32_t el = seg_element(e16, sc);
+                    run = lane ? seg_combine(run, el) : el;
+                }
+                rp = seg_combine(rp, run);
+            }
+            // publish
+            const uint32_t total = rp;
+            piece[chunk] = kReady | kDirty | (total & 0x1FFF0000u) | (total & kEpb);
+            // lookback_carry
+            uint32_t carry = 0;
+            bool done = false;
+            for (int64_t base = chunk; base > 0 && !done; base -= 32) {
+                uint32_t w[32], c[32];
+                uint32_t tmask = 0;
+                for (int lane = 0; lane < 32; lane++) {
+                    const int64_t idx = base - 1 - lane;
+                    bool term;
+                    if (idx < 0) {
+                        w[lane] = 0;
+                        c[lane] = 0;
+                        term = true;
+                    } else {
+                        w[lane] = piece[idx];
+                        c[lane] = piece_carry[idx];
+                        if ((w[lane] & kDirty) && !(w[lane] & kReady)) n_spin_would_wait++;  // (cannot happen in ticket order)
+                        term = (((w[lane] >> kNscShift) & kNsc) != 0) || (c[lane] & kReady);
+                    }
+                    if (term) tmask |= 1u << lane;
+                }
+                const int first = tmask ? __builtin_ctz(tmask) : 32;
+                for (int lane = 0; lane < 32 && lane <= first; lane++) {
+                    const int64_t idx = base - 1 - lane;
+                    if (lane < first) carry += w[lane] & kEpb;
+                    else carry += idx < 0 ? 0u : (((w[lane] >> kNscShift) & kNsc) ? (w[lane] & kEpb) : (c[lane] & ~kReady));
+                }
+                if (tmask) done = true;
+            }
+            piece_carry[chunk] = kReady | seg_apply(total, carry);
+
+            // ---- chunk_store
+            const uint32_t n_sc = (total >> 16) & 0x1FFFu;
+            const uint32_t cb = carry & 15u;
+            const int64_t base_a = pos - (int64_t)(carry & ~15u);
+            const int64_t limit = n - pos;
+            auto store_image = [&](int64_t base, int x0, int x1) {  // (aligned stores and ragged ends alike: bytes [x0, x1))
+                for (int x = x0; x < x1; x++) out[base + x] = tile_in[x];
+            };
+            if ((total & 0x7FFFu) == 0 && n_sc == 0 && cb == 0) {
+                store_image(base_a, 0, (int)(limit < kChunk ? limit : kChunk));
+                continue;
+            }
+            int first_end = 0, first_a_end = 0;
+            if (n_sc) {
+                const uint64_t slot0 = rec_start.size();
+                rec_start.resize(slot0 + n_sc);
+                rec_hdr.resize(slot0 + n_sc);
+                rec_epb.resize(slot0 + n_sc);
+                rec_rank.resize(slot0 + n_sc);
+                bool have_first = false;
+                for (int gi = 0; gi < kGran; gi++) {
+                    uint32_t sc = es[gi] >> 16;
+                    if (!sc) continue;
+                    const uint32_t ee = es[gi] & 0xFFFFu;
+                    if (((pre[gi] >> 16) & 0x1FFFu) == 0 && !have_first) {
+                        const int j = __builtin_ctz(sc);
+                        first_end = gi * 16 + j + 1;
+                        first_a_end = first_end - 2 - (int)cb - (int)((pre[gi] & 0x7FFFu) + bits_popc(ee & ((1u << j) - 1u)));
+                        have_first = true;
+                    }
+                    // emit_dirty_records
+                    uint32_t rank = (pre[gi] >> 16) & 0x1FFFu, c = pre[gi] & 0x7FFFu;
+                    int prev = -1;
+                    while (sc) {
+                        const int j = __builtin_ctz(sc);
+                        sc &= sc - 1;
+                        const uint32_t between = (ee >> (prev + 1)) & ((1u << (j - prev - 1)) - 1u);
+                        c += bits_popc(between);
+                        const uint64_t st = (uint64_t)pos + (uint64_t)gi * 16 + (uint64_t)j + 1;
+                        const uint8_t *hb = tile_in + gi * 16 + j + 1;
+                        rec_start[slot0 + rank] = st;
+                        rec_hdr[slot0 + rank] = (uint32_t)hb[0] | ((uint32_t)hb[1] << 8) | ((uint32_t)hb[2] << 16) | ((uint32_t)hb[3] << 24);
+                        rec_epb[slot0 + rank] = c;
+                        rec_rank[slot0 + rank] = rank;
+                        rank++;
+                        c = 0;
+                        prev = j;
+                    }
+                }
+            }
+            // every lane's granules into registers before anything is rewritten
+            std::vector<uint32_t> v((size_t)kGran * 4);
+            memcpy(v.data(), tile_in, kChunk);
+            auto put_word = [&](int wq, uint32_t x) { memcpy(tile_in + 4 * wq, &x, 4); };
+            std::vector<uint32_t> late_word(kGran);
+            std::vector<int> late_x(kGran), late_n(kGran);
+            uint32_t spill_prev = 0;
+            bool reg_prev = false;
+            for (int gi = 0; gi < kGran; gi++) {
+                const int lane = gi & 31, r = gi >> 5;
+                uint32_t ee = es[gi] & 0xFFFFu;
+                const uint32_t sc = es[gi] >> 16;
+                const bool regular = sc == 0;
+                const int shift = (int)(pre[gi] & 0x7FFFu) + ((pre[gi] >> 31) ? 0 : (int)cb);
+                const int q = gi * 16 - shift;
+                const int nb = 16 - (int)bits_popc(ee);
+                uint32_t w0 = v[gi * 4], w1 = v[gi * 4 + 1], w2 = v[gi * 4 + 2], w3 = v[gi * 4 + 3];
+                if (regular) {
+                    while (ee) {
+                        const int j = bits_msb(ee);
+                        ee &= ~(1u << j);
+                        const uint32_t s0 = funnel_r(w0, w1, 8), s1 = funnel_r(w1, w2, 8), s2 = funnel_r(w2, w3, 8), s3 = w3 >> 8;
+                        const uint32_t m = (1u << ((j & 3) * 8)) - 1u;
+                        const int wj = j >> 2;
+                        w0 = wj > 0 ? w0 : (w0 & m) | (s0 & ~m);
+                        w1 = wj > 1 ? w1 : (wj == 1 ? (w1 & m) | (s1 & ~m) : s1);
+                        w2 = wj > 2 ? w2 : (wj == 2 ? (w2 & m) | (s2 & ~m) : s2);
+                        w3 = wj == 3 ? (w3 & m) | (s3 & ~m) : s3;
+                    }
+                }
+                const uint32_t a8 = (uint32_t)(q & 3) * 8u;
+                auto fl = [&](uint32_t lo, uint32_t hi) { return a8 ? ((hi << a8) | (lo >> (32 - a8))) : hi; };  // __funnelshift_l
+                const uint32_t x0 = w0 << a8, x1 = fl(w0, w1), x2 = fl(w1, w2), x3 = fl(w2, w3), x4 = fl(w3, 0u);
+                const int wq = q >> 2;
+                const int cnt = ((q + nb) >> 2) - wq;
+                const int rem = (q + nb) & 3;
+                const uint32_t spill = cnt == 2 ? x2 : (cnt == 3 ? x3 : x4);
+                const uint32_t sp = spill_prev;
+                const bool rg = gi == 0 ? false : reg_prev;
+                spill_prev = spill;
+                reg_prev = regular;
+                const bool next_regular = gi + 1 < kGran && (es[gi + 1] >> 16) == 0;
+                (void)lane;
+                (void)r;
+                if (regular) {
+                    put_word(wq, x0 | (rg ? sp : 0u));
+                    put_word(wq + 1, x1);
+                    if (cnt > 2) put_word(wq + 2, x2);
+                    if (cnt > 3) put_word(wq + 3, x3);
+                }
+                late_word[gi] = spill;
+                late_x[gi] = (wq + cnt) * 4;
+                late_n[gi] = regular ? (next_regular ? 0 : rem) : -100;
+            }
+            for (int gi = 0; gi < kGran; gi++) {
+                if (late_n[gi] == -100) {  // image_boundary_granule
+                    uint32_t c = (pre[gi] & 0x7FFFu) + ((pre[gi] >> 31) ? 0u : cb);
+                    const uint32_t ee = es[gi] & 0xFFFFu, sc = es[gi] >> 16;
+                    const uint32_t vv[4] = {v[gi * 4], v[gi * 4 + 1], v[gi * 4 + 2], v[gi * 4 + 3]};
+                    for (int j = 0; j < 16; j++) {
+                        const uint32_t bit = 1u << j;
+                        if (ee & bit) c++;
+                        else tile_in[gi * 16 + j - (int)c] = (uint8_t)granule_byte(vv, j);
+                        if (sc & bit) c = 0;
+                    }
+                } else {
+                    for (int k = 0; k < late_n[gi]; k++) tile_in[late_x[gi] + k] = (uint8_t)(late_word[gi] >> (8 * k));
+                }
+            }
+            const int removed_end = (int)(total & 0x7FFFu);
+            if (n_sc == 0) {
+                int x1 = kChunk - (int)cb - removed_end;
+                const int64_t lim = limit - (int64_t)cb;
+                if ((int64_t)x1 > lim) x1 = (int)lim;
+                store_image(base_a, -(int)cb, x1);
+            } else {
+                int xb1 = kChunk - removed_end;
+                if ((int64_t)xb1 > limit) xb1 = (int)limit;
+                if (base_a == pos) {
+                    store_image(pos, -(int)cb, xb1);
+                } else {
+                    store_image(base_a, -(int)cb, first_a_end);
+                    store_image(pos, first_end, xb1);
+                }
+            }
+        }
+    }
+    // ---- order_reduce / order_apply: ordinals, S[], segmented carry -> re-copy list
+    std::vector<uint32_t> piece_ord((size_t)n_chunks + 1, 0), S((size_t)n_chunks + 1, 0);
+    struct Shift { int64_t t; uint32_t G; };
+    std::vector<Shift> shift_list;
+    {
+        uint32_t nsc_run = 0, epb_run = 0, seg_f = 0, seg_c = 0;
+        for (int64_t t = 0; t < n_chunks; t++) {
+            piece_ord[t] = nsc_run;
+            S[t] = epb_run;
+            if (!(piece[t] & kDirty) && nsc_run && seg_c) shift_list.push_back({t, seg_c});
+            const uint32_t nsc = (piece[t] >> kNscShift) & kNsc, epb = piece[t] & kEpb;
+            nsc_run += nsc;
+            epb_run += epb;
+            if (nsc) seg_f = 1, seg_c = epb; else seg_c += epb;
+        }
+        (void)seg_f;
+        S[n_chunks] = epb_run;
+    }
+    // ---- nal_permute_kernel
+    const int64_t Kall = (int64_t)rec_start.size();
+    std::vector<uint32_t> epb_local((size_t)std::min(Kall, cap) + 1, 0);
+    for (int64_t i = 0; i < Kall; i++) {
+        const uint64_t ord = (uint64_t)piece_ord[(rec_start[i] - 1) / kChunk] + rec_rank[i];
+        if ((int64_t)ord < cap) {
+            nal_start[ord] = rec_start[i];
+            epb_local[ord] = rec_epb[i];
+            nal_hdr[ord] = rec_hdr[i];
+        }
+    }
+    const int64_t K = Kall < cap ? Kall : cap;
+    // ---- chunk_shift_kernel (reads the INPUT)
+    for (const Shift &e : shift_list) {
+        const int64_t t = e.t, k = (int64_t)piece_ord[t] - 1;
+        if (k + 1 >= cap) continue;
+        const int64_t lo = t * kChunk;
+        int64_t ps = lo, pe = lo + kChunk;
+        const int64_t body = (int64_t)nal_start[k] + nal_header_bytes(nal_hdr[k] & 0xFFu, (nal_hdr[k] >> 8) & 0xFFu);
+        if (body > ps) ps = body;
+        if ((piece[t] >> kNscShift) & kNsc) pe = (int64_t)nal_start[k + 1] - 2;
+        if (pe > ps) {
+            n_recopied++;
+            for (int64_t p = ps; p < pe; p++) out[p - e.G] = s[p];
+        }
+    }
+    // ---- scan_finalize_kernel
+    for (int64_t k = 0; k < K; k++) nal_epb[k] = 0;
+    for (int64_t k = 0; k + 1 < K; k++) {
+        uint32_t later;
+        nal_epb[k + 1] = nal_removed(nal_start[k], nal_start[k + 1], epb_local[k + 1], S.data(), (uint64_t)kChunk, &later);
+    }
+    if (stats) {
+        stats[0] = n_verbatim;
+        stats[1] = n_dirty;
+        stats[2] = n_recopied;
+        stats[3] = n_spin_would_wait;
+    }
+    return Kall;
+}
+
 // the slice-header walk of slice_header_kernel, one slice
 void emul_slice_header(const h264b_param_sets *ps, uint32_t nal_type, uint32_t nal_ref_idc, const uint8_t *rbsp,
                        uint64_t len, h264b_slice_header *out) {

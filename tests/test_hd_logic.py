@@ -38,6 +38,9 @@ def emul():
     L.emul_stream_tiles.restype = C.c_int64
     L.emul_stream_tiles.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int64, C.c_int64, C.c_uint32, C.c_void_p]
+    L.emul_stream_carry.restype = C.c_int64
+    L.emul_stream_carry.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int64, C.c_void_p]
     L.emul_frame.restype = C.c_int64
     L.emul_frame.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     L.emul_cabac.restype = None
@@ -88,6 +91,7 @@ def check_stream(L, s):
             written[shift + a0 + H: shift + a0 + H + ln] = True
         # nothing may be written outside [first NAL body, stream end) and nothing before the destination
         assert np.all(out[:shift] == 0xEE) and np.all(out[shift + len(s8):] == 0xEE), "stray writes"
+    check_carry_pipeline(L, s8, nal, rbsp)
     assert mism == 0
     assert max(K, 1) - 1 == len(nal["start"])
     n = len(nal["start"])
@@ -101,6 +105,33 @@ def check_stream(L, s):
         assert e0 == nal["start"][0]
     else:
         assert len(rbsp) == 0
+
+
+def check_carry_pipeline(L, s8, nal, rbsp):
+    """the round-2 pipeline (counts carried from chunk to chunk, image built in place, re-copy list): same outputs"""
+    n_or = len(nal["start"])
+    stats_all = np.zeros(4, np.int64)
+    for shift in (0, 16):
+        out = np.full(len(s8) + 96 + shift, 0xEE, np.uint8)
+        cap = len(s8) // 4 + 2
+        t_st, t_epb, t_hd = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64), np.zeros(cap, np.uint32)
+        stats = np.zeros(4, np.int64)
+        Kt = L.emul_stream_carry(s8.ctypes.data, len(s8), out.ctypes.data, shift, t_st.ctypes.data, t_epb.ctypes.data,
+                                 t_hd.ctypes.data, cap, stats.ctypes.data)
+        assert stats[3] == 0, "a chunk looked back at one that had not published (ticket order broken)"
+        assert max(Kt, 1) - 1 == n_or
+        for k in range(n_or):
+            a0 = int(t_st[k])
+            assert a0 == nal["start"][k]
+            H = int(nal["header_bytes"][k])
+            ln = max(int(t_st[k + 1]) - a0 - H - 2, 0) - int(t_epb[k + 1])
+            assert ln == nal["rbsp_len"][k], (k, ln, int(nal["rbsp_len"][k]))
+            got = out[shift + a0 + H: shift + a0 + H + ln]
+            exp = rbsp[int(nal["rbsp_off"][k]): int(nal["rbsp_off"][k]) + ln]
+            assert np.array_equal(got, exp), "carry pipeline bytes differ (NAL %d, shift %d)" % (k, shift)
+        assert np.all(out[:shift] == 0xEE) and np.all(out[shift + len(s8):] == 0xEE), "stray writes"
+        stats_all += stats
+    return stats_all
 
 
 def random_stream(rng, n, p_zero, p_sc, ext_types=False):
@@ -259,3 +290,40 @@ def test_cabac_lane_random_bits_and_overrun(emul, flags_o):
         ops = ((kinds << 14) | ctxs).astype(np.uint16)
         init = rng.integers(0, 128, 32).astype(np.uint8)
         _cabac_case(emul, data, int(rng.integers(0, 9)), ops, init, flags_o, bool(trial & 1))
+
+
+def test_carry_pipeline_long_carries_and_recopied_chunks(emul):
+    """CPU twin of tests/test_gpu_parity.py::test_scan_carry_across_many_chunks: a NAL that loses 70 000 bytes (more than
+    the 15-bit per-chunk field holds), one EPB in front of 300 KB of clean payload (verbatim chunks on the re-copy
+    list), an EPB in every fourth chunk, a NAL whose every chunk is dirty, and that payload cut into odd NAL units."""
+    rng = np.random.default_rng(77)
+    sc, hdr = np.array([0, 0, 0, 1], np.uint8), np.array([0x65], np.uint8)
+    clean = lambda n: rng.integers(4, 256, n).astype(np.uint8)
+    cases = []
+    triples = np.tile(np.array([0, 0, 3], np.uint8), 70000)
+    cases.append(np.concatenate([sc, hdr, clean(100), triples, clean(50000), sc, hdr, clean(3000), sc]))
+    b = clean(300000 + 1234)
+    b[10:13] = [0, 0, 3]
+    cases.append(np.concatenate([sc, hdr, b, sc, hdr, clean(100), sc]))
+    b = clean(64 * 2048 + 321)
+    for k in range(0, 64, 4):
+        at = k * 2048 + int(rng.integers(8, 2000))
+        b[at:at + 3] = [0, 0, 3]
+    cases.append(np.concatenate([clean(7), sc, hdr, b, sc]))
+    b = clean(120000)
+    for p_ in np.sort(rng.choice(np.arange(4, 120000 - 4, 97), 1000, replace=False)):
+        b[p_:p_ + 3] = [0, 0, 3]
+    cases.append(np.concatenate([sc, hdr, b, sc]))
+    parts, pos = [], 0
+    while pos < len(b):
+        ln = int(rng.integers(50, 9000))
+        parts += [sc, hdr, b[pos:pos + ln]]
+        pos += ln
+    cases.append(np.concatenate(parts + [sc]))
+    recopied = 0
+    for s in cases:
+        s8 = np.ascontiguousarray(s, dtype=np.uint8)
+        nal, rbsp = orc.read_nal_units_arrays(s8)
+        st = check_carry_pipeline(emul, s8, nal, rbsp)
+        recopied += int(st[2])
+    assert recopied > 100   # the re-copy list was exercised
