@@ -552,6 +552,25 @@ inline void DecodeMbTypes(const h264b_mb_type_job &job, Device &dev = Device::De
 // share in up to three passes, longest slices first, each one split + strip pass and the CABAC engine in up to six
 // launches by slice length, side by side), and comes back as NAL units,
 // bins and final engine states per stream, with the time every slice's result reached host memory.
+// What Scheduler::Run would decide for a batch over n_devices devices of sm_count SMs each: per stream its device (-1:
+// no NAL unit in it) and its pass on that device, per slice its launch class (0: on a scheduler of its own, 1..5 by
+// length, 255: not decoded).  Host only: no device is touched.
+struct BatchPlan {
+    std::vector<int32_t> stream_device;
+    std::vector<uint32_t> stream_pass;
+    std::vector<uint8_t> slice_class;
+};
+inline BatchPlan PlanBatch(const h264b_batch_job &job, uint32_t n_devices, uint32_t sm_count = 148) {
+    BatchPlan p;
+    p.stream_device.assign(job.n_streams, -1);
+    p.stream_pass.assign(job.n_streams, 0);
+    p.slice_class.assign(job.total_slices, 255);
+    const int32_t rc = h264b_scheduler_plan(&job, n_devices, sm_count, p.stream_device.data(), p.stream_pass.data(),
+                                            p.slice_class.data());
+    if (rc != H264B_OK) throw std::runtime_error("h264b_scheduler_plan: status " + std::to_string(rc));
+    return p;
+}
+
 class Scheduler {
    public:
     // devices: CUDA ordinals; empty = every device of the process

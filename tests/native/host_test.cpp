@@ -205,6 +205,46 @@ int main(int argc, char **argv) {
             printf("core %d %lld %lld\n", std::get<0>(bd), (long long)std::get<1>(bd), (long long)std::get<2>(bd));
             c.StateTransitionProcess(1 - c.ValMPS);
             printf("trans %d %d\n", c.PStateIdx, c.ValMPS);
+        } else if (mode == "plan") {  // h264::PlanBatch on a batch file (see "sched"), argv[3] devices (no device call)
+            const auto f = slurp(argv[2]);
+            const uint8_t *p = f.data();
+            auto take = [&](void *dst, size_t n) {
+                memcpy(dst, p, n);
+                p += n;
+            };
+            uint32_t hdr[5];
+            take(hdr, sizeof(hdr));
+            std::vector<std::vector<uint8_t>> bytes(hdr[0]);
+            std::vector<h264b_batch_stream> streams(hdr[0]);
+            uint32_t total = 0;
+            for (uint32_t i = 0; i < hdr[0]; i++) {
+                uint64_t n;
+                uint32_t ns;
+                take(&n, 8);
+                take(&ns, 4);
+                bytes[i].resize(n);
+                take(bytes[i].data(), n);
+                streams[i].stream = bytes[i].data();
+                streams[i].n = n;
+                streams[i].first_slice = total;
+                streams[i].n_slices = ns;
+                total += ns;
+            }
+            p += (size_t)hdr[2] * 2;  // (the op schedule: not needed to plan)
+            std::vector<uint32_t> n_ops(total);
+            take(n_ops.data(), n_ops.size() * 4);
+            h264b_batch_job job;
+            memset(&job, 0, sizeof(job));
+            job.streams = streams.data();
+            job.n_streams = hdr[0];
+            job.total_slices = total;
+            job.n_ctx = hdr[1];
+            job.n_ops_max = hdr[2];
+            job.n_ops = n_ops.data();
+            job.group_bytes = strtoull(argv[4], nullptr, 10);
+            const h264::BatchPlan plan = h264::PlanBatch(job, (uint32_t)atoi(argv[3]));
+            for (uint32_t i = 0; i < hdr[0]; i++) printf("stream %u device %d pass %u\n", i, plan.stream_device[i], plan.stream_pass[i]);
+            for (uint32_t k = 0; k < total; k++) printf("slice %u class %u\n", k, (unsigned)plan.slice_class[k]);
         } else if (mode == "sched") {  // a batch of streams through h264::Scheduler; argv[2]: the batch as one file (see test)
             const auto f = slurp(argv[2]);
             const uint8_t *p = f.data();

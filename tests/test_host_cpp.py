@@ -367,3 +367,35 @@ def test_scheduler_wrapper_runs_a_batch_of_streams(exe, tmp_path):
             row += 1
     assert workers == {0, 1}
     assert out[-1][:3] == ["total", "bins", str(int(n_ops.sum()) + len(n_ops))]
+
+
+def test_plan_batch_wrapper_matches_the_python_binding(exe, tmp_path):
+    """h264::PlanBatch (host/h264.hpp) == capi.scheduler_plan on the same batch: host only, runs without a GPU"""
+    import struct
+    from h264decode_b200 import capi
+    rng = np.random.default_rng(21)
+    n_streams, per = 48, 4
+    sizes = (200 * 2 ** (8 * rng.random(n_streams) ** 3)).astype(np.int64)
+    streams = []
+    for i in range(n_streams):
+        body = rng.integers(4, 256, int(sizes[i]), dtype=np.uint8)
+        streams.append(np.concatenate([np.array([0, 0, 0, 1], np.uint8), body, np.array([0, 0, 0, 1], np.uint8)]))
+    streams[5] = np.array([9, 9, 9], np.uint8)                      # no NAL unit in it
+    n_ops = (100 * 2 ** (10 * rng.random(n_streams * per) ** 3)).astype(np.uint32)
+    n_ops_max = int(n_ops.max())
+    blob = [struct.pack("<5I", n_streams, 64, n_ops_max, 0, 1)]
+    for s in streams:
+        blob += [struct.pack("<QI", len(s), per), s.tobytes()]
+    blob += [np.zeros(n_ops_max, np.uint16).tobytes(), n_ops.tobytes()]
+    path = os.path.join(str(tmp_path), "plan.bin")
+    with open(path, "wb") as f:
+        f.write(b"".join(blob))
+    for nd, group in ((1, 1024), (3, 2048), (8, 1 << 30)):
+        rc, out = run(exe, "plan", path, nd, group)
+        assert rc == 0, out
+        dev, pas, cls = capi.scheduler_plan(streams, [per] * n_streams, n_ops, n_ops_max, nd, 148, group)
+        got_s = [(int(l[3]), int(l[5])) for l in out if l[0] == "stream"]
+        got_c = [int(l[3]) for l in out if l[0] == "slice"]
+        assert got_s == [(int(d), int(p)) for d, p in zip(dev, pas)]
+        assert got_c == [int(c) for c in cls]
+        assert dev[5] == -1 and set(dev) - {-1} == set(range(min(nd, n_streams - 1)))
