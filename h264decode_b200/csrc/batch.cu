@@ -5,8 +5,10 @@
 // worker thread per device, streams dealt to devices longest first (LPT by bytes).  A slice is serial work (~53 ns per
 // bin), so a device's share is taken in up to three passes by how long the streams' longest slices are -- the few
 // streams that hold the batch's longest slices are staged, copied, split and started first, while the bulk is still
-// being staged -- and every pass runs the CABAC engine in five launches by slice length, side by side, so that short
-// slices are back on the host long before the long ones are done.  Host code only (one gather kernel).
+// being staged -- and every pass runs the CABAC engine in up to six launches by slice length, side by side (the slices
+// the makespan hangs on one per warp on SMs of their own, the others 32 to a warp), so that short slices are back on the
+// host long before the long ones are done.  Results go straight into one pinned arena.  Host code only (one gather
+// kernel); the decisions (device, pass, class) are host-only functions shared with h264b_scheduler_plan.
 #include <stdlib.h>
 
 #include <algorithm>
